@@ -1,0 +1,389 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, kind::tf32, fp32 accumulate in
+// TMEM) fed by TMA.  Serves fprop and dgrad of every nn.Conv2d on the hot path
+// (architectures/deeplab2.py:65-128,140-150; torchvision ResNet-101 / ASPP and
+// architectures/deeplab3plus.py:29-48 for DeepLab v3+).
+//
+// GEMM view:  D[pixel, n] = sum_{tap} sum_{k} A[pixel @ tap, k] * B[n, tap, k]
+//   * M tile  = 128 output pixels = a (BW x BH x BN) box of the NHWC activation tensor.  The TMA
+//     engine gathers the box for a filter tap by shifting the start coordinate by (dh, dw); pixels
+//     outside the image are zero-filled by TMA (= conv padding), strided convs use TMA element strides.
+//     No im2col buffer ever exists in HBM.
+//   * N tile  <= 256 output channels, K block = 32 channels (one 128 B swizzle row).
+//   * 4-stage smem ring (16 KB A + 32 KB B per stage), 2 x 256-column TMEM accumulators, so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
+//   * persistent CTAs (one per SM), warp-specialised: warp0 TMA producer, warp1 MMA issuer
+//     (single elected thread), warp2 TMEM allocator, warps 4-7 epilogue (TMEM -> regs -> HBM).
+//   * taps whose box lies completely in the zero padding are skipped (ASPP dilation 12/24/36).
+//   * fused epilogue: BN scale/shift | bias, residual add, ReLU, ReLU-gate (backward), second scale,
+//     accumulate; output leading dimension + channel offset let a conv write into a slice of a wider
+//     buffer (no torch.cat), output stride/offset scatter handles strided dgrad.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                       // fp32 elements = 128 bytes
+constexpr int MAX_BLOCK_N = 256;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 4;  // 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MAX_TAPS = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+struct ConvKArgs {
+  int n, ih, iw, k;
+  int nb;
+  int oh, ow;
+  int fh, fw, ldd, ostride, ooh, oow;
+  int istride;
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles_n, block_n;
+  int num_tiles;
+  int n_taps;
+  short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
+  int kblocks;
+  int n_pass;
+  float* d;
+  const float* scale; const float* shift;
+  const float* addend; const float* gate; const float* scale2;
+  int ld_add, ld_gate;
+  int relu, accumulate;
+  int vec_ok;
+};
+
+struct TileInfo {
+  int n_idx, w0, h0, n0;
+  uint32_t tap_mask;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const ConvKArgs& a, int tile) {
+  TileInfo t;
+  t.n_idx = tile % a.n_tiles_n;
+  int m = tile / a.n_tiles_n;
+  const int wt = m % a.tiles_w; m /= a.tiles_w;
+  const int ht = m % a.tiles_h;
+  const int nt = m / a.tiles_h;
+  t.w0 = wt * a.bw; t.h0 = ht * a.bh; t.n0 = nt * a.bn;
+  uint32_t mask = 0;
+  for (int i = 0; i < a.n_taps; ++i) {
+    const int lo_h = t.h0 * a.istride + a.dh[i], hi_h = lo_h + (a.bh - 1) * a.istride;
+    const int lo_w = t.w0 * a.istride + a.dw[i], hi_w = lo_w + (a.bw - 1) * a.istride;
+    if (hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw) mask |= 1u << i;
+  }
+  if (mask == 0) mask = 1;  // accumulator must still be written (all-zero contribution)
+  t.tap_mask = mask;
+  return t;
+}
+
+__device__ __forceinline__ float epi1(const ConvKArgs& a, float v, int c, float add, float gate, float old) {
+  if (a.scale) v *= __ldg(a.scale + c);
+  if (a.shift) v += __ldg(a.shift + c);
+  if (a.addend) v += add;
+  if (a.relu) v = fmaxf(v, 0.0f);
+  if (a.gate) v = gate > 0.0f ? v : 0.0f;
+  if (a.scale2) v *= __ldg(a.scale2 + c);
+  if (a.accumulate) v += old;
+  return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                 const __grid_constant__ ConvKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmB);
+    if (a.n_pass > 1) { tc::tma_prefetch_desc(&tmAlo); tc::tma_prefetch_desc(&tmBlo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const uint32_t rows_a = a.bw * a.bh * a.bn;
+  const uint32_t stage_tx = rows_a * 128u + (uint32_t)a.block_n * 128u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(a, tile);
+        for (int tap = 0; tap < a.n_taps; ++tap) {
+          if (!(t.tap_mask >> tap & 1)) continue;
+          const int cw = t.w0 * a.istride + a.dw[tap];
+          const int ch = t.h0 * a.istride + a.dh[tap];
+          const int bt = a.btap[tap];
+          for (int kb = 0; kb < a.kblocks; ++kb) {
+            for (int p = 0; p < a.n_pass; ++p) {
+              tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+              tc::mbar_expect_tx(&full_bar[stage], stage_tx);
+              tc::tma_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
+                              kb * BLOCK_K, cw, ch, t.n0);
+              tc::tma_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
+                              kb * BLOCK_K, bt, t.n_idx * a.block_n);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(BLOCK_M, a.block_n, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(a, tile);
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+        uint32_t first = 1;
+        const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
+        for (int it = 0; it < iters; ++it) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
+            const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
+            const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
+            tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          tc::mma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int bwbh = a.bw * a.bh;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(a, tile);
+      const int dn = row / bwbh;
+      const int rem = row - dn * bwbh;
+      const int dhh = rem / a.bw;
+      const int dww = rem - dhh * a.bw;
+      const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
+      const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
+      const int64_t pix = ((int64_t)pn * a.fh + (int64_t)ph * a.ostride + a.ooh) * a.fw + (int64_t)pw * a.ostride + a.oow;
+      float* drow = a.d + pix * a.ldd;
+      const float* addrow = a.addend ? a.addend + pix * a.ld_add : nullptr;
+      const float* gaterow = a.gate ? a.gate + pix * a.ld_gate : nullptr;
+
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * MAX_BLOCK_N;
+      const int nchunks = a.block_n / 32;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t r[32];
+        tc::tmem_ld_x32(taddr + ch * 32, r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const int col0 = t.n_idx * a.block_n + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = col0 + j * 4;
+            if (c >= a.nb) break;
+            if (a.vec_ok && c + 3 < a.nb) {
+              float4 add = make_float4(0, 0, 0, 0), gt = make_float4(1, 1, 1, 1), old = make_float4(0, 0, 0, 0);
+              if (addrow) add = __ldg(reinterpret_cast<const float4*>(addrow + c));
+              if (gaterow) gt = __ldg(reinterpret_cast<const float4*>(gaterow + c));
+              if (a.accumulate) old = *reinterpret_cast<const float4*>(drow + c);
+              float4 o;
+              o.x = epi1(a, __uint_as_float(r[j * 4 + 0]), c + 0, add.x, gt.x, old.x);
+              o.y = epi1(a, __uint_as_float(r[j * 4 + 1]), c + 1, add.y, gt.y, old.y);
+              o.z = epi1(a, __uint_as_float(r[j * 4 + 2]), c + 2, add.z, gt.z, old.z);
+              o.w = epi1(a, __uint_as_float(r[j * 4 + 3]), c + 3, add.w, gt.w, old.w);
+              *reinterpret_cast<float4*>(drow + c) = o;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int cc = c + e;
+                if (cc < a.nb) {
+                  const float add = addrow ? __ldg(addrow + cc) : 0.f;
+                  const float gt = gaterow ? __ldg(gaterow + cc) : 1.f;
+                  const float old = a.accumulate ? drow[cc] : 0.f;
+                  drow[cc] = epi1(a, __uint_as_float(r[j * 4 + e]), cc, add, gt, old);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host
+namespace tc {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return b2_fail(B2_ERR_INVALID, "tensor map base %p not 16B aligned", ptr);
+  for (int i = 0; i < rank - 1; ++i)
+    if (strides_bytes[i] & 15) return b2_fail(B2_ERR_INVALID, "tensor map stride[%d]=%llu not a multiple of 16 B", i, (unsigned long long)strides_bytes[i]);
+  for (int i = 0; i < rank; ++i)
+    if (box[i] == 0 || box[i] > 256) return b2_fail(B2_ERR_INVALID, "tensor map box[%d]=%u out of range", i, box[i]);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return B2_OK;
+}
+
+}  // namespace tc
+
+namespace {
+
+// Pick the (BW, BH, BN) pixel box of at most `max_rows` rows that wastes the fewest tile slots.
+void choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o) {
+  double best = -1.0; int bbw = 1, bbh = 1, bbn = 1;
+  const int max_b = 256 / istride;
+  for (int bw = 1; bw <= ow && bw <= max_rows && bw <= max_b; ++bw) {
+    for (int bh = 1; bh <= oh && bw * bh <= max_rows && bh <= max_b; ++bh) {
+      int bn = 1;
+      if (bw == ow && bh == oh) { bn = max_rows / (bw * bh); if (bn > n) bn = n; if (bn < 1) bn = 1; }
+      const double tiles = (double)((ow + bw - 1) / bw) * ((oh + bh - 1) / bh) * ((n + bn - 1) / bn);
+      const double eff = ((double)ow * oh * n) / (tiles * max_rows);
+      // prefer wide boxes on ties (longer contiguous runs per TMA row group)
+      const double score = eff + 1e-6 * bw;
+      if (score > best) { best = score; bbw = bw; bbh = bh; bbn = bn; }
+    }
+  }
+  *bw_o = bbw; *bh_o = bbh; *bn_o = bbn;
+}
+
+}  // namespace
+
+extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
+  B2_REQUIRE(p && p->a && p->b && p->d, "b2_conv_gemm: null tensor");
+  B2_REQUIRE(p->n > 0 && p->ih > 0 && p->iw > 0 && p->k > 0 && p->nb > 0 && p->oh > 0 && p->ow > 0, "b2_conv_gemm: bad dims");
+  B2_REQUIRE(p->n_taps >= 1 && p->n_taps <= MAX_TAPS && p->taps, "b2_conv_gemm: n_taps=%d out of range", p->n_taps);
+  B2_REQUIRE(p->lda % 4 == 0 && p->lda >= p->k, "b2_conv_gemm: lda=%d must be a multiple of 4 and >= K", p->lda);
+  B2_REQUIRE(p->ldb % 4 == 0 && p->ldb >= p->k, "b2_conv_gemm: ldb=%d must be a multiple of 4 and >= K", p->ldb);
+  B2_REQUIRE(p->istride >= 1 && p->istride <= 8 && p->ostride >= 1, "b2_conv_gemm: bad strides");
+  B2_REQUIRE(p->n_split == 1 || p->n_split == 3 || p->n_split == 4, "b2_conv_gemm: n_split must be 1, 3 or 4");
+  B2_REQUIRE(p->n_split == 1 || (p->a_lo && p->b_lo), "b2_conv_gemm: split mode needs a_lo and b_lo");
+  B2_REQUIRE(p->ldd >= 1 && p->fh >= 1 && p->fw >= 1, "b2_conv_gemm: bad output geometry");
+
+  ConvKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = p->n; a.ih = p->ih; a.iw = p->iw; a.k = p->k; a.nb = p->nb; a.oh = p->oh; a.ow = p->ow;
+  a.fh = p->fh; a.fw = p->fw; a.ldd = p->ldd; a.ostride = p->ostride; a.ooh = p->ooh; a.oow = p->oow;
+  a.istride = p->istride;
+  choose_box(p->ow, p->oh, p->n, BLOCK_M, p->istride, &a.bw, &a.bh, &a.bn);
+  a.tiles_w = (p->ow + a.bw - 1) / a.bw; a.tiles_h = (p->oh + a.bh - 1) / a.bh; a.tiles_n = (p->n + a.bn - 1) / a.bn;
+  int block_n = ((p->nb + 31) / 32) * 32;
+  if (block_n > MAX_BLOCK_N) block_n = MAX_BLOCK_N;
+  a.block_n = block_n;
+  a.n_tiles_n = (p->nb + block_n - 1) / block_n;
+  const int64_t num_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles_n;
+  B2_REQUIRE(num_tiles < (1ll << 31), "b2_conv_gemm: too many tiles");
+  a.num_tiles = (int)num_tiles;
+  a.n_taps = p->n_taps;
+  for (int i = 0; i < p->n_taps; ++i) {
+    a.dh[i] = (short)p->taps[i * 3 + 0]; a.dw[i] = (short)p->taps[i * 3 + 1]; a.btap[i] = (short)p->taps[i * 3 + 2];
+    B2_REQUIRE(p->taps[i * 3 + 2] >= 0 && p->taps[i * 3 + 2] < p->tb, "b2_conv_gemm: tap %d references weight tap %d >= %d", i, p->taps[i * 3 + 2], p->tb);
+  }
+  a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
+  a.n_pass = p->n_split;
+  a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
+  a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
+             (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
+
+  // A: (K, IW, IH, N) fp32, box (32, BW*s, BH*s, BN) with element strides (1, s, s, 1)
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  {
+    const uint64_t dims[4] = {(uint64_t)p->k, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
+    const uint64_t strides[3] = {(uint64_t)p->lda * 4, (uint64_t)p->iw * p->lda * 4, (uint64_t)p->ih * p->iw * p->lda * 4};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn};
+    const uint32_t es[4] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1};
+    int rc = tc::make_tmap_f32(&tmA, p->a, 4, dims, strides, box, es);
+    if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmAlo, p->a_lo ? p->a_lo : p->a, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)p->k, (uint64_t)p->tb, (uint64_t)p->nb};
+    const uint64_t strides[2] = {(uint64_t)p->ldb * 4, (uint64_t)p->tb * p->ldb * 4};
+    const uint32_t box[3] = {BLOCK_K, 1, (uint32_t)block_n};
+    const uint32_t es[3] = {1, 1, 1};
+    int rc = tc::make_tmap_f32(&tmB, p->b, 3, dims, strides, box, es);
+    if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmBlo, p->b_lo ? p->b_lo : p->b, 3, dims, strides, box, es);
+    if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = b2_sm_count_cached();
+  if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_gemm: no CUDA device");
+  if (p->max_ctas > 0 && p->max_ctas < grid) grid = p->max_ctas;
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  conv_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+  B2_LAUNCH_CHECK("conv_gemm_kernel");
+  return B2_OK;
+}

@@ -1,0 +1,390 @@
+// Weight-gradient convolution on tcgen05 (kind::tf32, fp32 accumulate in TMEM), operands MN-major.
+//   dW[m, tap, c] (+)= sum_pixels dY[pixel, m] * X[pixel @ tap, c]
+// Backward of every student nn.Conv2d on the hot path (autograd of deeplab2.py:92-100 etc.,
+// triggered at train_seg_semisup_mask_mt.py:301,459).
+//
+// GEMM view: M = output channels (tile 128), N = input channels (tile <= 256), K = pixels.
+// Both operands are "pixel-major rows of channels" in HBM (NHWC), i.e. MN-major for this GEMM, so
+// TMA boxes of (32 channels x 32 pixels) land in smem exactly as the canonical MN-major 128B-swizzle
+// atoms the tensor core reads; no transposes anywhere.  K is split over CTAs (pixel ranges) and the
+// partial slabs are reduced in a fixed order by a second kernel => deterministic gradients.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int W_BLOCK_M = 128;
+constexpr int W_MAX_BLOCK_N = 256;
+constexpr int W_KPIX = 32;                              // pixels (GEMM-K) per stage
+constexpr int W_STAGES = 4;
+constexpr int W_SLOT_BYTES = W_KPIX * 128;              // one 32-channel block: 32 pixel rows x 128 B
+constexpr int W_A_STAGE_BYTES = (W_BLOCK_M / 32) * W_SLOT_BYTES;      // 16 KB
+constexpr int W_B_STAGE_BYTES = (W_MAX_BLOCK_N / 32) * W_SLOT_BYTES;  // 32 KB
+constexpr int W_SMEM_BYTES = W_STAGES * (W_A_STAGE_BYTES + W_B_STAGE_BYTES) + 1024 + 256;
+constexpr int W_MAX_TAPS = 16;
+constexpr int W_THREADS = 256;
+constexpr int W_TMEM_COLS = 512;
+
+struct WgradKArgs {
+  int n, oh, ow, m;
+  int ih, iw, c;
+  int istride;
+  int bw, bh, bn;            // pixel box, bw*bh*bn == kpix (multiple of 8)
+  int kpix;
+  int tiles_w, tiles_h, tiles_n, num_pb;
+  int m_tiles, c_tiles, block_n;
+  int n_taps;
+  short dh[W_MAX_TAPS], dw[W_MAX_TAPS], wtap[W_MAX_TAPS];
+  int tw;
+  int out_tiles, n_splits, num_units;
+  int n_pass;
+  float* out;                // dW (n_splits == 1) or workspace slabs
+  int64_t slab_elems;
+  int accumulate;
+  int desc_variant;
+};
+
+struct UnitInfo {
+  int m0, c0, tap, split, pb_begin, pb_end;
+};
+
+__device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, int u) {
+  UnitInfo r;
+  const int ot = u % a.out_tiles;
+  r.split = u / a.out_tiles;
+  int t = ot;
+  const int ct = t % a.c_tiles; t /= a.c_tiles;
+  r.tap = t % a.n_taps;
+  const int mt = t / a.n_taps;
+  r.m0 = mt * W_BLOCK_M; r.c0 = ct * a.block_n;
+  r.pb_begin = (int)(((int64_t)a.num_pb * r.split) / a.n_splits);
+  r.pb_end = (int)(((int64_t)a.num_pb * (r.split + 1)) / a.n_splits);
+  return r;
+}
+
+struct PBox { int w0, h0, n0; bool active; };
+
+__device__ __forceinline__ PBox decode_pb(const WgradKArgs& a, int pb, int tap) {
+  PBox b;
+  const int wt = pb % a.tiles_w; int t = pb / a.tiles_w;
+  const int ht = t % a.tiles_h;
+  const int nt = t / a.tiles_h;
+  b.w0 = wt * a.bw; b.h0 = ht * a.bh; b.n0 = nt * a.bn;
+  const int lo_h = b.h0 * a.istride + a.dh[tap], hi_h = lo_h + (a.bh - 1) * a.istride;
+  const int lo_w = b.w0 * a.istride + a.dw[tap], hi_w = lo_w + (a.bw - 1) * a.istride;
+  b.active = hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw;
+  return b;
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYlo,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                  const __grid_constant__ WgradKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + W_STAGES * W_A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_STAGES * (W_A_STAGE_BYTES + W_B_STAGE_BYTES));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + W_STAGES;
+  uint64_t* tfull_bar = bars + 2 * W_STAGES;
+  uint64_t* tempty_bar = bars + 2 * W_STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 4);
+  volatile int* zero_flag = reinterpret_cast<volatile int*>(tmem_ptr + 2);  // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmY); tc::tma_prefetch_desc(&tmX);
+    if (a.n_pass > 1) { tc::tma_prefetch_desc(&tmYlo); tc::tma_prefetch_desc(&tmXlo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_ptr, W_TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+        const UnitInfo ui = decode_unit(a, u);
+        int na = (a.m - ui.m0 + 31) / 32; if (na > W_BLOCK_M / 32) na = W_BLOCK_M / 32;
+        int nbk = (a.c - ui.c0 + 31) / 32; if (nbk > a.block_n / 32) nbk = a.block_n / 32;
+        const uint32_t tx = (uint32_t)(na + nbk) * (uint32_t)a.kpix * 128u;
+        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
+          const PBox b = decode_pb(a, pb, ui.tap);
+          if (!b.active) continue;
+          const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            tc::mbar_expect_tx(&full_bar[stage], tx);
+            const CUtensorMap* my = (p & 1) ? &tmYlo : &tmY;
+            const CUtensorMap* mx = (p & 2) ? &tmXlo : &tmX;
+            for (int j = 0; j < na; ++j)
+              tc::tma_load_4d(smem_a + stage * W_A_STAGE_BYTES + j * W_SLOT_BYTES, my, &full_bar[stage],
+                              ui.m0 + 32 * j, b.w0, b.h0, b.n0);
+            for (int j = 0; j < nbk; ++j)
+              tc::tma_load_4d(smem_b + stage * W_B_STAGE_BYTES + j * W_SLOT_BYTES, mx, &full_bar[stage],
+                              ui.c0 + 32 * j, xw, xh, b.n0);
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, 1, 1);
+      const uint32_t lbo = a.desc_variant == 1 ? 1024u : (uint32_t)W_SLOT_BYTES;
+      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)W_SLOT_BYTES : 1024u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int ksteps = a.kpix / 8;
+      for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+        const UnitInfo ui = decode_unit(a, u);
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
+        uint32_t first = 1;
+        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
+          const PBox b = decode_pb(a, pb, ui.tap);
+          if (!b.active) continue;
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&full_bar[stage], phase);
+            tc::tc_fence_after();
+            const uint32_t a_addr = tc::smem_u32(smem_a + stage * W_A_STAGE_BYTES);
+            const uint32_t b_addr = tc::smem_u32(smem_b + stage * W_B_STAGE_BYTES);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 1024, lbo, sbo);
+              const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 1024, lbo, sbo);
+              tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            tc::mma_commit(&empty_bar[stage]);
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (first) {              // no active pixel box: the tile is exactly zero
+          zero_flag[acc] = 1;
+          __threadfence_block();
+          tc::mbar_arrive(&tfull_bar[acc]);
+        } else {
+          zero_flag[acc] = 0;
+          __threadfence_block();
+          tc::mma_commit(&tfull_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const UnitInfo ui = decode_unit(a, u);
+      const int mrow = ui.m0 + row;
+      const bool valid = mrow < a.m;
+      float* orow = a.out + (int64_t)ui.split * a.slab_elems + ((int64_t)mrow * a.tw + a.wtap[ui.tap]) * a.c;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const bool is_zero = zero_flag[acc] != 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * W_MAX_BLOCK_N;
+      const int nchunks = a.block_n / 32;
+      const bool vec = (a.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t r[32];
+        tc::tmem_ld_x32(taddr + ch * 32, r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const int col0 = ui.c0 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = col0 + j * 4;
+            if (c >= a.c) break;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = is_zero ? 0.0f : __uint_as_float(r[j * 4 + e]);
+            if (vec && c + 3 < a.c) {
+              float4 o = make_float4(v[0], v[1], v[2], v[3]);
+              if (a.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(orow + c);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(orow + c) = o;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < a.c) orow[c + e] = a.accumulate ? orow[c + e] + v[e] : v[e];
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, W_TMEM_COLS);
+}
+
+// dw[i] = (accumulate ? dw[i] : 0) + sum_s slabs[s][i], fixed order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_splits, int64_t elems,
+                                    float* __restrict__ dw, int accumulate) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += stride) {
+    float s = accumulate ? dw[i] : 0.0f;
+    for (int k = 0; k < n_splits; ++k) s += slabs[(int64_t)k * elems + i];
+    dw[i] = s;
+  }
+}
+
+int g_wgrad_desc_variant = 0;
+
+struct WPlan {
+  WgradKArgs a;
+};
+
+// Pixel box with bw*bh*bn == kpix in {32,24,16,8}: every smem K-row must hold real (or TMA-zero) data.
+void choose_kbox(int ow, int oh, int n, int istride, int* bw_o, int* bh_o, int* bn_o, int* kpix_o) {
+  double best = -1.0; int bbw = 8, bbh = 1, bbn = 1, bk = 8;
+  const int max_b = 256 / istride;
+  for (int bw = 1; bw <= 32 && bw <= max_b; ++bw)
+    for (int bh = 1; bw * bh <= 32 && bh <= max_b; ++bh)
+      for (int bn = 1; bw * bh * bn <= 32; ++bn) {
+        const int kp = bw * bh * bn;
+        if (kp % 8) continue;
+        if (bn > 1 && !(bw >= ow && bh >= oh)) continue;
+        const double tiles = (double)((ow + bw - 1) / bw) * ((oh + bh - 1) / bh) * ((n + bn - 1) / bn);
+        const double eff = ((double)ow * oh * n) / (tiles * kp);    // useful rows / loaded rows
+        const double score = eff * (0.75 + 0.25 * kp / 32.0) + 1e-6 * bw;
+        if (score > best) { best = score; bbw = bw; bbh = bh; bbn = bn; bk = kp; }
+      }
+  *bw_o = bbw; *bh_o = bbh; *bn_o = bbn; *kpix_o = bk;
+}
+
+int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
+  B2_REQUIRE(p && p->dy && p->x && p->dw, "b2_conv_wgrad: null tensor");
+  B2_REQUIRE(p->n > 0 && p->oh > 0 && p->ow > 0 && p->m > 0 && p->ih > 0 && p->iw > 0 && p->c > 0, "b2_conv_wgrad: bad dims");
+  B2_REQUIRE(p->ldy % 4 == 0 && p->ldy >= p->m, "b2_conv_wgrad: ldy=%d must be a multiple of 4 and >= M", p->ldy);
+  B2_REQUIRE(p->ldx % 4 == 0 && p->ldx >= p->c, "b2_conv_wgrad: ldx=%d must be a multiple of 4 and >= C", p->ldx);
+  B2_REQUIRE(p->n_taps >= 1 && p->n_taps <= W_MAX_TAPS && p->taps, "b2_conv_wgrad: n_taps out of range");
+  B2_REQUIRE(p->istride >= 1 && p->istride <= 8, "b2_conv_wgrad: bad istride");
+  B2_REQUIRE(p->n_split == 1 || p->n_split == 3 || p->n_split == 4, "b2_conv_wgrad: n_split must be 1, 3 or 4");
+  B2_REQUIRE(p->n_split == 1 || (p->dy_lo && p->x_lo), "b2_conv_wgrad: split mode needs dy_lo and x_lo");
+  WgradKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = p->n; a.oh = p->oh; a.ow = p->ow; a.m = p->m; a.ih = p->ih; a.iw = p->iw; a.c = p->c; a.istride = p->istride;
+  choose_kbox(p->ow, p->oh, p->n, p->istride, &a.bw, &a.bh, &a.bn, &a.kpix);
+  a.tiles_w = (p->ow + a.bw - 1) / a.bw; a.tiles_h = (p->oh + a.bh - 1) / a.bh; a.tiles_n = (p->n + a.bn - 1) / a.bn;
+  const int64_t num_pb = (int64_t)a.tiles_w * a.tiles_h * a.tiles_n;
+  B2_REQUIRE(num_pb < (1ll << 31), "b2_conv_wgrad: too many pixel boxes");
+  a.num_pb = (int)num_pb;
+  a.m_tiles = (p->m + W_BLOCK_M - 1) / W_BLOCK_M;
+  int block_n = ((p->c + 31) / 32) * 32;
+  if (block_n > W_MAX_BLOCK_N) block_n = W_MAX_BLOCK_N;
+  a.block_n = block_n;
+  a.c_tiles = (p->c + block_n - 1) / block_n;
+  a.n_taps = p->n_taps;
+  for (int i = 0; i < p->n_taps; ++i) {
+    a.dh[i] = (short)p->taps[i * 3 + 0]; a.dw[i] = (short)p->taps[i * 3 + 1]; a.wtap[i] = (short)p->taps[i * 3 + 2];
+    B2_REQUIRE(p->taps[i * 3 + 2] >= 0 && p->taps[i * 3 + 2] < p->tw, "b2_conv_wgrad: tap index out of range");
+  }
+  a.tw = p->tw;
+  a.out_tiles = a.m_tiles * a.n_taps * a.c_tiles;
+  int sms = b2_sm_count_cached();
+  if (sms <= 0) sms = 148;
+  if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
+  int splits = sms / a.out_tiles;
+  if (splits < 1) splits = 1;
+  // keep at least ~8 pixel boxes per split so the pipeline fills
+  const int max_splits = (int)((num_pb + 7) / 8);
+  if (splits > max_splits) splits = max_splits < 1 ? 1 : max_splits;
+  a.n_splits = splits;
+  a.num_units = a.out_tiles * splits;
+  a.n_pass = p->n_split;
+  a.slab_elems = (int64_t)p->m * p->tw * p->c;
+  a.accumulate = p->accumulate;
+  a.desc_variant = g_wgrad_desc_variant;
+  *out = a;
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" void b2_debug_set(int key, int value) {
+  if (key == 1) g_wgrad_desc_variant = value;
+}
+
+extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {
+  WgradKArgs a;
+  if (plan_wgrad(p, &a) != B2_OK) return 0;
+  return a.n_splits > 1 ? (size_t)a.n_splits * a.slab_elems * sizeof(float) : 0;
+}
+
+extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
+  WgradKArgs a;
+  int rc = plan_wgrad(p, &a);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a.n_splits > 1) {
+    const size_t need = (size_t)a.n_splits * a.slab_elems * sizeof(float);
+    B2_REQUIRE(p->workspace && p->workspace_bytes >= need, "b2_conv_wgrad: workspace too small (%zu < %zu)", p->workspace_bytes, need);
+    a.out = reinterpret_cast<float*>(p->workspace);
+    a.accumulate = 0;
+  } else {
+    a.out = p->dw;
+    a.slab_elems = 0;
+  }
+
+  CUtensorMap tmY, tmYlo, tmX, tmXlo;
+  {
+    const uint64_t dims[4] = {(uint64_t)p->m, (uint64_t)p->ow, (uint64_t)p->oh, (uint64_t)p->n};
+    const uint64_t strides[3] = {(uint64_t)p->ldy * 4, (uint64_t)p->ow * p->ldy * 4, (uint64_t)p->oh * p->ow * p->ldy * 4};
+    const uint32_t box[4] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    rc = tc::make_tmap_f32(&tmY, p->dy, 4, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmYlo, p->dy_lo ? p->dy_lo : p->dy, 4, dims, strides, box, es); if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)p->c, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
+    const uint64_t strides[3] = {(uint64_t)p->ldx * 4, (uint64_t)p->iw * p->ldx * 4, (uint64_t)p->ih * p->iw * p->ldx * 4};
+    const uint32_t box[4] = {32, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn};
+    const uint32_t es[4] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1};
+    rc = tc::make_tmap_f32(&tmX, p->x, 4, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmXlo, p->x_lo ? p->x_lo : p->x, 4, dims, strides, box, es); if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = b2_sm_count_cached();
+  if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
+  if (p->max_ctas > 0 && p->max_ctas < grid) grid = p->max_ctas;
+  if (grid > a.num_units) grid = a.num_units;
+  conv_wgrad_kernel<<<grid, W_THREADS, W_SMEM_BYTES, s>>>(tmY, tmYlo, tmX, tmXlo, a);
+  B2_LAUNCH_CHECK("conv_wgrad_kernel");
+  if (a.n_splits > 1) {
+    const int64_t elems = (int64_t)p->m * p->tw * p->c;
+    int64_t blocks = ceil_div64(elems, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
+    B2_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
+  return B2_OK;
+}

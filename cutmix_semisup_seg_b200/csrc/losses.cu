@@ -1,0 +1,278 @@
+// Fused loss kernels of the CutMix mean-teacher hot path (NCHW fp32 logits, one thread per pixel,
+// channel loop strided by H*W so every warp access is a coalesced 128 B line):
+//   L1  consistency block   train_seg_semisup_mask_mt.py:363-367, 406-420, 428-459
+//   L2  supervised CE        train_seg_semisup_mask_mt.py:126, 300-301
+// Both write the UNSCALED logit gradient in the same pass and leave the global scalars
+// (conf_rate, 1/n_valid, ramp, cons_weight) to a 1-block finalize kernel + the gradient consumer,
+// so no host synchronisation is needed (the reference syncs at :413, :461, :469).
+#include "common.cuh"
+#include <math_constants.h>
+
+constexpr int LOSS_THREADS = 256;
+
+enum { LOSS_VAR = 0, LOSS_LOGITS_VAR = 1, LOSS_LOGITS_SMOOTHL1 = 2, LOSS_BCE = 3, LOSS_KLD = 4 };
+
+template <int MAXC>
+__global__ void __launch_bounds__(LOSS_THREADS)
+consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, const float* __restrict__ ls,
+                   const float* __restrict__ m, const float* __restrict__ lmask, float* __restrict__ dls,
+                   double* __restrict__ partials, int C, int64_t hw, int loss_fn, float conf_thresh,
+                   int conf_per_pixel) {
+  __shared__ double red[32];
+  const int img = blockIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
+  double s_conf = 0.0, s_q = 0.0, s_qc = 0.0;
+  if (p < hw) {
+    const int64_t base = (int64_t)img * C * hw + p;
+    const int64_t pm = (int64_t)img * hw + p;
+    float lt[MAXC], st[MAXC];
+    const float mv = m ? __ldg(m + pm) : 0.0f;
+    const float om = __fsub_rn(1.0f, mv);
+    const float w = lmask ? __ldg(lmask + pm) : 1.0f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const float a = __ldg(l0 + base + (int64_t)c * hw);
+        if (l1) {
+          const float b = __ldg(l1 + base + (int64_t)c * hw);
+          lt[c] = __fadd_rn(__fmul_rn(a, om), __fmul_rn(b, mv));  // line 363
+        } else {
+          lt[c] = a;
+        }
+        st[c] = __ldg(ls + base + (int64_t)c * hw);
+      }
+    }
+    // softmax statistics (lines 366-367)
+    float mt = -CUDART_INF_F, ms = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { mt = fmaxf(mt, lt[c]); ms = fmaxf(ms, st[c]); }
+    float sum_t = 0.f, sum_s = 0.f;
+    float pt[MAXC], ps[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) {
+      pt[c] = expf(lt[c] - mt); sum_t += pt[c];
+      ps[c] = expf(st[c] - ms); sum_s += ps[c];
+    }
+    float pmax = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) {
+      pt[c] = pt[c] / sum_t; ps[c] = ps[c] / sum_s;
+      pmax = fmaxf(pmax, pt[c]);
+    }
+    const float conf = (conf_thresh > 0.0f) ? (pmax >= conf_thresh ? 1.0f : 0.0f) : 1.0f;  // lines 407-411
+    // per-pixel loss q and dq/dls (g)
+    float q = 0.f;
+    float g[MAXC];
+    if (loss_fn == LOSS_VAR) {                       // lines 428-431
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float d = ps[c] - pt[c];
+        q += d * d;
+        g[c] = 2.0f * d;
+        dot += g[c] * ps[c];
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) g[c] = ps[c] * (g[c] - dot);
+    } else if (loss_fn == LOSS_LOGITS_VAR) {         // lines 432-435
+      const float inv = 1.0f / sqrtf((float)C);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float d = st[c] - lt[c];
+        q += d * d;
+        g[c] = 2.0f * d * inv;
+      }
+      q *= inv;
+    } else if (loss_fn == LOSS_LOGITS_SMOOTHL1) {    // lines 436-439
+      const float inv = 1.0f / sqrtf((float)C);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float d = st[c] - lt[c];
+        const float ad = fabsf(d);
+        if (ad < 1.0f) { q += 0.5f * d * d; g[c] = d * inv; }
+        else { q += ad - 0.5f; g[c] = (d > 0.f ? 1.0f : -1.0f) * inv; }
+      }
+      q *= inv;
+    } else if (loss_fn == LOSS_BCE) {                // lines 440-443, network_architectures.py:115-118
+      const float eps = 1e-6f;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float t = pt[c], pr = ps[c];
+        const float inv_t = 1.0f - t;
+        const float inv_p = 1.0f - pr + eps;
+        q += -(t * logf(pr + eps) + inv_t * logf(inv_p));
+        g[c] = -(t / (pr + eps) - inv_t / inv_p);
+        dot += g[c] * pr;
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) g[c] = ps[c] * (g[c] - dot);
+    } else {                                         // kld, lines 444-446
+      const float lse = logf(sum_s);
+      float st_sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float t = pt[c];
+        const float logp = (st[c] - ms) - lse;
+        const float tlogt = t > 0.f ? t * logf(t) : 0.f;
+        q += tlogt - t * logp;
+        st_sum += t;
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) g[c] = ps[c] * st_sum - pt[c];
+    }
+    const float gw = conf_per_pixel ? w * conf : w;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) dls[base + (int64_t)c * hw] = g[c] * gw;
+    s_conf = conf;
+    s_q = (double)q * (double)w;
+    s_qc = s_q * conf;
+  }
+  const int64_t bid = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  double r;
+  r = block_sum_d(s_conf, red); if (threadIdx.x == 0) partials[bid * 3 + 0] = r;
+  r = block_sum_d(s_q, red);    if (threadIdx.x == 0) partials[bid * 3 + 1] = r;
+  r = block_sum_d(s_qc, red);   if (threadIdx.x == 0) partials[bid * 3 + 2] = r;
+}
+
+extern "C" int64_t b2_consistency_num_partials(int n, int64_t hw) {
+  return (int64_t)n * ceil_div64(hw, LOSS_THREADS);
+}
+
+extern "C" int b2_consistency_fwd_bwd(const float* l0, const float* l1, const float* ls, const float* m,
+                                      const float* lmask, float* dls, double* partials, int n, int c,
+                                      int64_t hw, int loss_fn, float conf_thresh, int conf_per_pixel,
+                                      void* stream) {
+  B2_REQUIRE(l0 && ls && dls && partials && n > 0 && c > 0 && hw > 0, "b2_consistency_fwd_bwd: bad args");
+  B2_REQUIRE(c <= 64, "b2_consistency_fwd_bwd: C=%d > 64 unsupported", c);
+  B2_REQUIRE(loss_fn >= 0 && loss_fn <= 4, "b2_consistency_fwd_bwd: unknown loss_fn %d", loss_fn);
+  B2_REQUIRE(!(l1 && !m), "b2_consistency_fwd_bwd: l1 given without mix mask");
+  B2_REQUIRE(n <= 65535, "b2_consistency_fwd_bwd: n too large");
+  dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(MC) consistency_kernel<MC><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, m, lmask, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
+  if (c <= 8) LAUNCH(8);
+  else if (c <= 24) LAUNCH(24);
+  else if (c <= 32) LAUNCH(32);
+  else LAUNCH(64);
+#undef LAUNCH
+  B2_LAUNCH_CHECK("consistency_kernel");
+  return B2_OK;
+}
+
+__global__ void __launch_bounds__(1024)
+consistency_finalize_kernel(const double* __restrict__ partials, int64_t n_partials, int64_t n_pixels,
+                            float conf_thresh, int conf_per_pixel, float ramp, float cons_weight,
+                            float* __restrict__ out4) {
+  __shared__ double red[32];
+  double a = 0, b = 0, c = 0;
+  for (int64_t i = threadIdx.x; i < n_partials; i += blockDim.x) {
+    a += partials[i * 3 + 0]; b += partials[i * 3 + 1]; c += partials[i * 3 + 2];
+  }
+  a = block_sum_d(a, red); b = block_sum_d(b, red); c = block_sum_d(c, red);
+  if (threadIdx.x == 0) {
+    const double P = (double)n_pixels;
+    const double conf_rate = a / P;
+    double loss, gscale;
+    if (conf_thresh > 0.0f && !conf_per_pixel) {   // scalar-mean mask, line 415-416
+      loss = conf_rate * (b / P);
+      gscale = conf_rate / P;
+    } else {                                       // per-pixel mask (or no thresholding: conf == 1)
+      loss = c / P;
+      gscale = 1.0 / P;
+    }
+    loss *= (double)ramp;                          // line 454-455
+    out4[0] = (float)loss;
+    out4[1] = (float)conf_rate;
+    out4[2] = (float)(gscale * (double)ramp * (double)cons_weight);
+    out4[3] = (float)(loss * (double)cons_weight); // line 458
+  }
+}
+
+extern "C" int b2_consistency_finalize(const double* partials, int64_t n_partials, int64_t n_pixels,
+                                       float conf_thresh, int conf_per_pixel, float ramp, float cons_weight,
+                                       float* out4, void* stream) {
+  B2_REQUIRE(partials && out4 && n_partials > 0 && n_pixels > 0, "b2_consistency_finalize: bad args");
+  consistency_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_partials, n_pixels, conf_thresh,
+                                                                   conf_per_pixel, ramp, cons_weight, out4);
+  B2_LAUNCH_CHECK("consistency_finalize_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross entropy with ignore_index.
+// ------------------------------------------------------------------------------------------
+template <int MAXC>
+__global__ void __launch_bounds__(LOSS_THREADS)
+ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ dlogits,
+          double* __restrict__ partials, int C, int64_t hw, int64_t ignore_index) {
+  __shared__ double red[32];
+  const int img = blockIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
+  double s_nll = 0.0, s_valid = 0.0;
+  if (p < hw) {
+    const int64_t base = (int64_t)img * C * hw + p;
+    const int64_t lab = __ldg(labels + (int64_t)img * hw + p);
+    const bool valid = lab != ignore_index;
+    float x[MAXC];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { x[c] = __ldg(logits + base + (int64_t)c * hw); mx = fmaxf(mx, x[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { x[c] = x[c] - mx; sum += expf(x[c]); }
+    const float lse = logf(sum);
+    float xl = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) {
+      const float logp = x[c] - lse;
+      float gsm = valid ? expf(logp) : 0.f;
+      if (valid && (int64_t)c == lab) { xl = logp; gsm -= 1.0f; }
+      dlogits[base + (int64_t)c * hw] = gsm;
+    }
+    if (valid) { s_nll = -(double)xl; s_valid = 1.0; }
+  }
+  const int64_t bid = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  double r;
+  r = block_sum_d(s_nll, red);   if (threadIdx.x == 0) partials[bid * 2 + 0] = r;
+  r = block_sum_d(s_valid, red); if (threadIdx.x == 0) partials[bid * 2 + 1] = r;
+}
+
+extern "C" int64_t b2_ce_num_partials(int n, int64_t hw) { return (int64_t)n * ceil_div64(hw, LOSS_THREADS); }
+
+extern "C" int b2_ce_fwd_bwd(const float* logits, const int64_t* labels, float* dlogits, double* partials,
+                             int n, int c, int64_t hw, int64_t ignore_index, void* stream) {
+  B2_REQUIRE(logits && labels && dlogits && partials && n > 0 && c > 0 && hw > 0, "b2_ce_fwd_bwd: bad args");
+  B2_REQUIRE(c <= 64, "b2_ce_fwd_bwd: C=%d > 64 unsupported", c);
+  B2_REQUIRE(n <= 65535, "b2_ce_fwd_bwd: n too large");
+  dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(MC) ce_kernel<MC><<<grid, LOSS_THREADS, 0, s>>>(logits, labels, dlogits, partials, c, hw, ignore_index)
+  if (c <= 8) LAUNCH(8);
+  else if (c <= 24) LAUNCH(24);
+  else if (c <= 32) LAUNCH(32);
+  else LAUNCH(64);
+#undef LAUNCH
+  B2_LAUNCH_CHECK("ce_kernel");
+  return B2_OK;
+}
+
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const double* __restrict__ partials, int64_t n_partials, float* __restrict__ out3) {
+  __shared__ double red[32];
+  double a = 0, b = 0;
+  for (int64_t i = threadIdx.x; i < n_partials; i += blockDim.x) { a += partials[i * 2 + 0]; b += partials[i * 2 + 1]; }
+  a = block_sum_d(a, red); b = block_sum_d(b, red);
+  if (threadIdx.x == 0) {
+    out3[0] = (float)(a / b);          // mean over non-ignored pixels (NaN if none, like PyTorch)
+    out3[1] = (float)b;
+    out3[2] = b > 0 ? (float)(1.0 / b) : 0.f;
+  }
+}
+
+extern "C" int b2_ce_finalize(const double* partials, int64_t n_partials, float* out3, void* stream) {
+  B2_REQUIRE(partials && out3 && n_partials > 0, "b2_ce_finalize: bad args");
+  ce_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_partials, out3);
+  B2_LAUNCH_CHECK("ce_finalize_kernel");
+  return B2_OK;
+}

@@ -1,0 +1,549 @@
+// HBM-bound NHWC network operators around the tensor-core convolutions:
+// layout changes, stem im2col, 3x3/s2 max-pool, bilinear resize, global-average-pool / broadcast,
+// batch-norm (train-mode statistics, apply, backward; frozen-BN folding and parameter gradients),
+// per-channel reductions.  All reductions are two-level with a fixed summation order (deterministic).
+#include "common.cuh"
+#include <math_constants.h>
+
+// ------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int c, int64_t hw, int ldd) {
+  const int n = blockIdx.y;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (int64_t)gridDim.x * blockDim.x) {
+    float* d = dst + ((int64_t)n * hw + p) * ldd;
+    for (int ch = 0; ch < ldd; ++ch) d[ch] = ch < c ? __ldg(src + ((int64_t)n * c + ch) * hw + p) : 0.0f;
+  }
+}
+extern "C" int b2_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int ldd, void* stream) {
+  B2_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && ldd >= c, "b2_nchw_to_nhwc: bad args");
+  const int64_t hw = (int64_t)h * w;
+  int bx = (int)((hw + 255) / 256); if (bx > 4096) bx = 4096;
+  nchw_to_nhwc_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(src, dst, c, hw, ldd);
+  B2_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return B2_OK;
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int c, int64_t hw, int lds) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32; const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t p = p0 + i; const int ch = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && ch < c) ? src[((int64_t)n * hw + p) * lds + ch] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i; const int64_t p = p0 + threadIdx.x;
+    if (p < hw && ch < c) dst[((int64_t)n * c + ch) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+extern "C" int b2_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, int lds, void* stream) {
+  B2_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && lds >= c, "b2_nhwc_to_nchw: bad args");
+  const int64_t hw = (int64_t)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, n);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, c, hw, lds);
+  B2_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ im2col
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n, int h, int w, int c, int ldx,
+                              int kh, int kw, int stride, int pad, int dil, int oh, int ow, int kpad) {
+  const int64_t total = (int64_t)n * oh * ow * kpad;
+  const int kreal = kh * kw * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % kpad); int64_t row = i / kpad;
+    float v = 0.f;
+    if (j < kreal) {
+      const int cc = j % c; const int t = j / c; const int s = t % kw; const int r = t / kw;
+      const int x_o = (int)(row % ow); row /= ow; const int y_o = (int)(row % oh); const int img = (int)(row / oh);
+      const int iy = y_o * stride - pad + r * dil, ix = x_o * stride - pad + s * dil;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((int64_t)img * h + iy) * w + ix) * ldx + cc);
+    }
+    col[i] = v;
+  }
+}
+extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
+                         int dil, int oh, int ow, int kpad, void* stream) {
+  B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
+  const int64_t total = (int64_t)n * oh * ow * kpad;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, col, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad);
+  B2_LAUNCH_CHECK("im2col_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
+__global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, int n, int h, int w,
+                               int c, int oh, int ow) {
+  const int64_t total = (int64_t)n * oh * ow * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); int64_t t = i / c;
+    const int xo = (int)(t % ow); t /= ow; const int yo = (int)(t % oh); const int img = (int)(t / oh);
+    float best = -CUDART_INF_F; int bi = 0; bool any = false;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iy = yo * 2 - 1 + r, ix = xo * 2 - 1 + s;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          const float v = __ldg(x + (((int64_t)img * h + iy) * w + ix) * c + ch);
+          if (!any || v > best || v != v) { best = v; bi = r * 3 + s; any = true; }
+        }
+      }
+    y[i] = best; idx[i] = (uint8_t)bi;
+  }
+}
+extern "C" int b2_maxpool3x3s2(const float* x, float* y, uint8_t* idx, int n, int h, int w, int c, int oh, int ow, void* stream) {
+  B2_REQUIRE(x && y && idx && n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "b2_maxpool3x3s2: bad args");
+  const int64_t total = (int64_t)n * oh * ow * c;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  maxpool_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, idx, n, h, w, c, oh, ow);
+  B2_LAUNCH_CHECK("maxpool_kernel");
+  return B2_OK;
+}
+// gather form: each input pixel looks at the (up to 4) windows that contain it -> no atomics.
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx, int n,
+                                   int h, int w, int c, int oh, int ow) {
+  const int64_t total = (int64_t)n * h * w * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); int64_t t = i / c;
+    const int ix = (int)(t % w); t /= w; const int iy = (int)(t % h); const int img = (int)(t / h);
+    float g = 0.f;
+    const int yo_lo = iy / 2, yo_hi = (iy + 1) / 2;   // windows with yo*2-1 <= iy <= yo*2+1
+    const int xo_lo = ix / 2, xo_hi = (ix + 1) / 2;
+    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      if (yo >= oh) continue;
+      const int r = iy - (yo * 2 - 1);
+      if (r < 0 || r > 2) continue;
+      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+        if (xo >= ow) continue;
+        const int s = ix - (xo * 2 - 1);
+        if (s < 0 || s > 2) continue;
+        const int64_t o = (((int64_t)img * oh + yo) * ow + xo) * c + ch;
+        if (idx[o] == r * 3 + s) g += __ldg(dy + o);
+      }
+    }
+    dx[i] = g;
+  }
+}
+extern "C" int b2_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int n, int h, int w, int c, int oh, int ow,
+                                   void* stream) {
+  B2_REQUIRE(dy && idx && dx && n > 0, "b2_maxpool3x3s2_bwd: bad args");
+  const int64_t total = (int64_t)n * h * w * c;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  maxpool_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, idx, dx, n, h, w, c, oh, ow);
+  B2_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ bilinear
+// PyTorch upsample_bilinear2d index math (UpSample.h area_pixel_compute_source_index), fp32.
+struct LinCoef { int i0, i1; float l0, l1; };
+__device__ __forceinline__ float lin_scale(int in, int out, int align) {
+  if (align) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  return (float)in / (float)out;
+}
+__device__ __forceinline__ LinCoef lin_coef(int dst, int in, float scale, int align) {
+  float src;
+  if (align) src = scale * dst;
+  else { src = scale * (dst + 0.5f) - 0.5f; if (src < 0.f) src = 0.f; }
+  LinCoef k;
+  k.i0 = (int)src; if (k.i0 > in - 1) k.i0 = in - 1;
+  k.i1 = k.i0 + (k.i0 < in - 1 ? 1 : 0);
+  k.l1 = src - (float)k.i0; k.l0 = 1.f - k.l1;
+  return k;
+}
+
+// NHWC -> NHWC : thread per (pixel, channel), channel fastest.
+__global__ void bilinear_fwd_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw, int c, int ldx,
+                                         int oh, int ow, int ldy, int align) {
+  const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
+  const int64_t total = (int64_t)n * oh * ow * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); int64_t t = i / c;
+    const int xo = (int)(t % ow); t /= ow; const int yo = (int)(t % oh); const int img = (int)(t / oh);
+    const LinCoef ky = lin_coef(yo, ih, sh, align), kx = lin_coef(xo, iw, sw, align);
+    const float* b = x + (int64_t)img * ih * iw * ldx + ch;
+    const float v00 = __ldg(b + ((int64_t)ky.i0 * iw + kx.i0) * ldx), v01 = __ldg(b + ((int64_t)ky.i0 * iw + kx.i1) * ldx);
+    const float v10 = __ldg(b + ((int64_t)ky.i1 * iw + kx.i0) * ldx), v11 = __ldg(b + ((int64_t)ky.i1 * iw + kx.i1) * ldx);
+    y[(((int64_t)img * oh + yo) * ow + xo) * ldy + ch] = ky.l0 * (kx.l0 * v00 + kx.l1 * v01) + ky.l1 * (kx.l0 * v10 + kx.l1 * v11);
+  }
+}
+// NHWC -> NCHW : thread per output pixel (xo fastest), loop over channels: coalesced plane writes.
+__global__ void bilinear_fwd_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw, int c, int ldx,
+                                         int oh, int ow, int align) {
+  const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
+  const int64_t ohw = (int64_t)oh * ow;
+  const int64_t total = (int64_t)n * ohw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % ow); int64_t t = i / ow; const int yo = (int)(t % oh); const int img = (int)(t / oh);
+    const LinCoef ky = lin_coef(yo, ih, sh, align), kx = lin_coef(xo, iw, sw, align);
+    const float* b = x + (int64_t)img * ih * iw * ldx;
+    const float* p00 = b + ((int64_t)ky.i0 * iw + kx.i0) * ldx; const float* p01 = b + ((int64_t)ky.i0 * iw + kx.i1) * ldx;
+    const float* p10 = b + ((int64_t)ky.i1 * iw + kx.i0) * ldx; const float* p11 = b + ((int64_t)ky.i1 * iw + kx.i1) * ldx;
+    float* o = y + (int64_t)img * c * ohw + (int64_t)yo * ow + xo;
+    for (int ch = 0; ch < c; ++ch)
+      o[(int64_t)ch * ohw] = ky.l0 * (kx.l0 * __ldg(p00 + ch) + kx.l1 * __ldg(p01 + ch)) + ky.l1 * (kx.l0 * __ldg(p10 + ch) + kx.l1 * __ldg(p11 + ch));
+  }
+}
+extern "C" int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int c, int ldx, int oh, int ow, int ldy,
+                               int align_corners, int to_nchw, void* stream) {
+  B2_REQUIRE(x && y && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_fwd: bad args");
+  if (to_nchw) {
+    const int64_t total = (int64_t)n * oh * ow;
+    int64_t blocks = ceil_div64(total, 128); if (blocks > 148 * 64) blocks = 148 * 64;
+    bilinear_fwd_nchw_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(x, y, n, ih, iw, c, ldx, oh, ow, align_corners);
+  } else {
+    B2_REQUIRE(ldy >= c, "b2_bilinear_fwd: ldy < c");
+    const int64_t total = (int64_t)n * oh * ow * c;
+    int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+    bilinear_fwd_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
+  }
+  B2_LAUNCH_CHECK("bilinear_fwd");
+  return B2_OK;
+}
+
+// Backward, gather form: input index i receives from every output o whose (i0 == i) or (i1 == i).
+// Candidate range [lo, hi] of outputs is derived from the inverse map and widened; the exact
+// forward coefficients decide membership, so the result is independent of the widening.
+__device__ __forceinline__ void out_range(int i, int in, int out, float scale, int align, int* lo, int* hi) {
+  if (scale <= 0.f) { *lo = 0; *hi = out - 1; return; }
+  float a, b;
+  if (align) { a = ((float)i - 1.f) / scale; b = ((float)i + 1.f) / scale; }
+  else { a = ((float)i - 1.f + 0.5f) / scale - 0.5f; b = ((float)i + 1.f + 0.5f) / scale - 0.5f; }
+  int l = (int)floorf(a) - 1, h = (int)ceilf(b) + 1;
+  if (l < 0) l = 0; if (h > out - 1) h = out - 1;
+  *lo = l; *hi = h;
+}
+
+template <bool FROM_NCHW>
+__global__ void bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int ih, int iw, int c, int ldx,
+                                    int oh, int ow, int ldy, int align, const float* __restrict__ scale_dev, float scale_host,
+                                    int accumulate) {
+  const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
+  const float gs = (scale_dev ? scale_dev[0] : 1.f) * scale_host;
+  const int64_t total = (int64_t)n * ih * iw * c;
+  const int64_t ohw = (int64_t)oh * ow;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ch, xi, yi, img;
+    if (FROM_NCHW) {  // (n, c, yi, xi), xi fastest: coalesced reads of dy planes
+      xi = (int)(i % iw); int64_t t = i / iw; yi = (int)(t % ih); t /= ih; ch = (int)(t % c); img = (int)(t / c);
+    } else {          // (n, yi, xi, c), c fastest
+      ch = (int)(i % c); int64_t t = i / c; xi = (int)(t % iw); t /= iw; yi = (int)(t % ih); img = (int)(t / ih);
+    }
+    int ylo, yhi, xlo, xhi;
+    out_range(yi, ih, oh, sh, align, &ylo, &yhi);
+    out_range(xi, iw, ow, sw, align, &xlo, &xhi);
+    float acc = 0.f;
+    for (int yo = ylo; yo <= yhi; ++yo) {
+      const LinCoef ky = lin_coef(yo, ih, sh, align);
+      float wy = 0.f;
+      if (ky.i0 == yi) wy += ky.l0;
+      if (ky.i1 == yi) wy += ky.l1;
+      if (wy == 0.f && !(ky.i0 == yi || ky.i1 == yi)) continue;
+      float rowacc = 0.f;
+      for (int xo = xlo; xo <= xhi; ++xo) {
+        const LinCoef kx = lin_coef(xo, iw, sw, align);
+        float wx = 0.f; bool hit = false;
+        if (kx.i0 == xi) { wx += kx.l0; hit = true; }
+        if (kx.i1 == xi) { wx += kx.l1; hit = true; }
+        if (!hit) continue;
+        const float g = FROM_NCHW ? __ldg(dy + ((int64_t)img * c + ch) * ohw + (int64_t)yo * ow + xo)
+                                  : __ldg(dy + (((int64_t)img * oh + yo) * ow + xo) * ldy + ch);
+        rowacc += wx * g;
+      }
+      acc += wy * rowacc;
+    }
+    float* d = dx + (((int64_t)img * ih + yi) * iw + xi) * ldx + ch;
+    *d = accumulate ? *d + acc * gs : acc * gs;
+  }
+}
+extern "C" int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw, int c, int ldx, int oh, int ow, int ldy,
+                               int align_corners, int from_nchw, const float* scale_dev, float scale_host, int accumulate,
+                               void* stream) {
+  B2_REQUIRE(dy && dx && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_bwd: bad args");
+  const int64_t total = (int64_t)n * ih * iw * c;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  if (from_nchw)
+    bilinear_bwd_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+  else
+    bilinear_bwd_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+  B2_LAUNCH_CHECK("bilinear_bwd_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ column reductions
+// partial[chunk][c][k] = sum over the chunk's rows of f_k(row, c), k < 2, in double.
+// MODE 0: (x, -)            colsum
+// MODE 1: (x, x*x)          BN statistics
+// MODE 2: (g, g*xhat)       BN backward, g = dy * gate(y) * drop, xhat = (x - mean) * rstd
+// MODE 3: (g, g*y)          frozen-BN parameter gradients (y = BN output proxy), g = dy gated by gate>0
+constexpr int RED_ROWS_PER_CHUNK = 512;
+struct RedArgs {
+  const float* a; int lda;      // dy or x
+  const float* b; int ldb;      // x (mode 2) / y (mode 3)
+  const float* gate; int ldg;   // relu gate tensor (y > 0) or NULL
+  const float* drop; float drop_scale;  // dropout mask laid out like dy (ld = lda) or NULL
+  const float* mean; const float* rstd;
+  int64_t rows; int c;
+};
+template <int MODE>
+__global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __restrict__ partial) {
+  __shared__ double sm[8][32][2];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int ch = blockIdx.y * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS_PER_CHUNK;
+  int64_t r1 = r0 + RED_ROWS_PER_CHUNK; if (r1 > r.rows) r1 = r.rows;
+  double s0 = 0.0, s1 = 0.0;
+  if (ch < r.c) {
+    float mean = 0.f, rstd = 1.f;
+    if (MODE == 2) { mean = r.mean[ch]; rstd = r.rstd[ch]; }
+    for (int64_t row = r0 + ry; row < r1; row += 8) {
+      float v = __ldg(r.a + row * r.lda + ch);
+      if (MODE == 0) { s0 += v; }
+      else if (MODE == 1) { s0 += v; s1 += (double)v * (double)v; }
+      else {
+        if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
+        if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
+        const float bv = __ldg(r.b + row * r.ldb + ch);
+        const float o = MODE == 2 ? (bv - mean) * rstd : bv;
+        s0 += v; s1 += (double)v * (double)o;
+      }
+    }
+  }
+  sm[ry][cx][0] = s0; sm[ry][cx][1] = s1;
+  __syncthreads();
+  if (ry == 0 && ch < r.c) {
+    double t0 = 0, t1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t0 += sm[k][cx][0]; t1 += sm[k][cx][1]; }
+    partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 0] = t0;
+    partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 1] = t1;
+  }
+}
+static inline int64_t red_chunks(int64_t rows) { return ceil_div64(rows, RED_ROWS_PER_CHUNK); }
+extern "C" int64_t b2_bn_workspace_doubles(int64_t rows, int c) { return red_chunks(rows) * c * 2 + 2 * (int64_t)c; }
+
+template <int MODE>
+static int launch_col_reduce(const RedArgs& r, double* ws, cudaStream_t s) {
+  dim3 grid((unsigned)red_chunks(r.rows), (r.c + 31) / 32);
+  col_reduce_kernel<MODE><<<grid, 256, 0, s>>>(r, ws);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return b2_fail(B2_ERR_CUDA, "col_reduce launch failed: %s", cudaGetErrorString(e));
+  return B2_OK;
+}
+
+// final[c][k] = sum over chunks (fixed order); thread per channel.
+__global__ void col_finalize_kernel(const double* __restrict__ partial, int64_t chunks, int c, double* __restrict__ fin) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double t0 = 0, t1 = 0;
+  for (int64_t k = 0; k < chunks; ++k) { t0 += partial[(k * c + ch) * 2]; t1 += partial[(k * c + ch) * 2 + 1]; }
+  fin[ch * 2] = t0; fin[ch * 2 + 1] = t1;
+}
+
+__global__ void colsum_out_kernel(const double* __restrict__ fin, int c, float* __restrict__ out, int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch < c) out[ch] = (accumulate ? out[ch] : 0.f) + (float)fin[ch * 2];
+}
+extern "C" int b2_colsum(const float* dy, int ld, int64_t rows, int c, float* out, int accumulate, double* workspace, void* stream) {
+  B2_REQUIRE(dy && out && workspace && rows > 0 && c > 0 && ld >= c, "b2_colsum: bad args");
+  RedArgs r{}; r.a = dy; r.lda = ld; r.rows = rows; r.c = c;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_col_reduce<0>(r, workspace, s); if (rc) return rc;
+  double* fin = workspace + red_chunks(rows) * c * 2;
+  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  colsum_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, out, accumulate);
+  B2_LAUNCH_CHECK("colsum");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batch norm (train mode)
+__global__ void bn_stats_out_kernel(const double* __restrict__ fin, int c, int64_t rows, float eps, float momentum,
+                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rm, float* __restrict__ rv) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double n = (double)rows;
+  const double m = fin[ch * 2] / n;
+  double var = fin[ch * 2 + 1] / n - m * m; if (var < 0) var = 0;
+  mean[ch] = (float)m;
+  rstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rm) rm[ch] = (1.f - momentum) * rm[ch] + momentum * (float)m;
+  if (rv) {
+    const double unb = rows > 1 ? var * n / (n - 1.0) : var;
+    rv[ch] = (1.f - momentum) * rv[ch] + momentum * (float)unb;
+  }
+}
+extern "C" int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float eps, float momentum, float* mean, float* rstd,
+                           float* running_mean, float* running_var, double* workspace, void* stream) {
+  B2_REQUIRE(x && mean && rstd && workspace && rows > 0 && c > 0 && ldx >= c, "b2_bn_stats: bad args");
+  RedArgs r{}; r.a = x; r.lda = ldx; r.rows = rows; r.c = c;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_col_reduce<1>(r, workspace, s); if (rc) return rc;
+  double* fin = workspace + red_chunks(rows) * c * 2;
+  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  bn_stats_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, rows, eps, momentum, mean, rstd, running_mean, running_var);
+  B2_LAUNCH_CHECK("bn_stats");
+  return B2_OK;
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t rows, int c, int ldx, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int relu, const float* __restrict__ drop, float drop_scale, float* __restrict__ y, int ldy) {
+  const int64_t total = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); const int64_t row = i / c;
+    float v = (x[row * ldx + ch] - mean[ch]) * rstd[ch] * gamma[ch] + beta[ch];
+    if (relu) v = fmaxf(v, 0.f);
+    if (drop) v *= drop[row * c + ch] * drop_scale;
+    y[row * ldy + ch] = v;
+  }
+}
+extern "C" int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, int relu, const float* dropmask, float drop_scale, float* y, int ldy, void* stream) {
+  B2_REQUIRE(x && y && mean && rstd && gamma && beta && rows > 0 && c > 0, "b2_bn_apply: bad args");
+  const int64_t total = rows * c;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  bn_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy);
+  B2_LAUNCH_CHECK("bn_apply_kernel");
+  return B2_OK;
+}
+
+__global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, const float* __restrict__ y,
+                                 int ldy, int64_t rows, int c, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 const float* __restrict__ gamma, int relu, const float* __restrict__ drop, float drop_scale,
+                                 const double* __restrict__ fin, float* __restrict__ dx, int lddx) {
+  const int64_t total = rows * c;
+  const double inv_n = 1.0 / (double)rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); const int64_t row = i / c;
+    float g = dy[row * lddy + ch];
+    if (relu && !(y[row * ldy + ch] > 0.f)) g = 0.f;
+    if (drop) g *= drop[row * c + ch] * drop_scale;
+    const float xhat = (x[row * ldx + ch] - mean[ch]) * rstd[ch];
+    const float mdb = (float)(fin[ch * 2] * inv_n), mdg = (float)(fin[ch * 2 + 1] * inv_n);
+    dx[row * lddx + ch] = gamma[ch] * rstd[ch] * (g - mdb - xhat * mdg);
+  }
+}
+__global__ void bn_param_out_kernel(const double* __restrict__ fin, int c, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + (float)fin[ch * 2];
+  if (dgamma) dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)fin[ch * 2 + 1];
+}
+extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y, int ldy, int64_t rows, int c,
+                         const float* mean, const float* rstd, const float* gamma, int relu, const float* dropmask, float drop_scale,
+                         float* dx, int lddx, float* dgamma, float* dbeta, int accumulate_params, double* workspace, void* stream) {
+  B2_REQUIRE(dy && x && dx && mean && rstd && gamma && workspace && rows > 0 && c > 0, "b2_bn_bwd: bad args");
+  B2_REQUIRE(!relu || y, "b2_bn_bwd: relu gate needs y");
+  B2_REQUIRE(!dropmask || lddy == c, "b2_bn_bwd: dropout mask requires dense dy");
+  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = x; r.ldb = ldx; r.gate = relu ? y : nullptr; r.ldg = ldy;
+  r.drop = dropmask; r.drop_scale = drop_scale; r.mean = mean; r.rstd = rstd; r.rows = rows; r.c = c;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_col_reduce<2>(r, workspace, s); if (rc) return rc;
+  double* fin = workspace + red_chunks(rows) * c * 2;
+  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  const int64_t total = rows * c;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  bn_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx);
+  bn_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, dgamma, dbeta, accumulate_params);
+  B2_LAUNCH_CHECK("bn_bwd");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ frozen BN
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift, int c) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float s = gamma[ch] / sqrtf(var[ch] + eps);
+  scale[ch] = s; shift[ch] = beta[ch] - mean[ch] * s;
+}
+extern "C" int b2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                          float* shift, int c, void* stream) {
+  B2_REQUIRE(gamma && beta && mean && var && scale && shift && c > 0, "b2_bn_fold: bad args");
+  bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, shift, c);
+  B2_LAUNCH_CHECK("bn_fold_kernel");
+  return B2_OK;
+}
+
+// Frozen-statistics BN with trainable affine (torchvision backbone under freeze_batchnorm):
+//   y = xhat*gamma + beta  =>  dbeta = sum g, dgamma = sum g*xhat with xhat = (y - beta)/gamma recovered
+//   from the stored BN output proxy `ybn` (only needed where the gate is open).  g = dy gated by gate>0.
+__global__ void bn_eval_param_out_kernel(const double* __restrict__ fin, int c, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                         int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double sg = fin[ch * 2], sgy = fin[ch * 2 + 1];
+  const double ga = gamma[ch], be = beta[ch];
+  const double dg = ga != 0.0 ? (sgy - be * sg) / ga : 0.0;
+  dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + (float)sg;
+  dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)dg;
+}
+extern "C" int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, int64_t rows, int c, const float* gamma,
+                                     const float* beta, const float* gate, int ldg, float* dgamma, float* dbeta, int accumulate,
+                                     double* workspace, void* stream) {
+  B2_REQUIRE(dy && ybn && gamma && beta && dgamma && dbeta && workspace && rows > 0 && c > 0, "b2_bn_eval_param_grad: bad args");
+  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = ybn; r.ldb = ldy; r.gate = gate; r.ldg = ldg; r.rows = rows; r.c = c;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_col_reduce<3>(r, workspace, s); if (rc) return rc;
+  double* fin = workspace + red_chunks(rows) * c * 2;
+  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  bn_eval_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, gamma, beta, dgamma, dbeta, accumulate);
+  B2_LAUNCH_CHECK("bn_eval_param_grad");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ GAP / broadcast
+__global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c, int ldx, float mul) {
+  __shared__ float sm[8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx; const int n = blockIdx.y;
+  float s = 0.f;
+  if (ch < c) for (int p = ry; p < hw; p += 8) s += __ldg(x + ((int64_t)n * hw + p) * ldx + ch);
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && ch < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    y[(int64_t)n * c + ch] = t * mul;
+  }
+}
+extern "C" int b2_gap_fwd(const float* x, float* y, int n, int hw, int c, int ldx, void* stream) {
+  B2_REQUIRE(x && y && n > 0 && hw > 0 && c > 0 && ldx >= c, "b2_gap_fwd: bad args");
+  gap_fwd_kernel<<<dim3((c + 31) / 32, n), 256, 0, (cudaStream_t)stream>>>(x, y, hw, c, ldx, 1.0f / (float)hw);
+  B2_LAUNCH_CHECK("gap_fwd_kernel");
+  return B2_OK;
+}
+__global__ void bcast_kernel(const float* __restrict__ v, float* __restrict__ y, int hw, int c, int ldy, float mul, int accumulate) {
+  const int n = blockIdx.y;
+  const int64_t total = (int64_t)hw * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); const int64_t p = i / c;
+    float* d = y + ((int64_t)n * hw + p) * ldy + ch;
+    const float val = v[(int64_t)n * c + ch] * mul;
+    *d = accumulate ? *d + val : val;
+  }
+}
+extern "C" int b2_gap_bwd(const float* dy, float* dx, int n, int hw, int c, int ldx, int accumulate, void* stream) {
+  B2_REQUIRE(dy && dx && n > 0 && hw > 0 && c > 0, "b2_gap_bwd: bad args");
+  int bx = (int)(((int64_t)hw * c + 255) / 256); if (bx > 2048) bx = 2048;
+  bcast_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(dy, dx, hw, c, ldx, 1.0f / (float)hw, accumulate);
+  B2_LAUNCH_CHECK("gap_bwd");
+  return B2_OK;
+}
+extern "C" int b2_bcast_fwd(const float* v, float* y, int n, int hw, int c, int ldy, void* stream) {
+  B2_REQUIRE(v && y && n > 0 && hw > 0 && c > 0, "b2_bcast_fwd: bad args");
+  int bx = (int)(((int64_t)hw * c + 255) / 256); if (bx > 2048) bx = 2048;
+  bcast_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(v, y, hw, c, ldy, 1.0f, 0);
+  B2_LAUNCH_CHECK("bcast_fwd");
+  return B2_OK;
+}
+extern "C" int b2_bcast_bwd(const float* dy, float* dv, int n, int hw, int c, int ldy, void* stream) {
+  B2_REQUIRE(dy && dv && n > 0 && hw > 0 && c > 0, "b2_bcast_bwd: bad args");
+  gap_fwd_kernel<<<dim3((c + 31) / 32, n), 256, 0, (cudaStream_t)stream>>>(dy, dv, hw, c, ldy, 1.0f);
+  B2_LAUNCH_CHECK("bcast_bwd");
+  return B2_OK;
+}

@@ -1,0 +1,189 @@
+"""Python-side operator layer: thin wrappers that marshal torch CUDA tensors into the C ABI of
+libb200seg.so (include/b200seg.h).  No arithmetic happens here; every op fails loudly if the
+extension is missing or a tensor is not on a CUDA device (there is no CPU fallback).
+
+Internal activation layout is NHWC fp32: a tensor of shape (N, H, W, ld) of which channels
+[off, off + C) are addressed through views (`NHWC` below), so convolutions can write into slices
+of a concat buffer.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+LOSS_FNS = {'var': 0, 'logits_var': 1, 'logits_smoothl1': 2, 'bce': 3, 'kld': 4}
+
+
+class CudaBackend(object):
+    """The (only) product backend: every method is one or two launches of hand-written kernels."""
+
+    name = 'cuda'
+
+    def __init__(self):
+        L.load()
+        self._keep = []          # host-side arrays that must outlive an async launch (none today)
+        self.launches = 0
+        self.precision_split = 1  # 1 = single-pass TF32; 3/4 = 3xTF32 parity mode
+
+    # ------------------------------------------------------------------ helpers
+    def _s(self):
+        return L.stream_ptr()
+
+    def _call(self, name, *args):
+        self.launches += 1
+        return L.call(name, *args)
+
+    @staticmethod
+    def empty(shape, device, dtype=torch.float32):
+        return torch.empty(shape, device=device, dtype=dtype)
+
+    @staticmethod
+    def zeros(shape, device, dtype=torch.float32):
+        return torch.zeros(shape, device=device, dtype=dtype)
+
+    # ------------------------------------------------------------------ elementwise hot-path ops
+    def ema_step_flat(self, tgt, src, alpha):
+        L.require_cuda(tgt, src)
+        one_minus_alpha = 1.0 - alpha   # double, rounded to fp32 by ctypes like torch does (optim_weight_ema.py:22)
+        self._call('b2_ema_step_flat', tgt.data_ptr(), src.data_ptr(), tgt.numel(), alpha, one_minus_alpha, self._s())
+
+    def ema_step_table(self, table, n_chunks, alpha):
+        one_minus_alpha = 1.0 - alpha
+        self._call('b2_ema_step', table.data_ptr(), n_chunks, alpha, one_minus_alpha, self._s())
+
+    def box_mask_rasterize(self, boxes, h, w, init):
+        """boxes: int32 CUDA tensor (N, B, 4) [y0,y1,x0,x1) -> (N,1,H,W) fp32."""
+        L.require_cuda(boxes)
+        n, nb = boxes.shape[0], boxes.shape[1]
+        out = torch.empty((n, 1, h, w), device=boxes.device, dtype=torch.float32)
+        self._call('b2_box_mask_rasterize', boxes.data_ptr(), n, nb, h, w, float(init), out.data_ptr(), self._s())
+        return out
+
+    def mix(self, a, b, m, out=None):
+        """out = a*(1-m) + b*m (b None: a*m).  a: (N,C,H,W) contiguous, m: (N,1,H,W)."""
+        L.require_cuda(a, b, m)
+        a = a.contiguous(); m = m.contiguous()
+        if b is not None:
+            b = b.contiguous()
+        n, c, h, w = a.shape
+        if out is None:
+            out = torch.empty_like(a)
+        self._call('b2_mix', a.data_ptr(), L.ptr(b), m.data_ptr(), out.data_ptr(), n, c, h * w, self._s())
+        return out
+
+    def consistency(self, l0, l1, ls, m, lmask, loss_fn, conf_thresh, conf_per_pixel, ramp, cons_weight, dls=None):
+        """Fused consistency loss.  Returns (out4, dls_unscaled): out4 = [loss, conf_rate, grad_scale, unsup_loss]."""
+        L.require_cuda(l0, l1, ls, m, lmask)
+        n, c, h, w = ls.shape
+        hw = h * w
+        if dls is None:
+            dls = torch.empty_like(ls)
+        npart = L.call('b2_consistency_num_partials', n, hw)
+        partials = torch.empty((npart * 3,), device=ls.device, dtype=torch.float64)
+        out4 = torch.empty((4,), device=ls.device, dtype=torch.float32)
+        self._call('b2_consistency_fwd_bwd', l0.data_ptr(), L.ptr(l1), ls.data_ptr(), L.ptr(m), L.ptr(lmask),
+                   dls.data_ptr(), partials.data_ptr(), n, c, hw, LOSS_FNS[loss_fn], float(conf_thresh),
+                   int(bool(conf_per_pixel)), self._s())
+        self._call('b2_consistency_finalize', partials.data_ptr(), npart, n * hw, float(conf_thresh),
+                   int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
+        return out4, dls
+
+    def cross_entropy(self, logits, labels, ignore_index=255, dlogits=None):
+        """Returns (out3, dlogits_unscaled): out3 = [loss, n_valid, grad_scale]."""
+        L.require_cuda(logits, labels)
+        n, c, h, w = logits.shape
+        hw = h * w
+        if dlogits is None:
+            dlogits = torch.empty_like(logits)
+        npart = L.call('b2_ce_num_partials', n, hw)
+        partials = torch.empty((npart * 2,), device=logits.device, dtype=torch.float64)
+        out3 = torch.empty((3,), device=logits.device, dtype=torch.float32)
+        self._call('b2_ce_fwd_bwd', logits.data_ptr(), labels.data_ptr(), dlogits.data_ptr(), partials.data_ptr(),
+                   n, c, hw, int(ignore_index), self._s())
+        self._call('b2_ce_finalize', partials.data_ptr(), npart, out3.data_ptr(), self._s())
+        return out3, dlogits
+
+    def scale_inplace(self, x, scale_dev, scale_host=1.0):
+        self._call('b2_scale_inplace', x.data_ptr(), x.numel(), L.ptr(scale_dev), float(scale_host), self._s())
+
+    def add_inplace(self, dst, src):
+        self._call('b2_add_inplace', dst.data_ptr(), src.data_ptr(), dst.numel(), self._s())
+
+    def fill(self, dst, value):
+        self._call('b2_fill', dst.data_ptr(), float(value), dst.numel(), self._s())
+
+    def split_tf32(self, x):
+        hi = torch.empty_like(x); lo = torch.empty_like(x)
+        self._call('b2_split_tf32', x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), self._s())
+        return hi, lo
+
+    def transpose_w(self, w, a, t, b, out=None):
+        """(A,T,B) -> (B,T,A) on the raw storage of `w`."""
+        if out is None:
+            out = torch.empty((b, t, a), device=w.device, dtype=torch.float32)
+        self._call('b2_transpose_w', w.data_ptr(), out.data_ptr(), a, t, b, self._s())
+        return out
+
+    # ------------------------------------------------------------------ tensor-core convolution
+    def conv_gemm(self, a_ptr, n, ih, iw, k, lda, b_ptr, nb, tb, ldb, d_ptr, oh, ow, fh, fw, ldd, taps,
+                  ostride=1, ooh=0, oow=0, istride=1, scale=None, shift=None, addend=None, ld_add=0,
+                  gate=None, ld_gate=0, scale2=None, relu=False, accumulate=False,
+                  a_lo_ptr=None, b_lo_ptr=None, n_split=1, max_ctas=0):
+        """Raw-pointer form of b2_conv_gemm (see include/b200seg.h)."""
+        taps_arr = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(-1, 3))
+        p = L.ConvParams()
+        p.a = a_ptr; p.a_lo = a_lo_ptr; p.b = b_ptr; p.b_lo = b_lo_ptr; p.d = d_ptr
+        p.n, p.ih, p.iw, p.k, p.lda = n, ih, iw, k, lda
+        p.nb, p.tb, p.ldb = nb, tb, ldb
+        p.oh, p.ow = oh, ow
+        p.fh, p.fw, p.ldd, p.ostride, p.ooh, p.oow = fh, fw, ldd, ostride, ooh, oow
+        p.istride = istride
+        p.n_taps = taps_arr.shape[0]
+        p.taps = taps_arr.ctypes.data
+        p.scale = L.ptr(scale); p.shift = L.ptr(shift)
+        p.addend = addend; p.ld_add = ld_add
+        p.gate = gate; p.ld_gate = ld_gate
+        p.scale2 = L.ptr(scale2)
+        p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate)); p.n_split = n_split
+        p.max_ctas = max_ctas
+        self._call('b2_conv_gemm', ctypes.byref(p), self._s())
+
+    def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
+                   accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None):
+        taps_arr = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(-1, 3))
+        p = L.WgradParams()
+        p.dy = dy_ptr; p.dy_lo = dy_lo_ptr; p.x = x_ptr; p.x_lo = x_lo_ptr; p.dw = dw_ptr
+        p.n, p.oh, p.ow, p.m, p.ldy = n, oh, ow, m, ldy
+        p.ih, p.iw, p.c, p.ldx = ih, iw, c, ldx
+        p.istride = istride
+        p.n_taps = taps_arr.shape[0]
+        p.taps = taps_arr.ctypes.data
+        p.tw = tw
+        p.accumulate = int(bool(accumulate)); p.n_split = n_split
+        p.max_ctas = max_ctas
+        need = L.call('b2_conv_wgrad_workspace', ctypes.byref(p))
+        ws = None
+        if need > 0:
+            ws = self._workspace(need, device)
+            p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel()
+        self._call('b2_conv_wgrad', ctypes.byref(p), self._s())
+        self.launches += 1 if need > 0 else 0
+
+    _ws = None
+
+    def _workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != torch.device(device):
+            self._ws = torch.empty((int(nbytes),), device=device, dtype=torch.uint8)
+        return self._ws
+
+
+def conv_taps(kh, kw, dil, pad):
+    """Tap table (dh, dw, weight_tap) of a forward convolution (input offset of each filter tap)."""
+    return [(r * dil - pad, s * dil - pad, r * kw + s) for r in range(kh) for s in range(kw)]
+
+
+def dgrad_taps(kh, kw, dil, pad):
+    """Tap table of the stride-1 input-gradient convolution: dX[h] += dY[h + pad - r*dil] * W[r]."""
+    return [(pad - r * dil, pad - s * dil, r * kw + s) for r in range(kh) for s in range(kw)]

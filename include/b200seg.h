@@ -1,0 +1,244 @@
+/*
+ * b200seg.h — C ABI of libb200seg.so: the sm_100a kernels behind the CutMix mean-teacher
+ * hot path (reference: train_seg_semisup_mask_mt.py:287-476).
+ *
+ * The reference has no FFI; its boundary is its Python API.  This header is the
+ * boundary a maintainer would bind with ctypes: plain pointers + sizes, no
+ * torch types.  Every entry point
+ *   - returns 0 on success, a non-zero B2_ERR_* code otherwise (message: b2_last_error()),
+ *   - takes DEVICE pointers unless the argument is documented "host",
+ *   - enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *   - never allocates or frees device memory: outputs/workspaces are caller-owned.
+ *
+ * Tensor layouts: "NCHW" = PyTorch contiguous; "NHWC" = channels-last, channel stride 1 with an
+ * explicit leading dimension `ld` (floats per pixel) so ops can write into channel slices of a
+ * wider buffer (this is how torch.cat is eliminated).
+ */
+#ifndef B200SEG_H
+#define B200SEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_INVALID 1   /* bad shape / alignment / unsupported configuration */
+#define B2_ERR_CUDA 2      /* CUDA runtime / driver error at launch or map encode */
+#define B2_ERR_UNSUPPORTED 3
+
+const char* b2_last_error(void);  /* thread-local message of the last failing call */
+int b2_version(void);             /* ABI version (monotonic) */
+int b2_num_sms(void);             /* SM count of the current device (0 if no device) */
+
+/* ------------------------------------------------------------------------------------------
+ * E1  EMA teacher update — replaces optim_weight_ema.py:21-25
+ *   t = fl(fl(t*alpha) + fl(s*one_minus_alpha))  (three fp32 roundings, no FMA: bit-exact with
+ *   `t.mul_(a); t.add_(s*(1-a))`).  Multi-tensor: `table` is a DEVICE array of n_chunks entries
+ *   {tgt ptr, src ptr, count} (struct b2_ema_chunk), one thread block per entry.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2_ema_chunk {
+  float* tgt;
+  const float* src;
+  int64_t count;
+} b2_ema_chunk;
+int b2_ema_step(const b2_ema_chunk* table, int64_t n_chunks, float alpha, float one_minus_alpha,
+                void* stream);
+/* Flat fast path: one contiguous state buffer per network. */
+int b2_ema_step_flat(float* tgt, const float* src, int64_t count, float alpha,
+                     float one_minus_alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * M1/M2  Box mask rasterisation — device half of mask_gen.py:110-117
+ *   boxes: int32 (N, n_boxes, 4) = [y0, y1, x0, x1) half-open ranges ALREADY resolved with numpy
+ *   slice semantics (host side, mask_gen.BoxMaskGenerator.generate_boxes); each rectangle XOR-
+ *   toggles the mask which starts at `init` (0 if invert else 1).  out: fp32 (N,1,H,W).
+ * ------------------------------------------------------------------------------------------ */
+int b2_box_mask_rasterize(const int32_t* boxes, int n, int n_boxes, int h, int w, float init,
+                          float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * X1  CutMix image / valid-mask mix — train_seg_semisup_mask_mt.py:350-351
+ *   out = fl(fl(a*fl(1-m)) + fl(b*m)), m broadcast over channels.  a,b,out: (N,C,H,W); m: (N,1,H,W).
+ *   b == NULL  →  "cut" mode (line 389/401): out = fl(a*m).
+ * ------------------------------------------------------------------------------------------ */
+int b2_mix(const float* a, const float* b, const float* m, float* out, int n, int c, int64_t hw,
+           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459
+ *   Inputs (NCHW fp32): l0, l1 teacher logits of the two views (l1 == NULL → cut mode, l_t = l0),
+ *   ls student logits, m mix mask (N,1,H,W) (NULL → no logit mixing), lmask per-pixel loss mask
+ *   (N,1,H,W) (um_mixed for mix mode, cut_mask*um for cut mode).
+ *   One pass: l_t = l0*(1-m)+l1*m; p_t, p_s = softmax; conf = max p_t >= conf_thresh;
+ *   q = per-pixel loss (loss_fn); writes the UNSCALED gradient g = lmask * dq/dls (times conf if
+ *   conf_per_pixel) to dls and per-block partials to `partials` (3 doubles per block).
+ *   b2_consistency_finalize (1 block, fixed order) then produces out[0..3]:
+ *     out[0] loss  (= mean(q*lmask*conf) * ramp, the value the reference logs, line 461)
+ *     out[1] conf_rate
+ *     out[2] grad_scale: true dls = g * out[2]   ( = conf/(N*H*W) * ramp * cons_weight )
+ *     out[3] unsup_loss = out[0] * cons_weight
+ *   loss_fn: 0 var, 1 logits_var, 2 logits_smoothl1, 3 bce, 4 kld.   C <= 64.
+ *   conf_thresh <= 0 disables confidence masking (line 407/419).
+ * ------------------------------------------------------------------------------------------ */
+int64_t b2_consistency_num_partials(int n, int64_t hw);
+int b2_consistency_fwd_bwd(const float* l0, const float* l1, const float* ls, const float* m,
+                           const float* lmask, float* dls, double* partials, int n, int c,
+                           int64_t hw, int loss_fn, float conf_thresh, int conf_per_pixel,
+                           void* stream);
+int b2_consistency_finalize(const double* partials, int64_t n_partials, int64_t n_pixels,
+                            float conf_thresh, int conf_per_pixel, float ramp, float cons_weight,
+                            float* out4, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L2  Per-pixel cross-entropy, ignore_index — train_seg_semisup_mask_mt.py:126,300-301
+ *   logits NCHW fp32, labels int64 (N,H,W).  Writes UNSCALED gradient (softmax - onehot)*valid to
+ *   dlogits, partials (2 doubles/block: sum nll, n_valid).  Finalize: out[0] = mean nll over valid,
+ *   out[1] = n_valid, out[2] = grad_scale = 1/n_valid.
+ * ------------------------------------------------------------------------------------------ */
+int64_t b2_ce_num_partials(int n, int64_t hw);
+int b2_ce_fwd_bwd(const float* logits, const int64_t* labels, float* dlogits, double* partials,
+                  int n, int c, int64_t hw, int64_t ignore_index, void* stream);
+int b2_ce_finalize(const double* partials, int64_t n_partials, float* out3, void* stream);
+
+/* x[i] *= scale_dev[0] * scale_host   (applies a device-resident gradient scale) */
+int b2_scale_inplace(float* x, int64_t count, const float* scale_dev, float scale_host,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A3/A4/A5  Convolution as tcgen05 implicit GEMM (fprop, dgrad, wgrad) — replaces
+ *   nn.Conv2d forward/backward in architectures/deeplab2.py:65-128,140-150 and torchvision
+ *   ResNet/ASPP + architectures/deeplab3plus.py:29-48.
+ *
+ * b2_conv_gemm:  D[pix, n] = epilogue( sum_{tap, k} A[pix@tap, k] * B[n, tap, k] )
+ *   A: NHWC activations (N, IH, IW, K) with leading dim lda;  B: (NB, T_b, K) K-contiguous
+ *   (fprop: weights KRSC; dgrad: transposed weights CRSK).  TF32 tensor-core math, fp32 accum.
+ *   Taps: table of n_taps entries (dh, dw, b_tap): input pixel for output (h,w) is
+ *   (h*istride + dh, w*istride + dw); out-of-range pixels contribute zero (TMA OOB fill).
+ *   Output pixel (n,h,w) of the OH x OW grid is stored at out[((n*FH + h*ostride+ooh)*FW +
+ *   w*ostride+oow)*ldd + n_col]  (FH x FW = full output buffer; ostride>1 = scatter for strided
+ *   dgrad).  Epilogue, in order:  v = acc*scale[n] + shift[n] (NULL = identity);
+ *   v += addend[pix, n] (ld = ld_add);  relu;  v = (gate[pix, n] > 0) ? v : 0 (ld = ld_gate);
+ *   v *= scale2[n];  if accumulate v += D_old.
+ *   n_split > 1 = 3xTF32 precision mode: a_lo/b_lo hold the low parts (see b2_split_tf32) and the
+ *   kernel accumulates A*B + A_lo*B + A*B_lo (+ A_lo*B_lo when n_split == 4).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2_conv_params {
+  const float* a; const float* a_lo;      /* activations (and low part, or NULL) */
+  const float* b; const float* b_lo;      /* weights (NB, T_b, K) */
+  float* d;                               /* output */
+  int32_t n, ih, iw, k, lda;              /* A dims: batch, in H, in W, channels K, leading dim */
+  int32_t nb, tb, ldb;                    /* B dims: NB rows (GEMM-N), T_b taps, floats per (n,tap) row (>= K, %4) */
+  int32_t oh, ow;                         /* logical output grid */
+  int32_t fh, fw, ldd, ostride, ooh, oow; /* output buffer geometry */
+  int32_t istride;
+  int32_t n_taps;
+  const int32_t* taps;                    /* HOST array, 3*n_taps: dh, dw, b_tap */
+  const float* scale; const float* shift; /* per-output-channel, or NULL */
+  const float* addend; int32_t ld_add;    /* laid out like D (same pixel mapping) */
+  const float* gate; int32_t ld_gate;
+  const float* scale2;
+  int32_t relu, accumulate, n_split;
+  int32_t max_ctas;                       /* 0 = one persistent CTA per SM */
+} b2_conv_params;
+int b2_conv_gemm(const b2_conv_params* p, void* stream);
+
+/* wgrad:  dW[m, tap, c] (+)= sum_pix dY[pix, m] * X[pix@tap, c]
+ *   dY: NHWC (N, OH, OW, M) ld = ldy;  X: NHWC (N, IH, IW, C) ld = ldx;  dW: (M, T, C) fp32.
+ *   Split over pixel ranges: `workspace` holds n_splits partial (M,T,C) slabs reduced in fixed
+ *   order by a second kernel (deterministic).  b2_conv_wgrad_workspace returns the bytes needed. */
+typedef struct b2_wgrad_params {
+  const float* dy; const float* dy_lo;
+  const float* x;  const float* x_lo;
+  float* dw;
+  int32_t n, oh, ow, m, ldy;
+  int32_t ih, iw, c, ldx;
+  int32_t istride;
+  int32_t n_taps; const int32_t* taps;    /* HOST array 3*n_taps: dh, dw, w_tap */
+  int32_t tw;                             /* taps in dW's layout */
+  int32_t accumulate, n_split;
+  void* workspace; size_t workspace_bytes;
+  int32_t max_ctas;
+} b2_wgrad_params;
+size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p);
+int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
+
+/* Debug knob (tests only): key 1 = wgrad smem-descriptor variant. */
+void b2_debug_set(int key, int value);
+
+/* hi = x with the 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact). */
+int b2_split_tf32(const float* x, float* hi, float* lo, int64_t count, void* stream);
+
+/* (A, T, B) -> (B, T, A) transpose of a weight tensor (KRSC <-> CRSK). */
+int b2_transpose_w(const float* src, float* dst, int a, int t, int b, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound network ops (NHWC fp32).
+ * ------------------------------------------------------------------------------------------ */
+int b2_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int ldd, void* stream);
+int b2_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, int lds, void* stream);
+/* im2col for the Cin=3 stem: out (N*OH*OW, kpad) rows [r][s][c], zero padded to kpad. */
+int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw,
+              int stride, int pad, int dil, int oh, int ow, int kpad, void* stream);
+/* 3x3 stride-2 pad-1 max pooling (deeplab2.py:146 ceil_mode / torchvision floor): caller passes
+ * oh, ow.  idx: uint8 argmax tap (0..8) for the backward. */
+int b2_maxpool3x3s2(const float* x, float* y, uint8_t* idx, int n, int h, int w, int c, int oh,
+                    int ow, void* stream);
+int b2_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int n, int h, int w,
+                        int c, int oh, int ow, void* stream);
+/* Bilinear resize (F.interpolate, deeplab2.py:204 align_corners=True; deeplab3plus.py:54,77
+ * align_corners=False).  NHWC -> NHWC (ldd) or NHWC -> NCHW (to_nchw).  Backward: dy layout
+ * mirrors the forward output; `scale_dev` (may be NULL) * scale_host multiplies the gradient. */
+int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int c, int ldx, int oh, int ow,
+                    int ldy, int align_corners, int to_nchw, void* stream);
+int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw, int c, int ldx, int oh,
+                    int ow, int ldy, int align_corners, int from_nchw, const float* scale_dev,
+                    float scale_host, int accumulate, void* stream);
+/* Global average pool (ASPPPooling) and its backward (broadcast /HW). */
+int b2_gap_fwd(const float* x, float* y, int n, int hw, int c, int ldx, void* stream);
+int b2_gap_bwd(const float* dy, float* dx, int n, int hw, int c, int ldx, int accumulate,
+               void* stream);
+/* Broadcast a (N, C) vector over HW pixels into an NHWC slice (bilinear from 1x1), + backward. */
+int b2_bcast_fwd(const float* v, float* y, int n, int hw, int c, int ldy, void* stream);
+int b2_bcast_bwd(const float* dy, float* dv, int n, int hw, int c, int ldy, void* stream);
+/* Train-mode batch norm over NHWC (N*H*W rows, C channels), DLv3+ head.
+ *   stats: mean[c], rstd[c] (biased var, eps), updates running stats with momentum (unbiased var).
+ *   apply: y = relu?((x-mean)*rstd*gamma+beta) * dropmask? ; y may alias a channel slice (ldy).
+ *   bwd: given dy (w.r.t. y), y-side gate (relu: y>0), computes dx, dgamma, dbeta. */
+int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float eps, float momentum,
+                float* mean, float* rstd, float* running_mean, float* running_var,
+                double* workspace, void* stream);
+int64_t b2_bn_workspace_doubles(int64_t rows, int c);
+int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const float* mean, const float* rstd,
+                const float* gamma, const float* beta, int relu, const float* dropmask,
+                float drop_scale, float* y, int ldy, void* stream);
+int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y, int ldy,
+              int64_t rows, int c, const float* mean, const float* rstd, const float* gamma,
+              int relu, const float* dropmask, float drop_scale, float* dx, int lddx,
+              float* dgamma, float* dbeta, int accumulate_params, double* workspace, void* stream);
+/* Eval-mode (frozen) BN folded constants: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale. */
+int b2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+               float eps, float* scale, float* shift, int c, void* stream);
+/* Frozen-statistics BN with trainable affine (DLv3+ backbone under freeze_batchnorm):
+ *   dbeta[c] (+)= sum g, dgamma[c] (+)= sum g*xhat, g = dy where gate > 0 (gate NULL = always),
+ *   xhat = (ybn - beta)/gamma recovered from the stored BN output `ybn`. */
+int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, int64_t rows, int c,
+                          const float* gamma, const float* beta, const float* gate, int ldg,
+                          float* dgamma, float* dbeta, int accumulate, double* workspace,
+                          void* stream);
+/* dropout mask: mask[i] = (philox(seed, offset+i) >= p) ? 1 : 0 */
+int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset,
+                    void* stream);
+/* y = relu-gated / plain elementwise helpers used by the backward pass */
+int b2_add_inplace(float* dst, const float* src, int64_t count, void* stream);
+int b2_fill(float* dst, float value, int64_t count, void* stream);
+/* per-column bias gradient: db[c] (+)= sum_rows dy[row, c] */
+int b2_colsum(const float* dy, int ld, int64_t rows, int c, float* out, int accumulate,
+              double* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H */
