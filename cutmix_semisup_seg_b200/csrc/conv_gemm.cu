@@ -274,7 +274,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, const uint32_t* elem_strides) {
+                  const uint32_t* box, const uint32_t* elem_strides, bool atom32) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return b2_fail(B2_ERR_INVALID, "tensor map base %p not 16B aligned", ptr);
@@ -283,7 +283,7 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
   for (int i = 0; i < rank; ++i)
     if (box[i] == 0 || box[i] > 256) return b2_fail(B2_ERR_INVALID, "tensor map box[%d]=%u out of range", i, box[i]);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return B2_OK;

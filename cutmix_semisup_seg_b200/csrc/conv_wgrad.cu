@@ -5,7 +5,7 @@
 //
 // GEMM view: M = output channels (tile 128), N = input channels (tile <= 256), K = pixels.
 // Both operands are "pixel-major rows of channels" in HBM (NHWC), i.e. MN-major for this GEMM, so
-// TMA boxes of (32 channels x 32 pixels) land in smem exactly as the canonical MN-major 128B-swizzle
+// TMA boxes of (32 channels x 32 pixels) land in smem exactly as the canonical MN-major 128B-swizzle (32 B atom)
 // atoms the tensor core reads; no transposes anywhere.  K is split over CTAs (pixel ranges) and the
 // partial slabs are reduced in a fixed order by a second kernel => deterministic gradients.
 #include "tc_common.cuh"
@@ -41,6 +41,7 @@ struct WgradKArgs {
   int64_t slab_elems;
   int accumulate;
   int desc_variant;
+  const float* row_scale;   // per output channel m (folded BN scale), applied before accumulation
 };
 
 struct UnitInfo {
@@ -89,7 +90,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * W_STAGES;
   uint64_t* tempty_bar = bars + 2 * W_STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 4);
-  volatile int* zero_flag = reinterpret_cast<volatile int*>(tmem_ptr + 2);  // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -120,9 +120,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         int na = (a.m - ui.m0 + 31) / 32; if (na > W_BLOCK_M / 32) na = W_BLOCK_M / 32;
         int nbk = (a.c - ui.c0 + 31) / 32; if (nbk > a.block_n / 32) nbk = a.block_n / 32;
         const uint32_t tx = (uint32_t)(na + nbk) * (uint32_t)a.kpix * 128u;
+        bool any = false;
         for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
           const PBox b = decode_pb(a, pb, ui.tap);
-          if (!b.active) continue;
+          // a unit with no contributing pixel box still runs one (all-zero X) box so that the
+          // accumulator is written
+          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
+          any = true;
           const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -144,8 +148,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, 1, 1);
-      const uint32_t lbo = a.desc_variant == 1 ? 1024u : (uint32_t)W_SLOT_BYTES;
-      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)W_SLOT_BYTES : 1024u;
+      // MN-major tf32: SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B).  LBO = stride between the
+      // 32-channel column blocks (one TMA box each), SBO = stride between 4-row groups along K.
+      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)W_SLOT_BYTES;
+      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)W_SLOT_BYTES : 512u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const int ksteps = a.kpix / 8;
@@ -155,17 +161,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
         uint32_t first = 1;
+        bool any = false;
         for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
           const PBox b = decode_pb(a, pb, ui.tap);
-          if (!b.active) continue;
+          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
+          any = true;
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&full_bar[stage], phase);
             tc::tc_fence_after();
             const uint32_t a_addr = tc::smem_u32(smem_a + stage * W_A_STAGE_BYTES);
             const uint32_t b_addr = tc::smem_u32(smem_b + stage * W_B_STAGE_BYTES);
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 1024, lbo, sbo);
-              const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 1024, lbo, sbo);
+              const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
               tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -173,15 +181,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        if (first) {              // no active pixel box: the tile is exactly zero
-          zero_flag[acc] = 1;
-          __threadfence_block();
-          tc::mbar_arrive(&tfull_bar[acc]);
-        } else {
-          zero_flag[acc] = 0;
-          __threadfence_block();
-          tc::mma_commit(&tfull_bar[acc]);
-        }
+        tc::mma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -195,9 +195,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       const int mrow = ui.m0 + row;
       const bool valid = mrow < a.m;
       float* orow = a.out + (int64_t)ui.split * a.slab_elems + ((int64_t)mrow * a.tw + a.wtap[ui.tap]) * a.c;
+      const float rs = (a.row_scale && valid) ? __ldg(a.row_scale + mrow) : 1.0f;
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
-      const bool is_zero = zero_flag[acc] != 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * W_MAX_BLOCK_N;
       const int nchunks = a.block_n / 32;
       const bool vec = (a.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
@@ -213,7 +213,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             if (c >= a.c) break;
             float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = is_zero ? 0.0f : __uint_as_float(r[j * 4 + e]);
+            for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[j * 4 + e]) * rs;
             if (vec && c + 3 < a.c) {
               float4 o = make_float4(v[0], v[1], v[2], v[3]);
               if (a.accumulate) {
@@ -319,6 +319,7 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   a.slab_elems = (int64_t)p->m * p->tw * p->c;
   a.accumulate = p->accumulate;
   a.desc_variant = g_wgrad_desc_variant;
+  a.row_scale = p->row_scale;
   *out = a;
   return B2_OK;
 }
@@ -356,16 +357,16 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     const uint64_t strides[3] = {(uint64_t)p->ldy * 4, (uint64_t)p->ow * p->ldy * 4, (uint64_t)p->oh * p->ow * p->ldy * 4};
     const uint32_t box[4] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
     const uint32_t es[4] = {1, 1, 1, 1};
-    rc = tc::make_tmap_f32(&tmY, p->dy, 4, dims, strides, box, es); if (rc) return rc;
-    rc = tc::make_tmap_f32(&tmYlo, p->dy_lo ? p->dy_lo : p->dy, 4, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmY, p->dy, 4, dims, strides, box, es, true); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmYlo, p->dy_lo ? p->dy_lo : p->dy, 4, dims, strides, box, es, true); if (rc) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)p->c, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
     const uint64_t strides[3] = {(uint64_t)p->ldx * 4, (uint64_t)p->iw * p->ldx * 4, (uint64_t)p->ih * p->iw * p->ldx * 4};
     const uint32_t box[4] = {32, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn};
     const uint32_t es[4] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1};
-    rc = tc::make_tmap_f32(&tmX, p->x, 4, dims, strides, box, es); if (rc) return rc;
-    rc = tc::make_tmap_f32(&tmXlo, p->x_lo ? p->x_lo : p->x, 4, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmX, p->x, 4, dims, strides, box, es, true); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmXlo, p->x_lo ? p->x_lo : p->x, 4, dims, strides, box, es, true); if (rc) return rc;
   }
 
   static bool attr_set = false;

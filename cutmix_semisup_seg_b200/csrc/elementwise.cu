@@ -256,25 +256,26 @@ extern "C" int b2_split_tf32(const float* x, float* hi, float* lo, int64_t count
 }
 
 // (A, T, B) -> (B, T, A): 32x32 smem tile transpose per tap.
-__global__ void transpose_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int T, int B) {
+__global__ void transpose_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int T, int B, int ldd,
+                                   const float* __restrict__ scale_a) {
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int a = a0 + i, b = b0 + threadIdx.x;
-    tile[i][threadIdx.x] = (a < A && b < B) ? src[((int64_t)a * T + t) * B + b] : 0.0f;
+    tile[i][threadIdx.x] = (a < A && b < B) ? src[((int64_t)a * T + t) * B + b] * (scale_a ? scale_a[a] : 1.0f) : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int b = b0 + i, a = a0 + threadIdx.x;
-    if (a < A && b < B) dst[((int64_t)b * T + t) * A + a] = tile[threadIdx.x][i];
+    if (a < ldd && b < B) dst[((int64_t)b * T + t) * ldd + a] = a < A ? tile[threadIdx.x][i] : 0.0f;
   }
 }
-extern "C" int b2_transpose_w(const float* src, float* dst, int a, int t, int b, void* stream) {
-  B2_REQUIRE(src && dst && a > 0 && t > 0 && b > 0, "b2_transpose_w: bad args");
-  dim3 grid((b + 31) / 32, (a + 31) / 32, t), block(32, 8);
+extern "C" int b2_transpose_w(const float* src, float* dst, int a, int t, int b, int ldd, const float* scale_a, void* stream) {
+  B2_REQUIRE(src && dst && a > 0 && t > 0 && b > 0 && ldd >= a, "b2_transpose_w: bad args");
+  dim3 grid((b + 31) / 32, (ldd + 31) / 32, t), block(32, 8);
   B2_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "b2_transpose_w: too large");
-  transpose_w_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, a, t, b);
+  transpose_w_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, a, t, b, ldd, scale_a);
   B2_LAUNCH_CHECK("transpose_w_kernel");
   return B2_OK;
 }
@@ -301,5 +302,38 @@ extern "C" int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t see
   if (blocks > 148 * 16) blocks = 148 * 16;
   dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, count, p, seed, offset);
   B2_LAUNCH_CHECK("dropout_mask_kernel");
+  return B2_OK;
+}
+
+// g[row, c] = (y[row, c] > 0) ? g[row, c] : 0   (explicit ReLU backward where it cannot be fused)
+__global__ void relu_gate_kernel(float* __restrict__ g, int ldg, const float* __restrict__ y, int ldy, int64_t rows, int c) {
+  const int64_t total = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); const int64_t row = i / c;
+    if (!(y[row * ldy + ch] > 0.0f)) g[row * ldg + ch] = 0.0f;
+  }
+}
+extern "C" int b2_relu_gate(float* g, int ldg, const float* y, int ldy, int64_t rows, int c, void* stream) {
+  B2_REQUIRE(g && y && rows > 0 && c > 0 && ldg >= c && ldy >= c, "b2_relu_gate: bad args");
+  int64_t blocks = ceil_div64(rows * c, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  relu_gate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
+  B2_LAUNCH_CHECK("relu_gate_kernel");
+  return B2_OK;
+}
+// strided copy / add of an NHWC slice: dst[row, c] (+)= src[row, c]
+__global__ void slice_copy_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int64_t rows, int c, int accumulate) {
+  const int64_t total = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c); const int64_t row = i / c;
+    const float v = src[row * lds + ch];
+    float* d = dst + row * ldd + ch;
+    *d = accumulate ? *d + v : v;
+  }
+}
+extern "C" int b2_slice_copy(float* dst, int ldd, const float* src, int lds, int64_t rows, int c, int accumulate, void* stream) {
+  B2_REQUIRE(dst && src && rows > 0 && c > 0 && ldd >= c && lds >= c, "b2_slice_copy: bad args");
+  int64_t blocks = ceil_div64(rows * c, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  slice_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
+  B2_LAUNCH_CHECK("slice_copy_kernel");
   return B2_OK;
 }

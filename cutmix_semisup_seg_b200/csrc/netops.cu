@@ -285,6 +285,7 @@ struct RedArgs {
   const float* gate; int ldg;   // relu gate tensor (y > 0) or NULL
   const float* drop; float drop_scale;  // dropout mask laid out like dy (ld = lda) or NULL
   const float* mean; const float* rstd;
+  const float* sub; int lds;    // mode 3: o = b - sub (residual removed from the block output)
   int64_t rows; int c;
 };
 template <int MODE>
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
       else {
         if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
         if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
-        const float bv = __ldg(r.b + row * r.ldb + ch);
+        float bv = __ldg(r.b + row * r.ldb + ch);
+        if (MODE == 3 && r.sub) bv -= __ldg(r.sub + row * r.lds + ch);
         const float o = MODE == 2 ? (bv - mean) * rstd : bv;
         s0 += v; s1 += (double)v * (double)o;
       }
@@ -389,22 +391,25 @@ extern "C" int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float e
 
 __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t rows, int c, int ldx, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int relu, const float* __restrict__ drop, float drop_scale, float* __restrict__ y, int ldy) {
+                                int relu, const float* __restrict__ drop, float drop_scale, float* __restrict__ y, int ldy,
+                                const float* __restrict__ res, int ldr) {
   const int64_t total = rows * c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c); const int64_t row = i / c;
     float v = (x[row * ldx + ch] - mean[ch]) * rstd[ch] * gamma[ch] + beta[ch];
+    if (res) v += res[row * ldr + ch];
     if (relu) v = fmaxf(v, 0.f);
     if (drop) v *= drop[row * c + ch] * drop_scale;
     y[row * ldy + ch] = v;
   }
 }
 extern "C" int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const float* mean, const float* rstd, const float* gamma,
-                           const float* beta, int relu, const float* dropmask, float drop_scale, float* y, int ldy, void* stream) {
+                           const float* beta, int relu, const float* dropmask, float drop_scale, float* y, int ldy,
+                           const float* residual, int ldr, void* stream) {
   B2_REQUIRE(x && y && mean && rstd && gamma && beta && rows > 0 && c > 0, "b2_bn_apply: bad args");
   const int64_t total = rows * c;
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy);
+  bn_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy, residual, ldr);
   B2_LAUNCH_CHECK("bn_apply_kernel");
   return B2_OK;
 }
@@ -412,7 +417,7 @@ extern "C" int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const f
 __global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, const float* __restrict__ y,
                                  int ldy, int64_t rows, int c, const float* __restrict__ mean, const float* __restrict__ rstd,
                                  const float* __restrict__ gamma, int relu, const float* __restrict__ drop, float drop_scale,
-                                 const double* __restrict__ fin, float* __restrict__ dx, int lddx) {
+                                 const double* __restrict__ fin, float* __restrict__ dx, int lddx, float* __restrict__ g_out, int ldgo) {
   const int64_t total = rows * c;
   const double inv_n = 1.0 / (double)rows;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -420,6 +425,7 @@ __global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, int lddy, const f
     float g = dy[row * lddy + ch];
     if (relu && !(y[row * ldy + ch] > 0.f)) g = 0.f;
     if (drop) g *= drop[row * c + ch] * drop_scale;
+    if (g_out) g_out[row * ldgo + ch] = g;
     const float xhat = (x[row * ldx + ch] - mean[ch]) * rstd[ch];
     const float mdb = (float)(fin[ch * 2] * inv_n), mdg = (float)(fin[ch * 2 + 1] * inv_n);
     dx[row * lddx + ch] = gamma[ch] * rstd[ch] * (g - mdb - xhat * mdg);
@@ -433,7 +439,8 @@ __global__ void bn_param_out_kernel(const double* __restrict__ fin, int c, float
 }
 extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y, int ldy, int64_t rows, int c,
                          const float* mean, const float* rstd, const float* gamma, int relu, const float* dropmask, float drop_scale,
-                         float* dx, int lddx, float* dgamma, float* dbeta, int accumulate_params, double* workspace, void* stream) {
+                         float* dx, int lddx, float* dgamma, float* dbeta, int accumulate_params, float* g_out, int ldgo,
+                         double* workspace, void* stream) {
   B2_REQUIRE(dy && x && dx && mean && rstd && gamma && workspace && rows > 0 && c > 0, "b2_bn_bwd: bad args");
   B2_REQUIRE(!relu || y, "b2_bn_bwd: relu gate needs y");
   B2_REQUIRE(!dropmask || lddy == c, "b2_bn_bwd: dropout mask requires dense dy");
@@ -445,7 +452,7 @@ extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, con
   col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
   const int64_t total = rows * c;
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  bn_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx);
+  bn_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
   bn_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, dgamma, dbeta, accumulate_params);
   B2_LAUNCH_CHECK("bn_bwd");
   return B2_OK;
@@ -482,10 +489,10 @@ __global__ void bn_eval_param_out_kernel(const double* __restrict__ fin, int c, 
   dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)dg;
 }
 extern "C" int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, int64_t rows, int c, const float* gamma,
-                                     const float* beta, const float* gate, int ldg, float* dgamma, float* dbeta, int accumulate,
-                                     double* workspace, void* stream) {
+                                     const float* beta, const float* gate, int ldg, const float* sub, int lds, float* dgamma,
+                                     float* dbeta, int accumulate, double* workspace, void* stream) {
   B2_REQUIRE(dy && ybn && gamma && beta && dgamma && dbeta && workspace && rows > 0 && c > 0, "b2_bn_eval_param_grad: bad args");
-  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = ybn; r.ldb = ldy; r.gate = gate; r.ldg = ldg; r.rows = rows; r.c = c;
+  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = ybn; r.ldb = ldy; r.gate = gate; r.ldg = ldg; r.sub = sub; r.lds = lds; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<3>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows) * c * 2;

@@ -107,6 +107,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, u
 
 // Shared-memory matrix descriptor (PTX ISA "Matrix descriptor"): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version 1 at bit 46, swizzle mode [61,64) (2 = 128B).
+// layout_type: 2 = SWIZZLE_128B (16 B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32 B atoms: the only
+// swizzled layout the tensor core accepts for MN-major tf32 operands; TMA side = SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -126,6 +137,6 @@ PFN_encodeTiled get_encode_tiled();
 
 // fp32 tensor, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides_bytes has rank-1 entries.
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, const uint32_t* elem_strides);
+                  const uint32_t* box, const uint32_t* elem_strides, bool atom32 = false);
 
 }  // namespace tc

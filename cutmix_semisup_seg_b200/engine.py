@@ -1,0 +1,446 @@
+"""Define-by-run executor for the DeepLab forward/backward passes on the B200 kernels.
+
+The reference relies on torch.autograd over ~2000 ATen launches per iteration
+(train_seg_semisup_mask_mt.py:299-301, 355-358, 459).  Here each network layer is one fused kernel
+(conv + folded frozen-BN + residual + ReLU in the GEMM epilogue) and the backward pass is an
+explicit tape: every node knows its own gradient kernels, and ReLU / residual / BN-scale backward
+steps are folded into the producing dgrad epilogue, the transposed-weight pass or the wgrad
+epilogue instead of being separate HBM passes.
+
+Gradient bookkeeping
+  * `Act.pending` counts consumers that still owe a contribution to `Act.grad`.
+  * A convolution input-gradient that is the LAST contribution to an activation adds the partial
+    sum (`addend`) and applies the producer's ReLU gate in its epilogue (g-form gradient).
+  * Residual branches contribute by aliasing (no copy, no add kernel).
+"""
+import torch
+
+from .acts import Act
+
+
+class Tape(object):
+    def __init__(self, kernels, enabled):
+        self.K = kernels
+        self.enabled = enabled
+        self.nodes = []
+
+    def record(self, node, inputs):
+        if not self.enabled:
+            return
+        for a in inputs:
+            root = a
+            while root.parent is not None:
+                root = root.parent
+            root.pending += 1
+        self.nodes.append(node)
+
+    # ---------------------------------------------------------------- gradient accumulation
+    def _finish(self, t, fused_gate):
+        if t.pending == 0 and t.gate_on_grad and not fused_gate and t.grad is not None:
+            if not t.grad_owned:
+                owned = t.like()
+                self.K.copy_act(owned, t.grad)
+                t.grad, t.grad_owned = owned, True
+            self.K.relu_gate(t.grad, t)
+
+    def contribute_kernel(self, t, launch, fusable):
+        """launch(dst, accumulate, addend, gate) writes one consumer's contribution to d/d(t)."""
+        assert t.parent is None, 'gradients are accumulated on root activations'
+        t.pending -= 1
+        last = t.pending == 0
+        fused_gate = False
+        if fusable:
+            gate = t if (last and t.gate_on_grad) else None
+            fused_gate = gate is not None
+            if t.grad is None:
+                dst = t.like()
+                launch(dst, False, None, gate)
+            elif t.grad_owned and not last:
+                dst = t.grad
+                launch(dst, True, None, None)
+            elif t.grad_owned:
+                dst = t.grad
+                launch(dst, False, dst, gate)          # epilogue reads the partial before overwriting it
+            else:
+                dst = t.like()
+                launch(dst, False, t.grad, gate)
+            t.grad, t.grad_owned = dst, True
+        else:
+            if t.grad is None:
+                dst = t.like()
+                launch(dst, False, None, None)
+                t.grad, t.grad_owned = dst, True
+            else:
+                if not t.grad_owned:
+                    owned = t.like()
+                    self.K.copy_act(owned, t.grad)
+                    t.grad, t.grad_owned = owned, True
+                launch(t.grad, True, None, None)
+        self._finish(t, fused_gate)
+
+    def contribute_tensor(self, t, g):
+        """d/d(t) += g where g is an existing read-only gradient buffer (residual pass-through)."""
+        assert t.parent is None
+        t.pending -= 1
+        if t.grad is None:
+            t.grad, t.grad_owned = g, False
+        elif t.grad_owned:
+            self.K.copy_act(t.grad, g, accumulate=True)
+        else:
+            owned = t.like()
+            self.K.copy_act(owned, t.grad)
+            self.K.copy_act(owned, g, accumulate=True)
+            t.grad, t.grad_owned = owned, True
+        self._finish(t, False)
+
+    def skip(self, t):
+        root = t
+        while root.parent is not None:
+            root = root.parent
+        root.pending -= 1
+        self._finish(root, False)
+
+    def backward(self):
+        for node in reversed(self.nodes):
+            node.backward(self)
+        self.nodes = []
+
+
+def out_grad(act):
+    """Gradient buffer of an activation (a view into the parent's gradient for slices)."""
+    if act.parent is None:
+        return act.grad
+    root, off = act, 0
+    while root.parent is not None:
+        off += root.off - root.parent.off
+        root = root.parent
+    if root.grad is None:
+        return None
+    g = root.grad.slice(off, act.c)
+    return g
+
+
+def param_grad(p):
+    """(grad tensor laid out like p, accumulate?)  Creates p.grad on first use."""
+    if p.grad is None:
+        p.grad = torch.empty_like(p)
+        return p.grad, False
+    return p.grad, True
+
+
+# ====================================================================================== nodes
+class ConvNode(object):
+    """y = [relu]( conv(x, W) * scale + shift [+ residual] ); scale/shift = folded eval-mode BN or bias."""
+
+    def __init__(self, x, y, conv, bn, residual, relu, scale, geom, col_src=None):
+        self.x, self.y, self.conv, self.bn, self.residual, self.relu, self.scale = x, y, conv, bn, residual, relu, scale
+        self.geom = geom          # (cout, kh, kw, cin, stride, pad, dil)
+        self.col_src = col_src    # stem: (x_nhwc Act, im2col args) to rebuild the column matrix
+
+    def backward(self, tape):
+        K = tape.K
+        cout, kh, kw, cin, stride, pad, dil = self.geom
+        g = out_grad(self.y)
+        if g is None:
+            if self.residual is not None:
+                tape.skip(self.residual)
+            if self.col_src is None:
+                tape.skip(self.x)
+            return
+        if self.y.parent is not None and self.relu:
+            K.relu_gate(g, self.y)                 # slice outputs are gated here (parents carry plain sums)
+        if self.residual is not None:
+            tape.contribute_tensor(self.residual, g)
+        bn = self.bn
+        if bn is not None and bn.weight.requires_grad:
+            dgam, acc = param_grad(bn.weight)
+            dbet, acc2 = param_grad(bn.bias)
+            assert acc == acc2
+            K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, self.residual, dgam, dbet, acc)
+        if self.conv.bias is not None and self.conv.bias.requires_grad:
+            db, acc = param_grad(self.conv.bias)
+            K.colsum(g, db, acc)
+        w = self.conv.weight
+        if self.col_src is not None:
+            # stem: GEMM over the (recomputed) im2col matrix; weight gradient only
+            if w.requires_grad:
+                x_nhwc, (oh, ow, kpad) = self.col_src
+                col = K.im2col(x_nhwc, kh, kw, stride, pad, dil, oh, ow, kpad)
+                dw_pad = K.empty((cout, 1, kpad), g.device)
+                gflat = Act(g.base, 1, 1, g.rows, g.c, g.ld, g.off)
+                K.conv_wgrad(gflat, col, dw_pad, cout, 1, 1, kpad, 1, 0, 1, row_scale=self.scale, accumulate=False)
+                dw, acc = param_grad(w)
+                K.be.slice_copy(dw.data_ptr(), kh * kw * cin, dw_pad.data_ptr(), kpad, cout, kh * kw * cin, acc)
+            return
+        if w.requires_grad:
+            dw, acc = param_grad(w)
+            K.conv_wgrad(g, self.x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=self.scale, accumulate=acc)
+        root = self.x
+        if root.node is None and root.parent is None:
+            return                                   # network input: no gradient needed
+        wt, ldb = K.transpose_w(w, cout, kh * kw, cin, scale=self.scale)
+
+        def launch(dst, accumulate, addend, gate):
+            K.conv_dgrad(g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dst, addend=addend, gate=gate,
+                         accumulate=accumulate)
+        tape.contribute_kernel(self.x, launch, fusable=(stride == 1))
+
+
+class BNTrainNode(object):
+    """y = dropout( relu( bn_train(raw) [+ residual] ) )"""
+
+    def __init__(self, raw, y, bn, mean, rstd, residual, relu, dropmask, drop_scale):
+        self.raw, self.y, self.bn, self.mean, self.rstd = raw, y, bn, mean, rstd
+        self.residual, self.relu, self.dropmask, self.drop_scale = residual, relu, dropmask, drop_scale
+
+    def backward(self, tape):
+        K = tape.K
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.raw)
+            if self.residual is not None:
+                tape.skip(self.residual)
+            return
+        bn = self.bn
+        dx = self.raw.like()
+        g_out = self.y.like() if self.residual is not None else None
+        if bn.weight.requires_grad:
+            dgam, acc = param_grad(bn.weight)
+            dbet, _ = param_grad(bn.bias)
+        else:
+            dgam = dbet = None
+            acc = False
+        dyd = dy
+        if self.dropmask is not None and dy.ld != dy.c:
+            dyd = dy.like()
+            K.copy_act(dyd, dy)
+        K.bn_bwd(dyd, self.raw, self.y, self.mean, self.rstd, bn.weight, self.relu, self.dropmask, self.drop_scale, dx,
+                 dgam, dbet, acc, g_out=g_out)
+        tape.contribute_tensor(self.raw, dx)
+        if self.residual is not None:
+            tape.contribute_tensor(self.residual, g_out)
+
+
+class MaxPoolNode(object):
+    def __init__(self, x, y, idx):
+        self.x, self.y, self.idx = x, y, idx
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        tmp = self.x.like()
+        tape.K.maxpool_bwd(dy, self.idx, tmp)
+        tape.contribute_tensor(self.x, tmp)
+
+
+class BilinearNode(object):
+    def __init__(self, x, y, align_corners):
+        self.x, self.y, self.align = x, y, align_corners
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        K, align = tape.K, self.align
+        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate: K.bilinear_bwd(dy, dst, align, accumulate=acc), False)
+
+
+class GapNode(object):
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        K = tape.K
+        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate: K.gap_bwd(dy, dst, accumulate=acc), False)
+
+
+class BcastNode(object):
+    def __init__(self, v, y):
+        self.v, self.y = v, y
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.v)
+            return
+        dv = self.v.like()
+        tape.K.bcast_bwd(dy, dv)
+        tape.contribute_tensor(self.v, dv)
+
+
+# ====================================================================================== forward ops
+def _conv_out_hw(h, w, k, stride, pad, dil):
+    return ((h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1)
+
+
+def _geom(conv):
+    cout, cin, kh, kw = conv.weight.shape
+    return cout, kh, kw, cin, conv.stride, conv.padding, conv.dilation
+
+
+def fold_bn(tape, bn):
+    """scale/shift of an eval-mode BatchNorm (running statistics)."""
+    dev = bn.weight.device
+    scale = torch.empty_like(bn.running_mean)
+    shift = torch.empty_like(bn.running_mean)
+    tape.K.bn_fold(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
+    return scale, shift
+
+
+def conv_bn_act(tape, x, conv, bn=None, residual=None, relu=False, out=None, dropout=None, ld_out=None):
+    """conv -> (BatchNorm) -> (+residual) -> (ReLU) -> (Dropout), dispatching on the BN module's mode:
+    eval-mode BN (frozen) is folded into the GEMM epilogue, train-mode BN runs statistics + apply."""
+    K = tape.K
+    cout, kh, kw, cin, stride, pad, dil = _geom(conv)
+    assert x.c == cin, 'channel mismatch: {} vs {}'.format(x.c, cin)
+    oh, ow = _conv_out_hw(x.h, x.w, kh, stride, pad, dil)
+    w = conv.weight
+    bias = conv.bias
+    train_bn = bn is not None and bn.training
+    if not train_bn:
+        y = out if out is not None else Act.alloc(x.n, oh, ow, cout, x.device, ld=ld_out)
+        scale = shift = None
+        if bn is not None:
+            scale, shift = fold_bn(tape, bn)
+            assert bias is None
+        elif bias is not None:
+            shift = bias
+        K.conv_fwd(x, w, cout, kh, kw, cin, cin, stride, pad, dil, y, scale=scale, shift=shift, addend=residual, relu=relu)
+        y.gate_on_grad = bool(relu) and y.parent is None
+        node = ConvNode(x, y, conv, bn, residual, relu, scale, (cout, kh, kw, cin, stride, pad, dil))
+        y.node = node
+        tape.record(node, [x] + ([residual] if residual is not None else []))
+        assert dropout is None or not dropout.training, 'dropout after a frozen BN is not used by the reference nets'
+        return y
+    # train-mode BN: raw conv output -> batch statistics -> normalise (+residual, relu, dropout)
+    raw = Act.alloc(x.n, oh, ow, cout, x.device)
+    K.conv_fwd(x, w, cout, kh, kw, cin, cin, stride, pad, dil, raw, shift=bias)
+    cnode = ConvNode(x, raw, conv, None, None, False, None, (cout, kh, kw, cin, stride, pad, dil))
+    raw.node = cnode
+    tape.record(cnode, [x])
+    return bn_train(tape, raw, bn, residual=residual, relu=relu, out=out, dropout=dropout, ld_out=ld_out)
+
+
+def bn_train(tape, raw, bn, residual=None, relu=False, out=None, dropout=None, ld_out=None):
+    K = tape.K
+    mean = torch.empty_like(bn.running_mean)
+    rstd = torch.empty_like(bn.running_mean)
+    momentum = bn.momentum if bn.momentum is not None else 0.1
+    K.bn_stats(raw, bn.eps, momentum, mean, rstd, bn.running_mean, bn.running_var)
+    bn.num_batches_tracked += 1
+    y = out if out is not None else Act.alloc(raw.n, raw.h, raw.w, raw.c, raw.device, ld=ld_out)
+    dropmask, drop_scale = None, 1.0
+    if dropout is not None and dropout.training and dropout.p > 0:
+        dropmask = dropout.next_mask(K, raw.n, raw.h, raw.w, raw.c, raw.device)
+        drop_scale = 1.0 / (1.0 - dropout.p)
+    K.bn_apply(raw, mean, rstd, bn.weight, bn.bias, relu, dropmask, drop_scale, y, residual=residual)
+    node = BNTrainNode(raw, y, bn, mean, rstd, residual, relu, dropmask, drop_scale)
+    y.node = node
+    tape.record(node, [raw] + ([residual] if residual is not None else []))
+    return y
+
+
+def stem_conv(tape, x_nhwc, conv, bn):
+    """Cin=3 7x7/s2 stem: explicit im2col (K = 147 padded to 160) + the same tensor-core GEMM."""
+    K = tape.K
+    cout, kh, kw, cin, stride, pad, dil = _geom(conv)
+    oh, ow = _conv_out_hw(x_nhwc.h, x_nhwc.w, kh, stride, pad, dil)
+    kreal = kh * kw * cin
+    kpad = (kreal + 31) // 32 * 32
+    col = K.im2col(x_nhwc, kh, kw, stride, pad, dil, oh, ow, kpad)
+    wpad = torch.zeros((cout, 1, kpad), device=x_nhwc.device, dtype=torch.float32)
+    K.be.slice_copy(wpad.data_ptr(), kpad, conv.weight.data_ptr(), kreal, cout, kreal, False)
+    train_bn = bn.training
+    tgt = Act.alloc(x_nhwc.n, oh, ow, cout, x_nhwc.device)
+    flat = Act(tgt.base, 1, 1, tgt.rows, cout, cout, 0)
+    if not train_bn:
+        scale, shift = fold_bn(tape, bn)
+        K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat, scale=scale, shift=shift, relu=True)
+        tgt.gate_on_grad = True
+        node = ConvNode(col, tgt, conv, bn, None, True, scale, (cout, kh, kw, cin, stride, pad, dil),
+                        col_src=(x_nhwc, (oh, ow, kpad)))
+        tgt.node = node
+        tape.record(node, [])
+        return tgt
+    K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat)
+    cnode = ConvNode(col, tgt, conv, None, None, False, None, (cout, kh, kw, cin, stride, pad, dil),
+                     col_src=(x_nhwc, (oh, ow, kpad)))
+    tgt.node = cnode
+    tape.record(cnode, [])
+    return bn_train(tape, tgt, bn, relu=True)
+
+
+def maxpool3x3s2(tape, x, ceil_mode):
+    K = tape.K
+    if ceil_mode:
+        oh, ow = -(-(x.h + 2 - 3) // 2) + 1, -(-(x.w + 2 - 3) // 2) + 1
+        if (oh - 1) * 2 >= x.h + 1:     # PyTorch: the last window must start inside the input or left padding
+            oh -= 1
+        if (ow - 1) * 2 >= x.w + 1:
+            ow -= 1
+    else:
+        oh, ow = (x.h + 2 - 3) // 2 + 1, (x.w + 2 - 3) // 2 + 1
+    y = Act.alloc(x.n, oh, ow, x.c, x.device)
+    idx = torch.empty((x.n, oh, ow, x.c), device=x.device, dtype=torch.uint8)
+    xin = x
+    if x.ld != x.c:
+        xin = x.like()
+        K.copy_act(xin, x)
+    K.maxpool_fwd(xin, y, idx)
+    node = MaxPoolNode(x, y, idx)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def bilinear(tape, x, oh, ow, align_corners, out=None):
+    y = out if out is not None else Act.alloc(x.n, oh, ow, x.c, x.device)
+    tape.K.bilinear_fwd(x, y, align_corners)
+    node = BilinearNode(x, y, align_corners)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def global_avg_pool(tape, x):
+    y = Act.alloc(x.n, 1, 1, x.c, x.device)
+    tape.K.gap_fwd(x, y)
+    node = GapNode(x, y)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def broadcast(tape, v, out):
+    tape.K.bcast_fwd(v, out)
+    node = BcastNode(v, out)
+    out.node = node
+    tape.record(node, [v])
+    return out
+
+
+def to_logits_nchw(tape, x, out_h, out_w, align_corners):
+    """Final bilinear resize to the input resolution, written as an NCHW tensor (the reference's
+    output layout).  Returns (logits, backward_entry)."""
+    logits = torch.empty((x.n, x.c, out_h, out_w), device=x.device, dtype=torch.float32)
+    tape.K.bilinear_fwd_nchw(x, logits, align_corners)
+    if tape.enabled:
+        root = x
+        while root.parent is not None:
+            root = root.parent
+        root.pending += 1
+    return logits
+
+
+def seed_output_grad(tape, x, dlogits, align_corners, scale_dev=None, scale_host=1.0):
+    """Start of the backward pass: d(loss)/d(low-res logits) from d(loss)/d(logits) (NCHW)."""
+    K = tape.K
+    tape.contribute_kernel(x, lambda dst, acc, addend, gate: K.bilinear_bwd_nchw(
+        dlogits, dst, align_corners, scale_dev=scale_dev, scale_host=scale_host, accumulate=acc), False)

@@ -1,0 +1,242 @@
+"""Activation-level kernel interface used by the engine.
+
+`ActKernels` maps operations on `Act` views (NHWC, leading dimension + channel offset) onto the
+C-ABI launches of `ops.CudaBackend`.  It owns the launch-shape decisions that are not arithmetic:
+flattening 1x1 stride-1 convolutions into plain GEMMs, decomposing strided input-gradients into
+stride-1 phases, and the 3xTF32 precision mode (operand splitting).  There is no other
+implementation in the product; tests/_emu_kernels.py mirrors this interface with torch CPU math
+only to unit-test the engine's graph/backward logic without a GPU.
+"""
+import torch
+
+from .acts import Act
+from . import ops as O
+
+
+def _pad4(v):
+    return (v + 3) // 4 * 4
+
+
+class ActKernels(object):
+    name = 'cuda'
+
+    def __init__(self, backend=None, n_split=1):
+        self.be = backend if backend is not None else O.default_backend()
+        self.n_split = n_split          # 1: single-pass TF32 (throughput); 3: 3xTF32 (parity mode)
+
+    # ------------------------------------------------------------------------------ helpers
+    def _split(self, ptr_tensor_like):
+        raise NotImplementedError
+
+    def _split_act(self, a):
+        """Dense hi/lo copies of an Act (parity mode only)."""
+        hi = Act.alloc(a.n, a.h, a.w, a.c, a.device, ld=_pad4(a.c))
+        lo = Act.alloc(a.n, a.h, a.w, a.c, a.device, ld=_pad4(a.c))
+        if a.ld == hi.ld and a.off == 0 and a.c == a.ld:
+            h, l = self.be.split_tf32(a.base)
+            return Act(h, a.n, a.h, a.w, a.c, a.ld), Act(l, a.n, a.h, a.w, a.c, a.ld)
+        tmp = Act.alloc(a.n, a.h, a.w, a.c, a.device, ld=_pad4(a.c))
+        if tmp.ld != a.c:
+            self.be.fill(tmp.base, 0.0)
+        self.be.slice_copy(tmp.ptr, tmp.ld, a.ptr, a.ld, a.rows, a.c)
+        h, l = self.be.split_tf32(tmp.base)
+        return Act(h, a.n, a.h, a.w, a.c, tmp.ld), Act(l, a.n, a.h, a.w, a.c, tmp.ld)
+
+    def _split_w(self, w):
+        return self.be.split_tf32(w)
+
+    @staticmethod
+    def _linear(*acts):
+        """True if every Act can be addressed as one long row of pixels (always for NHWC + ld)."""
+        return True
+
+    # ------------------------------------------------------------------------------ convolution
+    def conv_fwd(self, x, w, cout, kh, kw, cin, ldb, stride, pad, dil, out, scale=None, shift=None, addend=None,
+                 gate=None, relu=False):
+        """out = epilogue(conv(x, w)).  w: tensor whose storage is (cout, kh*kw, ldb)."""
+        be = self.be
+        a_lo = b_lo = None
+        xa, wb = x, w
+        if self.n_split > 1:
+            xa, xlo = self._split_act(x)
+            wb, wlo = self._split_w(w)
+            a_lo, b_lo = xlo.ptr, wlo.data_ptr()
+        kwargs = dict(scale=scale, shift=shift, relu=relu, a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
+        if addend is not None:
+            kwargs['addend'] = addend.ptr; kwargs['ld_add'] = addend.ld
+        if gate is not None:
+            kwargs['gate'] = gate.ptr; kwargs['ld_gate'] = gate.ld
+        taps = O.conv_taps(kh, kw, dil, pad)
+        if kh == 1 and kw == 1 and stride == 1 and pad == 0:
+            npix = x.rows
+            be.conv_gemm(xa.ptr, 1, 1, npix, cin, xa.ld, wb.data_ptr(), cout, 1, ldb, out.ptr, 1, npix, 1, npix, out.ld,
+                         taps, **kwargs)
+        else:
+            be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
+                         out.h, out.w, out.ld, taps, istride=stride, **kwargs)
+
+    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False):
+        """dx (+)= dgrad(g, W).  wt: transposed weights, storage (cin, kh*kw, ldb) with K = cout.
+        Stride-1 convolutions fuse `addend` (partial gradient) and `gate` (ReLU of the producer);
+        strided ones are decomposed into stride-1 phases scattered with output stride (no fusion)."""
+        be = self.be
+        a_lo = b_lo = None
+        ga, wb = g, wt
+        if self.n_split > 1:
+            ga, glo = self._split_act(g)
+            wb, wlo = self._split_w(wt)
+            a_lo, b_lo = glo.ptr, wlo.data_ptr()
+        common = dict(a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
+        if stride == 1:
+            kwargs = dict(common, accumulate=accumulate)
+            if addend is not None:
+                kwargs['addend'] = addend.ptr; kwargs['ld_add'] = addend.ld
+            if gate is not None:
+                kwargs['gate'] = gate.ptr; kwargs['ld_gate'] = gate.ld
+            taps = O.dgrad_taps(kh, kw, dil, pad)
+            if kh == 1 and kw == 1 and pad == 0:
+                npix = g.rows
+                be.conv_gemm(ga.ptr, 1, 1, npix, cout, ga.ld, wb.data_ptr(), cin, 1, ldb, dx.ptr, 1, npix, 1, npix, dx.ld,
+                             taps, **kwargs)
+            else:
+                be.conv_gemm(ga.ptr, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), cin, kh * kw, ldb, dx.ptr, dx.h, dx.w,
+                             dx.h, dx.w, dx.ld, taps, **kwargs)
+            return
+        assert addend is None and gate is None, 'strided dgrad is not fused'
+        if not accumulate:
+            self.fill_act(dx, 0.0)
+        s = stride
+        for a in range(s):
+            for b in range(s):
+                taps = []
+                for r in range(kh):
+                    if (a + pad - r * dil) % s:
+                        continue
+                    for q in range(kw):
+                        if (b + pad - q * dil) % s:
+                            continue
+                        taps.append(((a + pad - r * dil) // s, (b + pad - q * dil) // s, r * kw + q))
+                ph, pw = (dx.h - a + s - 1) // s, (dx.w - b + s - 1) // s
+                if not taps or ph <= 0 or pw <= 0:
+                    continue
+                be.conv_gemm(ga.ptr, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), cin, kh * kw, ldb, dx.ptr, ph, pw,
+                             dx.h, dx.w, dx.ld, taps, ostride=s, ooh=a, oow=b, accumulate=True, **common)
+
+    def conv_wgrad(self, g, x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=None, accumulate=False):
+        """dw (+)= row_scale * wgrad(g, x).  dw: tensor whose storage is (cout, kh*kw, cin)."""
+        be = self.be
+        y_lo = x_lo = None
+        ga, xa = g, x
+        if self.n_split > 1:
+            ga, glo = self._split_act(g)
+            xa, xlo = self._split_act(x)
+            y_lo, x_lo = glo.ptr, xlo.ptr
+        taps = O.conv_taps(kh, kw, dil, pad)
+        if kh == 1 and kw == 1 and stride == 1 and pad == 0:
+            npix = x.rows
+            be.conv_wgrad(ga.ptr, 1, 1, npix, cout, ga.ld, xa.ptr, 1, npix, cin, xa.ld, dw.data_ptr(), taps, 1,
+                          accumulate=accumulate, dy_lo_ptr=y_lo, x_lo_ptr=x_lo, n_split=self.n_split, device=g.device,
+                          row_scale=row_scale)
+        else:
+            be.conv_wgrad(ga.ptr, g.n, g.h, g.w, cout, ga.ld, xa.ptr, x.h, x.w, cin, xa.ld, dw.data_ptr(), taps, kh * kw,
+                          istride=stride, accumulate=accumulate, dy_lo_ptr=y_lo, x_lo_ptr=x_lo, n_split=self.n_split,
+                          device=g.device, row_scale=row_scale)
+
+    def transpose_w(self, w, cout, t, cin, scale=None):
+        """(cout, t, cin) -> (cin, t, pad4(cout)) with optional per-cout scale.  Returns (tensor, ldb)."""
+        ldb = _pad4(cout)
+        return self.be.transpose_w(w, cout, t, cin, ldd=ldb, scale=scale), ldb
+
+    # ------------------------------------------------------------------------------ other ops
+    def nchw_to_act(self, x_nchw, ld):
+        n, c, h, w = x_nchw.shape
+        out = Act.alloc(n, h, w, c, x_nchw.device, ld=ld)
+        self.be.nchw_to_nhwc(x_nchw.contiguous(), out.ptr, n, c, h, w, ld)
+        return out
+
+    def im2col(self, x, kh, kw, stride, pad, dil, oh, ow, kpad):
+        col = Act.alloc(1, 1, x.n * oh * ow, kpad, x.device)
+        self.be.im2col(x.ptr, col.ptr, x.n, x.h, x.w, x.c, x.ld, kh, kw, stride, pad, dil, oh, ow, kpad)
+        return col
+
+    def maxpool_fwd(self, x, out, idx):
+        assert x.ld == x.c and out.ld == out.c
+        self.be.maxpool_fwd(x.ptr, out.ptr, idx.data_ptr(), x.n, x.h, x.w, x.c, out.h, out.w)
+
+    def maxpool_bwd(self, dy, idx, dx):
+        assert dy.ld == dy.c and dx.ld == dx.c
+        self.be.maxpool_bwd(dy.ptr, idx.data_ptr(), dx.ptr, dx.n, dx.h, dx.w, dx.c, dy.h, dy.w)
+
+    def bilinear_fwd(self, x, out, align_corners):
+        self.be.bilinear_fwd(x.ptr, out.ptr, x.n, x.h, x.w, x.c, x.ld, out.h, out.w, out.ld, align_corners, False)
+
+    def bilinear_fwd_nchw(self, x, out_nchw, align_corners):
+        n, c, oh, ow = out_nchw.shape
+        self.be.bilinear_fwd(x.ptr, out_nchw.data_ptr(), x.n, x.h, x.w, x.c, x.ld, oh, ow, 0, align_corners, True)
+
+    def bilinear_bwd(self, dy, dx, align_corners, accumulate=False):
+        self.be.bilinear_bwd(dy.ptr, dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, dy.h, dy.w, dy.ld, align_corners, False,
+                             accumulate=accumulate)
+
+    def bilinear_bwd_nchw(self, dy_nchw, dx, align_corners, scale_dev=None, scale_host=1.0, accumulate=False):
+        n, c, oh, ow = dy_nchw.shape
+        self.be.bilinear_bwd(dy_nchw.data_ptr(), dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, oh, ow, 0, align_corners, True,
+                             scale_dev=scale_dev, scale_host=scale_host, accumulate=accumulate)
+
+    def gap_fwd(self, x, out):
+        self.be.gap_fwd(x.ptr, out.ptr, x.n, x.h * x.w, x.c, x.ld)
+
+    def gap_bwd(self, dy, dx, accumulate=False):
+        self.be.gap_bwd(dy.ptr, dx.ptr, dx.n, dx.h * dx.w, dx.c, dx.ld, accumulate=accumulate)
+
+    def bcast_fwd(self, v, out):
+        self.be.bcast_fwd(v.ptr, out.ptr, out.n, out.h * out.w, out.c, out.ld)
+
+    def bcast_bwd(self, dy, dv):
+        self.be.bcast_bwd(dy.ptr, dv.ptr, dy.n, dy.h * dy.w, dy.c, dy.ld)
+
+    def bn_stats(self, x, eps, momentum, mean, rstd, running_mean, running_var):
+        self.be.bn_stats(x.ptr, x.rows, x.c, x.ld, eps, momentum, mean, rstd, running_mean, running_var)
+
+    def bn_apply(self, x, mean, rstd, gamma, beta, relu, dropmask, drop_scale, out, residual=None):
+        self.be.bn_apply(x.ptr, x.rows, x.c, x.ld, mean, rstd, gamma, beta, relu, dropmask, drop_scale, out.ptr, out.ld,
+                         res_ptr=None if residual is None else residual.ptr, ldr=0 if residual is None else residual.ld)
+
+    def bn_bwd(self, dy, x, y, mean, rstd, gamma, relu, dropmask, drop_scale, dx, dgamma, dbeta, accumulate_params,
+               g_out=None):
+        self.be.bn_bwd(dy.ptr, dy.ld, x.ptr, x.ld, y.ptr, y.ld, x.rows, x.c, mean, rstd, gamma, relu, dropmask, drop_scale,
+                       dx.ptr, dx.ld, dgamma, dbeta, accumulate_params,
+                       g_out_ptr=None if g_out is None else g_out.ptr, ldgo=0 if g_out is None else g_out.ld)
+
+    def bn_fold(self, gamma, beta, mean, var, eps, scale, shift):
+        self.be.bn_fold(gamma, beta, mean, var, eps, scale, shift)
+
+    def bn_eval_param_grad(self, g, y, gamma, beta, sub, dgamma, dbeta, accumulate):
+        self.be.bn_eval_param_grad(g.ptr, g.ld, y.ptr, y.ld, g.rows, g.c, gamma, beta, None, 0,
+                                   None if sub is None else sub.ptr, 0 if sub is None else sub.ld, dgamma, dbeta,
+                                   accumulate)
+
+    def colsum(self, g, out, accumulate):
+        self.be.colsum(g.ptr, g.ld, g.rows, g.c, out, accumulate)
+
+    def relu_gate(self, g, y):
+        self.be.relu_gate(g.ptr, g.ld, y.ptr, y.ld, g.rows, g.c)
+
+    def copy_act(self, dst, src, accumulate=False):
+        self.be.slice_copy(dst.ptr, dst.ld, src.ptr, src.ld, src.rows, src.c, accumulate)
+
+    def fill_act(self, a, value):
+        if a.ld == a.c and a.off == 0:
+            self.be.fill(a.base, value)
+        else:
+            raise NotImplementedError('fill of a strided slice')
+
+    def dropout_mask(self, n, h, w, c, p, seed, offset, device):
+        mask = torch.empty((n, h, w, c), device=device, dtype=torch.float32)
+        self.be.dropout_mask(mask, p, seed, offset)
+        return mask
+
+    # device-tensor helpers (allocation is plumbing, done through torch)
+    @staticmethod
+    def empty(shape, device, dtype=torch.float32):
+        return torch.empty(shape, device=device, dtype=dtype)

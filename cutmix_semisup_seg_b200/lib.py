@@ -56,6 +56,7 @@ class WgradParams(ctypes.Structure):
         ('accumulate', c_i32), ('n_split', c_i32),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
         ('max_ctas', c_i32),
+        ('row_scale', c_vp),
     ]
 
 
@@ -78,7 +79,9 @@ _SIGS = {
     'b2_conv_wgrad_workspace': (c_sz, [ctypes.POINTER(WgradParams)]),
     'b2_conv_wgrad': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
-    'b2_transpose_w': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+    'b2_transpose_w': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'b2_relu_gate': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp]),
+    'b2_slice_copy': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
     'b2_nchw_to_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_nhwc_to_nchw': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_im2col': (c_int, [c_vp, c_vp] + [c_int] * 13 + [c_vp]),
@@ -93,11 +96,11 @@ _SIGS = {
     'b2_bn_workspace_doubles': (c_i64, [c_i64, c_int]),
     'b2_bn_stats': (c_int, [c_vp, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b2_bn_apply': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_f32, c_vp, c_int,
-                            c_vp]),
+                            c_vp, c_int, c_vp]),
     'b2_bn_bwd': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp,
-                          c_f32, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+                          c_f32, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     'b2_bn_fold': (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp]),
-    'b2_bn_eval_param_grad': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int,
+    'b2_bn_eval_param_grad': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int,
                                       c_vp, c_vp, c_int, c_vp, c_vp]),
     'b2_dropout_mask': (c_int, [c_vp, c_i64, c_f32, c_u64, c_u64, c_vp]),
     'b2_add_inplace': (c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -119,11 +119,12 @@ class CudaBackend(object):
         self._call('b2_split_tf32', x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), self._s())
         return hi, lo
 
-    def transpose_w(self, w, a, t, b, out=None):
-        """(A,T,B) -> (B,T,A) on the raw storage of `w`."""
+    def transpose_w(self, w, a, t, b, out=None, ldd=None, scale=None):
+        """(A,T,B) -> (B,T,ldd) on the raw storage of `w` (rows zero-padded to ldd, optional per-A scale)."""
+        ldd = a if ldd is None else ldd
         if out is None:
-            out = torch.empty((b, t, a), device=w.device, dtype=torch.float32)
-        self._call('b2_transpose_w', w.data_ptr(), out.data_ptr(), a, t, b, self._s())
+            out = torch.empty((b, t, ldd), device=w.device, dtype=torch.float32)
+        self._call('b2_transpose_w', w.data_ptr(), out.data_ptr(), a, t, b, ldd, L.ptr(scale), self._s())
         return out
 
     # ------------------------------------------------------------------ tensor-core convolution
@@ -151,7 +152,8 @@ class CudaBackend(object):
         self._call('b2_conv_gemm', ctypes.byref(p), self._s())
 
     def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
-                   accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None):
+                   accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None,
+                   row_scale=None):
         taps_arr = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(-1, 3))
         p = L.WgradParams()
         p.dy = dy_ptr; p.dy_lo = dy_lo_ptr; p.x = x_ptr; p.x_lo = x_lo_ptr; p.dw = dw_ptr
@@ -163,6 +165,7 @@ class CudaBackend(object):
         p.tw = tw
         p.accumulate = int(bool(accumulate)); p.n_split = n_split
         p.max_ctas = max_ctas
+        p.row_scale = L.ptr(row_scale)
         need = L.call('b2_conv_wgrad_workspace', ctypes.byref(p))
         ws = None
         if need > 0:
@@ -170,6 +173,93 @@ class CudaBackend(object):
             p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel()
         self._call('b2_conv_wgrad', ctypes.byref(p), self._s())
         self.launches += 1 if need > 0 else 0
+
+    # ------------------------------------------------------------------ NHWC network ops (raw pointers)
+    def nchw_to_nhwc(self, src, dst_ptr, n, c, h, w, ldd):
+        self._call('b2_nchw_to_nhwc', src.data_ptr(), dst_ptr, n, c, h, w, ldd, self._s())
+
+    def nhwc_to_nchw(self, src_ptr, dst, n, c, h, w, lds):
+        self._call('b2_nhwc_to_nchw', src_ptr, dst.data_ptr(), n, c, h, w, lds, self._s())
+
+    def im2col(self, x_ptr, col_ptr, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad):
+        self._call('b2_im2col', x_ptr, col_ptr, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad, self._s())
+
+    def maxpool_fwd(self, x_ptr, y_ptr, idx_ptr, n, h, w, c, oh, ow):
+        self._call('b2_maxpool3x3s2', x_ptr, y_ptr, idx_ptr, n, h, w, c, oh, ow, self._s())
+
+    def maxpool_bwd(self, dy_ptr, idx_ptr, dx_ptr, n, h, w, c, oh, ow):
+        self._call('b2_maxpool3x3s2_bwd', dy_ptr, idx_ptr, dx_ptr, n, h, w, c, oh, ow, self._s())
+
+    def bilinear_fwd(self, x_ptr, y_ptr, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, to_nchw):
+        self._call('b2_bilinear_fwd', x_ptr, y_ptr, n, ih, iw, c, ldx, oh, ow, ldy, int(align_corners), int(to_nchw), self._s())
+
+    def bilinear_bwd(self, dy_ptr, dx_ptr, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, from_nchw, scale_dev=None,
+                     scale_host=1.0, accumulate=False):
+        self._call('b2_bilinear_bwd', dy_ptr, dx_ptr, n, ih, iw, c, ldx, oh, ow, ldy, int(align_corners), int(from_nchw),
+                   L.ptr(scale_dev), float(scale_host), int(accumulate), self._s())
+
+    def gap_fwd(self, x_ptr, y_ptr, n, hw, c, ldx):
+        self._call('b2_gap_fwd', x_ptr, y_ptr, n, hw, c, ldx, self._s())
+
+    def gap_bwd(self, dy_ptr, dx_ptr, n, hw, c, ldx, accumulate=False):
+        self._call('b2_gap_bwd', dy_ptr, dx_ptr, n, hw, c, ldx, int(accumulate), self._s())
+
+    def bcast_fwd(self, v_ptr, y_ptr, n, hw, c, ldy):
+        self._call('b2_bcast_fwd', v_ptr, y_ptr, n, hw, c, ldy, self._s())
+
+    def bcast_bwd(self, dy_ptr, dv_ptr, n, hw, c, ldy):
+        self._call('b2_bcast_bwd', dy_ptr, dv_ptr, n, hw, c, ldy, self._s())
+
+    def _red_ws(self, rows, c, device):
+        need = L.call('b2_bn_workspace_doubles', rows, c)
+        if getattr(self, '_rws', None) is None or self._rws.numel() < need or self._rws.device != torch.device(device):
+            self._rws = torch.empty((int(need),), device=device, dtype=torch.float64)
+        return self._rws
+
+    def bn_stats(self, x_ptr, rows, c, ldx, eps, momentum, mean, rstd, running_mean, running_var):
+        ws = self._red_ws(rows, c, mean.device)
+        self._call('b2_bn_stats', x_ptr, rows, c, ldx, float(eps), float(momentum), mean.data_ptr(), rstd.data_ptr(),
+                   L.ptr(running_mean), L.ptr(running_var), ws.data_ptr(), self._s())
+        self.launches += 2
+
+    def bn_apply(self, x_ptr, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y_ptr, ldy,
+                 res_ptr=None, ldr=0):
+        self._call('b2_bn_apply', x_ptr, rows, c, ldx, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                   int(bool(relu)), L.ptr(dropmask), float(drop_scale), y_ptr, ldy, res_ptr, ldr, self._s())
+
+    def bn_bwd(self, dy_ptr, lddy, x_ptr, ldx, y_ptr, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale,
+               dx_ptr, lddx, dgamma, dbeta, accumulate_params, g_out_ptr=None, ldgo=0):
+        ws = self._red_ws(rows, c, mean.device)
+        self._call('b2_bn_bwd', dy_ptr, lddy, x_ptr, ldx, y_ptr, ldy, rows, c, mean.data_ptr(), rstd.data_ptr(),
+                   gamma.data_ptr(), int(bool(relu)), L.ptr(dropmask), float(drop_scale), dx_ptr, lddx,
+                   L.ptr(dgamma), L.ptr(dbeta), int(bool(accumulate_params)), g_out_ptr, ldgo, ws.data_ptr(), self._s())
+        self.launches += 3
+
+    def bn_fold(self, gamma, beta, mean, var, eps, scale, shift):
+        self._call('b2_bn_fold', gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), var.data_ptr(), float(eps),
+                   scale.data_ptr(), shift.data_ptr(), gamma.numel(), self._s())
+
+    def bn_eval_param_grad(self, dy_ptr, lddy, ybn_ptr, ldy, rows, c, gamma, beta, gate_ptr, ldg, sub_ptr, lds,
+                           dgamma, dbeta, accumulate):
+        ws = self._red_ws(rows, c, gamma.device)
+        self._call('b2_bn_eval_param_grad', dy_ptr, lddy, ybn_ptr, ldy, rows, c, gamma.data_ptr(), beta.data_ptr(),
+                   gate_ptr, ldg, sub_ptr, lds, dgamma.data_ptr(), dbeta.data_ptr(), int(bool(accumulate)),
+                   ws.data_ptr(), self._s())
+        self.launches += 2
+
+    def colsum(self, dy_ptr, ld, rows, c, out, accumulate):
+        ws = self._red_ws(rows, c, out.device)
+        self._call('b2_colsum', dy_ptr, ld, rows, c, out.data_ptr(), int(bool(accumulate)), ws.data_ptr(), self._s())
+        self.launches += 2
+
+    def relu_gate(self, g_ptr, ldg, y_ptr, ldy, rows, c):
+        self._call('b2_relu_gate', g_ptr, ldg, y_ptr, ldy, rows, c, self._s())
+
+    def slice_copy(self, dst_ptr, ldd, src_ptr, lds, rows, c, accumulate=False):
+        self._call('b2_slice_copy', dst_ptr, ldd, src_ptr, lds, rows, c, int(bool(accumulate)), self._s())
+
+    def dropout_mask(self, mask, p, seed, offset):
+        self._call('b2_dropout_mask', mask.data_ptr(), mask.numel(), float(p), int(seed), int(offset), self._s())
 
     _ws = None
 
@@ -187,3 +277,14 @@ def conv_taps(kh, kw, dil, pad):
 def dgrad_taps(kh, kw, dil, pad):
     """Tap table of the stride-1 input-gradient convolution: dX[h] += dY[h + pad - r*dil] * W[r]."""
     return [(pad - r * dil, pad - s * dil, r * kw + s) for r in range(kh) for s in range(kw)]
+
+
+_default = None
+
+
+def default_backend():
+    """Process-wide CudaBackend (raises if libb200seg.so is missing: no CPU fallback)."""
+    global _default
+    if _default is None:
+        _default = CudaBackend()
+    return _default

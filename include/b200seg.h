@@ -161,6 +161,7 @@ typedef struct b2_wgrad_params {
   int32_t accumulate, n_split;
   void* workspace; size_t workspace_bytes;
   int32_t max_ctas;
+  const float* row_scale;                 /* per-m scale applied to the gradient rows, or NULL */
 } b2_wgrad_params;
 size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p);
 int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
@@ -171,8 +172,10 @@ void b2_debug_set(int key, int value);
 /* hi = x with the 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact). */
 int b2_split_tf32(const float* x, float* hi, float* lo, int64_t count, void* stream);
 
-/* (A, T, B) -> (B, T, A) transpose of a weight tensor (KRSC <-> CRSK). */
-int b2_transpose_w(const float* src, float* dst, int a, int t, int b, void* stream);
+/* (A, T, B) -> (B, T, ldd) transpose of a weight tensor (KRSC -> CRSK), rows padded with zeros to
+ * ldd >= A; optional per-A scale (folded BN scale of the output channel) applied on the fly. */
+int b2_transpose_w(const float* src, float* dst, int a, int t, int b, int ldd, const float* scale_a,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound network ops (NHWC fp32).
@@ -205,19 +208,21 @@ int b2_bcast_fwd(const float* v, float* y, int n, int hw, int c, int ldy, void* 
 int b2_bcast_bwd(const float* dy, float* dv, int n, int hw, int c, int ldy, void* stream);
 /* Train-mode batch norm over NHWC (N*H*W rows, C channels), DLv3+ head.
  *   stats: mean[c], rstd[c] (biased var, eps), updates running stats with momentum (unbiased var).
- *   apply: y = relu?((x-mean)*rstd*gamma+beta) * dropmask? ; y may alias a channel slice (ldy).
- *   bwd: given dy (w.r.t. y), y-side gate (relu: y>0), computes dx, dgamma, dbeta. */
+ *   apply: y = relu?((x-mean)*rstd*gamma+beta + residual?) * dropmask? ; y may be a channel slice (ldy).
+ *   bwd: given dy (w.r.t. y), y-side gate (relu: y>0), computes dx, dgamma, dbeta; g_out (optional)
+ *        receives the gated gradient (the residual branch's gradient). */
 int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float eps, float momentum,
                 float* mean, float* rstd, float* running_mean, float* running_var,
                 double* workspace, void* stream);
 int64_t b2_bn_workspace_doubles(int64_t rows, int c);
 int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const float* mean, const float* rstd,
                 const float* gamma, const float* beta, int relu, const float* dropmask,
-                float drop_scale, float* y, int ldy, void* stream);
+                float drop_scale, float* y, int ldy, const float* residual, int ldr, void* stream);
 int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y, int ldy,
               int64_t rows, int c, const float* mean, const float* rstd, const float* gamma,
               int relu, const float* dropmask, float drop_scale, float* dx, int lddx,
-              float* dgamma, float* dbeta, int accumulate_params, double* workspace, void* stream);
+              float* dgamma, float* dbeta, int accumulate_params, float* g_out, int ldgo,
+              double* workspace, void* stream);
 /* Eval-mode (frozen) BN folded constants: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale. */
 int b2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
                float eps, float* scale, float* shift, int c, void* stream);
@@ -226,12 +231,15 @@ int b2_bn_fold(const float* gamma, const float* beta, const float* mean, const f
  *   xhat = (ybn - beta)/gamma recovered from the stored BN output `ybn`. */
 int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, int64_t rows, int c,
                           const float* gamma, const float* beta, const float* gate, int ldg,
-                          float* dgamma, float* dbeta, int accumulate, double* workspace,
-                          void* stream);
+                          const float* sub, int lds, float* dgamma, float* dbeta, int accumulate,
+                          double* workspace, void* stream);
 /* dropout mask: mask[i] = (philox(seed, offset+i) >= p) ? 1 : 0 */
 int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset,
                     void* stream);
-/* y = relu-gated / plain elementwise helpers used by the backward pass */
+/* elementwise helpers used by the backward pass */
+int b2_relu_gate(float* g, int ldg, const float* y, int ldy, int64_t rows, int c, void* stream);
+int b2_slice_copy(float* dst, int ldd, const float* src, int lds, int64_t rows, int c, int accumulate,
+                  void* stream);
 int b2_add_inplace(float* dst, const float* src, int64_t count, void* stream);
 int b2_fill(float* dst, float value, int64_t count, void* stream);
 /* per-column bias gradient: db[c] (+)= sum_rows dy[row, c] */
