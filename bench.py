@@ -1,0 +1,338 @@
+"""Benchmark of the CutMix mean-teacher training iteration (BASELINE.json metric: images/sec at 512x512,
+bs=16 per GPU, DeepLab v3+ ResNet-101, 19 classes, synthetic Cityscapes-shaped data).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--arch v3plus|v2]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one full iteration of train_seg_semisup_mask_mt.py:287-476: supervised forward/backward on N
+labelled images, two teacher forwards + one student forward/backward on 2N unlabelled images (CutMix),
+fused losses, Adam step, EMA step, (N>1) one gradient all-reduce.  images/sec := N * world / iteration time.
+
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` repeats the measurement
+through the public API with pinned host batches copied H2D and the loss read back D2H every step.
+`--impl reference` times the CPU port of the reference path (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = {
+    'v3plus': dict(arch='resnet101_deeplabv3plus_imagenet', classes=19, h=512, w=512, batch=16, lr=1e-5,
+                   workload='DeepLab v3+ ResNet-101, synthetic Cityscapes 512x512, 19 classes, CutMix mean teacher, bs 16/GPU'),
+    'v2': dict(arch='resnet101_deeplab_imagenet', classes=21, h=321, w=321, batch=16, lr=3e-5,
+               workload='DeepLab v2 ResNet-101, synthetic Pascal-Aug 321x321, 21 classes, CutMix mean teacher, bs 16/GPU'),
+}
+# forward conv FLOPs per image (2*MAC, dense), stem FLOPs: SURVEY.md §8 / BASELINE.md §2
+FLOPS = {'v3plus': (520.28e9, 1.233e9), 'v2': (147.67e9, 0.488e9)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_burst=d['bf16_tflops'], bf16_sustained=d['bf16_tflops_sustained'],
+                    source='measured')
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle sampler running during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def build_trainer(cfg, device, dist_on):
+    from architectures import network_architectures
+    import mask_gen
+    import optim_weight_ema
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    torch.manual_seed(0)
+    Net = network_architectures.seg.get(cfg['arch'])
+    student = Net(cfg['classes'], pretrained=False)
+    synthetic.condition_classifier(student, 40.0)
+    student = student.to(device)
+    teacher = Net(cfg['classes'], pretrained=False).to(device)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=cfg['lr'] * 0.1),
+                                  dict(params=student.new_parameters(), lr=cfg['lr'])], foreach=False)
+    ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+    student.train(); teacher.train()
+    student.freeze_batchnorm(); teacher.freeze_batchnorm()         # every reference recipe uses --freeze_bn
+    mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
+                                   within_bounds=True, invert=True)
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, cons_loss_fn='var', cons_weight=1.0,
+                                       conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
+                                       dist_group=True if dist_on else None)
+    return trainer, mg
+
+
+def timed_conv_profile(trainer, sup, unsup):
+    """One instrumented iteration: CUDA-event duration of every tensor-core conv launch (on the launching
+    stream) and its algorithmic FLOPs -> aggregate achieved TFLOP/s per kernel."""
+    be = trainer.be
+    be.start_profile()
+    trainer.step(sup, [unsup])
+    torch.cuda.synchronize()
+    return be.stop_profile()
+
+
+def run_b200(args):
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (b200 arm) needs a CUDA device: there is no CPU fallback')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    from cutmix_semisup_seg_b200 import synthetic
+    cfg = CFG[args.arch]
+    n, h, w = args.batch or cfg['batch'], cfg['h'], cfg['w']
+    trainer, mg = build_trainer(cfg, device, dist_on)
+    be = trainer.be
+    # a small pool of distinct batches (per-iteration working set >> 126 MB L2: activations alone are ~20 GB)
+    pool = 3
+    sup_host = [synthetic.make_sup_batch(n, h, w, cfg['classes'], 100 + rank * 10 + i, pin=True) for i in range(pool)]
+    uns_host = [synthetic.make_unsup_batch(n, h, w, 200 + rank * 10 + i, mg, pin=True) for i in range(pool)]
+    sup_dev = [(a.to(device), b.to(device)) for a, b in sup_host]
+    uns_dev = [{k: v.to(device) for k, v in d.items()} for d in uns_host]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = be.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for i in range(args.steps):
+        out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = be.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    last = {k: float(v) for k, v in out.items() if v is not None}
+
+    # ---- end to end: pinned host batches -> H2D every step, loss scalars -> D2H every step
+    h2d = sum(t.numel() * t.element_size() for t in sup_host[0]) + \
+        sum(t.numel() * t.element_size() for t in {id(v): v for v in uns_host[0].values()}.values())
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h = 0
+    for i in range(args.steps):
+        sb = tuple(t.to(device, non_blocking=True) for t in sup_host[i % pool])
+        cache = {}
+        ub = {}
+        for k, v in uns_host[i % pool].items():
+            if id(v) not in cache:
+                cache[id(v)] = v.to(device, non_blocking=True)
+            ub[k] = cache[id(v)]
+        o = trainer.step(sb, [ub])
+        vals = torch.stack([o['sup_loss'], o['cons_loss'], o['conf_rate']]).cpu()    # D2H read of the step's result
+        d2h = vals.numel() * 4
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- per-kernel roofline (instrumented iteration outside the timed regions)
+    prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0]) if rank == 0 else None
+
+    if dist_on:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist_on:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    ms_step = ms / args.steps
+    value = n * world / (ms_step / 1e3)
+    F, Fs = FLOPS[args.arch]
+    flops_iter = (8 * F - 2 * Fs) * n
+    res = {
+        'metric': 'images/sec', 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
+                   'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
+                   'freeze_bn': True, 'optimizer': 'Adam foreach=False (reference param groups)',
+                   'conv_tflops_per_s_whole_step': round(flops_iter / (ms_step / 1e3) / 1e12, 2)},
+        'clocks': clocks,
+        'e2e': {'value': round(n * world / (ms_e2e / args.steps / 1e3), 3), 'unit': 'images/s',
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(launches),
+        'last_step': last,
+    }
+    if prof:
+        dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
+        name, d = dom
+        ach = d['flops'] / (d['ms'] / 1e3) / 1e12
+        res['roofline'] = {'kernel': name, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peaks['bf16_sustained'],
+                           'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16_sustained'], 4), 'traffic': None,
+                           'peak_source': peaks['source'] + ' cuBLAS bf16 sustained; kind::tf32 runs at half the bf16 rate',
+                           'frac_of_tf32_rate': round(ach / (peaks['bf16_sustained'] / 2), 4),
+                           'launches': d['n'], 'kernel_ms_per_step': round(d['ms'], 3),
+                           'share_of_step': round(d['ms'] / ms_step, 4),
+                           'per_kernel': {k: {'ms': round(v['ms'], 3), 'n': v['n'],
+                                              'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)} for k, v in prof.items()}}
+    res['cpu_baseline'] = cpu_baseline(args, sample_batch=1)
+    print(json.dumps(res))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _oracle_trainer(cfg, arch_key):
+    """CPU port of the reference path (oracle/): the same iteration on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_step
+    import torch_oracle as TO
+    from architectures import network_architectures
+    import mask_gen
+    net = network_architectures.seg.get(cfg['arch'])(cfg['classes'], pretrained=False)      # shapes/keys only
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    sd = TO.synth_state_dict(net.state_dict(), seed=0, logit_gain=40.0, final_keys=final)
+    tr = ref_step.OracleMeanTeacher('deeplab3plus' if arch_key == 'v3plus' else 'deeplab2', sd, cfg['lr'])
+    mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
+                                   within_bounds=True, invert=True)
+    return tr, mg
+
+
+def cpu_step_time(args, batch, steps, warmup):
+    from cutmix_semisup_seg_b200 import synthetic
+    cfg = CFG[args.arch]
+    torch.set_num_threads(os.cpu_count())
+    tr, mg = _oracle_trainer(cfg, args.arch)
+    sup = synthetic.make_sup_batch(batch, cfg['h'], cfg['w'], cfg['classes'], 100)
+    uns = synthetic.make_unsup_batch(batch, cfg['h'], cfg['w'], 200, mg, compact_masks=False)
+    times = []
+    for i in range(warmup + steps):
+        t = time.time()
+        tr.step(sup[0], sup[1], uns)
+        times.append(time.time() - t)
+    return times[warmup:], cfg
+
+
+def cpu_baseline(args, sample_batch=1):
+    """Reported baseline (not the target): one iteration of the oracle port on `sample_batch` images."""
+    try:
+        times, cfg = cpu_step_time(args, sample_batch, 1, 0)
+    except Exception as e:  # keep the GPU line even if the host leg fails
+        return {'value': None, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (e,)}
+    return {'value': round(sample_batch / times[0], 4), 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '1 iteration (4 fwd + 2 bwd + Adam + EMA) of the torch-CPU port of the reference path, batch {} at {}x{}'
+                      .format(sample_batch, cfg['h'], cfg['w'])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    batch = 1
+    warm = min(args.warmup, 1)
+    t0 = time.time()
+    probe, cfg = cpu_step_time(args, batch, 1, 0)
+    budget = 170.0
+    steps = max(1, min(args.steps, int(budget / max(probe[0], 1e-3)) - warm))
+    times, cfg = cpu_step_time(args, batch, steps, warm)
+    sec = float(np.mean(times))
+    val = batch / sec
+    res = {'impl': 'reference', 'metric': 'images/sec', 'value': round(val, 4), 'unit': 'images/s', 'n_gpus': args.gpus,
+           'steps': steps, 'warmup': warm, 'ms_per_step': round(sec * 1e3, 1), 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': cfg['workload'], 'note': 'reference path (torch CPU port, oracle/) on host cores; each step is a '
+                      'bounded sample of the workload: batch {} instead of {}'.format(batch, cfg['batch'])},
+           'cpu_baseline': {'value': round(val, 4), 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                            'sample': '{} iterations, batch {} at {}x{}'.format(steps, batch, cfg['h'], cfg['w'])},
+           'e2e': {'value': round(val, 4), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(res))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2'])
+    ap.add_argument('--batch', type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -7,7 +7,7 @@ class Act(object):
     channels [off, off + c) of every pixel.  Slices of a wider buffer replace torch.cat."""
 
     __slots__ = ('base', 'n', 'h', 'w', 'c', 'ld', 'off', 'gate_on_grad', 'node', 'parent', 'pending',
-                 'grad', 'grad_owned', 'name')
+                 'grad', 'grad_owned', 'name', 'needs_grad')
 
     def __init__(self, base, n, h, w, c, ld=None, off=0, name=''):
         self.base = base
@@ -21,6 +21,7 @@ class Act(object):
         self.grad = None            # Act holding d(loss)/d(this)
         self.grad_owned = False
         self.name = name
+        self.needs_grad = True      # False for network inputs (no dgrad is computed into them)
 
     @staticmethod
     def alloc(n, h, w, c, device, ld=None, name=''):

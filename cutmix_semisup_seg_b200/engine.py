@@ -170,13 +170,12 @@ class ConvNode(object):
                 gflat = Act(g.base, 1, 1, g.rows, g.c, g.ld, g.off)
                 K.conv_wgrad(gflat, col, dw_pad, cout, 1, 1, kpad, 1, 0, 1, row_scale=self.scale, accumulate=False)
                 dw, acc = param_grad(w)
-                K.be.slice_copy(dw.data_ptr(), kh * kw * cin, dw_pad.data_ptr(), kpad, cout, kh * kw * cin, acc)
+                K.copy_rows(dw, kh * kw * cin, dw_pad, kpad, cout, kh * kw * cin, acc)
             return
         if w.requires_grad:
             dw, acc = param_grad(w)
             K.conv_wgrad(g, self.x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=self.scale, accumulate=acc)
-        root = self.x
-        if root.node is None and root.parent is None:
+        if not self.x.needs_grad:
             return                                   # network input: no gradient needed
         wt, ldb = K.transpose_w(w, cout, kh * kw, cin, scale=self.scale)
 
@@ -356,7 +355,7 @@ def stem_conv(tape, x_nhwc, conv, bn):
     kpad = (kreal + 31) // 32 * 32
     col = K.im2col(x_nhwc, kh, kw, stride, pad, dil, oh, ow, kpad)
     wpad = torch.zeros((cout, 1, kpad), device=x_nhwc.device, dtype=torch.float32)
-    K.be.slice_copy(wpad.data_ptr(), kpad, conv.weight.data_ptr(), kreal, cout, kreal, False)
+    K.copy_rows(wpad, kpad, conv.weight, kreal, cout, kreal, False)
     train_bn = bn.training
     tgt = Act.alloc(x_nhwc.n, oh, ow, cout, x_nhwc.device)
     flat = Act(tgt.base, 1, 1, tgt.rows, cout, cout, 0)

@@ -225,6 +225,10 @@ class ActKernels(object):
     def copy_act(self, dst, src, accumulate=False):
         self.be.slice_copy(dst.ptr, dst.ld, src.ptr, src.ld, src.rows, src.c, accumulate)
 
+    def copy_rows(self, dst, ldd, src, lds, rows, c, accumulate=False):
+        """dst[r, :c] (+)= src[r, :c] on raw tensor storages with row pitches ldd / lds."""
+        self.be.slice_copy(dst.data_ptr(), ldd, src.data_ptr(), lds, rows, c, accumulate)
+
     def fill_act(self, a, value):
         if a.ld == a.c and a.off == 0:
             self.be.fill(a.base, value)

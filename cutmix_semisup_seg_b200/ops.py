@@ -25,7 +25,7 @@ class CudaBackend(object):
         L.load()
         self._keep = []          # host-side arrays that must outlive an async launch (none today)
         self.launches = 0
-        self.precision_split = 1  # 1 = single-pass TF32; 3/4 = 3xTF32 parity mode
+        self._prof = None        # list of (kernel, flops, ev0, ev1) while profiling
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -34,6 +34,30 @@ class CudaBackend(object):
     def _call(self, name, *args):
         self.launches += 1
         return L.call(name, *args)
+
+    def _timed_call(self, kernel, flops, name, *args):
+        """Launch with CUDA events recorded on the launching stream when profiling is on."""
+        if self._prof is None:
+            return self._call(name, *args)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = self._call(name, *args)
+        e1.record()
+        self._prof.append((kernel, flops, e0, e1))
+        return rc
+
+    def start_profile(self):
+        self._prof = []
+
+    def stop_profile(self):
+        """{kernel: {'ms': total device time, 'flops': algorithmic FLOPs, 'n': launches}}"""
+        torch.cuda.synchronize()
+        out = {}
+        for kernel, flops, e0, e1 in self._prof:
+            d = out.setdefault(kernel, {'ms': 0.0, 'flops': 0.0, 'n': 0})
+            d['ms'] += e0.elapsed_time(e1); d['flops'] += flops; d['n'] += 1
+        self._prof = None
+        return out
 
     @staticmethod
     def empty(shape, device, dtype=torch.float32):
@@ -149,7 +173,8 @@ class CudaBackend(object):
         p.scale2 = L.ptr(scale2)
         p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate)); p.n_split = n_split
         p.max_ctas = max_ctas
-        self._call('b2_conv_gemm', ctypes.byref(p), self._s())
+        flops = 2.0 * n * oh * ow * nb * k * taps_arr.shape[0] * n_split
+        self._timed_call('conv_gemm_kernel', flops / n_split, 'b2_conv_gemm', ctypes.byref(p), self._s())
 
     def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
                    accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None,
@@ -171,7 +196,8 @@ class CudaBackend(object):
         if need > 0:
             ws = self._workspace(need, device)
             p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel()
-        self._call('b2_conv_wgrad', ctypes.byref(p), self._s())
+        flops = 2.0 * n * oh * ow * m * c * taps_arr.shape[0]
+        self._timed_call('conv_wgrad_kernel', flops, 'b2_conv_wgrad', ctypes.byref(p), self._s())
         self.launches += 1 if need > 0 else 0
 
     # ------------------------------------------------------------------ NHWC network ops (raw pointers)

@@ -1,0 +1,152 @@
+"""One iteration of the CutMix / CutOut mean-teacher loop on the B200 kernels.
+
+This is the body of the reference's training loop (train_seg_semisup_mask_mt.py:287-476) with the
+same order of operations and the same arithmetic, restructured for the GPU:
+
+  reference (per iteration)                          here
+  ------------------------------------------------   ---------------------------------------------
+  CE = CrossEntropyLoss(ignore 255); backward        one fused CE kernel (loss + dlogits), engine tape
+  x0*(1-m)+x1*m for image and valid mask (6 ATen)    b2_mix (x2 launches)
+  2 teacher forwards, 1 student forward              engine forwards (teacher without a tape)
+  logit mix, 2 softmax, max, >=, mean, (p-q)^2 ...   ONE fused consistency kernel (loss, conf rate, dlogits)
+  float(conf_mask.mean()), float(loss) host syncs    scalars stay on the device (read them when logging)
+  loss.backward() through autograd                   engine tape; the 1/N, conf-rate, ramp and weight scalars
+                                                     are applied by the first backward kernel from a device scalar
+  student_optim.step(); teacher_optim.step()         torch.optim (unchanged) ; fused multi-tensor EMA kernel
+  (single GPU)                                       optional data parallelism: ONE all-reduce(avg) of the
+                                                     flat student-gradient buffer before the optimiser step
+"""
+import torch
+
+from . import ops as O
+
+
+class FlatGrads(object):
+    """All student gradients as views into one flat fp32 buffer: a single fill kernel zeroes them and a
+    single NCCL all-reduce averages them across ranks."""
+
+    def __init__(self, params):
+        seen, uniq = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        total = sum(p.numel() for p in uniq)
+        dev = uniq[0].device
+        self.flat = torch.zeros((total,), device=dev, dtype=torch.float32)
+        off = 0
+        for p in uniq:
+            n = p.numel()
+            view = torch.as_strided(self.flat, p.shape, p.stride(), off)   # same (channels-last) layout as p
+            p.grad = view
+            off += n
+        self.numel = total
+
+    def attach(self):
+        """Re-attach the views (after `optimizer.zero_grad(set_to_none=True)` removed them)."""
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
+                p.grad = torch.as_strided(self.flat, p.shape, p.stride(), off)
+            off += p.numel()
+
+    def zero(self, backend):
+        self.attach()
+        backend.fill(self.flat, 0.0)
+
+
+class MeanTeacherStep(object):
+    def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
+                 cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
+                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True):
+        self.student_net, self.teacher_net = student_net, teacher_net
+        self.student_optim, self.teacher_optim = student_optim, teacher_optim
+        self.mask_generator = mask_generator
+        self.cons_loss_fn, self.cons_weight = cons_loss_fn, cons_weight
+        self.conf_thresh, self.conf_per_pixel = conf_thresh, conf_per_pixel
+        self.rampup, self.mask_mix, self.unsup_batch_ratio = rampup, mask_mix, unsup_batch_ratio
+        self.be = O.default_backend()
+        self.world = 1
+        self.dist = None
+        if dist_group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.group = dist_group if dist_group is not True else None
+            self.world = dist.get_world_size(self.group)
+        self.flat = FlatGrads(list(student_net.parameters())) if (use_flat_grads or self.world > 1) else None
+
+    # ------------------------------------------------------------------------------------------
+    def _zero_grad(self):
+        if self.flat is not None:
+            self.flat.zero(self.be)
+        else:
+            self.student_optim.zero_grad()
+
+    def _allreduce(self):
+        if self.world > 1:
+            # natural shard: every rank holds the gradient of its own mini-batch; average them (DDP semantics)
+            self.dist.all_reduce(self.flat.flat, op=self.dist.ReduceOp.AVG, group=self.group)
+
+    def supervised(self, batch_x, batch_y):
+        """Lines 296-301: student forward, CE(ignore 255), backward.  Returns the loss as a device scalar."""
+        logits, state = self.student_net.b2_forward(batch_x, record=True)
+        labels = batch_y[:, 0] if batch_y.dim() == 4 else batch_y
+        out3, dlogits = self.be.cross_entropy(logits, labels.contiguous(), ignore_index=255)
+        self.student_net.b2_backward(state, dlogits, scale_dev=out3[2:3])
+        return out3[0]
+
+    def unsupervised_mix(self, ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params, ramp_val=1.0):
+        """Lines 309-369 + 406-459 (mix mode)."""
+        be = self.be
+        masks = self.mask_generator.torch_masks_from_params(mask_params, ux0_stu.shape[2:4], ux0_stu.device)
+        masks = masks.contiguous()
+        ux_mixed = be.mix(ux0_stu, ux1_stu, masks)                    # :350
+        um_mixed = be.mix(um0, um1, masks)                            # :351
+        with torch.no_grad():                                          # :354-356
+            l0 = self.teacher_net.b2_forward(ux0_tea, record=False)[0]
+            l1 = self.teacher_net.b2_forward(ux1_tea, record=False)[0]
+        ls, state = self.student_net.b2_forward(ux_mixed, record=True)            # :358
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.consistency(l0, l1, ls, masks, um_mixed, self.cons_loss_fn, self.conf_thresh, self.conf_per_pixel,
+                                   ramp, self.cons_weight)
+        self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])             # :458-459
+        return out4
+
+    def unsupervised_cut(self, ux_tea, ux_stu, um, mask_params, ramp_val=1.0):
+        """Lines 371-401 + 406-459 (cut / CutOut mode)."""
+        be = self.be
+        masks = self.mask_generator.torch_masks_from_params(mask_params, ux_stu.shape[2:4], ux_stu.device).contiguous()
+        ux_cut = be.mix(ux_stu, None, masks)                          # :389
+        with torch.no_grad():
+            lt = self.teacher_net.b2_forward(ux_tea, record=False)[0]             # :393
+        ls, state = self.student_net.b2_forward(ux_cut, record=True)              # :395
+        loss_mask = be.mix(um, None, masks)                           # :401  (um * mask)
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.consistency(lt, None, ls, None, loss_mask, self.cons_loss_fn, self.conf_thresh,
+                                   self.conf_per_pixel, ramp, self.cons_weight)
+        self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])
+        return out4
+
+    def step(self, sup_batch, unsup_batches, ramp_val=1.0):
+        """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
+        unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
+        mode) or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
+        {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising."""
+        self._zero_grad()                                              # :290
+        sup_loss = self.supervised(*sup_batch)
+        cons, conf = None, None
+        if self.cons_weight > 0.0:
+            for ub in unsup_batches:
+                if self.mask_mix:
+                    out4 = self.unsupervised_mix(ub['ux0_tea'], ub['ux0_stu'], ub['um0'], ub['ux1_tea'], ub['ux1_stu'],
+                                                 ub['um1'], ub['mask_params'], ramp_val)
+                else:
+                    out4 = self.unsupervised_cut(ub['ux_tea'], ub['ux_stu'], ub['um'], ub['mask_params'], ramp_val)
+                cons = out4[0] if cons is None else cons + out4[0]
+                conf = out4[1] if conf is None else conf + out4[1]
+        self._allreduce()
+        self.student_optim.step()                                      # :465
+        if self.teacher_optim is not None:
+            self.teacher_optim.step()                                  # :466-467
+        return {'sup_loss': sup_loss, 'cons_loss': cons, 'conf_rate': conf}

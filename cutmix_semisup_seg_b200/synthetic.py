@@ -1,0 +1,67 @@
+"""Synthetic stand-ins for the reference's DataLoader batches (tensor contract of SURVEY.md §8c/§8d):
+image fp32 (N,3,H,W) ~ N(0,1) (standardised images), labels int64 (N,1,H,W) with a 255 = ignore band,
+valid masks fp32 (N,1,H,W) in [0,1] with a zero border and a fractional ramp column, and CutMix box
+parameters from `mask_gen.BoxMaskGenerator` with a seeded numpy RandomState.  Used by bench.py, the smoke
+test and the `--dataset synthetic` mode of the entry point (there is no network access for real data)."""
+import numpy as np
+import torch
+
+
+def make_sup_batch(n, h, w, num_classes, seed, device='cpu', pin=False):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn((n, 3, h, w), generator=g)
+    labels = torch.randint(0, num_classes, (n, 1, h, w), generator=g, dtype=torch.int64)
+    labels[:, :, :min(8, h // 4)] = 255
+    if pin:
+        image, labels = image.pin_memory(), labels.pin_memory()
+    return image.to(device), labels.to(device)
+
+
+def make_valid_mask(n, h, w):
+    um = torch.ones((n, 1, h, w))
+    b = min(8, h // 8, w // 8)
+    if b > 0:
+        um[:, :, :b] = 0; um[:, :, -b:] = 0; um[:, :, :, :b] = 0; um[:, :, :, -b:] = 0
+    um[:, :, :, w // 2] *= 0.5
+    return um
+
+
+def make_unsup_batch(n, h, w, seed, mask_generator, mask_mix=True, compact_masks=True, paired=False, device='cpu',
+                     pin=False):
+    """Dict for MeanTeacherStep.step (mix mode: two views + mask params; cut mode: one view)."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(12345 + seed)
+    out = {}
+
+    def view():
+        tea = torch.randn((n, 3, h, w), generator=g)
+        stu = tea + 0.1 * torch.randn((n, 3, h, w), generator=g) if paired else tea
+        return tea, stu
+    if mask_mix:
+        out['ux0_tea'], out['ux0_stu'] = view()
+        out['ux1_tea'], out['ux1_stu'] = view()
+        out['um0'], out['um1'] = make_valid_mask(n, h, w), make_valid_mask(n, h, w)
+    else:
+        out['ux_tea'], out['ux_stu'] = view()
+        out['um'] = make_valid_mask(n, h, w)
+    if compact_masks:
+        out['mask_params'] = torch.from_numpy(mask_generator.generate_boxes(n, (h, w), rng=rng))
+    else:
+        out['mask_params'] = torch.from_numpy(mask_generator.generate_params(n, (h, w), rng=rng).astype(np.float32))
+    res = {}
+    cache = {}
+    for k, v in out.items():
+        if id(v) not in cache:
+            t = v.pin_memory() if pin else v
+            cache[id(v)] = t.to(device)
+        res[k] = cache[id(v)]
+    return res
+
+
+def condition_classifier(net, gain):
+    """Scale the last classification layer so that teacher soft-max confidences straddle the 0.97 threshold
+    on random inputs (random-init networks give conf_rate == 0, i.e. a vacuous consistency loss)."""
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if (name.startswith('layer5.') or 'classifier.classifier.6' in name) and p.dim() == 4:
+                p.mul_(gain)

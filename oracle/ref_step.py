@@ -1,0 +1,132 @@
+"""ORACLE — test infrastructure only (see oracle/torch_oracle.py header).
+
+Line-for-line CPU restatement of ONE iteration of the reference loop (train_seg_semisup_mask_mt.py:287-476)
+on top of the functional networks of torch_oracle.py: construction (:86-134), iteration prologue (:287-290),
+supervised branch (:296-301), mix (:309-369) / cut (:371-401) unsupervised branch, confidence + consistency
+loss (:406-459), optimiser and EMA steps (:465-467).  Pinned against the real reference modules by
+oracle/gen_golden.py (the reference's job function itself cannot run offline: datapipe needs skimage and
+real datasets).
+"""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch_oracle as TO  # noqa: E402
+
+
+def _is_bn_key(k):
+    return k.endswith(('.running_mean', '.running_var', '.num_batches_tracked'))
+
+
+def deeplab2_trainable(key):
+    """requires_grad of a DeepLab v2 state entry: conv weights / layer5 biases only (BN affine frozen,
+    deeplab2.py:72-84, 141-143, 167-168)."""
+    if _is_bn_key(key):
+        return False
+    if 'bn' in key.split('.')[-2] or '.downsample.1.' in key:
+        return False
+    return True
+
+
+def deeplab2_param_groups(sd):
+    """[pretrained (0.1 lr) with the reference's repetitions, new] — deeplab2.py:208-242.  A tensor under
+    `top` is yielded once per enclosing module of `top`'s module tree (modules() x parameters())."""
+    g0 = []
+    for k, v in sd.items():
+        if not deeplab2_trainable(k) or k.startswith('layer5.'):
+            continue
+        parts = k.split('.')[:-1]             # module path of the leaf module
+        g0.extend([v] * len(parts))           # conv1 -> 1, layerX.i.convY -> 3, layerX.i.downsample.0 -> 4
+    g1 = [v for k, v in sd.items() if k.startswith('layer5.') and not _is_bn_key(k)]
+    return g0, g1
+
+
+class OracleMeanTeacher(object):
+    """State + one-iteration function.  arch: 'deeplab2' | 'deeplab3plus'."""
+
+    def __init__(self, arch, state_dict, learning_rate, opt_type='adam', teacher_alpha=0.99, freeze_bn=True,
+                 cons_loss_fn='var', cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
+                 dtype=torch.float32):
+        self.arch, self.freeze_bn = arch, freeze_bn
+        self.cons_loss_fn, self.cons_weight = cons_loss_fn, cons_weight
+        self.conf_thresh, self.conf_per_pixel, self.rampup, self.mask_mix = conf_thresh, conf_per_pixel, rampup, mask_mix
+        self.teacher_alpha = teacher_alpha
+
+        def clone(sd):
+            return OrderedDict((k, (v.to(dtype) if v.dtype == torch.float32 else v).clone()) for k, v in sd.items())
+        self.student = clone(state_dict)
+        self.teacher = clone(state_dict)          # EMAWeightOptimizer.__init__ copies student -> teacher (:12-13)
+        if arch == 'deeplab2':
+            for k, v in self.student.items():
+                if deeplab2_trainable(k):
+                    v.requires_grad_(True)
+            g0, g1 = deeplab2_param_groups(self.student)
+        else:
+            for k, v in self.student.items():
+                if not _is_bn_key(k):
+                    v.requires_grad_(True)
+            g0, g1 = [], [v for k, v in self.student.items() if not _is_bn_key(k)]   # deeplab3plus.py:138-151
+        groups = [dict(params=g0, lr=learning_rate * 0.1), dict(params=g1, lr=learning_rate)]   # :90-93
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            if opt_type == 'adam':
+                self.optim = torch.optim.Adam(groups, foreach=False)
+            else:
+                self.optim = torch.optim.SGD(groups, momentum=0.9, nesterov=False, weight_decay=5e-4, foreach=False)
+
+    # ------------------------------------------------------------------------------------------
+    def _forward(self, sd, x, dropout_masks=None):
+        if self.arch == 'deeplab2':
+            return TO.deeplab2_forward(sd, x, bn_train=not self.freeze_bn)
+        # net.train() then freeze_batchnorm(): backbone BN eval, head BN train (:268-275, deeplab3plus.py:120-121)
+        return TO.deeplab3plus_forward(sd, x, backbone_bn_train=not self.freeze_bn, head_bn_train=True,
+                                       dropout_masks=dropout_masks)
+
+    def ema_step(self):
+        """optim_weight_ema.py:21-25 over every float state tensor (parameters and BN running statistics)."""
+        a = self.teacher_alpha
+        one_minus = 1.0 - a
+        with torch.no_grad():
+            for k, t in self.teacher.items():
+                if t.dtype.is_floating_point:
+                    t.mul_(a)
+                    t.add_(self.student[k].detach() * one_minus)
+
+    def step(self, sup_x, sup_y, unsup, ramp_val=1.0, drop=None):
+        """unsup: dict like cutmix_semisup_seg_b200.synthetic.make_unsup_batch with DENSE mask params
+        (N,1,H,W).  drop: optional dict of explicit dropout keep-masks (N,256,h,w) for the four forward passes:
+        {'sup','tea0','tea1','stu'}.  Returns python floats (sup_loss, cons_loss, conf_rate)."""
+        drop = drop or {}
+        self.optim.zero_grad()                                                      # :290
+        logits_sup = self._forward(self.student, sup_x, drop.get('sup'))            # :299
+        sup_loss = TO.supervised_loss(logits_sup, sup_y)                            # :300
+        sup_loss.backward()                                                         # :301
+        cons_val, conf_val = 0.0, 0.0
+        if self.cons_weight > 0.0:
+            m = unsup['mask_params']
+            if self.mask_mix:
+                ux_mixed = unsup['ux0_stu'] * (1 - m) + unsup['ux1_stu'] * m        # :350
+                um_mixed = unsup['um0'] * (1 - m) + unsup['um1'] * m                # :351
+                with torch.no_grad():                                               # :354-356
+                    l0 = self._forward(self.teacher, unsup['ux0_tea'], drop.get('tea0')).detach()
+                    l1 = self._forward(self.teacher, unsup['ux1_tea'], drop.get('tea1')).detach()
+                ls = self._forward(self.student, ux_mixed, drop.get('stu'))         # :358
+                loss, conf = TO.consistency_loss(l0, l1, ls, m, um_mixed, self.cons_loss_fn, self.conf_thresh,
+                                                 self.conf_per_pixel, ramp_val, self.rampup)
+            else:
+                ux_cut = unsup['ux_stu'] * m                                        # :389
+                with torch.no_grad():
+                    lt = self._forward(self.teacher, unsup['ux_tea'], drop.get('tea0')).detach()
+                ls = self._forward(self.student, ux_cut, drop.get('stu'))
+                loss, conf = TO.consistency_loss(lt, None, ls, None, m * unsup['um'], self.cons_loss_fn, self.conf_thresh,
+                                                 self.conf_per_pixel, ramp_val, self.rampup)
+            (loss * self.cons_weight).backward()                                    # :458-459
+            cons_val, conf_val = float(loss.detach()), float(conf)
+        self.optim.step()                                                           # :465
+        self.ema_step()                                                             # :466-467
+        return float(sup_loss.detach()), cons_val, conf_val

@@ -1,0 +1,242 @@
+"""ORACLE — test infrastructure only (never imported by the product path).
+
+A plain PyTorch fp32 (or fp64) CPU restatement of the reference's CutMix mean-teacher hot path, written
+functionally on top of a `state_dict`, so that it travels to the GPU box where /root/reference does
+not exist.  Each function cites the reference lines it follows.  It is pinned against the real reference
+(imported from /root/reference in the development container) by oracle/gen_golden.py, whose outputs are
+committed under tests/golden/ and re-checked by tests/test_oracle_golden.py.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# Building blocks
+# ----------------------------------------------------------------------------------------------
+def _bn(sd, prefix, x, train, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d forward; `train` selects batch statistics (and updates the running buffers in
+    place, like the module does)."""
+    return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'],
+                        sd[prefix + '.bias'], training=train, momentum=momentum, eps=eps)
+
+
+def _count_bn(sd, prefix, train):
+    if train:
+        sd[prefix + '.num_batches_tracked'] += 1
+
+
+# ----------------------------------------------------------------------------------------------
+# DeepLab v2 (reference architectures/deeplab2.py)
+# ----------------------------------------------------------------------------------------------
+_DL2_LAYERS = (('layer1', 64, 3, 1, 1), ('layer2', 128, 4, 2, 1), ('layer3', 256, 23, 1, 2), ('layer4', 512, 3, 1, 4))
+
+
+def deeplab2_forward(sd, x, bn_train=False):
+    """ResNetDeepLab.forward (deeplab2.py:183-206): stem, ceil-mode max-pool (:146), bottlenecks with the
+    stride on conv1 (:70) and dilated conv2 (:76-77), layer5 = conv(d=6) + conv(d=12) only (:124-128),
+    bilinear align_corners=True up-sampling to the input size (:204)."""
+    in_hw = x.shape[2:4]
+    t = F.conv2d(x, sd['conv1.weight'], stride=2, padding=3)
+    t = F.relu(_bn(sd, 'bn1', t, bn_train)); _count_bn(sd, 'bn1', bn_train)
+    t = F.max_pool2d(t, 3, 2, 1, ceil_mode=True)
+    for name, planes, blocks, stride, dil in _DL2_LAYERS:
+        for b in range(blocks):
+            p = '{}.{}'.format(name, b)
+            s = stride if b == 0 else 1
+            res = t
+            o = F.conv2d(t, sd[p + '.conv1.weight'], stride=s)
+            o = F.relu(_bn(sd, p + '.bn1', o, bn_train)); _count_bn(sd, p + '.bn1', bn_train)
+            o = F.conv2d(o, sd[p + '.conv2.weight'], padding=dil, dilation=dil)
+            o = F.relu(_bn(sd, p + '.bn2', o, bn_train)); _count_bn(sd, p + '.bn2', bn_train)
+            o = F.conv2d(o, sd[p + '.conv3.weight'])
+            o = _bn(sd, p + '.bn3', o, bn_train); _count_bn(sd, p + '.bn3', bn_train)
+            if (p + '.downsample.0.weight') in sd:
+                res = F.conv2d(t, sd[p + '.downsample.0.weight'], stride=s)
+                res = _bn(sd, p + '.downsample.1', res, bn_train); _count_bn(sd, p + '.downsample.1', bn_train)
+            t = F.relu(o + res)
+    out = F.conv2d(t, sd['layer5.conv2d_list.0.weight'], sd['layer5.conv2d_list.0.bias'], padding=6, dilation=6)
+    out = out + F.conv2d(t, sd['layer5.conv2d_list.1.weight'], sd['layer5.conv2d_list.1.bias'], padding=12, dilation=12)
+    return F.interpolate(out, size=in_hw, mode='bilinear', align_corners=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# DeepLab v3+ (reference architectures/deeplab3plus.py + torchvision ResNet-101 / ASPP)
+# ----------------------------------------------------------------------------------------------
+# torchvision resnet101(replace_stride_with_dilation=[False, True, True]): (name, planes, blocks, stride, first
+# block dilation, remaining blocks dilation)
+_DL3_LAYERS = (('layer1', 64, 3, 1, 1, 1), ('layer2', 128, 4, 2, 1, 1), ('layer3', 256, 23, 1, 1, 2),
+               ('layer4', 512, 3, 1, 2, 4))
+
+
+def deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dropout_masks=None, pre='deeplab.',
+                         aspp_rates=(12, 24, 36)):
+    """DeepLabv3Wrapper.forward -> DeepLabV3Plus.forward -> DeepLabHeadV3Plus.forward
+    (deeplab3plus.py:116-117, 73-78, 51-56) with torchvision's ASPP.  `dropout_masks`: list with one
+    (N,256,h,w) keep-mask for the ASPP Dropout(0.5) (None = dropout inactive)."""
+    in_hw = x.shape[2:4]
+    bb = pre + 'backbone.'
+    t = F.conv2d(x, sd[bb + 'conv1.weight'], stride=2, padding=3)
+    t = F.relu(_bn(sd, bb + 'bn1', t, backbone_bn_train)); _count_bn(sd, bb + 'bn1', backbone_bn_train)
+    t = F.max_pool2d(t, 3, 2, 1)
+    feats = {}
+    for name, planes, blocks, stride, d0, d1 in _DL3_LAYERS:
+        for b in range(blocks):
+            p = '{}{}.{}'.format(bb, name, b)
+            s = stride if b == 0 else 1
+            dil = d0 if b == 0 else d1
+            res = t
+            o = F.conv2d(t, sd[p + '.conv1.weight'])
+            o = F.relu(_bn(sd, p + '.bn1', o, backbone_bn_train)); _count_bn(sd, p + '.bn1', backbone_bn_train)
+            o = F.conv2d(o, sd[p + '.conv2.weight'], stride=s, padding=dil, dilation=dil)
+            o = F.relu(_bn(sd, p + '.bn2', o, backbone_bn_train)); _count_bn(sd, p + '.bn2', backbone_bn_train)
+            o = F.conv2d(o, sd[p + '.conv3.weight'])
+            o = _bn(sd, p + '.bn3', o, backbone_bn_train); _count_bn(sd, p + '.bn3', backbone_bn_train)
+            if (p + '.downsample.0.weight') in sd:
+                res = F.conv2d(t, sd[p + '.downsample.0.weight'], stride=s)
+                res = _bn(sd, p + '.downsample.1', res, backbone_bn_train); _count_bn(sd, p + '.downsample.1', backbone_bn_train)
+            t = F.relu(o + res)
+        feats[name] = t
+    hd = pre + 'classifier.'
+    tr = head_bn_train
+
+    def cbr(x_, cp, bp, **kw):
+        y = F.conv2d(x_, sd[cp + '.weight'], **kw)
+        y = F.relu(_bn(sd, bp, y, tr)); _count_bn(sd, bp, tr)
+        return y
+    low = cbr(feats['layer1'], hd + 'project.0', hd + 'project.1')
+    f = feats['layer4']
+    branches = [cbr(f, hd + 'aspp.convs.0.0', hd + 'aspp.convs.0.1')]
+    n_branches = 1 + len(aspp_rates)
+    for i in range(1, n_branches):
+        rate = aspp_rates[i - 1]
+        branches.append(cbr(f, hd + 'aspp.convs.{}.0'.format(i), hd + 'aspp.convs.{}.1'.format(i), padding=rate, dilation=rate))
+    pi = n_branches
+    pooled = F.adaptive_avg_pool2d(f, 1)
+    pooled = cbr(pooled, hd + 'aspp.convs.{}.1'.format(pi), hd + 'aspp.convs.{}.2'.format(pi))
+    branches.append(F.interpolate(pooled, size=f.shape[2:4], mode='bilinear', align_corners=False))
+    a = cbr(torch.cat(branches, dim=1), hd + 'aspp.project.0', hd + 'aspp.project.1')
+    if dropout_masks is not None:
+        a = a * dropout_masks[0] * 2.0            # nn.Dropout(0.5) in training mode
+    a = F.interpolate(a, size=low.shape[2:4], mode='bilinear', align_corners=False)
+    c = torch.cat([low, a], dim=1)
+    c = cbr(c, hd + 'classifier.0', hd + 'classifier.1', padding=1)
+    c = cbr(c, hd + 'classifier.3', hd + 'classifier.4', padding=1)
+    c = F.conv2d(c, sd[hd + 'classifier.6.weight'], sd[hd + 'classifier.6.bias'])
+    return F.interpolate(c, size=in_hw, mode='bilinear', align_corners=False)
+
+
+# ----------------------------------------------------------------------------------------------
+# Loss block (reference train_seg_semisup_mask_mt.py:363-367, 406-459) and CE (:126, :300)
+# ----------------------------------------------------------------------------------------------
+def consistency_loss(logits_tea0, logits_tea1, logits_stu, mix_mask, loss_mask, cons_loss_fn='var', conf_thresh=0.97,
+                     conf_per_pixel=False, ramp_val=1.0, rampup=-1):
+    """Returns (consistency_loss [what the reference logs, :461], conf_rate, loss tensor to back-propagate
+    before multiplication by cons_weight)."""
+    if logits_tea1 is not None:
+        logits_cons_tea = logits_tea0 * (1 - mix_mask) + logits_tea1 * mix_mask       # :363
+    else:
+        logits_cons_tea = logits_tea0
+    prob_tea = F.softmax(logits_cons_tea, dim=1)                                       # :366
+    prob_stu = F.softmax(logits_stu, dim=1)                                            # :367
+    n_classes = logits_stu.shape[1]
+    conf_rate = torch.tensor(float('nan'))
+    if conf_thresh > 0.0:                                                              # :407-418
+        conf_tea = prob_tea.max(dim=1)[0]
+        conf_mask = (conf_tea >= conf_thresh).float()[:, None, :, :]
+        conf_rate = conf_mask.mean()
+        if not conf_per_pixel:
+            conf_mask = conf_mask.mean()
+        loss_mask = loss_mask * conf_mask
+    if cons_loss_fn == 'var':                                                          # :428-431
+        d = prob_stu - prob_tea
+        q = (d * d).sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'logits_var':                                                 # :432-435
+        d = logits_stu - logits_cons_tea
+        q = (d * d).sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'logits_smoothl1':                                            # :436-439
+        q = F.smooth_l1_loss(logits_stu, logits_cons_tea, reduction='none').sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'bce':                                                        # :440-443
+        eps = 1e-6
+        q = -(prob_tea * torch.log(prob_stu + eps) + (1.0 - prob_tea) * torch.log(1.0 - prob_stu + eps))
+        q = q.sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'kld':                                                        # :444-446
+        q = F.kl_div(F.log_softmax(logits_stu, dim=1), prob_tea, reduction='none').sum(dim=1, keepdim=True)
+    else:
+        raise ValueError(cons_loss_fn)
+    loss = (q * loss_mask).mean()                                                      # :451
+    if rampup > 0:
+        loss = loss * ramp_val                                                         # :454-455
+    return loss, conf_rate
+
+
+def supervised_loss(logits, labels_n1hw):
+    """nn.CrossEntropyLoss(ignore_index=255)(logits, y[:, 0]) — :126, :300."""
+    return F.cross_entropy(logits, labels_n1hw[:, 0], ignore_index=255)
+
+
+# ----------------------------------------------------------------------------------------------
+# Bit-exact elementwise pieces (numpy float32, one rounding per operation)
+# ----------------------------------------------------------------------------------------------
+def ema_update(tgt, src, alpha):
+    """optim_weight_ema.py:21-25 on numpy float32 arrays: t*a then + s*(1-a), three roundings."""
+    a32 = np.float32(alpha)
+    oma32 = np.float32(1.0 - alpha)
+    return (tgt * a32).astype(np.float32) + (src * oma32).astype(np.float32)
+
+
+def mix(a, b, m):
+    """train_seg_semisup_mask_mt.py:350-351 (float32 numpy, separate roundings)."""
+    one_minus = (np.float32(1.0) - m).astype(np.float32)
+    return ((a * one_minus).astype(np.float32) + (b * m).astype(np.float32)).astype(np.float32)
+
+
+def box_masks(rect_boxes, shape, invert):
+    """mask_gen.py:110-116 toggle rasterisation from resolved integer boxes [y0,y1,x0,x1)."""
+    n = rect_boxes.shape[0]
+    out = np.zeros((n, 1) + tuple(shape), dtype=np.float32) if invert else np.ones((n, 1) + tuple(shape), dtype=np.float32)
+    for i in range(n):
+        for y0, y1, x0, x1 in rect_boxes[i]:
+            out[i, 0, y0:y1, x0:x1] = 1 - out[i, 0, y0:y1, x0:x1]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Deterministic synthetic weights: identical in every implementation
+# ----------------------------------------------------------------------------------------------
+def synth_state_dict(template, seed=0, logit_gain=1.0, final_keys=()):
+    """Fill a state_dict-shaped mapping {key: tensor} with well-conditioned synthetic values:
+    conv weights ~ N(0, 2/fan_in); BN gamma ~ U(0.5,1.5) (U(0.15,0.35) for the last BN of a residual unit and
+    for down-sample BNs so that activations stay O(1) through 33 residual units), beta ~ N(0,0.1),
+    running_mean ~ N(0,0.1), running_var ~ U(0.5,1.5), biases ~ N(0,0.1); `final_keys` weights are multiplied
+    by `logit_gain` so that teacher confidence straddles the threshold.  Every tensor has its own generator
+    (seed, key index) so values do not depend on iteration details."""
+    out = OrderedDict()
+    for i, (k, v) in enumerate(template.items()):
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        shape = tuple(v.shape)
+        if v.dtype != torch.float32:
+            out[k] = torch.zeros(shape, dtype=v.dtype)
+        elif k.endswith('running_mean'):
+            out[k] = torch.randn(shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            out[k] = torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            w = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+            if k in final_keys:
+                w = w * logit_gain
+            out[k] = w
+        elif k.endswith('.weight'):
+            if k.endswith('bn3.weight') or k.endswith('downsample.1.weight'):
+                out[k] = torch.rand(shape, generator=g) * 0.2 + 0.15
+            else:
+                out[k] = torch.rand(shape, generator=g) + 0.5
+        else:
+            out[k] = torch.randn(shape, generator=g) * 0.1
+    return out

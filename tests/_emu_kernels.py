@@ -1,0 +1,269 @@
+"""TEST DOUBLE — not part of the product.
+
+Mirrors cutmix_semisup_seg_b200.kernels.ActKernels with torch CPU math so that the engine's graph
+construction and hand-written backward tape (gradient accumulation, ReLU-gate / residual / BN-scale
+folding, concat slices, strided dgrad phases) can be unit-tested in the GPU-less container.  Nothing in
+the package imports this file; GPU tests exercise the real kernels.
+"""
+import torch
+import torch.nn.functional as F
+
+from cutmix_semisup_seg_b200.acts import Act
+
+DT = torch.float64
+
+
+def _v(a):
+    """(N,C,H,W) float64 copy of an Act's logical contents."""
+    return a.view4().permute(0, 3, 1, 2).to(DT)
+
+
+def _store(a, t_nchw, accumulate=False):
+    v = a.view4()
+    val = t_nchw.permute(0, 2, 3, 1).to(torch.float32)
+    if accumulate:
+        v += val
+    else:
+        v.copy_(val)
+
+
+def _w(w, cout, t, ldb, k):
+    """weights from raw storage (cout, t, ldb) -> (cout, t, k)."""
+    flat = torch.as_strided(w, (cout, t, ldb), (t * ldb, ldb, 1), storage_offset=w.storage_offset())
+    return flat[..., :k].to(DT)
+
+
+class EmuKernels(object):
+    name = 'emu'
+
+    def __init__(self):
+        self.calls = []
+
+    # ---- conv ---------------------------------------------------------------------------------
+    def conv_fwd(self, x, w, cout, kh, kw, cin, ldb, stride, pad, dil, out, scale=None, shift=None, addend=None,
+                 gate=None, relu=False):
+        self.calls.append('conv_fwd')
+        wt = _w(w, cout, kh * kw, ldb, cin).view(cout, kh, kw, cin).permute(0, 3, 1, 2)
+        xin = _v(x)
+        if x.h == 1 and x.n == 1 and kh == 1:        # flattened view
+            pass
+        y = F.conv2d(xin, wt, stride=stride, padding=pad, dilation=dil)
+        if scale is not None:
+            y = y * scale.to(DT).view(1, -1, 1, 1)
+        if shift is not None:
+            y = y + shift.to(DT).view(1, -1, 1, 1)
+        if addend is not None:
+            y = y + _v(addend)
+        if relu:
+            y = torch.relu(y)
+        if gate is not None:
+            y = y * (_v(gate) > 0)
+        _store(out, y)
+
+    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False):
+        self.calls.append('conv_dgrad')
+        w = _w(wt, cin, kh * kw, ldb, cout).view(cin, kh, kw, cout).permute(3, 0, 1, 2)   # (cout, cin, kh, kw)
+        gy = _v(g)
+        opad_h = dx.h - ((g.h - 1) * stride - 2 * pad + dil * (kh - 1) + 1)
+        opad_w = dx.w - ((g.w - 1) * stride - 2 * pad + dil * (kw - 1) + 1)
+        d = F.conv_transpose2d(gy, w, stride=stride, padding=pad, dilation=dil, output_padding=(opad_h, opad_w))
+        if addend is not None:
+            d = d + _v(addend)
+        if gate is not None:
+            d = d * (_v(gate) > 0)
+        _store(dx, d, accumulate)
+
+    def conv_wgrad(self, g, x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=None, accumulate=False):
+        self.calls.append('conv_wgrad')
+        xin = _v(x).requires_grad_(False)
+        with torch.enable_grad():
+            w = torch.zeros(cout, cin, kh, kw, dtype=DT, requires_grad=True)
+            y = F.conv2d(xin, w, stride=stride, padding=pad, dilation=dil)
+            y.backward(_v(g))
+        gw = w.grad.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        if row_scale is not None:
+            gw = gw * row_scale.to(DT).view(-1, 1, 1)
+        flat = torch.as_strided(dw, (cout, kh * kw, cin), (kh * kw * cin, cin, 1), storage_offset=dw.storage_offset())
+        if accumulate:
+            flat += gw.to(torch.float32)
+        else:
+            flat.copy_(gw.to(torch.float32))
+
+    def transpose_w(self, w, cout, t, cin, scale=None):
+        ldb = (cout + 3) // 4 * 4
+        src = _w(w, cout, t, cin, cin)
+        if scale is not None:
+            src = src * scale.to(DT).view(-1, 1, 1)
+        out = torch.zeros(cin, t, ldb)
+        out[..., :cout] = src.permute(2, 1, 0).to(torch.float32)
+        return out, ldb
+
+    # ---- other ops --------------------------------------------------------------------------------
+    def nchw_to_act(self, x_nchw, ld):
+        n, c, h, w = x_nchw.shape
+        out = Act.alloc(n, h, w, c, x_nchw.device, ld=ld)
+        out.base.zero_()
+        out.view4().copy_(x_nchw.permute(0, 2, 3, 1))
+        return out
+
+    def im2col(self, x, kh, kw, stride, pad, dil, oh, ow, kpad):
+        cols = F.unfold(_v(x), (kh, kw), dilation=dil, padding=pad, stride=stride)       # (N, C*kh*kw, L)
+        n = x.n
+        cols = cols.view(n, x.c, kh * kw, oh * ow).permute(0, 3, 2, 1).reshape(n * oh * ow, kh * kw * x.c)
+        col = Act.alloc(1, 1, n * oh * ow, kpad, x.device)
+        col.base.zero_()
+        col.base.view(-1, kpad)[:, :kh * kw * x.c] = cols.to(torch.float32)
+        return col
+
+    def maxpool_fwd(self, x, out, idx):
+        y, ind = F.max_pool2d(_v(x), 3, 2, 1, ceil_mode=False, return_indices=True) if False else (None, None)
+        xv = _v(x)
+        n, c, h, w = xv.shape
+        padded = F.pad(xv, (1, 2, 1, 2), value=float('-inf'))
+        best = torch.full((n, c, out.h, out.w), float('-inf'), dtype=DT)
+        bi = torch.zeros((n, c, out.h, out.w), dtype=torch.uint8)
+        for r in range(3):
+            for s in range(3):
+                cand = padded[:, :, r:r + 2 * out.h:2, s:s + 2 * out.w:2][:, :, :out.h, :out.w]
+                upd = cand > best
+                best = torch.where(upd, cand, best)
+                bi = torch.where(upd, torch.tensor(r * 3 + s, dtype=torch.uint8), bi)
+        _store(out, best)
+        idx.copy_(bi.permute(0, 2, 3, 1))
+
+    def maxpool_bwd(self, dy, idx, dx):
+        g = _v(dy)
+        n, c, oh, ow = g.shape
+        d = torch.zeros(n, c, dx.h + 3, dx.w + 3, dtype=DT)
+        ind = idx.permute(0, 3, 1, 2)
+        for r in range(3):
+            for s in range(3):
+                sel = (ind == r * 3 + s).to(DT) * g
+                d[:, :, r:r + 2 * oh:2, s:s + 2 * ow:2][:, :, :oh, :ow] += sel
+        _store(dx, d[:, :, 1:1 + dx.h, 1:1 + dx.w])
+
+    def bilinear_fwd(self, x, out, align_corners):
+        _store(out, F.interpolate(_v(x), size=(out.h, out.w), mode='bilinear', align_corners=bool(align_corners)))
+
+    def bilinear_fwd_nchw(self, x, out_nchw, align_corners):
+        out_nchw.copy_(F.interpolate(_v(x), size=out_nchw.shape[2:4], mode='bilinear', align_corners=bool(align_corners)))
+
+    def _bil_bwd(self, g_nchw, dx, align_corners, mul, accumulate):
+        with torch.enable_grad():
+            xz = torch.zeros(dx.n, dx.c, dx.h, dx.w, dtype=DT, requires_grad=True)
+            y = F.interpolate(xz, size=g_nchw.shape[2:4], mode='bilinear', align_corners=bool(align_corners))
+            y.backward(g_nchw.to(DT) * mul)
+        _store(dx, xz.grad, accumulate)
+
+    def bilinear_bwd(self, dy, dx, align_corners, accumulate=False):
+        self._bil_bwd(_v(dy), dx, align_corners, 1.0, accumulate)
+
+    def bilinear_bwd_nchw(self, dy_nchw, dx, align_corners, scale_dev=None, scale_host=1.0, accumulate=False):
+        mul = (float(scale_dev[0]) if scale_dev is not None else 1.0) * scale_host
+        self._bil_bwd(dy_nchw, dx, align_corners, mul, accumulate)
+
+    def gap_fwd(self, x, out):
+        _store(out, _v(x).mean(dim=(2, 3), keepdim=True))
+
+    def gap_bwd(self, dy, dx, accumulate=False):
+        _store(dx, (_v(dy) / (dx.h * dx.w)).expand(dx.n, dx.c, dx.h, dx.w), accumulate)
+
+    def bcast_fwd(self, v, out):
+        _store(out, _v(v).expand(out.n, out.c, out.h, out.w))
+
+    def bcast_bwd(self, dy, dv):
+        _store(dv, _v(dy).sum(dim=(2, 3), keepdim=True))
+
+    def bn_stats(self, x, eps, momentum, mean, rstd, running_mean, running_var):
+        xv = _v(x)
+        m = xv.mean(dim=(0, 2, 3)); var = xv.var(dim=(0, 2, 3), unbiased=False)
+        mean.copy_(m.to(torch.float32)); rstd.copy_((1.0 / torch.sqrt(var + eps)).to(torch.float32))
+        n = x.rows
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(momentum * m.to(torch.float32))
+            unb = var * n / (n - 1) if n > 1 else var
+            running_var.mul_(1 - momentum).add_(momentum * unb.to(torch.float32))
+
+    def bn_apply(self, x, mean, rstd, gamma, beta, relu, dropmask, drop_scale, out, residual=None):
+        sh = (1, -1, 1, 1)
+        y = (_v(x) - mean.to(DT).view(sh)) * rstd.to(DT).view(sh) * gamma.to(DT).view(sh) + beta.to(DT).view(sh)
+        if residual is not None:
+            y = y + _v(residual)
+        if relu:
+            y = torch.relu(y)
+        if dropmask is not None:
+            y = y * dropmask.permute(0, 3, 1, 2).to(DT) * drop_scale
+        _store(out, y)
+
+    def bn_bwd(self, dy, x, y, mean, rstd, gamma, relu, dropmask, drop_scale, dx, dgamma, dbeta, accumulate_params, g_out=None):
+        sh = (1, -1, 1, 1)
+        g = _v(dy)
+        if relu:
+            g = g * (_v(y) > 0)
+        if dropmask is not None:
+            g = g * dropmask.permute(0, 3, 1, 2).to(DT) * drop_scale
+        if g_out is not None:
+            _store(g_out, g)
+        xhat = (_v(x) - mean.to(DT).view(sh)) * rstd.to(DT).view(sh)
+        n = x.rows
+        db = g.sum(dim=(0, 2, 3)); dg = (g * xhat).sum(dim=(0, 2, 3))
+        d = gamma.to(DT).view(sh) * rstd.to(DT).view(sh) * (g - db.view(sh) / n - xhat * dg.view(sh) / n)
+        _store(dx, d)
+        for tgt, val in ((dgamma, dg), (dbeta, db)):
+            if tgt is not None:
+                if accumulate_params:
+                    tgt += val.to(torch.float32)
+                else:
+                    tgt.copy_(val.to(torch.float32))
+
+    def bn_fold(self, gamma, beta, mean, var, eps, scale, shift):
+        s = gamma / torch.sqrt(var + eps)
+        scale.copy_(s); shift.copy_(beta - mean * s)
+
+    def bn_eval_param_grad(self, g, y, gamma, beta, sub, dgamma, dbeta, accumulate):
+        gv = _v(g); yv = _v(y)
+        if sub is not None:
+            yv = yv - _v(sub)
+        sg = gv.sum(dim=(0, 2, 3)); sgy = (gv * yv).sum(dim=(0, 2, 3))
+        dg = (sgy - beta.to(DT) * sg) / gamma.to(DT)
+        for tgt, val in ((dgamma, dg), (dbeta, sg)):
+            if accumulate:
+                tgt += val.to(torch.float32)
+            else:
+                tgt.copy_(val.to(torch.float32))
+
+    def colsum(self, g, out, accumulate):
+        v = _v(g).sum(dim=(0, 2, 3)).to(torch.float32)
+        if accumulate:
+            out += v
+        else:
+            out.copy_(v)
+
+    def relu_gate(self, g, y):
+        v = g.view4()
+        v.mul_((y.view4() > 0).to(v.dtype))
+
+    def copy_act(self, dst, src, accumulate=False):
+        if accumulate:
+            dst.view4().add_(src.view4())
+        else:
+            dst.view4().copy_(src.view4())
+
+    def fill_act(self, a, value):
+        a.view4().fill_(value)
+
+    def dropout_mask(self, n, h, w, c, p, seed, offset, device):
+        g = torch.Generator().manual_seed((seed + offset) % (2 ** 31))
+        return (torch.rand((n, h, w, c), generator=g) >= p).float()
+
+    @staticmethod
+    def empty(shape, device, dtype=torch.float32):
+        return torch.empty(shape, device=device, dtype=dtype)
+
+    def copy_rows(self, dst, ldd, src, lds, rows, c, accumulate=False):
+        d = torch.as_strided(dst, (rows, c), (ldd, 1), storage_offset=dst.storage_offset())
+        s_ = torch.as_strided(src, (rows, c), (lds, 1), storage_offset=src.storage_offset())
+        if accumulate:
+            d += s_
+        else:
+            d.copy_(s_)
