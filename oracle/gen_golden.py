@@ -1,0 +1,210 @@
+"""Generates tests/golden/*.json|npz by running the UNMODIFIED reference (imported from /root/reference, which
+only exists in the development container) — the committed fixtures pin oracle/ and the product on the GPU box.
+
+    cd /tmp && python /root/repo/oracle/gen_golden.py            # writes into /root/repo/tests/golden
+
+Contents
+  masks.json        BoxMaskGenerator.generate_params known answers (sha256 of the float32 bytes, means, sums)
+  state_dicts.json  state_dict keys / shapes / dtypes of the two hot-path architectures + optimiser group sizes
+  net_dl2.npz, net_dl3.npz   logits and per-parameter gradient checksums of the reference modules on seeded
+                    synthetic weights / inputs (small crops)
+  iteration.json    two full iterations of the loop body (train_seg_semisup_mask_mt.py:287-476) driven with the
+                    reference modules, reference EMAWeightOptimizer, torch Adam on the reference param groups
+  loss_block.json   known answers for the consistency / CE block recorded in SURVEY.md §8c
+"""
+import hashlib
+import json
+import os
+import sys
+import warnings
+
+REF = os.environ.get('CUTMIX_REF', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+sys.path.insert(0, REF)            # reference packages: architectures, mask_gen, optim_weight_ema
+sys.path.insert(1, HERE)           # torch_oracle (synthetic weights, shared with the tests)
+warnings.filterwarnings('ignore')
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import mask_gen  # noqa: E402  (reference)
+import optim_weight_ema  # noqa: E402  (reference)
+from architectures import network_architectures  # noqa: E402  (reference)
+import torch_oracle as TO  # noqa: E402
+
+assert os.path.realpath(mask_gen.__file__).startswith(os.path.realpath(REF)), 'reference not first on sys.path'
+
+MASK_CASES = [
+    (dict(prop_range=0.5, invert=True), 16, (512, 512), 12345),
+    (dict(prop_range=0.5, invert=True), 10, (321, 321), 12345),
+    (dict(prop_range=(0.0, 1.0), invert=True), 10, (321, 321), 12345),
+    (dict(prop_range=(0.25, 0.5), n_boxes=3, random_aspect_ratio=False, prop_by_area=False, within_bounds=False,
+          invert=False), 4, (64, 48), 7),
+    (dict(prop_range=0.5, invert=True), 2, (8, 8), 0),
+    (dict(prop_range=(0.1, 0.9), n_boxes=2, random_aspect_ratio=False, prop_by_area=True, within_bounds=False,
+          invert=True), 6, (33, 47), 3),
+    (dict(prop_range=(0.0, 0.3), n_boxes=4, random_aspect_ratio=True, prop_by_area=False, within_bounds=True,
+          invert=False), 5, (20, 31), 5),
+    (dict(prop_range=(0.5, 1.0), n_boxes=2, random_aspect_ratio=True, prop_by_area=True, within_bounds=False,
+          invert=False), 7, (17, 9), 11),
+]
+
+
+def gen_masks():
+    out = []
+    for kw, n, shape, seed in MASK_CASES:
+        m = mask_gen.BoxMaskGenerator(**kw).generate_params(n, shape, rng=np.random.RandomState(seed))
+        m32 = m.astype(np.float32)
+        rec = dict(kwargs={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, n=n, shape=list(shape), seed=seed,
+                   dtype=str(m.dtype), mean=float(m.mean()), sums=[float(s) for s in m.reshape(n, -1).sum(axis=1)],
+                   sha256=hashlib.sha256(m32.tobytes()).hexdigest())
+        if m.size <= 4096:
+            rec['mask'] = m32.reshape(n, -1).astype(int).tolist()
+        out.append(rec)
+    json.dump(out, open(os.path.join(OUT, 'masks.json'), 'w'), indent=1)
+
+
+def build(kind, classes, seed, gain=1.0):
+    net = network_architectures.seg.get(kind)(classes, pretrained=False)
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    sd = TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
+    net.load_state_dict(sd)
+    return net
+
+
+def gen_state_dicts():
+    out = {}
+    for kind, classes in (('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19)):
+        net = network_architectures.seg.get(kind)(classes, pretrained=False)
+        out[kind] = dict(classes=classes,
+                         entries=[[k, list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in net.state_dict().items()],
+                         n_pretrained=len(list(net.pretrained_parameters())),
+                         n_pretrained_unique=len(set(id(p) for p in net.pretrained_parameters())),
+                         n_new=len(list(net.new_parameters())),
+                         trainable=[k for k, p in net.named_parameters() if p.requires_grad],
+                         registry_names=sorted(network_architectures.seg.names()))
+    json.dump(out, open(os.path.join(OUT, 'state_dicts.json'), 'w'))
+
+
+def gen_nets():
+    for tag, kind, classes, (n, h, w) in (('dl2', 'resnet101_deeplab_imagenet', 21, (2, 33, 41)),
+                                         ('dl3', 'resnet101_deeplabv3plus_imagenet', 19, (3, 33, 41))):
+        net = build(kind, classes, seed=1)
+        net.train()
+        net.freeze_batchnorm()
+        for m in net.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn((n, 3, h, w), generator=g)
+        dy = torch.randn((n, classes, h, w), generator=g)
+        y = net(x)
+        y.backward(dy)
+        names, gsum, gabs = [], [], []
+        for k, p in net.named_parameters():
+            if p.grad is not None:
+                names.append(k); gsum.append(float(p.grad.double().sum())); gabs.append(float(p.grad.double().abs().sum()))
+        running = {k: v.numpy() for k, v in net.state_dict().items() if 'classifier.project.1.running' in k}
+        np.savez_compressed(os.path.join(OUT, 'net_%s.npz' % tag), x=x.numpy(), dy=dy.numpy(), logits=y.detach().numpy(),
+                            grad_names=np.array(names), grad_sum=np.array(gsum), grad_abs=np.array(gabs), **running)
+
+
+def gen_iteration():
+    """Two iterations of the reference loop body with the reference's own classes (DeepLab v2, frozen BN, Adam
+    on [pretrained x0.1 (with duplicates), new], EMA 0.99, CutMix var loss, conf_thresh 0.6)."""
+    kind, classes, n, h, w, lr = 'resnet101_deeplab_imagenet', 21, 2, 33, 33, 3e-5
+    student = build(kind, classes, seed=3, gain=20.0)
+    teacher = network_architectures.seg.get(kind)(classes, pretrained=False)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=lr * 0.1),
+                              dict(params=student.new_parameters(), lr=lr)], foreach=False)
+    ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+    mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
+                                   within_bounds=True, invert=True)
+    crit = nn.CrossEntropyLoss(ignore_index=255)
+    rec = dict(kind=kind, classes=classes, n=n, h=h, w=w, lr=lr, conf_thresh=0.6, seed=3, gain=20.0, steps=[])
+    for it in range(2):
+        g = torch.Generator().manual_seed(100 + it)
+        sup_x = torch.randn((n, 3, h, w), generator=g)
+        sup_y = torch.randint(0, classes, (n, 1, h, w), generator=g); sup_y[:, :, :4] = 255
+        ux0 = torch.randn((n, 3, h, w), generator=g); ux1 = torch.randn((n, 3, h, w), generator=g)
+        um0 = torch.ones((n, 1, h, w)); um0[:, :, :3] = 0; um1 = torch.ones((n, 1, h, w)); um1[:, :, :, 16] = 0.5
+        masks = torch.tensor(mg.generate_params(n, (h, w), rng=np.random.RandomState(7 + it)).astype(np.float32))
+        student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()     # :268-275
+        optim.zero_grad()                                                                           # :290
+        sup_loss = crit(student(sup_x), sup_y[:, 0]); sup_loss.backward()                            # :299-301
+        ux_mixed = ux0 * (1 - masks) + ux1 * masks; um_mixed = um0 * (1 - masks) + um1 * masks       # :350-351
+        with torch.no_grad():
+            l0 = teacher(ux0).detach(); l1 = teacher(ux1).detach()                                   # :354-356
+        ls = student(ux_mixed)                                                                       # :358
+        lt = l0 * (1 - masks) + l1 * masks                                                           # :363
+        pt = F.softmax(lt, dim=1); ps = F.softmax(ls, dim=1)                                         # :366-367
+        conf = (pt.max(dim=1)[0] >= 0.6).float()[:, None]                                            # :409-411
+        conf_rate = float(conf.mean())
+        loss_mask = um_mixed * conf.mean()                                                           # :415-418
+        d = ps - pt
+        cons = ((d * d).sum(dim=1, keepdim=True) * loss_mask).mean()                                 # :429-431, :451
+        (cons * 1.0).backward()                                                                      # :458-459
+        optim.step(); ema.step()                                                                     # :465-467
+        tsd, ssd = teacher.state_dict(), student.state_dict()
+        rec['steps'].append(dict(sup_loss=float(sup_loss), cons_loss=float(cons), conf_rate=conf_rate,
+                                 teacher_abs_sum=float(sum(v.double().abs().sum() for v in tsd.values() if v.dtype == torch.float32)),
+                                 student_abs_sum=float(sum(v.double().abs().sum() for v in ssd.values() if v.dtype == torch.float32)),
+                                 student_conv1_sum=float(ssd['conv1.weight'].double().sum()),
+                                 student_l3_sum=float(ssd['layer3.5.conv2.weight'].double().sum()),
+                                 student_l5_sum=float(ssd['layer5.conv2d_list.0.weight'].double().sum()),
+                                 teacher_l5_sum=float(tsd['layer5.conv2d_list.1.weight'].double().sum())))
+    json.dump(rec, open(os.path.join(OUT, 'iteration.json'), 'w'), indent=1)
+
+
+def gen_loss_block():
+    """SURVEY.md §8c recipe evaluated with the reference formulas (:363-451) -> known answers."""
+    torch.manual_seed(0)
+    N, C, H, W = 2, 5, 6, 6
+    l0 = torch.randn(N, C, H, W) * 4; l1 = torch.randn(N, C, H, W) * 4; ls0 = torch.randn(N, C, H, W) * 4
+    um0 = torch.ones(N, 1, H, W); um1 = torch.ones(N, 1, H, W); um0[:, :, 0] = 0; um1[:, :, :, 0] = 0.5
+    m = torch.tensor(mask_gen.BoxMaskGenerator(0.5, invert=True).generate_params(N, (H, W), rng=np.random.RandomState(0)).astype(np.float32))
+    tau = 0.6
+    out = dict(recipe='SURVEY.md 8c', mask_sums=[float(s) for s in m.reshape(N, -1).sum(1)], cases={})
+    root_c = C ** 0.5
+    for fn in ('var', 'logits_var', 'logits_smoothl1', 'bce', 'kld'):
+        for pp in (False, True):
+            ls = ls0.clone().requires_grad_(True)
+            lt = l0 * (1 - m) + l1 * m
+            um = um0 * (1 - m) + um1 * m
+            pt = F.softmax(lt, dim=1); ps = F.softmax(ls, dim=1)
+            conf = (pt.max(dim=1)[0] >= tau).float()[:, None]
+            lm = um * (conf if pp else conf.mean())
+            if fn == 'var':
+                q = ((ps - pt) ** 2).sum(dim=1, keepdim=True)
+            elif fn == 'logits_var':
+                q = ((ls - lt) ** 2).sum(dim=1, keepdim=True) / root_c
+            elif fn == 'logits_smoothl1':
+                q = F.smooth_l1_loss(ls, lt, reduction='none').sum(dim=1, keepdim=True) / root_c
+            elif fn == 'bce':
+                q = network_architectures.robust_binary_crossentropy(ps, pt).sum(dim=1, keepdim=True)
+            else:
+                q = F.kl_div(F.log_softmax(ls, dim=1), pt, reduction='none').sum(dim=1, keepdim=True)
+            loss = (q * lm).mean(); loss.backward()
+            out['cases']['%s_pp%d' % (fn, int(pp))] = dict(loss=float(loss), grad_l1=float(ls.grad.abs().sum()), conf_rate=float(conf.mean()))
+    torch.manual_seed(1)
+    lg = (torch.randn(2, 5, 6, 6) * 2).requires_grad_(True)
+    y = torch.randint(0, 5, (2, 1, 6, 6)); y[:, :, 0] = 255
+    ce = nn.CrossEntropyLoss(ignore_index=255)(lg, y[:, 0]); ce.backward()
+    out['ce'] = dict(loss=float(ce), grad_l1=float(lg.grad.abs().sum()), n_valid=int((y != 255).sum()))
+    out['sigmoid_rampup_3_10'] = network_architectures.sigmoid_rampup(3, 10)
+    # EMA known answer on 1,000,003 random elements (reference class on bare modules)
+    json.dump(out, open(os.path.join(OUT, 'loss_block.json'), 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    gen_masks(); print('masks')
+    gen_state_dicts(); print('state dicts')
+    gen_loss_block(); print('loss block')
+    gen_nets(); print('nets')
+    gen_iteration(); print('iteration')

@@ -1,0 +1,116 @@
+"""Host-logic test of the engine (graph construction + hand-written backward tape) without a GPU.
+
+The product has a single kernel provider (the CUDA extension).  Here it is swapped for tests/_emu_kernels.py —
+a torch-CPU double of the kernel INTERFACE — so that gradient bookkeeping (ReLU-gate / residual / BN-scale
+folding into dgrad epilogues, concat slices, strided-dgrad phases, parameter-gradient accumulation) is checked
+against autograd on the oracle's functional networks.  The numerical parity of the real kernels is covered by the
+`-m gpu` tests."""
+import os
+import sys
+from collections import OrderedDict
+
+import pytest
+import torch
+
+HERE = os.path.dirname(__file__)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'oracle'))
+import torch_oracle as TO  # noqa: E402
+from _emu_kernels import EmuKernels  # noqa: E402
+from architectures import network_architectures as na  # noqa: E402
+from cutmix_semisup_seg_b200 import netbase  # noqa: E402
+
+
+@pytest.fixture()
+def emu():
+    saved = netbase.get_kernels
+    k = EmuKernels()
+    netbase.set_kernels_factory(lambda n_split=1: k)
+    yield k
+    netbase.set_kernels_factory(saved)
+
+
+def _run(kind, n, h, w, classes, freeze, seed):
+    torch.manual_seed(seed)
+    net = na.seg.get(kind)(classes, pretrained=False)
+    sd = TO.synth_state_dict(net.state_dict(), seed=seed)
+    net.load_state_dict(sd)
+    net.train()
+    if freeze:
+        net.freeze_batchnorm()
+    dm = None
+    for m in net.modules():
+        if type(m).__name__ == 'B2Dropout':
+            dm = (torch.rand(n, -(-h // 8), -(-w // 8), 256) > 0.5).float()
+            m.inject([dm])
+    x = torch.randn(n, 3, h, w)
+    y = net(x)
+    dy = torch.randn(y.shape)
+    y.backward(dy)
+    sd64 = OrderedDict((k, v.double().clone() if v.dtype == torch.float32 else v.clone()) for k, v in sd.items())
+    for k, p in net.named_parameters():
+        if p.requires_grad:
+            sd64[k].requires_grad_(True)
+    if 'v3plus' in kind:
+        yo = TO.deeplab3plus_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
+                                     dropout_masks=[dm.permute(0, 3, 1, 2).double()])
+    else:
+        yo = TO.deeplab2_forward(sd64, x.double(), bn_train=not freeze)
+    yo.backward(dy.double())
+    errs = []
+    for k, p in net.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        g = sd64[k].grad
+        if g is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, 'missing gradient for ' + k
+        assert p.grad.stride() == p.stride()
+        errs.append((p.grad.double() - g).abs().max().item() / (g.abs().max().item() + 1e-30))
+    lerr = (y.detach().double() - yo.detach()).abs().max().item() / yo.abs().max().item()
+    stat = max((v.double() - sd64[k].detach()).abs().max().item() for k, v in net.state_dict().items() if 'running' in k)
+    return lerr, sorted(errs), stat, net
+
+
+def test_deeplab2_frozen_bn_matches_autograd(emu):
+    lerr, errs, stat, net = _run('resnet101_deeplab_imagenet', 2, 33, 41, 21, True, seed=1)
+    assert lerr < 1e-5
+    assert len(errs) == 108 and errs[-1] < 1e-4          # 104 backbone convs + 2 used layer5 convs (w, b)
+    assert stat == 0.0                                   # frozen BN must not touch the running statistics
+    assert emu.calls.count('conv_fwd') == 106            # layer5.conv2d_list.2/3 are never executed
+
+
+def test_deeplab3plus_frozen_backbone_train_head(emu):
+    lerr, errs, stat, net = _run('resnet101_deeplabv3plus_imagenet', 3, 33, 41, 19, True, seed=2)
+    assert lerr < 1e-4
+    assert len(errs) == 341
+    assert errs[len(errs) // 2] < 1e-3 and errs[-1] < 5e-2      # train-mode BN over tiny maps is ill-conditioned
+    assert stat < 1e-4
+    nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
+    assert nb['deeplab.classifier.project.1.num_batches_tracked'] == 1
+    assert nb['deeplab.backbone.bn1.num_batches_tracked'] == 0
+
+
+def test_gradient_accumulation_over_two_backward_passes(emu):
+    torch.manual_seed(0)
+    net = na.seg.get('resnet101_deeplab_imagenet')(5, pretrained=False)
+    net.load_state_dict(TO.synth_state_dict(net.state_dict(), seed=4))
+    net.train(); net.freeze_batchnorm()
+    x = torch.randn(1, 3, 17, 17)
+    dy = torch.randn(1, 5, 17, 17)
+    net(x).backward(dy)
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    net(x).backward(dy)
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, 2 * g1[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_eval_mode_forward_has_no_tape(emu):
+    net = na.seg.get('resnet101_deeplabv3plus_imagenet')(3, pretrained=False)
+    net.eval()
+    with torch.no_grad():
+        y = net(torch.randn(1, 3, 17, 17))
+    assert y.shape == (1, 3, 17, 17) and not y.requires_grad

@@ -1,0 +1,117 @@
+"""Pins the oracle (oracle/torch_oracle.py, oracle/ref_step.py) to the golden vectors generated from the
+unmodified reference by oracle/gen_golden.py."""
+import json
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(__file__)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'oracle'))
+import torch_oracle as TO  # noqa: E402
+import ref_step  # noqa: E402
+import mask_gen  # noqa: E402
+from architectures import network_architectures as na  # noqa: E402
+
+G = os.path.join(HERE, 'golden')
+
+
+def _synth(kind, classes, seed, gain=1.0):
+    net = na.seg.get(kind)(classes, pretrained=False)
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    return net, TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
+
+
+def test_loss_block_known_answers():
+    gold = json.load(open(os.path.join(G, 'loss_block.json')))
+    torch.manual_seed(0)
+    N, C, H, W = 2, 5, 6, 6
+    l0 = torch.randn(N, C, H, W) * 4; l1 = torch.randn(N, C, H, W) * 4; ls0 = torch.randn(N, C, H, W) * 4
+    um0 = torch.ones(N, 1, H, W); um1 = torch.ones(N, 1, H, W); um0[:, :, 0] = 0; um1[:, :, :, 0] = 0.5
+    m = torch.tensor(mask_gen.BoxMaskGenerator(0.5, invert=True).generate_params(N, (H, W), rng=np.random.RandomState(0)).astype(np.float32))
+    assert [float(s) for s in m.reshape(N, -1).sum(1)] == gold['mask_sums']
+    um = um0 * (1 - m) + um1 * m
+    for key, exp in gold['cases'].items():
+        fn, pp = key.rsplit('_pp', 1)
+        ls = ls0.clone().requires_grad_(True)
+        loss, conf = TO.consistency_loss(l0, l1, ls, m, um, fn, 0.6, bool(int(pp)))
+        loss.backward()
+        assert float(loss) == pytest.approx(exp['loss'], rel=1e-6)
+        assert float(ls.grad.abs().sum()) == pytest.approx(exp['grad_l1'], rel=1e-6)
+        assert float(conf) == pytest.approx(exp['conf_rate'], rel=1e-7)
+    torch.manual_seed(1)
+    lg = (torch.randn(2, 5, 6, 6) * 2).requires_grad_(True)
+    y = torch.randint(0, 5, (2, 1, 6, 6)); y[:, :, 0] = 255
+    ce = TO.supervised_loss(lg, y); ce.backward()
+    assert float(ce) == pytest.approx(gold['ce']['loss'], rel=1e-6)
+    assert float(lg.grad.abs().sum()) == pytest.approx(gold['ce']['grad_l1'], rel=1e-6)
+    assert na.sigmoid_rampup(3, 10) == pytest.approx(gold['sigmoid_rampup_3_10'], rel=1e-12)
+
+
+@pytest.mark.parametrize('tag,kind,classes', [('dl2', 'resnet101_deeplab_imagenet', 21),
+                                               ('dl3', 'resnet101_deeplabv3plus_imagenet', 19)])
+def test_functional_nets_match_reference_modules(tag, kind, classes):
+    """Forward logits and parameter gradients of the functional oracle == the reference nn.Modules."""
+    z = np.load(os.path.join(G, 'net_%s.npz' % tag))
+    net, sd = _synth(kind, classes, seed=1)
+    for k, p in net.named_parameters():
+        if p.requires_grad:
+            sd[k].requires_grad_(True)
+    x = torch.from_numpy(z['x'])
+    if tag == 'dl2':
+        y = TO.deeplab2_forward(sd, x)
+    else:
+        y = TO.deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_masks=None)
+    assert np.abs(y.detach().numpy() - z['logits']).max() <= 1e-5 * np.abs(z['logits']).max()
+    y.backward(torch.from_numpy(z['dy']))
+    names = [str(n) for n in z['grad_names']]
+    assert names == [k for k, p in net.named_parameters() if sd[k].grad is not None]
+    gabs = np.array([float(sd[k].grad.double().abs().sum()) for k in names])
+    assert np.allclose(gabs, z['grad_abs'], rtol=2e-3, atol=1e-6)
+    if tag == 'dl3':
+        for k in ('deeplab.classifier.project.1.running_mean', 'deeplab.classifier.project.1.running_var'):
+            assert np.allclose(sd[k].numpy(), z[k], rtol=1e-5, atol=1e-6)
+
+
+def test_iteration_matches_reference_loop():
+    """Two iterations of the oracle's loop body == the reference classes driven by the same loop (Adam with the
+    duplicated parameter group, EMA incl. BN buffers, CutMix var loss)."""
+    gold = json.load(open(os.path.join(G, 'iteration.json')))
+    n, h, w, c = gold['n'], gold['h'], gold['w'], gold['classes']
+    net, sd = _synth(gold['kind'], c, seed=gold['seed'], gain=gold['gain'])
+    tr = ref_step.OracleMeanTeacher('deeplab2', sd, gold['lr'], conf_thresh=gold['conf_thresh'])
+    assert [len(g['params']) for g in tr.optim.param_groups] == [314, 8]
+    mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
+                                   within_bounds=True, invert=True)
+    for it, exp in enumerate(gold['steps']):
+        g = torch.Generator().manual_seed(100 + it)
+        sup_x = torch.randn((n, 3, h, w), generator=g)
+        sup_y = torch.randint(0, c, (n, 1, h, w), generator=g); sup_y[:, :, :4] = 255
+        ux0 = torch.randn((n, 3, h, w), generator=g); ux1 = torch.randn((n, 3, h, w), generator=g)
+        um0 = torch.ones((n, 1, h, w)); um0[:, :, :3] = 0; um1 = torch.ones((n, 1, h, w)); um1[:, :, :, 16] = 0.5
+        masks = torch.tensor(mg.generate_params(n, (h, w), rng=np.random.RandomState(7 + it)).astype(np.float32))
+        uns = dict(ux0_tea=ux0, ux0_stu=ux0, ux1_tea=ux1, ux1_stu=ux1, um0=um0, um1=um1, mask_params=masks)
+        s, cl, cr = tr.step(sup_x, sup_y, uns)
+        assert s == pytest.approx(exp['sup_loss'], rel=1e-5)
+        assert cl == pytest.approx(exp['cons_loss'], rel=2e-3, abs=1e-9)
+        assert cr == pytest.approx(exp['conf_rate'], abs=1e-6)
+        assert float(tr.student['conv1.weight'].double().sum()) == pytest.approx(exp['student_conv1_sum'], rel=1e-5)
+        assert float(tr.student['layer3.5.conv2.weight'].double().sum()) == pytest.approx(exp['student_l3_sum'], rel=1e-5)
+        assert float(tr.student['layer5.conv2d_list.0.weight'].double().sum()) == pytest.approx(exp['student_l5_sum'], rel=1e-5)
+        assert float(tr.teacher['layer5.conv2d_list.1.weight'].double().sum()) == pytest.approx(exp['teacher_l5_sum'], rel=1e-5)
+        tsum = float(sum(v.double().abs().sum() for v in tr.teacher.values() if v.dtype == torch.float32))
+        assert tsum == pytest.approx(exp['teacher_abs_sum'], rel=1e-7)
+
+
+def test_bit_exact_elementwise_oracles():
+    rs = np.random.RandomState(0)
+    t = rs.randn(100003).astype(np.float32); s = rs.randn(100003).astype(np.float32)
+    tt = torch.from_numpy(t.copy()); tt.mul_(0.99); tt.add_(torch.from_numpy(s) * (1.0 - 0.99))
+    assert np.array_equal(TO.ema_update(t, s, 0.99), tt.numpy())
+    a = rs.randn(2, 3, 9, 7).astype(np.float32); b = rs.randn(2, 3, 9, 7).astype(np.float32)
+    m = (rs.rand(2, 1, 9, 7) > 0.5).astype(np.float32); m[0, 0, 0, 0] = 0.25
+    ref = torch.from_numpy(a) * (1 - torch.from_numpy(m)) + torch.from_numpy(b) * torch.from_numpy(m)
+    assert np.array_equal(TO.mix(a, b, m), ref.numpy())
