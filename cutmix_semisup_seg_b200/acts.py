@@ -25,7 +25,7 @@ class Act(object):
 
     @staticmethod
     def alloc(n, h, w, c, device, ld=None, name=''):
-        ld = c if ld is None else ld
+        ld = (c + 3) // 4 * 4 if ld is None else ld      # 16-byte pixel pitch (TMA global-stride rule)
         return Act(torch.empty((n, h, w, ld), device=device, dtype=torch.float32), n, h, w, c, ld, 0, name)
 
     @property

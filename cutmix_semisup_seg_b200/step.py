@@ -56,6 +56,20 @@ class FlatGrads(object):
         backend.fill(self.flat, 0.0)
 
 
+def average_gradients(flat, dist, group=None):
+    """ONE collective per iteration: average the flat student-gradient buffer over the data-parallel ranks
+    (natural shard: every rank holds the gradient of its own mini-batch).  NCCL reduces with ncclAvg over
+    NVLink/NVSwitch; other backends (gloo, used by the CPU tests of this host logic) sum and divide."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    if dist.get_backend(group) == 'nccl':
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+
+
 class MeanTeacherStep(object):
     def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
                  cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
@@ -85,8 +99,7 @@ class MeanTeacherStep(object):
 
     def _allreduce(self):
         if self.world > 1:
-            # natural shard: every rank holds the gradient of its own mini-batch; average them (DDP semantics)
-            self.dist.all_reduce(self.flat.flat, op=self.dist.ReduceOp.AVG, group=self.group)
+            average_gradients(self.flat.flat, self.dist, self.group)
 
     def supervised(self, batch_x, batch_y):
         """Lines 296-301: student forward, CE(ignore 255), backward.  Returns the loss as a device scalar."""

@@ -1,0 +1,57 @@
+"""Micro-benchmark of the tensor-core conv kernels on the DeepLab v3+ ASPP shapes (N=16, 2048x64x64 -> 256):
+CUDA-event timing per launch (L2 flushed between launches), TFLOP/s vs the measured peak.  Used for the ncu
+captures committed under profiles/."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from cutmix_semisup_seg_b200.kernels import ActKernels
+from cutmix_semisup_seg_b200.acts import Act
+
+dev = torch.device('cuda:0')
+K = ActKernels(n_split=1)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+
+def timeit(fn, flops, name):
+    ts = []
+    for i in range(reps + 1):
+        flush.fill_(float(i))                      # evict L2 (256 MB write)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        if i > 0:
+            ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    print('{:<44s} {:8.3f} ms  {:8.1f} TFLOP/s'.format(name, ms, flops / ms / 1e9), flush=True)
+    return ms
+
+
+def conv_case(n, h, w, cin, cout, k, dil, name):
+    pad = dil * (k // 2)
+    x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+    wt = torch.randn(cout, k * k, cin, device=dev) * 0.01
+    y = Act.alloc(n, h, w, cout, dev)
+    g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+    dx = Act.alloc(n, h, w, cin, dev)
+    dw = torch.zeros(cout, k * k, cin, device=dev)
+    wtt, ldb = K.transpose_w(wt, cout, k * k, cin)
+    fl = 2.0 * n * h * w * cin * cout * k * k
+    timeit(lambda: K.conv_fwd(x, wt, cout, k, k, cin, cin, 1, pad, dil, y), fl, name + ' fprop')
+    timeit(lambda: K.conv_dgrad(g, wtt, cin, k, k, cout, ldb, 1, pad, dil, dx), fl, name + ' dgrad')
+    timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), fl, name + ' wgrad')
+
+
+if __name__ == '__main__':
+    which = sys.argv[2] if len(sys.argv) > 2 else 'all'
+    if which in ('all', 'aspp'):
+        conv_case(16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N16')
+    if which == 'all':
+        conv_case(16, 64, 64, 2048, 256, 3, 36, 'ASPP 3x3 d36 2048->256 @64x64 N16')
+        conv_case(16, 64, 64, 2048, 256, 1, 1, 'ASPP 1x1 2048->256 @64x64 N16')
+        conv_case(16, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256 @64x64 N16')
+        conv_case(16, 64, 64, 256, 1024, 1, 1, 'layer3 1x1 256->1024 @64x64 N16')
+        conv_case(16, 64, 64, 1024, 256, 1, 1, 'layer3 1x1 1024->256 @64x64 N16')
+        conv_case(16, 64, 64, 512, 512, 3, 4, 'layer4 3x3 d4 512->512 @64x64 N16')
+        conv_case(16, 128, 128, 304, 256, 3, 1, 'decoder 3x3 304->256 @128x128 N16')
+        conv_case(16, 128, 128, 64, 64, 3, 1, 'layer1 3x3 64->64 @128x128 N16')
+        conv_case(16, 128, 128, 64, 256, 1, 1, 'layer1 1x1 64->256 @128x128 N16')
