@@ -26,6 +26,11 @@ class Tape(object):
 
     def record(self, node, inputs):
         if not self.enabled:
+            y = getattr(node, 'y', None)
+            if y is not None:
+                y.node = None
+            for k in list(vars(node).keys()):
+                setattr(node, k, None)
             return
         for a in inputs:
             root = a
@@ -101,8 +106,28 @@ class Tape(object):
         self._finish(root, False)
 
     def backward(self):
-        for node in reversed(self.nodes):
+        """Run the recorded nodes in reverse.  Each node is released as soon as it has run: its output's
+        gradient and its saved activations are dropped (Act <-> node reference cycles are broken explicitly so
+        tens of GB of activations are freed by reference counting, not by the cyclic GC)."""
+        nodes, self.nodes = self.nodes, []
+        while nodes:
+            node = nodes.pop()
             node.backward(self)
+            y = getattr(node, 'y', None)
+            if y is not None:
+                y.node = None
+                if y.parent is None:
+                    y.grad = None
+            for k in list(vars(node).keys()):
+                setattr(node, k, None)
+
+    def discard(self):
+        for node in self.nodes:
+            y = getattr(node, 'y', None)
+            if y is not None:
+                y.node = None
+            for k in list(vars(node).keys()):
+                setattr(node, k, None)
         self.nodes = []
 
 

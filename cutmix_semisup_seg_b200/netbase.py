@@ -81,7 +81,10 @@ class B2SegNet(nn.Module):
         xin.needs_grad = False
         low, align = self._graph(tape, xin, x.shape[2], x.shape[3])
         logits = E.to_logits_nchw(tape, low, x.shape[2], x.shape[3], align)
-        return logits, (_RunState(tape, low, align) if record else None)
+        if not record:
+            tape.discard()
+            return logits, None
+        return logits, _RunState(tape, low, align)
 
     def b2_backward(self, state, dlogits, scale_dev=None, scale_host=1.0):
         """Back-propagate d(loss)/d(logits) (NCHW, optionally to be multiplied by a device scalar) into
@@ -91,6 +94,8 @@ class B2SegNet(nn.Module):
         state.consumed = True
         E.seed_output_grad(state.tape, state.low, dlogits, state.align, scale_dev=scale_dev, scale_host=scale_host)
         state.tape.backward()
+        state.low.grad = None
+        state.tape, state.low = None, None
 
     # ---- nn.Module surface ------------------------------------------------------------------
     def forward(self, x, feature_maps=False, use_dropout=False):

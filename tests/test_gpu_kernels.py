@@ -80,8 +80,12 @@ def test_mix_and_cut_bit_exact(be):
         m[0, 0, 0, :3] = [0.25, 0.5, 0.75]          # fractional mask values (valid-mask borders)
         a[0, 0, 1, 1] = -0.0; b[0, 0, 1, 2] = np.inf
         out = be.mix(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), torch.from_numpy(m).to(dev))
-        ref = TO.mix(a, b, m)
-        assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+        with np.errstate(invalid='ignore'):
+            ref = TO.mix(a, b, m)
+        got = out.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(ref))              # inf * 0 -> NaN in both
+        ok = ~np.isnan(ref)
+        assert np.array_equal(got.view(np.uint32)[ok], ref.view(np.uint32)[ok])   # bit-exact incl. -0.0
         cut = be.mix(torch.from_numpy(a).to(dev), None, torch.from_numpy(m).to(dev))
         assert np.array_equal(cut.cpu().numpy().view(np.uint32), (a * m).astype(np.float32).view(np.uint32))
 
