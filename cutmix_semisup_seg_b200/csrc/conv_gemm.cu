@@ -27,7 +27,10 @@ constexpr int MAX_BLOCK_N = 256;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 4;  // 32 KB
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_ROW_FLOATS = 36;                          // 32 columns + 4 pad: conflict-free 128-bit smem access
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;     // one 32x32 fp32 chunk per epilogue warp
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 4 * 32 * 8;  // staging + per-row output offsets
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int MAX_TAPS = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
@@ -186,23 +189,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers (thread = pixel row) -> padded smem (transpose) -> coalesced 128 B row segments to HBM:
+    // each group of 8 lanes reads/writes 32 consecutive channels of one pixel, so residual / gate loads and
+    // the output stores are full-line transactions instead of 32 scattered 16 B pieces per instruction.
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * EPI_ROW_FLOATS);
+    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * EPI_WARP_BYTES) + ew * 32;
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
+    const int sub_r = lane >> 3;          // row within a group of 4
+    const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(a, tile);
-      const int dn = row / bwbh;
-      const int rem = row - dn * bwbh;
-      const int dhh = rem / a.bw;
-      const int dww = rem - dhh * a.bw;
-      const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
-      const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
-      const int64_t pix = ((int64_t)pn * a.fh + (int64_t)ph * a.ostride + a.ooh) * a.fw + (int64_t)pw * a.ostride + a.oow;
-      float* drow = a.d + pix * a.ldd;
-      const float* addrow = a.addend ? a.addend + pix * a.ld_add : nullptr;
-      const float* gaterow = a.gate ? a.gate + pix * a.ld_gate : nullptr;
-
+      {
+        const int dn = row / bwbh;
+        const int rem = row - dn * bwbh;
+        const int dhh = rem / a.bw;
+        const int dww = rem - dhh * a.bw;
+        const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
+        const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
+        const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
+        __syncwarp();
+        rowpix[lane] = valid ? pix : -1;
+        __syncwarp();
+      }
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * MAX_BLOCK_N;
@@ -211,41 +222,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tc::tmem_ld_x32(taddr + ch * 32, r);
         tc::tmem_ld_wait();
-        if (valid) {
-          const int col0 = t.n_idx * a.block_n + ch * 32;
+        if (ch == nchunks - 1) {            // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+        }
+        const int col0 = t.n_idx * a.block_n + ch * 32;
+        if (col0 >= a.nb) continue;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = col0 + j * 4;
-            if (c >= a.nb) break;
-            if (a.vec_ok && c + 3 < a.nb) {
-              float4 add = make_float4(0, 0, 0, 0), gt = make_float4(1, 1, 1, 1), old = make_float4(0, 0, 0, 0);
-              if (addrow) add = __ldg(reinterpret_cast<const float4*>(addrow + c));
-              if (gaterow) gt = __ldg(reinterpret_cast<const float4*>(gaterow + c));
-              if (a.accumulate) old = *reinterpret_cast<const float4*>(drow + c);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stg + lane * EPI_ROW_FLOATS + q * 4) =
+              make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+        __syncwarp();
+        const int c = col0 + sub_c;
+        if (c < a.nb) {
+          const bool vec = a.vec_ok && c + 3 < a.nb;
+          float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), s2 = make_float4(1, 1, 1, 1);
+          if (vec) {
+            if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + c));
+            if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + c));
+            if (a.scale2) s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + c));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + sub_r;
+            const long long pix = rowpix[rr];
+            if (pix < 0) continue;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_ROW_FLOATS + sub_c);
+            float* drow = a.d + pix * a.ldd;
+            if (vec) {
               float4 o;
-              o.x = epi1(a, __uint_as_float(r[j * 4 + 0]), c + 0, add.x, gt.x, old.x);
-              o.y = epi1(a, __uint_as_float(r[j * 4 + 1]), c + 1, add.y, gt.y, old.y);
-              o.z = epi1(a, __uint_as_float(r[j * 4 + 2]), c + 2, add.z, gt.z, old.z);
-              o.w = epi1(a, __uint_as_float(r[j * 4 + 3]), c + 3, add.w, gt.w, old.w);
+              o.x = v.x * sc.x + sh.x; o.y = v.y * sc.y + sh.y; o.z = v.z * sc.z + sh.z; o.w = v.w * sc.w + sh.w;
+              if (a.addend) {
+                const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend + pix * a.ld_add + c));
+                o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+              }
+              if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (a.gate) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(a.gate + pix * a.ld_gate + c));
+                o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+              }
+              o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
+              if (a.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(drow + c);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
               *reinterpret_cast<float4*>(drow + c) = o;
             } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int cc = c + e;
                 if (cc < a.nb) {
-                  const float add = addrow ? __ldg(addrow + cc) : 0.f;
-                  const float gt = gaterow ? __ldg(gaterow + cc) : 1.f;
+                  const float add = a.addend ? __ldg(a.addend + pix * a.ld_add + cc) : 0.f;
+                  const float gt = a.gate ? __ldg(a.gate + pix * a.ld_gate + cc) : 1.f;
                   const float old = a.accumulate ? drow[cc] : 0.f;
-                  drow[cc] = epi1(a, __uint_as_float(r[j * 4 + e]), cc, add, gt, old);
+                  drow[cc] = epi1(a, vv[e], cc, add, gt, old);
                 }
               }
             }
           }
         }
+        __syncwarp();
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

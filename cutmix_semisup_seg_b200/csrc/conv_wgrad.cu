@@ -42,6 +42,7 @@ struct WgradKArgs {
   int accumulate;
   int desc_variant;
   const float* row_scale;   // per output channel m (folded BN scale), applied before accumulation
+  int use5_a, use5_b;       // operand fetched with ONE 5-D TMA per stage (channel count multiple of 32)
 };
 
 struct UnitInfo {
@@ -79,6 +80,8 @@ __device__ __forceinline__ PBox decode_pb(const WgradKArgs& a, int pb, int tap) 
 __global__ void __launch_bounds__(W_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYlo,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                  const __grid_constant__ CUtensorMap tmY5, const __grid_constant__ CUtensorMap tmY5lo,
+                  const __grid_constant__ CUtensorMap tmX5, const __grid_constant__ CUtensorMap tmX5lo,
                   const __grid_constant__ WgradKArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -119,7 +122,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         const UnitInfo ui = decode_unit(a, u);
         int na = (a.m - ui.m0 + 31) / 32; if (na > W_BLOCK_M / 32) na = W_BLOCK_M / 32;
         int nbk = (a.c - ui.c0 + 31) / 32; if (nbk > a.block_n / 32) nbk = a.block_n / 32;
-        const uint32_t tx = (uint32_t)(na + nbk) * (uint32_t)a.kpix * 128u;
+        const int slot = a.kpix * 128;   // bytes of one 32-channel block: kpix pixel rows x 128 B
+        // 5-D boxes always carry the full block count of the tile (blocks past the tensor are zero-filled)
+        const uint32_t tx = (uint32_t)((a.use5_a ? W_BLOCK_M / 32 : na) + (a.use5_b ? a.block_n / 32 : nbk)) * (uint32_t)slot;
         bool any = false;
         for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
           const PBox b = decode_pb(a, pb, ui.tap);
@@ -131,14 +136,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
             tc::mbar_expect_tx(&full_bar[stage], tx);
-            const CUtensorMap* my = (p & 1) ? &tmYlo : &tmY;
-            const CUtensorMap* mx = (p & 2) ? &tmXlo : &tmX;
-            for (int j = 0; j < na; ++j)
-              tc::tma_load_4d(smem_a + stage * W_A_STAGE_BYTES + j * W_SLOT_BYTES, my, &full_bar[stage],
-                              ui.m0 + 32 * j, b.w0, b.h0, b.n0);
-            for (int j = 0; j < nbk; ++j)
-              tc::tma_load_4d(smem_b + stage * W_B_STAGE_BYTES + j * W_SLOT_BYTES, mx, &full_bar[stage],
-                              ui.c0 + 32 * j, xw, xh, b.n0);
+            uint8_t* sa = smem_a + stage * W_A_STAGE_BYTES;
+            uint8_t* sb = smem_b + stage * W_B_STAGE_BYTES;
+            if (a.use5_a) {
+              tc::tma_load_5d(sa, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0, ui.m0 / 32);
+            } else {
+              const CUtensorMap* my = (p & 1) ? &tmYlo : &tmY;
+              for (int j = 0; j < na; ++j)
+                tc::tma_load_4d(sa + j * slot, my, &full_bar[stage], ui.m0 + 32 * j, b.w0, b.h0, b.n0);
+            }
+            if (a.use5_b) {
+              tc::tma_load_5d(sb, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, xw, xh, b.n0, ui.c0 / 32);
+            } else {
+              const CUtensorMap* mx = (p & 2) ? &tmXlo : &tmX;
+              for (int j = 0; j < nbk; ++j)
+                tc::tma_load_4d(sb + j * slot, mx, &full_bar[stage], ui.c0 + 32 * j, xw, xh, b.n0);
+            }
             if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -150,8 +163,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, 1, 1);
       // MN-major tf32: SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B).  LBO = stride between the
       // 32-channel column blocks (one TMA box each), SBO = stride between 4-row groups along K.
-      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)W_SLOT_BYTES;
-      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)W_SLOT_BYTES : 512u;
+      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
+      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const int ksteps = a.kpix / 8;
@@ -351,7 +364,9 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     a.slab_elems = 0;
   }
 
-  CUtensorMap tmY, tmYlo, tmX, tmXlo;
+  CUtensorMap tmY, tmYlo, tmX, tmXlo, tmY5, tmY5lo, tmX5, tmX5lo;
+  a.use5_a = (p->m % 32 == 0) ? 1 : 0;
+  a.use5_b = (p->c % 32 == 0) ? 1 : 0;
   {
     const uint64_t dims[4] = {(uint64_t)p->m, (uint64_t)p->ow, (uint64_t)p->oh, (uint64_t)p->n};
     const uint64_t strides[3] = {(uint64_t)p->ldy * 4, (uint64_t)p->ow * p->ldy * 4, (uint64_t)p->oh * p->ow * p->ldy * 4};
@@ -359,6 +374,17 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     const uint32_t es[4] = {1, 1, 1, 1};
     rc = tc::make_tmap_f32(&tmY, p->dy, 4, dims, strides, box, es, true); if (rc) return rc;
     rc = tc::make_tmap_f32(&tmYlo, p->dy_lo ? p->dy_lo : p->dy, 4, dims, strides, box, es, true); if (rc) return rc;
+    tmY5 = tmY; tmY5lo = tmYlo;
+    if (a.use5_a) {   // (32, OW, OH, N, M/32): channel blocks as an outer dimension with a 128 B stride
+      const uint64_t d5[5] = {32, (uint64_t)p->ow, (uint64_t)p->oh, (uint64_t)p->n, (uint64_t)(p->m / 32)};
+      const uint64_t s5[4] = {(uint64_t)p->ldy * 4, (uint64_t)p->ow * p->ldy * 4, (uint64_t)p->oh * p->ow * p->ldy * 4, 128};
+      const uint32_t b5[5] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn, (uint32_t)(W_BLOCK_M / 32)};
+      const uint32_t e5[5] = {1, 1, 1, 1, 1};
+      if (tc::make_tmap_f32(&tmY5, p->dy, 5, d5, s5, b5, e5, true) != B2_OK ||
+          tc::make_tmap_f32(&tmY5lo, p->dy_lo ? p->dy_lo : p->dy, 5, d5, s5, b5, e5, true) != B2_OK) {
+        a.use5_a = 0; tmY5 = tmY; tmY5lo = tmYlo;
+      }
+    }
   }
   {
     const uint64_t dims[4] = {(uint64_t)p->c, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
@@ -367,6 +393,17 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     const uint32_t es[4] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1};
     rc = tc::make_tmap_f32(&tmX, p->x, 4, dims, strides, box, es, true); if (rc) return rc;
     rc = tc::make_tmap_f32(&tmXlo, p->x_lo ? p->x_lo : p->x, 4, dims, strides, box, es, true); if (rc) return rc;
+    tmX5 = tmX; tmX5lo = tmXlo;
+    if (a.use5_b) {
+      const uint64_t d5[5] = {32, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n, (uint64_t)(p->c / 32)};
+      const uint64_t s5[4] = {(uint64_t)p->ldx * 4, (uint64_t)p->iw * p->ldx * 4, (uint64_t)p->ih * p->iw * p->ldx * 4, 128};
+      const uint32_t b5[5] = {32, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn, (uint32_t)(a.block_n / 32)};
+      const uint32_t e5[5] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1, 1};
+      if (tc::make_tmap_f32(&tmX5, p->x, 5, d5, s5, b5, e5, true) != B2_OK ||
+          tc::make_tmap_f32(&tmX5lo, p->x_lo ? p->x_lo : p->x, 5, d5, s5, b5, e5, true) != B2_OK) {
+        a.use5_b = 0; tmX5 = tmX; tmX5lo = tmXlo;
+      }
+    }
   }
 
   static bool attr_set = false;
@@ -378,7 +415,7 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
   if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
   if (p->max_ctas > 0 && p->max_ctas < grid) grid = p->max_ctas;
   if (grid > a.num_units) grid = a.num_units;
-  conv_wgrad_kernel<<<grid, W_THREADS, W_SMEM_BYTES, s>>>(tmY, tmYlo, tmX, tmXlo, a);
+  conv_wgrad_kernel<<<grid, W_THREADS, W_SMEM_BYTES, s>>>(tmY, tmYlo, tmX, tmXlo, tmY5, tmY5lo, tmX5, tmX5lo, a);
   B2_LAUNCH_CHECK("conv_wgrad_kernel");
   if (a.n_splits > 1) {
     const int64_t elems = (int64_t)p->m * p->tw * p->c;

@@ -46,7 +46,9 @@ def deeplab2_forward(sd, x, bn_train=False):
     t = F.relu(_bn(sd, 'bn1', t, bn_train)); _count_bn(sd, 'bn1', bn_train)
     t = F.max_pool2d(t, 3, 2, 1, ceil_mode=True)
     for name, planes, blocks, stride, dil in _DL2_LAYERS:
-        for b in range(blocks):
+        b = -1
+        while '{}.{}.conv1.weight'.format(name, b + 1) in sd:        # block count from the keys (ResNet-101: 3,4,23,3)
+            b += 1
             p = '{}.{}'.format(name, b)
             s = stride if b == 0 else 1
             res = t
@@ -86,7 +88,9 @@ def deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dr
     t = F.max_pool2d(t, 3, 2, 1)
     feats = {}
     for name, planes, blocks, stride, d0, d1 in _DL3_LAYERS:
-        for b in range(blocks):
+        b = -1
+        while '{}{}.{}.conv1.weight'.format(bb, name, b + 1) in sd:
+            b += 1
             p = '{}{}.{}'.format(bb, name, b)
             s = stride if b == 0 else 1
             dil = d0 if b == 0 else d1
