@@ -104,11 +104,7 @@ def build_trainer(cfg, device, dist_on):
     teacher = Net(cfg['classes'], pretrained=False).to(device)
     for p in teacher.parameters():
         p.requires_grad = False
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore')
-        optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=cfg['lr'] * 0.1),
-                                  dict(params=student.new_parameters(), lr=cfg['lr'])], foreach=False)
+    optim = step_mod.make_optimizer(student, 'adam', cfg['lr'])
     ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
     student.train(); teacher.train()
     student.freeze_batchnorm(); teacher.freeze_batchnorm()         # every reference recipe uses --freeze_bn
@@ -169,11 +165,14 @@ def run_b200(args):
     launches0 = be.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_start = time.time()
     ev0.record()
     for i in range(args.steps):
         out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
     ev1.record()
+    t_enq = time.time()
     sync_all()
+    t_done = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = be.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -223,7 +222,8 @@ def run_b200(args):
         'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
         'config': {'workload': cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
-                   'freeze_bn': True, 'optimizer': 'Adam foreach=False (reference param groups)',
+                   'freeze_bn': True, 'optimizer': trainer.optim_note,
+                   'host_enqueue_ms_per_step': round((t_enq - t_start) * 1e3 / args.steps, 2),
                    'conv_tflops_per_s_whole_step': round(flops_iter / (ms_step / 1e3) / 1e12, 2)},
         'clocks': clocks,
         'e2e': {'value': round(n * world / (ms_e2e / args.steps / 1e3), 3), 'unit': 'images/s',
@@ -243,7 +243,12 @@ def run_b200(args):
                            'share_of_step': round(d['ms'] / ms_step, 4),
                            'per_kernel': {k: {'ms': round(v['ms'], 3), 'n': v['n'],
                                               'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)} for k, v in prof.items()}}
-    res['cpu_baseline'] = cpu_baseline(args, sample_batch=1)
+    if prof and os.environ.get('B200SEG_SHAPE_PROFILE'):
+        top = sorted(be.last_shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:40]
+        with open(os.environ['B200SEG_SHAPE_PROFILE'], 'w') as f:
+            for k, v in top:
+                f.write('{:<70s} {:8.3f} ms  n={:4d}  {:7.1f} TFLOP/s\n'.format(k, v['ms'], v['n'], v['flops'] / max(v['ms'], 1e-9) / 1e9))
+    res['cpu_baseline'] = cpu_baseline(args, sample_batch=2)
     print(json.dumps(res))
     if dist_on:
         dist.destroy_process_group()
@@ -297,7 +302,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get('WORLD_SIZE', 1))
-    batch = 1
+    batch = 2          # train-mode BatchNorm of the DLv3+ pooling branch needs > 1 sample
     warm = min(args.warmup, 1)
     t0 = time.time()
     probe, cfg = cpu_step_time(args, batch, 1, 0)

@@ -326,6 +326,15 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   // keep at least ~8 pixel boxes per split so the pipeline fills
   const int max_splits = (int)((num_pb + 7) / 8);
   if (splits > max_splits) splits = max_splits < 1 ? 1 : max_splits;
+  if (p->kchunk > 0) {
+    // precision mode: the tensor core accumulates in fp32 with truncation, so the error of one accumulator grows
+    // with the number of pixels it sums; bound that count and let the fp32 (round-to-nearest) slab reduction
+    // combine the partial sums.
+    int64_t want = (num_pb * a.kpix + p->kchunk - 1) / p->kchunk;
+    if (want > num_pb) want = num_pb;
+    if (want > 4096) want = 4096;
+    if (want > splits) splits = (int)want;
+  }
   a.n_splits = splits;
   a.num_units = a.out_tiles * splits;
   a.n_pass = p->n_split;

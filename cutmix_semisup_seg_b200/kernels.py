@@ -23,6 +23,7 @@ class ActKernels(object):
     def __init__(self, backend=None, n_split=1):
         self.be = backend if backend is not None else O.default_backend()
         self.n_split = n_split          # 1: single-pass TF32 (throughput); 3: 3xTF32 (parity mode)
+        self.kchunk = 1024 if n_split > 1 else 0   # parity mode also bounds the pixels per TMEM accumulation in wgrad
 
     # ------------------------------------------------------------------------------ helpers
     def _split(self, ptr_tensor_like):
@@ -136,11 +137,11 @@ class ActKernels(object):
             npix = x.rows
             be.conv_wgrad(ga.ptr, 1, 1, npix, cout, ga.ld, xa.ptr, 1, npix, cin, xa.ld, dw.data_ptr(), taps, 1,
                           accumulate=accumulate, dy_lo_ptr=y_lo, x_lo_ptr=x_lo, n_split=self.n_split, device=g.device,
-                          row_scale=row_scale)
+                          row_scale=row_scale, kchunk=self.kchunk)
         else:
             be.conv_wgrad(ga.ptr, g.n, g.h, g.w, cout, ga.ld, xa.ptr, x.h, x.w, cin, xa.ld, dw.data_ptr(), taps, kh * kw,
                           istride=stride, accumulate=accumulate, dy_lo_ptr=y_lo, x_lo_ptr=x_lo, n_split=self.n_split,
-                          device=g.device, row_scale=row_scale)
+                          device=g.device, row_scale=row_scale, kchunk=self.kchunk)
 
     def transpose_w(self, w, cout, t, cin, scale=None):
         """(cout, t, cin) -> (cin, t, pad4(cout)) with optional per-cout scale.  Returns (tensor, ldb)."""

@@ -57,6 +57,7 @@ class WgradParams(ctypes.Structure):
         ('workspace', c_vp), ('workspace_bytes', c_sz),
         ('max_ctas', c_i32),
         ('row_scale', c_vp),
+        ('kchunk', c_i32),
     ]
 
 

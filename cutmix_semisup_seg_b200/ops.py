@@ -43,7 +43,7 @@ class CudaBackend(object):
         e0.record()
         rc = self._call(name, *args)
         e1.record()
-        self._prof.append((kernel, flops, e0, e1))
+        self._prof.append((kernel, flops, e0, e1, getattr(self, '_prof_tag', '')))
         return rc
 
     def start_profile(self):
@@ -52,11 +52,15 @@ class CudaBackend(object):
     def stop_profile(self):
         """{kernel: {'ms': total device time, 'flops': algorithmic FLOPs, 'n': launches}}"""
         torch.cuda.synchronize()
-        out = {}
-        for kernel, flops, e0, e1 in self._prof:
+        out, shapes = {}, {}
+        for kernel, flops, e0, e1, tag in self._prof:
+            ms = e0.elapsed_time(e1)
             d = out.setdefault(kernel, {'ms': 0.0, 'flops': 0.0, 'n': 0})
-            d['ms'] += e0.elapsed_time(e1); d['flops'] += flops; d['n'] += 1
+            d['ms'] += ms; d['flops'] += flops; d['n'] += 1
+            d = shapes.setdefault(kernel + ' ' + tag, {'ms': 0.0, 'flops': 0.0, 'n': 0})
+            d['ms'] += ms; d['flops'] += flops; d['n'] += 1
         self._prof = None
+        self.last_shape_profile = shapes
         return out
 
     @staticmethod
@@ -174,11 +178,12 @@ class CudaBackend(object):
         p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate)); p.n_split = n_split
         p.max_ctas = max_ctas
         flops = 2.0 * n * oh * ow * nb * k * taps_arr.shape[0] * n_split
+        self._prof_tag = 'pix{} k{} n{} taps{} s{}'.format(n * oh * ow, k, nb, taps_arr.shape[0], istride)
         self._timed_call('conv_gemm_kernel', flops / n_split, 'b2_conv_gemm', ctypes.byref(p), self._s())
 
     def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
                    accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None,
-                   row_scale=None):
+                   row_scale=None, kchunk=0):
         taps_arr = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(-1, 3))
         p = L.WgradParams()
         p.dy = dy_ptr; p.dy_lo = dy_lo_ptr; p.x = x_ptr; p.x_lo = x_lo_ptr; p.dw = dw_ptr
@@ -191,12 +196,14 @@ class CudaBackend(object):
         p.accumulate = int(bool(accumulate)); p.n_split = n_split
         p.max_ctas = max_ctas
         p.row_scale = L.ptr(row_scale)
+        p.kchunk = kchunk
         need = L.call('b2_conv_wgrad_workspace', ctypes.byref(p))
         ws = None
         if need > 0:
             ws = self._workspace(need, device)
             p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel()
         flops = 2.0 * n * oh * ow * m * c * taps_arr.shape[0]
+        self._prof_tag = 'pix{} m{} c{} taps{} s{}'.format(n * oh * ow, m, c, taps_arr.shape[0], istride)
         self._timed_call('conv_wgrad_kernel', flops, 'b2_conv_wgrad', ctypes.byref(p), self._s())
         self.launches += 1 if need > 0 else 0
 

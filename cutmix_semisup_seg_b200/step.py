@@ -56,6 +56,31 @@ class FlatGrads(object):
         backend.fill(self.flat, 0.0)
 
 
+def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4):
+    """torch.optim optimiser on the reference's parameter groups (train_seg_semisup_mask_mt.py:90-100): group 0 =
+    `pretrained_parameters()` at 0.1 x lr, group 1 = `new_parameters()` at lr.  DeepLab v2's group 0 repeats tensors
+    (reference quirk): a tensor listed k times must receive k sequential updates per step, which only the
+    per-tensor implementation (`foreach=False`, what torch 1.4 did) reproduces.  Without duplicates the single
+    fused multi-tensor kernel of torch is the same algorithm and is used instead."""
+    import warnings
+    g0 = list(student_net.pretrained_parameters())
+    g1 = list(student_net.new_parameters())
+    dup = len(set(id(p) for p in g0 + g1)) != len(g0) + len(g1)
+    groups = [dict(params=g0, lr=learning_rate * 0.1), dict(params=g1, lr=learning_rate)]
+    on_cuda = all(p.is_cuda for p in g0 + g1)
+    kw = dict(foreach=False) if (dup or not on_cuda) else dict(fused=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        if opt_type == 'adam':
+            opt = torch.optim.Adam(groups, **kw)
+        elif opt_type == 'sgd':
+            opt = torch.optim.SGD(groups, momentum=sgd_momentum, nesterov=sgd_nesterov, weight_decay=sgd_weight_decay, **kw)
+        else:
+            raise ValueError('Unknown opt_type {}'.format(opt_type))
+    opt.b2_note = '{} ({})'.format(opt_type, 'per-tensor, duplicated reference group' if dup else 'torch fused multi-tensor')
+    return opt
+
+
 def average_gradients(flat, dist, group=None):
     """ONE collective per iteration: average the flat student-gradient buffer over the data-parallel ranks
     (natural shard: every rank holds the gradient of its own mini-batch).  NCCL reduces with ncclAvg over
@@ -81,6 +106,7 @@ class MeanTeacherStep(object):
         self.conf_thresh, self.conf_per_pixel = conf_thresh, conf_per_pixel
         self.rampup, self.mask_mix, self.unsup_batch_ratio = rampup, mask_mix, unsup_batch_ratio
         self.be = O.default_backend()
+        self.optim_note = getattr(student_optim, 'b2_note', type(student_optim).__name__)
         self.world = 1
         self.dist = None
         if dist_group is not None:

@@ -162,6 +162,7 @@ typedef struct b2_wgrad_params {
   void* workspace; size_t workspace_bytes;
   int32_t max_ctas;
   const float* row_scale;                 /* per-m scale applied to the gradient rows, or NULL */
+  int32_t kchunk;                         /* >0: at most this many pixels per TMEM accumulation (precision mode) */
 } b2_wgrad_params;
 size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p);
 int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);

@@ -203,7 +203,8 @@ def test_conv_fprop_dgrad_wgrad(case, n_split):
     N, H, W, Cin, Cout, k, stride, dil = case
     torch.manual_seed(sum(case))
     K = ActKernels(n_split=n_split)
-    tol = 2e-3 if n_split == 1 else 5e-5
+    # tcgen05 accumulates the fp32 sum with truncation: the 3xTF32 error grows with the reduction length
+    tol = 2e-3 if n_split == 1 else 5e-5 * max(1.0, Cin * k * k / 4096.0)
     pad = dil * (k // 2)
     x = torch.randn(N, Cin, H, W, dtype=torch.double, requires_grad=True)
     w = (torch.randn(Cout, Cin, k, k, dtype=torch.double) / (Cin * k * k) ** 0.5).requires_grad_(True)

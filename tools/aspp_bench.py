@@ -45,6 +45,8 @@ if __name__ == '__main__':
     which = sys.argv[2] if len(sys.argv) > 2 else 'all'
     if which in ('all', 'aspp'):
         conv_case(16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N16')
+    if which == 'l3':
+        conv_case(16, 64, 64, 256, 1024, 1, 1, 'layer3 1x1 256->1024 @64x64 N16')
     if which == 'all':
         conv_case(16, 64, 64, 2048, 256, 3, 36, 'ASPP 3x3 d36 2048->256 @64x64 N16')
         conv_case(16, 64, 64, 2048, 256, 1, 1, 'ASPP 1x1 2048->256 @64x64 N16')

@@ -86,17 +86,7 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
 
     NetClass = network_architectures.seg.get(arch)
     student_net = NetClass(n_classes, pretrained=not no_pretrained).to(torch_device)
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore')     # the DeepLab v2 pretrained group repeats tensors, like the reference's
-        groups = [dict(params=student_net.pretrained_parameters(), lr=learning_rate * 0.1),
-                  dict(params=student_net.new_parameters(), lr=learning_rate)]
-        if opt_type == 'adam':
-            student_optim = torch.optim.Adam(groups, foreach=False)
-        elif opt_type == 'sgd':
-            student_optim = torch.optim.SGD(groups, momentum=sgd_momentum, nesterov=sgd_nesterov,
-                                            weight_decay=sgd_weight_decay, foreach=False)
-        else:
-            raise ValueError('Unknown opt_type {}'.format(opt_type))
+    student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay)
     if model == 'mean_teacher':
         teacher_net = NetClass(n_classes, pretrained=False).to(torch_device)
         for p in teacher_net.parameters():
