@@ -1,0 +1,136 @@
+// Shared epilogue of the convolution GEMM kernels: TMEM accumulator (128 rows x block_n columns per CTA) -> HBM.
+//
+// Design notes (from the ncu captures under profiles/): the first version ran ~2200 SASS instructions per 32-column
+// chunk (run-time feature tests and 64-bit address arithmetic inside fully unrolled loops) and serialised its residual /
+// gate loads, so small-K 1x1 layers were epilogue-issue-bound at ~0.4 TB/s of output.  This version
+//   * hoists every per-row quantity (output / residual / gate element offsets) into registers once per tile,
+//   * folds optional scale / shift / second scale / ReLU into unconditional FMA / FMUL / FMAX with neutral constants,
+//   * issues the residual and gate loads of all 8 row groups of a chunk before touching them (8-16 independent 16 B
+//     loads in flight per lane),
+//   * keeps the rare ragged path (channel count not a multiple of 4, unaligned pointers) out of line.
+// Rows are staged through a padded smem tile so that 8 consecutive lanes own 32 consecutive channels of one pixel:
+// loads and stores are full 128 B segments.
+#pragma once
+#include "tc_common.cuh"
+
+namespace epi {
+
+constexpr int ROW_FLOATS = 36;                      // 32 columns + 4 pad: conflict-free 128-bit smem access
+constexpr int WARP_BYTES = 32 * ROW_FLOATS * 4;
+constexpr int BYTES = 4 * WARP_BYTES + 4 * 32 * 8;  // staging tiles + per-row pixel offsets
+
+struct Params {
+  float* d; int ldd;
+  const float* scale; const float* shift; const float* scale2;
+  const float* addend; int ld_add;
+  const float* gate; int ld_gate;
+  int relu, accumulate, vec_ok, nb;
+};
+
+static __device__ __noinline__ void ragged_store(const Params& p, float4 v, long long pix, int c) {
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  float* drow = p.d + pix * p.ldd;
+  for (int e = 0; e < 4; ++e) {
+    const int cc = c + e;
+    if (cc >= p.nb) break;
+    float o = vv[e];
+    if (p.scale) o *= __ldg(p.scale + cc);
+    if (p.shift) o += __ldg(p.shift + cc);
+    if (p.addend) o += __ldg(p.addend + pix * p.ld_add + cc);
+    if (p.relu) o = fmaxf(o, 0.f);
+    if (p.gate) o = __ldg(p.gate + pix * p.ld_gate + cc) > 0.f ? o : 0.f;
+    if (p.scale2) o *= __ldg(p.scale2 + cc);
+    if (p.accumulate) o += drow[cc];
+    drow[cc] = o;
+  }
+}
+
+// One epilogue warp (ew = 0..3) drains lanes [32*ew, 32*ew+32) of the accumulator at TMEM column `tmem_col0`.
+// rowpix[32]: output pixel offset of each of the warp's rows (-1 = row not stored).  `release()` is called once the
+// accumulator has been completely read (so the MMA warp may overwrite it).
+template <class Release>
+__device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
+                                           const long long* rowpix, int lane, Release release) {
+  const int sub_r = lane >> 3;          // row within a group of 4
+  const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
+  long long od[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
+  const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
+  const int nchunks = block_n / 32;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    uint32_t r[32];
+    tc::tmem_ld_x32(taddr + ch * 32, r);
+    tc::tmem_ld_wait();
+    if (ch == nchunks - 1) release();
+    const int col0 = n0 + ch * 32;
+    if (col0 >= p.nb) continue;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(stg + lane * ROW_FLOATS + q * 4) =
+          make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+    __syncwarp();
+    const int c = col0 + sub_c;
+    if (c < p.nb) {
+      if (p.vec_ok && c + 3 < p.nb) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), s2 = sc;
+        if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+        if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+        if (p.scale2) s2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
+        float4 ad[8], gt[8];
+        if (p.addend) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            ad[i] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + od[i] * p.ld_add + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.gate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            gt[i] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.gate + od[i] * p.ld_gate + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        if (p.accumulate) {
+          // rare (dgrad accumulation into an owned partial): reuse the addend slots
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (od[i] < 0) continue;
+            const float4 old = *reinterpret_cast<const float4*>(p.d + od[i] * p.ldd + c);
+            const float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c);
+            float4 o;
+            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+            if (p.addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+            o.x = fmaxf(o.x, relu_floor); o.y = fmaxf(o.y, relu_floor); o.z = fmaxf(o.z, relu_floor); o.w = fmaxf(o.w, relu_floor);
+            if (p.gate) {
+              o.x = gt[i].x > 0.f ? o.x : 0.f; o.y = gt[i].y > 0.f ? o.y : 0.f; o.z = gt[i].z > 0.f ? o.z : 0.f; o.w = gt[i].w > 0.f ? o.w : 0.f;
+            }
+            o.x = o.x * s2.x + old.x; o.y = o.y * s2.y + old.y; o.z = o.z * s2.z + old.z; o.w = o.w * s2.w + old.w;
+            *reinterpret_cast<float4*>(p.d + od[i] * p.ldd + c) = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (od[i] < 0) continue;
+            const float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c);
+            float4 o;
+            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+            if (p.addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+            o.x = fmaxf(o.x, relu_floor); o.y = fmaxf(o.y, relu_floor); o.z = fmaxf(o.z, relu_floor); o.w = fmaxf(o.w, relu_floor);
+            if (p.gate) {
+              o.x = gt[i].x > 0.f ? o.x : 0.f; o.y = gt[i].y > 0.f ? o.y : 0.f; o.z = gt[i].z > 0.f ? o.z : 0.f; o.w = gt[i].w > 0.f ? o.w : 0.f;
+            }
+            o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
+            *reinterpret_cast<float4*>(p.d + od[i] * p.ldd + c) = o;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          if (od[i] < 0) continue;
+          ragged_store(p, *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c), od[i], c);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace epi

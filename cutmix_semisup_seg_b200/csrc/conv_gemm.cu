@@ -18,6 +18,7 @@
 //     accumulate; output leading dimension + channel offset let a conv write into a slice of a wider
 //     buffer (no torch.cat), output stride/offset scatter handles strided dgrad.
 #include "tc_common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace {
 
@@ -27,9 +28,7 @@ constexpr int MAX_BLOCK_N = 256;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 4;  // 32 KB
-constexpr int EPI_ROW_FLOATS = 36;                          // 32 columns + 4 pad: conflict-free 128-bit smem access
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_FLOATS * 4;     // one 32x32 fp32 chunk per epilogue warp
-constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 4 * 32 * 8;  // staging + per-row output offsets
+constexpr int EPI_BYTES = epi::BYTES;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int MAX_TAPS = 16;
 constexpr int NUM_THREADS = 256;
@@ -188,18 +187,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // TMEM -> registers (thread = pixel row) -> padded smem (transpose) -> coalesced 128 B row segments to HBM:
-    // each group of 8 lanes reads/writes 32 consecutive channels of one pixel, so residual / gate loads and
-    // the output stores are full-line transactions instead of 32 scattered 16 B pieces per instruction.
+    // ===================== epilogue (conv_epilogue.cuh) =====================
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * EPI_ROW_FLOATS);
-    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * EPI_WARP_BYTES) + ew * 32;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * epi::ROW_FLOATS);
+    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * epi::WARP_BYTES) + ew * 32;
+    epi::Params ep;
+    ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
+    ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
+    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb;
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
-    const int sub_r = lane >> 3;          // row within a group of 4
-    const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(a, tile);
       {
@@ -217,74 +215,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * MAX_BLOCK_N;
-      const int nchunks = a.block_n / 32;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t r[32];
-        tc::tmem_ld_x32(taddr + ch * 32, r);
-        tc::tmem_ld_wait();
-        if (ch == nchunks - 1) {            // accumulator fully read: hand the TMEM stage back to the MMA warp
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
-        }
-        const int col0 = t.n_idx * a.block_n + ch * 32;
-        if (col0 >= a.nb) continue;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stg + lane * EPI_ROW_FLOATS + q * 4) =
-              make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, [&]() {
+        tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
-        const int c = col0 + sub_c;
-        if (c < a.nb) {
-          const bool vec = a.vec_ok && c + 3 < a.nb;
-          float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), s2 = make_float4(1, 1, 1, 1);
-          if (vec) {
-            if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + c));
-            if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + c));
-            if (a.scale2) s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + c));
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + sub_r;
-            const long long pix = rowpix[rr];
-            if (pix < 0) continue;
-            const float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_ROW_FLOATS + sub_c);
-            float* drow = a.d + pix * a.ldd;
-            if (vec) {
-              float4 o;
-              o.x = v.x * sc.x + sh.x; o.y = v.y * sc.y + sh.y; o.z = v.z * sc.z + sh.z; o.w = v.w * sc.w + sh.w;
-              if (a.addend) {
-                const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend + pix * a.ld_add + c));
-                o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-              }
-              if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (a.gate) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(a.gate + pix * a.ld_gate + c));
-                o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
-              }
-              o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
-              if (a.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(drow + c);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(drow + c) = o;
-            } else {
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cc = c + e;
-                if (cc < a.nb) {
-                  const float add = a.addend ? __ldg(a.addend + pix * a.ld_add + cc) : 0.f;
-                  const float gt = a.gate ? __ldg(a.gate + pix * a.ld_gate + cc) : 1.f;
-                  const float old = a.accumulate ? drow[cc] : 0.f;
-                  drow[cc] = epi1(a, vv[e], cc, add, gt, old);
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
+        if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -330,10 +265,8 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
 
 }  // namespace tc
 
-namespace {
-
 // Pick the (BW, BH, BN) pixel box of at most `max_rows` rows that wastes the fewest tile slots.
-void choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o) {
+void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o) {
   double best = -1.0; int bbw = 1, bbh = 1, bbn = 1;
   const int max_b = 256 / istride;
   for (int bw = 1; bw <= ow && bw <= max_rows && bw <= max_b; ++bw) {
@@ -350,7 +283,8 @@ void choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int
   *bw_o = bbw; *bh_o = bbh; *bn_o = bbn;
 }
 
-}  // namespace
+int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream);   // conv_gemm2.cu
+int g_conv_force_1cta = 0;
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   B2_REQUIRE(p && p->a && p->b && p->d, "b2_conv_gemm: null tensor");
@@ -363,12 +297,18 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   B2_REQUIRE(p->n_split == 1 || (p->a_lo && p->b_lo), "b2_conv_gemm: split mode needs a_lo and b_lo");
   B2_REQUIRE(p->ldd >= 1 && p->fh >= 1 && p->fw >= 1, "b2_conv_gemm: bad output geometry");
 
+  for (int i = 0; i < p->n_taps; ++i)
+    B2_REQUIRE(p->taps[i * 3 + 2] >= 0 && p->taps[i * 3 + 2] < p->tb, "b2_conv_gemm: tap %d references weight tap %d >= %d", i, p->taps[i * 3 + 2], p->tb);
+  // N tiles of 256 output channels run on CTA pairs (tcgen05 cta_group::2): see conv_gemm2.cu
+  if (p->nb > 224 && !g_conv_force_1cta && b2_sm_count_cached() >= 2 && (p->max_ctas == 0 || p->max_ctas >= 2))
+    return b2_conv_gemm_2cta(p, stream);
+
   ConvKArgs a;
   memset(&a, 0, sizeof(a));
   a.n = p->n; a.ih = p->ih; a.iw = p->iw; a.k = p->k; a.nb = p->nb; a.oh = p->oh; a.ow = p->ow;
   a.fh = p->fh; a.fw = p->fw; a.ldd = p->ldd; a.ostride = p->ostride; a.ooh = p->ooh; a.oow = p->oow;
   a.istride = p->istride;
-  choose_box(p->ow, p->oh, p->n, BLOCK_M, p->istride, &a.bw, &a.bh, &a.bn);
+  b2_choose_box(p->ow, p->oh, p->n, BLOCK_M, p->istride, &a.bw, &a.bh, &a.bn);
   a.tiles_w = (p->ow + a.bw - 1) / a.bw; a.tiles_h = (p->oh + a.bh - 1) / a.bh; a.tiles_n = (p->n + a.bn - 1) / a.bn;
   int block_n = ((p->nb + 31) / 32) * 32;
   if (block_n > MAX_BLOCK_N) block_n = MAX_BLOCK_N;

@@ -1,0 +1,354 @@
+// 2-CTA variant of the implicit-GEMM convolution (see conv_gemm.cu for the single-CTA kernel and the GEMM view).
+//
+// Why: with kind::tf32 a 128x256x8 MMA reads 12 KB of operands from shared memory while TMA writes the same 12 KB,
+// i.e. ~192 B/cycle against a ~128 B/cycle shared-memory port: the single-CTA kernel saturates at ~63 % tensor-pipe
+// (ncu, profiles/r01_v1_conv_gemm_aspp_d12.txt; the MMA issuer never waits for data, the producer waits for slots).
+// Here the two CTAs of a cluster (one SM pair) execute ONE tcgen05.mma.cta_group::2 of shape M256 x N256 x K8: each CTA
+// holds its own 128 pixel rows of A and HALF of the weight tile (128 of the 256 output channels), so per CTA and K step
+// shared memory sees 8 KB of reads + 8 KB of TMA writes, and L2 -> SM traffic per MAC drops by a third.
+//
+// Protocol (leader = cluster rank 0):
+//   * both CTAs run a TMA producer; their loads carry .cta_group::2 and complete on the LEADER's full barrier, which the
+//     leader arms with the byte count of both CTAs;
+//   * only the leader issues MMAs; tcgen05.commit.cta_group::2 ... multicast::cluster releases the smem stage in both
+//     CTAs and publishes the finished accumulator to both epilogues;
+//   * each CTA's TMEM holds its 128 rows of the 256-row accumulator; both epilogues arrive (the peer remotely) on the
+//     leader's "accumulator empty" barrier.
+#include "tc_common.cuh"
+#include "conv_epilogue.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;            // per CTA; the pair computes 256 rows
+constexpr int BLOCK_K = 32;
+constexpr int BLOCK_N = 256;
+constexpr int STAGES = 6;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB
+constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;      // 16 KB: this CTA's half of the weight tile
+constexpr int EPI_BYTES = epi::BYTES;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + EPI_BYTES;
+constexpr int MAX_TAPS = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+struct Conv2KArgs {
+  int n, ih, iw, k;
+  int nb;
+  int oh, ow;
+  int fh, fw, ldd, ostride, ooh, oow;
+  int istride;
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles_n;
+  int num_pairs;              // (pairs of M tiles) x (N tiles)
+  int n_taps;
+  short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
+  int kblocks;
+  int n_pass;
+  float* d;
+  const float* scale; const float* shift;
+  const float* addend; const float* gate; const float* scale2;
+  int ld_add, ld_gate;
+  int relu, accumulate;
+  int vec_ok;
+};
+
+struct TileInfo {
+  int n_idx, w0, h0, n0;
+  uint32_t tap_mask;
+};
+
+__device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, int m) {
+  const int wt = m % a.tiles_w; m /= a.tiles_w;
+  const int ht = m % a.tiles_h;
+  if (m / a.tiles_h >= a.tiles_n) return 0;       // phantom tile of an odd tile count
+  const int w0 = wt * a.bw, h0 = ht * a.bh;
+  uint32_t mask = 0;
+  for (int i = 0; i < a.n_taps; ++i) {
+    const int lo_h = h0 * a.istride + a.dh[i], hi_h = lo_h + (a.bh - 1) * a.istride;
+    const int lo_w = w0 * a.istride + a.dw[i], hi_w = lo_w + (a.bw - 1) * a.istride;
+    if (hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw) mask |= 1u << i;
+  }
+  return mask;
+}
+
+// `pair` indexes (pair of adjacent M tiles, N tile), N fastest; `half` selects this CTA's M tile.  The tap mask is the
+// union over both halves: the two producers and the single MMA issuer must walk the same K sequence.
+__device__ __forceinline__ TileInfo decode_tile(const Conv2KArgs& a, int pair, int half) {
+  TileInfo t;
+  t.n_idx = pair % a.n_tiles_n;
+  const int mp = pair / a.n_tiles_n;
+  const uint32_t both = tile_tap_mask(a, mp * 2) | tile_tap_mask(a, mp * 2 + 1);
+  int m = mp * 2 + half;
+  const int wt = m % a.tiles_w; m /= a.tiles_w;
+  const int ht = m % a.tiles_h;
+  const int nt = m / a.tiles_h;                   // == tiles_n for the phantom tile: every pixel out of range
+  t.w0 = wt * a.bw; t.h0 = ht * a.bh; t.n0 = nt * a.bn;
+  t.tap_mask = both ? both : 1u;
+  return t;
+}
+
+__device__ __forceinline__ float epi1(const Conv2KArgs& a, float v, int c, float add, float gate, float old) {
+  if (a.scale) v *= __ldg(a.scale + c);
+  if (a.shift) v += __ldg(a.shift + c);
+  if (a.addend) v += add;
+  if (a.relu) v = fmaxf(v, 0.0f);
+  if (a.gate) v = gate > 0.0f ? v : 0.0f;
+  if (a.scale2) v *= __ldg(a.scale2 + c);
+  if (a.accumulate) v += old;
+  return v;
+}
+
+// ---- cta_group::2 / cluster PTX ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared-window address -> leader CTA
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma2_commit_mcast(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (local when this CTA is the leader)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(tc::smem_u32(bar)));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                  const __grid_constant__ Conv2KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                        // [STAGES]  (leader's copies are the live ones)
+  uint64_t* empty_bar = bars + STAGES;              // [STAGES]  per CTA
+  uint64_t* tfull_bar = bars + 2 * STAGES;          // [2]       per CTA
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;     // [2]       leader's copies are the live ones
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmB);
+    if (a.n_pass > 1) { tc::tma_prefetch_desc(&tmAlo); tc::tma_prefetch_desc(&tmBlo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 8); }   // 4 warps x 2 CTAs
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem2_alloc(tmem_ptr, TMEM_COLS);
+    tmem2_relinquish();
+  }
+  tc::tc_fence_before();
+  cluster_sync_all();                               // barriers of BOTH CTAs initialised, TMEM allocated
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const uint32_t rows_a = a.bw * a.bh * a.bn;
+  const uint32_t stage_tx = 2u * (rows_a * 128u + (uint32_t)(BLOCK_N / 2) * 128u);     // both CTAs' bytes
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
+        const TileInfo t = decode_tile(a, pair, (int)rank);
+        for (int tap = 0; tap < a.n_taps; ++tap) {
+          if (!(t.tap_mask >> tap & 1)) continue;
+          const int cw = t.w0 * a.istride + a.dw[tap];
+          const int ch = t.h0 * a.istride + a.dh[tap];
+          const int bt = a.btap[tap];
+          for (int kb = 0; kb < a.kblocks; ++kb) {
+            for (int p = 0; p < a.n_pass; ++p) {
+              tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
+              tma2_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
+                           kb * BLOCK_K, cw, ch, t.n0);
+              tma2_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
+                           kb * BLOCK_K, bt, t.n_idx * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(2 * BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
+        const TileInfo t = decode_tile(a, pair, 0);
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        uint32_t first = 1;
+        const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
+        for (int it = 0; it < iters; ++it) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
+            const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
+            const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
+            mma2_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          mma2_commit_mcast(&empty_bar[stage]);   // frees this stage in both CTAs when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma2_commit_mcast(&tfull_bar[acc]);       // accumulator complete -> both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows; conv_epilogue.cuh) =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * epi::ROW_FLOATS);
+    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * epi::WARP_BYTES) + ew * 32;
+    epi::Params ep;
+    ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
+    ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
+    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int bwbh = a.bw * a.bh;
+    for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
+      const TileInfo t = decode_tile(a, pair, (int)rank);
+      {
+        const int dn = row / bwbh;
+        const int rem = row - dn * bwbh;
+        const int dhh = rem / a.bw;
+        const int dww = rem - dhh * a.bw;
+        const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
+        const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
+        const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
+        __syncwarp();
+        rowpix[lane] = valid ? pix : -1;
+        __syncwarp();
+      }
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, [&]() {
+        tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  cluster_sync_all();                               // nobody leaves (or frees TMEM) while the pair is still working
+  if (warp == 2) tmem2_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+// choose_box is defined in conv_gemm.cu
+void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
+
+int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
+  Conv2KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = p->n; a.ih = p->ih; a.iw = p->iw; a.k = p->k; a.nb = p->nb; a.oh = p->oh; a.ow = p->ow;
+  a.fh = p->fh; a.fw = p->fw; a.ldd = p->ldd; a.ostride = p->ostride; a.ooh = p->ooh; a.oow = p->oow;
+  a.istride = p->istride;
+  b2_choose_box(p->ow, p->oh, p->n, BLOCK_M, p->istride, &a.bw, &a.bh, &a.bn);
+  a.tiles_w = (p->ow + a.bw - 1) / a.bw; a.tiles_h = (p->oh + a.bh - 1) / a.bh; a.tiles_n = (p->n + a.bn - 1) / a.bn;
+  a.n_tiles_n = (p->nb + BLOCK_N - 1) / BLOCK_N;
+  const int64_t m_tiles = (int64_t)a.tiles_w * a.tiles_h * a.tiles_n;
+  const int64_t num_pairs = ((m_tiles + 1) / 2) * a.n_tiles_n;
+  B2_REQUIRE(num_pairs < (1ll << 30), "b2_conv_gemm: too many tiles");
+  a.num_pairs = (int)num_pairs;
+  a.n_taps = p->n_taps;
+  for (int i = 0; i < p->n_taps; ++i) {
+    a.dh[i] = (short)p->taps[i * 3 + 0]; a.dw[i] = (short)p->taps[i * 3 + 1]; a.btap[i] = (short)p->taps[i * 3 + 2];
+  }
+  a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
+  a.n_pass = p->n_split;
+  a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
+  a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
+             (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  {
+    const uint64_t dims[4] = {(uint64_t)p->k, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
+    const uint64_t strides[3] = {(uint64_t)p->lda * 4, (uint64_t)p->iw * p->lda * 4, (uint64_t)p->ih * p->iw * p->lda * 4};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn};
+    const uint32_t es[4] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1};
+    int rc = tc::make_tmap_f32(&tmA, p->a, 4, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmAlo, p->a_lo ? p->a_lo : p->a, 4, dims, strides, box, es); if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)p->k, (uint64_t)p->tb, (uint64_t)p->nb};
+    const uint64_t strides[2] = {(uint64_t)p->ldb * 4, (uint64_t)p->tb * p->ldb * 4};
+    const uint32_t box[3] = {BLOCK_K, 1, (uint32_t)(BLOCK_N / 2)};
+    const uint32_t es[3] = {1, 1, 1};
+    int rc = tc::make_tmap_f32(&tmB, p->b, 3, dims, strides, box, es); if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmBlo, p->b_lo ? p->b_lo : p->b, 3, dims, strides, box, es); if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int sms = b2_sm_count_cached();
+  if (sms <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_gemm: no CUDA device");
+  if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
+  int clusters = sms / 2;
+  if (clusters < 1) clusters = 1;
+  if (clusters > a.num_pairs) clusters = a.num_pairs;
+  conv_gemm2_kernel<<<clusters * 2, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+  B2_LAUNCH_CHECK("conv_gemm2_kernel");
+  return B2_OK;
+}

@@ -167,7 +167,7 @@ typedef struct b2_wgrad_params {
 size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p);
 int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
 
-/* Debug knob (tests only): key 1 = wgrad smem-descriptor variant. */
+/* Debug knobs (tests only): key 1 = wgrad smem-descriptor variant; key 2 = 1 forces the single-CTA conv kernel. */
 void b2_debug_set(int key, int value);
 
 /* hi = x with the 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact). */
