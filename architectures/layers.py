@@ -74,7 +74,7 @@ class B2Dropout(nn.Module):
         super(B2Dropout, self).__init__()
         self.p = p
         self._injected = []
-        self._counter = 0
+        self._dev_counter = None
         self.seed = 0x5EED
 
     def inject(self, masks):
@@ -86,12 +86,16 @@ class B2Dropout(nn.Module):
             m = self._injected.pop(0).to(device=device, dtype=torch.float32).contiguous()
             assert tuple(m.shape) == (n, h, w, c), 'injected dropout mask has shape {}'.format(tuple(m.shape))
             return m
-        self._counter += 1
-        return kernels.dropout_mask(n, h, w, c, self.p, self.seed, self._counter * (1 << 40), device)
+        # the stream position lives on the device so that a CUDA-graph replay still draws a fresh mask
+        if self._dev_counter is None or self._dev_counter.device != torch.device(device):
+            self._dev_counter = torch.zeros((1,), dtype=torch.int64, device=device)
+        self._dev_counter += n * h * w * c
+        return kernels.dropout_mask(n, h, w, c, self.p, self.seed, 0, device, offset_dev=self._dev_counter)
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_injected'] = []
+        d['_dev_counter'] = None
         return d
 
 

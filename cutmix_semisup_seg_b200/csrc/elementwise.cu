@@ -287,7 +287,9 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t count, float p, uint64_t seed, uint64_t offset) {
+__global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t count, float p, uint64_t seed, uint64_t offset,
+                                    const uint64_t* __restrict__ offset_dev) {
+  if (offset_dev) offset += offset_dev[0];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
     const uint64_t r = splitmix64(seed ^ splitmix64(offset + (uint64_t)i));
@@ -295,12 +297,13 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t count, flo
     mask[i] = u >= p ? 1.0f : 0.0f;
   }
 }
-extern "C" int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                               void* stream) {
   if (count == 0) return B2_OK;
   B2_REQUIRE(mask && count > 0 && p >= 0.f && p < 1.f, "b2_dropout_mask: bad args");
   int64_t blocks = ceil_div64(count, 256 * 4);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, count, p, seed, offset);
+  dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, count, p, seed, offset, offset_dev);
   B2_LAUNCH_CHECK("dropout_mask_kernel");
   return B2_OK;
 }

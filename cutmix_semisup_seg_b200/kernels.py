@@ -236,9 +236,9 @@ class ActKernels(object):
         else:
             raise NotImplementedError('fill of a strided slice')
 
-    def dropout_mask(self, n, h, w, c, p, seed, offset, device):
+    def dropout_mask(self, n, h, w, c, p, seed, offset, device, offset_dev=None):
         mask = torch.empty((n, h, w, c), device=device, dtype=torch.float32)
-        self.be.dropout_mask(mask, p, seed, offset)
+        self.be.dropout_mask(mask, p, seed, offset, offset_dev=offset_dev)
         return mask
 
     # device-tensor helpers (allocation is plumbing, done through torch)

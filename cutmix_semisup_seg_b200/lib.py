@@ -103,7 +103,7 @@ _SIGS = {
     'b2_bn_fold': (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp]),
     'b2_bn_eval_param_grad': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int,
                                       c_vp, c_vp, c_int, c_vp, c_vp]),
-    'b2_dropout_mask': (c_int, [c_vp, c_i64, c_f32, c_u64, c_u64, c_vp]),
+    'b2_dropout_mask': (c_int, [c_vp, c_i64, c_f32, c_u64, c_u64, c_vp, c_vp]),
     'b2_add_inplace': (c_int, [c_vp, c_vp, c_i64, c_vp]),
     'b2_fill': (c_int, [c_vp, c_f32, c_i64, c_vp]),
     'b2_colsum': (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_int, c_vp, c_vp]),

@@ -291,8 +291,9 @@ class CudaBackend(object):
     def slice_copy(self, dst_ptr, ldd, src_ptr, lds, rows, c, accumulate=False):
         self._call('b2_slice_copy', dst_ptr, ldd, src_ptr, lds, rows, c, int(bool(accumulate)), self._s())
 
-    def dropout_mask(self, mask, p, seed, offset):
-        self._call('b2_dropout_mask', mask.data_ptr(), mask.numel(), float(p), int(seed), int(offset), self._s())
+    def dropout_mask(self, mask, p, seed, offset, offset_dev=None):
+        self._call('b2_dropout_mask', mask.data_ptr(), mask.numel(), float(p), int(seed), int(offset), L.ptr(offset_dev),
+                   self._s())
 
     _ws = None
 

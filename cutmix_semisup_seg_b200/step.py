@@ -56,7 +56,8 @@ class FlatGrads(object):
         backend.fill(self.flat, 0.0)
 
 
-def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4):
+def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4,
+                   capturable=False):
     """torch.optim optimiser on the reference's parameter groups (train_seg_semisup_mask_mt.py:90-100): group 0 =
     `pretrained_parameters()` at 0.1 x lr, group 1 = `new_parameters()` at lr.  DeepLab v2's group 0 repeats tensors
     (reference quirk): a tensor listed k times must receive k sequential updates per step, which only the
@@ -69,6 +70,8 @@ def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_n
     groups = [dict(params=g0, lr=learning_rate * 0.1), dict(params=g1, lr=learning_rate)]
     on_cuda = all(p.is_cuda for p in g0 + g1)
     kw = dict(foreach=False) if (dup or not on_cuda) else dict(fused=True)
+    if capturable and opt_type == 'adam' and on_cuda:
+        kw['capturable'] = True          # step counters live on the device: the step can be replayed from a CUDA graph
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         if opt_type == 'adam':
@@ -98,7 +101,7 @@ def average_gradients(flat, dist, group=None):
 class MeanTeacherStep(object):
     def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
                  cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True):
+                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True, use_cuda_graph=False):
         self.student_net, self.teacher_net = student_net, teacher_net
         self.student_optim, self.teacher_optim = student_optim, teacher_optim
         self.mask_generator = mask_generator
@@ -115,6 +118,12 @@ class MeanTeacherStep(object):
             self.group = dist_group if dist_group is not True else None
             self.world = dist.get_world_size(self.group)
         self.flat = FlatGrads(list(student_net.parameters())) if (use_flat_grads or self.world > 1) else None
+        # CUDA-graph replay of the iteration (the eager path issues ~6000 launches per iteration from Python and is
+        # host-bound: profiles/r01_v2_*).  Two graphs: forward/backward/losses, and optimiser + EMA, with the
+        # gradient all-reduce between them.
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.launches_per_replay = 0
 
     # ------------------------------------------------------------------------------------------
     def _zero_grad(self):
@@ -167,11 +176,50 @@ class MeanTeacherStep(object):
         self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])
         return out4
 
-    def step(self, sup_batch, unsup_batches, ramp_val=1.0):
-        """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
-        unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
-        mode) or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
-        {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising."""
+    def _capture(self, sup_batch, unsup_batches, ramp_val):
+        dev = sup_batch[0].device if sup_batch[0].is_cuda else next(self.student_net.parameters()).device
+        st_sup = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in sup_batch)
+        st_uns = []
+        for ub in unsup_batches:
+            cache, d = {}, {}
+            for k, v in ub.items():
+                if id(v) not in cache:
+                    cache[id(v)] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                d[k] = cache[id(v)]
+            st_uns.append(d)
+        self._static = (st_sup, st_uns)
+        self._load_static(sup_batch, unsup_batches)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, lazy inits)
+            self._fwd_bwd(st_sup, st_uns, ramp_val)
+            self._allreduce()
+            self._opt_ema()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = self.be.launches
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            out = self._fwd_bwd(st_sup, st_uns, ramp_val)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._opt_ema()
+        self.launches_per_replay = self.be.launches - l0
+        self._graph = (g1, g2, out, float(ramp_val), tuple(tuple(t.shape) for t in sup_batch))
+
+    def _load_static(self, sup_batch, unsup_batches):
+        st_sup, st_uns = self._static
+        for dst, src in zip(st_sup, sup_batch):
+            dst.copy_(src, non_blocking=True)
+        for d, ub in zip(st_uns, unsup_batches):
+            done = set()
+            for k, v in ub.items():
+                if id(d[k]) not in done:
+                    d[k].copy_(v, non_blocking=True)
+                    done.add(id(d[k]))
+
+    def _fwd_bwd(self, sup_batch, unsup_batches, ramp_val):
         self._zero_grad()                                              # :290
         sup_loss = self.supervised(*sup_batch)
         cons, conf = None, None
@@ -184,8 +232,37 @@ class MeanTeacherStep(object):
                     out4 = self.unsupervised_cut(ub['ux_tea'], ub['ux_stu'], ub['um'], ub['mask_params'], ramp_val)
                 cons = out4[0] if cons is None else cons + out4[0]
                 conf = out4[1] if conf is None else conf + out4[1]
-        self._allreduce()
+        return {'sup_loss': sup_loss, 'cons_loss': cons, 'conf_rate': conf}
+
+    def _opt_ema(self):
         self.student_optim.step()                                      # :465
         if self.teacher_optim is not None:
             self.teacher_optim.step()                                  # :466-467
-        return {'sup_loss': sup_loss, 'cons_loss': cons, 'conf_rate': conf}
+
+    def step(self, sup_batch, unsup_batches, ramp_val=1.0, eager=False):
+        """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
+        unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
+        mode) or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
+        {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising.  With `use_cuda_graph` the iteration is captured
+        once per (shapes, ramp value) and replayed; inputs may then be pinned host tensors (copied straight into the
+        graph's static buffers)."""
+        if self.use_cuda_graph and not eager:
+            key = (float(ramp_val), tuple(tuple(t.shape) for t in sup_batch))
+            if self._graph is None or (self._graph[3], self._graph[4]) != key:
+                self._capture(sup_batch, unsup_batches, ramp_val)
+            self._load_static(sup_batch, unsup_batches)
+            g1, g2, out = self._graph[0], self._graph[1], self._graph[2]
+            g1.replay()
+            self._allreduce()
+            g2.replay()
+            self.be.launches += self.launches_per_replay
+            return out
+        sup_batch = tuple(t.to(self._device(), non_blocking=True) for t in sup_batch)
+        out = self._fwd_bwd(sup_batch, [{k: v.to(self._device(), non_blocking=True) for k, v in ub.items()} for ub in unsup_batches],
+                            ramp_val)
+        self._allreduce()
+        self._opt_ema()
+        return out
+
+    def _device(self):
+        return next(self.student_net.parameters()).device

@@ -234,9 +234,10 @@ int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, 
                           const float* gamma, const float* beta, const float* gate, int ldg,
                           const float* sub, int lds, float* dgamma, float* dbeta, int accumulate,
                           double* workspace, void* stream);
-/* dropout mask: mask[i] = (philox(seed, offset+i) >= p) ? 1 : 0 */
+/* dropout keep-mask: mask[i] = (hash(seed, offset + *offset_dev + i) >= p) ? 1 : 0; offset_dev (may be NULL) is a
+ * device counter so that CUDA-graph replays advance the random stream. */
 int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset,
-                    void* stream);
+                    const uint64_t* offset_dev, void* stream);
 /* elementwise helpers used by the backward pass */
 int b2_relu_gate(float* g, int ldg, const float* y, int ldy, int64_t rows, int c, void* stream);
 int b2_slice_copy(float* dst, int ldd, const float* src, int lds, int64_t rows, int c, int accumulate,

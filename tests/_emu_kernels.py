@@ -252,8 +252,9 @@ class EmuKernels(object):
     def fill_act(self, a, value):
         a.view4().fill_(value)
 
-    def dropout_mask(self, n, h, w, c, p, seed, offset, device):
-        g = torch.Generator().manual_seed((seed + offset) % (2 ** 31))
+    def dropout_mask(self, n, h, w, c, p, seed, offset, device, offset_dev=None):
+        off = offset + (int(offset_dev[0]) if offset_dev is not None else 0)
+        g = torch.Generator().manual_seed((seed + off) % (2 ** 31))
         return (torch.rand((n, h, w, c), generator=g) >= p).float()
 
     @staticmethod
