@@ -189,6 +189,7 @@ class MeanTeacherStep(object):
             st_uns.append(d)
         self._static = (st_sup, st_uns)
         self._load_static(sup_batch, unsup_batches)
+        snap = self._snapshot()            # the warm-up iteration below must not count as a training step
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -206,7 +207,40 @@ class MeanTeacherStep(object):
         with torch.cuda.graph(g2, pool=g1.pool()):
             self._opt_ema()
         self.launches_per_replay = self.be.launches - l0
+        self._restore(snap)
         self._graph = (g1, g2, out, float(ramp_val), tuple(tuple(t.shape) for t in sup_batch))
+
+    def _state_tensors(self):
+        ts = list(self.student_net.state_dict().values())
+        if self.teacher_net is not self.student_net:
+            ts += list(self.teacher_net.state_dict().values())
+        for net in (self.student_net, self.teacher_net):
+            for m in net.modules():
+                c = getattr(m, '_dev_counter', None)
+                if c is not None:
+                    ts.append(c)
+        return ts
+
+    def _snapshot(self):
+        opt = {}
+        for p, st in self.student_optim.state.items():
+            opt[id(p)] = {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+        return [t.clone() for t in self._state_tensors()], opt
+
+    def _restore(self, snap):
+        """In-place restore (the captured graphs hold the addresses of these tensors)."""
+        tensors, opt = snap
+        with torch.no_grad():
+            for dst, src in zip(self._state_tensors(), tensors):
+                dst.copy_(src)
+            for p, st in self.student_optim.state.items():
+                old = opt.get(id(p))
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()          # state created by the warm-up step: back to its initial value
 
     def _load_static(self, sup_batch, unsup_batches):
         st_sup, st_uns = self._static
