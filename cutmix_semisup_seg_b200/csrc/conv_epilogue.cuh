@@ -17,7 +17,8 @@ namespace epi {
 
 constexpr int ROW_FLOATS = 36;                      // 32 columns + 4 pad: conflict-free 128-bit smem access
 constexpr int WARP_BYTES = 32 * ROW_FLOATS * 4;
-constexpr int BYTES = 4 * WARP_BYTES + 4 * 32 * 8;  // staging tiles + per-row pixel offsets
+constexpr int NUM_WARPS = 8;                        // two warps per TMEM lane quarter (even / odd 32-column chunks)
+constexpr int BYTES = NUM_WARPS * WARP_BYTES + NUM_WARPS * 32 * 8;  // staging tiles + per-row pixel offsets
 
 struct Params {
   float* d; int ldd;
@@ -48,9 +49,11 @@ static __device__ __noinline__ void ragged_store(const Params& p, float4 v, long
 // One epilogue warp (ew = 0..3) drains lanes [32*ew, 32*ew+32) of the accumulator at TMEM column `tmem_col0`.
 // rowpix[32]: output pixel offset of each of the warp's rows (-1 = row not stored).  `release()` is called once the
 // accumulator has been completely read (so the MMA warp may overwrite it).
+// `half` (0/1) selects the even or odd chunks: two warps share a lane quarter so that twice as many loads/stores are in
+// flight per SM (the epilogue of the HBM-bound 1x1 layers is latency-bound, not issue-bound).
 template <class Release>
 __device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                           const long long* rowpix, int lane, Release release) {
+                                           const long long* rowpix, int lane, int half, Release release) {
   const int sub_r = lane >> 3;          // row within a group of 4
   const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
   long long od[8];
@@ -58,11 +61,12 @@ __device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int 
   for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
   const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
   const int nchunks = block_n / 32;
-  for (int ch = 0; ch < nchunks; ++ch) {
+  if (half >= nchunks) release();       // nothing to read for this warp: still owes its arrival
+  for (int ch = half; ch < nchunks; ch += 2) {
     uint32_t r[32];
     tc::tmem_ld_x32(taddr + ch * 32, r);
     tc::tmem_ld_wait();
-    if (ch == nchunks - 1) release();
+    if (ch + 2 >= nchunks) release();
     const int col0 = n0 + ch * 32;
     if (col0 >= p.nb) continue;
 #pragma unroll

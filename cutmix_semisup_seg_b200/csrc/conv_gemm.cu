@@ -24,14 +24,15 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                       // fp32 elements = 128 bytes
-constexpr int MAX_BLOCK_N = 256;
+constexpr int MAX_BLOCK_N = 224;                  // wider N tiles run on CTA pairs (conv_gemm2.cu)
+constexpr int ACC_COLS = 256;                     // TMEM columns per accumulator stage
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K * 4;  // 32 KB
 constexpr int EPI_BYTES = epi::BYTES;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int MAX_TAPS = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 
 struct ConvKArgs {
@@ -114,7 +115,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 8); }
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -164,7 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const TileInfo t = decode_tile(a, tile);
         tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
         uint32_t first = 1;
         const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
         for (int it = 0; it < iters; ++it) {
@@ -188,10 +189,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (conv_epilogue.cuh) =====================
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;        // TMEM lane quarter
+    const int eh = (warp - 4) >> 2;       // even / odd chunks
+    const int ewi = warp - 4;
     const int row = ew * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * epi::ROW_FLOATS);
-    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * epi::WARP_BYTES) + ew * 32;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ewi * (32 * epi::ROW_FLOATS);
+    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
     epi::Params ep;
     ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
     ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
@@ -214,8 +217,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * MAX_BLOCK_N;
-      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, [&]() {
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
+      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);

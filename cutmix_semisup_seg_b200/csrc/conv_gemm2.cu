@@ -22,13 +22,13 @@ namespace {
 constexpr int BLOCK_M = 128;            // per CTA; the pair computes 256 rows
 constexpr int BLOCK_K = 32;
 constexpr int BLOCK_N = 256;
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB
 constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;      // 16 KB: this CTA's half of the weight tile
 constexpr int EPI_BYTES = epi::BYTES;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + EPI_BYTES;
 constexpr int MAX_TAPS = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 
 struct Conv2KArgs {
@@ -176,7 +176,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 8); }   // 4 warps x 2 CTAs
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 16); }   // 8 warps x 2 CTAs
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -250,10 +250,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows; conv_epilogue.cuh) =====================
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;        // TMEM lane quarter
+    const int eh = (warp - 4) >> 2;       // even / odd chunks
+    const int ewi = warp - 4;
     const int row = ew * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ew * (32 * epi::ROW_FLOATS);
-    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 4 * epi::WARP_BYTES) + ew * 32;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ewi * (32 * epi::ROW_FLOATS);
+    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
     epi::Params ep;
     ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
     ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
@@ -277,7 +279,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, [&]() {
+      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);

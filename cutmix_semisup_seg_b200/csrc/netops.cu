@@ -48,25 +48,30 @@ extern "C" int b2_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h
 // ------------------------------------------------------------------------------------------ im2col
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n, int h, int w, int c, int ldx,
                               int kh, int kw, int stride, int pad, int dil, int oh, int ow, int kpad) {
-  const int64_t total = (int64_t)n * oh * ow * kpad;
+  // one thread per (output pixel, filter row r): copies kw pixels x c channels = one contiguous run of the column row;
+  // thread 0 of each pixel also zero-fills the K padding.
+  const int64_t total = (int64_t)n * oh * ow * kh;
   const int kreal = kh * kw * c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % kpad); int64_t row = i / kpad;
-    float v = 0.f;
-    if (j < kreal) {
-      const int cc = j % c; const int t = j / c; const int s = t % kw; const int r = t / kw;
-      const int x_o = (int)(row % ow); row /= ow; const int y_o = (int)(row % oh); const int img = (int)(row / oh);
-      const int iy = y_o * stride - pad + r * dil, ix = x_o * stride - pad + s * dil;
-      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((int64_t)img * h + iy) * w + ix) * ldx + cc);
+    const int r = (int)(i % kh); int64_t row = i / kh;
+    const int x_o = (int)(row % ow); int64_t t = row / ow; const int y_o = (int)(t % oh); const int img = (int)(t / oh);
+    float* dst = col + row * kpad + (int64_t)r * kw * c;
+    const int iy = y_o * stride - pad + r * dil;
+    const bool yin = iy >= 0 && iy < h;
+    for (int s_ = 0; s_ < kw; ++s_) {
+      const int ix = x_o * stride - pad + s_ * dil;
+      const bool in = yin && ix >= 0 && ix < w;
+      const float* src = x + (((int64_t)img * h + iy) * w + ix) * ldx;
+      for (int cc = 0; cc < c; ++cc) dst[s_ * c + cc] = in ? __ldg(src + cc) : 0.f;
     }
-    col[i] = v;
+    if (r == 0) for (int j = kreal; j < kpad; ++j) col[row * kpad + j] = 0.f;
   }
 }
 extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
                          int dil, int oh, int ow, int kpad, void* stream) {
   B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
-  const int64_t total = (int64_t)n * oh * ow * kpad;
-  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  const int64_t total = (int64_t)n * oh * ow * kh;
+  int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 64) blocks = 148 * 64;
   im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, col, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad);
   B2_LAUNCH_CHECK("im2col_kernel");
   return B2_OK;
@@ -278,7 +283,7 @@ extern "C" int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw
 // MODE 1: (x, x*x)          BN statistics
 // MODE 2: (g, g*xhat)       BN backward, g = dy * gate(y) * drop, xhat = (x - mean) * rstd
 // MODE 3: (g, g*y)          frozen-BN parameter gradients (y = BN output proxy), g = dy gated by gate>0
-constexpr int RED_ROWS_PER_CHUNK = 512;
+constexpr int RED_ROWS_PER_CHUNK = 2048;
 struct RedArgs {
   const float* a; int lda;      // dy or x
   const float* b; int ldb;      // x (mode 2) / y (mode 3)
@@ -287,47 +292,108 @@ struct RedArgs {
   const float* mean; const float* rstd;
   const float* sub; int lds;    // mode 3: o = b - sub (residual removed from the block output)
   int64_t rows; int c;
+  int vec;                      // every pointer 16 B aligned and every ld / c a multiple of 4
 };
+// Block = 32 channels x one chunk of rows.  Thread (cg = tid & 7, rl = tid >> 3) owns 4 consecutive channels and walks
+// rows rl, rl+32, ... with 16 B loads: 8 lanes cover a 128 B row segment, a warp covers 4 rows per instruction, and the
+// loop is unrolled so that 8-12 independent 16 B loads per thread are in flight (HBM-bound kernel).
 template <int MODE>
 __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __restrict__ partial) {
   __shared__ double sm[8][32][2];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int ch = blockIdx.y * 32 + cx;
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch0 = blockIdx.y * 32 + cg * 4;
   const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS_PER_CHUNK;
   int64_t r1 = r0 + RED_ROWS_PER_CHUNK; if (r1 > r.rows) r1 = r.rows;
-  double s0 = 0.0, s1 = 0.0;
-  if (ch < r.c) {
-    float mean = 0.f, rstd = 1.f;
-    if (MODE == 2) { mean = r.mean[ch]; rstd = r.rstd[ch]; }
-    for (int64_t row = r0 + ry; row < r1; row += 8) {
-      float v = __ldg(r.a + row * r.lda + ch);
-      if (MODE == 0) { s0 += v; }
-      else if (MODE == 1) { s0 += v; s1 += (double)v * (double)v; }
-      else {
-        if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
-        if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
-        float bv = __ldg(r.b + row * r.ldb + ch);
-        if (MODE == 3 && r.sub) bv -= __ldg(r.sub + row * r.lds + ch);
-        const float o = MODE == 2 ? (bv - mean) * rstd : bv;
-        s0 += v; s1 += (double)v * (double)o;
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1};
+  if (MODE == 2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (ch0 + e < r.c) { mean[e] = r.mean[ch0 + e]; rstd[e] = r.rstd[ch0 + e]; }
+  }
+  if (r.vec && ch0 + 3 < r.c) {
+#pragma unroll 2
+    for (int64_t row = r0 + rl; row < r1; row += 32) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(r.a + row * r.lda + ch0));
+      float va[4] = {v.x, v.y, v.z, v.w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s0[e] += va[e];
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s0[e] += va[e]; s1[e] += (double)va[e] * (double)va[e]; }
+      } else {
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(r.b + row * r.ldb + ch0));
+        float vb[4] = {bq.x, bq.y, bq.z, bq.w};
+        if (r.gate) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(r.gate + row * r.ldg + ch0));
+          if (!(g.x > 0.f)) va[0] = 0.f; if (!(g.y > 0.f)) va[1] = 0.f; if (!(g.z > 0.f)) va[2] = 0.f; if (!(g.w > 0.f)) va[3] = 0.f;
+        }
+        if (r.drop) {
+          const float4 d = __ldg(reinterpret_cast<const float4*>(r.drop + row * r.lda + ch0));
+          va[0] *= d.x * r.drop_scale; va[1] *= d.y * r.drop_scale; va[2] *= d.z * r.drop_scale; va[3] *= d.w * r.drop_scale;
+        }
+        if (MODE == 3 && r.sub) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(r.sub + row * r.lds + ch0));
+          vb[0] -= q.x; vb[1] -= q.y; vb[2] -= q.z; vb[3] -= q.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float o = MODE == 2 ? (vb[e] - mean[e]) * rstd[e] : vb[e];
+          s0[e] += va[e]; s1[e] += (double)va[e] * (double)o;
+        }
+      }
+    }
+  } else {
+    for (int64_t row = r0 + rl; row < r1; row += 32) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ch = ch0 + e;
+        if (ch >= r.c) continue;
+        float v = __ldg(r.a + row * r.lda + ch);
+        if (MODE == 0) { s0[e] += v; }
+        else if (MODE == 1) { s0[e] += v; s1[e] += (double)v * (double)v; }
+        else {
+          if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
+          if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
+          float bv = __ldg(r.b + row * r.ldb + ch);
+          if (MODE == 3 && r.sub) bv -= __ldg(r.sub + row * r.lds + ch);
+          const float o = MODE == 2 ? (bv - mean[e]) * rstd[e] : bv;
+          s0[e] += v; s1[e] += (double)v * (double)o;
+        }
       }
     }
   }
-  sm[ry][cx][0] = s0; sm[ry][cx][1] = s1;
-  __syncthreads();
-  if (ry == 0 && ch < r.c) {
-    double t0 = 0, t1 = 0;
+  // lanes l, l^8, l^16, l^24 hold the same channels (different rows): fixed-order shuffle tree, then 8 warps via smem
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { t0 += sm[k][cx][0]; t1 += sm[k][cx][1]; }
-    partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 0] = t0;
-    partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 1] = t1;
+  for (int e = 0; e < 4; ++e) {
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8);  s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16); s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { sm[warp][lane * 4 + e][0] = s0[e]; sm[warp][lane * 4 + e][1] = s1[e]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int ch = blockIdx.y * 32 + threadIdx.x;
+    if (ch < r.c) {
+      double t0 = 0, t1 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { t0 += sm[k][threadIdx.x][0]; t1 += sm[k][threadIdx.x][1]; }
+      partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 0] = t0;
+      partial[((int64_t)blockIdx.x * r.c + ch) * 2 + 1] = t1;
+    }
   }
 }
 static inline int64_t red_chunks(int64_t rows) { return ceil_div64(rows, RED_ROWS_PER_CHUNK); }
 extern "C" int64_t b2_bn_workspace_doubles(int64_t rows, int c) { return red_chunks(rows) * c * 2 + 2 * (int64_t)c; }
 
 template <int MODE>
-static int launch_col_reduce(const RedArgs& r, double* ws, cudaStream_t s) {
+static int launch_col_reduce(const RedArgs& r0, double* ws, cudaStream_t s) {
+  RedArgs r = r0;
+  auto ok = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0); };
+  r.vec = (r.c % 4 == 0) && ok(r.a, r.lda) && ok(r.b, r.ldb) && ok(r.gate, r.ldg) && ok(r.sub, r.lds) && ok(r.drop, r.lda);
   dim3 grid((unsigned)red_chunks(r.rows), (r.c + 31) / 32);
   col_reduce_kernel<MODE><<<grid, 256, 0, s>>>(r, ws);
   cudaError_t e = cudaGetLastError();
