@@ -55,6 +55,7 @@ struct ConvKArgs {
   int ld_add, ld_gate;
   int relu, accumulate;
   int vec_ok;
+  int dbg;
 };
 
 struct TileInfo {
@@ -198,7 +199,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     epi::Params ep;
     ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
     ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
-    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb;
+    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb; ep.dbg = a.dbg;
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -288,6 +289,7 @@ void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, 
 
 int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream);   // conv_gemm2.cu
 int g_conv_force_1cta = 0;
+int g_conv_epi_debug = 0;
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   B2_REQUIRE(p && p->a && p->b && p->d, "b2_conv_gemm: null tensor");
@@ -330,6 +332,7 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
   a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  a.dbg = g_conv_epi_debug;
   a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
              (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
 

@@ -51,6 +51,7 @@ struct Conv2KArgs {
   int ld_add, ld_gate;
   int relu, accumulate;
   int vec_ok;
+  int dbg;
 };
 
 struct TileInfo {
@@ -259,7 +260,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     epi::Params ep;
     ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
     ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
-    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb;
+    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb; ep.dbg = a.dbg;
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
     for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
@@ -296,6 +297,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }  // namespace
 
 // choose_box is defined in conv_gemm.cu
+extern int g_conv_epi_debug;
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
 
 int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
@@ -320,6 +322,7 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
   a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  a.dbg = g_conv_epi_debug;
   a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
              (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
   CUtensorMap tmA, tmAlo, tmB, tmBlo;

@@ -349,9 +349,11 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
 }  // namespace
 
 extern int g_conv_force_1cta;
+extern int g_conv_epi_debug;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 1) g_wgrad_desc_variant = value;
   if (key == 2) g_conv_force_1cta = value;
+  if (key == 3) g_conv_epi_debug = value;
 }
 
 extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {

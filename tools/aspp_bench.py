@@ -57,3 +57,21 @@ if __name__ == '__main__':
         conv_case(16, 128, 128, 304, 256, 3, 1, 'decoder 3x3 304->256 @128x128 N16')
         conv_case(16, 128, 128, 64, 64, 3, 1, 'layer1 3x3 64->64 @128x128 N16')
         conv_case(16, 128, 128, 64, 256, 1, 1, 'layer1 1x1 64->256 @128x128 N16')
+    if which == 'epi':
+        # timing experiment for the HBM-bound 1x1 layers: where does the per-tile time go?
+        # debug knob 3: 1 = epilogue skips its HBM stores, 2 = also skips the TMEM loads; knob 2: force the 1-CTA kernel
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        for force1 in (0, 1):
+            L.b2_debug_set(2, force1)
+            for dbg in (0, 1, 2):
+                L.b2_debug_set(3, dbg)
+                tag = ' [1cta={} dbg={}]'.format(force1, dbg)
+                n, h, w = 16, 64, 64
+                for cin, cout in ((256, 1024), (1024, 256)):
+                    x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+                    wt = torch.randn(cout, 1, cin, device=dev) * 0.01
+                    y = Act.alloc(n, h, w, cout, dev)
+                    fl = 2.0 * n * h * w * cin * cout
+                    timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y), fl, '1x1 {}->{}'.format(cin, cout) + tag)
+        L.b2_debug_set(3, 0); L.b2_debug_set(2, 0)
