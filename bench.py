@@ -227,7 +227,7 @@ def run_b200(args):
         'last_step': last,
     }
     if prof:
-        dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
+        dom = max(((k, v) for k, v in prof.items() if v['flops'] > 0), key=lambda kv: kv[1]['ms'])
         name, d = dom
         ach = d['flops'] / (d['ms'] / 1e3) / 1e12
         res['roofline'] = {'kernel': name, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peaks['bf16_sustained'],
@@ -236,10 +236,12 @@ def run_b200(args):
                            'frac_of_tf32_rate': round(ach / (peaks['bf16_sustained'] / 2), 4),
                            'launches': d['n'], 'kernel_ms_per_step': round(d['ms'], 3),
                            'share_of_step': round(d['ms'] / ms_step, 4),
+                           'profiled_step_kernel_ms_total': round(sum(v['ms'] for v in prof.values()), 3),
                            'per_kernel': {k: {'ms': round(v['ms'], 3), 'n': v['n'],
-                                              'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)} for k, v in prof.items()}}
+                                              'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)}
+                                          for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:24]}}
     if prof and os.environ.get('B200SEG_SHAPE_PROFILE'):
-        top = sorted(be.last_shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:40]
+        top = sorted(be.last_shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:70]
         with open(os.environ['B200SEG_SHAPE_PROFILE'], 'w') as f:
             for k, v in top:
                 f.write('{:<70s} {:8.3f} ms  n={:4d}  {:7.1f} TFLOP/s\n'.format(k, v['ms'], v['n'], v['flops'] / max(v['ms'], 1e-9) / 1e9))

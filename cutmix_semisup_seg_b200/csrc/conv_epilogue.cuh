@@ -1,13 +1,16 @@
 // Shared epilogue of the convolution GEMM kernels: TMEM accumulator (128 rows x block_n columns per CTA) -> HBM.
 //
-// Design notes (from the ncu captures under profiles/): the first version ran ~2200 SASS instructions per 32-column
-// chunk (run-time feature tests and 64-bit address arithmetic inside fully unrolled loops) and serialised its residual /
-// gate loads, so small-K 1x1 layers were epilogue-issue-bound at ~0.4 TB/s of output.  This version
-//   * hoists every per-row quantity (output / residual / gate element offsets) into registers once per tile,
-//   * folds optional scale / shift / second scale / ReLU into unconditional FMA / FMUL / FMAX with neutral constants,
-//   * issues the residual and gate loads of all 8 row groups of a chunk before touching them (8-16 independent 16 B
+// Design notes (from the ncu captures and the clock64 pipeline traces under profiles/): with two TMEM accumulators the
+// MMA of tile i+2 waits for the epilogue of tile i, so for the small-K 1x1 layers (4k MMA cycles per tile) the
+// epilogue IS the kernel.  v1 ran ~2200 SASS instructions per 32-column chunk, v2 ~590 (64-bit pixel offsets, a
+// stack copy of the parameter block read back with LDL, every optional term executed) and measured 14k cycles per tile
+// even with loads and stores disabled, i.e. issue/latency-bound.  This version
+//   * reads its parameters straight from the kernel's __grid_constant__ block (uniform loads, no stack frame),
+//   * keeps one 32-bit pixel index per row; an address is one IMAD.WIDE,
+//   * is specialised on <residual addend, gate> so that absent terms cost no instructions,
+//   * issues the residual and gate loads of all 8 row groups of a chunk before touching them (16 independent 16 B
 //     loads in flight per lane),
-//   * keeps the rare ragged path (channel count not a multiple of 4, unaligned pointers) out of line.
+//   * keeps the rare paths (channel count not a multiple of 4, unaligned pointers, accumulate) out of line.
 // Rows are staged through a padded smem tile so that 8 consecutive lanes own 32 consecutive channels of one pixel:
 // loads and stores are full 128 B segments.
 #pragma once
@@ -15,10 +18,20 @@
 
 namespace epi {
 
+// explicit shared-space 128-bit accesses (a generic float* compiles to ST.E / LD.E with 64-bit addressing)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 constexpr int ROW_FLOATS = 36;                      // 32 columns + 4 pad: conflict-free 128-bit smem access
 constexpr int WARP_BYTES = 32 * ROW_FLOATS * 4;
 constexpr int NUM_WARPS = 8;                        // two warps per TMEM lane quarter (even / odd 32-column chunks)
-constexpr int BYTES = NUM_WARPS * WARP_BYTES + NUM_WARPS * 32 * 8;  // staging tiles + per-row pixel offsets
+constexpr int BYTES = NUM_WARPS * WARP_BYTES + NUM_WARPS * 32 * 4;  // staging tiles + per-row pixel indices
 
 struct Params {
   float* d; int ldd;
@@ -29,40 +42,46 @@ struct Params {
   int dbg;          // debug knob 3: 1 = skip HBM stores, 2 = also skip the TMEM loads (timing experiments only)
 };
 
-static __device__ __noinline__ void ragged_store(const Params& p, float4 v, long long pix, int c) {
+// Out-of-line general path for one lane's 4 columns of one row: any channel count / alignment, accumulate.
+static __device__ __noinline__ void slow_store(const Params& p, float4 v, int pix, int c) {
   const float vv[4] = {v.x, v.y, v.z, v.w};
-  float* drow = p.d + pix * p.ldd;
+  float* drow = p.d + (long long)pix * p.ldd;
+#pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int cc = c + e;
-    if (cc >= p.nb) break;
-    float o = vv[e];
-    if (p.scale) o *= __ldg(p.scale + cc);
-    if (p.shift) o += __ldg(p.shift + cc);
-    if (p.addend) o += __ldg(p.addend + pix * p.ld_add + cc);
-    if (p.relu) o = fmaxf(o, 0.f);
-    if (p.gate) o = __ldg(p.gate + pix * p.ld_gate + cc) > 0.f ? o : 0.f;
-    if (p.scale2) o *= __ldg(p.scale2 + cc);
-    if (p.accumulate) o += drow[cc];
-    drow[cc] = o;
+    if (cc < p.nb) {
+      float o = vv[e];
+      if (p.scale) o *= __ldg(p.scale + cc);
+      if (p.shift) o += __ldg(p.shift + cc);
+      if (p.addend) o += __ldg(p.addend + (long long)pix * p.ld_add + cc);
+      if (p.relu) o = fmaxf(o, 0.f);
+      if (p.gate) o = __ldg(p.gate + (long long)pix * p.ld_gate + cc) > 0.f ? o : 0.f;
+      if (p.scale2) o *= __ldg(p.scale2 + cc);
+      if (p.accumulate) o += drow[cc];
+      drow[cc] = o;
+    }
   }
 }
 
-// One epilogue warp (ew = 0..3) drains lanes [32*ew, 32*ew+32) of the accumulator at TMEM column `tmem_col0`.
-// rowpix[32]: output pixel offset of each of the warp's rows (-1 = row not stored).  `release()` is called once the
-// accumulator has been completely read (so the MMA warp may overwrite it).
-// `half` (0/1) selects the even or odd chunks: two warps share a lane quarter so that twice as many loads/stores are in
-// flight per SM (the epilogue of the HBM-bound 1x1 layers is latency-bound, not issue-bound).
-template <class Release>
-__device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                           const long long* rowpix, int lane, int half, Release release) {
+// One epilogue warp drains lanes [32*ew, 32*ew+32) of the accumulator at TMEM address `taddr` (lane quarter already
+// applied).  rowpix[32]: output pixel index of each of the warp's rows (-1 = row not stored).  `release()` is called
+// once the accumulator has been completely read (so the MMA warp may overwrite it).
+// `half` (0/1) selects the even or odd chunks: two warps share a lane quarter.
+template <bool ADD, bool GATE, class Release>
+__device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
+                                             const int* rowpix, int lane, int half, Release release) {
   const int sub_r = lane >> 3;          // row within a group of 4
   const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
-  long long od[8];
+  int od[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
   const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
+  const bool fast = p.vec_ok && !p.accumulate;
   const int nchunks = block_n / 32;
+  const uint32_t st_w = tc::smem_u32(stg + lane * ROW_FLOATS);
+  const uint32_t st_r = tc::smem_u32(stg + sub_r * ROW_FLOATS + sub_c);
   if (half >= nchunks) release();       // nothing to read for this warp: still owes its arrival
+#pragma unroll 1                        // keep the body resident in the instruction cache (4 specialisations x 2 kernels)
   for (int ch = half; ch < nchunks; ch += 2) {
     uint32_t r[32];
     if (p.dbg < 2) {
@@ -75,72 +94,72 @@ __device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int 
     if (ch + 2 >= nchunks) release();
     const int col0 = n0 + ch * 32;
     if (col0 >= p.nb) continue;
+    const int c = col0 + sub_c;
+    const bool lane_fast = fast && c + 3 < p.nb;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(stg + lane * ROW_FLOATS + q * 4) =
-          make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+      sts128(st_w + q * 16, r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
     __syncwarp();
-    const int c = col0 + sub_c;
-    if (c < p.nb) {
-      if (p.vec_ok && c + 3 < p.nb) {
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), s2 = sc;
-        if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-        if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-        if (p.scale2) s2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
-        float4 ad[8], gt[8];
-        if (p.addend) {
+    if (lane_fast) {
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), s2 = sc;
+      if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+      if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+      if (p.scale2) s2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
+      // two batches of 4 row groups: up to 8 independent 16 B residual / gate loads in flight per lane without
+      // spilling (all 16 at once needs > 168 registers)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            ad[i] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + od[i] * p.ld_add + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (p.gate) {
+      for (int b = 0; b < 2; ++b) {
+        float4 ad[4], gt[4];
+        if (ADD) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            gt[i] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.gate + od[i] * p.ld_gate + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-        if (p.accumulate) {
-          // rare (dgrad accumulation into an owned partial): reuse the addend slots
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (od[i] < 0) continue;
-            const float4 old = *reinterpret_cast<const float4*>(p.d + od[i] * p.ldd + c);
-            const float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c);
-            float4 o;
-            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
-            if (p.addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-            o.x = fmaxf(o.x, relu_floor); o.y = fmaxf(o.y, relu_floor); o.z = fmaxf(o.z, relu_floor); o.w = fmaxf(o.w, relu_floor);
-            if (p.gate) {
-              o.x = gt[i].x > 0.f ? o.x : 0.f; o.y = gt[i].y > 0.f ? o.y : 0.f; o.z = gt[i].z > 0.f ? o.z : 0.f; o.w = gt[i].w > 0.f ? o.w : 0.f;
-            }
-            o.x = o.x * s2.x + old.x; o.y = o.y * s2.y + old.y; o.z = o.z * s2.z + old.z; o.w = o.w * s2.w + old.w;
-            *reinterpret_cast<float4*>(p.d + od[i] * p.ldd + c) = o;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (od[i] < 0) continue;
-            const float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c);
-            float4 o;
-            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
-            if (p.addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-            o.x = fmaxf(o.x, relu_floor); o.y = fmaxf(o.y, relu_floor); o.z = fmaxf(o.z, relu_floor); o.w = fmaxf(o.w, relu_floor);
-            if (p.gate) {
-              o.x = gt[i].x > 0.f ? o.x : 0.f; o.y = gt[i].y > 0.f ? o.y : 0.f; o.z = gt[i].z > 0.f ? o.z : 0.f; o.w = gt[i].w > 0.f ? o.w : 0.f;
-            }
-            o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
-            if (!p.dbg) *reinterpret_cast<float4*>(p.d + od[i] * p.ldd + c) = o;
-            else if (o.x == 123.456f) p.d[0] = o.y;
+          for (int j = 0; j < 4; ++j) {
+            const int i = b * 4 + j;
+            ad[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + (long long)od[i] * p.ld_add + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-      } else {
+        if (GATE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = b * 4 + j;
+            gt[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.gate + (long long)od[i] * p.ld_gate + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = b * 4 + j;
+          const float4 v = lds128(st_r + i * 4 * ROW_FLOATS * 4);
+          float4 o;
+          o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+          if (ADD) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
+          o.x = fmaxf(o.x, relu_floor); o.y = fmaxf(o.y, relu_floor); o.z = fmaxf(o.z, relu_floor); o.w = fmaxf(o.w, relu_floor);
+          if (GATE) {
+            o.x = gt[j].x > 0.f ? o.x : 0.f; o.y = gt[j].y > 0.f ? o.y : 0.f; o.z = gt[j].z > 0.f ? o.z : 0.f; o.w = gt[j].w > 0.f ? o.w : 0.f;
+          }
+          o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
+          if (od[i] >= 0 && !p.dbg) *reinterpret_cast<float4*>(p.d + (long long)od[i] * p.ldd + c) = o;
+        }
+      }
+    } else if (c < p.nb) {
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-          if (od[i] < 0) continue;
-          ragged_store(p, *reinterpret_cast<const float4*>(stg + (i * 4 + sub_r) * ROW_FLOATS + sub_c), od[i], c);
-        }
+      for (int i = 0; i < 8; ++i) {
+        if (od[i] < 0) continue;
+        slow_store(p, lds128(st_r + i * 4 * ROW_FLOATS * 4), od[i], c);
       }
     }
     __syncwarp();
+  }
+}
+
+template <class Release>
+__device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
+                                           const int* rowpix, int lane, int half, Release release) {
+  // the four specialisations are selected once per tile (uniform branch)
+  if (p.addend) {
+    if (p.gate) drain_tile_t<true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
+    else drain_tile_t<true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
+  } else {
+    if (p.gate) drain_tile_t<false, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
+    else drain_tile_t<false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
   }
 }
 

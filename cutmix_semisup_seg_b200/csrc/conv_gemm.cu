@@ -49,13 +49,7 @@ struct ConvKArgs {
   short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
   int kblocks;
   int n_pass;
-  float* d;
-  const float* scale; const float* shift;
-  const float* addend; const float* gate; const float* scale2;
-  int ld_add, ld_gate;
-  int relu, accumulate;
-  int vec_ok;
-  int dbg;
+  epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
 };
 
 struct TileInfo {
@@ -80,17 +74,6 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvKArgs& a, int tile) {
   if (mask == 0) mask = 1;  // accumulator must still be written (all-zero contribution)
   t.tap_mask = mask;
   return t;
-}
-
-__device__ __forceinline__ float epi1(const ConvKArgs& a, float v, int c, float add, float gate, float old) {
-  if (a.scale) v *= __ldg(a.scale + c);
-  if (a.shift) v += __ldg(a.shift + c);
-  if (a.addend) v += add;
-  if (a.relu) v = fmaxf(v, 0.0f);
-  if (a.gate) v = gate > 0.0f ? v : 0.0f;
-  if (a.scale2) v *= __ldg(a.scale2 + c);
-  if (a.accumulate) v += old;
-  return v;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -195,11 +178,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ewi = warp - 4;
     const int row = ew * 32 + lane;
     float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ewi * (32 * epi::ROW_FLOATS);
-    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
-    epi::Params ep;
-    ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
-    ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
-    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb; ep.dbg = a.dbg;
+    int* rowpix = reinterpret_cast<int*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
+    const epi::Params& ep = a.ep;     // stays in the kernel's constant parameter space
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -213,7 +193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
         const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
         __syncwarp();
-        rowpix[lane] = valid ? pix : -1;
+        rowpix[lane] = valid ? (int)pix : -1;
         __syncwarp();
       }
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -329,11 +309,12 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
-  a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
-  a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
+  a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
+  a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
+  a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  a.dbg = g_conv_epi_debug;
-  a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
+  a.ep.dbg = g_conv_epi_debug;
+  a.ep.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
              (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
 
   // A: (K, IW, IH, N) fp32, box (32, BW*s, BH*s, BN) with element strides (1, s, s, 1)

@@ -45,13 +45,8 @@ struct Conv2KArgs {
   short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
   int kblocks;
   int n_pass;
-  float* d;
-  const float* scale; const float* shift;
-  const float* addend; const float* gate; const float* scale2;
-  int ld_add, ld_gate;
-  int relu, accumulate;
-  int vec_ok;
-  int dbg;
+  epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
+  long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
 };
 
 struct TileInfo {
@@ -87,17 +82,6 @@ __device__ __forceinline__ TileInfo decode_tile(const Conv2KArgs& a, int pair, i
   t.w0 = wt * a.bw; t.h0 = ht * a.bh; t.n0 = nt * a.bn;
   t.tap_mask = both ? both : 1u;
   return t;
-}
-
-__device__ __forceinline__ float epi1(const Conv2KArgs& a, float v, int c, float add, float gate, float old) {
-  if (a.scale) v *= __ldg(a.scale + c);
-  if (a.shift) v += __ldg(a.shift + c);
-  if (a.addend) v += add;
-  if (a.relu) v = fmaxf(v, 0.0f);
-  if (a.gate) v = gate > 0.0f ? v : 0.0f;
-  if (a.scale2) v *= __ldg(a.scale2 + c);
-  if (a.accumulate) v += old;
-  return v;
 }
 
 // ---- cta_group::2 / cluster PTX ---------------------------------------------------------------------
@@ -144,11 +128,14 @@ __device__ __forceinline__ void mma2_commit_mcast(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
 }
-// arrive on the leader CTA's copy of `bar` (local when this CTA is the leader)
+// arrive on the leader CTA's copy of `bar` (local when this CTA is the leader).  Default (.release.cta) semantics, as
+// CUTLASS' ClusterBarrier::arrive(cta_id): the TMEM reads it orders are fenced by tcgen05.fence::before_thread_sync.
+// (A `.release.cluster` arrive compiles to MEMBAR.ALL.GPU, which stalls the warp until every earlier output store has
+// been acknowledged by L2 -- ~8k cycles per tile in the pipeline trace of the 1x1 layers.)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(tc::smem_u32(bar)));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -196,6 +183,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int tr_n = 0;
       for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
         const TileInfo t = decode_tile(a, pair, (int)rank);
         for (int tap = 0; tap < a.n_taps; ++tap) {
@@ -206,6 +194,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kb = 0; kb < a.kblocks; ++kb) {
             for (int p = 0; p < a.n_pass; ++p) {
               tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[tr_n++] = clock64();
               if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
               tma2_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
                            kb * BLOCK_K, cw, ch, t.n0);
@@ -223,16 +212,20 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t idesc = tc::make_idesc_tf32(2 * BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      int tr_n = 0, tr_t = 0;
       for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
         const TileInfo t = decode_tile(a, pair, 0);
+        if (a.trace && blockIdx.x == 0 && tr_t < 510) a.trace[1024 + tr_t++] = clock64();
         tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
+        if (a.trace && blockIdx.x == 0 && tr_t < 510) a.trace[1024 + tr_t++] = clock64();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         uint32_t first = 1;
         const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
         for (int it = 0; it < iters; ++it) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
+          if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[512 + tr_n++] = clock64();
           const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
@@ -256,13 +249,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ewi = warp - 4;
     const int row = ew * 32 + lane;
     float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ewi * (32 * epi::ROW_FLOATS);
-    long long* rowpix = reinterpret_cast<long long*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
-    epi::Params ep;
-    ep.d = a.d; ep.ldd = a.ldd; ep.scale = a.scale; ep.shift = a.shift; ep.scale2 = a.scale2;
-    ep.addend = a.addend; ep.ld_add = a.ld_add; ep.gate = a.gate; ep.ld_gate = a.ld_gate;
-    ep.relu = a.relu; ep.accumulate = a.accumulate; ep.vec_ok = a.vec_ok; ep.nb = a.nb; ep.dbg = a.dbg;
+    int* rowpix = reinterpret_cast<int*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
+    const epi::Params& ep = a.ep;     // stays in the kernel's constant parameter space
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
+    int tr_e = 0;
+    const bool tracer = a.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
     for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
       const TileInfo t = decode_tile(a, pair, (int)rank);
       {
@@ -274,11 +266,13 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
         const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
         __syncwarp();
-        rowpix[lane] = valid ? pix : -1;
+        rowpix[lane] = valid ? (int)pix : -1;
         __syncwarp();
       }
+      if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
+      if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
       epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -298,6 +292,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // choose_box is defined in conv_gemm.cu
 extern int g_conv_epi_debug;
+static long long* g_conv_trace = nullptr;
+extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
 
 int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
@@ -319,11 +315,12 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
-  a.d = p->d; a.scale = p->scale; a.shift = p->shift; a.addend = p->addend; a.gate = p->gate; a.scale2 = p->scale2;
-  a.ld_add = p->ld_add; a.ld_gate = p->ld_gate; a.relu = p->relu; a.accumulate = p->accumulate;
+  a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
+  a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
+  a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  a.dbg = g_conv_epi_debug;
-  a.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
+  a.ep.dbg = g_conv_epi_debug; a.trace = g_conv_trace;
+  a.ep.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&
              (!p->gate || (p->ld_gate % 4 == 0 && al16(p->gate)));
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   {

@@ -138,6 +138,8 @@ def load():
         fn.argtypes = args
     lib.b2_debug_set.restype = None
     lib.b2_debug_set.argtypes = [c_int, c_int]
+    lib.b2_debug_trace.restype = None
+    lib.b2_debug_trace.argtypes = [c_vp]
     _lib = lib
     return lib
 

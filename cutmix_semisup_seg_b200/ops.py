@@ -32,18 +32,27 @@ class CudaBackend(object):
         return L.stream_ptr()
 
     def _call(self, name, *args):
+        if self._prof is not None:
+            return self._timed_call(name, 0.0, name, *args, _tag='')
         self.launches += 1
         return L.call(name, *args)
 
-    def _timed_call(self, kernel, flops, name, *args):
+    # Profiling: CUDA events on the launching stream around every launch.  A device-side spin (~0.2 ms) is queued
+    # ahead of the start event so that the host's enqueue latency (ctypes + tensor-map encode, ~50-100 us) is hidden
+    # behind it: without the spin the GPU idles between `e0` and the launch and every short kernel reads ~0.1 ms.
+    PROFILE_SPIN_CYCLES = 400000
+
+    def _timed_call(self, kernel, flops, name, *args, _tag=None):
         """Launch with CUDA events recorded on the launching stream when profiling is on."""
         if self._prof is None:
             return self._call(name, *args)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(self.PROFILE_SPIN_CYCLES)
         e0.record()
-        rc = self._call(name, *args)
+        self.launches += 1
+        rc = L.call(name, *args)
         e1.record()
-        self._prof.append((kernel, flops, e0, e1, getattr(self, '_prof_tag', '')))
+        self._prof.append((kernel, flops, e0, e1, getattr(self, '_prof_tag', '') if _tag is None else _tag))
         return rc
 
     def start_profile(self):
@@ -179,7 +188,7 @@ class CudaBackend(object):
         p.max_ctas = max_ctas
         flops = 2.0 * n * oh * ow * nb * k * taps_arr.shape[0] * n_split
         self._prof_tag = 'pix{} k{} n{} taps{} s{}'.format(n * oh * ow, k, nb, taps_arr.shape[0], istride)
-        self._timed_call('conv_gemm_kernel', flops / n_split, 'b2_conv_gemm', ctypes.byref(p), self._s())
+        self._timed_call('conv_gemm2_kernel' if (nb > 224 and max_ctas != 1) else 'conv_gemm_kernel', flops / n_split, 'b2_conv_gemm', ctypes.byref(p), self._s())
 
     def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
                    accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None,

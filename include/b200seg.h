@@ -169,6 +169,10 @@ int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
 
 /* Debug knobs (tests only): key 1 = wgrad smem-descriptor variant; key 2 = 1 forces the single-CTA conv kernel. */
 void b2_debug_set(int key, int value);
+/* Diagnostics: device buffer of 2048 int64 receiving clock64 stamps of CTA 0's pipeline roles in the 2-CTA conv
+ * kernel ([0,512) producer stage issue, [512,1024) MMA stage acquired, [1024,1536) MMA tile begin/accumulator
+ * acquired, [1536,2048) epilogue warp tile wait begin/end); NULL disables.  Not part of the product path. */
+void b2_debug_trace(void* buf);
 
 /* hi = x with the 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact). */
 int b2_split_tf32(const float* x, float* hi, float* lo, int64_t count, void* stream);

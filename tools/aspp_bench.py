@@ -17,6 +17,7 @@ def timeit(fn, flops, name):
     ts = []
     for i in range(reps + 1):
         flush.fill_(float(i))                      # evict L2 (256 MB write)
+        torch.cuda._sleep(600000)                  # let the host run ahead: keeps enqueue latency out of e0..e1
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         if i > 0:
@@ -75,3 +76,32 @@ if __name__ == '__main__':
                     fl = 2.0 * n * h * w * cin * cout
                     timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y), fl, '1x1 {}->{}'.format(cin, cout) + tag)
         L.b2_debug_set(3, 0); L.b2_debug_set(2, 0)
+    if which == 'trace':
+        # pipeline timeline of CTA 0 of the 2-CTA kernel (clock64 stamps, see b2_debug_trace in include/b200seg.h)
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        n, h, w = 16, 64, 64
+        for cin, cout, dbg in ((256, 1024, 0), (256, 1024, 2), (1024, 256, 0), (1024, 256, 2)):
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            wt = torch.randn(cout, 1, cin, device=dev) * 0.01
+            y = Act.alloc(n, h, w, cout, dev)
+            buf = torch.zeros(2048, dtype=torch.int64, device=dev)
+            K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y)
+            flush.fill_(1.0); torch.cuda._sleep(600000)
+            L.b2_debug_set(3, dbg); L.b2_debug_trace(buf.data_ptr())
+            K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y)
+            torch.cuda.synchronize()
+            L.b2_debug_trace(None); L.b2_debug_set(3, 0)
+            b = buf.cpu().numpy()
+            t0 = min(v for v in b if v > 0)
+            kb = cin // 32
+            prod = [v - t0 for v in b[0:512] if v > 0]
+            mma = [v - t0 for v in b[512:1024] if v > 0]
+            tile = [v - t0 for v in b[1024:1536] if v > 0]
+            epi = [v - t0 for v in b[1536:2048] if v > 0]
+            print('--- 1x1 {}->{} dbg={} kblocks/tile={}'.format(cin, cout, dbg, kb))
+            print('producer stage issue (first 48):', prod[:48])
+            print('mma stage acquired   (first 48):', mma[:48])
+            print('mma tile [begin, acc acquired]*:', tile[:24])
+            print('epi  tile [wait begin, tfull ]*:', epi[:24])
+            print('last stamps: prod {} mma {} tile {} epi {}'.format(prod[-1] if prod else 0, mma[-1] if mma else 0, tile[-1] if tile else 0, epi[-1] if epi else 0))
