@@ -7,7 +7,7 @@ class Act(object):
     channels [off, off + c) of every pixel.  Slices of a wider buffer replace torch.cat."""
 
     __slots__ = ('base', 'n', 'h', 'w', 'c', 'ld', 'off', 'gate_on_grad', 'node', 'parent', 'pending',
-                 'grad', 'grad_owned', 'name', 'needs_grad')
+                 'grad', 'grad_owned', 'name', 'needs_grad', 'fused_stats')
 
     def __init__(self, base, n, h, w, c, ld=None, off=0, name=''):
         self.base = base
@@ -22,6 +22,7 @@ class Act(object):
         self.grad_owned = False
         self.name = name
         self.needs_grad = True      # False for network inputs (no dgrad is computed into them)
+        self.fused_stats = None     # column sums written by the epilogue that finished .grad (engine.Tape)
 
     @staticmethod
     def alloc(n, h, w, c, device, ld=None, name=''):

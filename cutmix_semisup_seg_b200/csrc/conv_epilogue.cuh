@@ -10,7 +10,7 @@
 //   * is specialised on <residual addend, gate> so that absent terms cost no instructions,
 //   * issues the residual and gate loads of all 8 row groups of a chunk before touching them (16 independent 16 B
 //     loads in flight per lane),
-//   * keeps the rare paths (channel count not a multiple of 4, unaligned pointers, accumulate) out of line.
+//   * keeps the rare paths (channel count not a multiple of 4, unaligned pointers) out of line.
 // Rows are staged through a padded smem tile so that 8 consecutive lanes own 32 consecutive channels of one pixel:
 // loads and stores are full 128 B segments.
 #pragma once
@@ -39,6 +39,10 @@ struct Params {
   const float* addend; int ld_add;
   const float* gate; int ld_gate;
   int relu, accumulate, vec_ok, nb;
+  // Optional fused column statistics of the stored gradient (frozen-BN parameter gradients, see b200seg.h):
+  // stats[(row_block*2 + j)*ld_stats + ch], j = 0: sum v, j = 1: sum v*(gate - sub); row_block = m_tile*4 + lane quarter
+  float* stats; int ld_stats;
+  const float* sub; int ld_sub;
   int dbg;          // debug knob 3: 1 = skip HBM stores, 2 = also skip the TMEM loads (timing experiments only)
 };
 
@@ -67,16 +71,17 @@ static __device__ __noinline__ void slow_store(const Params& p, float4 v, int pi
 // applied).  rowpix[32]: output pixel index of each of the warp's rows (-1 = row not stored).  `release()` is called
 // once the accumulator has been completely read (so the MMA warp may overwrite it).
 // `half` (0/1) selects the even or odd chunks: two warps share a lane quarter.
-template <bool ADD, bool GATE, class Release>
+template <bool ADD, bool GATE, bool STATS, class Release>
 __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                             const int* rowpix, int lane, int half, Release release) {
+                                             const int* rowpix, int lane, int half, int stat_row, Release release) {
   const int sub_r = lane >> 3;          // row within a group of 4
   const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
   int od[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
   const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
-  const bool fast = p.vec_ok && !p.accumulate;
+  const bool fast = p.vec_ok;
+  const bool acc = p.accumulate != 0;
   const int nchunks = block_n / 32;
   const uint32_t st_w = tc::smem_u32(stg + lane * ROW_FLOATS);
   const uint32_t st_r = tc::smem_u32(stg + sub_r * ROW_FLOATS + sub_c);
@@ -96,6 +101,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
     if (col0 >= p.nb) continue;
     const int c = col0 + sub_c;
     const bool lane_fast = fast && c + 3 < p.nb;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;     // STATS: this lane's column sums over its 8 rows
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       sts128(st_w + q * 16, r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
@@ -109,7 +115,14 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
       // spilling (all 16 at once needs > 168 registers)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        float4 ad[4], gt[4];
+        float4 ad[4], gt[4], sb[4];
+        if (STATS && p.sub) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = b * 4 + j;
+            sb[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.sub + (long long)od[i] * p.ld_sub + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         if (ADD) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -136,7 +149,20 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
             o.x = gt[j].x > 0.f ? o.x : 0.f; o.y = gt[j].y > 0.f ? o.y : 0.f; o.z = gt[j].z > 0.f ? o.z : 0.f; o.w = gt[j].w > 0.f ? o.w : 0.f;
           }
           o.x *= s2.x; o.y *= s2.y; o.z *= s2.z; o.w *= s2.w;
-          if (od[i] >= 0 && !p.dbg) *reinterpret_cast<float4*>(p.d + (long long)od[i] * p.ldd + c) = o;
+          if (STATS && od[i] >= 0) {
+            float4 yv = gt[j];
+            if (p.sub) { yv.x -= sb[j].x; yv.y -= sb[j].y; yv.z -= sb[j].z; yv.w -= sb[j].w; }
+            a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
+            a1.x = fmaf(o.x, yv.x, a1.x); a1.y = fmaf(o.y, yv.y, a1.y); a1.z = fmaf(o.z, yv.z, a1.z); a1.w = fmaf(o.w, yv.w, a1.w);
+          }
+          if (od[i] >= 0 && !p.dbg) {
+            float4* dst = reinterpret_cast<float4*>(p.d + (long long)od[i] * p.ldd + c);
+            if (acc) {                    // several dgrads summing into one input gradient (ASPP branches, phases)
+              const float4 old = *dst;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *dst = o;
+          }
         }
       }
     } else if (c < p.nb) {
@@ -146,20 +172,37 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
         slow_store(p, lds128(st_r + i * 4 * ROW_FLOATS * 4), od[i], c);
       }
     }
+    if (STATS) {
+      // fixed-order reduction over the 4 row groups (lanes differing in bits 3, 4): deterministic partials
+      float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+      }
+      if (sub_r == 0 && stat_row >= 0 && c < p.nb) {
+        float* srow = p.stats + (long long)stat_row * 2 * p.ld_stats + c;
+        *reinterpret_cast<float4*>(srow) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(srow + p.ld_stats) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
     __syncwarp();
   }
 }
 
 template <class Release>
 __device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                           const int* rowpix, int lane, int half, Release release) {
-  // the four specialisations are selected once per tile (uniform branch)
-  if (p.addend) {
-    if (p.gate) drain_tile_t<true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
-    else drain_tile_t<true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
+                                           const int* rowpix, int lane, int half, int stat_row, Release release) {
+  // the specialisations are selected once per tile (uniform branch); stats imply a gate (host-checked)
+  if (p.stats) {
+    if (p.addend) drain_tile_t<true, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    else drain_tile_t<false, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+  } else if (p.addend) {
+    if (p.gate) drain_tile_t<true, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    else drain_tile_t<true, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
   } else {
-    if (p.gate) drain_tile_t<false, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
-    else drain_tile_t<false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, release);
+    if (p.gate) drain_tile_t<false, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    else drain_tile_t<false, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
   }
 }
 

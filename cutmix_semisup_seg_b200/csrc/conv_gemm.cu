@@ -199,7 +199,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
-      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, [&]() {
+      const int stat_row = (tile / a.n_tiles_n) * 4 + ew;      // fused column statistics: (M tile, lane quarter)
+      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, stat_row, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
@@ -268,6 +269,15 @@ void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, 
 }
 
 int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream);   // conv_gemm2.cu
+
+// Row blocks of the fused-statistics buffer: 4 (TMEM lane quarters) per 128-pixel M tile; same tiling in both kernels.
+extern "C" int64_t b2_conv_stats_rows(const b2_conv_params* p) {
+  if (!p || p->ow < 1 || p->oh < 1 || p->n < 1 || p->istride < 1) return 0;
+  int bw, bh, bn;
+  b2_choose_box(p->ow, p->oh, p->n, 128, p->istride, &bw, &bh, &bn);
+  const int64_t m_tiles = (int64_t)((p->ow + bw - 1) / bw) * ((p->oh + bh - 1) / bh) * ((p->n + bn - 1) / bn);
+  return m_tiles * 4;
+}
 int g_conv_force_1cta = 0;
 int g_conv_epi_debug = 0;
 
@@ -284,6 +294,13 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
 
   for (int i = 0; i < p->n_taps; ++i)
     B2_REQUIRE(p->taps[i * 3 + 2] >= 0 && p->taps[i * 3 + 2] < p->tb, "b2_conv_gemm: tap %d references weight tap %d >= %d", i, p->taps[i * 3 + 2], p->tb);
+  if (p->stats) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    B2_REQUIRE(p->gate && !p->accumulate && p->nb % 4 == 0 && p->ldd % 4 == 0 && p->ld_gate % 4 == 0 && al16(p->d) && al16(p->gate) &&
+               (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) && p->ld_stats % 4 == 0 && p->ld_stats >= p->nb && al16(p->stats) &&
+               (!p->stats_sub || (p->ld_stats_sub % 4 == 0 && al16(p->stats_sub))),
+               "b2_conv_gemm: fused statistics need a gate, no accumulate, and 16 B aligned / 4-float-padded operands");
+  }
   // N tiles of 256 output channels run on CTA pairs (tcgen05 cta_group::2): see conv_gemm2.cu
   if (p->nb > 224 && !g_conv_force_1cta && b2_sm_count_cached() >= 2 && (p->max_ctas == 0 || p->max_ctas >= 2))
     return b2_conv_gemm_2cta(p, stream);
@@ -312,6 +329,7 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;
+  a.ep.stats = p->stats; a.ep.ld_stats = p->ld_stats; a.ep.sub = p->stats_sub; a.ep.ld_sub = p->ld_stats_sub;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   a.ep.dbg = g_conv_epi_debug;
   a.ep.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&

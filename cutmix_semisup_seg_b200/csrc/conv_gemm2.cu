@@ -274,7 +274,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc::tc_fence_after();
       if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, [&]() {
+      const int m_idx = (pair / a.n_tiles_n) * 2 + (int)rank;
+      const int stat_row = m_idx < a.tiles_w * a.tiles_h * a.tiles_n ? m_idx * 4 + ew : -1;   // phantom tile: none
+      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, stat_row, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -318,6 +320,7 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;
+  a.ep.stats = p->stats; a.ep.ld_stats = p->ld_stats; a.ep.sub = p->stats_sub; a.ep.ld_sub = p->ld_stats_sub;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   a.ep.dbg = g_conv_epi_debug; a.trace = g_conv_trace;
   a.ep.vec_ok = (p->ldd % 4 == 0) && al16(p->d) && (!p->addend || (p->ld_add % 4 == 0 && al16(p->addend))) &&

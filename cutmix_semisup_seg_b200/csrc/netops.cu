@@ -568,6 +568,62 @@ extern "C" int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn
   return B2_OK;
 }
 
+// Reduction of the partial sums written by the conv epilogue (b2_conv_params.stats), two fixed-order stages:
+// stage 1: grid (c/32, STAT_SPLITS); block = 32 channels x 8 row lanes over one contiguous slice of the row blocks
+//          -> workspace[split][c][2] (double);  stage 2: thread per channel sums the splits and writes the gradients.
+constexpr int STAT_SPLITS = 16;
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float* __restrict__ stats, int64_t rows, int ld, int c,
+                                                              double* __restrict__ ws) {
+  __shared__ double sm[8][32][2];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  const int64_t per = (rows + STAT_SPLITS - 1) / STAT_SPLITS;
+  const int64_t k0 = blockIdx.y * per;
+  int64_t k1 = k0 + per; if (k1 > rows) k1 = rows;
+  double s0 = 0, s1 = 0;
+  if (ch < c) {
+#pragma unroll 4
+    for (int64_t k = k0 + ry; k < k1; k += 8) {
+      s0 += (double)__ldg(stats + (k * 2) * ld + ch);
+      s1 += (double)__ldg(stats + (k * 2 + 1) * ld + ch);
+    }
+  }
+  sm[ry][cx][0] = s0; sm[ry][cx][1] = s1;
+  __syncthreads();
+  if (ry == 0 && ch < c) {
+    double t0 = 0, t1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t0 += sm[k][cx][0]; t1 += sm[k][cx][1]; }
+    ws[((int64_t)blockIdx.y * c + ch) * 2] = t0;
+    ws[((int64_t)blockIdx.y * c + ch) * 2 + 1] = t1;
+  }
+}
+__global__ void bn_eval_param_from_stats_out_kernel(const double* __restrict__ ws, int c, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ dgamma,
+                                                    float* __restrict__ dbeta, int accumulate) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double sg = 0, sgy = 0;
+#pragma unroll
+  for (int k = 0; k < STAT_SPLITS; ++k) { sg += ws[((int64_t)k * c + ch) * 2]; sgy += ws[((int64_t)k * c + ch) * 2 + 1]; }
+  const double ga = gamma[ch], be = beta[ch];
+  const double dg = ga != 0.0 ? (sgy - be * sg) / ga : 0.0;
+  dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + (float)sg;
+  dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)dg;
+}
+extern "C" int64_t b2_bn_stats_workspace_doubles(int c) { return (int64_t)STAT_SPLITS * 2 * c; }
+extern "C" int b2_bn_eval_param_grad_from_stats(const float* stats, int64_t stat_rows, int ld_stats, int c, const float* gamma,
+                                                const float* beta, float* dgamma, float* dbeta, int accumulate,
+                                                double* workspace, void* stream) {
+  B2_REQUIRE(stats && gamma && beta && dgamma && dbeta && workspace && stat_rows > 0 && c > 0 && ld_stats >= c,
+             "b2_bn_eval_param_grad_from_stats: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_stats_partial_kernel<<<dim3((c + 31) / 32, STAT_SPLITS), 256, 0, s>>>(stats, stat_rows, ld_stats, c, workspace);
+  bn_eval_param_from_stats_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, c, gamma, beta, dgamma, dbeta, accumulate);
+  B2_LAUNCH_CHECK("bn_eval_param_grad_from_stats");
+  return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ GAP / broadcast
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c, int ldx, float mul) {
   __shared__ float sm[8][32];

@@ -12,6 +12,8 @@ Gradient bookkeeping
   * A convolution input-gradient that is the LAST contribution to an activation adds the partial
     sum (`addend`) and applies the producer's ReLU gate in its epilogue (g-form gradient).
   * Residual branches contribute by aliasing (no copy, no add kernel).
+  * The same epilogue that finishes the gradient of a frozen-BN layer's output also writes the column sums the
+    BN affine parameters need (sum g, sum g*(y - residual)); the separate reduction pass over g and y is skipped.
 """
 import torch
 
@@ -48,8 +50,19 @@ class Tape(object):
                 t.grad, t.grad_owned = owned, True
             self.K.relu_gate(t.grad, t)
 
+    def _stats_request(self, t):
+        """Residual Act to subtract (or False) if the epilogue finishing d/d(t) should also emit the frozen-BN
+        parameter-gradient statistics of the node that produced t; None = no statistics wanted."""
+        node = t.node
+        if not isinstance(node, ConvNode) or node.bn is None or not node.bn.weight.requires_grad:
+            return None
+        if not self.K.stats_ok(t) or (node.residual is not None and not self.K.stats_ok(node.residual)):
+            return None
+        return node.residual if node.residual is not None else False
+
     def contribute_kernel(self, t, launch, fusable):
-        """launch(dst, accumulate, addend, gate) writes one consumer's contribution to d/d(t)."""
+        """launch(dst, accumulate, addend, gate, stats_sub) writes one consumer's contribution to d/d(t); stats_sub is
+        None (no statistics), False (statistics, nothing subtracted) or the residual Act; it returns the statistics."""
         assert t.parent is None, 'gradients are accumulated on root activations'
         t.pending -= 1
         last = t.pending == 0
@@ -57,30 +70,32 @@ class Tape(object):
         if fusable:
             gate = t if (last and t.gate_on_grad) else None
             fused_gate = gate is not None
+            want = self._stats_request(t) if fused_gate else None
             if t.grad is None:
                 dst = t.like()
-                launch(dst, False, None, gate)
+                st = launch(dst, False, None, gate, want)
             elif t.grad_owned and not last:
                 dst = t.grad
-                launch(dst, True, None, None)
+                st = launch(dst, True, None, None, None)
             elif t.grad_owned:
                 dst = t.grad
-                launch(dst, False, dst, gate)          # epilogue reads the partial before overwriting it
+                st = launch(dst, False, dst, gate, want)   # epilogue reads the partial before overwriting it
             else:
                 dst = t.like()
-                launch(dst, False, t.grad, gate)
+                st = launch(dst, False, t.grad, gate, want)
             t.grad, t.grad_owned = dst, True
+            t.fused_stats = st if want is not None else None
         else:
             if t.grad is None:
                 dst = t.like()
-                launch(dst, False, None, None)
+                launch(dst, False, None, None, None)
                 t.grad, t.grad_owned = dst, True
             else:
                 if not t.grad_owned:
                     owned = t.like()
                     self.K.copy_act(owned, t.grad)
                     t.grad, t.grad_owned = owned, True
-                launch(t.grad, True, None, None)
+                launch(t.grad, True, None, None, None)
         self._finish(t, fused_gate)
 
     def contribute_tensor(self, t, g):
@@ -181,7 +196,12 @@ class ConvNode(object):
             dgam, acc = param_grad(bn.weight)
             dbet, acc2 = param_grad(bn.bias)
             assert acc == acc2
-            K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, self.residual, dgam, dbet, acc)
+            st = getattr(self.y, 'fused_stats', None) if self.y.parent is None else None
+            if st is not None:
+                K.bn_eval_param_grad_from_stats(st, bn.weight, bn.bias, dgam, dbet, acc)    # sums came with g
+                self.y.fused_stats = None
+            else:
+                K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, self.residual, dgam, dbet, acc)
         if self.conv.bias is not None and self.conv.bias.requires_grad:
             db, acc = param_grad(self.conv.bias)
             K.colsum(g, db, acc)
@@ -203,9 +223,10 @@ class ConvNode(object):
             return                                   # network input: no gradient needed
         wt, ldb = K.transpose_w(w, cout, kh * kw, cin, scale=self.scale)
 
-        def launch(dst, accumulate, addend, gate):
-            K.conv_dgrad(g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dst, addend=addend, gate=gate,
-                         accumulate=accumulate)
+        def launch(dst, accumulate, addend, gate, stats_sub):
+            return K.conv_dgrad(g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dst, addend=addend, gate=gate,
+                                accumulate=accumulate, want_stats=stats_sub is not None,
+                                stats_sub=stats_sub if stats_sub else None)
         tape.contribute_kernel(self.x, launch, fusable=(stride == 1))
 
 
@@ -268,7 +289,7 @@ class BilinearNode(object):
             tape.skip(self.x)
             return
         K, align = tape.K, self.align
-        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate: K.bilinear_bwd(dy, dst, align, accumulate=acc), False)
+        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate, stats: K.bilinear_bwd(dy, dst, align, accumulate=acc), False)
 
 
 class GapNode(object):
@@ -281,7 +302,7 @@ class GapNode(object):
             tape.skip(self.x)
             return
         K = tape.K
-        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate: K.gap_bwd(dy, dst, accumulate=acc), False)
+        tape.contribute_kernel(self.x, lambda dst, acc, addend, gate, stats: K.gap_bwd(dy, dst, accumulate=acc), False)
 
 
 class BcastNode(object):
@@ -465,5 +486,5 @@ def to_logits_nchw(tape, x, out_h, out_w, align_corners):
 def seed_output_grad(tape, x, dlogits, align_corners, scale_dev=None, scale_host=1.0):
     """Start of the backward pass: d(loss)/d(low-res logits) from d(loss)/d(logits) (NCHW)."""
     K = tape.K
-    tape.contribute_kernel(x, lambda dst, acc, addend, gate: K.bilinear_bwd_nchw(
+    tape.contribute_kernel(x, lambda dst, acc, addend, gate, stats: K.bilinear_bwd_nchw(
         dlogits, dst, align_corners, scale_dev=scale_dev, scale_host=scale_host, accumulate=acc), False)

@@ -76,10 +76,14 @@ class ActKernels(object):
             be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
                          out.h, out.w, out.ld, taps, istride=stride, **kwargs)
 
-    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False):
+    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False,
+                   want_stats=False, stats_sub=None):
         """dx (+)= dgrad(g, W).  wt: transposed weights, storage (cin, kh*kw, ldb) with K = cout.
         Stride-1 convolutions fuse `addend` (partial gradient) and `gate` (ReLU of the producer);
-        strided ones are decomposed into stride-1 phases scattered with output stride (no fusion)."""
+        strided ones are decomposed into stride-1 phases scattered with output stride (no fusion).
+        want_stats (needs gate): the epilogue also writes partial column sums of the gated gradient and of
+        gradient * (gate - stats_sub); returned for bn_eval_param_grad_from_stats (frozen-BN parameter gradients of the
+        layer that produced `gate` without another pass over HBM)."""
         be = self.be
         a_lo = b_lo = None
         ga, wb = g, wt
@@ -94,16 +98,19 @@ class ActKernels(object):
                 kwargs['addend'] = addend.ptr; kwargs['ld_add'] = addend.ld
             if gate is not None:
                 kwargs['gate'] = gate.ptr; kwargs['ld_gate'] = gate.ld
+            if want_stats:
+                assert gate is not None and not accumulate
+                kwargs['want_stats'] = True; kwargs['device'] = g.device
+                if stats_sub is not None:
+                    kwargs['stats_sub'] = stats_sub.ptr; kwargs['ld_stats_sub'] = stats_sub.ld
             taps = O.dgrad_taps(kh, kw, dil, pad)
             if kh == 1 and kw == 1 and pad == 0:
                 npix = g.rows
-                be.conv_gemm(ga.ptr, 1, 1, npix, cout, ga.ld, wb.data_ptr(), cin, 1, ldb, dx.ptr, 1, npix, 1, npix, dx.ld,
-                             taps, **kwargs)
-            else:
-                be.conv_gemm(ga.ptr, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), cin, kh * kw, ldb, dx.ptr, dx.h, dx.w,
-                             dx.h, dx.w, dx.ld, taps, **kwargs)
-            return
-        assert addend is None and gate is None, 'strided dgrad is not fused'
+                return be.conv_gemm(ga.ptr, 1, 1, npix, cout, ga.ld, wb.data_ptr(), cin, 1, ldb, dx.ptr, 1, npix, 1, npix,
+                                    dx.ld, taps, **kwargs)
+            return be.conv_gemm(ga.ptr, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), cin, kh * kw, ldb, dx.ptr, dx.h, dx.w,
+                                dx.h, dx.w, dx.ld, taps, **kwargs)
+        assert addend is None and gate is None and not want_stats, 'strided dgrad is not fused'
         if not accumulate:
             self.fill_act(dx, 0.0)
         s = stride
@@ -216,6 +223,13 @@ class ActKernels(object):
         self.be.bn_eval_param_grad(g.ptr, g.ld, y.ptr, y.ld, g.rows, g.c, gamma, beta, None, 0,
                                    None if sub is None else sub.ptr, 0 if sub is None else sub.ld, dgamma, dbeta,
                                    accumulate)
+
+    def bn_eval_param_grad_from_stats(self, stats, gamma, beta, dgamma, dbeta, accumulate):
+        self.be.bn_eval_param_grad_from_stats(stats, gamma, beta, dgamma, dbeta, accumulate)
+
+    def stats_ok(self, t):
+        """Can a dgrad epilogue produce the column statistics of activation t's gradient?  (vector-path layout)"""
+        return t.c % 4 == 0 and t.ld % 4 == 0 and t.off % 4 == 0
 
     def colsum(self, g, out, accumulate):
         self.be.colsum(g.ptr, g.ld, g.rows, g.c, out, accumulate)

@@ -41,6 +41,8 @@ class ConvParams(ctypes.Structure):
         ('scale2', c_vp),
         ('relu', c_i32), ('accumulate', c_i32), ('n_split', c_i32),
         ('max_ctas', c_i32),
+        ('stats', c_vp), ('ld_stats', c_i32),
+        ('stats_sub', c_vp), ('ld_stats_sub', c_i32),
     ]
 
 
@@ -77,6 +79,7 @@ _SIGS = {
     'b2_ce_finalize': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'b2_scale_inplace': (c_int, [c_vp, c_i64, c_vp, c_f32, c_vp]),
     'b2_conv_gemm': (c_int, [ctypes.POINTER(ConvParams), c_vp]),
+    'b2_conv_stats_rows': (c_i64, [ctypes.POINTER(ConvParams)]),
     'b2_conv_wgrad_workspace': (c_sz, [ctypes.POINTER(WgradParams)]),
     'b2_conv_wgrad': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
@@ -103,6 +106,8 @@ _SIGS = {
     'b2_bn_fold': (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp]),
     'b2_bn_eval_param_grad': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int,
                                       c_vp, c_vp, c_int, c_vp, c_vp]),
+    'b2_bn_eval_param_grad_from_stats': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    'b2_bn_stats_workspace_doubles': (c_i64, [c_int]),
     'b2_dropout_mask': (c_int, [c_vp, c_i64, c_f32, c_u64, c_u64, c_vp, c_vp]),
     'b2_add_inplace': (c_int, [c_vp, c_vp, c_i64, c_vp]),
     'b2_fill': (c_int, [c_vp, c_f32, c_i64, c_vp]),
@@ -111,7 +116,8 @@ _SIGS = {
 
 # Functions that return a size/count rather than an error code.
 _NON_STATUS = {'b2_version', 'b2_num_sms', 'b2_consistency_num_partials', 'b2_ce_num_partials',
-               'b2_conv_wgrad_workspace', 'b2_bn_workspace_doubles'}
+               'b2_conv_wgrad_workspace', 'b2_bn_workspace_doubles', 'b2_conv_stats_rows',
+               'b2_bn_stats_workspace_doubles'}
 
 _lib = None
 

@@ -168,8 +168,10 @@ class CudaBackend(object):
     def conv_gemm(self, a_ptr, n, ih, iw, k, lda, b_ptr, nb, tb, ldb, d_ptr, oh, ow, fh, fw, ldd, taps,
                   ostride=1, ooh=0, oow=0, istride=1, scale=None, shift=None, addend=None, ld_add=0,
                   gate=None, ld_gate=0, scale2=None, relu=False, accumulate=False,
-                  a_lo_ptr=None, b_lo_ptr=None, n_split=1, max_ctas=0):
-        """Raw-pointer form of b2_conv_gemm (see include/b200seg.h)."""
+                  a_lo_ptr=None, b_lo_ptr=None, n_split=1, max_ctas=0, want_stats=False, stats_sub=None,
+                  ld_stats_sub=0, device=None):
+        """Raw-pointer form of b2_conv_gemm (see include/b200seg.h).  want_stats: also return the fused column
+        statistics buffer (stats tensor (row blocks, 2, ld), row blocks, ld) for b2_bn_eval_param_grad_from_stats."""
         taps_arr = np.ascontiguousarray(np.asarray(taps, dtype=np.int32).reshape(-1, 3))
         p = L.ConvParams()
         p.a = a_ptr; p.a_lo = a_lo_ptr; p.b = b_ptr; p.b_lo = b_lo_ptr; p.d = d_ptr
@@ -186,9 +188,18 @@ class CudaBackend(object):
         p.scale2 = L.ptr(scale2)
         p.relu = int(bool(relu)); p.accumulate = int(bool(accumulate)); p.n_split = n_split
         p.max_ctas = max_ctas
+        stats = None
+        if want_stats:
+            rows = int(L.call('b2_conv_stats_rows', ctypes.byref(p)))
+            ld = (nb + 3) // 4 * 4
+            buf = torch.empty((rows, 2, ld), device=device, dtype=torch.float32)
+            p.stats = buf.data_ptr(); p.ld_stats = ld
+            p.stats_sub = stats_sub; p.ld_stats_sub = ld_stats_sub
+            stats = (buf, rows, ld)
         flops = 2.0 * n * oh * ow * nb * k * taps_arr.shape[0] * n_split
         self._prof_tag = 'pix{} k{} n{} taps{} s{}'.format(n * oh * ow, k, nb, taps_arr.shape[0], istride)
         self._timed_call('conv_gemm2_kernel' if (nb > 224 and max_ctas != 1) else 'conv_gemm_kernel', flops / n_split, 'b2_conv_gemm', ctypes.byref(p), self._s())
+        return stats
 
     def conv_wgrad(self, dy_ptr, n, oh, ow, m, ldy, x_ptr, ih, iw, c, ldx, dw_ptr, taps, tw, istride=1,
                    accumulate=False, dy_lo_ptr=None, x_lo_ptr=None, n_split=1, max_ctas=0, device=None,
@@ -288,6 +299,16 @@ class CudaBackend(object):
                    gate_ptr, ldg, sub_ptr, lds, dgamma.data_ptr(), dbeta.data_ptr(), int(bool(accumulate)),
                    ws.data_ptr(), self._s())
         self.launches += 2
+
+    def bn_eval_param_grad_from_stats(self, stats, gamma, beta, dgamma, dbeta, accumulate):
+        buf, rows, ld = stats
+        c = gamma.numel()
+        need = int(L.call('b2_bn_stats_workspace_doubles', c))
+        if getattr(self, '_rws', None) is None or self._rws.numel() < need or self._rws.device != gamma.device:
+            self._rws = torch.empty((need,), device=gamma.device, dtype=torch.float64)
+        self._call('b2_bn_eval_param_grad_from_stats', buf.data_ptr(), rows, ld, c, gamma.data_ptr(), beta.data_ptr(),
+                   dgamma.data_ptr(), dbeta.data_ptr(), int(bool(accumulate)), self._rws.data_ptr(), self._s())
+        self.launches += 1
 
     def colsum(self, dy_ptr, ld, rows, c, out, accumulate):
         ws = self._red_ws(rows, c, out.device)

@@ -142,8 +142,15 @@ typedef struct b2_conv_params {
   const float* scale2;
   int32_t relu, accumulate, n_split;
   int32_t max_ctas;                       /* 0 = one persistent CTA per SM */
+  /* Optional fused column statistics of the stored value v (needs gate, no accumulate, nb % 4 == 0): partial sums
+   * over row blocks of <= 32 pixels, stats[(blk*2 + j)*ld_stats + ch], j = 0: sum v, j = 1: sum v*(gate - stats_sub),
+   * blk < b2_conv_stats_rows(p).  Every (blk, ch < nb) entry is written exactly once (deterministic); reduce them with
+   * b2_bn_eval_param_grad_from_stats.  Replaces a separate b2_bn_eval_param_grad pass over g and y. */
+  float* stats; int32_t ld_stats;
+  const float* stats_sub; int32_t ld_stats_sub;   /* laid out like D, or NULL */
 } b2_conv_params;
 int b2_conv_gemm(const b2_conv_params* p, void* stream);
+int64_t b2_conv_stats_rows(const b2_conv_params* p);
 
 /* wgrad:  dW[m, tap, c] (+)= sum_pix dY[pix, m] * X[pix@tap, c]
  *   dY: NHWC (N, OH, OW, M) ld = ldy;  X: NHWC (N, IH, IW, C) ld = ldx;  dW: (M, T, C) fp32.
@@ -238,6 +245,12 @@ int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn, int ldy, 
                           const float* gamma, const float* beta, const float* gate, int ldg,
                           const float* sub, int lds, float* dgamma, float* dbeta, int accumulate,
                           double* workspace, void* stream);
+/* Same result from the partial sums a b2_conv_gemm epilogue wrote (b2_conv_params.stats): fixed-order reduction over
+ * the `stat_rows` row blocks in double, then dbeta (+)= S0, dgamma (+)= (S1 - beta*S0)/gamma. */
+int b2_bn_eval_param_grad_from_stats(const float* stats, int64_t stat_rows, int ld_stats, int c, const float* gamma,
+                                     const float* beta, float* dgamma, float* dbeta, int accumulate,
+                                     double* workspace, void* stream);   /* >= b2_bn_stats_workspace_doubles(c) */
+int64_t b2_bn_stats_workspace_doubles(int c);
 /* dropout keep-mask: mask[i] = (hash(seed, offset + *offset_dev + i) >= p) ? 1 : 0; offset_dev (may be NULL) is a
  * device counter so that CUDA-graph replays advance the random stream. */
 int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset,

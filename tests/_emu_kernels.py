@@ -60,8 +60,9 @@ class EmuKernels(object):
             y = y * (_v(gate) > 0)
         _store(out, y)
 
-    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False):
-        self.calls.append('conv_dgrad')
+    def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False,
+                   want_stats=False, stats_sub=None):
+        self.calls.append('conv_dgrad' + ('+stats' if want_stats else ''))
         w = _w(wt, cin, kh * kw, ldb, cout).view(cin, kh, kw, cout).permute(3, 0, 1, 2)   # (cout, cin, kh, kw)
         gy = _v(g)
         opad_h = dx.h - ((g.h - 1) * stride - 2 * pad + dil * (kh - 1) + 1)
@@ -72,6 +73,24 @@ class EmuKernels(object):
         if gate is not None:
             d = d * (_v(gate) > 0)
         _store(dx, d, accumulate)
+        if want_stats:
+            assert gate is not None and not accumulate
+            yv = _v(gate) if stats_sub is None else _v(gate) - _v(stats_sub)
+            return (d.sum(dim=(0, 2, 3)), (d * yv).sum(dim=(0, 2, 3)))
+        return None
+
+    def stats_ok(self, t):
+        return t.c % 4 == 0 and t.ld % 4 == 0 and t.off % 4 == 0
+
+    def bn_eval_param_grad_from_stats(self, stats, gamma, beta, dgamma, dbeta, accumulate):
+        self.calls.append('bn_eval_param_grad_from_stats')
+        sg, sgy = stats
+        dg = (sgy - beta.to(DT) * sg) / gamma.to(DT)
+        for tgt, val in ((dgamma, dg), (dbeta, sg)):
+            if accumulate:
+                tgt += val.to(torch.float32)
+            else:
+                tgt.copy_(val.to(torch.float32))
 
     def conv_wgrad(self, g, x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=None, accumulate=False):
         self.calls.append('conv_wgrad')
@@ -221,6 +240,7 @@ class EmuKernels(object):
         scale.copy_(s); shift.copy_(beta - mean * s)
 
     def bn_eval_param_grad(self, g, y, gamma, beta, sub, dgamma, dbeta, accumulate):
+        self.calls.append('bn_eval_param_grad')
         gv = _v(g); yv = _v(y)
         if sub is not None:
             yv = yv - _v(sub)

@@ -91,6 +91,10 @@ def test_deeplab3plus_frozen_backbone_train_head(emu):
     nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
     assert nb['deeplab.classifier.project.1.num_batches_tracked'] == 1
     assert nb['deeplab.backbone.bn1.num_batches_tracked'] == 0
+    # frozen-BN parameter gradients: nearly every backbone layer gets its column sums from the dgrad epilogue that
+    # finished its output gradient; only strided / slice / pooled consumers fall back to the separate reduction
+    fused, plain = emu.calls.count('bn_eval_param_grad_from_stats'), emu.calls.count('bn_eval_param_grad')
+    assert fused == emu.calls.count('conv_dgrad+stats') and fused + plain == 104 and fused >= 90, (fused, plain)
 
 
 def test_gradient_accumulation_over_two_backward_passes(emu):

@@ -234,6 +234,51 @@ def test_conv_fprop_dgrad_wgrad(case, n_split):
     assert relerr(dw.view(Cout, k, k, Cin), ref) < tol
 
 
+@pytest.mark.parametrize('case', [
+    # N, H, W, Cout(gemm K), Cin(gemm N = stats channels), k, dil, addend, sub
+    (2, 12, 10, 48, 96, 3, 2, True, True),        # single-CTA kernel, ragged M tiles
+    (3, 17, 12, 64, 256, 1, 1, True, False),      # CTA-pair kernel, 5 M tiles (phantom sixth)
+    (2, 16, 16, 128, 512, 3, 1, False, True),     # CTA-pair kernel, two N tiles
+    (1, 33, 41, 64, 64, 1, 1, False, False),
+], ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_dgrad_fused_bn_statistics(case):
+    """The dgrad epilogue that finishes a frozen-BN layer's output gradient also writes the column sums its affine
+    parameters need; b2_bn_eval_param_grad_from_stats must reproduce the separate reduction (fp64 reference)."""
+    from cutmix_semisup_seg_b200.kernels import ActKernels
+    from cutmix_semisup_seg_b200.acts import Act
+    N, H, W, Cout, Cin, k, dil, use_add, use_sub = case
+    torch.manual_seed(sum(map(int, case)))
+    K = ActKernels(n_split=3)
+    pad = dil * (k // 2)
+    w = torch.randn(Cout, Cin, k, k) / (Cin * k * k) ** 0.5
+    g = torch.randn(N, Cout, H, W); partial = torch.randn(N, Cin, H, W); yprev = torch.randn(N, Cin, H, W)
+    sub = torch.randn(N, Cin, H, W)
+    gamma = torch.rand(Cin) + 0.5; beta = torch.randn(Cin)
+    xg = torch.zeros(N, Cin, H, W, dtype=torch.double, requires_grad=True)
+    F.conv2d(xg, w.double(), padding=pad, dilation=dil).backward(g.double())
+    gin = (xg.grad + (partial.double() if use_add else 0)) * (yprev > 0)
+    yv = yprev.double() - (sub.double() if use_sub else 0)
+    sg = gin.sum(dim=(0, 2, 3)); sgy = (gin * yv).sum(dim=(0, 2, 3))
+    ref_dbeta = sg; ref_dgamma = (sgy - beta.double() * sg) / gamma.double()
+    wt, ldb = K.transpose_w(w.permute(0, 2, 3, 1).contiguous().to(dev), Cout, k * k, Cin)
+    dx = Act.alloc(N, H, W, Cin, dev)
+    st = K.conv_dgrad(Act(nhwc(g).to(dev), N, H, W, Cout), wt, Cin, k, k, Cout, ldb, 1, pad, dil, dx,
+                      addend=Act(nhwc(partial).to(dev), N, H, W, Cin) if use_add else None,
+                      gate=Act(nhwc(yprev).to(dev), N, H, W, Cin), want_stats=True,
+                      stats_sub=Act(nhwc(sub).to(dev), N, H, W, Cin) if use_sub else None)
+    assert relerr(dx.to_nchw(), gin) < 5e-5
+    dgam = torch.full((Cin,), 3.0, device=dev); dbet = torch.full((Cin,), -2.0, device=dev)
+    K.bn_eval_param_grad_from_stats(st, gamma.to(dev), beta.to(dev), dgam, dbet, False)
+    assert relerr(dbet, ref_dbeta) < 1e-4 and relerr(dgam, ref_dgamma) < 1e-4
+    K.bn_eval_param_grad_from_stats(st, gamma.to(dev), beta.to(dev), dgam, dbet, True)       # accumulate
+    assert relerr(dbet, 2 * ref_dbeta) < 1e-4 and relerr(dgam, 2 * ref_dgamma) < 1e-4
+    # and it agrees with the stand-alone reduction kernel on the same stored gradient
+    dgam2 = torch.empty(Cin, device=dev); dbet2 = torch.empty(Cin, device=dev)
+    K.bn_eval_param_grad(dx, Act(nhwc(yprev).to(dev), N, H, W, Cin), gamma.to(dev), beta.to(dev),
+                         Act(nhwc(sub).to(dev), N, H, W, Cin) if use_sub else None, dgam2, dbet2, False)
+    assert relerr(dgam2, ref_dgamma) < 1e-4 and relerr(dbet2, ref_dbeta) < 1e-4
+
+
 def test_conv_fused_epilogue_and_concat_slice():
     """scale/shift + residual + ReLU epilogue writing into a channel slice of a wider buffer; dgrad with the
     fused addend + ReLU gate (the backward fusion the engine relies on)."""
