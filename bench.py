@@ -137,7 +137,9 @@ def run_b200(args):
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
+        import datetime
+        # fail fast on a rank mismatch instead of NCCL's 10 minute default (a hung box burns the GPU budget)
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
     from cutmix_semisup_seg_b200 import synthetic
     cfg = CFG[args.arch]
     n, h, w = args.batch or cfg['batch'], cfg['h'], cfg['w']
@@ -196,7 +198,10 @@ def run_b200(args):
     ms_e2e = e0.elapsed_time(e1)
 
     # ---- per-kernel roofline (instrumented iteration outside the timed regions)
-    prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0]) if rank == 0 else None
+    # every rank runs it (the iteration contains the gradient all-reduce); only rank 0 reports
+    prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0])
+    if rank != 0:
+        prof = None
 
     if dist_on:
         t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)

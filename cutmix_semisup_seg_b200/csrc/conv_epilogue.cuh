@@ -43,8 +43,28 @@ struct Params {
   // stats[(row_block*2 + j)*ld_stats + ch], j = 0: sum v, j = 1: sum v*(gate - sub); row_block = m_tile*4 + lane quarter
   float* stats; int ld_stats;
   const float* sub; int ld_sub;
-  int dbg;          // debug knob 3: 1 = skip HBM stores, 2 = also skip the TMEM loads (timing experiments only)
+  int dbg;          // debug knob 3 (timing experiments only): low bits 1 = skip HBM stores, 2 = also skip the TMEM
+                    // loads; bit 2 (value 4) = L2-prefetch the next tile's epilogue operands (measured slower: see below)
 };
+
+// EXPERIMENT (off by default, debug knob 3 bit 2): L2 prefetch of the epilogue's read operands (residual addend / ReLU gate / statistics `sub`) for one output row of an
+// upcoming tile: `cols` channels starting at `c0` (one contiguous run per row).  The loads themselves are issued only
+// after the accumulator is ready, 4-8 row groups at a time (~16-32 KB in flight per SM, far below the ~90 KB that
+// HBM latency x 1/148 of HBM bandwidth needs), so without this the HBM-bound 1x1 layers run latency-bound; L2
+// prefetches (one per 128 B line; no registers, no smem) should turn those loads into L2 hits.  Measured in situ (run 19/20,
+// profiles/): both this and cp.async.bulk.prefetch.L2 made the k256->n1024 layers 14-16% SLOWER, so it is disabled.
+__device__ __forceinline__ void prefetch_lines(const float* p, int floats) {
+  for (int o = 0; o < floats; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+__device__ __forceinline__ void prefetch_row(const Params& p, int pix, int c0, int cols) {
+  if (pix < 0) return;
+  int n = p.nb - c0; if (n > cols) n = cols;
+  if (n <= 0) return;
+  if (p.addend) prefetch_lines(p.addend + (long long)pix * p.ld_add + c0, n);
+  if (p.gate) prefetch_lines(p.gate + (long long)pix * p.ld_gate + c0, n);
+  if (p.stats && p.sub) prefetch_lines(p.sub + (long long)pix * p.ld_sub + c0, n);
+  if (p.accumulate) prefetch_lines(p.d + (long long)pix * p.ldd + c0, n);
+}
 
 // Out-of-line general path for one lane's 4 columns of one row: any channel count / alignment, accumulate.
 static __device__ __noinline__ void slow_store(const Params& p, float4 v, int pix, int c) {
@@ -89,7 +109,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
 #pragma unroll 1                        // keep the body resident in the instruction cache (4 specialisations x 2 kernels)
   for (int ch = half; ch < nchunks; ch += 2) {
     uint32_t r[32];
-    if (p.dbg < 2) {
+    if ((p.dbg & 3) < 2) {
       tc::tmem_ld_x32(taddr + ch * 32, r);
       tc::tmem_ld_wait();
     } else {
@@ -155,7 +175,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
             a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
             a1.x = fmaf(o.x, yv.x, a1.x); a1.y = fmaf(o.y, yv.y, a1.y); a1.z = fmaf(o.z, yv.z, a1.z); a1.w = fmaf(o.w, yv.w, a1.w);
           }
-          if (od[i] >= 0 && !p.dbg) {
+          if (od[i] >= 0 && !(p.dbg & 3)) {
             float4* dst = reinterpret_cast<float4*>(p.d + (long long)od[i] * p.ldd + c);
             if (acc) {                    // several dgrads summing into one input gradient (ASPP branches, phases)
               const float4 old = *dst;

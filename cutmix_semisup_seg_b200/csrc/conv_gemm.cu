@@ -182,19 +182,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const epi::Params& ep = a.ep;     // stays in the kernel's constant parameter space
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
+    const int dn = row / bwbh;
+    const int rem = row - dn * bwbh;
+    const int dhh = rem / a.bw;
+    const int dww = rem - dhh * a.bw;
+    auto row_pixel = [&](const TileInfo& ti) -> int {       // output pixel index of this thread's accumulator row
+      const int pn = ti.n0 + dn, ph = ti.h0 + dhh, pw = ti.w0 + dww;
+      const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
+      const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
+      return valid ? (int)pix : -1;
+    };
+    const bool has_reads = (ep.dbg & 4) && (ep.addend || ep.gate || ep.accumulate);
+    const int half_cols = ((a.block_n / 32 + 1) / 2) * 32;      // the two warps of a lane quarter prefetch half a row each
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(a, tile);
-      {
-        const int dn = row / bwbh;
-        const int rem = row - dn * bwbh;
-        const int dhh = rem / a.bw;
-        const int dww = rem - dhh * a.bw;
-        const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
-        const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
-        const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
-        __syncwarp();
-        rowpix[lane] = valid ? (int)pix : -1;
-        __syncwarp();
+      __syncwarp();
+      rowpix[lane] = row_pixel(t);
+      __syncwarp();
+      if (has_reads && tile + (int)gridDim.x < a.num_tiles) {   // next tile's epilogue operands -> L2 (see prefetch_row)
+        const TileInfo tn = decode_tile(a, tile + gridDim.x);
+        epi::prefetch_row(ep, row_pixel(tn), tn.n_idx * a.block_n + eh * half_cols, eh ? a.block_n - half_cols : half_cols);
       }
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();

@@ -255,19 +255,25 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int bwbh = a.bw * a.bh;
     int tr_e = 0;
     const bool tracer = a.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const int dn = row / bwbh;
+    const int rem = row - dn * bwbh;
+    const int dhh = rem / a.bw;
+    const int dww = rem - dhh * a.bw;
+    auto row_pixel = [&](const TileInfo& ti) -> int {       // output pixel index of this thread's accumulator row
+      const int pn = ti.n0 + dn, ph = ti.h0 + dhh, pw = ti.w0 + dww;
+      const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
+      const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
+      return valid ? (int)pix : -1;
+    };
+    const bool has_reads = (ep.dbg & 4) && (ep.addend || ep.gate || ep.accumulate);
     for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
       const TileInfo t = decode_tile(a, pair, (int)rank);
-      {
-        const int dn = row / bwbh;
-        const int rem = row - dn * bwbh;
-        const int dhh = rem / a.bw;
-        const int dww = rem - dhh * a.bw;
-        const int pn = t.n0 + dn, ph = t.h0 + dhh, pw = t.w0 + dww;
-        const bool valid = (uint32_t)row < rows_a && pn < a.n && ph < a.oh && pw < a.ow;
-        const long long pix = ((long long)pn * a.fh + (long long)ph * a.ostride + a.ooh) * a.fw + (long long)pw * a.ostride + a.oow;
-        __syncwarp();
-        rowpix[lane] = valid ? (int)pix : -1;
-        __syncwarp();
+      __syncwarp();
+      rowpix[lane] = row_pixel(t);
+      __syncwarp();
+      if (has_reads && pair + num_clusters < a.num_pairs) {     // next tile's epilogue operands -> L2 (see prefetch_row)
+        const TileInfo tn = decode_tile(a, pair + num_clusters, (int)rank);
+        epi::prefetch_row(ep, row_pixel(tn), tn.n_idx * BLOCK_N + eh * (BLOCK_N / 2), BLOCK_N / 2);
       }
       if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       tc::mbar_wait(&tfull_bar[acc], acc_phase);

@@ -105,3 +105,27 @@ if __name__ == '__main__':
             print('mma tile [begin, acc acquired]*:', tile[:24])
             print('epi  tile [wait begin, tfull ]*:', epi[:24])
             print('last stamps: prod {} mma {} tile {} epi {}'.format(prod[-1] if prod else 0, mma[-1] if mma else 0, tile[-1] if tile else 0, epi[-1] if epi else 0))
+    if which == 'l3full':
+        # the two in-situ flavours of the HBM-bound layer3 1x1 (256 -> 1024 channels): forward with folded BN +
+        # residual + ReLU, and the dgrad with partial-gradient addend + ReLU gate + fused BN statistics (+ residual sub)
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        n, h, w, cin, cout = 16, 64, 64, 256, 1024
+        x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+        wt = torch.randn(cout, 1, cin, device=dev) * 0.01
+        y = Act.alloc(n, h, w, cout, dev)
+        res = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+        gate = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+        sub = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+        sc = torch.rand(cout, device=dev) + 0.5; sh = torch.randn(cout, device=dev)
+        fl = 2.0 * n * h * w * cin * cout
+        g = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+        wtt, ldb = K.transpose_w(torch.randn(cin, 1, cout, device=dev) * 0.01, cin, 1, cout)
+        for dbg in (0, 4):
+            L.b2_debug_set(3, dbg)
+            tag = ' [prefetch={}]'.format(dbg >> 2)
+            timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y), fl, 'fwd plain' + tag)
+            timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y, scale=sc, shift=sh, addend=res, relu=True), fl, 'fwd bn+residual+relu' + tag)
+            timeit(lambda: K.conv_dgrad(g, wtt, cout, 1, 1, cin, ldb, 1, 0, 1, y, addend=res, gate=gate), fl, 'dgrad addend+gate' + tag)
+            timeit(lambda: K.conv_dgrad(g, wtt, cout, 1, 1, cin, ldb, 1, 0, 1, y, addend=res, gate=gate, want_stats=True, stats_sub=sub), fl, 'dgrad addend+gate+stats+sub' + tag)
+        L.b2_debug_set(3, 0)
