@@ -12,12 +12,16 @@ constexpr int LOSS_THREADS = 256;
 
 enum { LOSS_VAR = 0, LOSS_LOGITS_VAR = 1, LOSS_LOGITS_SMOOTHL1 = 2, LOSS_BCE = 3, LOSS_KLD = 4 };
 
-template <int MAXC>
+// EXACT: the class count is the compile-time constant MAXC (19 / 21 / 2: the reference's data sets), so the channel
+// loops carry no run-time guards: every load of a pixel's 3*C logits is issued before the first use (with the guarded
+// form the compiler serialised them -- three loads in flight per thread, 1.6 ms for 1.3 GB; profiles/r01_v6_*).
+template <int MAXC, bool EXACT>
 __global__ void __launch_bounds__(LOSS_THREADS)
 consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, const float* __restrict__ ls,
                    const float* __restrict__ m, const float* __restrict__ lmask, float* __restrict__ dls,
-                   double* __restrict__ partials, int C, int64_t hw, int loss_fn, float conf_thresh,
+                   double* __restrict__ partials, int C_rt, int64_t hw, int loss_fn, float conf_thresh,
                    int conf_per_pixel) {
+  const int C = EXACT ? MAXC : C_rt;
   __shared__ double red[32];
   const int img = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
@@ -30,17 +34,13 @@ consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, c
     const float om = __fsub_rn(1.0f, mv);
     const float w = lmask ? __ldg(lmask + pm) : 1.0f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const float a = __ldg(l0 + base + (int64_t)c * hw);
-        if (l1) {
-          const float b = __ldg(l1 + base + (int64_t)c * hw);
-          lt[c] = __fadd_rn(__fmul_rn(a, om), __fmul_rn(b, mv));  // line 363
-        } else {
-          lt[c] = a;
-        }
-        st[c] = __ldg(ls + base + (int64_t)c * hw);
-      }
+    for (int c = 0; c < MAXC; ++c) if (c < C) { lt[c] = __ldg(l0 + base + (int64_t)c * hw); st[c] = __ldg(ls + base + (int64_t)c * hw); }
+    if (l1) {
+      float lb[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) lb[c] = __ldg(l1 + base + (int64_t)c * hw);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) lt[c] = __fadd_rn(__fmul_rn(lt[c], om), __fmul_rn(lb[c], mv));  // line 363
     }
     // softmax statistics (lines 366-367)
     float mt = -CUDART_INF_F, ms = -CUDART_INF_F;
@@ -150,11 +150,14 @@ extern "C" int b2_consistency_fwd_bwd(const float* l0, const float* l1, const fl
   B2_REQUIRE(n <= 65535, "b2_consistency_fwd_bwd: n too large");
   dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(MC) consistency_kernel<MC><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, m, lmask, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
-  if (c <= 8) LAUNCH(8);
-  else if (c <= 24) LAUNCH(24);
-  else if (c <= 32) LAUNCH(32);
-  else LAUNCH(64);
+#define LAUNCH(MC, EX) consistency_kernel<MC, EX><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, m, lmask, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
+  if (c == 19) LAUNCH(19, true);            // Cityscapes
+  else if (c == 21) LAUNCH(21, true);       // Pascal VOC
+  else if (c == 2) LAUNCH(2, true);         // ISIC
+  else if (c <= 8) LAUNCH(8, false);
+  else if (c <= 24) LAUNCH(24, false);
+  else if (c <= 32) LAUNCH(32, false);
+  else LAUNCH(64, false);
 #undef LAUNCH
   B2_LAUNCH_CHECK("consistency_kernel");
   return B2_OK;
@@ -202,10 +205,11 @@ extern "C" int b2_consistency_finalize(const double* partials, int64_t n_partial
 // ------------------------------------------------------------------------------------------
 // Cross entropy with ignore_index.
 // ------------------------------------------------------------------------------------------
-template <int MAXC>
+template <int MAXC, bool EXACT>
 __global__ void __launch_bounds__(LOSS_THREADS)
 ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ dlogits,
-          double* __restrict__ partials, int C, int64_t hw, int64_t ignore_index) {
+          double* __restrict__ partials, int C_rt, int64_t hw, int64_t ignore_index) {
+  const int C = EXACT ? MAXC : C_rt;
   __shared__ double red[32];
   const int img = blockIdx.y;
   const int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
@@ -247,11 +251,14 @@ extern "C" int b2_ce_fwd_bwd(const float* logits, const int64_t* labels, float* 
   B2_REQUIRE(n <= 65535, "b2_ce_fwd_bwd: n too large");
   dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(MC) ce_kernel<MC><<<grid, LOSS_THREADS, 0, s>>>(logits, labels, dlogits, partials, c, hw, ignore_index)
-  if (c <= 8) LAUNCH(8);
-  else if (c <= 24) LAUNCH(24);
-  else if (c <= 32) LAUNCH(32);
-  else LAUNCH(64);
+#define LAUNCH(MC, EX) ce_kernel<MC, EX><<<grid, LOSS_THREADS, 0, s>>>(logits, labels, dlogits, partials, c, hw, ignore_index)
+  if (c == 19) LAUNCH(19, true);
+  else if (c == 21) LAUNCH(21, true);
+  else if (c == 2) LAUNCH(2, true);
+  else if (c <= 8) LAUNCH(8, false);
+  else if (c <= 24) LAUNCH(24, false);
+  else if (c <= 32) LAUNCH(32, false);
+  else LAUNCH(64, false);
 #undef LAUNCH
   B2_LAUNCH_CHECK("ce_kernel");
   return B2_OK;

@@ -46,31 +46,41 @@ extern "C" int b2_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h
 }
 
 // ------------------------------------------------------------------------------------------ im2col
-__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n, int h, int w, int c, int ldx,
-                              int kh, int kw, int stride, int pad, int dil, int oh, int ow, int kpad) {
-  // one thread per (output pixel, filter row r): copies kw pixels x c channels = one contiguous run of the column row;
-  // thread 0 of each pixel also zero-fills the K padding.
-  const int64_t total = (int64_t)n * oh * ow * kh;
+// Thread per (output pixel, group of 4 consecutive K columns): one 16 B store per thread, consecutive threads write
+// consecutive 16 B pieces of the column matrix (write-bound: the matrix is ~13x the image).  K index = (r*kw + s)*c + ch;
+// columns >= kh*kw*c are the zero padding.  Requires kpad % 4 == 0 and a 16 B aligned matrix (host-checked).
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n, int h, int w, int c,
+                                                     int ldx, int kh, int kw, int stride, int pad, int dil, int oh, int ow, int kpad) {
+  const int groups = kpad >> 2;
   const int kreal = kh * kw * c;
+  const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i % kh); int64_t row = i / kh;
-    const int x_o = (int)(row % ow); int64_t t = row / ow; const int y_o = (int)(t % oh); const int img = (int)(t / oh);
-    float* dst = col + row * kpad + (int64_t)r * kw * c;
-    const int iy = y_o * stride - pad + r * dil;
-    const bool yin = iy >= 0 && iy < h;
-    for (int s_ = 0; s_ < kw; ++s_) {
-      const int ix = x_o * stride - pad + s_ * dil;
-      const bool in = yin && ix >= 0 && ix < w;
-      const float* src = x + (((int64_t)img * h + iy) * w + ix) * ldx;
-      for (int cc = 0; cc < c; ++cc) dst[s_ * c + cc] = in ? __ldg(src + cc) : 0.f;
+    const int64_t row = i / groups;
+    const int grp = (int)(i - row * groups);
+    const int x_o = (int)(row % ow); const int64_t t = row / ow; const int y_o = (int)(t % oh); const int img = (int)(t / oh);
+    int k = grp * 4;
+    int tap = k / c, ch = k - tap * c;
+    int r = tap / kw, s_ = tap - r * kw;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float val = 0.f;
+      if (k < kreal) {
+        const int iy = y_o * stride - pad + r * dil, ix = x_o * stride - pad + s_ * dil;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(x + (((int64_t)img * h + iy) * w + ix) * ldx + ch);
+      }
+      v[e] = val;
+      ++k;
+      if (++ch == c) { ch = 0; if (++s_ == kw) { s_ = 0; ++r; } }
     }
-    if (r == 0) for (int j = kreal; j < kpad; ++j) col[row * kpad + j] = 0.f;
+    *reinterpret_cast<float4*>(col + row * kpad + grp * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
                          int dil, int oh, int ow, int kpad, void* stream) {
   B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
-  const int64_t total = (int64_t)n * oh * ow * kh;
+  B2_REQUIRE(kpad % 4 == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, "b2_im2col: kpad must be a multiple of 4 and col 16 B aligned");
+  const int64_t total = (int64_t)n * oh * ow * (kpad / 4);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 64) blocks = 148 * 64;
   im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, col, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad);
   B2_LAUNCH_CHECK("im2col_kernel");
@@ -78,42 +88,67 @@ extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c,
 }
 
 // ------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
-__global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, int n, int h, int w,
-                               int c, int oh, int ow) {
-  const int64_t total = (int64_t)n * oh * ow * c;
+// V = 4: thread per (output pixel, 4 channels), 16 B loads / stores and one 32-bit store of the four argmax bytes
+// (needs c % 4 == 0 and 16 B aligned tensors); V = 1: any channel count.  First maximum wins, NaN propagates (PyTorch).
+template <int V>
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
+                                                      int n, int h, int w, int c, int oh, int ow) {
+  const int cg = c / V;
+  const int64_t total = (int64_t)n * oh * ow * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); int64_t t = i / c;
+    const int ch = (int)(i % cg) * V; int64_t t = i / cg;
     const int xo = (int)(t % ow); t /= ow; const int yo = (int)(t % oh); const int img = (int)(t / oh);
-    float best = -CUDART_INF_F; int bi = 0; bool any = false;
+    float best[V]; int bi[V]; bool any = false;
+#pragma unroll
+    for (int e = 0; e < V; ++e) { best[e] = -CUDART_INF_F; bi[e] = 0; }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int iy = yo * 2 - 1 + r, ix = xo * 2 - 1 + s;
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-          const float v = __ldg(x + (((int64_t)img * h + iy) * w + ix) * c + ch);
-          if (!any || v > best || v != v) { best = v; bi = r * 3 + s; any = true; }
+          const float* src = x + (((int64_t)img * h + iy) * w + ix) * c + ch;
+          float v[V];
+          if (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+          else v[0] = __ldg(src);
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (!any || v[e] > best[e] || v[e] != v[e]) { best[e] = v[e]; bi[e] = r * 3 + s; }
+          any = true;
         }
       }
-    y[i] = best; idx[i] = (uint8_t)bi;
+    const int64_t o = i * V;
+    if (V == 4) {
+      *reinterpret_cast<float4*>(y + o) = make_float4(best[0], best[1], best[2], best[3]);
+      *reinterpret_cast<uint32_t*>(idx + o) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    } else {
+      y[o] = best[0]; idx[o] = (uint8_t)bi[0];
+    }
   }
 }
 extern "C" int b2_maxpool3x3s2(const float* x, float* y, uint8_t* idx, int n, int h, int w, int c, int oh, int ow, void* stream) {
   B2_REQUIRE(x && y && idx && n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "b2_maxpool3x3s2: bad args");
-  const int64_t total = (int64_t)n * oh * ow * c;
+  const bool vec = c % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
+  const int64_t total = (int64_t)n * oh * ow * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  maxpool_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, idx, n, h, w, c, oh, ow);
+  if (vec) maxpool_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, idx, n, h, w, c, oh, ow);
+  else maxpool_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, idx, n, h, w, c, oh, ow);
   B2_LAUNCH_CHECK("maxpool_kernel");
   return B2_OK;
 }
 // gather form: each input pixel looks at the (up to 4) windows that contain it -> no atomics.
-__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx, int n,
-                                   int h, int w, int c, int oh, int ow) {
-  const int64_t total = (int64_t)n * h * w * c;
+template <int V>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                          float* __restrict__ dx, int n, int h, int w, int c, int oh, int ow) {
+  const int cg = c / V;
+  const int64_t total = (int64_t)n * h * w * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); int64_t t = i / c;
+    const int ch = (int)(i % cg) * V; int64_t t = i / cg;
     const int ix = (int)(t % w); t /= w; const int iy = (int)(t % h); const int img = (int)(t / h);
-    float g = 0.f;
+    float g[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) g[e] = 0.f;
     const int yo_lo = iy / 2, yo_hi = (iy + 1) / 2;   // windows with yo*2-1 <= iy <= yo*2+1
     const int xo_lo = ix / 2, xo_hi = (ix + 1) / 2;
     for (int yo = yo_lo; yo <= yo_hi; ++yo) {
@@ -125,18 +160,34 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
         const int s = ix - (xo * 2 - 1);
         if (s < 0 || s > 2) continue;
         const int64_t o = (((int64_t)img * oh + yo) * ow + xo) * c + ch;
-        if (idx[o] == r * 3 + s) g += __ldg(dy + o);
+        const uint32_t want = (uint32_t)(r * 3 + s);
+        if (V == 4) {
+          const uint32_t k = __ldg(reinterpret_cast<const uint32_t*>(idx + o));
+          if (((k & 255u) == want) | (((k >> 8) & 255u) == want) | (((k >> 16) & 255u) == want) | ((k >> 24) == want)) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(dy + o));
+            if ((k & 255u) == want) g[0] += q.x;
+            if (((k >> 8) & 255u) == want) g[1] += q.y;
+            if (((k >> 16) & 255u) == want) g[2] += q.z;
+            if ((k >> 24) == want) g[3] += q.w;
+          }
+        } else {
+          if (idx[o] == want) g[0] += __ldg(dy + o);
+        }
       }
     }
-    dx[i] = g;
+    if (V == 4) *reinterpret_cast<float4*>(dx + i * 4) = make_float4(g[0], g[1], g[2], g[3]);
+    else dx[i] = g[0];
   }
 }
 extern "C" int b2_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int n, int h, int w, int c, int oh, int ow,
                                    void* stream) {
   B2_REQUIRE(dy && idx && dx && n > 0, "b2_maxpool3x3s2_bwd: bad args");
-  const int64_t total = (int64_t)n * h * w * c;
+  const bool vec = c % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
+  const int64_t total = (int64_t)n * h * w * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  maxpool_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, idx, dx, n, h, w, c, oh, ow);
+  if (vec) maxpool_bwd_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, idx, dx, n, h, w, c, oh, ow);
+  else maxpool_bwd_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, idx, dx, n, h, w, c, oh, ow);
   B2_LAUNCH_CHECK("maxpool_bwd_kernel");
   return B2_OK;
 }
@@ -159,24 +210,40 @@ __device__ __forceinline__ LinCoef lin_coef(int dst, int in, float scale, int al
   return k;
 }
 
-// NHWC -> NHWC : thread per (pixel, channel), channel fastest.
-__global__ void bilinear_fwd_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw, int c, int ldx,
-                                         int oh, int ow, int ldy, int align) {
+// NHWC -> NHWC : thread per (output pixel, V channels), channel fastest (V = 4: 16 B loads / stores).
+template <int V>
+__global__ void __launch_bounds__(256) bilinear_fwd_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw,
+                                                                int c, int ldx, int oh, int ow, int ldy, int align) {
   const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
-  const int64_t total = (int64_t)n * oh * ow * c;
+  const int cg = c / V;
+  const int64_t total = (int64_t)n * oh * ow * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); int64_t t = i / c;
+    const int ch = (int)(i % cg) * V; int64_t t = i / cg;
     const int xo = (int)(t % ow); t /= ow; const int yo = (int)(t % oh); const int img = (int)(t / oh);
     const LinCoef ky = lin_coef(yo, ih, sh, align), kx = lin_coef(xo, iw, sw, align);
     const float* b = x + (int64_t)img * ih * iw * ldx + ch;
-    const float v00 = __ldg(b + ((int64_t)ky.i0 * iw + kx.i0) * ldx), v01 = __ldg(b + ((int64_t)ky.i0 * iw + kx.i1) * ldx);
-    const float v10 = __ldg(b + ((int64_t)ky.i1 * iw + kx.i0) * ldx), v11 = __ldg(b + ((int64_t)ky.i1 * iw + kx.i1) * ldx);
-    y[(((int64_t)img * oh + yo) * ow + xo) * ldy + ch] = ky.l0 * (kx.l0 * v00 + kx.l1 * v01) + ky.l1 * (kx.l0 * v10 + kx.l1 * v11);
+    const float* p00 = b + ((int64_t)ky.i0 * iw + kx.i0) * ldx; const float* p01 = b + ((int64_t)ky.i0 * iw + kx.i1) * ldx;
+    const float* p10 = b + ((int64_t)ky.i1 * iw + kx.i0) * ldx; const float* p11 = b + ((int64_t)ky.i1 * iw + kx.i1) * ldx;
+    float* o = y + (((int64_t)img * oh + yo) * ow + xo) * ldy + ch;
+    if (V == 4) {
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00)), v01 = __ldg(reinterpret_cast<const float4*>(p01));
+      const float4 v10 = __ldg(reinterpret_cast<const float4*>(p10)), v11 = __ldg(reinterpret_cast<const float4*>(p11));
+      float4 r;
+      r.x = ky.l0 * (kx.l0 * v00.x + kx.l1 * v01.x) + ky.l1 * (kx.l0 * v10.x + kx.l1 * v11.x);
+      r.y = ky.l0 * (kx.l0 * v00.y + kx.l1 * v01.y) + ky.l1 * (kx.l0 * v10.y + kx.l1 * v11.y);
+      r.z = ky.l0 * (kx.l0 * v00.z + kx.l1 * v01.z) + ky.l1 * (kx.l0 * v10.z + kx.l1 * v11.z);
+      r.w = ky.l0 * (kx.l0 * v00.w + kx.l1 * v01.w) + ky.l1 * (kx.l0 * v10.w + kx.l1 * v11.w);
+      *reinterpret_cast<float4*>(o) = r;
+    } else {
+      *o = ky.l0 * (kx.l0 * __ldg(p00) + kx.l1 * __ldg(p01)) + ky.l1 * (kx.l0 * __ldg(p10) + kx.l1 * __ldg(p11));
+    }
   }
 }
-// NHWC -> NCHW : thread per output pixel (xo fastest), loop over channels: coalesced plane writes.
-__global__ void bilinear_fwd_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw, int c, int ldx,
-                                         int oh, int ow, int align) {
+// NHWC -> NCHW : thread per output pixel (xo fastest), loop over channels: coalesced plane writes.  V = 4 reads the four
+// corner pixels 16 B at a time (needs ldx % 4 == 0 and a 16 B aligned x; channels past c inside the pitch are read, not stored).
+template <int V>
+__global__ void __launch_bounds__(128) bilinear_fwd_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int ih, int iw,
+                                                                int c, int ldx, int oh, int ow, int align) {
   const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
   const int64_t ohw = (int64_t)oh * ow;
   const int64_t total = (int64_t)n * ohw;
@@ -187,22 +254,40 @@ __global__ void bilinear_fwd_nchw_kernel(const float* __restrict__ x, float* __r
     const float* p00 = b + ((int64_t)ky.i0 * iw + kx.i0) * ldx; const float* p01 = b + ((int64_t)ky.i0 * iw + kx.i1) * ldx;
     const float* p10 = b + ((int64_t)ky.i1 * iw + kx.i0) * ldx; const float* p11 = b + ((int64_t)ky.i1 * iw + kx.i1) * ldx;
     float* o = y + (int64_t)img * c * ohw + (int64_t)yo * ow + xo;
-    for (int ch = 0; ch < c; ++ch)
-      o[(int64_t)ch * ohw] = ky.l0 * (kx.l0 * __ldg(p00 + ch) + kx.l1 * __ldg(p01 + ch)) + ky.l1 * (kx.l0 * __ldg(p10 + ch) + kx.l1 * __ldg(p11 + ch));
+    if (V == 4) {
+      for (int ch = 0; ch < c; ch += 4) {
+        const float4 v00 = __ldg(reinterpret_cast<const float4*>(p00 + ch)), v01 = __ldg(reinterpret_cast<const float4*>(p01 + ch));
+        const float4 v10 = __ldg(reinterpret_cast<const float4*>(p10 + ch)), v11 = __ldg(reinterpret_cast<const float4*>(p11 + ch));
+        o[(int64_t)ch * ohw] = ky.l0 * (kx.l0 * v00.x + kx.l1 * v01.x) + ky.l1 * (kx.l0 * v10.x + kx.l1 * v11.x);
+        if (ch + 1 < c) o[(int64_t)(ch + 1) * ohw] = ky.l0 * (kx.l0 * v00.y + kx.l1 * v01.y) + ky.l1 * (kx.l0 * v10.y + kx.l1 * v11.y);
+        if (ch + 2 < c) o[(int64_t)(ch + 2) * ohw] = ky.l0 * (kx.l0 * v00.z + kx.l1 * v01.z) + ky.l1 * (kx.l0 * v10.z + kx.l1 * v11.z);
+        if (ch + 3 < c) o[(int64_t)(ch + 3) * ohw] = ky.l0 * (kx.l0 * v00.w + kx.l1 * v01.w) + ky.l1 * (kx.l0 * v10.w + kx.l1 * v11.w);
+      }
+    } else {
+      for (int ch = 0; ch < c; ++ch)
+        o[(int64_t)ch * ohw] = ky.l0 * (kx.l0 * __ldg(p00 + ch) + kx.l1 * __ldg(p01 + ch)) + ky.l1 * (kx.l0 * __ldg(p10 + ch) + kx.l1 * __ldg(p11 + ch));
+    }
   }
 }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 extern "C" int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int c, int ldx, int oh, int ow, int ldy,
                                int align_corners, int to_nchw, void* stream) {
   B2_REQUIRE(x && y && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_fwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
   if (to_nchw) {
     const int64_t total = (int64_t)n * oh * ow;
     int64_t blocks = ceil_div64(total, 128); if (blocks > 148 * 64) blocks = 148 * 64;
-    bilinear_fwd_nchw_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(x, y, n, ih, iw, c, ldx, oh, ow, align_corners);
+    if (ldx % 4 == 0 && al16(x) && ldx >= (c + 3) / 4 * 4)
+      bilinear_fwd_nchw_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, align_corners);
+    else
+      bilinear_fwd_nchw_kernel<1><<<(unsigned)blocks, 128, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, align_corners);
   } else {
     B2_REQUIRE(ldy >= c, "b2_bilinear_fwd: ldy < c");
-    const int64_t total = (int64_t)n * oh * ow * c;
+    const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && al16(y);
+    const int64_t total = (int64_t)n * oh * ow * (vec ? c / 4 : c);
     int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-    bilinear_fwd_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
+    if (vec) bilinear_fwd_nhwc_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
+    else bilinear_fwd_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
   }
   B2_LAUNCH_CHECK("bilinear_fwd");
   return B2_OK;
@@ -221,6 +306,152 @@ __device__ __forceinline__ void out_range(int i, int in, int out, float scale, i
   *lo = l; *hi = h;
 }
 
+// The forward coefficients of every output row / column are tabulated once per block in shared memory
+// (tab[o] = {i0, i1, l1}; rows first, then columns), so the gather loops cost two LDS per candidate instead of
+// re-deriving lin_coef (float -> int conversions) for every (row, column) pair.  The summation order (rows outer,
+// columns inner, ascending) is the same for both source layouts.
+struct LinTab { int i0, i1; float l1; };
+constexpr int BIL_MAX_TAB = 3072;     // oh + ow entries (36 KB); larger outputs use the direct kernel below
+__device__ __forceinline__ float tab_weight(const LinTab& k, int i, bool* hit) {
+  float wgt = 0.f; *hit = false;
+  if (k.i0 == i) { wgt += 1.f - k.l1; *hit = true; }
+  if (k.i1 == i) { wgt += k.l1; *hit = true; }
+  return wgt;
+}
+// FROM_NCHW: thread per input pixel (xi fastest: coalesced plane reads), loop over channels, each thread writes its
+// pixel's contiguous channel vector.  Otherwise: thread per (input pixel, V channels), channel fastest.
+template <bool FROM_NCHW, int V>
+__global__ void __launch_bounds__(256) bilinear_bwd_tab_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int ih, int iw,
+                                                               int c, int ldx, int oh, int ow, int ldy, int align,
+                                                               const float* __restrict__ scale_dev, float scale_host, int accumulate) {
+  extern __shared__ LinTab tab[];
+  const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
+  for (int o = threadIdx.x; o < oh + ow; o += blockDim.x) {
+    const LinCoef k = o < oh ? lin_coef(o, ih, sh, align) : lin_coef(o - oh, iw, sw, align);
+    tab[o].i0 = k.i0; tab[o].i1 = k.i1; tab[o].l1 = k.l1;
+  }
+  __syncthreads();
+  const LinTab* ytab = tab; const LinTab* xtab = tab + oh;
+  const float gs = (scale_dev ? scale_dev[0] : 1.f) * scale_host;
+  const int64_t ohw = (int64_t)oh * ow;
+  const int cg = FROM_NCHW ? 1 : c / V;
+  const int64_t total = (int64_t)n * ih * iw * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ch0 = 0, xi, yi, img;
+    if (FROM_NCHW) { xi = (int)(i % iw); int64_t t = i / iw; yi = (int)(t % ih); img = (int)(t / ih); }
+    else { ch0 = (int)(i % cg) * V; int64_t t = i / cg; xi = (int)(t % iw); t /= iw; yi = (int)(t % ih); img = (int)(t / ih); }
+    int ylo, yhi, xlo, xhi;
+    out_range(yi, ih, oh, sh, align, &ylo, &yhi);
+    out_range(xi, iw, ow, sw, align, &xlo, &xhi);
+    bool hit;
+    // trim the candidate ranges to the outputs that really touch this input (membership by the exact coefficients)
+    while (ylo <= yhi) { tab_weight(ytab[ylo], yi, &hit); if (hit) break; ++ylo; }
+    while (yhi >= ylo) { tab_weight(ytab[yhi], yi, &hit); if (hit) break; --yhi; }
+    while (xlo <= xhi) { tab_weight(xtab[xlo], xi, &hit); if (hit) break; ++xlo; }
+    while (xhi >= xlo) { tab_weight(xtab[xhi], xi, &hit); if (hit) break; --xhi; }
+    float* d = dx + (((int64_t)img * ih + yi) * iw + xi) * ldx + ch0;
+    const int ny = yhi - ylo + 1, nx = xhi - xlo + 1;
+    // The outputs touching one input form a contiguous run (the source index is monotone), so after trimming every
+    // candidate is a hit; runs of <= 8 (any up-sampling factor <= 4) keep their weights in registers.
+    const bool small = ny <= 8 && nx <= 8;
+    float wyr[8], wxr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wyr[j] = (small && j < ny) ? tab_weight(ytab[ylo + j], yi, &hit) : 0.f;
+      wxr[j] = (small && j < nx) ? tab_weight(xtab[xlo + j], xi, &hit) : 0.f;
+    }
+    if (FROM_NCHW) {
+      for (int ch = 0; ch < c; ++ch) {
+        const float* plane = dy + ((int64_t)img * c + ch) * ohw;
+        float acc = 0.f;
+        if (small) {
+#pragma unroll
+          for (int jy = 0; jy < 8; ++jy) {
+            if (jy < ny) {
+              const float* rowp = plane + (int64_t)(ylo + jy) * ow + xlo;
+              float rowacc = 0.f;
+#pragma unroll
+              for (int jx = 0; jx < 8; ++jx)
+                if (jx < nx) rowacc += wxr[jx] * __ldg(rowp + jx);
+              acc += wyr[jy] * rowacc;
+            }
+          }
+        } else {
+          for (int yo = ylo; yo <= yhi; ++yo) {
+            const float wy = tab_weight(ytab[yo], yi, &hit);
+            if (!hit) continue;
+            float rowacc = 0.f;
+            for (int xo = xlo; xo <= xhi; ++xo) {
+              const float wx = tab_weight(xtab[xo], xi, &hit);
+              if (!hit) continue;
+              rowacc += wx * __ldg(plane + (int64_t)yo * ow + xo);
+            }
+            acc += wy * rowacc;
+          }
+        }
+        d[ch] = accumulate ? d[ch] + acc * gs : acc * gs;
+      }
+    } else {
+      float acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = 0.f;
+      if (small) {
+#pragma unroll
+        for (int jy = 0; jy < 8; ++jy) {
+          if (jy < ny) {
+            const float* rowp = dy + (((int64_t)img * oh + ylo + jy) * ow + xlo) * ldy + ch0;
+            float rowacc[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) rowacc[e] = 0.f;
+#pragma unroll
+            for (int jx = 0; jx < 8; ++jx) {
+              if (jx < nx) {
+                if (V == 4) {
+                  const float4 g = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)jx * ldy));
+                  rowacc[0] += wxr[jx] * g.x; rowacc[1] += wxr[jx] * g.y; rowacc[2] += wxr[jx] * g.z; rowacc[3] += wxr[jx] * g.w;
+                } else {
+                  rowacc[0] += wxr[jx] * __ldg(rowp + (int64_t)jx * ldy);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += wyr[jy] * rowacc[e];
+          }
+        }
+      } else {
+        for (int yo = ylo; yo <= yhi; ++yo) {
+          const float wy = tab_weight(ytab[yo], yi, &hit);
+          if (!hit) continue;
+          float rowacc[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) rowacc[e] = 0.f;
+          for (int xo = xlo; xo <= xhi; ++xo) {
+            const float wx = tab_weight(xtab[xo], xi, &hit);
+            if (!hit) continue;
+            const float* src = dy + (((int64_t)img * oh + yo) * ow + xo) * ldy + ch0;
+            if (V == 4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(src));
+              rowacc[0] += wx * g.x; rowacc[1] += wx * g.y; rowacc[2] += wx * g.z; rowacc[3] += wx * g.w;
+            } else {
+              rowacc[0] += wx * __ldg(src);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] += wy * rowacc[e];
+        }
+      }
+      if (V == 4) {
+        float4 o = make_float4(acc[0] * gs, acc[1] * gs, acc[2] * gs, acc[3] * gs);
+        if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(d); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *reinterpret_cast<float4*>(d) = o;
+      } else {
+        *d = accumulate ? *d + acc[0] * gs : acc[0] * gs;
+      }
+    }
+  }
+}
+
+// Direct form (no tables): any output size.
 template <bool FROM_NCHW>
 __global__ void bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int ih, int iw, int c, int ldx,
                                     int oh, int ow, int ldy, int align, const float* __restrict__ scale_dev, float scale_host,
@@ -267,12 +498,29 @@ extern "C" int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw
                                int align_corners, int from_nchw, const float* scale_dev, float scale_host, int accumulate,
                                void* stream) {
   B2_REQUIRE(dy && dx && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_bwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (oh + ow <= BIL_MAX_TAB) {
+    const size_t smem = (size_t)(oh + ow) * sizeof(LinTab);
+    if (from_nchw) {
+      const int64_t total = (int64_t)n * ih * iw;
+      int64_t blocks = ceil_div64(total, 128); if (blocks > 148 * 16) blocks = 148 * 16;
+      bilinear_bwd_tab_kernel<true, 1><<<(unsigned)blocks, 128, smem, s>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+    } else {
+      const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(dy) && al16(dx);
+      const int64_t total = (int64_t)n * ih * iw * (vec ? c / 4 : c);
+      int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 16) blocks = 148 * 16;
+      if (vec) bilinear_bwd_tab_kernel<false, 4><<<(unsigned)blocks, 256, smem, s>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+      else bilinear_bwd_tab_kernel<false, 1><<<(unsigned)blocks, 256, smem, s>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+    }
+    B2_LAUNCH_CHECK("bilinear_bwd_tab_kernel");
+    return B2_OK;
+  }
   const int64_t total = (int64_t)n * ih * iw * c;
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
   if (from_nchw)
-    bilinear_bwd_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+    bilinear_bwd_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
   else
-    bilinear_bwd_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
+    bilinear_bwd_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(dy, dx, n, ih, iw, c, ldx, oh, ow, ldy, align_corners, scale_dev, scale_host, accumulate);
   B2_LAUNCH_CHECK("bilinear_bwd_kernel");
   return B2_OK;
 }
@@ -401,13 +649,31 @@ static int launch_col_reduce(const RedArgs& r0, double* ws, cudaStream_t s) {
   return B2_OK;
 }
 
-// final[c][k] = sum over chunks (fixed order); thread per channel.
-__global__ void col_finalize_kernel(const double* __restrict__ partial, int64_t chunks, int c, double* __restrict__ fin) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// final[c][k] = sum over chunks, fixed order: block = 32 channels x 8 chunk lanes (lane j sums chunks j, j+8, ...; the
+// 8 lane sums are then added in ascending order) -- deterministic, and 8x less serial latency than a thread per channel.
+__global__ void __launch_bounds__(256) col_finalize_kernel(const double* __restrict__ partial, int64_t chunks, int c,
+                                                           double* __restrict__ fin) {
+  __shared__ double sm[8][32][2];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
   double t0 = 0, t1 = 0;
-  for (int64_t k = 0; k < chunks; ++k) { t0 += partial[(k * c + ch) * 2]; t1 += partial[(k * c + ch) * 2 + 1]; }
-  fin[ch * 2] = t0; fin[ch * 2 + 1] = t1;
+  if (ch < c) {
+    for (int64_t k = ry; k < chunks; k += 8) {
+      const double2 v = *reinterpret_cast<const double2*>(partial + (k * c + ch) * 2);
+      t0 += v.x; t1 += v.y;
+    }
+  }
+  sm[ry][cx][0] = t0; sm[ry][cx][1] = t1;
+  __syncthreads();
+  if (ry == 0 && ch < c) {
+    double a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0 += sm[k][cx][0]; a1 += sm[k][cx][1]; }
+    fin[ch * 2] = a0; fin[ch * 2 + 1] = a1;
+  }
+}
+static inline void launch_col_finalize(const double* partial, int64_t chunks, int c, double* fin, cudaStream_t s) {
+  col_finalize_kernel<<<(c + 31) / 32, 256, 0, s>>>(partial, chunks, c, fin);
 }
 
 __global__ void colsum_out_kernel(const double* __restrict__ fin, int c, float* __restrict__ out, int accumulate) {
@@ -420,7 +686,7 @@ extern "C" int b2_colsum(const float* dy, int ld, int64_t rows, int c, float* ou
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<0>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows) * c * 2;
-  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
   colsum_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, out, accumulate);
   B2_LAUNCH_CHECK("colsum");
   return B2_OK;
@@ -449,52 +715,105 @@ extern "C" int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float e
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<1>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows) * c * 2;
-  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
   bn_stats_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, rows, eps, momentum, mean, rstd, running_mean, running_var);
   B2_LAUNCH_CHECK("bn_stats");
   return B2_OK;
 }
 
-__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t rows, int c, int ldx, const float* __restrict__ mean,
-                                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int relu, const float* __restrict__ drop, float drop_scale, float* __restrict__ y, int ldy,
-                                const float* __restrict__ res, int ldr) {
-  const int64_t total = rows * c;
+template <int V>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, int64_t rows, int c, int ldx,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                                       const float* __restrict__ drop, float drop_scale, float* __restrict__ y, int ldy,
+                                                       const float* __restrict__ res, int ldr) {
+  const int cg = c / V;
+  const int64_t total = rows * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); const int64_t row = i / c;
-    float v = (x[row * ldx + ch] - mean[ch]) * rstd[ch] * gamma[ch] + beta[ch];
-    if (res) v += res[row * ldr + ch];
-    if (relu) v = fmaxf(v, 0.f);
-    if (drop) v *= drop[row * c + ch] * drop_scale;
-    y[row * ldy + ch] = v;
+    const int ch = (int)(i % cg) * V; const int64_t row = i / cg;
+    float v[V], m[V], r[V], g[V], b[V];
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      const float4 qm = __ldg(reinterpret_cast<const float4*>(mean + ch)); m[0] = qm.x; m[1] = qm.y; m[2] = qm.z; m[3] = qm.w;
+      const float4 qr = __ldg(reinterpret_cast<const float4*>(rstd + ch)); r[0] = qr.x; r[1] = qr.y; r[2] = qr.z; r[3] = qr.w;
+      const float4 qg = __ldg(reinterpret_cast<const float4*>(gamma + ch)); g[0] = qg.x; g[1] = qg.y; g[2] = qg.z; g[3] = qg.w;
+      const float4 qb = __ldg(reinterpret_cast<const float4*>(beta + ch)); b[0] = qb.x; b[1] = qb.y; b[2] = qb.z; b[3] = qb.w;
+    } else {
+      v[0] = x[row * ldx + ch]; m[0] = mean[ch]; r[0] = rstd[ch]; g[0] = gamma[ch]; b[0] = beta[ch];
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = (v[e] - m[e]) * r[e] * g[e] + b[e];
+    if (res) {
+      if (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(res + row * ldr + ch)); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
+      else v[0] += res[row * ldr + ch];
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    if (drop) {
+      if (V == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(drop + row * c + ch));
+        v[0] *= q.x * drop_scale; v[1] *= q.y * drop_scale; v[2] *= q.z * drop_scale; v[3] *= q.w * drop_scale;
+      } else v[0] *= drop[row * c + ch] * drop_scale;
+    }
+    if (V == 4) *reinterpret_cast<float4*>(y + row * ldy + ch) = make_float4(v[0], v[1], v[2], v[3]);
+    else y[row * ldy + ch] = v[0];
   }
 }
 extern "C" int b2_bn_apply(const float* x, int64_t rows, int c, int ldx, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, int relu, const float* dropmask, float drop_scale, float* y, int ldy,
                            const float* residual, int ldr, void* stream) {
   B2_REQUIRE(x && y && mean && rstd && gamma && beta && rows > 0 && c > 0, "b2_bn_apply: bad args");
-  const int64_t total = rows * c;
+  const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && al16(y) && al16(mean) && al16(rstd) && al16(gamma) &&
+                   al16(beta) && (!residual || (ldr % 4 == 0 && al16(residual))) && (!dropmask || al16(dropmask));
+  const int64_t total = rows * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy, residual, ldr);
+  if (vec) bn_apply_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy, residual, ldr);
+  else bn_apply_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, c, ldx, mean, rstd, gamma, beta, relu, dropmask, drop_scale, y, ldy, residual, ldr);
   B2_LAUNCH_CHECK("bn_apply_kernel");
   return B2_OK;
 }
 
-__global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, const float* __restrict__ y,
-                                 int ldy, int64_t rows, int c, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                 const float* __restrict__ gamma, int relu, const float* __restrict__ drop, float drop_scale,
-                                 const double* __restrict__ fin, float* __restrict__ dx, int lddx, float* __restrict__ g_out, int ldgo) {
-  const int64_t total = rows * c;
+template <int V>
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                        const float* __restrict__ y, int ldy, int64_t rows, int c,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, int relu, const float* __restrict__ drop,
+                                                        float drop_scale, const double* __restrict__ fin, float* __restrict__ dx, int lddx,
+                                                        float* __restrict__ g_out, int ldgo) {
+  const int cg = c / V;
+  const int64_t total = rows * cg;
   const double inv_n = 1.0 / (double)rows;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); const int64_t row = i / c;
-    float g = dy[row * lddy + ch];
-    if (relu && !(y[row * ldy + ch] > 0.f)) g = 0.f;
-    if (drop) g *= drop[row * c + ch] * drop_scale;
-    if (g_out) g_out[row * ldgo + ch] = g;
-    const float xhat = (x[row * ldx + ch] - mean[ch]) * rstd[ch];
-    const float mdb = (float)(fin[ch * 2] * inv_n), mdg = (float)(fin[ch * 2 + 1] * inv_n);
-    dx[row * lddx + ch] = gamma[ch] * rstd[ch] * (g - mdb - xhat * mdg);
+    const int ch = (int)(i % cg) * V; const int64_t row = i / cg;
+    float g[V], xv[V], yv[V], dv[V];
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + ch)); g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
+      const float4 qx = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch)); xv[0] = qx.x; xv[1] = qx.y; xv[2] = qx.z; xv[3] = qx.w;
+      if (relu) { const float4 qy = __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)); yv[0] = qy.x; yv[1] = qy.y; yv[2] = qy.z; yv[3] = qy.w; }
+      if (drop) { const float4 qd = __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)); dv[0] = qd.x; dv[1] = qd.y; dv[2] = qd.z; dv[3] = qd.w; }
+    } else {
+      g[0] = dy[row * lddy + ch]; xv[0] = x[row * ldx + ch];
+      if (relu) yv[0] = y[row * ldy + ch];
+      if (drop) dv[0] = drop[row * c + ch];
+    }
+    float o[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (relu && !(yv[e] > 0.f)) g[e] = 0.f;
+      if (drop) g[e] *= dv[e] * drop_scale;
+      const float xhat = (xv[e] - mean[ch + e]) * rstd[ch + e];
+      const float mdb = (float)(fin[(ch + e) * 2] * inv_n), mdg = (float)(fin[(ch + e) * 2 + 1] * inv_n);
+      o[e] = gamma[ch + e] * rstd[ch + e] * (g[e] - mdb - xhat * mdg);
+    }
+    if (V == 4) {
+      if (g_out) *reinterpret_cast<float4*>(g_out + row * ldgo + ch) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(dx + row * lddx + ch) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      if (g_out) g_out[row * ldgo + ch] = g[0];
+      dx[row * lddx + ch] = o[0];
+    }
   }
 }
 __global__ void bn_param_out_kernel(const double* __restrict__ fin, int c, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
@@ -515,10 +834,13 @@ extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, con
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<2>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows) * c * 2;
-  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
-  const int64_t total = rows * c;
+  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  const bool vec = c % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && al16(dy) && al16(x) && al16(dx) &&
+                   (!relu || (ldy % 4 == 0 && al16(y))) && (!dropmask || al16(dropmask)) && (!g_out || (ldgo % 4 == 0 && al16(g_out)));
+  const int64_t total = rows * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  bn_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
+  if (vec) bn_bwd_dx_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
+  else bn_bwd_dx_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
   bn_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, dgamma, dbeta, accumulate_params);
   B2_LAUNCH_CHECK("bn_bwd");
   return B2_OK;
@@ -562,7 +884,7 @@ extern "C" int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<3>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows) * c * 2;
-  col_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(workspace, red_chunks(rows), c, fin);
+  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
   bn_eval_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, gamma, beta, dgamma, dbeta, accumulate);
   B2_LAUNCH_CHECK("bn_eval_param_grad");
   return B2_OK;
@@ -624,6 +946,82 @@ extern "C" int b2_bn_eval_param_grad_from_stats(const float* stats, int64_t stat
   return B2_OK;
 }
 
+// Frozen-BN parameter gradients from the WEIGHT gradient (no pass over activations at all):
+//   y = scale*conv(x, W) + shift, scale = gamma*invstd  =>  dgamma = invstd * (sum_pix g*conv - mean * sum_pix g)
+//   and  sum_pix g[pix,c]*conv[pix,c] = <W[c,:], dWraw[c,:]>  with dWraw the un-scaled weight gradient.  The wgrad
+//   epilogue stores gw = scale*dWraw, hence  dgamma = <W[c], gw[c]>/gamma - invstd*mean*dbeta,  dbeta = sum_pix g.
+// Because gw accumulates over backward passes, dgamma is SET from the accumulated totals (gw, dbeta); this is the
+// accumulated value as long as W.grad, gamma.grad and beta.grad were zeroed together (they always are: zero_grad).
+// ws[k][c][2] (double): n_splits partial column sums of g (entry 0 used).  One block per channel.
+__global__ void __launch_bounds__(128) bn_wdot_out_kernel(const double* __restrict__ ws, int n_splits, int c,
+                                                          const float* __restrict__ w, const float* __restrict__ gw,
+                                                          int64_t row_len, const float* __restrict__ gamma,
+                                                          const float* __restrict__ mean, const float* __restrict__ var,
+                                                          float eps, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                          int accumulate, int vec) {
+  __shared__ double sm[4];
+  const int ch = blockIdx.x;
+  const float* wr = w + (int64_t)ch * row_len;
+  const float* gr = gw + (int64_t)ch * row_len;
+  double acc = 0.0;
+  if (vec) {
+    const int64_t n4 = row_len >> 2;
+    for (int64_t i = threadIdx.x; i < n4; i += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wr) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(gr) + i);
+      acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < row_len; i += 128) acc += (double)__ldg(wr + i) * (double)__ldg(gr + i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double dot = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+    double sg = 0.0;
+    for (int k = 0; k < n_splits; ++k) sg += ws[((int64_t)k * c + ch) * 2];
+    const float db = (accumulate ? dbeta[ch] : 0.f) + (float)sg;
+    dbeta[ch] = db;
+    const double ga = gamma[ch];
+    const double invstd = 1.0 / sqrt((double)var[ch] + (double)eps);
+    dgamma[ch] = (float)((ga != 0.0 ? dot / ga : 0.0) - invstd * (double)mean[ch] * (double)db);
+  }
+}
+static int launch_wdot(const double* ws, int n_splits, int c, const float* w, const float* gw, int64_t row_len,
+                       const float* gamma, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
+                       int accumulate, cudaStream_t s) {
+  const int vec = (row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gw) & 15) == 0);
+  bn_wdot_out_kernel<<<c, 128, 0, s>>>(ws, n_splits, c, w, gw, row_len, gamma, mean, var, eps, dgamma, dbeta, accumulate, vec);
+  B2_LAUNCH_CHECK("bn_wdot_out_kernel");
+  return B2_OK;
+}
+extern "C" int b2_bn_eval_param_grad_wdot_from_stats(const float* stats, int64_t stat_rows, int ld_stats, int c, const float* w,
+                                                     const float* gw, int64_t row_len, const float* gamma, const float* mean,
+                                                     const float* var, float eps, float* dgamma, float* dbeta, int accumulate,
+                                                     double* workspace, void* stream) {
+  B2_REQUIRE(stats && w && gw && gamma && mean && var && dgamma && dbeta && workspace && stat_rows > 0 && c > 0 &&
+             ld_stats >= c && row_len > 0, "b2_bn_eval_param_grad_wdot_from_stats: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_stats_partial_kernel<<<dim3((c + 31) / 32, STAT_SPLITS), 256, 0, s>>>(stats, stat_rows, ld_stats, c, workspace);
+  B2_LAUNCH_CHECK("bn_stats_partial_kernel");
+  return launch_wdot(workspace, STAT_SPLITS, c, w, gw, row_len, gamma, mean, var, eps, dgamma, dbeta, accumulate, s);
+}
+extern "C" int b2_bn_eval_param_grad_wdot(const float* dy, int lddy, int64_t rows, int c, const float* w, const float* gw,
+                                          int64_t row_len, const float* gamma, const float* mean, const float* var, float eps,
+                                          float* dgamma, float* dbeta, int accumulate, double* workspace, void* stream) {
+  B2_REQUIRE(dy && w && gw && gamma && mean && var && dgamma && dbeta && workspace && rows > 0 && c > 0 && lddy >= c &&
+             row_len > 0, "b2_bn_eval_param_grad_wdot: bad args");
+  RedArgs r{}; r.a = dy; r.lda = lddy; r.rows = rows; r.c = c;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_col_reduce<0>(r, workspace, s); if (rc) return rc;
+  double* fin = workspace + red_chunks(rows) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  B2_LAUNCH_CHECK("col_finalize_kernel");
+  return launch_wdot(fin, 1, c, w, gw, row_len, gamma, mean, var, eps, dgamma, dbeta, accumulate, s);
+}
+
 // ------------------------------------------------------------------------------------------ GAP / broadcast
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c, int ldx, float mul) {
   __shared__ float sm[8][32];
@@ -646,27 +1044,42 @@ extern "C" int b2_gap_fwd(const float* x, float* y, int n, int hw, int c, int ld
   B2_LAUNCH_CHECK("gap_fwd_kernel");
   return B2_OK;
 }
-__global__ void bcast_kernel(const float* __restrict__ v, float* __restrict__ y, int hw, int c, int ldy, float mul, int accumulate) {
+template <int V>
+__global__ void __launch_bounds__(256) bcast_kernel(const float* __restrict__ v, float* __restrict__ y, int hw, int c, int ldy, float mul,
+                                                    int accumulate) {
   const int n = blockIdx.y;
-  const int64_t total = (int64_t)hw * c;
+  const int cg = c / V;
+  const int64_t total = (int64_t)hw * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c); const int64_t p = i / c;
+    const int ch = (int)(i % cg) * V; const int64_t p = i / cg;
     float* d = y + ((int64_t)n * hw + p) * ldy + ch;
-    const float val = v[(int64_t)n * c + ch] * mul;
-    *d = accumulate ? *d + val : val;
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(v + (int64_t)n * c + ch));
+      float4 o = make_float4(q.x * mul, q.y * mul, q.z * mul, q.w * mul);
+      if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(d); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+      *reinterpret_cast<float4*>(d) = o;
+    } else {
+      const float val = v[(int64_t)n * c + ch] * mul;
+      *d = accumulate ? *d + val : val;
+    }
   }
+}
+static int launch_bcast(const float* v, float* y, int n, int hw, int c, int ldy, float mul, int accumulate, cudaStream_t s) {
+  const bool vec = c % 4 == 0 && ldy % 4 == 0 && al16(v) && al16(y);
+  int bx = (int)(((int64_t)hw * (vec ? c / 4 : c) + 255) / 256); if (bx > 2048) bx = 2048;
+  if (vec) bcast_kernel<4><<<dim3(bx, n), 256, 0, s>>>(v, y, hw, c, ldy, mul, accumulate);
+  else bcast_kernel<1><<<dim3(bx, n), 256, 0, s>>>(v, y, hw, c, ldy, mul, accumulate);
+  return B2_OK;
 }
 extern "C" int b2_gap_bwd(const float* dy, float* dx, int n, int hw, int c, int ldx, int accumulate, void* stream) {
   B2_REQUIRE(dy && dx && n > 0 && hw > 0 && c > 0, "b2_gap_bwd: bad args");
-  int bx = (int)(((int64_t)hw * c + 255) / 256); if (bx > 2048) bx = 2048;
-  bcast_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(dy, dx, hw, c, ldx, 1.0f / (float)hw, accumulate);
+  launch_bcast(dy, dx, n, hw, c, ldx, 1.0f / (float)hw, accumulate, (cudaStream_t)stream);
   B2_LAUNCH_CHECK("gap_bwd");
   return B2_OK;
 }
 extern "C" int b2_bcast_fwd(const float* v, float* y, int n, int hw, int c, int ldy, void* stream) {
   B2_REQUIRE(v && y && n > 0 && hw > 0 && c > 0, "b2_bcast_fwd: bad args");
-  int bx = (int)(((int64_t)hw * c + 255) / 256); if (bx > 2048) bx = 2048;
-  bcast_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(v, y, hw, c, ldy, 1.0f, 0);
+  launch_bcast(v, y, n, hw, c, ldy, 1.0f, 0, (cudaStream_t)stream);
   B2_LAUNCH_CHECK("bcast_fwd");
   return B2_OK;
 }

@@ -15,9 +15,29 @@ Gradient bookkeeping
   * The same epilogue that finishes the gradient of a frozen-BN layer's output also writes the column sums the
     BN affine parameters need (sum g, sum g*(y - residual)); the separate reduction pass over g and y is skipped.
 """
+import weakref
+
 import torch
 
 from .acts import Act
+
+# ---------------------------------------------------------------------------------------- derived-weight caches
+# Folded frozen-BN constants and transposed (dgrad) weights depend only on the parameters, so the two student passes
+# and the two teacher passes of one iteration share them.  An entry is valid while (generation, tensor versions)
+# are unchanged: torch bumps `_version` on every in-place update (optimiser step, load_state_dict), and code that
+# writes parameters through raw pointers (the fused EMA kernel) or wants a fresh start (every training step, so that
+# a CUDA-graph capture always contains the producing kernels) calls `invalidate_caches()`.
+_GENERATION = [0]
+_FOLD_CACHE = weakref.WeakKeyDictionary()
+_WT_CACHE = weakref.WeakKeyDictionary()
+
+
+def invalidate_caches():
+    _GENERATION[0] += 1
+
+
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors)
 
 
 class Tape(object):
@@ -56,6 +76,9 @@ class Tape(object):
         node = t.node
         if not isinstance(node, ConvNode) or node.bn is None or not node.bn.weight.requires_grad:
             return None
+        if node.conv.weight.requires_grad:
+            # dgamma comes from <W, dW> (ConvNode.backward): only sum_pix g is wanted, no pass over y / the residual
+            return False if self.K.stats_ok(t) else None
         if not self.K.stats_ok(t) or (node.residual is not None and not self.K.stats_ok(node.residual)):
             return None
         return node.residual if node.residual is not None else False
@@ -192,20 +215,25 @@ class ConvNode(object):
         if self.residual is not None:
             tape.contribute_tensor(self.residual, g)
         bn = self.bn
-        if bn is not None and bn.weight.requires_grad:
+        w = self.conv.weight
+        bn_grads = bn is not None and bn.weight.requires_grad
+        st = None
+        if bn_grads:
+            st = getattr(self.y, 'fused_stats', None) if self.y.parent is None else None
+            self.y.fused_stats = None
+        if bn_grads and not w.requires_grad:
+            # frozen convolution weights: recover xhat from the stored BN output
             dgam, acc = param_grad(bn.weight)
             dbet, acc2 = param_grad(bn.bias)
             assert acc == acc2
-            st = getattr(self.y, 'fused_stats', None) if self.y.parent is None else None
             if st is not None:
                 K.bn_eval_param_grad_from_stats(st, bn.weight, bn.bias, dgam, dbet, acc)    # sums came with g
-                self.y.fused_stats = None
             else:
                 K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, self.residual, dgam, dbet, acc)
+            bn_grads = False
         if self.conv.bias is not None and self.conv.bias.requires_grad:
             db, acc = param_grad(self.conv.bias)
             K.colsum(g, db, acc)
-        w = self.conv.weight
         if self.col_src is not None:
             # stem: GEMM over the (recomputed) im2col matrix; weight gradient only
             if w.requires_grad:
@@ -215,19 +243,34 @@ class ConvNode(object):
                 K.conv_wgrad(gflat, col, dw_pad, cout, 1, 1, kpad, 1, 0, 1, row_scale=self.scale, accumulate=False)
                 dw, acc = param_grad(w)
                 K.copy_rows(dw, kh * kw * cin, dw_pad, kpad, cout, kh * kw * cin, acc)
+                if bn_grads:
+                    self._bn_grads_from_wgrad(K, st, g, w, dw, bn)
             return
         if w.requires_grad:
             dw, acc = param_grad(w)
             K.conv_wgrad(g, self.x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=self.scale, accumulate=acc)
+            if bn_grads:
+                self._bn_grads_from_wgrad(K, st, g, w, dw, bn)
         if not self.x.needs_grad:
             return                                   # network input: no gradient needed
-        wt, ldb = K.transpose_w(w, cout, kh * kw, cin, scale=self.scale)
+        wt, ldb = transposed_weights(K, self.conv, cout, kh * kw, cin, self.scale)
 
         def launch(dst, accumulate, addend, gate, stats_sub):
             return K.conv_dgrad(g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dst, addend=addend, gate=gate,
                                 accumulate=accumulate, want_stats=stats_sub is not None,
                                 stats_sub=stats_sub if stats_sub else None)
         tape.contribute_kernel(self.x, launch, fusable=(stride == 1))
+
+
+    @staticmethod
+    def _bn_grads_from_wgrad(K, st, g, w, dw, bn):
+        """Frozen BN with trainable affine: dbeta += sum_pix g, dgamma = <W, dW>/gamma - invstd*mean*dbeta, where dW
+        (already scaled by gamma*invstd and accumulated over passes by the wgrad epilogue) replaces every pass over
+        the activations (see b2_bn_eval_param_grad_wdot in include/b200seg.h)."""
+        dgam, acc = param_grad(bn.weight)
+        dbet, acc2 = param_grad(bn.bias)
+        assert acc == acc2
+        K.bn_eval_param_grad_wdot(st, g, w, dw, bn, dgam, dbet, acc)
 
 
 class BNTrainNode(object):
@@ -331,11 +374,27 @@ def _geom(conv):
 
 def fold_bn(tape, bn):
     """scale/shift of an eval-mode BatchNorm (running statistics)."""
-    dev = bn.weight.device
+    key = (_GENERATION[0], tape.K.name, _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    hit = _FOLD_CACHE.get(bn)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
     scale = torch.empty_like(bn.running_mean)
     shift = torch.empty_like(bn.running_mean)
     tape.K.bn_fold(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
+    _FOLD_CACHE[bn] = (key, scale, shift)
     return scale, shift
+
+
+def transposed_weights(K, conv, cout, taps, cin, scale):
+    """(cin, taps, pad4(cout)) dgrad operand with the folded BN scale, shared by the backward passes of one iteration."""
+    w = conv.weight
+    key = (_GENERATION[0], K.name, getattr(K, 'n_split', 1), _versions(w), None if scale is None else _versions(scale))
+    hit = _WT_CACHE.get(conv)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    wt, ldb = K.transpose_w(w, cout, taps, cin, scale=scale)
+    _WT_CACHE[conv] = (key, wt, ldb, scale)        # holds `scale` so its data_ptr cannot be recycled while cached
+    return wt, ldb
 
 
 def conv_bn_act(tape, x, conv, bn=None, residual=None, relu=False, out=None, dropout=None, ld_out=None):

@@ -227,6 +227,12 @@ class ActKernels(object):
     def bn_eval_param_grad_from_stats(self, stats, gamma, beta, dgamma, dbeta, accumulate):
         self.be.bn_eval_param_grad_from_stats(stats, gamma, beta, dgamma, dbeta, accumulate)
 
+    def bn_eval_param_grad_wdot(self, stats, g, w, gw, bn, dgamma, dbeta, accumulate):
+        """dbeta (+)= sum_pix g; dgamma = <W, gw>/gamma - invstd*mean*dbeta (set from the accumulated totals).
+        stats: what conv_dgrad(want_stats=True) returned for g, or None."""
+        self.be.bn_eval_param_grad_wdot(stats, g.ptr, g.ld, g.rows, w, gw, bn.weight, bn.running_mean, bn.running_var,
+                                        bn.eps, dgamma, dbeta, accumulate)
+
     def stats_ok(self, t):
         """Can a dgrad epilogue produce the column statistics of activation t's gradient?  (vector-path layout)"""
         return t.c % 4 == 0 and t.ld % 4 == 0 and t.off % 4 == 0

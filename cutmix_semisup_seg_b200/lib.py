@@ -108,6 +108,10 @@ _SIGS = {
                                       c_vp, c_vp, c_int, c_vp, c_vp]),
     'b2_bn_eval_param_grad_from_stats': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     'b2_bn_stats_workspace_doubles': (c_i64, [c_int]),
+    'b2_bn_eval_param_grad_wdot_from_stats': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32,
+                                                      c_vp, c_vp, c_int, c_vp, c_vp]),
+    'b2_bn_eval_param_grad_wdot': (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32,
+                                           c_vp, c_vp, c_int, c_vp, c_vp]),
     'b2_dropout_mask': (c_int, [c_vp, c_i64, c_f32, c_u64, c_u64, c_vp, c_vp]),
     'b2_add_inplace': (c_int, [c_vp, c_vp, c_i64, c_vp]),
     'b2_fill': (c_int, [c_vp, c_f32, c_i64, c_vp]),

@@ -310,6 +310,27 @@ class CudaBackend(object):
                    dgamma.data_ptr(), dbeta.data_ptr(), int(bool(accumulate)), self._rws.data_ptr(), self._s())
         self.launches += 1
 
+    def bn_eval_param_grad_wdot(self, stats, dy_ptr, lddy, rows, w, gw, gamma, mean, var, eps, dgamma, dbeta, accumulate):
+        """Frozen-BN dgamma / dbeta from <W, dW> (b2_bn_eval_param_grad_wdot*).  stats: fused epilogue partial sums
+        (buffer, row blocks, ld) or None -> sum_pix g is reduced from dy."""
+        c = gamma.numel()
+        row_len = w.numel() // c
+        if stats is not None:
+            buf, srows, ld = stats
+            need = int(L.call('b2_bn_stats_workspace_doubles', c))
+            if getattr(self, '_rws', None) is None or self._rws.numel() < need or self._rws.device != gamma.device:
+                self._rws = torch.empty((need,), device=gamma.device, dtype=torch.float64)
+            self._call('b2_bn_eval_param_grad_wdot_from_stats', buf.data_ptr(), srows, ld, c, w.data_ptr(), gw.data_ptr(),
+                       row_len, gamma.data_ptr(), mean.data_ptr(), var.data_ptr(), float(eps), dgamma.data_ptr(),
+                       dbeta.data_ptr(), int(bool(accumulate)), self._rws.data_ptr(), self._s())
+            self.launches += 1
+        else:
+            ws = self._red_ws(rows, c, gamma.device)
+            self._call('b2_bn_eval_param_grad_wdot', dy_ptr, lddy, rows, c, w.data_ptr(), gw.data_ptr(), row_len,
+                       gamma.data_ptr(), mean.data_ptr(), var.data_ptr(), float(eps), dgamma.data_ptr(), dbeta.data_ptr(),
+                       int(bool(accumulate)), ws.data_ptr(), self._s())
+            self.launches += 2
+
     def colsum(self, dy_ptr, ld, rows, c, out, accumulate):
         ws = self._red_ws(rows, c, out.device)
         self._call('b2_colsum', dy_ptr, ld, rows, c, out.data_ptr(), int(bool(accumulate)), ws.data_ptr(), self._s())

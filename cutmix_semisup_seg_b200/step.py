@@ -254,6 +254,8 @@ class MeanTeacherStep(object):
                     done.add(id(d[k]))
 
     def _fwd_bwd(self, sup_batch, unsup_batches, ramp_val):
+        from . import engine
+        engine.invalidate_caches()       # derived weights (BN folds, dgrad transposes) are rebuilt once per iteration
         self._zero_grad()                                              # :290
         sup_loss = self.supervised(*sup_batch)
         cons, conf = None, None

@@ -251,6 +251,23 @@ int b2_bn_eval_param_grad_from_stats(const float* stats, int64_t stat_rows, int 
                                      const float* beta, float* dgamma, float* dbeta, int accumulate,
                                      double* workspace, void* stream);   /* >= b2_bn_stats_workspace_doubles(c) */
 int64_t b2_bn_stats_workspace_doubles(int c);
+/* Frozen-BN parameter gradients from the WEIGHT gradient of the convolution feeding the BN (no pass over the
+ * activations): with y = scale*conv(x, W) + shift and gw = scale*dWraw (what b2_conv_wgrad stores with
+ * row_scale = scale = gamma*rsqrt(var+eps)),  sum_pix g*conv = <W[c,:], dWraw[c,:]>  gives
+ *   dbeta[c] = (accumulate ? dbeta[c] : 0) + sum_pix g[pix,c];   dgamma[c] = <W[c], gw[c]>/gamma - rsqrt(var+eps)*mean*dbeta[c].
+ * dgamma is SET from the accumulated totals (gw and dbeta accumulate over backward passes), which equals the accumulated
+ * gradient whenever W.grad, gamma.grad and beta.grad were zeroed together.  w, gw: (c, row_len) contiguous rows.
+ * Replaces autograd's native_batch_norm_backward for eval-mode BN with trainable affine (torchvision backbone under
+ * freeze_batchnorm, reference deeplab3plus.py:120-121).  `_from_stats` takes sum_pix g from the partial sums a
+ * b2_conv_gemm epilogue wrote (b2_conv_params.stats, entry j = 0); the other form reduces dy itself.
+ * workspace: >= b2_bn_stats_workspace_doubles(c) / b2_bn_workspace_doubles(rows, c) doubles. */
+int b2_bn_eval_param_grad_wdot_from_stats(const float* stats, int64_t stat_rows, int ld_stats, int c, const float* w,
+                                          const float* gw, int64_t row_len, const float* gamma, const float* mean,
+                                          const float* var, float eps, float* dgamma, float* dbeta, int accumulate,
+                                          double* workspace, void* stream);
+int b2_bn_eval_param_grad_wdot(const float* dy, int lddy, int64_t rows, int c, const float* w, const float* gw,
+                               int64_t row_len, const float* gamma, const float* mean, const float* var, float eps,
+                               float* dgamma, float* dbeta, int accumulate, double* workspace, void* stream);
 /* dropout keep-mask: mask[i] = (hash(seed, offset + *offset_dev + i) >= p) ? 1 : 0; offset_dev (may be NULL) is a
  * device counter so that CUDA-graph replays advance the random stream. */
 int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t seed, uint64_t offset,

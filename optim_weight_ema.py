@@ -77,8 +77,9 @@ class EMAWeightOptimizer(object):
         if dev.type != 'cuda' or any(p.device != dev for p in self.target_params + self.source_params):
             raise RuntimeError('EMAWeightOptimizer (B200 hot path) needs all tensors on one CUDA device; '
                                'there is no CPU fallback')
-        from cutmix_semisup_seg_b200 import ops
+        from cutmix_semisup_seg_b200 import ops, engine
         be = ops.default_backend()
+        engine.invalidate_caches()      # the kernel writes the teacher through raw pointers (no torch version bump)
         with torch.cuda.device(dev):
             flat = self._flat_pair()
             if flat is not None:

@@ -92,6 +92,16 @@ class EmuKernels(object):
             else:
                 tgt.copy_(val.to(torch.float32))
 
+    def bn_eval_param_grad_wdot(self, stats, g, w, gw, bn, dgamma, dbeta, accumulate):
+        self.calls.append('bn_eval_param_grad_wdot' + ('+stats' if stats is not None else ''))
+        sg = stats[0] if stats is not None else _v(g).sum(dim=(0, 2, 3))
+        c = bn.weight.numel()
+        db = (dbeta.to(DT) if accumulate else 0.0) + sg
+        dot = (w.detach().to(DT).reshape(c, -1) * gw.to(DT).reshape(c, -1)).sum(dim=1)
+        invstd = 1.0 / torch.sqrt(bn.running_var.to(DT) + bn.eps)
+        dg = dot / bn.weight.detach().to(DT) - invstd * bn.running_mean.to(DT) * db
+        dbeta.copy_(db.to(torch.float32)); dgamma.copy_(dg.to(torch.float32))
+
     def conv_wgrad(self, g, x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=None, accumulate=False):
         self.calls.append('conv_wgrad')
         xin = _v(x).requires_grad_(False)

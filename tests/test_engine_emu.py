@@ -93,8 +93,10 @@ def test_deeplab3plus_frozen_backbone_train_head(emu):
     assert nb['deeplab.backbone.bn1.num_batches_tracked'] == 0
     # frozen-BN parameter gradients: nearly every backbone layer gets its column sums from the dgrad epilogue that
     # finished its output gradient; only strided / slice / pooled consumers fall back to the separate reduction
-    fused, plain = emu.calls.count('bn_eval_param_grad_from_stats'), emu.calls.count('bn_eval_param_grad')
+    # (dgamma itself comes from <W, dW>: no pass over the activations, ConvNode._bn_grads_from_wgrad)
+    fused, plain = emu.calls.count('bn_eval_param_grad_wdot+stats'), emu.calls.count('bn_eval_param_grad_wdot')
     assert fused == emu.calls.count('conv_dgrad+stats') and fused + plain == 104 and fused >= 90, (fused, plain)
+    assert emu.calls.count('bn_eval_param_grad_from_stats') == 0 and emu.calls.count('bn_eval_param_grad') == 0
 
 
 def test_gradient_accumulation_over_two_backward_passes(emu):
@@ -110,6 +112,27 @@ def test_gradient_accumulation_over_two_backward_passes(emu):
     for k, p in net.named_parameters():
         if p.grad is not None:
             assert torch.allclose(p.grad, 2 * g1[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_frozen_bn_affine_gradients_accumulate_over_two_passes(emu):
+    """dgamma is SET from the accumulated <W, dW> and dbeta totals: two passes must give exactly twice one pass."""
+    torch.manual_seed(0)
+    net = na.seg.get('resnet101_deeplabv3plus_imagenet')(4, pretrained=False)
+    net.load_state_dict(TO.synth_state_dict(net.state_dict(), seed=5))
+    net.train(); net.freeze_batchnorm()
+    for m in net.modules():
+        if hasattr(m, 'p') and hasattr(m, 'next_mask'):
+            m.p = 0.0                                   # deterministic head
+    x = torch.randn(2, 3, 17, 17)
+    dy = torch.randn(2, 4, 17, 17)
+    net(x).backward(dy)
+    keys = [k for k, p in net.named_parameters() if 'backbone' in k and 'bn' in k and p.grad is not None]
+    assert len(keys) >= 200
+    g1 = {k: p.grad.clone() for k, p in net.named_parameters() if k in keys}
+    net(x).backward(dy)
+    sd = dict(net.named_parameters())
+    for k in keys:
+        assert torch.allclose(sd[k].grad, 2 * g1[k], rtol=2e-4, atol=1e-6 * float(g1[k].abs().max()) + 1e-12), k
 
 
 def test_eval_mode_forward_has_no_tape(emu):
