@@ -28,10 +28,30 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// Ampere-style asynchronous 16 B global -> shared copies (LDGSTS): no destination register, so a lane can keep many
+// more bytes in flight than its register budget allows; completion is tracked per thread with commit / wait groups.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Asynchronous operand prefetch (kernels built with the PF layout): the residual addend / ReLU gate values a lane needs
+// for its NEXT chunk are copied into a per-lane shared-memory slot while it works on the current chunk.  Each lane reads
+// back exactly the 16 B pieces it copied itself (entry i of lane l at (i*32 + l)*16), so no cross-lane synchronisation is
+// involved; a piece is re-issued for the next chunk right after its current value has been consumed.  Two commit groups
+// per chunk (row groups 0-3 / 4-7), always `wait_group 1`.  16 pieces x 16 B in flight per lane = 64 KB per SM, against
+// ~16 KB for the register-limited direct loads (profiles/r01_v6_l3_1x1_insitu_flavours*: the HBM-bound 1x1 layers ran at
+// half the bandwidth they need).
+constexpr int PF_OPERAND_BYTES = 8 * 32 * 16;       // 8 row groups x 32 lanes x 16 B
+constexpr int PF_WARP_BYTES = 2 * PF_OPERAND_BYTES; // addend + gate
+
 constexpr int ROW_FLOATS = 36;                      // 32 columns + 4 pad: conflict-free 128-bit smem access
 constexpr int WARP_BYTES = 32 * ROW_FLOATS * 4;
 constexpr int NUM_WARPS = 8;                        // two warps per TMEM lane quarter (even / odd 32-column chunks)
 constexpr int BYTES = NUM_WARPS * WARP_BYTES + NUM_WARPS * 32 * 4;  // staging tiles + per-row pixel indices
+constexpr int PF_BYTES = NUM_WARPS * PF_WARP_BYTES;                // prefetch slots (PF kernels only)
 
 struct Params {
   float* d; int ldd;
@@ -66,6 +86,39 @@ __device__ __forceinline__ void prefetch_row(const Params& p, int pix, int c0, i
   if (p.accumulate) prefetch_lines(p.d + (long long)pix * p.ldd + c0, n);
 }
 
+// Issue the asynchronous copies of row groups [4b, 4b+4) of the chunk whose first column (for this lane) is `c`.
+template <bool ADD, bool GATE>
+__device__ __forceinline__ void pf_issue(const Params& p, const int (&od)[8], int c, bool lane_ok, int b, uint32_t slot, int lane) {
+  if (lane_ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = b * 4 + j;
+      if (od[i] >= 0) {
+        if (ADD) cp_async16(slot + (i * 32 + lane) * 16, p.addend + (long long)od[i] * p.ld_add + c);
+        if (GATE) cp_async16(slot + PF_OPERAND_BYTES + (i * 32 + lane) * 16, p.gate + (long long)od[i] * p.ld_gate + c);
+      }
+    }
+  }
+  cp_async_commit();
+}
+// Tile prologue of a PF kernel: start the copies for this warp's first chunk (called before waiting for the accumulator).
+__device__ __forceinline__ void pf_prologue(const Params& p, int block_n, int n0, const int* rowpix, int lane, int half, uint32_t slot) {
+  if (!(p.addend || p.gate)) return;
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  int od[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
+  const int col0 = n0 + half * 32;
+  if (half >= block_n / 32 || col0 >= p.nb) return;          // this warp has no chunk in the tile
+  const int c = col0 + sub_c;
+  const bool ok = p.vec_ok && c + 3 < p.nb;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    if (p.addend) { if (p.gate) pf_issue<true, true>(p, od, c, ok, b, slot, lane); else pf_issue<true, false>(p, od, c, ok, b, slot, lane); }
+    else pf_issue<false, true>(p, od, c, ok, b, slot, lane);
+  }
+}
+
 // Out-of-line general path for one lane's 4 columns of one row: any channel count / alignment, accumulate.
 static __device__ __noinline__ void slow_store(const Params& p, float4 v, int pix, int c) {
   const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -93,7 +146,9 @@ static __device__ __noinline__ void slow_store(const Params& p, float4 v, int pi
 // `half` (0/1) selects the even or odd chunks: two warps share a lane quarter.
 template <bool ADD, bool GATE, bool STATS, class Release>
 __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                             const int* rowpix, int lane, int half, int stat_row, Release release) {
+                                             const int* rowpix, int lane, int half, int stat_row, uint32_t pf_slot,
+                                             Release release) {
+  const bool pf = (ADD || GATE) && pf_slot != 0;       // operands arrive through the asynchronous prefetch slots
   const int sub_r = lane >> 3;          // row within a group of 4
   const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
   int od[8];
@@ -143,18 +198,36 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
             sb[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.sub + (long long)od[i] * p.ld_sub + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (ADD) {
+        if (pf) {
+          cp_async_wait<1>();           // this batch's group has landed (only the other batch's may still be pending)
+          if (ADD) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = b * 4 + j;
-            ad[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + (long long)od[i] * p.ld_add + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
+              const int i = b * 4 + j;
+              ad[j] = od[i] >= 0 ? lds128(pf_slot + (i * 32 + lane) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
-        }
-        if (GATE) {
+          if (GATE) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = b * 4 + j;
-            gt[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.gate + (long long)od[i] * p.ld_gate + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            for (int j = 0; j < 4; ++j) {
+              const int i = b * 4 + j;
+              gt[j] = od[i] >= 0 ? lds128(pf_slot + PF_OPERAND_BYTES + (i * 32 + lane) * 16) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+          }
+        } else {
+          if (ADD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = b * 4 + j;
+              ad[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + (long long)od[i] * p.ld_add + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (GATE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = b * 4 + j;
+              gt[j] = od[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.gate + (long long)od[i] * p.ld_gate + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
           }
         }
 #pragma unroll
@@ -184,6 +257,12 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
             *dst = o;
           }
         }
+        if (pf) {
+          // the values of this batch have been consumed: re-use their slot entries for this warp's next chunk
+          const int ncol = n0 + (ch + 2) * 32 + sub_c;
+          const bool more = ch + 2 < nchunks && n0 + (ch + 2) * 32 < p.nb && ncol + 3 < p.nb;
+          pf_issue<ADD, GATE>(p, od, ncol, more, b, pf_slot, lane);
+        }
       }
     } else if (c < p.nb) {
 #pragma unroll 1
@@ -212,17 +291,17 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
 
 template <class Release>
 __device__ __forceinline__ void drain_tile(const Params& p, uint32_t taddr, int block_n, int n0, float* stg,
-                                           const int* rowpix, int lane, int half, int stat_row, Release release) {
+                                           const int* rowpix, int lane, int half, int stat_row, uint32_t pf_slot, Release release) {
   // the specialisations are selected once per tile (uniform branch); stats imply a gate (host-checked)
   if (p.stats) {
-    if (p.addend) drain_tile_t<true, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
-    else drain_tile_t<false, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    if (p.addend) drain_tile_t<true, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
+    else drain_tile_t<false, true, true>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
   } else if (p.addend) {
-    if (p.gate) drain_tile_t<true, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
-    else drain_tile_t<true, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    if (p.gate) drain_tile_t<true, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
+    else drain_tile_t<true, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
   } else {
-    if (p.gate) drain_tile_t<false, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
-    else drain_tile_t<false, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, release);
+    if (p.gate) drain_tile_t<false, true, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
+    else drain_tile_t<false, false, false>(p, taddr, block_n, n0, stg, rowpix, lane, half, stat_row, pf_slot, release);
   }
 }
 

@@ -207,7 +207,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
       const int stat_row = (tile / a.n_tiles_n) * 4 + ew;      // fused column statistics: (M tile, lane quarter)
-      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, stat_row, [&]() {
+      epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, stat_row, 0u, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);

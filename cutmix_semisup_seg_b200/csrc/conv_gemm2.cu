@@ -22,11 +22,18 @@ namespace {
 constexpr int BLOCK_M = 128;            // per CTA; the pair computes 256 rows
 constexpr int BLOCK_K = 32;
 constexpr int BLOCK_N = 256;
-constexpr int STAGES = 5;
+// Two builds of the kernel: the compute-bound one keeps a 5-stage operand ring; the PF one (HBM-bound small-K layers
+// whose epilogue reads a residual addend / ReLU gate) trades two stages for the epilogue's asynchronous prefetch slots
+// (conv_epilogue.cuh).
+constexpr int STAGES_MAIN = 5;
+constexpr int STAGES_PF = 3;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB
 constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;      // 16 KB: this CTA's half of the weight tile
 constexpr int EPI_BYTES = epi::BYTES;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + EPI_BYTES;
+constexpr int smem_bytes(int stages, bool pf) {
+  return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + EPI_BYTES + (pf ? epi::PF_BYTES : 0);
+}
+static_assert(smem_bytes(STAGES_MAIN, false) <= 232448 && smem_bytes(STAGES_PF, true) <= 232448, "shared memory budget");
 constexpr int MAX_TAPS = 16;
 constexpr int NUM_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS = 512;
@@ -138,6 +145,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+template <int STAGES, bool PF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -251,6 +259,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* stg = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + ewi * (32 * epi::ROW_FLOATS);
     int* rowpix = reinterpret_cast<int*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + epi::NUM_WARPS * epi::WARP_BYTES) + ewi * 32;
     const epi::Params& ep = a.ep;     // stays in the kernel's constant parameter space
+    const uint32_t pf_slot = PF ? tc::smem_u32(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + EPI_BYTES) + ewi * epi::PF_WARP_BYTES : 0u;
     int acc = 0; uint32_t acc_phase = 0;
     const int bwbh = a.bw * a.bh;
     int tr_e = 0;
@@ -275,6 +284,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const TileInfo tn = decode_tile(a, pair + num_clusters, (int)rank);
         epi::prefetch_row(ep, row_pixel(tn), tn.n_idx * BLOCK_N + eh * (BLOCK_N / 2), BLOCK_N / 2);
       }
+      if (PF) epi::pf_prologue(ep, BLOCK_N, t.n_idx * BLOCK_N, rowpix, lane, eh, pf_slot);   // first chunk's operands
       if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
@@ -282,7 +292,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
       const int m_idx = (pair / a.n_tiles_n) * 2 + (int)rank;
       const int stat_row = m_idx < a.tiles_w * a.tiles_h * a.tiles_n ? m_idx * 4 + ew : -1;   // phantom tile: none
-      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, stat_row, [&]() {
+      epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, stat_row, pf_slot, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -300,6 +310,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // choose_box is defined in conv_gemm.cu
 extern int g_conv_epi_debug;
+// PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never; b2_debug_set(4, v))
+int g_conv_pf_max_k = 0;
 static long long* g_conv_trace = nullptr;
 extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
@@ -350,16 +362,22 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_MAIN, false)));
+    B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_PF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_PF, true)));
     attr_set = true;
   }
+  const bool use_pf = g_conv_pf_max_k > 0 && (p->addend || p->gate) && a.ep.vec_ok && p->n_split == 1 &&
+                      (int64_t)p->k * p->n_taps <= g_conv_pf_max_k;
   int sms = b2_sm_count_cached();
   if (sms <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_gemm: no CUDA device");
   if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
   int clusters = sms / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > a.num_pairs) clusters = a.num_pairs;
-  conv_gemm2_kernel<<<clusters * 2, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+  if (use_pf)
+    conv_gemm2_kernel<STAGES_PF, true><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+  else
+    conv_gemm2_kernel<STAGES_MAIN, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
   B2_LAUNCH_CHECK("conv_gemm2_kernel");
   return B2_OK;
 }

@@ -350,10 +350,12 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
 
 extern int g_conv_force_1cta;
 extern int g_conv_epi_debug;
+extern int g_conv_pf_max_k;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 1) g_wgrad_desc_variant = value;
   if (key == 2) g_conv_force_1cta = value;
   if (key == 3) g_conv_epi_debug = value;
+  if (key == 4) g_conv_pf_max_k = value;
 }
 
 extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {

@@ -129,3 +129,45 @@ if __name__ == '__main__':
             timeit(lambda: K.conv_dgrad(g, wtt, cout, 1, 1, cin, ldb, 1, 0, 1, y, addend=res, gate=gate), fl, 'dgrad addend+gate' + tag)
             timeit(lambda: K.conv_dgrad(g, wtt, cout, 1, 1, cin, ldb, 1, 0, 1, y, addend=res, gate=gate, want_stats=True, stats_sub=sub), fl, 'dgrad addend+gate+stats+sub' + tag)
         L.b2_debug_set(3, 0)
+    if which == 'pf':
+        # asynchronous epilogue-operand prefetch (cp.async slots, conv_epilogue.cuh) on / off: timing of the HBM-bound
+        # flavours and a bit-exactness check of the two builds of the 2-CTA kernel (debug knob 4 = K*taps threshold)
+        from cutmix_semisup_seg_b200 import lib as _lib, ops as O
+        L = _lib.load()
+        n, h, w = 16, 64, 64
+
+        def flavours(cin, cout, k, dil, tag):
+            pad = dil * (k // 2)
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            wt = torch.randn(cout, k * k, cin, device=dev) * 0.01
+            res = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            gate = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            sc = torch.rand(cout, device=dev) + 0.5; sh = torch.randn(cout, device=dev)
+            fl = 2.0 * n * h * w * cin * cout * k * k
+            outs = {}
+            for thr in (0, 1 << 20):
+                L.b2_debug_set(4, thr)
+                t = ' {} [pf={}]'.format(tag, int(thr > 0))
+                y1 = Act.alloc(n, h, w, cout, dev); y2 = Act.alloc(n, h, w, cout, dev); y3 = Act.alloc(n, h, w, cout, dev)
+                timeit(lambda: K.conv_fwd(x, wt, cout, k, k, cin, cin, 1, pad, dil, y1, scale=sc, shift=sh, addend=res, relu=True), fl, 'fwd bn+residual+relu' + t)
+                timeit(lambda: K.conv_fwd(x, wt, cout, k, k, cin, cin, 1, pad, dil, y2, addend=res, gate=gate), fl, 'gemm addend+gate' + t)
+                stats = [None]
+
+                def run3b():
+                    stats[0] = K.be.conv_gemm(x.ptr, x.n, x.h, x.w, cin, x.ld, wt.data_ptr(), cout, k * k, cin, y3.ptr, h, w, h, w,
+                                              y3.ld, O.conv_taps(k, k, dil, pad), addend=res.ptr, ld_add=res.ld, gate=gate.ptr,
+                                              ld_gate=gate.ld, want_stats=True, device=dev)
+                timeit(run3b, fl, 'gemm addend+gate+stats' + t)
+                outs[thr] = (y1.base.clone(), y2.base.clone(), y3.base.clone(), stats[0][0].clone())
+            same = all(torch.equal(a, b) for a, b in zip(outs[0], outs[1 << 20]))
+            print('   bit-identical with / without prefetch: {}'.format(same), flush=True)
+            L.b2_debug_set(4, 0)
+
+        flavours(256, 1024, 1, 1, '1x1 256->1024')
+        flavours(512, 2048, 1, 1, '1x1 512->2048')
+        flavours(1024, 256, 1, 1, '1x1 1024->256')
+        flavours(128, 512, 1, 1, '1x1 128->512')
+        flavours(256, 256, 3, 2, '3x3 d2 256->256')
+        # ragged case: odd spatial size, channel tail (nb % 32 != 0), batch 3
+        n, h, w = 3, 33, 41
+        flavours(96, 304, 1, 1, 'ragged 1x1 96->304')
