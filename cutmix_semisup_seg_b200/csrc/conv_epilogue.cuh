@@ -86,37 +86,54 @@ __device__ __forceinline__ void prefetch_row(const Params& p, int pix, int c0, i
   if (p.accumulate) prefetch_lines(p.d + (long long)pix * p.ldd + c0, n);
 }
 
-// Issue the asynchronous copies of row groups [4b, 4b+4) of the chunk whose first column (for this lane) is `c`.
+// Issue the asynchronous copies of row groups [4b, 4b+4) of the chunk whose first column (for this lane) is `c` into the
+// slot regions `sa` (addend) / `sg` (gate), and close the commit group (always, so every lane counts the same groups).
 template <bool ADD, bool GATE>
-__device__ __forceinline__ void pf_issue(const Params& p, const int (&od)[8], int c, bool lane_ok, int b, uint32_t slot, int lane) {
+__device__ __forceinline__ void pf_issue(const Params& p, const int (&od)[8], int c, bool lane_ok, int b, uint32_t sa, uint32_t sg, int lane) {
   if (lane_ok) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = b * 4 + j;
       if (od[i] >= 0) {
-        if (ADD) cp_async16(slot + (i * 32 + lane) * 16, p.addend + (long long)od[i] * p.ld_add + c);
-        if (GATE) cp_async16(slot + PF_OPERAND_BYTES + (i * 32 + lane) * 16, p.gate + (long long)od[i] * p.ld_gate + c);
+        if (ADD) cp_async16(sa + (i * 32 + lane) * 16, p.addend + (long long)od[i] * p.ld_add + c);
+        if (GATE) cp_async16(sg + (i * 32 + lane) * 16, p.gate + (long long)od[i] * p.ld_gate + c);
       }
     }
   }
   cp_async_commit();
 }
-// Tile prologue of a PF kernel: start the copies for this warp's first chunk (called before waiting for the accumulator).
+// Slot regions of the q-th chunk a warp processes in a tile: with both operands each owns one region (prefetch distance
+// 1 chunk); a single operand alternates between the two regions (distance 2), so 16 pieces stay in flight either way.
+template <bool ADD, bool GATE>
+__device__ __forceinline__ void pf_regions(uint32_t slot, int q, uint32_t* sa, uint32_t* sg) {
+  if (ADD && GATE) { *sa = slot; *sg = slot + PF_OPERAND_BYTES; }
+  else { *sa = *sg = slot + (q & 1) * PF_OPERAND_BYTES; }
+}
+template <bool ADD, bool GATE>
+__device__ __forceinline__ void pf_prologue_t(const Params& p, int block_n, int n0, const int (&od)[8], int lane, int half, uint32_t slot) {
+  constexpr int DIST = (ADD && GATE) ? 1 : 2;
+  const int sub_c = (lane & 7) * 4;
+#pragma unroll
+  for (int q = 0; q < DIST; ++q) {
+    const int ch = half + 2 * q;
+    const int c = n0 + ch * 32 + sub_c;
+    const bool ok = ch < block_n / 32 && p.vec_ok && c + 3 < p.nb;
+    uint32_t sa, sg;
+    pf_regions<ADD, GATE>(slot, q, &sa, &sg);
+    pf_issue<ADD, GATE>(p, od, c, ok, 0, sa, sg, lane);
+    pf_issue<ADD, GATE>(p, od, c, ok, 1, sa, sg, lane);
+  }
+}
+// Tile prologue of a PF kernel: start the copies for this warp's first chunk(s) (called before waiting for the accumulator).
 __device__ __forceinline__ void pf_prologue(const Params& p, int block_n, int n0, const int* rowpix, int lane, int half, uint32_t slot) {
   if (!(p.addend || p.gate)) return;
-  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  if (half >= block_n / 32 || n0 + half * 32 >= p.nb) return;          // this warp has no chunk in the tile
+  const int sub_r = lane >> 3;
   int od[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) od[i] = rowpix[i * 4 + sub_r];
-  const int col0 = n0 + half * 32;
-  if (half >= block_n / 32 || col0 >= p.nb) return;          // this warp has no chunk in the tile
-  const int c = col0 + sub_c;
-  const bool ok = p.vec_ok && c + 3 < p.nb;
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    if (p.addend) { if (p.gate) pf_issue<true, true>(p, od, c, ok, b, slot, lane); else pf_issue<true, false>(p, od, c, ok, b, slot, lane); }
-    else pf_issue<false, true>(p, od, c, ok, b, slot, lane);
-  }
+  if (p.addend) { if (p.gate) pf_prologue_t<true, true>(p, block_n, n0, od, lane, half, slot); else pf_prologue_t<true, false>(p, block_n, n0, od, lane, half, slot); }
+  else pf_prologue_t<false, true>(p, block_n, n0, od, lane, half, slot);
 }
 
 // Out-of-line general path for one lane's 4 columns of one row: any channel count / alignment, accumulate.
@@ -149,6 +166,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
                                              const int* rowpix, int lane, int half, int stat_row, uint32_t pf_slot,
                                              Release release) {
   const bool pf = (ADD || GATE) && pf_slot != 0;       // operands arrive through the asynchronous prefetch slots
+  constexpr int PF_DIST = (ADD && GATE) ? 1 : 2;
   const int sub_r = lane >> 3;          // row within a group of 4
   const int sub_c = (lane & 7) * 4;     // first of this lane's 4 columns inside a chunk
   int od[8];
@@ -176,6 +194,8 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
     if (col0 >= p.nb) continue;
     const int c = col0 + sub_c;
     const bool lane_fast = fast && c + 3 < p.nb;
+    uint32_t pf_sa = 0, pf_sg = 0;
+    if (pf) pf_regions<ADD, GATE>(pf_slot, (ch - half) >> 1, &pf_sa, &pf_sg);
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;     // STATS: this lane's column sums over its 8 rows
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -199,19 +219,19 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
           }
         }
         if (pf) {
-          cp_async_wait<1>();           // this batch's group has landed (only the other batch's may still be pending)
+          cp_async_wait<2 * PF_DIST - 1>();   // this batch's group has landed (only the later ones may still be pending)
           if (ADD) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = b * 4 + j;
-              ad[j] = od[i] >= 0 ? lds128(pf_slot + (i * 32 + lane) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+              ad[j] = od[i] >= 0 ? lds128(pf_sa + (i * 32 + lane) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           if (GATE) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = b * 4 + j;
-              gt[j] = od[i] >= 0 ? lds128(pf_slot + PF_OPERAND_BYTES + (i * 32 + lane) * 16) : make_float4(1.f, 1.f, 1.f, 1.f);
+              gt[j] = od[i] >= 0 ? lds128(pf_sg + (i * 32 + lane) * 16) : make_float4(1.f, 1.f, 1.f, 1.f);
             }
           }
         } else {
@@ -258,10 +278,11 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
           }
         }
         if (pf) {
-          // the values of this batch have been consumed: re-use their slot entries for this warp's next chunk
-          const int ncol = n0 + (ch + 2) * 32 + sub_c;
-          const bool more = ch + 2 < nchunks && n0 + (ch + 2) * 32 < p.nb && ncol + 3 < p.nb;
-          pf_issue<ADD, GATE>(p, od, ncol, more, b, pf_slot, lane);
+          // the values of this batch have been consumed: re-use their slot entries for the chunk PF_DIST ahead
+          const int nch = ch + 2 * PF_DIST;
+          const int ncol = n0 + nch * 32 + sub_c;
+          const bool more = nch < nchunks && ncol + 3 < p.nb;
+          pf_issue<ADD, GATE>(p, od, ncol, more, b, pf_sa, pf_sg, lane);
         }
       }
     } else if (c < p.nb) {

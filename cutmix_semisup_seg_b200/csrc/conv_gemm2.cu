@@ -14,6 +14,7 @@
 //     CTAs and publishes the finished accumulator to both epilogues;
 //   * each CTA's TMEM holds its 128 rows of the 256-row accumulator; both epilogues arrive (the peer remotely) on the
 //     leader's "accumulator empty" barrier.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv_epilogue.cuh"
 
@@ -310,8 +311,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // choose_box is defined in conv_gemm.cu
 extern int g_conv_epi_debug;
-// PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never; b2_debug_set(4, v))
-int g_conv_pf_max_k = 0;
+// PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never).  Measured on B200
+// (profiles/r01_v7_pf_microbench.log): faster up to K = 512 (HBM-bound 1x1 layers, 0.231 -> 0.163 ms for 256 -> 1024 with
+// addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
+// Override: environment B200SEG_PF_MAX_K or b2_debug_set(4, v).
+int g_conv_pf_max_k = -1;
 static long long* g_conv_trace = nullptr;
 extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
@@ -365,6 +369,10 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
     B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_MAIN, false)));
     B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_PF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_PF, true)));
     attr_set = true;
+  }
+  if (g_conv_pf_max_k < 0) {
+    const char* e = getenv("B200SEG_PF_MAX_K");
+    g_conv_pf_max_k = e ? atoi(e) : 512;
   }
   const bool use_pf = g_conv_pf_max_k > 0 && (p->addend || p->gate) && a.ep.vec_ok && p->n_split == 1 &&
                       (int64_t)p->k * p->n_taps <= g_conv_pf_max_k;

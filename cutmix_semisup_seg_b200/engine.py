@@ -513,7 +513,7 @@ def bilinear(tape, x, oh, ow, align_corners, out=None):
 
 
 def global_avg_pool(tape, x):
-    y = Act.alloc(x.n, 1, 1, x.c, x.device)
+    y = Act.alloc(x.n, 1, 1, x.c, x.device, ld=x.c)     # dense (N, C) vector
     tape.K.gap_fwd(x, y)
     node = GapNode(x, y)
     y.node = node

@@ -191,16 +191,21 @@ class ActKernels(object):
         self.be.bilinear_bwd(dy_nchw.data_ptr(), dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, oh, ow, 0, align_corners, True,
                              scale_dev=scale_dev, scale_host=scale_host, accumulate=accumulate)
 
+    # pooled / broadcast vectors are dense (N, C) in the C ABI
     def gap_fwd(self, x, out):
+        assert out.ld == out.c, 'pooled vector must be dense'
         self.be.gap_fwd(x.ptr, out.ptr, x.n, x.h * x.w, x.c, x.ld)
 
     def gap_bwd(self, dy, dx, accumulate=False):
+        assert dy.ld == dy.c, 'pooled vector must be dense'
         self.be.gap_bwd(dy.ptr, dx.ptr, dx.n, dx.h * dx.w, dx.c, dx.ld, accumulate=accumulate)
 
     def bcast_fwd(self, v, out):
+        assert v.ld == v.c, 'broadcast vector must be dense'
         self.be.bcast_fwd(v.ptr, out.ptr, out.n, out.h * out.w, out.c, out.ld)
 
     def bcast_bwd(self, dy, dv):
+        assert dv.ld == dv.c, 'broadcast vector must be dense'
         self.be.bcast_bwd(dy.ptr, dv.ptr, dy.n, dy.h * dy.w, dy.c, dy.ld)
 
     def bn_stats(self, x, eps, momentum, mean, rstd, running_mean, running_var):

@@ -158,7 +158,7 @@ def test_bn_train_stats_apply_bwd(K, case):
 def test_gap_and_broadcast(K, case):
     n, h, w, c, ld = case
     xg, xc = pair(n, h, w, c, ld=ld, seed=14)
-    vg = Act.alloc(n, 1, 1, c, dev); vc = Act.alloc(n, 1, 1, c, 'cpu')
+    vg = Act.alloc(n, 1, 1, c, dev, ld=c); vc = Act.alloc(n, 1, 1, c, 'cpu', ld=c)      # pooled vectors are dense (N, C)
     K.gap_fwd(xg, vg); E.gap_fwd(xc, vc)
     assert rel(vg, vc) < 1e-5
     dxg, dxc = pair(n, h, w, c, ld=ld, seed=15)
@@ -169,7 +169,7 @@ def test_gap_and_broadcast(K, case):
     og, oc = pair(n, h, w, c, ld=ld + 8, off=4, fill=1.0)
     K.bcast_fwd(vg, og); E.bcast_fwd(vc, oc)
     assert rel(og, oc) < 1e-6 and same_outside(og, oc)
-    sg = Act.alloc(n, 1, 1, c, dev); sc = Act.alloc(n, 1, 1, c, 'cpu')
+    sg = Act.alloc(n, 1, 1, c, dev, ld=c); sc = Act.alloc(n, 1, 1, c, 'cpu', ld=c)
     K.bcast_bwd(og, sg); E.bcast_bwd(oc, sc)
     assert rel(sg, sc) < 1e-5
 
