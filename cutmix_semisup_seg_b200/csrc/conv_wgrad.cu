@@ -43,6 +43,7 @@ struct WgradKArgs {
   int desc_variant;
   const float* row_scale;   // per output channel m (folded BN scale), applied before accumulation
   int use5_a, use5_b;       // operand fetched with ONE 5-D TMA per stage (channel count multiple of 32)
+  int m_tile_rows;          // 128 (single-CTA kernel) or 256 (CTA-pair kernel)
 };
 
 struct UnitInfo {
@@ -57,7 +58,7 @@ __device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, int u) {
   const int ct = t % a.c_tiles; t /= a.c_tiles;
   r.tap = t % a.n_taps;
   const int mt = t / a.n_taps;
-  r.m0 = mt * W_BLOCK_M; r.c0 = ct * a.block_n;
+  r.m0 = mt * a.m_tile_rows; r.c0 = ct * a.block_n;
   r.pb_begin = (int)(((int64_t)a.num_pb * r.split) / a.n_splits);
   r.pb_end = (int)(((int64_t)a.num_pb * (r.split + 1)) / a.n_splits);
   return r;
@@ -254,6 +255,206 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   if (warp == 2) tc::tmem_dealloc(tmem_base, W_TMEM_COLS);
 }
 
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2, M = 256 output channels per CTA pair).  Same reason as conv_gemm2.cu: with fp32 operands a
+// single-CTA 128 x 256 x 8 MMA reads 12 KB of shared memory per K step while TMA writes the same 12 KB, ~190 B/cycle
+// against a ~128 B/cycle port, and the single-CTA kernel saturates at ~65 % of the tf32 rate (450-520 TFLOP/s on the
+// layer3/4 shapes, profiles/r01_v7_*).  Here each CTA of the pair holds its own 128 output channels of dY and HALF of the
+// input-channel tile of X, so per K step shared memory sees 8 KB of reads + 8 KB of TMA writes per CTA.
+// Protocol as in conv_gemm2.cu (leader = cluster rank 0 issues the MMAs; TMA loads of both CTAs complete on the leader's
+// full barrier; tcgen05.commit multicasts to both CTAs; both epilogues arrive on the leader's accumulator-empty barrier).
+// Requirements (host-checked, else the single-CTA kernel runs): M % 256 == 0, C % 64 == 0 (5-D TMA for both operands).
+constexpr int W2_STAGES = 6;
+constexpr int W2_A_STAGE_BYTES = (W_BLOCK_M / 32) * W_SLOT_BYTES;              // 16 KB: this CTA's 128 output channels
+constexpr int W2_B_STAGE_BYTES = (W_MAX_BLOCK_N / 64) * W_SLOT_BYTES;          // 16 KB: this CTA's half of the N tile
+constexpr int W2_SMEM_BYTES = W2_STAGES * (W2_A_STAGE_BYTES + W2_B_STAGE_BYTES) + 1024 + 256;
+
+__device__ __forceinline__ uint32_t w2_cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void w2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t W2_PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared-window address -> leader CTA
+__device__ __forceinline__ void w2_tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & W2_PEER_BIT_MASK),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void w2_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void w2_commit_mcast(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void w2_arrive_leader(uint64_t* bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(tc::smem_u32(bar)));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W_THREADS, 1)
+conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_constant__ CUtensorMap tmY5lo,
+                   const __grid_constant__ CUtensorMap tmX5, const __grid_constant__ CUtensorMap tmX5lo,
+                   const __grid_constant__ WgradKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + W2_STAGES * W2_A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W2_STAGES * (W2_A_STAGE_BYTES + W2_B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                          // [W2_STAGES]  leader's copies are the live ones
+  uint64_t* empty_bar = bars + W2_STAGES;             // [W2_STAGES]  per CTA
+  uint64_t* tfull_bar = bars + 2 * W2_STAGES;         // [2]          per CTA
+  uint64_t* tempty_bar = bars + 2 * W2_STAGES + 2;    // [2]          leader's copies are the live ones
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * W2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = w2_cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmY5); tc::tma_prefetch_desc(&tmX5);
+    if (a.n_pass > 1) { tc::tma_prefetch_desc(&tmY5lo); tc::tma_prefetch_desc(&tmX5lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < W2_STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 8); }   // 4 warps x 2 CTAs
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr)), "r"(W_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  w2_cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int half_n = a.block_n / 2;                   // this CTA's input channels of the N tile (multiple of 32)
+  const int slot = a.kpix * 128;
+  const uint32_t stage_tx = 2u * (uint32_t)((W_BLOCK_M / 32) + half_n / 32) * (uint32_t)slot;     // both CTAs' bytes
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = cluster_id; u < a.num_units; u += num_clusters) {
+        const UnitInfo ui = decode_unit(a, u);
+        bool any = false;
+        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
+          const PBox b = decode_pb(a, pb, ui.tap);
+          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
+          any = true;
+          const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
+            w2_tma_load_5d(smem_a + stage * W2_A_STAGE_BYTES, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0,
+                           (ui.m0 + (int)rank * W_BLOCK_M) / 32);
+            w2_tma_load_5d(smem_b + stage * W2_B_STAGE_BYTES, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, xw, xh, b.n0,
+                           (ui.c0 + (int)rank * half_n) / 32);
+            if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(2 * W_BLOCK_M, a.block_n, 1, 1);
+      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
+      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int ksteps = a.kpix / 8;
+      for (int u = cluster_id; u < a.num_units; u += num_clusters) {
+        const UnitInfo ui = decode_unit(a, u);
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
+        uint32_t first = 1;
+        bool any = false;
+        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
+          const PBox b = decode_pb(a, pb, ui.tap);
+          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
+          any = true;
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&full_bar[stage], phase);
+            tc::tc_fence_after();
+            const uint32_t a_addr = tc::smem_u32(smem_a + stage * W2_A_STAGE_BYTES);
+            const uint32_t b_addr = tc::smem_u32(smem_b + stage * W2_B_STAGE_BYTES);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
+              w2_mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            w2_commit_mcast(&empty_bar[stage]);
+            if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        w2_commit_mcast(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: own 128 output channels) =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = cluster_id; u < a.num_units; u += num_clusters) {
+      const UnitInfo ui = decode_unit(a, u);
+      const int mrow = ui.m0 + (int)rank * W_BLOCK_M + row;
+      const bool valid = mrow < a.m;
+      float* orow = a.out + (int64_t)ui.split * a.slab_elems + ((int64_t)mrow * a.tw + a.wtap[ui.tap]) * a.c;
+      const float rs = (a.row_scale && valid) ? __ldg(a.row_scale + mrow) : 1.0f;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * W_MAX_BLOCK_N;
+      const int nchunks = a.block_n / 32;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t r[32];
+        tc::tmem_ld_x32(taddr + ch * 32, r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const int col0 = ui.c0 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = col0 + j * 4;
+            if (c >= a.c) break;
+            float4 o = make_float4(__uint_as_float(r[j * 4]) * rs, __uint_as_float(r[j * 4 + 1]) * rs,
+                                   __uint_as_float(r[j * 4 + 2]) * rs, __uint_as_float(r[j * 4 + 3]) * rs);
+            if (a.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(orow + c);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(orow + c) = o;       // C % 64 == 0 and a 16 B aligned output (host-checked)
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) w2_arrive_leader(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  w2_cluster_sync();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(W_TMEM_COLS) : "memory");
+}
+
 // dw[i] = (accumulate ? dw[i] : 0) + sum_s slabs[s][i], fixed order.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_splits, int64_t elems,
                                     float* __restrict__ dw, int accumulate) {
@@ -266,6 +467,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_split
 }
 
 int g_wgrad_desc_variant = 0;
+int g_wgrad_force_1cta = 0;       // b2_debug_set(5, 1): always the single-CTA kernel
 
 struct WPlan {
   WgradKArgs a;
@@ -306,11 +508,19 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   const int64_t num_pb = (int64_t)a.tiles_w * a.tiles_h * a.tiles_n;
   B2_REQUIRE(num_pb < (1ll << 31), "b2_conv_wgrad: too many pixel boxes");
   a.num_pb = (int)num_pb;
-  a.m_tiles = (p->m + W_BLOCK_M - 1) / W_BLOCK_M;
-  int block_n = ((p->c + 31) / 32) * 32;
-  if (block_n > W_MAX_BLOCK_N) block_n = W_MAX_BLOCK_N;
+  // CTA-pair kernel (M = 256 per pair, each CTA loads half of the N tile): needs whole 256-channel M tiles, N tiles that
+  // split into two multiples of 32, the 5-D TMA form of both operands and vector stores.
+  const bool two_cta = !g_wgrad_force_1cta && p->m % 256 == 0 && p->c % 64 == 0 && p->max_ctas != 1 &&
+                       (reinterpret_cast<uintptr_t>(p->dw) & 15) == 0 &&
+                       (!p->workspace || (reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0);
+  a.m_tile_rows = two_cta ? 2 * W_BLOCK_M : W_BLOCK_M;
+  a.m_tiles = (p->m + a.m_tile_rows - 1) / a.m_tile_rows;
+  // balanced N tiles: C = 304 -> two tiles of 160 channels instead of 256 + 48
+  const int gran = two_cta ? 64 : 32;
+  const int cblk = (p->c + gran - 1) / gran;                         // channel blocks of `gran`
+  a.c_tiles = (cblk * gran + W_MAX_BLOCK_N - 1) / W_MAX_BLOCK_N;
+  const int block_n = ((cblk + a.c_tiles - 1) / a.c_tiles) * gran;
   a.block_n = block_n;
-  a.c_tiles = (p->c + block_n - 1) / block_n;
   a.n_taps = p->n_taps;
   for (int i = 0; i < p->n_taps; ++i) {
     a.dh[i] = (short)p->taps[i * 3 + 0]; a.dw[i] = (short)p->taps[i * 3 + 1]; a.wtap[i] = (short)p->taps[i * 3 + 2];
@@ -321,6 +531,7 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   int sms = b2_sm_count_cached();
   if (sms <= 0) sms = 148;
   if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
+  if (two_cta) sms /= 2;            // work units are processed by CTA pairs
   int splits = sms / a.out_tiles;
   if (splits < 1) splits = 1;
   // keep at least ~8 pixel boxes per split so the pipeline fills
@@ -352,6 +563,7 @@ extern int g_conv_force_1cta;
 extern int g_conv_epi_debug;
 extern int g_conv_pf_max_k;
 extern "C" void b2_debug_set(int key, int value) {
+  if (key == 5) g_wgrad_force_1cta = value;
   if (key == 1) g_wgrad_desc_variant = value;
   if (key == 2) g_conv_force_1cta = value;
   if (key == 3) g_conv_epi_debug = value;
@@ -424,7 +636,43 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES));
     attr_set = true;
+  }
+  if (a.m_tile_rows == 2 * W_BLOCK_M) {
+    // CTA-pair kernel: 5-D maps whose outermost box covers this CTA's share of the tile (4 blocks of dY, block_n/64 of X)
+    B2_REQUIRE(a.use5_a && a.use5_b, "b2_conv_wgrad: 5-D tensor maps unavailable for the CTA-pair kernel");
+    CUtensorMap y5, y5lo, x5, x5lo;
+    {
+      const uint64_t d5[5] = {32, (uint64_t)p->ow, (uint64_t)p->oh, (uint64_t)p->n, (uint64_t)(p->m / 32)};
+      const uint64_t s5[4] = {(uint64_t)p->ldy * 4, (uint64_t)p->ow * p->ldy * 4, (uint64_t)p->oh * p->ow * p->ldy * 4, 128};
+      const uint32_t b5[5] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn, (uint32_t)(W_BLOCK_M / 32)};
+      const uint32_t e5[5] = {1, 1, 1, 1, 1};
+      rc = tc::make_tmap_f32(&y5, p->dy, 5, d5, s5, b5, e5, true); if (rc) return rc;
+      rc = tc::make_tmap_f32(&y5lo, p->dy_lo ? p->dy_lo : p->dy, 5, d5, s5, b5, e5, true); if (rc) return rc;
+    }
+    {
+      const uint64_t d5[5] = {32, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n, (uint64_t)(p->c / 32)};
+      const uint64_t s5[4] = {(uint64_t)p->ldx * 4, (uint64_t)p->iw * p->ldx * 4, (uint64_t)p->ih * p->iw * p->ldx * 4, 128};
+      const uint32_t b5[5] = {32, (uint32_t)(a.bw * p->istride), (uint32_t)(a.bh * p->istride), (uint32_t)a.bn, (uint32_t)(a.block_n / 64)};
+      const uint32_t e5[5] = {1, (uint32_t)p->istride, (uint32_t)p->istride, 1, 1};
+      rc = tc::make_tmap_f32(&x5, p->x, 5, d5, s5, b5, e5, true); if (rc) return rc;
+      rc = tc::make_tmap_f32(&x5lo, p->x_lo ? p->x_lo : p->x, 5, d5, s5, b5, e5, true); if (rc) return rc;
+    }
+    int clusters = b2_sm_count_cached() / 2;
+    if (clusters <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
+    if (p->max_ctas > 0 && p->max_ctas / 2 < clusters) clusters = p->max_ctas / 2 > 0 ? p->max_ctas / 2 : 1;
+    if (clusters > a.num_units) clusters = a.num_units;
+    conv_wgrad2_kernel<<<clusters * 2, W_THREADS, W2_SMEM_BYTES, s>>>(y5, y5lo, x5, x5lo, a);
+    B2_LAUNCH_CHECK("conv_wgrad2_kernel");
+    if (a.n_splits > 1) {
+      const int64_t elems = (int64_t)p->m * p->tw * p->c;
+      int64_t blocks = ceil_div64(elems, 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
+      B2_LAUNCH_CHECK("wgrad_reduce_kernel");
+    }
+    return B2_OK;
   }
   int grid = b2_sm_count_cached();
   if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");

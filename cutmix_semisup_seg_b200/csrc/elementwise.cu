@@ -310,12 +310,12 @@ extern "C" int b2_dropout_mask(float* mask, int64_t count, float p, uint64_t see
 
 // g[row, c] = (y[row, c] > 0) ? g[row, c] : 0   (explicit ReLU backward where it cannot be fused)
 static inline bool ew_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-template <int V>
+template <int V, typename I>
 __global__ void __launch_bounds__(256) relu_gate_kernel(float* __restrict__ g, int ldg, const float* __restrict__ y, int ldy, int64_t rows, int c) {
   const int cg = c / V;
-  const int64_t total = rows * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cg) * V; const int64_t row = i / cg;
+  const I total = (I)(rows * cg);
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cg) * V; const int64_t row = (int64_t)(i / cg);
     if (V == 4) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch));
       float4* gp = reinterpret_cast<float4*>(g + row * ldg + ch);
@@ -331,18 +331,19 @@ extern "C" int b2_relu_gate(float* g, int ldg, const float* y, int ldy, int64_t 
   B2_REQUIRE(g && y && rows > 0 && c > 0 && ldg >= c && ldy >= c, "b2_relu_gate: bad args");
   const bool vec = c % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 && ew_al16(g) && ew_al16(y);
   int64_t blocks = ceil_div64(rows * (vec ? c / 4 : c), 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  if (vec) relu_gate_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
-  else relu_gate_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
+  if (vec && rows * (c / 4) < (1ll << 31)) relu_gate_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
+  else if (vec) relu_gate_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
+  else relu_gate_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, c);
   B2_LAUNCH_CHECK("relu_gate_kernel");
   return B2_OK;
 }
 // strided copy / add of an NHWC slice: dst[row, c] (+)= src[row, c]
-template <int V>
+template <int V, typename I>
 __global__ void __launch_bounds__(256) slice_copy_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int64_t rows, int c, int accumulate) {
   const int cg = c / V;
-  const int64_t total = rows * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cg) * V; const int64_t row = i / cg;
+  const I total = (I)(rows * cg);
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cg) * V; const int64_t row = (int64_t)(i / cg);
     if (V == 4) {
       float4 v = __ldg(reinterpret_cast<const float4*>(src + row * lds + ch));
       float4* d = reinterpret_cast<float4*>(dst + row * ldd + ch);
@@ -359,8 +360,9 @@ extern "C" int b2_slice_copy(float* dst, int ldd, const float* src, int lds, int
   B2_REQUIRE(dst && src && rows > 0 && c > 0 && ldd >= c && lds >= c, "b2_slice_copy: bad args");
   const bool vec = c % 4 == 0 && ldd % 4 == 0 && lds % 4 == 0 && ew_al16(dst) && ew_al16(src);
   int64_t blocks = ceil_div64(rows * (vec ? c / 4 : c), 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  if (vec) slice_copy_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
-  else slice_copy_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
+  if (vec && rows * (c / 4) < (1ll << 31)) slice_copy_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
+  else if (vec) slice_copy_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
+  else slice_copy_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, c, accumulate);
   B2_LAUNCH_CHECK("slice_copy_kernel");
   return B2_OK;
 }

@@ -188,8 +188,12 @@ class ActKernels(object):
 
     def bilinear_bwd_nchw(self, dy_nchw, dx, align_corners, scale_dev=None, scale_host=1.0, accumulate=False):
         n, c, oh, ow = dy_nchw.shape
-        self.be.bilinear_bwd(dy_nchw.data_ptr(), dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, oh, ow, 0, align_corners, True,
-                             scale_dev=scale_dev, scale_host=scale_host, accumulate=accumulate)
+        if max(oh, ow) <= 3072:
+            self.be.bilinear_bwd_nchw(dy_nchw, dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, align_corners, scale_dev=scale_dev,
+                                      scale_host=scale_host, accumulate=accumulate)
+        else:
+            self.be.bilinear_bwd(dy_nchw.data_ptr(), dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, oh, ow, 0, align_corners, True,
+                                 scale_dev=scale_dev, scale_host=scale_host, accumulate=accumulate)
 
     # pooled / broadcast vectors are dense (N, C) in the C ABI
     def gap_fwd(self, x, out):

@@ -93,6 +93,8 @@ _SIGS = {
     'b2_maxpool3x3s2_bwd': (c_int, [c_vp, c_vp, c_vp] + [c_int] * 6 + [c_vp]),
     'b2_bilinear_fwd': (c_int, [c_vp, c_vp] + [c_int] * 10 + [c_vp]),
     'b2_bilinear_bwd': (c_int, [c_vp, c_vp] + [c_int] * 10 + [c_vp, c_f32, c_int, c_vp]),
+    'b2_bilinear_bwd_nchw_workspace_floats': (c_i64, [c_int, c_int, c_int, c_int]),
+    'b2_bilinear_bwd_nchw': (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp, c_f32, c_int, c_vp]),
     'b2_gap_fwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     'b2_gap_bwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_bcast_fwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
@@ -121,7 +123,7 @@ _SIGS = {
 # Functions that return a size/count rather than an error code.
 _NON_STATUS = {'b2_version', 'b2_num_sms', 'b2_consistency_num_partials', 'b2_ce_num_partials',
                'b2_conv_wgrad_workspace', 'b2_bn_workspace_doubles', 'b2_conv_stats_rows',
-               'b2_bn_stats_workspace_doubles'}
+               'b2_bn_stats_workspace_doubles', 'b2_bilinear_bwd_nchw_workspace_floats'}
 
 _lib = None
 

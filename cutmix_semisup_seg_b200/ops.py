@@ -251,6 +251,15 @@ class CudaBackend(object):
         self._call('b2_bilinear_bwd', dy_ptr, dx_ptr, n, ih, iw, c, ldx, oh, ow, ldy, int(align_corners), int(from_nchw),
                    L.ptr(scale_dev), float(scale_host), int(accumulate), self._s())
 
+    def bilinear_bwd_nchw(self, dy, dx_ptr, n, ih, iw, c, ldx, align_corners, scale_dev=None, scale_host=1.0, accumulate=False):
+        """Backward of the final resize: dy (N,C,OH,OW) contiguous -> NHWC dx, separable two-pass kernel."""
+        oh, ow = dy.shape[2], dy.shape[3]
+        need = int(L.call('b2_bilinear_bwd_nchw_workspace_floats', n, c, iw, oh))
+        tmp = torch.empty((need,), device=dy.device, dtype=torch.float32)
+        self._call('b2_bilinear_bwd_nchw', dy.data_ptr(), dx_ptr, tmp.data_ptr(), n, ih, iw, c, ldx, oh, ow, int(align_corners),
+                   L.ptr(scale_dev), float(scale_host), int(accumulate), self._s())
+        self.launches += 1
+
     def gap_fwd(self, x_ptr, y_ptr, n, hw, c, ldx):
         self._call('b2_gap_fwd', x_ptr, y_ptr, n, hw, c, ldx, self._s())
 

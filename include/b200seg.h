@@ -211,6 +211,12 @@ int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int c, int 
 int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw, int c, int ldx, int oh,
                     int ow, int ldy, int align_corners, int from_nchw, const float* scale_dev,
                     float scale_host, int accumulate, void* stream);
+/* Separable form of the same backward for an NCHW dY (the final resize to the input resolution, reference
+ * deeplab3plus.py:77 / deeplab2.py:204): horizontal pass into `workspace` (b2_bilinear_bwd_nchw_workspace_floats(n, c, iw, oh)
+ * floats), then the vertical pass; identical results to b2_bilinear_bwd(from_nchw = 1). */
+int64_t b2_bilinear_bwd_nchw_workspace_floats(int n, int c, int iw, int oh);
+int b2_bilinear_bwd_nchw(const float* dy, float* dx, float* workspace, int n, int ih, int iw, int c, int ldx, int oh, int ow,
+                         int align_corners, const float* scale_dev, float scale_host, int accumulate, void* stream);
 /* Global average pool (ASPPPooling) and its backward (broadcast /HW). */
 int b2_gap_fwd(const float* x, float* y, int n, int hw, int c, int ldx, void* stream);
 int b2_gap_bwd(const float* dy, float* dx, int n, int hw, int c, int ldx, int accumulate,

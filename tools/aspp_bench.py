@@ -171,3 +171,29 @@ if __name__ == '__main__':
         # ragged case: odd spatial size, channel tail (nb % 32 != 0), batch 3
         n, h, w = 3, 33, 41
         flavours(96, 304, 1, 1, 'ragged 1x1 96->304')
+    if which == 'wg2':
+        # weight-gradient kernel: single-CTA vs CTA-pair build (debug knob 5) on the hot-path shapes, with a bit-level
+        # comparison of the two results (same K order per accumulator => expected identical up to the split count)
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        for (n, h, w, cin, cout, k, dil, name) in ((16, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256'),
+                                                   (16, 64, 64, 256, 1024, 1, 1, 'layer3 1x1 256->1024'),
+                                                   (16, 64, 64, 1024, 256, 1, 1, 'layer3 1x1 1024->256'),
+                                                   (16, 64, 64, 512, 512, 3, 4, 'layer4 3x3 d4 512->512'),
+                                                   (16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256'),
+                                                   (16, 64, 64, 512, 2048, 1, 1, 'layer4 1x1 512->2048'),
+                                                   (16, 128, 128, 256, 256, 3, 1, 'decoder 3x3 256->256'),
+                                                   (16, 128, 128, 304, 256, 3, 1, 'decoder 3x3 304->256')):
+            pad = dil * (k // 2)
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            fl = 2.0 * n * h * w * cin * cout * k * k
+            res = []
+            for force1 in (1, 0):
+                L.b2_debug_set(5, force1)
+                dw = torch.zeros(cout, k * k, cin, device=dev)
+                timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), fl, name + ' wgrad [2cta={}]'.format(1 - force1))
+                res.append(dw.clone())
+            d = (res[0] - res[1]).abs().max().item() / res[0].abs().max().item()
+            print('   max rel diff 1-CTA vs 2-CTA: {:.3e}'.format(d), flush=True)
+        L.b2_debug_set(5, 0)
