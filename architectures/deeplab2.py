@@ -126,14 +126,22 @@ class ResNetDeepLab(B2SegNet):
         return nn.Sequential(*units)
 
     # ---- engine graph (reference forward: deeplab2.py:183-206) -------------------------------
-    def _graph(self, tape, x, in_h, in_w):
+    def _graph_trunk(self, tape, x, in_h, in_w):
+        # every BatchNorm of DeepLab v2 is a frozen one: the whole network is the batch-invariant trunk and the "head"
+        # is the final resize of the low-resolution logits
         t = E.stem_conv(tape, x, self.conv1, self.bn1)
         t = E.maxpool3x3s2(tape, t, ceil_mode=True)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for unit in layer:
                 t = unit.graph(tape, t)
         t = self.layer5.graph(tape, t)
-        return t, True
+        return [(t, True)]
+
+    def _graph_head(self, tape, feats, in_h, in_w):
+        return feats[0], True
+
+    def _trunk_module(self):
+        return self
 
     def forward(self, x, use_dropout=False):
         return super(ResNetDeepLab, self).forward(x)

@@ -191,9 +191,16 @@ class DeepLabv3Wrapper(B2SegNet):
         self.deeplab = model
         self.pretraining = pretraining
 
-    def _graph(self, tape, x, in_h, in_w):
+    def _graph_trunk(self, tape, x, in_h, in_w):
         feats = self.deeplab.backbone.graph(tape, x)
-        return self.deeplab.classifier.graph(tape, feats), False
+        # layer1's output also feeds layer2; layer4's output is consumed by the head only
+        return [(feats['low_level'], False), (feats['out'], True)]
+
+    def _graph_head(self, tape, feats, in_h, in_w):
+        return self.deeplab.classifier.graph(tape, {'low_level': feats[0], 'out': feats[1]}), False
+
+    def _trunk_module(self):
+        return self.deeplab.backbone
 
     def forward(self, x, feature_maps=False, use_dropout=False):
         return super(DeepLabv3Wrapper, self).forward(x)

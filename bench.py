@@ -112,7 +112,8 @@ def build_trainer(cfg, device, dist_on, use_graph=True):
                                    within_bounds=True, invert=True)
     trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, cons_loss_fn='var', cons_weight=1.0,
                                        conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                                       dist_group=True if dist_on else None, use_cuda_graph=use_graph)
+                                       dist_group=True if dist_on else None, use_cuda_graph=use_graph,
+                                       batch_trunk=os.environ.get('B200SEG_BATCH_TRUNK', '1') != '0')
     return trainer, mg
 
 
@@ -222,7 +223,9 @@ def run_b200(args):
         'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
         'config': {'workload': cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
-                   'freeze_bn': True, 'optimizer': trainer.optim_note, 'launch_mode': 'eager' if args.eager else 'cuda-graph replay (2 graphs/step)',
+                   'freeze_bn': True, 'optimizer': trainer.optim_note,
+                   'trunk_batching': 'frozen-BN backbone once per network over 2 concatenated mini-batches'
+                                     if trainer._can_batch_trunk([None]) else 'pass by pass', 'launch_mode': 'eager' if args.eager else 'cuda-graph replay (2 graphs/step)',
                    'host_enqueue_ms_per_step': round((t_enq - t_start) * 1e3 / args.steps, 2),
                    'conv_tflops_per_s_whole_step': round(flops_iter / (ms_step / 1e3) / 1e12, 2)},
         'clocks': clocks,

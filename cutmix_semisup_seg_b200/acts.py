@@ -7,7 +7,7 @@ class Act(object):
     channels [off, off + c) of every pixel.  Slices of a wider buffer replace torch.cat."""
 
     __slots__ = ('base', 'n', 'h', 'w', 'c', 'ld', 'off', 'gate_on_grad', 'node', 'parent', 'pending',
-                 'grad', 'grad_owned', 'name', 'needs_grad', 'fused_stats')
+                 'grad', 'grad_owned', 'name', 'needs_grad', 'fused_stats', 'grad_home')
 
     def __init__(self, base, n, h, w, c, ld=None, off=0, name=''):
         self.base = base
@@ -23,6 +23,7 @@ class Act(object):
         self.name = name
         self.needs_grad = True      # False for network inputs (no dgrad is computed into them)
         self.fused_stats = None     # column sums written by the epilogue that finished .grad (engine.Tape)
+        self.grad_home = None       # pre-assigned gradient buffer (batch slices write into their parent's gradient)
 
     @staticmethod
     def alloc(n, h, w, c, device, ld=None, name=''):
@@ -45,6 +46,12 @@ class Act(object):
         s = Act(self.base, self.n, self.h, self.w, c, self.ld, self.off + off, name)
         s.parent = self
         return s
+
+    def batch_slice(self, n0, n, name=''):
+        """Samples [n0, n0 + n) as an independent root activation sharing this one's storage (N is the outermost
+        dimension of NHWC, so the slice is contiguous)."""
+        assert 0 <= n0 and n0 + n <= self.n
+        return Act(self.base[n0:n0 + n], n, self.h, self.w, self.c, self.ld, self.off, name)
 
     def like(self, name=''):
         """Fresh dense buffer with the same logical shape."""

@@ -204,11 +204,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int p = 0; p < a.n_pass; ++p) {
               tc::mbar_wait(&empty_bar[stage], phase ^ 1);
               if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[tr_n++] = clock64();
-              if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
-              tma2_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
-                           kb * BLOCK_K, cw, ch, t.n0);
-              tma2_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
-                           kb * BLOCK_K, bt, t.n_idx * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (a.ep.dbg & 8) {               // timing experiment: no operand traffic (stale smem contents)
+                if (leader) tc::mbar_arrive(&full_bar[stage]);
+              } else {
+                if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
+                tma2_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
+                             kb * BLOCK_K, cw, ch, t.n0);
+                tma2_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
+                             kb * BLOCK_K, bt, t.n_idx * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              }
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -237,12 +241,14 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[512 + tr_n++] = clock64();
           const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
+          if (!(a.ep.dbg & 16)) {             // (16: timing experiment without tensor-core work)
 #pragma unroll
-          for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
-            const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
-            const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
-            mma2_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-            first = 0;
+            for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
+              const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
+              const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
+              mma2_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
           }
           mma2_commit_mcast(&empty_bar[stage]);   // frees this stage in both CTAs when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

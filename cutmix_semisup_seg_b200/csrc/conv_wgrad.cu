@@ -44,6 +44,7 @@ struct WgradKArgs {
   const float* row_scale;   // per output channel m (folded BN scale), applied before accumulation
   int use5_a, use5_b;       // operand fetched with ONE 5-D TMA per stage (channel count multiple of 32)
   int m_tile_rows;          // 128 (single-CTA kernel) or 256 (CTA-pair kernel)
+  int dbg;                  // debug knob 6 (timing experiments only): 8 = no TMA traffic, 16 = no MMAs
 };
 
 struct UnitInfo {
@@ -136,6 +137,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (a.dbg & 8) { tc::mbar_arrive(&full_bar[stage]); if (++stage == W_STAGES) { stage = 0; phase ^= 1; } continue; }
             tc::mbar_expect_tx(&full_bar[stage], tx);
             uint8_t* sa = smem_a + stage * W_A_STAGE_BYTES;
             uint8_t* sb = smem_b + stage * W_B_STAGE_BYTES;
@@ -185,7 +187,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             tc::tc_fence_after();
             const uint32_t a_addr = tc::smem_u32(smem_a + stage * W_A_STAGE_BYTES);
             const uint32_t b_addr = tc::smem_u32(smem_b + stage * W_B_STAGE_BYTES);
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
               const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
               const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
               tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
@@ -359,6 +361,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
           const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (a.dbg & 8) { if (leader) tc::mbar_arrive(&full_bar[stage]); if (++stage == W2_STAGES) { stage = 0; phase ^= 1; } continue; }
             if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
             w2_tma_load_5d(smem_a + stage * W2_A_STAGE_BYTES, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0,
                            (ui.m0 + (int)rank * W_BLOCK_M) / 32);
@@ -394,7 +397,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
             tc::tc_fence_after();
             const uint32_t a_addr = tc::smem_u32(smem_a + stage * W2_A_STAGE_BYTES);
             const uint32_t b_addr = tc::smem_u32(smem_b + stage * W2_B_STAGE_BYTES);
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
               const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
               const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
               w2_mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
@@ -467,6 +470,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_split
 }
 
 int g_wgrad_desc_variant = 0;
+int g_wgrad_dbg = 0;              // b2_debug_set(6, v)
 int g_wgrad_force_1cta = 0;       // b2_debug_set(5, 1): always the single-CTA kernel
 
 struct WPlan {
@@ -552,6 +556,7 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   a.slab_elems = (int64_t)p->m * p->tw * p->c;
   a.accumulate = p->accumulate;
   a.desc_variant = g_wgrad_desc_variant;
+  a.dbg = g_wgrad_dbg;
   a.row_scale = p->row_scale;
   *out = a;
   return B2_OK;
@@ -564,6 +569,7 @@ extern int g_conv_epi_debug;
 extern int g_conv_pf_max_k;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 5) g_wgrad_force_1cta = value;
+  if (key == 6) g_wgrad_dbg = value;
   if (key == 1) g_wgrad_desc_variant = value;
   if (key == 2) g_conv_force_1cta = value;
   if (key == 3) g_conv_epi_debug = value;

@@ -62,10 +62,18 @@ class Tape(object):
         self.nodes.append(node)
 
     # ---------------------------------------------------------------- gradient accumulation
+    @staticmethod
+    def _new_grad(t):
+        """Fresh gradient buffer for t: its pre-assigned home (batch slices, see batch_split) or a new allocation."""
+        return t.grad_home if t.grad_home is not None else t.like()
+
     def _finish(self, t, fused_gate):
+        if t.pending == 0 and t.grad_home is not None and t.grad is not None and t.grad is not t.grad_home:
+            self.K.copy_act(t.grad_home, t.grad)         # (aliased residual gradient: move it home)
+            t.grad, t.grad_owned = t.grad_home, True
         if t.pending == 0 and t.gate_on_grad and not fused_gate and t.grad is not None:
             if not t.grad_owned:
-                owned = t.like()
+                owned = self._new_grad(t)
                 self.K.copy_act(owned, t.grad)
                 t.grad, t.grad_owned = owned, True
             self.K.relu_gate(t.grad, t)
@@ -95,7 +103,7 @@ class Tape(object):
             fused_gate = gate is not None
             want = self._stats_request(t) if fused_gate else None
             if t.grad is None:
-                dst = t.like()
+                dst = self._new_grad(t)
                 st = launch(dst, False, None, gate, want)
             elif t.grad_owned and not last:
                 dst = t.grad
@@ -104,18 +112,18 @@ class Tape(object):
                 dst = t.grad
                 st = launch(dst, False, dst, gate, want)   # epilogue reads the partial before overwriting it
             else:
-                dst = t.like()
+                dst = self._new_grad(t)
                 st = launch(dst, False, t.grad, gate, want)
             t.grad, t.grad_owned = dst, True
             t.fused_stats = st if want is not None else None
         else:
             if t.grad is None:
-                dst = t.like()
+                dst = self._new_grad(t)
                 launch(dst, False, None, None, None)
                 t.grad, t.grad_owned = dst, True
             else:
                 if not t.grad_owned:
-                    owned = t.like()
+                    owned = self._new_grad(t)
                     self.K.copy_act(owned, t.grad)
                     t.grad, t.grad_owned = owned, True
                 launch(t.grad, True, None, None, None)
@@ -130,7 +138,7 @@ class Tape(object):
         elif t.grad_owned:
             self.K.copy_act(t.grad, g, accumulate=True)
         else:
-            owned = t.like()
+            owned = self._new_grad(t)
             self.K.copy_act(owned, t.grad)
             self.K.copy_act(owned, g, accumulate=True)
             t.grad, t.grad_owned = owned, True
@@ -362,7 +370,62 @@ class BcastNode(object):
         tape.contribute_tensor(self.v, dv)
 
 
+class BatchSplitNode(object):
+    """parts[i] = x[n_i : n_i + sizes[i]] (views).  Backward: the parts' gradients are batch slices of ONE buffer
+    (their `grad_home`), which is handed to x as a single contribution -- no concatenation copy."""
+
+    def __init__(self, x, parts, gbuf):
+        self.x, self.parts, self.gbuf = x, parts, gbuf
+
+    def backward(self, tape):
+        K = tape.K
+        any_grad = False
+        for p in self.parts:
+            if p.grad is None:
+                K.fill_act(p.grad_home, 0.0)             # nobody consumed this part
+            else:
+                any_grad = True
+                if p.grad is not p.grad_home:
+                    K.copy_act(p.grad_home, p.grad)
+            p.grad = None
+            p.grad_home = None
+            p.node = None
+        if not any_grad:
+            tape.skip(self.x)
+            return
+        tape.contribute_tensor(self.x, self.gbuf)
+
+
 # ====================================================================================== forward ops
+def batch_split(tape, x, sizes, delegate_gate=False):
+    """Split a root activation along the batch dimension into independent root activations (views).  Used to run the
+    batch-invariant (frozen-BN) part of a network ONCE over several mini-batches and the batch-dependent head
+    (train-mode BatchNorm) per mini-batch.  `delegate_gate`: x has no other consumer, so the ReLU gate of its gradient
+    is applied by the epilogues that finish the parts' gradients instead of a separate pass over x.grad."""
+    assert x.parent is None and sum(sizes) == x.n
+    parts, n0 = [], 0
+    for n in sizes:
+        parts.append(x.batch_slice(n0, n, name=x.name + '[{}:{}]'.format(n0, n0 + n)))
+        n0 += n
+    if not tape.enabled:
+        return parts
+    gbuf = x.like()
+    n0 = 0
+    for p, n in zip(parts, sizes):
+        p.grad_home = gbuf.batch_slice(n0, n)
+        n0 += n
+    if delegate_gate and x.gate_on_grad:
+        assert x.pending == 0, 'gate delegation needs the split to be the only consumer'
+        x.gate_on_grad = False
+        for p in parts:
+            p.gate_on_grad = True
+    node = BatchSplitNode(x, parts, gbuf)
+    for p in parts:
+        p.node = node
+    tape.record(node, [x])
+    return parts
+
+
 def _conv_out_hw(h, w, k, stride, pad, dil):
     return ((h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1)
 

@@ -33,6 +33,14 @@ class _RunState(object):
         self.tape, self.low, self.align, self.consumed = tape, low, align, False
 
 
+class _MultiRunState(object):
+    """Recorded multi-batch pass (b2_forward_multi): one tape, one (low-res logits, align_corners) per mini-batch."""
+    __slots__ = ('tape', 'lows', 'consumed')
+
+    def __init__(self, tape, lows):
+        self.tape, self.lows, self.consumed = tape, lows, False
+
+
 class _B2Function(torch.autograd.Function):
     """Bridges torch.autograd to the engine tape for drop-in use (`loss.backward()` on any loss built
     from the returned logits).  Parameter gradients are written straight into `p.grad`."""
@@ -62,9 +70,34 @@ class B2SegNet(nn.Module):
         return {'tf32': 1, '3xtf32': 3, '4xtf32': 4}[self.b2_precision]
 
     # ---- subclasses define the graph --------------------------------------------------------
+    # The graph is given in two parts: a TRUNK (the ResNet-101 backbone; DeepLab v2: the whole network) and a HEAD.  With
+    # frozen BatchNorm the trunk is batch-invariant (every sample is processed independently), so the training step
+    # runs it ONCE over the concatenation of several mini-batches (b2_forward_multi) -- bigger GEMMs, half the
+    # launches, no partial last wave on the 256-channel layers -- while the head (train-mode BatchNorm statistics,
+    # dropout; DeepLab v3+) runs per mini-batch exactly as in the reference.
+    def _graph_trunk(self, tape, x, in_h, in_w):
+        """Run the trunk on `x` (Act, NHWC, ld 4); return [(feature Act, split_is_only_consumer), ...]."""
+        raise NotImplementedError
+
+    def _graph_head(self, tape, feats, in_h, in_w):
+        """Run the head on the trunk features; return (low-res logits Act, align_corners)."""
+        raise NotImplementedError
+
+    def _trunk_module(self):
+        raise NotImplementedError
+
     def _graph(self, tape, x, in_h, in_w):
         """Run the network on `x` (Act, NHWC, ld 4); return (low-res logits Act, align_corners)."""
-        raise NotImplementedError
+        feats = self._graph_trunk(tape, x, in_h, in_w)
+        return self._graph_head(tape, [f for f, _ in feats], in_h, in_w)
+
+    def b2_trunk_is_batch_invariant(self):
+        """True when no layer of the trunk mixes samples: every BatchNorm in eval mode (frozen), no active dropout."""
+        for m in self._trunk_module().modules():
+            name = type(m).__name__
+            if m.training and ('BatchNorm' in name or ('Dropout' in name and getattr(m, 'p', 0) > 0)):
+                return False
+        return True
 
     # ---- explicit API used by the fused training step ---------------------------------------
     def b2_forward(self, x, record):
@@ -85,6 +118,52 @@ class B2SegNet(nn.Module):
             tape.discard()
             return logits, None
         return logits, _RunState(tape, low, align)
+
+    def b2_forward_multi(self, xs, record):
+        """Several mini-batches [(N_i,3,H,W)] of the same spatial size in one pass: the batch-invariant trunk runs once
+        over their concatenation, the head once per mini-batch, in list order (so BatchNorm running statistics and
+        dropout draws advance exactly as in consecutive `b2_forward` calls).  Returns ([logits_i], state)."""
+        if not self.b2_trunk_is_batch_invariant():
+            raise RuntimeError('b2_forward_multi needs a batch-invariant trunk (call freeze_batchnorm() first)')
+        K = get_kernels(self._n_split())
+        for x in xs:
+            if x.dim() != 4 or x.shape[1] != 3 or x.shape[2:] != xs[0].shape[2:]:
+                raise ValueError('expected (N,3,H,W) image batches of one spatial size')
+            if K.name == 'cuda' and not x.is_cuda:
+                raise RuntimeError('B200 network received a CPU tensor: there is no CPU fallback')
+        sizes = [int(x.shape[0]) for x in xs]
+        x_all = torch.cat([x.detach().to(torch.float32) for x in xs], dim=0)
+        in_h, in_w = x_all.shape[2], x_all.shape[3]
+        tape = E.Tape(K, enabled=record)
+        xin = K.nchw_to_act(x_all, 4)
+        xin.needs_grad = False
+        feats = self._graph_trunk(tape, xin, in_h, in_w)
+        split = [E.batch_split(tape, f, sizes, delegate_gate=only) for f, only in feats]
+        logits, lows = [], []
+        for i in range(len(xs)):
+            low, align = self._graph_head(tape, [parts[i] for parts in split], in_h, in_w)
+            logits.append(E.to_logits_nchw(tape, low, in_h, in_w, align))
+            lows.append((low, align))
+        if not record:
+            tape.discard()
+            return logits, None
+        return logits, _MultiRunState(tape, lows)
+
+    def b2_backward_multi(self, state, dlogits_list, scale_devs=None):
+        """Backward of b2_forward_multi: one d(loss_i)/d(logits_i) (NCHW, optionally times a device scalar) per
+        mini-batch; parameter gradients accumulate into .grad as the sum over the mini-batches."""
+        if state is None or state.consumed:
+            raise RuntimeError('this forward pass was not recorded or has already been back-propagated')
+        state.consumed = True
+        if scale_devs is None:
+            scale_devs = [None] * len(dlogits_list)
+        assert len(dlogits_list) == len(state.lows) == len(scale_devs)
+        for (low, align), dl, sc in zip(state.lows, dlogits_list, scale_devs):
+            E.seed_output_grad(state.tape, low, dl, align, scale_dev=sc)
+        state.tape.backward()
+        for low, _ in state.lows:
+            low.grad = None
+        state.tape, state.lows = None, None
 
     def b2_backward(self, state, dlogits, scale_dev=None, scale_host=1.0):
         """Back-propagate d(loss)/d(logits) (NCHW, optionally to be multiplied by a device scalar) into

@@ -101,7 +101,7 @@ def average_gradients(flat, dist, group=None):
 class MeanTeacherStep(object):
     def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
                  cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True, use_cuda_graph=False):
+                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True, use_cuda_graph=False, batch_trunk=True):
         self.student_net, self.teacher_net = student_net, teacher_net
         self.student_optim, self.teacher_optim = student_optim, teacher_optim
         self.mask_generator = mask_generator
@@ -122,6 +122,9 @@ class MeanTeacherStep(object):
         # host-bound: profiles/r01_v2_*).  Two graphs: forward/backward/losses, and optimiser + EMA, with the
         # gradient all-reduce between them.
         self.use_cuda_graph = use_cuda_graph
+        # run the frozen-BN trunk once per network and iteration over the concatenated mini-batches (see
+        # netbase.B2SegNet.b2_forward_multi); falls back to the reference's pass-by-pass order when BatchNorm is not frozen
+        self.batch_trunk = batch_trunk
         self._graph = None
         self.launches_per_replay = 0
 
@@ -175,6 +178,43 @@ class MeanTeacherStep(object):
                                    self.conf_per_pixel, ramp, self.cons_weight)
         self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])
         return out4
+
+    def _can_batch_trunk(self, unsup_batches):
+        return (self.batch_trunk and self.cons_weight > 0.0 and len(unsup_batches) == 1 and
+                self.teacher_net is not self.student_net and
+                hasattr(self.student_net, 'b2_forward_multi') and hasattr(self.teacher_net, 'b2_forward_multi') and
+                self.student_net.b2_trunk_is_batch_invariant() and self.teacher_net.b2_trunk_is_batch_invariant())
+
+    def _fwd_bwd_batched(self, sup_batch, ub, ramp_val):
+        """The same iteration with the batch-invariant trunks run once per network: student on [labelled ; mixed]
+        images, teacher on [view 0 ; view 1].  Per-sample arithmetic, head BatchNorm statistics / dropout order and the
+        losses are those of `supervised` + `unsupervised_mix` / `unsupervised_cut`; parameter gradients are summed by one
+        backward pass instead of two accumulating ones (same sums, different fp32 association)."""
+        be = self.be
+        batch_x, batch_y = sup_batch
+        if self.mask_mix:
+            ux_stu = ub['ux0_stu']
+            masks = self.mask_generator.torch_masks_from_params(ub['mask_params'], ux_stu.shape[2:4], ux_stu.device).contiguous()
+            ux_in = be.mix(ux_stu, ub['ux1_stu'], masks)                   # :350
+            loss_mask = be.mix(ub['um0'], ub['um1'], masks)                # :351
+        else:
+            ux_stu = ub['ux_stu']
+            masks = self.mask_generator.torch_masks_from_params(ub['mask_params'], ux_stu.shape[2:4], ux_stu.device).contiguous()
+            ux_in = be.mix(ux_stu, None, masks)                            # :389
+            loss_mask = be.mix(ub['um'], None, masks)                      # :401
+        (sup_logits, ls), state = self.student_net.b2_forward_multi([batch_x, ux_in], record=True)   # :299, :358 / :395
+        with torch.no_grad():                                              # :354-356 / :393
+            if self.mask_mix:
+                (l0, l1), _ = self.teacher_net.b2_forward_multi([ub['ux0_tea'], ub['ux1_tea']], record=False)
+            else:
+                l0, l1 = self.teacher_net.b2_forward(ub['ux_tea'], record=False)[0], None
+        labels = batch_y[:, 0] if batch_y.dim() == 4 else batch_y
+        out3, dsup = be.cross_entropy(sup_logits, labels.contiguous(), ignore_index=255)        # :300
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.consistency(l0, l1, ls, masks if self.mask_mix else None, loss_mask, self.cons_loss_fn,
+                                   self.conf_thresh, self.conf_per_pixel, ramp, self.cons_weight)
+        self.student_net.b2_backward_multi(state, [dsup, dls], [out3[2:3], out4[2:3]])          # :301, :459
+        return {'sup_loss': out3[0], 'cons_loss': out4[0], 'conf_rate': out4[1]}
 
     def _capture(self, sup_batch, unsup_batches, ramp_val):
         dev = sup_batch[0].device if sup_batch[0].is_cuda else next(self.student_net.parameters()).device
@@ -257,6 +297,8 @@ class MeanTeacherStep(object):
         from . import engine
         engine.invalidate_caches()       # derived weights (BN folds, dgrad transposes) are rebuilt once per iteration
         self._zero_grad()                                              # :290
+        if self._can_batch_trunk(unsup_batches):
+            return self._fwd_bwd_batched(sup_batch, unsup_batches[0], ramp_val)
         sup_loss = self.supervised(*sup_batch)
         cons, conf = None, None
         if self.cons_weight > 0.0:

@@ -141,3 +141,64 @@ def test_eval_mode_forward_has_no_tape(emu):
     with torch.no_grad():
         y = net(torch.randn(1, 3, 17, 17))
     assert y.shape == (1, 3, 17, 17) and not y.requires_grad
+
+
+@pytest.mark.parametrize('kind,classes', [('resnet101_deeplabv3plus_imagenet', 5), ('resnet101_deeplab_imagenet', 4)])
+def test_multi_batch_trunk_equals_consecutive_passes(emu, kind, classes):
+    """b2_forward_multi / b2_backward_multi (frozen trunk once over [x1 ; x2], head per mini-batch) must give the logits,
+    parameter gradients, BatchNorm running statistics and dropout draws of two consecutive forward/backward passes."""
+    sizes, h, w = (2, 3), 33, 25
+    torch.manual_seed(7)
+    xs = [torch.randn(n, 3, h, w) for n in sizes]
+    dys = [torch.randn(n, classes, h, w) for n in sizes]
+    masks = [(torch.rand(n, -(-h // 8), -(-w // 8), 256) > 0.5).float() for n in sizes]
+
+    def make():
+        net = na.seg.get(kind)(classes, pretrained=False)
+        net.load_state_dict(TO.synth_state_dict(net.state_dict(), seed=11))
+        net.train(); net.freeze_batchnorm()
+        for m in net.modules():
+            if type(m).__name__ == 'B2Dropout':
+                m.inject([m_.clone() for m_ in masks])
+        return net
+
+    seq = make()
+    ys = []
+    for x, dy in zip(xs, dys):
+        y = seq(x)
+        y.backward(dy)
+        ys.append(y.detach())
+    multi = make()
+    assert multi.b2_trunk_is_batch_invariant()
+    n_conv0 = emu.calls.count('conv_fwd')
+    with torch.no_grad():                    # (the engine never relies on autograd; the emulation uses torch ops)
+        logits, state = multi.b2_forward_multi(xs, record=True)
+        n_conv = emu.calls.count('conv_fwd') - n_conv0
+        multi.b2_backward_multi(state, dys)
+    for a, b in zip(logits, ys):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+    sd_s, sd_m = seq.state_dict(), multi.state_dict()
+    for k in sd_s:
+        if 'running' in k or 'num_batches' in k:
+            assert torch.allclose(sd_s[k].double(), sd_m[k].double(), rtol=1e-5, atol=1e-7), k
+    ps, pm = dict(seq.named_parameters()), dict(multi.named_parameters())
+    worst = 0.0
+    for k, p in ps.items():
+        if p.grad is None:
+            assert pm[k].grad is None, k
+            continue
+        assert pm[k].grad is not None, 'missing gradient for ' + k
+        err = (pm[k].grad - p.grad).abs().max().item() / (p.grad.abs().max().item() + 1e-30)
+        worst = max(worst, err)
+    assert worst < 2e-3, worst
+    if 'v3plus' in kind:
+        assert n_conv == 104 + 2 * 10        # 104 trunk convolutions once, 10 head convolutions per mini-batch
+    else:
+        assert n_conv == 106                 # DeepLab v2: the whole network is the trunk
+
+
+def test_multi_batch_needs_frozen_trunk(emu):
+    net = na.seg.get('resnet101_deeplabv3plus_imagenet')(3, pretrained=False)
+    net.train()
+    with pytest.raises(RuntimeError):
+        net.b2_forward_multi([torch.randn(1, 3, 17, 17)] * 2, record=False)

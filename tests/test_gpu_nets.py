@@ -119,8 +119,10 @@ def test_full_resnet101_3xtf32(kind, classes, shape):
     assert stat < 1e-3
 
 
-def test_training_iteration_matches_oracle_and_reference_golden():
-    """Three full iterations (DeepLab v2, frozen BN, CutMix var loss, Adam with the duplicated group, EMA) on the GPU
+@pytest.mark.parametrize('batch_trunk', [True, False])
+def test_training_iteration_matches_oracle_and_reference_golden(batch_trunk):
+    """(batch_trunk: the frozen trunk runs once per network over the concatenated mini-batches, or pass by pass in the
+    reference's order.)  Three full iterations (DeepLab v2, frozen BN, CutMix var loss, Adam with the duplicated group, EMA) on the GPU
     vs the oracle's CPU iterations (which tests/test_oracle_golden.py pins to the reference): losses within 1e-4
     relative (3xTF32), identical confidence decisions up to 2e-3, teacher/student state within 1e-5 of range."""
     from cutmix_semisup_seg_b200 import step as step_mod, synthetic
@@ -141,7 +143,7 @@ def test_training_iteration_matches_oracle_and_reference_golden():
     ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
     student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
     mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
-    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, conf_thresh=0.5)
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, conf_thresh=0.5, batch_trunk=batch_trunk)
     orc = ref_step.OracleMeanTeacher('deeplab2', sd, lr, conf_thresh=0.5)
     for it in range(3):
         sup = synthetic.make_sup_batch(n, h, w, c, 10 + it)
@@ -162,3 +164,51 @@ def test_training_iteration_matches_oracle_and_reference_golden():
         # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr (3e-5, i.e.
         # ~3e-4 of the weight range); everything else agrees to ~1e-6
         assert worst < 1.5e-3, (name, worst)
+
+
+@pytest.mark.parametrize('mask_mix', [True, False])
+def test_batched_trunk_iteration_equals_pass_by_pass(mask_mix):
+    """DeepLab v3+ (frozen backbone, train-mode head BatchNorm, active dropout): running the backbone once over
+    [labelled ; mixed] (student) and [view 0 ; view 1] (teacher) must reproduce the pass-by-pass iteration -- same
+    losses and confidence rate (the forward arithmetic per sample is identical), same BatchNorm running statistics and
+    dropout draws, parameter updates equal up to the fp32 association of the gradient sums."""
+    import copy
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    kind, n, h, w, c = 'resnet101_deeplabv3plus_imagenet', 2, 64, 64, 19
+    net = na.seg.get(kind)(c, pretrained=False)
+    final = [k for k in net.state_dict() if 'classifier.classifier.6' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(net.state_dict(), seed=9, logit_gain=4.0, final_keys=final)
+    runs = []
+    for batch_trunk in (False, True):
+        student = na.seg.get(kind)(c, pretrained=False)
+        student.load_state_dict(copy.deepcopy(sd))
+        teacher = na.seg.get(kind)(c, pretrained=False)
+        student.to(dev); teacher.to(dev)
+        student.b2_precision = teacher.b2_precision = '3xtf32'
+        for p in teacher.parameters():
+            p.requires_grad = False
+        optim = step_mod.make_optimizer(student, 'adam', 1e-5)
+        ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+        student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+        mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
+        tr = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, conf_thresh=0.5, mask_mix=mask_mix,
+                                      batch_trunk=batch_trunk)
+        assert tr._can_batch_trunk([None]) == batch_trunk
+        losses = []
+        for it in range(2):
+            sup = synthetic.make_sup_batch(n, h, w, c, 50 + it, device=dev)
+            uns = synthetic.make_unsup_batch(n, h, w, 60 + it, mg, mask_mix=mask_mix, device=dev)
+            out = tr.step(sup, [uns])
+            losses.append([float(out['sup_loss']), float(out['cons_loss']), float(out['conf_rate'])])
+        runs.append((losses, {k: v.detach().cpu().clone() for k, v in student.state_dict().items()},
+                     {k: v.detach().cpu().clone() for k, v in teacher.state_dict().items()}))
+    (l_seq, s_seq, t_seq), (l_bat, s_bat, t_bat) = runs
+    assert l_seq[0] == pytest.approx(l_bat[0], rel=1e-6, abs=1e-9)         # first iteration: identical forward passes
+    assert l_seq[1] == pytest.approx(l_bat[1], rel=2e-3, abs=1e-6)         # second: after one (re-associated) update
+    for ref, got in ((s_seq, s_bat), (t_seq, t_bat)):
+        for k, r in ref.items():
+            if r.dtype == torch.float32:
+                scale = r.abs().max().item() + 1e-12
+                assert (got[k] - r).abs().max().item() / scale < 1.5e-3, k
+            else:
+                assert torch.equal(got[k], r), k

@@ -171,6 +171,31 @@ if __name__ == '__main__':
         # ragged case: odd spatial size, channel tail (nb % 32 != 0), batch 3
         n, h, w = 3, 33, 41
         flavours(96, 304, 1, 1, 'ragged 1x1 96->304')
+    if which == 'iso':
+        # pipeline isolation (timing experiments, results are garbage): conv knob 3 / wgrad knob 6, bit 8 = producer
+        # skips the TMA loads, bit 16 = issuer skips the MMAs.  full ~ max(parts): bound by that part; full ~ sum: latency.
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        for (n, h, w, cin, cout, k, dil, name) in ((16, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256'),
+                                                   (16, 64, 64, 1024, 256, 1, 1, 'layer3 1x1 1024->256'),
+                                                   (16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256')):
+            pad = dil * (k // 2)
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            wt = torch.randn(cout, k * k, cin, device=dev) * 0.01
+            y = Act.alloc(n, h, w, cout, dev)
+            dw = torch.zeros(cout, k * k, cin, device=dev)
+            fl = 2.0 * n * h * w * cin * cout * k * k
+            for dbg in (0, 8, 16, 24):
+                L.b2_debug_set(3, dbg)
+                timeit(lambda: K.conv_fwd(x, wt, cout, k, k, cin, cin, 1, pad, dil, y), fl, name + ' fprop [dbg={}]'.format(dbg))
+            L.b2_debug_set(3, 0)
+            for force1 in (1, 0):
+                L.b2_debug_set(5, force1)
+                for dbg in (0, 8, 16, 24):
+                    L.b2_debug_set(6, dbg)
+                    timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), fl, name + ' wgrad [2cta={} dbg={}]'.format(1 - force1, dbg))
+            L.b2_debug_set(6, 0); L.b2_debug_set(5, 0)
     if which == 'wg2':
         # weight-gradient kernel: single-CTA vs CTA-pair build (debug knob 5) on the hot-path shapes, with a bit-level
         # comparison of the two results (same K order per accumulator => expected identical up to the split count)

@@ -28,6 +28,8 @@ def timeit(name, nbytes, fn):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         if i > 0:
             ts.append(e0.elapsed_time(e1))
+    if not ts:
+        return                                     # reps == 0: single untimed call (ncu captures)
     ms = sorted(ts)[len(ts) // 2]
     print('{:<46s} {:8.3f} ms  {:8.1f} GB/s  ({:.0f} MB)'.format(name, ms, nbytes / ms / 1e6, nbytes / 1e6), flush=True)
 
@@ -72,6 +74,10 @@ mk = (torch.rand((N, 1, 512, 512), device=dev) > 0.5).float(); um = torch.ones_l
 dls = torch.empty_like(ls)
 timeit('consistency var 19ch 512^2', 4 * l0.numel() * 4 + 2 * mk.numel() * 4,
        lambda: be.consistency(l0, l1, ls, mk, um, 'var', 0.97, False, 1.0, 1.0, dls=dls))
+l0p, l1p, lsp = l0 * 40.0, l1 * 40.0, ls * 40.0          # peaked logits (the bench's conditioned classifier): p == 0 for most classes
+timeit('consistency var 19ch 512^2 peaked x40', 4 * l0.numel() * 4 + 2 * mk.numel() * 4,
+       lambda: be.consistency(l0p, l1p, lsp, mk, um, 'var', 0.97, False, 1.0, 1.0, dls=dls))
+del l0p, l1p, lsp
 lab = torch.randint(0, 19, (N, 512, 512), device=dev)
 timeit('cross entropy 19ch 512^2', 2 * l0.numel() * 4 + lab.numel() * 8, lambda: be.cross_entropy(l0, lab, dlogits=dls))
 # gate / copies / pooling
@@ -100,3 +106,13 @@ timeit('bn wdot from epilogue stats c1024', stats[0].numel() * 4 + 2 * W.numel()
 timeit('bn wdot from g (colsum) c1024', gact.base.numel() * 4, lambda: K.bn_eval_param_grad_wdot(None, gact, W, gW, bn, dgam, dbet, True))
 w3 = torch.randn(256, 9, 256, device=dev)
 timeit('transpose_w 256x9x256', 2 * w3.numel() * 4, lambda: K.transpose_w(w3, 256, 9, 256))
+# CutMix image / valid-mask mix (X1), box-mask rasterisation (M2), fused multi-tensor EMA over the DeepLab v3+ state (E1)
+import numpy as np  # noqa: E402
+x0 = torch.randn((N, 3, 512, 512), device=dev); x1 = torch.randn_like(x0)
+timeit('mix image 3ch 512^2', 3 * x0.numel() * 4 + mk.numel() * 4, lambda: be.mix(x0, x1, mk))
+timeit('mix valid-mask 1ch 512^2', 4 * mk.numel() * 4, lambda: be.mix(um, um, mk))
+boxes = torch.from_numpy(np.tile(np.array([[[100, 120, 400, 380]]], dtype=np.int32), (N, 1, 1))).to(dev)
+timeit('box mask rasterise 512^2', mk.numel() * 4, lambda: be.box_mask_rasterize(boxes, 512, 512, 0.0))
+n_state = 59453331                      # float32 state elements of DeepLab v3+
+t_flat = torch.randn(n_state, device=dev); s_flat = torch.randn(n_state, device=dev)
+timeit('EMA flat 59.45M elems', 12 * n_state, lambda: be.ema_step_flat(t_flat, s_flat, 0.99))
