@@ -104,7 +104,8 @@ def build_trainer(cfg, device, dist_on, use_graph=True):
     teacher = Net(cfg['classes'], pretrained=False).to(device)
     for p in teacher.parameters():
         p.requires_grad = False
-    optim = step_mod.make_optimizer(student, 'adam', cfg['lr'], capturable=use_graph)
+    optim = step_mod.make_optimizer(student, 'adam', cfg['lr'], capturable=use_graph,
+                                    fused_kernel=os.environ.get('B200SEG_FUSED_OPT', '1') != '0')
     ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
     student.train(); teacher.train()
     student.freeze_batchnorm(); teacher.freeze_batchnorm()         # every reference recipe uses --freeze_bn

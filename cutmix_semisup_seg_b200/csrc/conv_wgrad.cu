@@ -163,7 +163,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, 1, 1);
+      // (debug knob 6 bits 32 / 64, timing only, garbage results: pretend A / B are K-major SWIZZLE_128B operands)
+      const bool a_k = a.dbg & 32, b_k = a.dbg & 64;
+      const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, a_k ? 0 : 1, b_k ? 0 : 1);
       // MN-major tf32: SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B).  LBO = stride between the
       // 32-channel column blocks (one TMA box each), SBO = stride between 4-row groups along K.
       const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
@@ -188,8 +190,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
             const uint32_t a_addr = tc::smem_u32(smem_a + stage * W_A_STAGE_BYTES);
             const uint32_t b_addr = tc::smem_u32(smem_b + stage * W_B_STAGE_BYTES);
             for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
-              const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
-              const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t adesc = a_k ? tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024) : tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t bdesc = b_k ? tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024) : tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
               tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -375,7 +377,8 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = tc::make_idesc_tf32(2 * W_BLOCK_M, a.block_n, 1, 1);
+      const bool a_k = a.dbg & 32, b_k = a.dbg & 64;        // timing-only majorness flips, see the single-CTA kernel
+      const uint32_t idesc = tc::make_idesc_tf32(2 * W_BLOCK_M, a.block_n, a_k ? 0 : 1, b_k ? 0 : 1);
       const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
       const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
       int stage = 0; uint32_t phase = 0;
@@ -398,8 +401,8 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
             const uint32_t a_addr = tc::smem_u32(smem_a + stage * W2_A_STAGE_BYTES);
             const uint32_t b_addr = tc::smem_u32(smem_b + stage * W2_B_STAGE_BYTES);
             for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
-              const uint64_t adesc = tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
-              const uint64_t bdesc = tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t adesc = a_k ? tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024) : tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
+              const uint64_t bdesc = b_k ? tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024) : tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
               w2_mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }

@@ -68,6 +68,9 @@ _SIGS = {
     'b2_num_sms': (c_int, []),
     'b2_ema_step': (c_int, [c_vp, c_i64, c_f32, c_f32, c_vp]),
     'b2_ema_step_flat': (c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]),
+    'b2_opt_ema_step': (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, ctypes.c_double, ctypes.c_double, c_f32, c_f32, c_f32, c_int,
+                                c_int, c_f32, c_f32, c_vp]),
+    'b2_argmax_confusion': (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'b2_box_mask_rasterize': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp]),
     'b2_mix': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     'b2_consistency_num_partials': (c_i64, [c_int, c_i64]),

@@ -90,6 +90,19 @@ class CudaBackend(object):
         one_minus_alpha = 1.0 - alpha
         self._call('b2_ema_step', table.data_ptr(), n_chunks, alpha, one_minus_alpha, self._s())
 
+    def argmax_confusion(self, logits, labels, cm, ignore_value=255, want_pred=False):
+        """cm (C*C int64, device) += confusion matrix of argmax(logits) vs labels; optionally returns the argmax map."""
+        L.require_cuda(logits, labels, cm)
+        n, c, h, w = logits.shape
+        logits = logits.contiguous()
+        if labels is not None:
+            labels = labels.reshape(n, h, w).contiguous()
+            assert labels.dtype == torch.int64
+        pred = torch.empty((n, h, w), device=logits.device, dtype=torch.int64) if want_pred else None
+        self._call('b2_argmax_confusion', logits.data_ptr(), L.ptr(labels), n, c, h * w,
+                   -1 if ignore_value is None else int(ignore_value), L.ptr(cm), L.ptr(pred), self._s())
+        return pred
+
     def box_mask_rasterize(self, boxes, h, w, init):
         """boxes: int32 CUDA tensor (N, B, 4) [y0,y1,x0,x1) -> (N,1,H,W) fp32."""
         L.require_cuda(boxes)

@@ -57,7 +57,7 @@ class FlatGrads(object):
 
 
 def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4,
-                   capturable=False):
+                   capturable=False, fused_kernel=False):
     """torch.optim optimiser on the reference's parameter groups (train_seg_semisup_mask_mt.py:90-100): group 0 =
     `pretrained_parameters()` at 0.1 x lr, group 1 = `new_parameters()` at lr.  DeepLab v2's group 0 repeats tensors
     (reference quirk): a tensor listed k times must receive k sequential updates per step, which only the
@@ -66,6 +66,17 @@ def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_n
     import warnings
     g0 = list(student_net.pretrained_parameters())
     g1 = list(student_net.new_parameters())
+    if fused_kernel:
+        # ONE sm_100a launch for the optimiser step (+ the teacher's EMA step when MeanTeacherStep pairs them), with the
+        # k-sequential-updates rule for duplicated entries implemented in the kernel (cutmix_semisup_seg_b200/optim.py)
+        from .optim import FusedOptimizer
+        groups = [dict(params=g0, lr=learning_rate * 0.1), dict(params=g1, lr=learning_rate)]
+        if opt_type == 'adam':
+            return FusedOptimizer(groups, 'adam', lr=learning_rate)
+        if opt_type == 'sgd':
+            return FusedOptimizer(groups, 'sgd', lr=learning_rate, momentum=sgd_momentum, nesterov=sgd_nesterov,
+                                  weight_decay=sgd_weight_decay)
+        raise ValueError('Unknown opt_type {}'.format(opt_type))
     dup = len(set(id(p) for p in g0 + g1)) != len(g0) + len(g1)
     groups = [dict(params=g0, lr=learning_rate * 0.1), dict(params=g1, lr=learning_rate)]
     on_cuda = all(p.is_cuda for p in g0 + g1)
@@ -313,6 +324,9 @@ class MeanTeacherStep(object):
         return {'sup_loss': sup_loss, 'cons_loss': cons, 'conf_rate': conf}
 
     def _opt_ema(self):
+        if getattr(self.student_optim, 'b2_fused', False):
+            self.student_optim.step(ema=self.teacher_optim)            # :465-467 in one launch
+            return
         self.student_optim.step()                                      # :465
         if self.teacher_optim is not None:
             self.teacher_optim.step()                                  # :466-467
@@ -332,6 +346,8 @@ class MeanTeacherStep(object):
             g1, g2, out = self._graph[0], self._graph[1], self._graph[2]
             g1.replay()
             self._allreduce()
+            if hasattr(self.student_optim, 'refresh_lr'):
+                self.student_optim.refresh_lr()        # the captured step re-reads the learning rates from pinned memory
             g2.replay()
             self.be.launches += self.launches_per_replay
             return out

@@ -1,5 +1,7 @@
-"""mIoU evaluation with the reference's semantics (evaluation.py:6-62): per-sample intersection / union counts
-accumulated on the CPU, `score()` = I / max(U, 1) per class."""
+"""mIoU evaluation with the reference's semantics (evaluation.py:6-62): per-sample intersection / union counts,
+`score()` = I / max(U, 1) per class.  `EvaluatorIoU.sample(truth, prediction)` is the reference's CPU/numpy call;
+`EvaluatorIoU.sample_logits(logits, truth)` (new) takes the network output on the GPU and accumulates the same counts
+with ONE fused argmax + confusion-matrix kernel (b2_argmax_confusion) and no host synchronisation until `score()`."""
 import numpy as np
 
 
@@ -41,5 +43,32 @@ class EvaluatorIoU(object):
         self.union += u
         self.cm += cm
 
+    def sample_logits(self, logits, truth, ignore_value=None):
+        """Device path: logits (N,C,H,W) fp32 CUDA tensor, truth (N,1,H,W) / (N,H,W) int64 CUDA tensor.  Equivalent to
+        `sample(truth[i], argmax(logits[i]))` for every i; counts stay on the device until `score()` / `flush()`."""
+        import torch
+        from cutmix_semisup_seg_b200 import ops
+        if self.fill_holes:
+            raise ValueError('fill_holes needs the CPU path: use sample() on the argmax map')
+        if logits.shape[1] != self.num_classes:
+            raise ValueError('logits have {} classes, evaluator {}'.format(logits.shape[1], self.num_classes))
+        if getattr(self, '_cm_dev', None) is None or self._cm_dev.device != logits.device:
+            self.flush()
+            self._cm_dev = torch.zeros((self.num_classes * self.num_classes,), dtype=torch.int64, device=logits.device)
+        ops.default_backend().argmax_confusion(logits, truth.to(torch.int64), self._cm_dev, ignore_value=ignore_value)
+
+    def flush(self):
+        """Fold the device-side confusion matrix into the numpy accumulators (one D2H copy of C*C integers)."""
+        cm_dev = getattr(self, '_cm_dev', None)
+        if cm_dev is None:
+            return
+        cm = cm_dev.cpu().numpy().reshape(self.num_classes, self.num_classes)
+        self._cm_dev = None
+        diag = np.diag(cm)
+        self.intersection += diag                                   # (pred == c) & (truth == c)
+        self.union += cm.sum(axis=1) + cm.sum(axis=0) - diag         # (pred == c) | (truth == c) over valid pixels
+        self.cm += cm
+
     def score(self):
+        self.flush()
         return self.intersection.astype(float) / np.maximum(self.union.astype(float), 1.0)

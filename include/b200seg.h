@@ -51,6 +51,52 @@ int b2_ema_step_flat(float* tgt, const float* src, int64_t count, float alpha,
                      float one_minus_alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * O1 + E1  Fused optimiser step (student) + EMA step (teacher) -- replaces train_seg_semisup_mask_mt.py:465-467
+ *   (torch.optim.Adam / SGD on the groups built at :90-98, then optim_weight_ema.py:21-25) with ONE launch.
+ *   `table`: DEVICE array, one thread block per entry.  An entry covers <= 8192 consecutive elements of one tensor:
+ *     p  student parameter (updated in place)      g  its gradient
+ *     m  exp_avg (Adam) / momentum buffer (SGD)     v  exp_avg_sq (Adam; unused for SGD)
+ *     t  teacher copy (EMA target; NULL = none)     group  index into lr_groups
+ *     k  how many times the reference's parameter group lists this tensor: the per-tensor loop of torch.optim
+ *        applies k sequential updates per step() with shared state and step += k (DeepLab v2: deeplab2.py:224-230,
+ *        up to k = 4).  k == 0: no optimiser update, EMA only (BatchNorm running statistics: p = student buffer).
+ *   lr_groups: DEVICE doubles (one per group; the LR schedule rewrites them, also between CUDA-graph replays).
+ *   iter_dev:  DEVICE int64, optimiser steps completed so far; incremented by the call (bias corrections use
+ *              step = iter * k + j + 1 for the j-th sequential update).
+ *   algo 0 = Adam(beta1, beta2, eps; no weight decay, no amsgrad: the reference's defaults :91-93),
+ *        1 = SGD(momentum, weight_decay, nesterov; dampening 0: :95-98).
+ *   Arithmetic: fp32, operation order of torch.optim's single-tensor implementations, no FMA contraction; EMA as in
+ *   b2_ema_step (three roundings), applied to the parameter value just written.
+ * ------------------------------------------------------------------------------------------ */
+#define B2_OPT_MAX_K 8
+#define B2_OPT_CHUNK 8192
+typedef struct b2_opt_chunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* t;
+  int32_t count;
+  int16_t group;
+  int16_t k;
+} b2_opt_chunk;
+int b2_opt_ema_step(const b2_opt_chunk* table, int64_t n_chunks, const double* lr_groups, int64_t* iter_dev,
+                    int algo, double beta1, double beta2, float eps, float sgd_momentum, float sgd_weight_decay,
+                    int sgd_nesterov, int do_ema, float ema_alpha, float ema_one_minus_alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation -- replaces the validation loop's argmax + D2H + numpy confusion matrices
+ * (train_seg_semisup_mask_mt.py:484-517, evaluation.py:6-62) with one pass over the logits.
+ *   logits (N,C,H,W) fp32, labels (N,H,W) int64 (`ignore` and out-of-range labels are skipped),
+ *   cm: DEVICE int64 [C*C], ACCUMULATED: cm[truth * C + prediction] += 1 (may be NULL when only pred_out is wanted);
+ *   pred_out: optional (N,H,W) int64 argmax (ties -> lowest class index, like torch.argmax).
+ *   evaluation.EvaluatorIoU's per-class intersection / union follow exactly from cm:
+ *   I[c] = cm[c][c], U[c] = sum_p cm[c][p] + sum_t cm[t][c] - cm[c][c].
+ * ------------------------------------------------------------------------------------------ */
+int b2_argmax_confusion(const float* logits, const int64_t* labels, int n, int c, int64_t hw, int64_t ignore,
+                        int64_t* cm, int64_t* pred_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * M1/M2  Box mask rasterisation — device half of mask_gen.py:110-117
  *   boxes: int32 (N, n_boxes, 4) = [y0, y1, x0, x1) half-open ranges ALREADY resolved with numpy
  *   slice semantics (host side, mask_gen.BoxMaskGenerator.generate_boxes); each rectangle XOR-

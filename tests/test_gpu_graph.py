@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 dev = torch.device('cuda:0')
 
 
-def _trainer(kind, classes, sd, use_graph):
+def _trainer(kind, classes, sd, use_graph, fused_opt=False):
     from cutmix_semisup_seg_b200 import step as step_mod
     student = na.seg.get(kind)(classes, pretrained=False)
     student.load_state_dict(sd)
@@ -25,7 +25,7 @@ def _trainer(kind, classes, sd, use_graph):
     student.to(dev); teacher.to(dev)
     for p in teacher.parameters():
         p.requires_grad = False
-    optim = step_mod.make_optimizer(student, 'adam', 1e-5, capturable=True)
+    optim = step_mod.make_optimizer(student, 'adam', 1e-5, capturable=True, fused_kernel=fused_opt)
     ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
     student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
     for m in list(student.modules()) + list(teacher.modules()):
@@ -35,8 +35,10 @@ def _trainer(kind, classes, sd, use_graph):
     return step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, conf_thresh=0.5, use_cuda_graph=use_graph), mg
 
 
-@pytest.mark.parametrize('kind,classes', [('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19)])
-def test_graph_replay_equals_eager(kind, classes):
+@pytest.mark.parametrize('kind,classes,fused_opt', [('resnet101_deeplab_imagenet', 21, False),
+                                                    ('resnet101_deeplabv3plus_imagenet', 19, False),
+                                                    ('resnet101_deeplab_imagenet', 21, True)])
+def test_graph_replay_equals_eager(kind, classes, fused_opt):
     from cutmix_semisup_seg_b200 import synthetic
     n, h, w = 2, 64, 64
     net = na.seg.get(kind)(classes, pretrained=False)
@@ -44,11 +46,14 @@ def test_graph_replay_equals_eager(kind, classes):
     sd = TO.synth_state_dict(net.state_dict(), seed=5, logit_gain=4.0, final_keys=final)
     results = []
     for use_graph in (False, True):
-        tr, mg = _trainer(kind, classes, copy.deepcopy(sd), use_graph)
+        tr, mg = _trainer(kind, classes, copy.deepcopy(sd), use_graph, fused_opt)
         losses = []
         for it in range(3):
             sup = synthetic.make_sup_batch(n, h, w, classes, 30 + it, device=dev)
             uns = synthetic.make_unsup_batch(n, h, w, 40 + it, mg, device=dev)
+            if fused_opt:        # a per-iteration LR schedule must reach the replayed step (pinned-host LR buffer)
+                for grp in tr.student_optim.param_groups:
+                    grp['lr'] = grp['lr'] * 0.5
             out = tr.step(sup, [uns])
             losses.append([float(out['sup_loss']), float(out['cons_loss']), float(out['conf_rate'])])
         results.append((losses, {k: v.detach().cpu().clone() for k, v in tr.teacher_net.state_dict().items()}))

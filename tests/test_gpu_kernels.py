@@ -308,3 +308,30 @@ def test_conv_fused_epilogue_and_concat_slice():
     K.conv_dgrad(Act(nhwc(g).to(dev), N, H, W, Cout), wt, Cin, 3, 3, Cout, ldb, 1, 2, 2, dx,
                  addend=Act(nhwc(partial).to(dev), N, H, W, Cin), gate=Act(nhwc(yprev).to(dev), N, H, W, Cin))
     assert relerr(dx.to_nchw(), refdx) < 5e-5
+
+
+@pytest.mark.parametrize('shape', [(3, 19, 37, 53), (2, 21, 64, 64), (1, 2, 9, 1000)])
+def test_argmax_confusion_matches_reference_evaluator(be, shape):
+    """Fused argmax + confusion matrix (b2_argmax_confusion) vs the reference's numpy evaluator fed with torch.argmax:
+    integer counts, so intersection / union / cm / mIoU must be identical (incl. ties, ignore label, NaN-free input)."""
+    import evaluation
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(c)
+    logits = torch.randn(n, c, h, w, generator=g)
+    logits[:, :, :2] = torch.round(logits[:, :, :2])            # rows with many exact ties
+    truth = torch.randint(0, c, (n, 1, h, w), generator=g)
+    truth[:, :, -3:] = 255
+    ref = evaluation.EvaluatorIoU(c)
+    pred = torch.argmax(logits, dim=1).numpy()
+    for i in range(n):
+        ref.sample(truth[i, 0].numpy(), pred[i], ignore_value=255)
+    got = evaluation.EvaluatorIoU(c)
+    got.sample_logits(logits.to(dev), truth.to(dev), ignore_value=255)
+    got.sample_logits(logits.to(dev), truth.to(dev), ignore_value=255)         # accumulates
+    score = got.score()
+    assert np.array_equal(got.cm, 2 * ref.cm)
+    assert np.array_equal(got.intersection, 2 * ref.intersection) and np.array_equal(got.union, 2 * ref.union)
+    assert np.array_equal(score, ref.score())
+    cm = torch.zeros(c * c, dtype=torch.int64, device=dev)
+    p = be.argmax_confusion(logits.to(dev), truth.to(dev), cm, ignore_value=255, want_pred=True)
+    assert np.array_equal(p.cpu().numpy(), pred)

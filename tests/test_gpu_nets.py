@@ -119,8 +119,8 @@ def test_full_resnet101_3xtf32(kind, classes, shape):
     assert stat < 1e-3
 
 
-@pytest.mark.parametrize('batch_trunk', [True, False])
-def test_training_iteration_matches_oracle_and_reference_golden(batch_trunk):
+@pytest.mark.parametrize('batch_trunk,fused_opt', [(True, False), (False, False), (True, True)])
+def test_training_iteration_matches_oracle_and_reference_golden(batch_trunk, fused_opt):
     """(batch_trunk: the frozen trunk runs once per network over the concatenated mini-batches, or pass by pass in the
     reference's order.)  Three full iterations (DeepLab v2, frozen BN, CutMix var loss, Adam with the duplicated group, EMA) on the GPU
     vs the oracle's CPU iterations (which tests/test_oracle_golden.py pins to the reference): losses within 1e-4
@@ -138,8 +138,11 @@ def test_training_iteration_matches_oracle_and_reference_golden(batch_trunk):
         p.requires_grad = False
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=lr * 0.1),
-                                  dict(params=student.new_parameters(), lr=lr)], foreach=False)
+        if fused_opt:          # one launch: Adam (k sequential updates for the duplicated group) + EMA
+            optim = step_mod.make_optimizer(student, 'adam', lr, fused_kernel=True)
+        else:
+            optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=lr * 0.1),
+                                      dict(params=student.new_parameters(), lr=lr)], foreach=False)
     ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
     student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
     mg = mask_gen.BoxMaskGenerator(0.5, invert=True)

@@ -196,6 +196,22 @@ if __name__ == '__main__':
                     L.b2_debug_set(6, dbg)
                     timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), fl, name + ' wgrad [2cta={} dbg={}]'.format(1 - force1, dbg))
             L.b2_debug_set(6, 0); L.b2_debug_set(5, 0)
+    if which == 'major':
+        # which MN-major operand costs the tensor-pipe rate?  MMA-only runs (wgrad knob 6 bit 8: no TMA traffic) with the
+        # A / B descriptors flipped to K-major SWIZZLE_128B (bits 32 / 64; timing only, the products are garbage)
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        n, h, w, cin, cout, k, dil = 16, 64, 64, 256, 256, 3, 2
+        x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+        g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+        dw = torch.zeros(cout, k * k, cin, device=dev)
+        fl = 2.0 * n * h * w * cin * cout * k * k
+        for force1 in (1, 0):
+            L.b2_debug_set(5, force1)
+            for bits, tag in ((0, 'A mn, B mn (product)'), (32, 'A k , B mn'), (64, 'A mn, B k '), (96, 'A k , B k ')):
+                L.b2_debug_set(6, 8 | bits)
+                timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, 2, dil), fl, '3x3 d2 256->256 wgrad MMA-only [2cta={}] {}'.format(1 - force1, tag))
+        L.b2_debug_set(6, 0); L.b2_debug_set(5, 0)
     if which == 'wg2':
         # weight-gradient kernel: single-CTA vs CTA-pair build (debug knob 5) on the hot-path shapes, with a bit-level
         # comparison of the two results (same K order per accumulator => expected identical up to the split count)

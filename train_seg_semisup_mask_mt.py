@@ -169,10 +169,13 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
         iou_eval = evaluation.EvaluatorIoU(n_classes, bin_fill_holes)
         with torch.no_grad():
             vx, vy = synthetic.make_sup_batch(min(batch_size, 4), h, w, n_classes, 999, device=torch_device)
-            pred = torch.argmax(eval_net(vx), dim=1).cpu().numpy()
-            truth = vy.cpu().numpy()
-            for i in range(len(pred)):
-                iou_eval.sample(truth[i, 0], pred[i], ignore_value=255)
+            if bin_fill_holes:      # hole filling is a CPU (scipy) post-process of the argmax map, as in the reference
+                pred = torch.argmax(eval_net(vx), dim=1).cpu().numpy()
+                truth = vy.cpu().numpy()
+                for i in range(len(pred)):
+                    iou_eval.sample(truth[i, 0], pred[i], ignore_value=255)
+            else:                   # fused argmax + confusion matrix on the device, one C*C read-back per epoch
+                iou_eval.sample_logits(eval_net(vx), vy, ignore_value=255)
         iou = iou_eval.score()
         t2 = time.time()
         if rank == 0:
