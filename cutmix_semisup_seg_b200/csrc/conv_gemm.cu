@@ -91,7 +91,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)tc::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;     // uniform: role branches converge
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmB);
@@ -115,61 +115,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_tx = rows_a * 128u + (uint32_t)a.block_n * 128u;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(a, tile);
-        for (int tap = 0; tap < a.n_taps; ++tap) {
-          if (!(t.tap_mask >> tap & 1)) continue;
-          const int cw = t.w0 * a.istride + a.dw[tap];
-          const int ch = t.h0 * a.istride + a.dh[tap];
-          const int bt = a.btap[tap];
-          for (int kb = 0; kb < a.kblocks; ++kb) {
-            for (int p = 0; p < a.n_pass; ++p) {
-              tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (converged warp, one elected lane issues; tc_common.cuh) =====================
+    const uint32_t el = tc::elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(a, tile);
+      for (int tap = 0; tap < a.n_taps; ++tap) {
+        if (!(t.tap_mask >> tap & 1)) continue;
+        const int cw = t.w0 * a.istride + a.dw[tap];
+        const int ch = t.h0 * a.istride + a.dh[tap];
+        const int bt = a.btap[tap];
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (el) {
               tc::mbar_expect_tx(&full_bar[stage], stage_tx);
               tc::tma_load_4d(smem_a + stage * A_STAGE_BYTES, (p & 1) ? &tmAlo : &tmA, &full_bar[stage],
                               kb * BLOCK_K, cw, ch, t.n0);
               tc::tma_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
                               kb * BLOCK_K, bt, t.n_idx * a.block_n);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_tf32(BLOCK_M, a.block_n, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(a, tile);
-        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    const uint32_t el = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_tf32(BLOCK_M, a.block_n, 0, 0);
+    // K-major SWIZZLE_128B descriptors: low word = start address >> 4 | LBO << 16, high word constant; one K step of
+    // 8 tf32 = 32 B = +2 in the low word
+    const uint32_t desc_hi = (uint32_t)(tc::make_smem_desc_sw128(0, 16, 1024) >> 32);
+    const uint32_t a_lo0 = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(smem_a), 16, 1024);
+    const uint32_t b_lo0 = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(smem_b), 16, 1024);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(a, tile);
+      tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+      uint32_t accum = 0;
+      const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
+      for (int it = 0; it < iters; ++it) {
+        tc::mbar_wait(&full_bar[stage], phase);
         tc::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-        uint32_t first = 1;
-        const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
-        for (int it = 0; it < iters; ++it) {
-          tc::mbar_wait(&full_bar[stage], phase);
-          tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)stage * (B_STAGE_BYTES >> 4);
+        if (el) {
 #pragma unroll
-          for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
-            const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
-            const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
-            tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-            first = 0;
-          }
+          for (int ks = 0; ks < BLOCK_K / 8; ++ks)
+            tc::mma_tf32(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 2 * ks), ((uint64_t)desc_hi << 32) | (b_lo + 2 * ks), idesc,
+                         ks == 0 ? accum : 1u);
           tc::mma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        accum = 1;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (el) tc::mma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (conv_epilogue.cuh) =====================

@@ -162,8 +162,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;     // [2]       leader's copies are the live ones
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = (int)tc::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;     // uniform: role branches converge
+  const uint32_t rank = tc::uniform(cluster_ctarank());
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
@@ -189,21 +189,22 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t stage_tx = 2u * (rows_a * 128u + (uint32_t)(BLOCK_N / 2) * 128u);     // both CTAs' bytes
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int tr_n = 0;
-      for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
-        const TileInfo t = decode_tile(a, pair, (int)rank);
-        for (int tap = 0; tap < a.n_taps; ++tap) {
-          if (!(t.tap_mask >> tap & 1)) continue;
-          const int cw = t.w0 * a.istride + a.dw[tap];
-          const int ch = t.h0 * a.istride + a.dh[tap];
-          const int bt = a.btap[tap];
-          for (int kb = 0; kb < a.kblocks; ++kb) {
-            for (int p = 0; p < a.n_pass; ++p) {
-              tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[tr_n++] = clock64();
+    // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
+    const uint32_t el = tc::elect_one();
+    int stage = 0; uint32_t phase = 0;
+    int tr_n = 0;
+    for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
+      const TileInfo t = decode_tile(a, pair, (int)rank);
+      for (int tap = 0; tap < a.n_taps; ++tap) {
+        if (!(t.tap_mask >> tap & 1)) continue;
+        const int cw = t.w0 * a.istride + a.dw[tap];
+        const int ch = t.h0 * a.istride + a.dh[tap];
+        const int bt = a.btap[tap];
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          for (int p = 0; p < a.n_pass; ++p) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (a.trace && blockIdx.x == 0 && tr_n < 512) { if (el) a.trace[tr_n] = clock64(); ++tr_n; }
+            if (el) {
               if (a.ep.dbg & 8) {               // timing experiment: no operand traffic (stale smem contents)
                 if (leader) tc::mbar_arrive(&full_bar[stage]);
               } else {
@@ -213,47 +214,54 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma2_load_3d(smem_b + stage * B_STAGE_BYTES, (p & 2) ? &tmBlo : &tmB, &full_bar[stage],
                              kb * BLOCK_K, bt, t.n_idx * BLOCK_N + (int)rank * (BLOCK_N / 2));
               }
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA only; converged warp, one elected lane issues) =====================
+    if (leader) {
+      const uint32_t el = tc::elect_one();
       const uint32_t idesc = tc::make_idesc_tf32(2 * BLOCK_M, BLOCK_N, 0, 0);
+      // K-major SWIZZLE_128B descriptors: low word = start address >> 4 | LBO (16 B) << 16, high word constant
+      // (SBO = 1024 B, version 1, swizzle mode 2).  One K step of 8 tf32 = 32 B = +2 in the low word.
+      const uint32_t desc_hi = (uint32_t)(tc::make_smem_desc_sw128(0, 16, 1024) >> 32);
+      const uint32_t a_lo0 = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(smem_a), 16, 1024);
+      const uint32_t b_lo0 = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(smem_b), 16, 1024);
+      const bool no_mma = a.ep.dbg & 16;      // (16: timing experiment without tensor-core work)
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int tr_n = 0, tr_t = 0;
       for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
         const TileInfo t = decode_tile(a, pair, 0);
-        if (a.trace && blockIdx.x == 0 && tr_t < 510) a.trace[1024 + tr_t++] = clock64();
+        if (a.trace && blockIdx.x == 0 && tr_t < 510) { if (el) a.trace[1024 + tr_t] = clock64(); ++tr_t; }
         tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
-        if (a.trace && blockIdx.x == 0 && tr_t < 510) a.trace[1024 + tr_t++] = clock64();
+        if (a.trace && blockIdx.x == 0 && tr_t < 510) { if (el) a.trace[1024 + tr_t] = clock64(); ++tr_t; }
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        uint32_t first = 1;
+        uint32_t accum = 0;
         const int iters = __popc(t.tap_mask) * a.kblocks * a.n_pass;
         for (int it = 0; it < iters; ++it) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
-          if (a.trace && blockIdx.x == 0 && tr_n < 512) a.trace[512 + tr_n++] = clock64();
-          const uint32_t a_addr = tc::smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = tc::smem_u32(smem_b + stage * B_STAGE_BYTES);
-          if (!(a.ep.dbg & 16)) {             // (16: timing experiment without tensor-core work)
+          if (a.trace && blockIdx.x == 0 && tr_n < 512) { if (el) a.trace[512 + tr_n] = clock64(); ++tr_n; }
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * (B_STAGE_BYTES >> 4);
+          if (el) {
+            if (!no_mma) {
 #pragma unroll
-            for (int ks = 0; ks < BLOCK_K / 8; ++ks) {
-              const uint64_t adesc = tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
-              const uint64_t bdesc = tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
-              mma2_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-              first = 0;
+              for (int ks = 0; ks < BLOCK_K / 8; ++ks)
+                mma2_tf32(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 2 * ks), ((uint64_t)desc_hi << 32) | (b_lo + 2 * ks), idesc,
+                          ks == 0 ? accum : 1u);
             }
+            mma2_commit_mcast(&empty_bar[stage]);   // frees this stage in both CTAs when the MMAs retire
           }
-          mma2_commit_mcast(&empty_bar[stage]);   // frees this stage in both CTAs when the MMAs retire
+          accum = 1;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma2_commit_mcast(&tfull_bar[acc]);       // accumulator complete -> both epilogues
+        if (el) mma2_commit_mcast(&tfull_bar[acc]);   // accumulator complete -> both epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

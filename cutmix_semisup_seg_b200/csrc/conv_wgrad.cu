@@ -65,18 +65,48 @@ __device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, int u) {
   return r;
 }
 
-struct PBox { int w0, h0, n0; bool active; };
+// Walks the pixel boxes [pb_begin, pb_end) of one work unit in order.  One division per unit (init), additions per box:
+// the producer and the MMA issuer run this once per pipeline stage, and the issuing thread's instruction stream is what
+// bounds this kernel (see tc_common.cuh "Warp-uniform role code").
+struct PbWalk {
+  int w0, h0, n0;      // output-space corner of the box (dY coordinates)
+  int xw, xh;          // input-space corner for the unit's tap (X coordinates; may lie in the padding)
+  int wt, ht;
+  __device__ __forceinline__ void init(const WgradKArgs& a, int pb, int tap) {
+    wt = pb % a.tiles_w; const int t = pb / a.tiles_w;
+    ht = t % a.tiles_h;
+    w0 = wt * a.bw; h0 = ht * a.bh; n0 = (t / a.tiles_h) * a.bn;
+    xw = w0 * a.istride + a.dw[tap]; xh = h0 * a.istride + a.dh[tap];
+  }
+  // false: every input pixel of the box lies in the padding (contributes zero)
+  __device__ __forceinline__ bool active(const WgradKArgs& a) const {
+    return xh + (a.bh - 1) * a.istride >= 0 && xh < a.ih && xw + (a.bw - 1) * a.istride >= 0 && xw < a.iw;
+  }
+  __device__ __forceinline__ void next(const WgradKArgs& a, int tap) {
+    if (++wt < a.tiles_w) { w0 += a.bw; xw += a.bw * a.istride; return; }
+    wt = 0; w0 = 0; xw = a.dw[tap];
+    if (++ht < a.tiles_h) { h0 += a.bh; xh += a.bh * a.istride; return; }
+    ht = 0; h0 = 0; xh = a.dh[tap]; n0 += a.bn;
+  }
+};
 
-__device__ __forceinline__ PBox decode_pb(const WgradKArgs& a, int pb, int tap) {
-  PBox b;
-  const int wt = pb % a.tiles_w; int t = pb / a.tiles_w;
-  const int ht = t % a.tiles_h;
-  const int nt = t / a.tiles_h;
-  b.w0 = wt * a.bw; b.h0 = ht * a.bh; b.n0 = nt * a.bn;
-  const int lo_h = b.h0 * a.istride + a.dh[tap], hi_h = lo_h + (a.bh - 1) * a.istride;
-  const int lo_w = b.w0 * a.istride + a.dw[tap], hi_w = lo_w + (a.bw - 1) * a.istride;
-  b.active = hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw;
-  return b;
+// Operand descriptors of the MMA issuer as (low word at stage 0, constant high word, low-word step per K step of 8
+// pixels).  Product: MN-major SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B), LBO = stride between the 32-channel
+// column blocks (one TMA box each), SBO = stride between 4-row groups along K, 8 pixels = 1024 B.  Debug knob 6 bits
+// 32 / 64 (timing only, garbage results) pretend the operand is a K-major SWIZZLE_128B tile.
+struct OperandDesc { uint32_t lo0, hi, step; };
+__device__ __forceinline__ OperandDesc make_operand_desc(const WgradKArgs& a, uint32_t smem_addr, bool k_major_dbg) {
+  OperandDesc d;
+  if (k_major_dbg) {
+    const uint64_t v = tc::make_smem_desc_sw128(smem_addr, 16, 1024);
+    d.lo0 = (uint32_t)v; d.hi = (uint32_t)(v >> 32); d.step = 32 >> 4;
+  } else {
+    const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
+    const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
+    const uint64_t v = tc::make_smem_desc(smem_addr, lbo, sbo, 1);
+    d.lo0 = (uint32_t)v; d.hi = (uint32_t)(v >> 32); d.step = 1024 >> 4;
+  }
+  return d;
 }
 
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -96,7 +126,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   uint64_t* tempty_bar = bars + 2 * W_STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)tc::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;     // uniform: role branches converge
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmY); tc::tma_prefetch_desc(&tmX);
@@ -117,91 +147,99 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
-        const UnitInfo ui = decode_unit(a, u);
-        int na = (a.m - ui.m0 + 31) / 32; if (na > W_BLOCK_M / 32) na = W_BLOCK_M / 32;
-        int nbk = (a.c - ui.c0 + 31) / 32; if (nbk > a.block_n / 32) nbk = a.block_n / 32;
-        const int slot = a.kpix * 128;   // bytes of one 32-channel block: kpix pixel rows x 128 B
-        // 5-D boxes always carry the full block count of the tile (blocks past the tensor are zero-filled)
-        const uint32_t tx = (uint32_t)((a.use5_a ? W_BLOCK_M / 32 : na) + (a.use5_b ? a.block_n / 32 : nbk)) * (uint32_t)slot;
-        bool any = false;
-        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
-          const PBox b = decode_pb(a, pb, ui.tap);
-          // a unit with no contributing pixel box still runs one (all-zero X) box so that the
-          // accumulator is written
-          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
-          any = true;
-          const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
-          for (int p = 0; p < a.n_pass; ++p) {
-            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (a.dbg & 8) { tc::mbar_arrive(&full_bar[stage]); if (++stage == W_STAGES) { stage = 0; phase ^= 1; } continue; }
-            tc::mbar_expect_tx(&full_bar[stage], tx);
-            uint8_t* sa = smem_a + stage * W_A_STAGE_BYTES;
-            uint8_t* sb = smem_b + stage * W_B_STAGE_BYTES;
-            if (a.use5_a) {
-              tc::tma_load_5d(sa, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0, ui.m0 / 32);
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    const uint32_t el = tc::elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const UnitInfo ui = decode_unit(a, u);
+      int na = (a.m - ui.m0 + 31) / 32; if (na > W_BLOCK_M / 32) na = W_BLOCK_M / 32;
+      int nbk = (a.c - ui.c0 + 31) / 32; if (nbk > a.block_n / 32) nbk = a.block_n / 32;
+      const int slot = a.kpix * 128;   // bytes of one 32-channel block: kpix pixel rows x 128 B
+      // 5-D boxes always carry the full block count of the tile (blocks past the tensor are zero-filled)
+      const uint32_t tx = (uint32_t)((a.use5_a ? W_BLOCK_M / 32 : na) + (a.use5_b ? a.block_n / 32 : nbk)) * (uint32_t)slot;
+      bool any = false;
+      PbWalk b; b.init(a, ui.pb_begin, ui.tap);
+      for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
+        // a unit with no contributing pixel box still runs one (all-zero X) box so that the
+        // accumulator is written
+        if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
+        any = true;
+        for (int p = 0; p < a.n_pass; ++p) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (el) {
+            if (a.dbg & 8) {
+              tc::mbar_arrive(&full_bar[stage]);
             } else {
-              const CUtensorMap* my = (p & 1) ? &tmYlo : &tmY;
-              for (int j = 0; j < na; ++j)
-                tc::tma_load_4d(sa + j * slot, my, &full_bar[stage], ui.m0 + 32 * j, b.w0, b.h0, b.n0);
+              tc::mbar_expect_tx(&full_bar[stage], tx);
+              uint8_t* sa = smem_a + stage * W_A_STAGE_BYTES;
+              uint8_t* sb = smem_b + stage * W_B_STAGE_BYTES;
+              if (a.use5_a) {
+                tc::tma_load_5d(sa, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0, ui.m0 / 32);
+              } else {
+                const CUtensorMap* my = (p & 1) ? &tmYlo : &tmY;
+                for (int j = 0; j < na; ++j)
+                  tc::tma_load_4d(sa + j * slot, my, &full_bar[stage], ui.m0 + 32 * j, b.w0, b.h0, b.n0);
+              }
+              if (a.use5_b) {
+                tc::tma_load_5d(sb, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, b.xw, b.xh, b.n0, ui.c0 / 32);
+              } else {
+                const CUtensorMap* mx = (p & 2) ? &tmXlo : &tmX;
+                for (int j = 0; j < nbk; ++j)
+                  tc::tma_load_4d(sb + j * slot, mx, &full_bar[stage], ui.c0 + 32 * j, b.xw, b.xh, b.n0);
+              }
             }
-            if (a.use5_b) {
-              tc::tma_load_5d(sb, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, xw, xh, b.n0, ui.c0 / 32);
-            } else {
-              const CUtensorMap* mx = (p & 2) ? &tmXlo : &tmX;
-              for (int j = 0; j < nbk; ++j)
-                tc::tma_load_4d(sb + j * slot, mx, &full_bar[stage], ui.c0 + 32 * j, xw, xh, b.n0);
-            }
-            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // (debug knob 6 bits 32 / 64, timing only, garbage results: pretend A / B are K-major SWIZZLE_128B operands)
-      const bool a_k = a.dbg & 32, b_k = a.dbg & 64;
-      const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, a_k ? 0 : 1, b_k ? 0 : 1);
-      // MN-major tf32: SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B).  LBO = stride between the
-      // 32-channel column blocks (one TMA box each), SBO = stride between 4-row groups along K.
-      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
-      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      const int ksteps = a.kpix / 8;
-      for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
-        const UnitInfo ui = decode_unit(a, u);
-        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
-        uint32_t first = 1;
-        bool any = false;
-        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
-          const PBox b = decode_pb(a, pb, ui.tap);
-          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
-          any = true;
-          for (int p = 0; p < a.n_pass; ++p) {
-            tc::mbar_wait(&full_bar[stage], phase);
-            tc::tc_fence_after();
-            const uint32_t a_addr = tc::smem_u32(smem_a + stage * W_A_STAGE_BYTES);
-            const uint32_t b_addr = tc::smem_u32(smem_b + stage * W_B_STAGE_BYTES);
-            for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
-              const uint64_t adesc = a_k ? tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024) : tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
-              const uint64_t bdesc = b_k ? tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024) : tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
-              tc::mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-              first = 0;
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    const uint32_t el = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_tf32(W_BLOCK_M, a.block_n, (a.dbg & 32) ? 0 : 1, (a.dbg & 64) ? 0 : 1);
+    const OperandDesc da = make_operand_desc(a, tc::smem_u32(smem_a), a.dbg & 32);
+    const OperandDesc db = make_operand_desc(a, tc::smem_u32(smem_b), a.dbg & 64);
+    const bool no_mma = a.dbg & 16;
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int ksteps = a.kpix / 8;
+    for (int u = blockIdx.x; u < a.num_units; u += gridDim.x) {
+      const UnitInfo ui = decode_unit(a, u);
+      tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
+      uint32_t accum = 0;
+      bool any = false;
+      PbWalk b; b.init(a, ui.pb_begin, ui.tap);
+      for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
+        if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
+        any = true;
+        for (int p = 0; p < a.n_pass; ++p) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t a_lo = da.lo0 + (uint32_t)stage * (W_A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = db.lo0 + (uint32_t)stage * (W_B_STAGE_BYTES >> 4);
+          if (el) {
+            if (!no_mma) {
+              if (ksteps == 4) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  tc::mma_tf32(tmem_d, ((uint64_t)da.hi << 32) | (a_lo + ks * da.step), ((uint64_t)db.hi << 32) | (b_lo + ks * db.step),
+                               idesc, ks == 0 ? accum : 1u);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks)
+                  tc::mma_tf32(tmem_d, ((uint64_t)da.hi << 32) | (a_lo + ks * da.step), ((uint64_t)db.hi << 32) | (b_lo + ks * db.step),
+                               idesc, ks == 0 ? accum : 1u);
+              }
             }
             tc::mma_commit(&empty_bar[stage]);
-            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
+          accum = 1;
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (el) tc::mma_commit(&tfull_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -322,8 +360,8 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
   uint64_t* tempty_bar = bars + 2 * W2_STAGES + 2;    // [2]          leader's copies are the live ones
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * W2_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = w2_cluster_ctarank();
+  const int warp = (int)tc::uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;     // uniform: role branches converge
+  const uint32_t rank = tc::uniform(w2_cluster_ctarank());
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
@@ -350,37 +388,41 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
   const uint32_t stage_tx = 2u * (uint32_t)((W_BLOCK_M / 32) + half_n / 32) * (uint32_t)slot;     // both CTAs' bytes
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int u = cluster_id; u < a.num_units; u += num_clusters) {
-        const UnitInfo ui = decode_unit(a, u);
-        bool any = false;
-        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
-          const PBox b = decode_pb(a, pb, ui.tap);
-          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
-          any = true;
-          const int xw = b.w0 * a.istride + a.dw[ui.tap], xh = b.h0 * a.istride + a.dh[ui.tap];
-          for (int p = 0; p < a.n_pass; ++p) {
-            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (a.dbg & 8) { if (leader) tc::mbar_arrive(&full_bar[stage]); if (++stage == W2_STAGES) { stage = 0; phase ^= 1; } continue; }
-            if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
-            w2_tma_load_5d(smem_a + stage * W2_A_STAGE_BYTES, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0,
-                           (ui.m0 + (int)rank * W_BLOCK_M) / 32);
-            w2_tma_load_5d(smem_b + stage * W2_B_STAGE_BYTES, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, xw, xh, b.n0,
-                           (ui.c0 + (int)rank * half_n) / 32);
-            if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
+    // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
+    const uint32_t el = tc::elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int u = cluster_id; u < a.num_units; u += num_clusters) {
+      const UnitInfo ui = decode_unit(a, u);
+      bool any = false;
+      PbWalk b; b.init(a, ui.pb_begin, ui.tap);
+      for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
+        if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
+        any = true;
+        for (int p = 0; p < a.n_pass; ++p) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (el) {
+            if (a.dbg & 8) {
+              if (leader) tc::mbar_arrive(&full_bar[stage]);
+            } else {
+              if (leader) tc::mbar_expect_tx(&full_bar[stage], stage_tx);
+              w2_tma_load_5d(smem_a + stage * W2_A_STAGE_BYTES, (p & 1) ? &tmY5lo : &tmY5, &full_bar[stage], 0, b.w0, b.h0, b.n0,
+                             (ui.m0 + (int)rank * W_BLOCK_M) / 32);
+              w2_tma_load_5d(smem_b + stage * W2_B_STAGE_BYTES, (p & 2) ? &tmX5lo : &tmX5, &full_bar[stage], 0, b.xw, b.xh, b.n0,
+                             (ui.c0 + (int)rank * half_n) / 32);
+            }
           }
+          if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
-      const bool a_k = a.dbg & 32, b_k = a.dbg & 64;        // timing-only majorness flips, see the single-CTA kernel
-      const uint32_t idesc = tc::make_idesc_tf32(2 * W_BLOCK_M, a.block_n, a_k ? 0 : 1, b_k ? 0 : 1);
-      const uint32_t lbo = a.desc_variant == 1 ? 512u : (uint32_t)(a.kpix * 128);
-      const uint32_t sbo = a.desc_variant == 1 ? (uint32_t)(a.kpix * 128) : 512u;
+    // ===================== MMA issuer (leader CTA only; converged warp, one elected lane issues) =====================
+    if (leader) {
+      const uint32_t el = tc::elect_one();
+      const uint32_t idesc = tc::make_idesc_tf32(2 * W_BLOCK_M, a.block_n, (a.dbg & 32) ? 0 : 1, (a.dbg & 64) ? 0 : 1);
+      const OperandDesc da = make_operand_desc(a, tc::smem_u32(smem_a), a.dbg & 32);
+      const OperandDesc db = make_operand_desc(a, tc::smem_u32(smem_b), a.dbg & 64);
+      const bool no_mma = a.dbg & 16;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const int ksteps = a.kpix / 8;
@@ -389,28 +431,37 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
         tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
-        uint32_t first = 1;
+        uint32_t accum = 0;
         bool any = false;
-        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb) {
-          const PBox b = decode_pb(a, pb, ui.tap);
-          if (!b.active && !(pb == ui.pb_end - 1 && !any)) continue;
+        PbWalk b; b.init(a, ui.pb_begin, ui.tap);
+        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
+          if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
           any = true;
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&full_bar[stage], phase);
             tc::tc_fence_after();
-            const uint32_t a_addr = tc::smem_u32(smem_a + stage * W2_A_STAGE_BYTES);
-            const uint32_t b_addr = tc::smem_u32(smem_b + stage * W2_B_STAGE_BYTES);
-            for (int ks = 0; ks < ksteps && !(a.dbg & 16); ++ks) {
-              const uint64_t adesc = a_k ? tc::make_smem_desc_sw128(a_addr + ks * 32, 16, 1024) : tc::make_smem_desc(a_addr + ks * 1024, lbo, sbo, 1);
-              const uint64_t bdesc = b_k ? tc::make_smem_desc_sw128(b_addr + ks * 32, 16, 1024) : tc::make_smem_desc(b_addr + ks * 1024, lbo, sbo, 1);
-              w2_mma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-              first = 0;
+            const uint32_t a_lo = da.lo0 + (uint32_t)stage * (W2_A_STAGE_BYTES >> 4);
+            const uint32_t b_lo = db.lo0 + (uint32_t)stage * (W2_B_STAGE_BYTES >> 4);
+            if (el) {
+              if (!no_mma) {
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    w2_mma_tf32(tmem_d, ((uint64_t)da.hi << 32) | (a_lo + ks * da.step), ((uint64_t)db.hi << 32) | (b_lo + ks * db.step),
+                                idesc, ks == 0 ? accum : 1u);
+                } else {
+                  for (int ks = 0; ks < ksteps; ++ks)
+                    w2_mma_tf32(tmem_d, ((uint64_t)da.hi << 32) | (a_lo + ks * da.step), ((uint64_t)db.hi << 32) | (b_lo + ks * db.step),
+                                idesc, ks == 0 ? accum : 1u);
+                }
+              }
+              w2_commit_mcast(&empty_bar[stage]);
             }
-            w2_commit_mcast(&empty_bar[stage]);
+            accum = 1;
             if (++stage == W2_STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        w2_commit_mcast(&tfull_bar[acc]);
+        if (el) w2_commit_mcast(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -40,6 +40,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// Warp-uniform role code.  The single-thread instructions of this file (UTMALDG, UTCHMMA, UTCBAR in SASS) take their
+// operands from UNIFORM registers.  Issued from an `if (lane == 0)` region the compiler treats every value as per-thread
+// and wraps each instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~20 dependent instructions per MMA): the
+// issuing thread then needs about as long for its instruction stream as the tensor pipe needs for the MMAs.  The role
+// warps therefore run CONVERGED (all 32 lanes walk the pipeline loops, branch conditions made uniform with `uniform()`),
+// and only the instruction itself is predicated on the lane `elect_one()` picked: descriptors, coordinates and barrier
+// addresses then live in uniform registers and the MMAs of a stage issue back to back.
+__device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one (always the same) lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }   // provably warp-uniform
+
 // ---------------------------------------------------------------------------- TMA
 // bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16 B aligned global address
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
