@@ -34,6 +34,8 @@ struct WgradKArgs {
   int m_tiles, c_tiles, block_n;
   int n_taps;
   short dh[W_MAX_TAPS], dw[W_MAX_TAPS], wtap[W_MAX_TAPS];
+  // per tap: the box columns [wlo, whi] / box rows [hlo, hhi] whose input pixels are not all padding (empty: lo > hi)
+  int wlo[W_MAX_TAPS], whi[W_MAX_TAPS], hlo[W_MAX_TAPS], hhi[W_MAX_TAPS];
   int tw;
   int out_tiles, n_splits, num_units;
   int n_pass;
@@ -89,6 +91,21 @@ struct PbWalk {
     ht = 0; h0 = 0; xh = a.dh[tap]; n0 += a.bn;
   }
 };
+
+// Number of pipeline stages (pixel boxes that are not all padding) of a unit, in closed form: the MMA issuer walks no
+// boxes, its loop is wait / 4 MMAs / commit.  Agrees with PbWalk::active by construction of wlo..hhi (plan_wgrad).
+__device__ __forceinline__ int active_before(const WgradKArgs& a, int tap, int pb) {   // active boxes with index < pb
+  const int nw = max(a.whi[tap] - a.wlo[tap] + 1, 0), nh = max(a.hhi[tap] - a.hlo[tap] + 1, 0);
+  const int wt = pb % a.tiles_w, t = pb / a.tiles_w;
+  const int ht = t % a.tiles_h, nt = t / a.tiles_h;
+  int f = nt * nh * nw + min(max(ht - a.hlo[tap], 0), nh) * nw;
+  if (ht >= a.hlo[tap] && ht <= a.hhi[tap]) f += min(max(wt - a.wlo[tap], 0), nw);
+  return f;
+}
+__device__ __forceinline__ int unit_boxes(const WgradKArgs& a, const UnitInfo& ui) {
+  const int n = active_before(a, ui.tap, ui.pb_end) - active_before(a, ui.tap, ui.pb_begin);
+  return n > 0 ? n : 1;        // a unit with no contributing box still runs one (all-zero X) box: see the producer
+}
 
 // Operand descriptors of the MMA issuer as (low word at stage 0, constant high word, low-word step per K step of 8
 // pixels).  Product: MN-major SWIZZLE_128B_BASE32B atoms of (4 pixel rows x 128 B), LBO = stride between the 32-channel
@@ -209,12 +226,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       tc::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
       uint32_t accum = 0;
-      bool any = false;
-      PbWalk b; b.init(a, ui.pb_begin, ui.tap);
-      for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
-        if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
-        any = true;
-        for (int p = 0; p < a.n_pass; ++p) {
+      const int iters = unit_boxes(a, ui) * a.n_pass;
+      {
+        for (int it = 0; it < iters; ++it) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
           const uint32_t a_lo = da.lo0 + (uint32_t)stage * (W_A_STAGE_BYTES >> 4);
@@ -432,12 +446,9 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * W_MAX_BLOCK_N;
         uint32_t accum = 0;
-        bool any = false;
-        PbWalk b; b.init(a, ui.pb_begin, ui.tap);
-        for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
-          if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
-          any = true;
-          for (int p = 0; p < a.n_pass; ++p) {
+        const int iters = unit_boxes(a, ui) * a.n_pass;
+        {
+          for (int it = 0; it < iters; ++it) {
             tc::mbar_wait(&full_bar[stage], phase);
             tc::tc_fence_after();
             const uint32_t a_lo = da.lo0 + (uint32_t)stage * (W2_A_STAGE_BYTES >> 4);
@@ -583,6 +594,18 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   for (int i = 0; i < p->n_taps; ++i) {
     a.dh[i] = (short)p->taps[i * 3 + 0]; a.dw[i] = (short)p->taps[i * 3 + 1]; a.wtap[i] = (short)p->taps[i * 3 + 2];
     B2_REQUIRE(p->taps[i * 3 + 2] >= 0 && p->taps[i * 3 + 2] < p->tw, "b2_conv_wgrad: tap index out of range");
+  }
+  for (int i = 0; i < p->n_taps; ++i) {      // same predicate as PbWalk::active, per axis (the active set is an interval)
+    int wlo = 1, whi = 0, hlo = 1, hhi = 0; bool fw = false, fh = false;
+    for (int wt = 0; wt < a.tiles_w; ++wt) {
+      const int xw = wt * a.bw * a.istride + a.dw[i];
+      if (xw + (a.bw - 1) * a.istride >= 0 && xw < a.iw) { if (!fw) { wlo = wt; fw = true; } whi = wt; }
+    }
+    for (int ht = 0; ht < a.tiles_h; ++ht) {
+      const int xh = ht * a.bh * a.istride + a.dh[i];
+      if (xh + (a.bh - 1) * a.istride >= 0 && xh < a.ih) { if (!fh) { hlo = ht; fh = true; } hhi = ht; }
+    }
+    a.wlo[i] = wlo; a.whi[i] = whi; a.hlo[i] = hlo; a.hhi[i] = hhi;
   }
   a.tw = p->tw;
   a.out_tiles = a.m_tiles * a.n_taps * a.c_tiles;
