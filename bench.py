@@ -36,6 +36,28 @@ CFG = {
 FLOPS = {'v3plus': (520.28e9, 1.233e9), 'v2': (147.67e9, 0.488e9)}
 
 
+def committed_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one eager step) of
+    `kernel` from the newest committed ncu launch-list summary under profiles/ (tools/ncu_step.py + launch_list_summary.py).
+    ncu cannot run inside the timed bench, so this is the committed measurement of the same step, not a live one."""
+    import glob
+    import re
+
+    def version(path):          # profiles/rNN_vMM_...: newest round, then newest capture
+        m = re.search(r'r(\d+)_v(\d+)_', os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_launch_list_summary.txt')), key=version)
+    for path in reversed(files):
+        try:
+            for line in open(path):
+                f = line.split()
+                if len(f) >= 7 and f[0] == kernel:
+                    return int((float(f[4]) + float(f[5])) * 1e6), os.path.relpath(path, ROOT)
+        except (OSError, ValueError):
+            continue
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -239,8 +261,10 @@ def run_b200(args):
         dom = max(((k, v) for k, v in prof.items() if v['flops'] > 0), key=lambda kv: kv[1]['ms'])
         name, d = dom
         ach = d['flops'] / (d['ms'] / 1e3) / 1e12
+        traffic, traffic_src = committed_traffic(name)
         res['roofline'] = {'kernel': name, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peaks['bf16_sustained'],
-                           'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16_sustained'], 4), 'traffic': None,
+                           'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16_sustained'], 4), 'traffic': traffic,
+                           'traffic_source': traffic_src,
                            'peak_source': peaks['source'] + ' cuBLAS bf16 sustained; kind::tf32 runs at half the bf16 rate',
                            'frac_of_tf32_rate': round(ach / (peaks['bf16_sustained'] / 2), 4),
                            'launches': d['n'], 'kernel_ms_per_step': round(d['ms'], 3),

@@ -11,6 +11,9 @@ Contents
   iteration.json    two full iterations of the loop body (train_seg_semisup_mask_mt.py:287-476) driven with the
                     reference modules, reference EMAWeightOptimizer, torch Adam on the reference param groups
   loss_block.json   known answers for the consistency / CE block recorded in SURVEY.md §8c
+  entry_point.json  click surface of the reference's `train_seg_semisup_mask_mt.experiment` (option names, flags,
+                    defaults, choices) and the parameter list of the job function, plus lr_schedules / sigmoid_rampup
+                    known answers the entry point depends on
 """
 import hashlib
 import json
@@ -201,8 +204,28 @@ def gen_loss_block():
     json.dump(out, open(os.path.join(OUT, 'loss_block.json'), 'w'), indent=1)
 
 
+def gen_entry_point():
+    """Reference CLI / job-function surface (train_seg_semisup_mask_mt.py:16-42, 581-650)."""
+    import importlib
+    import inspect
+    import click
+    m = importlib.import_module('train_seg_semisup_mask_mt')
+    assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF))
+    opts = []
+    for p in m.experiment.params:
+        opts.append(dict(name=p.name, opts=list(p.opts), is_flag=bool(getattr(p, 'is_flag', False)),
+                         default=None if callable(p.default) else p.default, type=type(p.type).__name__,
+                         choices=list(p.type.choices) if isinstance(p.type, click.Choice) else None))
+    job = m.train_seg_semisup_mask_mt          # job_helper.job returns the function itself with .submit attached
+    job_params = list(inspect.signature(job).parameters)
+    out = dict(options=opts, job_params=job_params, has_submit=hasattr(job, 'submit'),
+               rampup=[network_architectures.sigmoid_rampup(e, 10) for e in range(0, 12)])
+    json.dump(out, open(os.path.join(OUT, 'entry_point.json'), 'w'), indent=1)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    gen_entry_point(); print('entry point')
     gen_masks(); print('masks')
     gen_state_dicts(); print('state dicts')
     gen_loss_block(); print('loss block')

@@ -1,0 +1,67 @@
+"""CPU: the drop-in entry point keeps the reference's CLI and job-function surface
+(train_seg_semisup_mask_mt.py:16-42, 581-650; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
+import inspect
+import json
+import os
+
+import click
+import pytest
+
+import train_seg_semisup_mask_mt as entry
+from architectures import network_architectures
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'entry_point.json')))
+# options this build adds (documented in the module docstring); everything else must be the reference's
+EXTRA_OPTIONS = {'no_pretrained', 'ddp', 'synthetic_classes'}
+EXTRA_CHOICES = {'dataset': {'synthetic'}}
+
+
+def _ours():
+    return {p.name: p for p in entry.experiment.params}
+
+
+def test_every_reference_option_is_kept_with_its_default_and_type():
+    ours = _ours()
+    for ref in GOLD['options']:
+        assert ref['name'] in ours, 'missing option --{}'.format(ref['name'])
+        p = ours[ref['name']]
+        assert list(p.opts) == ref['opts']
+        assert bool(getattr(p, 'is_flag', False)) == ref['is_flag'], ref['name']
+        assert type(p.type).__name__ == ref['type'], ref['name']
+        if not callable(p.default):
+            assert p.default == ref['default'], ref['name']
+        if ref['choices'] is not None:
+            assert isinstance(p.type, click.Choice)
+            mine = list(p.type.choices)
+            assert mine[:len(ref['choices'])] == ref['choices'], ref['name']
+            assert set(mine) - set(ref['choices']) <= EXTRA_CHOICES.get(ref['name'], set()), ref['name']
+
+
+def test_only_documented_options_are_added():
+    ref_names = {o['name'] for o in GOLD['options']}
+    assert set(_ours()) - ref_names == EXTRA_OPTIONS
+    for name in EXTRA_OPTIONS:            # additions must not change behaviour unless asked for
+        p = _ours()[name]
+        assert p.default in (False, 21)
+
+
+def test_job_function_signature_and_submit():
+    params = list(inspect.signature(entry.train_seg_semisup_mask_mt).parameters)
+    assert params[:len(GOLD['job_params'])] == GOLD['job_params']
+    extra = params[len(GOLD['job_params']):]
+    assert set(extra) == EXTRA_OPTIONS
+    sig = inspect.signature(entry.train_seg_semisup_mask_mt)
+    assert all(sig.parameters[k].default is not inspect.Parameter.empty for k in extra)      # reference callers still work
+    assert GOLD['has_submit'] and callable(entry.train_seg_semisup_mask_mt.submit)
+
+
+def test_sigmoid_rampup_known_answers():
+    for e, want in enumerate(GOLD['rampup']):
+        assert network_architectures.sigmoid_rampup(e, 10) == pytest.approx(want, rel=1e-12, abs=0.0)
+
+
+def test_bad_mask_mode_is_rejected_before_any_gpu_work():
+    # click validates the choice: the reference exits with usage error 2 as well
+    from click.testing import CliRunner
+    r = CliRunner().invoke(entry.experiment, ['--mask_mode', 'blend'])
+    assert r.exit_code == 2

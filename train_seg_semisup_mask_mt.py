@@ -86,7 +86,10 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
 
     NetClass = network_architectures.seg.get(arch)
     student_net = NetClass(n_classes, pretrained=not no_pretrained).to(torch_device)
-    student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay)
+    # one fused launch for the optimiser step + the teacher's EMA step (cutmix_semisup_seg_b200/optim.py: torch's per-tensor
+    # arithmetic incl. the duplicated DeepLab v2 group); B200SEG_FUSED_OPT=0 keeps torch.optim + the EMA kernel
+    student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay,
+                                            fused_kernel=os.environ.get('B200SEG_FUSED_OPT', '1') != '0')
     if model == 'mean_teacher':
         teacher_net = NetClass(n_classes, pretrained=False).to(torch_device)
         for p in teacher_net.parameters():
