@@ -142,7 +142,8 @@ __device__ __forceinline__ float mix1(float a, float b, float m) {
   return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, m)), __fmul_rn(b, m));
 }
 
-template <bool CUT>
+// PER_SAMPLE: `m` holds one factor per image (ICT mix factors, train_seg_semisup_ict.py:306-311) instead of a mask plane.
+template <bool CUT, bool PER_SAMPLE>
 __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                   const float* __restrict__ m, float* __restrict__ out,
                                                   int c, int64_t hw) {
@@ -150,15 +151,16 @@ __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ a, c
   const int img = plane / c;
   const float* ap = a + (int64_t)plane * hw;
   const float* bp = CUT ? nullptr : b + (int64_t)plane * hw;
-  const float* mp = m + (int64_t)img * hw;
+  const float* mp = PER_SAMPLE ? m : m + (int64_t)img * hw;
+  const float ms = PER_SAMPLE ? __ldg(m + img) : 0.0f;
   float* op = out + (int64_t)plane * hw;
-  const bool vec = (hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(m) |
+  const bool vec = (hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | (PER_SAMPLE ? 0 : reinterpret_cast<uintptr_t>(m)) |
                                       reinterpret_cast<uintptr_t>(out) | (CUT ? 0 : reinterpret_cast<uintptr_t>(b))) & 15) == 0;
   if (vec) {
     const int64_t n4 = hw >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
       const float4 av = __ldg(reinterpret_cast<const float4*>(ap) + i);
-      const float4 mv = __ldg(reinterpret_cast<const float4*>(mp) + i);
+      const float4 mv = PER_SAMPLE ? make_float4(ms, ms, ms, ms) : __ldg(reinterpret_cast<const float4*>(mp) + i);
       float4 r;
       if (CUT) {
         r.x = __fmul_rn(av.x, mv.x); r.y = __fmul_rn(av.y, mv.y); r.z = __fmul_rn(av.z, mv.z); r.w = __fmul_rn(av.w, mv.w);
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ a, c
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
-      op[i] = CUT ? __fmul_rn(ap[i], mp[i]) : mix1(ap[i], bp[i], mp[i]);
+      const float mi = PER_SAMPLE ? ms : mp[i];
+      op[i] = CUT ? __fmul_rn(ap[i], mi) : mix1(ap[i], bp[i], mi);
     }
   }
 }
@@ -183,9 +186,22 @@ extern "C" int b2_mix(const float* a, const float* b, const float* m, float* out
   if (bx < 1) bx = 1;
   if (bx > 2048) bx = 2048;
   dim3 grid(bx, n * c);
-  if (b) mix_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, m, out, c, hw);
-  else   mix_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a, nullptr, m, out, c, hw);
+  if (b) mix_kernel<false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, m, out, c, hw);
+  else   mix_kernel<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, nullptr, m, out, c, hw);
   B2_LAUNCH_CHECK("mix_kernel");
+  return B2_OK;
+}
+
+extern "C" int b2_mix_per_sample(const float* a, const float* b, const float* factors, float* out, int n, int c,
+                                 int64_t hw, void* stream) {
+  B2_REQUIRE(a && b && factors && out && n > 0 && c > 0 && hw > 0, "b2_mix_per_sample: bad args");
+  B2_REQUIRE((int64_t)n * c <= 65535, "b2_mix_per_sample: n*c too large");
+  int bx = (int)((hw / 4 + 255) / 256);
+  if (bx < 1) bx = 1;
+  if (bx > 2048) bx = 2048;
+  dim3 grid(bx, n * c);
+  mix_kernel<false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, factors, out, c, hw);
+  B2_LAUNCH_CHECK("mix_kernel<per sample>");
   return B2_OK;
 }
 

@@ -2,6 +2,8 @@
 // channel loop strided by H*W so every warp access is a coalesced 128 B line):
 //   L1  consistency block   train_seg_semisup_mask_mt.py:363-367, 406-420, 428-459
 //   L2  supervised CE        train_seg_semisup_mask_mt.py:126, 300-301
+//   L1' ICT consistency block train_seg_semisup_ict.py:306-392: per-sample Beta mix factors, teacher
+//       PROBABILITIES and confidences mixed (not logits), same five loss functions
 // Both write the UNSCALED logit gradient in the same pass and leave the global scalars
 // (conf_rate, 1/n_valid, ramp, cons_weight) to a 1-block finalize kernel + the gradient consumer,
 // so no host synchronisation is needed (the reference syncs at :413, :461, :469).
@@ -15,12 +17,17 @@ enum { LOSS_VAR = 0, LOSS_LOGITS_VAR = 1, LOSS_LOGITS_SMOOTHL1 = 2, LOSS_BCE = 3
 // EXACT: the class count is the compile-time constant MAXC (19 / 21 / 2: the reference's data sets), so the channel
 // loops carry no run-time guards: every load of a pixel's 3*C logits is issued before the first use (with the guarded
 // form the compiler serialised them -- three loads in flight per thread, 1.6 ms for 1.3 GB; profiles/r01_v6_*).
-template <int MAXC, bool EXACT>
+// ICT = true (train_seg_semisup_ict.py): `m` holds ONE mix factor per sample (:306-307); the teacher's two softmaxes are
+// mixed as probabilities (:329) and as confidences (:340-342), the logits mix (:328) feeds the two logit losses.
+// `confbar` (ICT, per-pixel confidence mask): mean over the batch of the confidence mask at this pixel -- the reference's
+// `conf_mask[:, None, :, :]` (:344) turns (N,1,H,W) into (N,1,1,H,W), so `loss_mask * conf_mask` broadcasts to
+// (N,N,1,H,W) and every sample's loss is weighted by the batch-mean confidence of the pixel (b2_ict_conf_mean).
+template <int MAXC, bool EXACT, bool ICT>
 __global__ void __launch_bounds__(LOSS_THREADS)
 consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, const float* __restrict__ ls,
-                   const float* __restrict__ m, const float* __restrict__ lmask, float* __restrict__ dls,
-                   double* __restrict__ partials, int C_rt, int64_t hw, int loss_fn, float conf_thresh,
-                   int conf_per_pixel) {
+                   const float* __restrict__ m, const float* __restrict__ lmask, const float* __restrict__ confbar,
+                   float* __restrict__ dls, double* __restrict__ partials, int C_rt, int64_t hw, int loss_fn,
+                   float conf_thresh, int conf_per_pixel) {
   const int C = EXACT ? MAXC : C_rt;
   __shared__ double red[32];
   const int img = blockIdx.y;
@@ -30,12 +37,39 @@ consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, c
     const int64_t base = (int64_t)img * C * hw + p;
     const int64_t pm = (int64_t)img * hw + p;
     float lt[MAXC], st[MAXC];
-    const float mv = m ? __ldg(m + pm) : 0.0f;
+    const float mv = ICT ? __ldg(m + img) : (m ? __ldg(m + pm) : 0.0f);
     const float om = __fsub_rn(1.0f, mv);
     const float w = lmask ? __ldg(lmask + pm) : 1.0f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) if (c < C) { lt[c] = __ldg(l0 + base + (int64_t)c * hw); st[c] = __ldg(ls + base + (int64_t)c * hw); }
-    if (l1) {
+    float pt[MAXC], ps[MAXC];
+    float pmax = 0.f;
+    if (ICT) {
+      // teacher: softmax of each view (:322-323), then mix probabilities (:329), confidences (:340-342) and logits (:328)
+      float lb[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) lb[c] = __ldg(l1 + base + (int64_t)c * hw);
+      float ma = -CUDART_INF_F, mb = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) { ma = fmaxf(ma, lt[c]); mb = fmaxf(mb, lb[c]); }
+      float pb[MAXC];
+      float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        pt[c] = expf(lt[c] - ma); sum_a += pt[c];
+        pb[c] = expf(lb[c] - mb); sum_b += pb[c];
+      }
+      const float inv_a = 1.0f / sum_a, inv_b = 1.0f / sum_b;
+      float conf_a = 0.f, conf_b = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        const float pa = pt[c] * inv_a, pbv = pb[c] * inv_b;
+        conf_a = fmaxf(conf_a, pa); conf_b = fmaxf(conf_b, pbv);
+        pt[c] = __fadd_rn(__fmul_rn(pa, om), __fmul_rn(pbv, mv));
+        lt[c] = __fadd_rn(__fmul_rn(lt[c], om), __fmul_rn(lb[c], mv));
+      }
+      pmax = __fadd_rn(__fmul_rn(conf_a, om), __fmul_rn(conf_b, mv));
+    } else if (l1) {
       float lb[MAXC];
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) if (c < C) lb[c] = __ldg(l1 + base + (int64_t)c * hw);
@@ -47,23 +81,21 @@ consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, c
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) if (c < C) { mt = fmaxf(mt, lt[c]); ms = fmaxf(ms, st[c]); }
     float sum_t = 0.f, sum_s = 0.f;
-    float pt[MAXC], ps[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) if (c < C) {
-      pt[c] = expf(lt[c] - mt); sum_t += pt[c];
+      if (!ICT) { pt[c] = expf(lt[c] - mt); sum_t += pt[c]; }
       ps[c] = expf(st[c] - ms); sum_s += ps[c];
     }
     // one reciprocal per softmax (the sums lie in [1, C]: always the fast path) instead of C divisions: IEEE division
     // falls into its slow subroutine whenever the numerator is zero / denormal, which is most classes of a confident
     // pixel (3x kernel time on peaked logits, profiles/r01_v8_launch_list_summary.txt); <= 1 ulp from exp / sum
-    const float inv_t = 1.0f / sum_t, inv_s = 1.0f / sum_s;
-    float pmax = 0.f;
+    const float inv_t = ICT ? 1.0f : 1.0f / sum_t, inv_s = 1.0f / sum_s;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) if (c < C) {
-      pt[c] = pt[c] * inv_t; ps[c] = ps[c] * inv_s;
-      pmax = fmaxf(pmax, pt[c]);
+      ps[c] = ps[c] * inv_s;
+      if (!ICT) { pt[c] = pt[c] * inv_t; pmax = fmaxf(pmax, pt[c]); }
     }
-    const float conf = (conf_thresh > 0.0f) ? (pmax >= conf_thresh ? 1.0f : 0.0f) : 1.0f;  // lines 407-411
+    const float conf = (conf_thresh > 0.0f) ? (pmax >= conf_thresh ? 1.0f : 0.0f) : 1.0f;  // lines 407-411 / ict :343
     // per-pixel loss q and dq/dls (g)
     float q = 0.f;
     float g[MAXC];
@@ -125,12 +157,13 @@ consistency_kernel(const float* __restrict__ l0, const float* __restrict__ l1, c
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) if (c < C) g[c] = ps[c] * st_sum - pt[c];
     }
-    const float gw = conf_per_pixel ? w * conf : w;
+    const float cw = (ICT && confbar) ? __ldg(confbar + p) : conf;      // weight of the per-pixel confidence mask
+    const float gw = conf_per_pixel ? w * cw : w;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) if (c < C) dls[base + (int64_t)c * hw] = g[c] * gw;
     s_conf = conf;
     s_q = (double)q * (double)w;
-    s_qc = s_q * conf;
+    s_qc = s_q * cw;
   }
   const int64_t bid = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
   double r;
@@ -154,7 +187,7 @@ extern "C" int b2_consistency_fwd_bwd(const float* l0, const float* l1, const fl
   B2_REQUIRE(n <= 65535, "b2_consistency_fwd_bwd: n too large");
   dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(MC, EX) consistency_kernel<MC, EX><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, m, lmask, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
+#define LAUNCH(MC, EX) consistency_kernel<MC, EX, false><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, m, lmask, nullptr, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
   if (c == 19) LAUNCH(19, true);            // Cityscapes
   else if (c == 21) LAUNCH(21, true);       // Pascal VOC
   else if (c == 2) LAUNCH(2, true);         // ISIC
@@ -164,6 +197,84 @@ extern "C" int b2_consistency_fwd_bwd(const float* l0, const float* l1, const fl
   else LAUNCH(64, false);
 #undef LAUNCH
   B2_LAUNCH_CHECK("consistency_kernel");
+  return B2_OK;
+}
+
+// ---- ICT (train_seg_semisup_ict.py:306-392) ----------------------------------------------------------------------------
+// confbar[p] = mean over the batch of (mix(conf_u0, conf_u1) >= thresh) at pixel p: the weight the reference's
+// (N,N,1,H,W) broadcast gives every sample at that pixel when --conf_per_pixel is set (see consistency_kernel).
+template <int MAXC, bool EXACT>
+__global__ void __launch_bounds__(LOSS_THREADS)
+ict_conf_mean_kernel(const float* __restrict__ l0, const float* __restrict__ l1, const float* __restrict__ lam,
+                     float* __restrict__ confbar, int n, int C_rt, int64_t hw, float conf_thresh) {
+  const int C = EXACT ? MAXC : C_rt;
+  const int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
+  if (p >= hw) return;
+  float acc = 0.f;
+  for (int img = 0; img < n; ++img) {
+    const int64_t base = (int64_t)img * C * hw + p;
+    const float mv = __ldg(lam + img), om = __fsub_rn(1.0f, mv);
+    float la[MAXC], lb[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { la[c] = __ldg(l0 + base + (int64_t)c * hw); lb[c] = __ldg(l1 + base + (int64_t)c * hw); }
+    float ma = -CUDART_INF_F, mb = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { ma = fmaxf(ma, la[c]); mb = fmaxf(mb, lb[c]); }
+    float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { la[c] = expf(la[c] - ma); sum_a += la[c]; lb[c] = expf(lb[c] - mb); sum_b += lb[c]; }
+    const float inv_a = 1.0f / sum_a, inv_b = 1.0f / sum_b;
+    float conf_a = 0.f, conf_b = 0.f;                  // same expressions as consistency_kernel<.., ICT>: identical mask
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) if (c < C) { conf_a = fmaxf(conf_a, la[c] * inv_a); conf_b = fmaxf(conf_b, lb[c] * inv_b); }
+    const float cf = __fadd_rn(__fmul_rn(conf_a, om), __fmul_rn(conf_b, mv));
+    acc += cf >= conf_thresh ? 1.0f : 0.0f;
+  }
+  confbar[p] = acc / (float)n;
+}
+
+extern "C" int b2_ict_conf_mean(const float* l0, const float* l1, const float* lam, float* confbar, int n, int c,
+                                int64_t hw, float conf_thresh, void* stream) {
+  B2_REQUIRE(l0 && l1 && lam && confbar && n > 0 && c > 0 && hw > 0, "b2_ict_conf_mean: bad args");
+  B2_REQUIRE(c <= 64, "b2_ict_conf_mean: C=%d > 64 unsupported", c);
+  const unsigned grid = (unsigned)ceil_div64(hw, LOSS_THREADS);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(MC, EX) ict_conf_mean_kernel<MC, EX><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, lam, confbar, n, c, hw, conf_thresh)
+  if (c == 19) LAUNCH(19, true);
+  else if (c == 21) LAUNCH(21, true);
+  else if (c == 2) LAUNCH(2, true);
+  else if (c <= 8) LAUNCH(8, false);
+  else if (c <= 24) LAUNCH(24, false);
+  else if (c <= 32) LAUNCH(32, false);
+  else LAUNCH(64, false);
+#undef LAUNCH
+  B2_LAUNCH_CHECK("ict_conf_mean_kernel");
+  return B2_OK;
+}
+
+extern "C" int b2_ict_consistency_fwd_bwd(const float* l0, const float* l1, const float* ls, const float* lam,
+                                          const float* lmask, const float* confbar, float* dls, double* partials, int n,
+                                          int c, int64_t hw, int loss_fn, float conf_thresh, int conf_per_pixel,
+                                          void* stream) {
+  B2_REQUIRE(l0 && l1 && ls && lam && dls && partials && n > 0 && c > 0 && hw > 0, "b2_ict_consistency_fwd_bwd: bad args");
+  B2_REQUIRE(c <= 64, "b2_ict_consistency_fwd_bwd: C=%d > 64 unsupported", c);
+  B2_REQUIRE(loss_fn >= 0 && loss_fn <= 4, "b2_ict_consistency_fwd_bwd: unknown loss_fn %d", loss_fn);
+  B2_REQUIRE(n <= 65535, "b2_ict_consistency_fwd_bwd: n too large");
+  B2_REQUIRE(!(conf_per_pixel && conf_thresh > 0.0f && !confbar),
+             "b2_ict_consistency_fwd_bwd: the per-pixel confidence mask needs confbar (b2_ict_conf_mean)");
+  dim3 grid((unsigned)ceil_div64(hw, LOSS_THREADS), n);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* cb = (conf_per_pixel && conf_thresh > 0.0f) ? confbar : nullptr;
+#define LAUNCH(MC, EX) consistency_kernel<MC, EX, true><<<grid, LOSS_THREADS, 0, s>>>(l0, l1, ls, lam, lmask, cb, dls, partials, c, hw, loss_fn, conf_thresh, conf_per_pixel)
+  if (c == 19) LAUNCH(19, true);
+  else if (c == 21) LAUNCH(21, true);
+  else if (c == 2) LAUNCH(2, true);
+  else if (c <= 8) LAUNCH(8, false);
+  else if (c <= 24) LAUNCH(24, false);
+  else if (c <= 32) LAUNCH(32, false);
+  else LAUNCH(64, false);
+#undef LAUNCH
+  B2_LAUNCH_CHECK("consistency_kernel<ict>");
   return B2_OK;
 }
 

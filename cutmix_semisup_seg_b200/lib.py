@@ -73,6 +73,10 @@ _SIGS = {
     'b2_argmax_confusion': (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'b2_box_mask_rasterize': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp]),
     'b2_mix': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    'b2_mix_per_sample': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    'b2_ict_conf_mean': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_vp]),
+    'b2_ict_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f32,
+                                           c_int, c_vp]),
     'b2_consistency_num_partials': (c_i64, [c_int, c_i64]),
     'b2_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                        c_f32, c_int, c_vp]),

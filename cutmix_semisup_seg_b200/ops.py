@@ -140,6 +140,41 @@ class CudaBackend(object):
                    int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
         return out4, dls
 
+    def mix_per_sample(self, a, b, factors, out=None):
+        """ICT image / valid-mask mix (train_seg_semisup_ict.py:310-311): out = a*(1-f) + b*f, f: (N,) fp32, one per sample."""
+        L.require_cuda(a, b, factors)
+        a = a.contiguous(); b = b.contiguous(); factors = factors.contiguous()
+        n, c, h, w = a.shape
+        assert factors.dtype == torch.float32 and factors.numel() == n
+        if out is None:
+            out = torch.empty_like(a)
+        self._call('b2_mix_per_sample', a.data_ptr(), b.data_ptr(), factors.data_ptr(), out.data_ptr(), n, c, h * w, self._s())
+        return out
+
+    def ict_consistency(self, l0, l1, ls, factors, lmask, loss_fn, conf_thresh, conf_per_pixel, ramp, cons_weight, dls=None):
+        """Fused ICT consistency block (train_seg_semisup_ict.py:318-392).  Returns (out4, dls_unscaled) like consistency()."""
+        L.require_cuda(l0, l1, ls, factors, lmask)
+        n, c, h, w = ls.shape
+        hw = h * w
+        factors = factors.contiguous()
+        assert factors.dtype == torch.float32 and factors.numel() == n
+        if dls is None:
+            dls = torch.empty_like(ls)
+        confbar = None
+        if conf_per_pixel and conf_thresh > 0.0:      # the reference's (N,N,1,H,W) broadcast: see include/b200seg.h
+            confbar = torch.empty((hw,), device=ls.device, dtype=torch.float32)
+            self._call('b2_ict_conf_mean', l0.data_ptr(), l1.data_ptr(), factors.data_ptr(), confbar.data_ptr(), n, c, hw,
+                       float(conf_thresh), self._s())
+        npart = L.call('b2_consistency_num_partials', n, hw)
+        partials = torch.empty((npart * 3,), device=ls.device, dtype=torch.float64)
+        out4 = torch.empty((4,), device=ls.device, dtype=torch.float32)
+        self._call('b2_ict_consistency_fwd_bwd', l0.data_ptr(), l1.data_ptr(), ls.data_ptr(), factors.data_ptr(), L.ptr(lmask),
+                   L.ptr(confbar), dls.data_ptr(), partials.data_ptr(), n, c, hw, LOSS_FNS[loss_fn], float(conf_thresh),
+                   int(bool(conf_per_pixel)), self._s())
+        self._call('b2_consistency_finalize', partials.data_ptr(), npart, n * hw, float(conf_thresh),
+                   int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
+        return out4, dls
+
     def cross_entropy(self, logits, labels, ignore_index=255, dlogits=None):
         """Returns (out3, dlogits_unscaled): out3 = [loss, n_valid, grad_scale]."""
         L.require_cuda(logits, labels)

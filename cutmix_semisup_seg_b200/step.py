@@ -175,6 +175,23 @@ class MeanTeacherStep(object):
         self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])             # :458-459
         return out4
 
+    def unsupervised_ict(self, ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, ict_mix_factors, ramp_val=1.0):
+        """ICT (train_seg_semisup_ict.py:306-392): images and valid masks mixed with one Beta factor per sample, teacher
+        probabilities / confidences mixed with the same factor inside the fused loss kernel."""
+        be = self.be
+        f = ict_mix_factors.reshape(-1).to(torch.float32)
+        ux_mixed = be.mix_per_sample(ux0_stu, ux1_stu, f)             # ict :310
+        um_mixed = be.mix_per_sample(um0, um1, f)                     # ict :311
+        with torch.no_grad():                                          # ict :314-316
+            l0 = self.teacher_net.b2_forward(ux0_tea, record=False)[0]
+            l1 = self.teacher_net.b2_forward(ux1_tea, record=False)[0]
+        ls, state = self.student_net.b2_forward(ux_mixed, record=True)            # ict :318
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.ict_consistency(l0, l1, ls, f, um_mixed, self.cons_loss_fn, self.conf_thresh, self.conf_per_pixel,
+                                       ramp, self.cons_weight)
+        self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])             # ict :389-390
+        return out4
+
     def unsupervised_cut(self, ux_tea, ux_stu, um, mask_params, ramp_val=1.0):
         """Lines 371-401 + 406-459 (cut / CutOut mode)."""
         be = self.be
@@ -203,7 +220,12 @@ class MeanTeacherStep(object):
         backward pass instead of two accumulating ones (same sums, different fp32 association)."""
         be = self.be
         batch_x, batch_y = sup_batch
-        if self.mask_mix:
+        ict = 'ict_mix_factors' in ub
+        if ict:
+            f = ub['ict_mix_factors'].reshape(-1).to(torch.float32)
+            ux_in = be.mix_per_sample(ub['ux0_stu'], ub['ux1_stu'], f)    # ict :310
+            loss_mask = be.mix_per_sample(ub['um0'], ub['um1'], f)        # ict :311
+        elif self.mask_mix:
             ux_stu = ub['ux0_stu']
             masks = self.mask_generator.torch_masks_from_params(ub['mask_params'], ux_stu.shape[2:4], ux_stu.device).contiguous()
             ux_in = be.mix(ux_stu, ub['ux1_stu'], masks)                   # :350
@@ -215,15 +237,19 @@ class MeanTeacherStep(object):
             loss_mask = be.mix(ub['um'], None, masks)                      # :401
         (sup_logits, ls), state = self.student_net.b2_forward_multi([batch_x, ux_in], record=True)   # :299, :358 / :395
         with torch.no_grad():                                              # :354-356 / :393
-            if self.mask_mix:
+            if self.mask_mix or ict:
                 (l0, l1), _ = self.teacher_net.b2_forward_multi([ub['ux0_tea'], ub['ux1_tea']], record=False)
             else:
                 l0, l1 = self.teacher_net.b2_forward(ub['ux_tea'], record=False)[0], None
         labels = batch_y[:, 0] if batch_y.dim() == 4 else batch_y
         out3, dsup = be.cross_entropy(sup_logits, labels.contiguous(), ignore_index=255)        # :300
         ramp = ramp_val if self.rampup > 0 else 1.0
-        out4, dls = be.consistency(l0, l1, ls, masks if self.mask_mix else None, loss_mask, self.cons_loss_fn,
-                                   self.conf_thresh, self.conf_per_pixel, ramp, self.cons_weight)
+        if ict:
+            out4, dls = be.ict_consistency(l0, l1, ls, f, loss_mask, self.cons_loss_fn, self.conf_thresh, self.conf_per_pixel,
+                                           ramp, self.cons_weight)
+        else:
+            out4, dls = be.consistency(l0, l1, ls, masks if self.mask_mix else None, loss_mask, self.cons_loss_fn,
+                                       self.conf_thresh, self.conf_per_pixel, ramp, self.cons_weight)
         self.student_net.b2_backward_multi(state, [dsup, dls], [out3[2:3], out4[2:3]])          # :301, :459
         return {'sup_loss': out3[0], 'cons_loss': out4[0], 'conf_rate': out4[1]}
 
@@ -314,7 +340,10 @@ class MeanTeacherStep(object):
         cons, conf = None, None
         if self.cons_weight > 0.0:
             for ub in unsup_batches:
-                if self.mask_mix:
+                if 'ict_mix_factors' in ub:
+                    out4 = self.unsupervised_ict(ub['ux0_tea'], ub['ux0_stu'], ub['um0'], ub['ux1_tea'], ub['ux1_stu'],
+                                                 ub['um1'], ub['ict_mix_factors'], ramp_val)
+                elif self.mask_mix:
                     out4 = self.unsupervised_mix(ub['ux0_tea'], ub['ux0_stu'], ub['um0'], ub['ux1_tea'], ub['ux1_stu'],
                                                  ub['um1'], ub['mask_params'], ramp_val)
                 else:
@@ -334,7 +363,8 @@ class MeanTeacherStep(object):
     def step(self, sup_batch, unsup_batches, ramp_val=1.0, eager=False):
         """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
         unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
-        mode) or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
+        mode), the same with ict_mix_factors ((N,) fp32 Beta draws) instead of mask_params (ICT,
+        train_seg_semisup_ict.py), or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
         {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising.  With `use_cuda_graph` the iteration is captured
         once per (shapes, ramp value) and replayed; inputs may then be pinned host tensors (copied straight into the
         graph's static buffers)."""

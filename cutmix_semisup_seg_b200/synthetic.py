@@ -58,6 +58,31 @@ def make_unsup_batch(n, h, w, seed, mask_generator, mask_mix=True, compact_masks
     return res
 
 
+def make_ict_batch(n, h, w, seed, ict_alpha, paired=False, device='cpu', pin=False):
+    """Dict for MeanTeacherStep.step in ICT mode (train_seg_semisup_ict.py:270-307): two unlabelled views with their valid
+    masks and one Beta(ict_alpha, ict_alpha) mix factor per sample -- float64 numpy draws cast to float32 like the
+    reference's `torch.tensor(..., dtype=torch.float)`."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(12345 + seed)
+    out = {}
+
+    def view():
+        tea = torch.randn((n, 3, h, w), generator=g)
+        stu = tea + 0.1 * torch.randn((n, 3, h, w), generator=g) if paired else tea
+        return tea, stu
+    out['ux0_tea'], out['ux0_stu'] = view()
+    out['ux1_tea'], out['ux1_stu'] = view()
+    out['um0'], out['um1'] = make_valid_mask(n, h, w), make_valid_mask(n, h, w)
+    out['ict_mix_factors'] = torch.tensor(rng.beta(ict_alpha, ict_alpha, size=(n,)), dtype=torch.float)
+    res, cache = {}, {}
+    for k, v in out.items():
+        if id(v) not in cache:
+            t = v.pin_memory() if pin else v
+            cache[id(v)] = t.to(device)
+        res[k] = cache[id(v)]
+    return res
+
+
 def condition_classifier(net, gain):
     """Scale the last classification layer so that teacher soft-max confidences straddle the 0.97 threshold
     on random inputs (random-init networks give conf_rate == 0, i.e. a vacuous consistency loss)."""

@@ -1,0 +1,156 @@
+"""The training procedure shared by the drop-in entry points (`train_seg_semisup_mask_mt.py`, `train_seg_semisup_ict.py`):
+network / optimiser / EMA construction, LR schedules, the per-epoch loop around `MeanTeacherStep.step`, on-device
+evaluation and reporting -- reference train_seg_semisup_mask_mt.py:86-134, 257-530 (the ICT script's outer loop is the
+same code, train_seg_semisup_ict.py:62-110, 226-468; only the unsupervised branch of the iteration differs).
+
+Differences from the reference, forced by the offline / GPU-native setting, are listed in the entry points' docstrings.
+"""
+import os
+import time
+
+
+def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, *, dataset, model, arch, freeze_bn, opt_type,
+                 sgd_momentum, sgd_nesterov, sgd_weight_decay, learning_rate, lr_sched, lr_step_epochs, lr_step_gamma,
+                 lr_poly_power, teacher_alpha, bin_fill_holes, crop_size, cons_loss_fn, cons_weight, conf_thresh,
+                 conf_per_pixel, rampup, unsup_batch_ratio, num_epochs, iters_per_epoch, batch_size, save_model,
+                 no_pretrained, ddp, synthetic_classes):
+    """`make_unsup(batch_size, h, w, seed, device)` -> one unsupervised batch dict for MeanTeacherStep.step (CutMix / CutOut
+    box parameters or ICT mix factors included)."""
+    import numpy as np
+    import torch
+    from architectures import network_architectures
+    import evaluation
+    import lr_schedules
+    import optim_weight_ema
+    from . import step as step_mod, synthetic
+
+    crop = None if crop_size == '' else [int(x.strip()) for x in crop_size.split(',')]
+
+    rank, world = 0, 1
+    if ddp:
+        import torch.distributed as dist
+        dist.init_process_group('nccl')
+        rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch_device = torch.device('cuda', local)
+    torch.cuda.set_device(torch_device)
+
+    if dataset != 'synthetic':
+        try:
+            from datapipe import datasets  # noqa: F401  (the reference's CPU data pipeline, if the user provides it)
+        except ImportError:
+            raise NotImplementedError(
+                'dataset {!r} needs the reference data pipeline (datapipe/, CPU, out of scope of the B200 hot path); put '
+                'the reference repository on PYTHONPATH or use --dataset synthetic'.format(dataset))
+        raise NotImplementedError('real-dataset loaders are wired through the reference datapipe in a later round; '
+                                  'use --dataset synthetic')
+    n_classes = synthetic_classes
+    if bin_fill_holes and n_classes != 2:
+        print('Binary hole filling can only be used with binary (2-class) segmentation datasets')
+        return
+    if crop is None:
+        crop = [321, 321]
+    print('Loaded data')
+
+    NetClass = network_architectures.seg.get(arch)
+    student_net = NetClass(n_classes, pretrained=not no_pretrained).to(torch_device)
+    # one fused launch for the optimiser step + the teacher's EMA step (cutmix_semisup_seg_b200/optim.py: torch's per-tensor
+    # arithmetic incl. the duplicated DeepLab v2 group); B200SEG_FUSED_OPT=0 keeps torch.optim + the EMA kernel
+    student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay,
+                                            fused_kernel=os.environ.get('B200SEG_FUSED_OPT', '1') != '0')
+    if model == 'mean_teacher':
+        teacher_net = NetClass(n_classes, pretrained=False).to(torch_device)
+        for p in teacher_net.parameters():
+            p.requires_grad = False
+        teacher_optim = optim_weight_ema.EMAWeightOptimizer(teacher_net, student_net, teacher_alpha)
+        eval_net = teacher_net
+    elif model == 'pi':
+        teacher_net, teacher_optim, eval_net = student_net, None, student_net
+    else:
+        print('Unknown model type {}'.format(model))
+        return
+    if freeze_bn and not hasattr(student_net, 'freeze_batchnorm'):
+        raise ValueError('Network {} does not support batchnorm freezing'.format(arch))
+    print('Built network')
+
+    if iters_per_epoch == -1:
+        iters_per_epoch = 100
+    total_iters = iters_per_epoch * num_epochs
+    lr_epoch_scheduler, lr_iter_scheduler = lr_schedules.make_lr_schedulers(
+        optimizer=student_optim, total_iters=total_iters, schedule_type=lr_sched, step_epochs=lr_step_epochs,
+        step_gamma=lr_step_gamma, poly_power=lr_poly_power)
+
+    trainer = step_mod.MeanTeacherStep(student_net, teacher_net, student_optim, teacher_optim, mask_generator,
+                                       cons_loss_fn=cons_loss_fn, cons_weight=cons_weight, conf_thresh=conf_thresh,
+                                       conf_per_pixel=conf_per_pixel, rampup=rampup, mask_mix=mask_mix,
+                                       unsup_batch_ratio=unsup_batch_ratio, dist_group=True if ddp else None)
+
+    if rank == 0:
+        print('Settings:')
+        print(', '.join(['{}={}'.format(key, settings[key]) for key in sorted(list(settings.keys()))]))
+
+    h, w = crop
+    iter_i = 0
+    print('Training...')
+    for epoch_i in range(num_epochs):
+        if lr_epoch_scheduler is not None:
+            lr_epoch_scheduler.step(epoch_i)
+        t1 = time.time()
+        ramp_val = network_architectures.sigmoid_rampup(epoch_i, rampup) if rampup > 0 else 1.0
+        student_net.train()
+        if teacher_net is not student_net:
+            teacher_net.train()
+        if freeze_bn:
+            student_net.freeze_batchnorm()
+            if teacher_net is not student_net:
+                teacher_net.freeze_batchnorm()
+        sup_acc = torch.zeros((), device=torch_device)
+        cons_acc = torch.zeros((), device=torch_device)
+        conf_acc = torch.zeros((), device=torch_device)
+        n_unsup_batches = 0
+        for it in range(iters_per_epoch):
+            if lr_iter_scheduler is not None:
+                lr_iter_scheduler.step(iter_i)
+            seed = (iter_i * world + rank) * 7
+            sup = synthetic.make_sup_batch(batch_size, h, w, n_classes, seed, device=torch_device)
+            unsup = []
+            if cons_weight > 0.0:
+                for r in range(unsup_batch_ratio):
+                    unsup.append(make_unsup(batch_size, h, w, seed + 1 + r, torch_device))
+            out = trainer.step(sup, unsup, ramp_val=ramp_val)
+            sup_acc += out['sup_loss']
+            if out['cons_loss'] is not None:
+                cons_acc += out['cons_loss']
+                conf_acc += out['conf_rate'] if conf_thresh > 0.0 else ramp_val
+                n_unsup_batches += len(unsup)
+            iter_i += 1
+        sup_loss_val = float(sup_acc) / iters_per_epoch                # the only host sync of the epoch
+        if np.isnan(sup_loss_val):
+            print('NaN detected; network dead, bailing.')
+            return
+        cons_val = float(cons_acc) / max(n_unsup_batches, 1)
+        conf_val = float(conf_acc) / max(n_unsup_batches, 1)
+
+        eval_net.eval()
+        iou_eval = evaluation.EvaluatorIoU(n_classes, bin_fill_holes)
+        with torch.no_grad():
+            vx, vy = synthetic.make_sup_batch(min(batch_size, 4), h, w, n_classes, 999, device=torch_device)
+            if bin_fill_holes:      # hole filling is a CPU (scipy) post-process of the argmax map, as in the reference
+                pred = torch.argmax(eval_net(vx), dim=1).cpu().numpy()
+                truth = vy.cpu().numpy()
+                for i in range(len(pred)):
+                    iou_eval.sample(truth[i, 0], pred[i], ignore_value=255)
+            else:                   # fused argmax + confusion matrix on the device, one C*C read-back per epoch
+                iou_eval.sample_logits(eval_net(vx), vy, ignore_value=255)
+        iou = iou_eval.score()
+        t2 = time.time()
+        if rank == 0:
+            print('Epoch {}: took {:.3f}s, TRAIN clf loss={:.6f}, consistency loss={:.6f}, conf rate={:.3%}, VAL mIoU={:.3%}, '
+                  '{:.1f} images/s'.format(epoch_i + 1, t2 - t1, sup_loss_val, cons_val, conf_val, iou.mean(),
+                                           iters_per_epoch * batch_size * world / (t2 - t1)))
+            print('-- {}'.format(', '.join(['{:.3%}'.format(x) for x in iou])))
+
+    if save_model and rank == 0:
+        torch.save(eval_net, os.path.join(submit_config.run_dir, 'model.pth'))
+    if ddp:
+        dist.destroy_process_group()

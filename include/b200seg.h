@@ -114,6 +114,26 @@ int b2_mix(const float* a, const float* b, const float* m, float* out, int n, in
            void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ICT (interpolation consistency training) -- train_seg_semisup_ict.py:306-392
+ *   b2_mix_per_sample: out = fl(fl(a*fl(1-f[i])) + fl(b*f[i])) with ONE factor per sample i (:310-311);
+ *     factors: DEVICE fp32 [N] (np.random.beta draws of the host, :306-307).
+ *   b2_ict_consistency_fwd_bwd: the consistency block with ICT's teacher target -- softmax of both teacher views, then
+ *     probabilities (:329), confidences (:340-342) and logits (:328) mixed with the per-sample factor; same five loss
+ *     functions, outputs and partials layout as b2_consistency_fwd_bwd (finish with b2_consistency_finalize).
+ *   b2_ict_conf_mean: confbar[p] = mean over the batch of the confidence mask at pixel p.  REQUIRED when
+ *     conf_per_pixel && conf_thresh > 0: the reference indexes `conf_mask[:, None, :, :]` (:344), the product with the
+ *     (N,1,H,W) loss mask broadcasts to (N,N,1,H,W), i.e. every sample is weighted by the batch-mean mask of the pixel;
+ *     conf_rate stays the mean of the mask itself.  confbar: DEVICE fp32 [H*W].
+ * ------------------------------------------------------------------------------------------ */
+int b2_mix_per_sample(const float* a, const float* b, const float* factors, float* out, int n, int c, int64_t hw,
+                      void* stream);
+int b2_ict_conf_mean(const float* l0, const float* l1, const float* factors, float* confbar, int n, int c, int64_t hw,
+                     float conf_thresh, void* stream);
+int b2_ict_consistency_fwd_bwd(const float* l0, const float* l1, const float* ls, const float* factors,
+                               const float* lmask, const float* confbar, float* dls, double* partials, int n, int c,
+                               int64_t hw, int loss_fn, float conf_thresh, int conf_per_pixel, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459
  *   Inputs (NCHW fp32): l0, l1 teacher logits of the two views (l1 == NULL → cut mode, l_t = l0),
  *   ls student logits, m mix mask (N,1,H,W) (NULL → no logit mixing), lmask per-pixel loss mask

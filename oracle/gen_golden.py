@@ -11,12 +11,15 @@ Contents
   iteration.json    two full iterations of the loop body (train_seg_semisup_mask_mt.py:287-476) driven with the
                     reference modules, reference EMAWeightOptimizer, torch Adam on the reference param groups
   loss_block.json   known answers for the consistency / CE block recorded in SURVEY.md §8c
+  ict_block.json    ICT loss block (train_seg_semisup_ict.py:306-387): the reference's own source lines executed on seeded
+                    tensors, all five loss functions x {scalar / per-pixel confidence mask, ramp-up without threshold}
   entry_point.json  click surface of the reference's `train_seg_semisup_mask_mt.experiment` (option names, flags,
                     defaults, choices) and the parameter list of the job function, plus lr_schedules / sigmoid_rampup
                     known answers the entry point depends on
 """
 import hashlib
 import json
+import math
 import os
 import sys
 import warnings
@@ -204,28 +207,78 @@ def gen_loss_block():
     json.dump(out, open(os.path.join(OUT, 'loss_block.json'), 'w'), indent=1)
 
 
+def gen_ict_block():
+    """ICT loss block: the reference's OWN source lines (train_seg_semisup_ict.py, from the Beta draw to the ramp-up
+    multiplication) are cut out of the script and executed on small seeded tensors; teacher_net / student_net are stand-ins
+    returning fixed logits.  -> tests/golden/ict_block.json (inputs are re-created from the recipe by the tests)."""
+    import textwrap
+    lines = open(os.path.join(REF, 'train_seg_semisup_ict.py')).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.strip() == '# ICT mix factors')
+    end = next(i for i, l in enumerate(lines) if l.strip() == 'consistency_loss = consistency_loss * ramp_val') + 1
+    block = textwrap.dedent('\n'.join(lines[start:end]))
+    assert 'ict_mix_factors = np.random.beta' in block and '[:, None, :, :]' in block
+    N, C, H, W = 3, 5, 6, 6
+    out = dict(recipe='manual_seed(0); l0,l1,ls = randn(3,5,6,6)*4; x0,x1 = randn(3,3,6,6); um0[:,:,0]=0; um1[:,:,:,0]=0.5; '
+                      'np.random.seed(case index); ict_alpha=0.4; tau=0.6', ref_lines=[start + 1, end], cases={})
+    torch.manual_seed(0)
+    l0 = torch.randn(N, C, H, W) * 4; l1 = torch.randn(N, C, H, W) * 4; ls0 = torch.randn(N, C, H, W) * 4
+    x0 = torch.randn(N, 3, H, W); x1 = torch.randn(N, 3, H, W)
+    um0 = torch.ones(N, 1, H, W); um1 = torch.ones(N, 1, H, W); um0[:, :, 0] = 0; um1[:, :, :, 0] = 0.5
+    idx = 0
+    for fn in ('var', 'logits_var', 'logits_smoothl1', 'bce', 'kld'):
+        for tau, pp, rampup in ((0.6, False, -1), (0.6, True, -1), (0.0, False, 5)):
+            ls = ls0.clone().requires_grad_(True)
+            seen = {}
+
+            def teacher_net(x):
+                return l0 if x is x0 else l1
+
+            def student_net(x):
+                seen['mixed'] = x.detach().clone()
+                return ls
+            np.random.seed(idx)
+            ns = dict(np=np, torch=torch, F=F, network_architectures=network_architectures, ict_alpha=0.4,
+                      batch_ux0_tea=x0, batch_ux1_tea=x1, batch_ux0_stu=x0, batch_ux1_stu=x1, batch_um0=um0, batch_um1=um1,
+                      torch_device=torch.device('cpu'), teacher_net=teacher_net, student_net=student_net,
+                      conf_thresh=tau, conf_per_pixel=pp, conf_rate_acc=0.0, rampup=rampup, ramp_val=0.25,
+                      cons_loss_fn=fn, root_n_classes=math.sqrt(C))
+            exec(block, ns)
+            loss = ns['consistency_loss']
+            loss.backward()
+            out['cases']['%s_tau%g_pp%d_ramp%d' % (fn, tau, int(pp), rampup)] = dict(
+                seed=idx, factors=[float(v) for v in ns['ict_mix_factors'].reshape(-1)], loss=float(loss),
+                grad_l1=float(ls.grad.abs().sum()), grad_max=float(ls.grad.abs().max()),
+                conf_rate_acc=float(ns['conf_rate_acc']), mixed_sum=float(seen['mixed'].double().sum()),
+                um_mixed_sum=float(ns['batch_um_mixed'].double().sum()))
+            idx += 1
+    json.dump(out, open(os.path.join(OUT, 'ict_block.json'), 'w'), indent=1)
+
+
 def gen_entry_point():
-    """Reference CLI / job-function surface (train_seg_semisup_mask_mt.py:16-42, 581-650)."""
+    """Reference CLI / job-function surface of the two drop-in scripts (train_seg_semisup_mask_mt.py:16-42, 581-650;
+    train_seg_semisup_ict.py:4-14, 508-577)."""
     import importlib
     import inspect
     import click
-    m = importlib.import_module('train_seg_semisup_mask_mt')
-    assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF))
-    opts = []
-    for p in m.experiment.params:
-        opts.append(dict(name=p.name, opts=list(p.opts), is_flag=bool(getattr(p, 'is_flag', False)),
-                         default=None if callable(p.default) else p.default, type=type(p.type).__name__,
-                         choices=list(p.type.choices) if isinstance(p.type, click.Choice) else None))
-    job = m.train_seg_semisup_mask_mt          # job_helper.job returns the function itself with .submit attached
-    job_params = list(inspect.signature(job).parameters)
-    out = dict(options=opts, job_params=job_params, has_submit=hasattr(job, 'submit'),
-               rampup=[network_architectures.sigmoid_rampup(e, 10) for e in range(0, 12)])
+    out = dict(scripts={}, rampup=[network_architectures.sigmoid_rampup(e, 10) for e in range(0, 12)])
+    for name in ('train_seg_semisup_mask_mt', 'train_seg_semisup_ict'):
+        m = importlib.import_module(name)
+        assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF))
+        opts = []
+        for p in m.experiment.params:
+            opts.append(dict(name=p.name, opts=list(p.opts), is_flag=bool(getattr(p, 'is_flag', False)),
+                             default=None if callable(p.default) else p.default, type=type(p.type).__name__,
+                             choices=list(p.type.choices) if isinstance(p.type, click.Choice) else None))
+        job = getattr(m, name)                     # job_helper.job returns the function itself with .submit attached
+        out['scripts'][name] = dict(options=opts, job_params=list(inspect.signature(job).parameters),
+                                    has_submit=hasattr(job, 'submit'))
     json.dump(out, open(os.path.join(OUT, 'entry_point.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     gen_entry_point(); print('entry point')
+    gen_ict_block(); print('ict block')
     gen_masks(); print('masks')
     gen_state_dicts(); print('state dicts')
     gen_loss_block(); print('loss block')

@@ -108,8 +108,18 @@ class OracleMeanTeacher(object):
         sup_loss.backward()                                                         # :301
         cons_val, conf_val = 0.0, 0.0
         if self.cons_weight > 0.0:
-            m = unsup['mask_params']
-            if self.mask_mix:
+            m = unsup.get('mask_params')
+            if 'ict_mix_factors' in unsup:                                          # train_seg_semisup_ict.py:306-392
+                f = unsup['ict_mix_factors'].reshape(-1, 1, 1, 1)
+                ux_mixed = unsup['ux0_stu'] * (1.0 - f) + unsup['ux1_stu'] * f      # ict :310
+                um_mixed = unsup['um0'] * (1.0 - f) + unsup['um1'] * f              # ict :311
+                with torch.no_grad():                                               # ict :314-316
+                    l0 = self._forward(self.teacher, unsup['ux0_tea'], drop.get('tea0')).detach()
+                    l1 = self._forward(self.teacher, unsup['ux1_tea'], drop.get('tea1')).detach()
+                ls = self._forward(self.student, ux_mixed, drop.get('stu'))         # ict :318
+                loss, conf = TO.ict_consistency_loss(l0, l1, ls, f, um_mixed, self.cons_loss_fn, self.conf_thresh,
+                                                     self.conf_per_pixel, ramp_val, self.rampup)
+            elif self.mask_mix:
                 ux_mixed = unsup['ux0_stu'] * (1 - m) + unsup['ux1_stu'] * m        # :350
                 um_mixed = unsup['um0'] * (1 - m) + unsup['um1'] * m                # :351
                 with torch.no_grad():                                               # :354-356

@@ -179,6 +179,51 @@ def consistency_loss(logits_tea0, logits_tea1, logits_stu, mix_mask, loss_mask, 
     return loss, conf_rate
 
 
+def ict_consistency_loss(logits_u0_tea, logits_u1_tea, logits_cons_stu, ict_mix_factors, loss_mask, cons_loss_fn='var',
+                         conf_thresh=0.97, conf_per_pixel=False, ramp_val=1.0, rampup=-1):
+    """ICT loss block, reference train_seg_semisup_ict.py:320-386 line by line.  `ict_mix_factors`: (N,1,1,1) float32;
+    `loss_mask` = the mixed valid mask (:332).  Returns (consistency_loss, conf_rate) like consistency_loss().
+
+    Kept on purpose: `conf_mask[:, None, :, :]` (:344) is applied to an (N,1,H,W) tensor (max(..., keepdim=True), :338-339),
+    so with --conf_per_pixel the product with the (N,1,H,W) loss mask broadcasts to (N,N,1,H,W)."""
+    prob_u0_tea = F.softmax(logits_u0_tea, dim=1)                                      # :320
+    prob_u1_tea = F.softmax(logits_u1_tea, dim=1)                                      # :321
+    prob_cons_stu = F.softmax(logits_cons_stu, dim=1)                                  # :322
+    logits_cons_tea = logits_u0_tea * (1 - ict_mix_factors) + logits_u1_tea * ict_mix_factors   # :328
+    prob_cons_tea = prob_u0_tea * (1 - ict_mix_factors) + prob_u1_tea * ict_mix_factors         # :329
+    n_classes = logits_cons_stu.shape[1]
+    conf_rate = torch.tensor(float('nan'))
+    if conf_thresh > 0.0:                                                              # :335-351
+        conf_u0_tea = prob_u0_tea.max(dim=1, keepdim=True)[0]
+        conf_u1_tea = prob_u1_tea.max(dim=1, keepdim=True)[0]
+        conf_tea = conf_u0_tea * (1 - ict_mix_factors) + conf_u1_tea * ict_mix_factors
+        conf_mask = (conf_tea >= conf_thresh).float()[:, None, :, :]
+        conf_rate = conf_mask.mean()
+        if not conf_per_pixel:
+            conf_mask = conf_mask.mean()
+        loss_mask = loss_mask * conf_mask
+    if cons_loss_fn == 'var':                                                          # :360-363
+        d = prob_cons_stu - prob_cons_tea
+        q = (d * d).sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'logits_var':                                                 # :364-367
+        d = logits_cons_stu - logits_cons_tea
+        q = (d * d).sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'logits_smoothl1':                                            # :368-371
+        q = F.smooth_l1_loss(logits_cons_stu, logits_cons_tea, reduction='none').sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'bce':                                                        # :372-375
+        eps = 1e-6
+        q = -(prob_cons_tea * torch.log(prob_cons_stu + eps) + (1.0 - prob_cons_tea) * torch.log(1.0 - prob_cons_stu + eps))
+        q = q.sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'kld':                                                        # :376-378
+        q = F.kl_div(F.log_softmax(logits_cons_stu, dim=1), prob_cons_tea, reduction='none').sum(dim=1, keepdim=True)
+    else:
+        raise ValueError(cons_loss_fn)
+    loss = (q * loss_mask).mean()                                                      # :383
+    if rampup > 0:
+        loss = loss * ramp_val                                                         # :386-387
+    return loss, conf_rate
+
+
 def supervised_loss(logits, labels_n1hw):
     """nn.CrossEntropyLoss(ignore_index=255)(logits, y[:, 0]) — :126, :300."""
     return F.cross_entropy(logits, labels_n1hw[:, 0], ignore_index=255)

@@ -1,5 +1,5 @@
-"""CPU: the drop-in entry point keeps the reference's CLI and job-function surface
-(train_seg_semisup_mask_mt.py:16-42, 581-650; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
+"""CPU: the drop-in entry points keep the reference's CLI and job-function surface (train_seg_semisup_mask_mt.py:16-42,
+581-650; train_seg_semisup_ict.py:4-14, 508-577; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
 import inspect
 import json
 import os
@@ -7,7 +7,8 @@ import os
 import click
 import pytest
 
-import train_seg_semisup_mask_mt as entry
+import train_seg_semisup_ict
+import train_seg_semisup_mask_mt
 from architectures import network_architectures
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'entry_point.json')))
@@ -16,13 +17,18 @@ EXTRA_OPTIONS = {'no_pretrained', 'ddp', 'synthetic_classes'}
 EXTRA_CHOICES = {'dataset': {'synthetic'}}
 
 
-def _ours():
-    return {p.name: p for p in entry.experiment.params}
+SCRIPTS = {'train_seg_semisup_mask_mt': train_seg_semisup_mask_mt, 'train_seg_semisup_ict': train_seg_semisup_ict}
+entry = train_seg_semisup_mask_mt
 
 
-def test_every_reference_option_is_kept_with_its_default_and_type():
-    ours = _ours()
-    for ref in GOLD['options']:
+def _ours(script):
+    return {p.name: p for p in SCRIPTS[script].experiment.params}
+
+
+@pytest.mark.parametrize('script', sorted(SCRIPTS))
+def test_every_reference_option_is_kept_with_its_default_and_type(script):
+    ours = _ours(script)
+    for ref in GOLD['scripts'][script]['options']:
         assert ref['name'] in ours, 'missing option --{}'.format(ref['name'])
         p = ours[ref['name']]
         assert list(p.opts) == ref['opts']
@@ -37,22 +43,26 @@ def test_every_reference_option_is_kept_with_its_default_and_type():
             assert set(mine) - set(ref['choices']) <= EXTRA_CHOICES.get(ref['name'], set()), ref['name']
 
 
-def test_only_documented_options_are_added():
-    ref_names = {o['name'] for o in GOLD['options']}
-    assert set(_ours()) - ref_names == EXTRA_OPTIONS
+@pytest.mark.parametrize('script', sorted(SCRIPTS))
+def test_only_documented_options_are_added(script):
+    ref_names = {o['name'] for o in GOLD['scripts'][script]['options']}
+    assert set(_ours(script)) - ref_names == EXTRA_OPTIONS
     for name in EXTRA_OPTIONS:            # additions must not change behaviour unless asked for
-        p = _ours()[name]
+        p = _ours(script)[name]
         assert p.default in (False, 21)
 
 
-def test_job_function_signature_and_submit():
-    params = list(inspect.signature(entry.train_seg_semisup_mask_mt).parameters)
-    assert params[:len(GOLD['job_params'])] == GOLD['job_params']
-    extra = params[len(GOLD['job_params']):]
+@pytest.mark.parametrize('script', sorted(SCRIPTS))
+def test_job_function_signature_and_submit(script):
+    gold = GOLD['scripts'][script]
+    job = getattr(SCRIPTS[script], script)
+    params = list(inspect.signature(job).parameters)
+    assert params[:len(gold['job_params'])] == gold['job_params']
+    extra = params[len(gold['job_params']):]
     assert set(extra) == EXTRA_OPTIONS
-    sig = inspect.signature(entry.train_seg_semisup_mask_mt)
+    sig = inspect.signature(job)
     assert all(sig.parameters[k].default is not inspect.Parameter.empty for k in extra)      # reference callers still work
-    assert GOLD['has_submit'] and callable(entry.train_seg_semisup_mask_mt.submit)
+    assert gold['has_submit'] and callable(job.submit)
 
 
 def test_sigmoid_rampup_known_answers():

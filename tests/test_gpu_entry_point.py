@@ -8,6 +8,7 @@ import re
 import pytest
 from click.testing import CliRunner
 
+import train_seg_semisup_ict
 import train_seg_semisup_mask_mt as entry
 
 pytestmark = pytest.mark.gpu
@@ -22,6 +23,11 @@ CASES = {
                                     '--mask_prop_range', '0:1', '--opt_type', 'sgd', '--sgd_nesterov', '--rampup', '3',
                                     '--unsup_batch_ratio', '2', '--cons_loss_fn', 'logits_var', '--aug_strong_colour'],
     'supervised_only': ['--arch', 'resnet101_deeplab_imagenet', '--cons_weight', '0.0', '--lr_sched', 'cosine'],
+}
+ICT_CASES = {
+    'ict_mean_teacher_dl2': ['--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21', '--ict_alpha', '0.4'],
+    'ict_dl3plus_per_pixel_bce': ['--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes', '19',
+                                  '--conf_per_pixel', '--cons_loss_fn', 'bce', '--opt_type', 'sgd', '--rampup', '2'],
 }
 
 
@@ -47,3 +53,21 @@ def test_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
     # a finished job is not executed twice (job_helper.py:40-52)
     r2 = CliRunner().invoke(entry.experiment, BASE + CASES[name] + ['--job_desc', name], catch_exceptions=False)
     assert r2.exit_code == 0 and 'already executed' in r2.output
+
+
+@pytest.mark.parametrize('name', sorted(ICT_CASES))
+def test_ict_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
+    """train_seg_semisup_ict.py through its click command."""
+    monkeypatch.chdir(tmp_path)
+    r = CliRunner().invoke(train_seg_semisup_ict.experiment, BASE + ICT_CASES[name] + ['--job_desc', name],
+                           catch_exceptions=False)
+    assert r.exit_code == 0, r.output
+    lines = [l for l in r.output.splitlines() if l.startswith('Epoch ')]
+    assert len(lines) == 2, r.output
+    for l in lines:
+        m = re.search(r'TRAIN clf loss=([-0-9.enainf]+), consistency loss=([-0-9.enainf]+), conf rate=([-0-9.]+)%, VAL mIoU=([-0-9.]+)%', l)
+        assert m, l
+        sup, cons, conf, miou = (float(x) for x in m.groups())
+        assert math.isfinite(sup) and sup > 0.0 and math.isfinite(cons) and cons >= 0.0
+        assert 0.0 <= conf <= 100.0 and 0.0 <= miou <= 100.0
+    assert os.path.exists(os.path.join('results', 'train_seg_semisup_ict', 'log_{}.txt'.format(name)))

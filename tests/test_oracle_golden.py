@@ -106,6 +106,31 @@ def test_iteration_matches_reference_loop():
         assert tsum == pytest.approx(exp['teacher_abs_sum'], rel=1e-7)
 
 
+def test_ict_loss_block_matches_the_reference_source_lines():
+    """oracle ICT block (torch_oracle.ict_consistency_loss) vs the reference's own lines executed by gen_golden.py,
+    including the (N,N,1,H,W) broadcast of the per-pixel confidence mask."""
+    from ict_recipe import ict_inputs, parse_case, factors_of
+    gold = json.load(open(os.path.join(G, 'ict_block.json')))
+    l0, l1, ls0, x0, x1, um0, um1 = ict_inputs()
+    assert len(gold['cases']) == 15
+    for key, exp in gold['cases'].items():
+        fn, tau, pp, rampup = parse_case(key)
+        f = factors_of(exp)
+        um = um0 * (1.0 - f) + um1 * f
+        assert float((x0 * (1.0 - f) + x1 * f).double().sum()) == pytest.approx(exp['mixed_sum'], rel=1e-12)
+        assert float(um.double().sum()) == pytest.approx(exp['um_mixed_sum'], rel=1e-12)
+        ls = ls0.clone().requires_grad_(True)
+        loss, conf = TO.ict_consistency_loss(l0, l1, ls, f, um, fn, tau, pp, ramp_val=0.25, rampup=rampup)
+        loss.backward()
+        assert float(loss) == pytest.approx(exp['loss'], rel=1e-6), key
+        assert float(ls.grad.abs().sum()) == pytest.approx(exp['grad_l1'], rel=1e-6), key
+        assert float(ls.grad.abs().max()) == pytest.approx(exp['grad_max'], rel=1e-6), key
+        if tau > 0:
+            assert float(conf) == pytest.approx(exp['conf_rate_acc'], rel=1e-6), key
+        else:
+            assert exp['conf_rate_acc'] == 0.25           # `elif rampup > 0: conf_rate_acc += ramp_val` (:352-353)
+
+
 def test_bit_exact_elementwise_oracles():
     rs = np.random.RandomState(0)
     t = rs.randn(100003).astype(np.float32); s = rs.randn(100003).astype(np.float32)

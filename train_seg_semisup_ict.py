@@ -1,63 +1,42 @@
-"""Drop-in entry point for the reference's `train_seg_semisup_mask_mt.py`: CutMix / CutOut mean-teacher
-semi-supervised segmentation, with the per-iteration hot path (reference lines 287-476) running on the B200
-kernels (cutmix_semisup_seg_b200.step.MeanTeacherStep; the outer loop is cutmix_semisup_seg_b200.train_loop.run_training).
+"""Drop-in entry point for the reference's `train_seg_semisup_ict.py` (interpolation consistency training, SURVEY.md 8f
+row 3): mean-teacher semi-supervised segmentation where the student sees a convex combination of two unlabelled images
+(one Beta(ict_alpha, ict_alpha) factor per sample, reference lines 306-311) and is trained towards the same combination
+of the teacher's predictions (lines 318-392).  The iteration runs on the B200 kernels
+(cutmix_semisup_seg_b200.step.MeanTeacherStep.unsupervised_ict: per-sample mix kernel + the fused ICT consistency kernel);
+the outer loop is cutmix_semisup_seg_b200.train_loop.run_training, shared with train_seg_semisup_mask_mt.py.
 
-The click surface (option names and defaults, reference lines 581-650) and the job function signature are kept.
-Differences, all forced by the offline / GPU-native setting:
-  * `--dataset synthetic` (new choice) trains on synthetic tensors with the DataLoader's tensor contract; the real
-    datasets need the reference's CPU data pipeline (`datapipe`, out of scope of the hot path): if that package is
-    importable it is used unchanged, otherwise a clear error is raised;
-  * `--arch` networks are built with `pretrained` only if the weights are cached locally (`--no_pretrained`);
-  * losses / confidence rate are kept on the device and read once per epoch (the reference synchronises three
-    times per iteration, lines 413, 461, 469); the NaN bail-out is checked at the same point;
-  * `--ddp` (new): data parallelism, one process per GPU launched by torchrun; gradients are averaged with one
-    all-reduce per iteration.
+The click surface (option names and defaults, reference lines 508-577 -- note `--sgd_nesterov` defaults to True and
+`--cons_weight` to 0.3 in this script) and the job function signature are kept; the additions (`--dataset synthetic`,
+`--no_pretrained`, `--ddp`, `--synthetic_classes`) are those of train_seg_semisup_mask_mt.py.  The mix factors are drawn with
+numpy on the host like the reference (one seeded RandomState per batch instead of the global generator).
 """
 import click
 
 import job_helper
 
 
-@job_helper.job('train_seg_semisup_mask_mt', enumerate_job_names=False)
-def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
-                              opt_type, sgd_momentum, sgd_nesterov, sgd_weight_decay,
-                              learning_rate, lr_sched, lr_step_epochs, lr_step_gamma, lr_poly_power,
-                              teacher_alpha, bin_fill_holes,
-                              crop_size, aug_hflip, aug_vflip, aug_hvflip, aug_scale_hung, aug_max_scale,
-                              aug_scale_non_uniform, aug_rot_mag,
-                              aug_strong_colour, aug_colour_brightness, aug_colour_contrast, aug_colour_saturation,
-                              aug_colour_hue, aug_colour_prob, aug_colour_greyscale_prob,
-                              mask_mode, mask_prop_range,
-                              boxmask_n_boxes, boxmask_fixed_aspect_ratio, boxmask_by_size, boxmask_outside_bounds,
-                              boxmask_no_invert,
-                              cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
-                              num_epochs, iters_per_epoch, batch_size,
-                              n_sup, n_unsup, n_val, split_seed, split_path, val_seed, save_preds, save_model,
-                              num_workers, no_pretrained=False, ddp=False, synthetic_classes=21):
+@job_helper.job('train_seg_semisup_ict', enumerate_job_names=False)
+def train_seg_semisup_ict(submit_config, dataset, model, arch, freeze_bn,
+                          opt_type, sgd_momentum, sgd_nesterov, sgd_weight_decay,
+                          learning_rate, lr_sched, lr_step_epochs, lr_step_gamma, lr_poly_power,
+                          teacher_alpha, bin_fill_holes,
+                          crop_size, aug_hflip, aug_vflip, aug_hvflip, aug_scale_hung, aug_max_scale, aug_scale_non_uniform,
+                          aug_rot_mag,
+                          aug_strong_colour, aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
+                          aug_colour_prob, aug_colour_greyscale_prob,
+                          ict_alpha, cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
+                          num_epochs, iters_per_epoch, batch_size,
+                          n_sup, n_unsup, n_val, split_seed, split_path, val_seed, save_preds, save_model, num_workers,
+                          no_pretrained=False, ddp=False, synthetic_classes=21):
     settings = locals().copy()
     del settings['submit_config']
-    import mask_gen
     from cutmix_semisup_seg_b200 import synthetic, train_loop
 
-    if ':' in mask_prop_range:
-        lo, hi = mask_prop_range.split(':')
-        mask_prop_range = (float(lo.strip()), float(hi.strip()))
-    else:
-        mask_prop_range = float(mask_prop_range)
-    if mask_mode not in ('zero', 'mix'):
-        raise ValueError('Unknown mask_mode {}'.format(mask_mode))
-    mask_mix = mask_mode == 'mix'
-    mask_generator = mask_gen.BoxMaskGenerator(prop_range=mask_prop_range, n_boxes=boxmask_n_boxes,
-                                               random_aspect_ratio=not boxmask_fixed_aspect_ratio,
-                                               prop_by_area=not boxmask_by_size, within_bounds=not boxmask_outside_bounds,
-                                               invert=not boxmask_no_invert)
-
     def make_unsup(n, h, w, seed, device):
-        return synthetic.make_unsup_batch(n, h, w, seed, mask_generator, mask_mix=mask_mix, paired=aug_strong_colour,
-                                          device=device)
+        return synthetic.make_ict_batch(n, h, w, seed, ict_alpha, paired=aug_strong_colour, device=device)
 
     train_loop.run_training(
-        submit_config, settings, make_unsup, mask_generator, mask_mix,
+        submit_config, settings, make_unsup, None, True,
         dataset=dataset, model=model, arch=arch, freeze_bn=freeze_bn, opt_type=opt_type, sgd_momentum=sgd_momentum,
         sgd_nesterov=sgd_nesterov, sgd_weight_decay=sgd_weight_decay, learning_rate=learning_rate, lr_sched=lr_sched,
         lr_step_epochs=lr_step_epochs, lr_step_gamma=lr_step_gamma, lr_poly_power=lr_poly_power, teacher_alpha=teacher_alpha,
@@ -76,7 +55,7 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
 @click.option('--freeze_bn', is_flag=True, default=False)
 @click.option('--opt_type', type=click.Choice(['adam', 'sgd']), default='adam')
 @click.option('--sgd_momentum', type=float, default=0.9)
-@click.option('--sgd_nesterov', is_flag=True, default=False)
+@click.option('--sgd_nesterov', is_flag=True, default=True)
 @click.option('--sgd_weight_decay', type=float, default=5e-4)
 @click.option('--learning_rate', type=float, default=1e-4)
 @click.option('--lr_sched', type=click.Choice(['none', 'stepped', 'cosine', 'poly']), default='none')
@@ -100,15 +79,9 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
 @click.option('--aug_colour_hue', type=float, default=0.1)
 @click.option('--aug_colour_prob', type=float, default=0.8)
 @click.option('--aug_colour_greyscale_prob', type=float, default=0.2)
-@click.option('--mask_mode', type=click.Choice(['zero', 'mix']), default='mix')
-@click.option('--mask_prop_range', type=str, default='0.5')
-@click.option('--boxmask_n_boxes', type=int, default=1)
-@click.option('--boxmask_fixed_aspect_ratio', is_flag=True, default=False)
-@click.option('--boxmask_by_size', is_flag=True, default=False)
-@click.option('--boxmask_outside_bounds', is_flag=True, default=False)
-@click.option('--boxmask_no_invert', is_flag=True, default=False)
+@click.option('--ict_alpha', type=float, default=0.1)
 @click.option('--cons_loss_fn', type=click.Choice(['var', 'bce', 'kld', 'logits_var', 'logits_smoothl1']), default='var')
-@click.option('--cons_weight', type=float, default=1.0)
+@click.option('--cons_weight', type=float, default=0.3)
 @click.option('--conf_thresh', type=float, default=0.97)
 @click.option('--conf_per_pixel', is_flag=True, default=False)
 @click.option('--rampup', type=int, default=-1)
@@ -135,14 +108,12 @@ def experiment(job_desc, dataset, model, arch, freeze_bn,
                crop_size, aug_hflip, aug_vflip, aug_hvflip, aug_scale_hung, aug_max_scale, aug_scale_non_uniform, aug_rot_mag,
                aug_strong_colour, aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
                aug_colour_prob, aug_colour_greyscale_prob,
-               mask_mode, mask_prop_range,
-               boxmask_n_boxes, boxmask_fixed_aspect_ratio, boxmask_by_size, boxmask_outside_bounds, boxmask_no_invert,
-               cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
+               ict_alpha, cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
                num_epochs, iters_per_epoch, batch_size,
                n_sup, n_unsup, n_val, split_seed, split_path, val_seed, save_preds, save_model, num_workers,
                no_pretrained, ddp, synthetic_classes):
     params = locals().copy()
-    train_seg_semisup_mask_mt.submit(**params)
+    train_seg_semisup_ict.submit(**params)
 
 
 if __name__ == '__main__':
