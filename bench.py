@@ -172,7 +172,10 @@ def run_b200(args):
     # a small pool of distinct batches (per-iteration working set >> 126 MB L2: activations alone are ~20 GB)
     pool = 3
     sup_host = [synthetic.make_sup_batch(n, h, w, cfg['classes'], 100 + rank * 10 + i, pin=True) for i in range(pool)]
-    uns_host = [synthetic.make_unsup_batch(n, h, w, 200 + rank * 10 + i, mg, pin=True) for i in range(pool)]
+    if args.loss == 'ict':       # train_seg_semisup_ict.py iteration: per-sample Beta mix factors
+        uns_host = [synthetic.make_ict_batch(n, h, w, 200 + rank * 10 + i, 0.1, pin=True) for i in range(pool)]
+    else:
+        uns_host = [synthetic.make_unsup_batch(n, h, w, 200 + rank * 10 + i, mg, pin=True) for i in range(pool)]
     sup_dev = [(a.to(device), b.to(device)) for a, b in sup_host]
     uns_dev = [{k: v.to(device) for k, v in d.items()} for d in uns_host]
 
@@ -244,7 +247,7 @@ def run_b200(args):
         'metric': 'images/sec', 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-        'config': {'workload': cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
+        'config': {'workload': cfg['workload'].replace('CutMix', 'ICT') if args.loss == 'ict' else cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
                    'freeze_bn': True, 'optimizer': trainer.optim_note,
                    'trunk_batching': 'frozen-BN backbone once per network over 2 concatenated mini-batches'
@@ -364,6 +367,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2'])
     ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict'],
+                    help='unsupervised branch: CutMix (the headline workload) or ICT (train_seg_semisup_ict.py)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':
