@@ -77,10 +77,46 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
     *reinterpret_cast<float4*>(col + (int64_t)row * kpad + grp * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
+// The stem of both hot-path networks (7x7, 3 channels, K padded 147 -> 160): the same mapping with every divisor a
+// compile-time constant and the (image, output row) taken from blockIdx.y -- the generic kernel spends most of its time
+// in seven run-time integer divisions per 16 B store (1.7 TB/s; profiles/r01_v11_launch_list_summary.txt).
+template <int C, int KH, int KW, int KPAD>
+__global__ void __launch_bounds__(256) im2col_const_kernel(const float* __restrict__ x, float* __restrict__ col, int h, int w,
+                                                           int ldx, int stride, int pad, int dil, int oh, int ow) {
+  constexpr int GROUPS = KPAD / 4, KREAL = KH * KW * C;
+  const int y_o = blockIdx.y % oh, img = blockIdx.y / oh;
+  const float* __restrict__ ximg = x + (int64_t)img * h * w * ldx;
+  float* __restrict__ crow = col + (int64_t)blockIdx.y * ow * KPAD;
+  const int per_row = ow * GROUPS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const int x_o = i / GROUPS, grp = i - x_o * GROUPS;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = grp * 4 + e;
+      const int tap = k / C, ch = k - tap * C;
+      const int r = tap / KW, s_ = tap - r * KW;
+      float val = 0.f;
+      if (k < KREAL) {
+        const int iy = y_o * stride - pad + r * dil, ix = x_o * stride - pad + s_ * dil;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(ximg + ((int64_t)iy * w + ix) * ldx + ch);
+      }
+      v[e] = val;
+    }
+    *reinterpret_cast<float4*>(crow + (int64_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
                          int dil, int oh, int ow, int kpad, void* stream) {
   B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
   B2_REQUIRE(kpad % 4 == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, "b2_im2col: kpad must be a multiple of 4 and col 16 B aligned");
+  if (c == 3 && kh == 7 && kw == 7 && kpad == 160 && (int64_t)n * oh <= 65535 && (int64_t)ow * 40 < (1ll << 30)) {
+    // 8 stores per thread: one-store blocks are bound by the block launch rate (330 k blocks per stem at 512 x 512)
+    dim3 grid((unsigned)((ow * 40 + 256 * 8 - 1) / (256 * 8)), (unsigned)(n * oh));
+    im2col_const_kernel<3, 7, 7, 160><<<grid, 256, 0, (cudaStream_t)stream>>>(x, col, h, w, ldx, stride, pad, dil, oh, ow);
+    B2_LAUNCH_CHECK("im2col_const_kernel");
+    return B2_OK;
+  }
   const int64_t total = (int64_t)n * oh * ow * (kpad / 4);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 64) blocks = 148 * 64;
   if (total < (1ll << 31)) im2col_kernel<int32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, col, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad);
@@ -919,6 +955,64 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict_
     }
   }
 }
+// Same arithmetic with the thread -> channel mapping fixed for the whole kernel (block = rpb rows x c/4 channel groups,
+// c/4 <= 256): the per-channel constants (mean, rstd, gamma, the two batch means of the reduction) live in registers and
+// the row loop carries no index division, no double-precision multiplies and no per-element constant loads -- the
+// flat-index kernel above is instruction-bound at 2.8 TB/s (profiles/r01_v11_launch_list_summary.txt).  Two rows per
+// iteration keep 6-8 independent 16 B loads in flight per thread.
+__global__ void __launch_bounds__(256) bn_bwd_dx_rows_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                             const float* __restrict__ y, int ldy, int64_t rows, int c,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, int relu, const float* __restrict__ drop,
+                                                             float drop_scale, const double* __restrict__ fin, float* __restrict__ dx, int lddx,
+                                                             float* __restrict__ g_out, int ldgo, int cg, int rpb) {
+  const int lc = threadIdx.x % cg, lr = threadIdx.x / cg;          // blockDim.x == cg * rpb
+  const int ch = lc * 4;
+  const double inv_n = 1.0 / (double)rows;
+  float mu[4], rs[4], ga[4], mdb[4], mdg[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    mu[e] = mean[ch + e]; rs[e] = rstd[ch + e]; ga[e] = gamma[ch + e];
+    mdb[e] = (float)(fin[(ch + e) * 2] * inv_n); mdg[e] = (float)(fin[(ch + e) * 2 + 1] * inv_n);
+  }
+  const int64_t step = (int64_t)gridDim.x * rpb;
+  auto one_row = [&](int64_t row, const float4 q, const float4 qx, const float4 qy, const float4 qd) {
+    float g[4] = {q.x, q.y, q.z, q.w};
+    const float xv[4] = {qx.x, qx.y, qx.z, qx.w}, yv[4] = {qy.x, qy.y, qy.z, qy.w}, dv[4] = {qd.x, qd.y, qd.z, qd.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (relu && !(yv[e] > 0.f)) g[e] = 0.f;
+      if (drop) g[e] *= dv[e] * drop_scale;
+      const float xhat = (xv[e] - mu[e]) * rs[e];
+      o[e] = ga[e] * rs[e] * (g[e] - mdb[e] - xhat * mdg[e]);
+    }
+    if (g_out) *reinterpret_cast<float4*>(g_out + row * ldgo + ch) = make_float4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<float4*>(dx + row * lddx + ch) = make_float4(o[0], o[1], o[2], o[3]);
+  };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t row = (int64_t)blockIdx.x * rpb + lr;
+  for (; row + step < rows; row += 2 * step) {
+    const int64_t r2 = row + step;
+    const float4 qa = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + ch));
+    const float4 qb = __ldg(reinterpret_cast<const float4*>(dy + r2 * lddy + ch));
+    const float4 xa = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch));
+    const float4 xb = __ldg(reinterpret_cast<const float4*>(x + r2 * ldx + ch));
+    const float4 ya = relu ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
+    const float4 yb = relu ? __ldg(reinterpret_cast<const float4*>(y + r2 * ldy + ch)) : zero;
+    const float4 da = drop ? __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)) : zero;
+    const float4 db = drop ? __ldg(reinterpret_cast<const float4*>(drop + r2 * c + ch)) : zero;
+    one_row(row, qa, xa, ya, da);
+    one_row(r2, qb, xb, yb, db);
+  }
+  if (row < rows) {
+    const float4 qa = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + ch));
+    const float4 xa = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch));
+    const float4 ya = relu ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
+    const float4 da = drop ? __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)) : zero;
+    one_row(row, qa, xa, ya, da);
+  }
+}
 __global__ void bn_param_out_kernel(const double* __restrict__ fin, int c, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
@@ -942,7 +1036,11 @@ extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, con
                    (!relu || (ldy % 4 == 0 && al16(y))) && (!dropmask || al16(dropmask)) && (!g_out || (ldgo % 4 == 0 && al16(g_out)));
   const int64_t total = rows * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  if (vec && total < (1ll << 31)) bn_bwd_dx_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
+  if (vec && c / 4 <= 256) {
+    const int cg = c / 4, rpb = 256 / cg;
+    int64_t nb = ceil_div64(rows, rpb); if (nb > 148 * 16) nb = 148 * 16;
+    bn_bwd_dx_rows_kernel<<<(unsigned)nb, cg * rpb, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, cg, rpb);
+  } else if (vec && total < (1ll << 31)) bn_bwd_dx_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
   else if (vec) bn_bwd_dx_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
   else bn_bwd_dx_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
   bn_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, dgamma, dbeta, accumulate_params);
