@@ -430,3 +430,12 @@ def default_backend():
     if _default is None:
         _default = CudaBackend()
     return _default
+
+
+def set_default_backend(backend):
+    """Test hook (like netbase.set_kernels_factory): tests/_emu_backend.py swaps in a torch-CPU double of this op
+    INTERFACE so that the iteration's host logic (step.py, gradient all-reduce) runs without a GPU.  Returns the previous
+    backend object (None: the CUDA backend has not been created yet); the product never calls this."""
+    global _default
+    prev, _default = _default, backend
+    return prev

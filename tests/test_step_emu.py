@@ -1,0 +1,167 @@
+"""Host-logic tests of the training iteration without a GPU: `MeanTeacherStep` (step.py) driven with the torch-CPU doubles of
+the kernel interfaces (tests/_emu_kernels.py for the networks, tests/_emu_backend.py for the losses / mixes / masks) against
+the oracle's iterations (oracle/ref_step.py, pinned to the reference by tests/test_oracle_golden.py).  Covers the CutMix,
+CutOut and ICT branches, the batched-trunk and pass-by-pass schedules, and the world-size-2 data-parallel path over gloo.
+The numerical parity of the real kernels is the job of the `-m gpu` tests."""
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N, H, W, C, LR = 2, 33, 33, 21, 3e-5
+KIND = 'resnet101_deeplab_imagenet'
+
+
+def _install_doubles():
+    from _emu_kernels import EmuKernels
+    from _emu_backend import EmuBackend
+    from cutmix_semisup_seg_b200 import netbase, ops
+    k = EmuKernels()
+    saved = (netbase.get_kernels, ops.set_default_backend(EmuBackend()))
+    netbase.set_kernels_factory(lambda n_split=1: k)
+    return saved
+
+
+def _restore(saved):
+    from cutmix_semisup_seg_b200 import netbase, ops
+    netbase.set_kernels_factory(saved[0])
+    ops.set_default_backend(saved[1])
+
+
+@pytest.fixture()
+def doubles():
+    saved = _install_doubles()
+    yield
+    _restore(saved)
+
+
+def _build(mode, conf_per_pixel, batch_trunk, dist_group=None, cons_loss_fn='var'):
+    import torch_oracle as TO
+    import ref_step
+    import mask_gen
+    from _emu_backend import EmuEMA
+    from architectures import network_architectures as na
+    from cutmix_semisup_seg_b200 import step as step_mod
+    student = na.seg.get(KIND)(C, pretrained=False)
+    final = [k for k in student.state_dict() if 'layer5' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(student.state_dict(), seed=3, logit_gain=4.0, final_keys=final)
+    student.load_state_dict(sd)
+    teacher = na.seg.get(KIND)(C, pretrained=False)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'adam', LR)              # torch Adam, per-tensor loop (duplicated group)
+    ema = EmuEMA(teacher, student, 0.99)
+    student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+    mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, cons_loss_fn=cons_loss_fn, cons_weight=0.7,
+                                       conf_thresh=0.5, conf_per_pixel=conf_per_pixel, mask_mix=(mode != 'cut'),
+                                       batch_trunk=batch_trunk, dist_group=dist_group)
+    orc = ref_step.OracleMeanTeacher('deeplab2', sd, LR, cons_loss_fn=cons_loss_fn, cons_weight=0.7, conf_thresh=0.5,
+                                     conf_per_pixel=conf_per_pixel, mask_mix=(mode != 'cut'))
+    return student, teacher, trainer, orc, mg
+
+
+def _batches(mode, mg, seed):
+    import torch_oracle as TO
+    from cutmix_semisup_seg_b200 import synthetic
+    sup = synthetic.make_sup_batch(N, H, W, C, 10 + seed)
+    if mode == 'ict':
+        uns = synthetic.make_ict_batch(N, H, W, 20 + seed, 0.4)
+        uns_o = dict(uns)
+    else:
+        uns = synthetic.make_unsup_batch(N, H, W, 20 + seed, mg, mask_mix=(mode == 'mix'), compact_masks=True)
+        uns_o = dict(uns)
+        uns_o['mask_params'] = torch.from_numpy(TO.box_masks(uns['mask_params'].numpy(), (H, W), invert=True))
+    return sup, uns, uns_o
+
+
+def _state_gap(net, ref):
+    worst = 0.0
+    for k, v in net.state_dict().items():
+        if v.dtype == torch.float32:
+            r = ref[k].detach()
+            worst = max(worst, (v - r).abs().max().item() / (r.abs().max().item() + 1e-12))
+    return worst
+
+
+@pytest.mark.parametrize('mode,conf_per_pixel,batch_trunk,fn', [('mix', False, True, 'var'), ('mix', True, False, 'kld'),
+                                                               ('cut', False, True, 'logits_var'), ('ict', True, True, 'var'),
+                                                               ('ict', False, False, 'bce')])
+def test_iteration_host_logic_matches_oracle(doubles, mode, conf_per_pixel, batch_trunk, fn):
+    student, teacher, trainer, orc, mg = _build(mode, conf_per_pixel, batch_trunk, cons_loss_fn=fn)
+    assert trainer._can_batch_trunk([None]) == batch_trunk
+    for it in range(2):
+        sup, uns, uns_o = _batches(mode, mg, it)
+        with torch.no_grad():        # the iteration never uses autograd; the torch-CPU doubles would otherwise record a graph
+            out = trainer.step(sup, [uns])
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], uns_o)
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=2e-5)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-4, abs=1e-8)
+        assert float(out['conf_rate']) == pytest.approx(r_ref, abs=1e-6)
+    # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr; everything else ~1e-6
+    assert _state_gap(student, orc.student) < 1.5e-3
+    assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
+# ---------------------------------------------------------------------------------------------- world size 2 (gloo)
+def _dp_worker(rank, world, port, q):
+    try:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        torch.set_num_threads(2)
+        _install_doubles()
+        student, teacher, trainer, orc, mg = _build('mix', False, True, dist_group=True)
+        sup, uns, uns_o = _batches('mix', mg, 100 + rank)                    # every rank draws its own batches / masks
+        with torch.no_grad():
+            out = trainer.step(sup, [uns])
+        # (1) the gradient every rank applied == mean over ranks of the per-shard oracle gradients (SURVEY.md 8e caveat 1)
+        orc.step(sup[0], sup[1], uns_o)                                       # leaves the local gradients in .grad
+        names = [k for k, v in orc.student.items() if v.requires_grad and v.grad is not None]
+        local = torch.cat([orc.student[k].grad.reshape(-1) for k in names])
+        mean = local.clone()
+        dist.all_reduce(mean); mean /= world
+        params = dict(student.named_parameters())
+        got = torch.cat([params[k].grad.reshape(-1) for k in names])         # logical (NCHW) order, like the oracle's
+        gerr = (got - mean).abs().max().item() / (mean.abs().max().item() + 1e-30)
+        differs = (local - mean).abs().max().item() / (mean.abs().max().item() + 1e-30)
+        # (2) parameters stay replicated: identical bits on both ranks after the step
+        flat = torch.cat([p.detach().reshape(-1) for p in student.parameters()])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        same = bool(torch.equal(other[0], other[1]))
+        q.put((rank, gerr, differs, same, float(out['sup_loss'])))
+        dist.destroy_process_group()
+    except Exception as e:                                                    # surface the failure instead of a queue timeout
+        import traceback
+        q.put((rank, 'error', traceback.format_exc(), False, repr(e)))
+
+
+def test_data_parallel_iteration_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, gerr, differs, same, sup in res:
+        assert gerr != 'error', differs
+        assert gerr < 2e-4                     # averaged gradient == mean of the per-shard reference gradients
+        assert differs > 1e-2                  # ... and the shards really had different gradients
+        assert same                            # replicated parameters after the optimiser step
+    assert res[0][4] != res[1][4]              # different batches per rank (losses are rank-local, never reduced)
