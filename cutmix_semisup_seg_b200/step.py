@@ -265,6 +265,7 @@ class MeanTeacherStep(object):
                 d[k] = cache[id(v)]
             st_uns.append(d)
         self._static = (st_sup, st_uns)
+        self._staging, self._staged = None, None
         self._load_static(sup_batch, unsup_batches)
         snap = self._snapshot()            # the warm-up iteration below must not count as a training step
         cur = torch.cuda.current_stream()
@@ -319,6 +320,62 @@ class MeanTeacherStep(object):
                         else:
                             v.zero_()          # state created by the warm-up step: back to its initial value
 
+    # -- input prefetch (graph mode): the NEXT call's pinned host batch is copied to staging buffers on a side stream while
+    # this iteration computes; the next step() then only moves staging -> static buffers device to device.
+    @staticmethod
+    def _same_batch(a, b):
+        (sa, ua), (sb, ub) = a, b
+        if len(sa) != len(sb) or len(ua) != len(ub) or any(x is not y for x, y in zip(sa, sb)):
+            return False
+        return all(da.keys() == db.keys() and all(da[k] is db[k] for k in da) for da, db in zip(ua, ub))
+
+    def _prefetch(self, sup_batch, unsup_batches):
+        st_sup, st_uns = self._static
+        if getattr(self, '_staging', None) is None:
+            cache = {}
+
+            def like(t):
+                if id(t) not in cache:
+                    cache[id(t)] = torch.empty_like(t)
+                return cache[id(t)]
+            self._staging = (tuple(like(t) for t in st_sup), [{k: like(v) for k, v in d.items()} for d in st_uns])
+            self._side = torch.cuda.Stream()
+            self._stage_free = None
+        sg_sup, sg_uns = self._staging
+        if len(sup_batch) != len(sg_sup) or len(unsup_batches) != len(sg_uns):
+            return
+        if self._stage_free is not None:
+            self._side.wait_event(self._stage_free)          # the previous staging -> static copy has read the buffers
+        with torch.cuda.stream(self._side):
+            for dst, src in zip(sg_sup, sup_batch):
+                dst.copy_(src, non_blocking=True)
+            for d, ub in zip(sg_uns, unsup_batches):
+                done = set()
+                for k, v in ub.items():
+                    if id(d[k]) not in done:
+                        d[k].copy_(v, non_blocking=True)
+                        done.add(id(d[k]))
+            self._stage_done = torch.cuda.Event()
+            self._stage_done.record(self._side)
+        self._staged = (tuple(sup_batch), [dict(ub) for ub in unsup_batches])      # keeps the pinned tensors alive
+
+    def _load_staged(self):
+        st_sup, st_uns = self._static
+        sg_sup, sg_uns = self._staging
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_done)
+        for dst, src in zip(st_sup, sg_sup):
+            dst.copy_(src, non_blocking=True)
+        for d, g in zip(st_uns, sg_uns):
+            done = set()
+            for k in d:
+                if id(d[k]) not in done:
+                    d[k].copy_(g[k], non_blocking=True)
+                    done.add(id(d[k]))
+        self._stage_free = torch.cuda.Event()
+        self._stage_free.record(cur)
+        self._staged = None
+
     def _load_static(self, sup_batch, unsup_batches):
         st_sup, st_uns = self._static
         for dst, src in zip(st_sup, sup_batch):
@@ -360,19 +417,24 @@ class MeanTeacherStep(object):
         if self.teacher_optim is not None:
             self.teacher_optim.step()                                  # :466-467
 
-    def step(self, sup_batch, unsup_batches, ramp_val=1.0, eager=False):
+    def step(self, sup_batch, unsup_batches, ramp_val=1.0, eager=False, prefetch=None):
         """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
         unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
         mode), the same with ict_mix_factors ((N,) fp32 Beta draws) instead of mask_params (ICT,
         train_seg_semisup_ict.py), or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
         {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising.  With `use_cuda_graph` the iteration is captured
         once per (shapes, ramp value) and replayed; inputs may then be pinned host tensors (copied straight into the
-        graph's static buffers)."""
+        graph's static buffers).  `prefetch=(sup_batch, unsup_batches)`: the (pinned host) batch of the NEXT call; its
+        host-to-device copy then runs on a side stream underneath this iteration (graph mode; ignored otherwise)."""
         if self.use_cuda_graph and not eager:
             key = (float(ramp_val), tuple(tuple(t.shape) for t in sup_batch))
             if self._graph is None or (self._graph[3], self._graph[4]) != key:
                 self._capture(sup_batch, unsup_batches, ramp_val)
-            self._load_static(sup_batch, unsup_batches)
+            staged = getattr(self, '_staged', None)
+            if staged is not None and self._same_batch(staged, (sup_batch, unsup_batches)):
+                self._load_staged()                    # prefetched during the previous call: device-to-device only
+            else:
+                self._load_static(sup_batch, unsup_batches)
             g1, g2, out = self._graph[0], self._graph[1], self._graph[2]
             g1.replay()
             self._allreduce()
@@ -380,6 +442,8 @@ class MeanTeacherStep(object):
                 self.student_optim.refresh_lr()        # the captured step re-reads the learning rates from pinned memory
             g2.replay()
             self.be.launches += self.launches_per_replay
+            if prefetch is not None:
+                self._prefetch(*prefetch)
             return out
         sup_batch = tuple(t.to(self._device(), non_blocking=True) for t in sup_batch)
         out = self._fwd_bwd(sup_batch, [{k: v.to(self._device(), non_blocking=True) for k, v in ub.items()} for ub in unsup_batches],

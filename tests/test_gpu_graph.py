@@ -63,3 +63,29 @@ def test_graph_replay_equals_eager(kind, classes, fused_opt):
     assert l_graph[0] != l_graph[1] != l_graph[2]          # replays consume the new inputs
     for k in t_eager:
         assert torch.equal(t_eager[k], t_graph[k]), k
+
+
+def test_prefetched_inputs_equal_direct_loads():
+    """`step(..., prefetch=next_batch)`: the next pinned host batch is copied on a side stream during the iteration and moved
+    device-to-device at the start of its own step -- results must be bit-identical to loading every batch directly."""
+    from cutmix_semisup_seg_b200 import synthetic
+    kind, classes, n, h, w = 'resnet101_deeplab_imagenet', 21, 2, 64, 64
+    net = na.seg.get(kind)(classes, pretrained=False)
+    final = [k for k in net.state_dict() if 'layer5' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(net.state_dict(), seed=5, logit_gain=4.0, final_keys=final)
+    results = []
+    for use_prefetch in (False, True):
+        tr, mg = _trainer(kind, classes, copy.deepcopy(sd), True)
+        batches = [(synthetic.make_sup_batch(n, h, w, classes, 30 + it, pin=True),
+                    synthetic.make_unsup_batch(n, h, w, 40 + it, mg, pin=True)) for it in range(4)]
+        losses = []
+        for it, (sup, uns) in enumerate(batches):
+            nxt = (batches[it + 1][0], [batches[it + 1][1]]) if use_prefetch and it + 1 < len(batches) else None
+            out = tr.step(sup, [uns], prefetch=nxt)
+            assert (tr._staged is not None) == (nxt is not None)         # consumed by this step, re-armed with the next
+            losses.append([float(out['sup_loss']), float(out['cons_loss']), float(out['conf_rate'])])
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in tr.teacher_net.state_dict().items()}))
+    (l_direct, t_direct), (l_pref, t_pref) = results
+    assert l_direct == l_pref
+    for k, v in t_direct.items():
+        assert torch.equal(v, t_pref[k]), k
