@@ -50,7 +50,7 @@ class OracleMeanTeacher(object):
 
     def __init__(self, arch, state_dict, learning_rate, opt_type='adam', teacher_alpha=0.99, freeze_bn=True,
                  cons_loss_fn='var', cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                 dtype=torch.float32):
+                 dtype=torch.float32, model='mean_teacher'):
         self.arch, self.freeze_bn = arch, freeze_bn
         self.cons_loss_fn, self.cons_weight = cons_loss_fn, cons_weight
         self.conf_thresh, self.conf_per_pixel, self.rampup, self.mask_mix = conf_thresh, conf_per_pixel, rampup, mask_mix
@@ -59,7 +59,11 @@ class OracleMeanTeacher(object):
         def clone(sd):
             return OrderedDict((k, (v.to(dtype) if v.dtype == torch.float32 else v).clone()) for k, v in sd.items())
         self.student = clone(state_dict)
-        self.teacher = clone(state_dict)          # EMAWeightOptimizer.__init__ copies student -> teacher (:12-13)
+        self.model = model
+        if model == 'pi':                         # :110-113: teacher_net = student_net, no teacher optimiser
+            self.teacher = self.student
+        else:
+            self.teacher = clone(state_dict)      # EMAWeightOptimizer.__init__ copies student -> teacher (:12-13)
         if arch == 'deeplab2':
             for k, v in self.student.items():
                 if deeplab2_trainable(k):
@@ -89,6 +93,8 @@ class OracleMeanTeacher(object):
 
     def ema_step(self):
         """optim_weight_ema.py:21-25 over every float state tensor (parameters and BN running statistics)."""
+        if self.model == 'pi':                    # :466 `if teacher_optim is not None`
+            return
         a = self.teacher_alpha
         one_minus = 1.0 - a
         with torch.no_grad():
@@ -107,7 +113,8 @@ class OracleMeanTeacher(object):
         sup_loss = TO.supervised_loss(logits_sup, sup_y)                            # :300
         sup_loss.backward()                                                         # :301
         cons_val, conf_val = 0.0, 0.0
-        if self.cons_weight > 0.0:
+        unsup_list = unsup if isinstance(unsup, (list, tuple)) else [unsup]        # :304 `for _ in range(unsup_batch_ratio)`
+        for unsup in (unsup_list if self.cons_weight > 0.0 else []):
             m = unsup.get('mask_params')
             if 'ict_mix_factors' in unsup:                                          # train_seg_semisup_ict.py:306-392
                 f = unsup['ict_mix_factors'].reshape(-1, 1, 1, 1)
@@ -136,7 +143,7 @@ class OracleMeanTeacher(object):
                 loss, conf = TO.consistency_loss(lt, None, ls, None, m * unsup['um'], self.cons_loss_fn, self.conf_thresh,
                                                  self.conf_per_pixel, ramp_val, self.rampup)
             (loss * self.cons_weight).backward()                                    # :458-459
-            cons_val, conf_val = float(loss.detach()), float(conf)
+            cons_val += float(loss.detach()); conf_val += float(conf)               # :461 / :413 accumulators
         self.optim.step()                                                           # :465
         self.ema_step()                                                             # :466-467
         return float(sup_loss.detach()), cons_val, conf_val

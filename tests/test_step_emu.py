@@ -115,6 +115,45 @@ def test_iteration_host_logic_matches_oracle(doubles, mode, conf_per_pixel, batc
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
 
 
+def test_loop_variants_pi_model_cutout_rampup_and_batch_ratio(doubles):
+    """`--model pi` (teacher_net is student_net, no EMA; train_seg_semisup_mask_mt.py:110-113) with
+    `--mask_mode zero`, `--rampup` and `--unsup_batch_ratio 2` (:304), paired weak / strong views (:313-323)."""
+    import torch_oracle as TO
+    import ref_step
+    import mask_gen
+    from architectures import network_architectures as na
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    student = na.seg.get(KIND)(C, pretrained=False)
+    final = [k for k in student.state_dict() if 'layer5' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(student.state_dict(), seed=4, logit_gain=4.0, final_keys=final)
+    student.load_state_dict(sd)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'sgd', LR * 10, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4)
+    student.train(); student.freeze_batchnorm()
+    mg = mask_gen.BoxMaskGenerator((0.0, 1.0), invert=True)
+    trainer = step_mod.MeanTeacherStep(student, student, optim, None, mg, cons_loss_fn='logits_smoothl1', cons_weight=0.5,
+                                       conf_thresh=0.0, rampup=3, mask_mix=False, unsup_batch_ratio=2)
+    assert not trainer._can_batch_trunk([None, None])
+    orc = ref_step.OracleMeanTeacher('deeplab2', sd, LR * 10, opt_type='sgd', cons_loss_fn='logits_smoothl1', cons_weight=0.5,
+                                     conf_thresh=0.0, rampup=3, mask_mix=False, model='pi')
+    for it in range(2):
+        sup = synthetic.make_sup_batch(N, H, W, C, 70 + it)
+        uns = [synthetic.make_unsup_batch(N, H, W, 80 + 2 * it + r, mg, mask_mix=False, paired=True) for r in range(2)]
+        uns_o = []
+        for u in uns:
+            d = dict(u)
+            d['mask_params'] = torch.from_numpy(TO.box_masks(u['mask_params'].numpy(), (H, W), invert=True))
+            uns_o.append(d)
+        ramp = 0.3 + 0.2 * it
+        with torch.no_grad():
+            out = trainer.step(sup, uns, ramp_val=ramp)
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], uns_o, ramp_val=ramp)
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=2e-5)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-4, abs=1e-8)          # sum over the two batches (:461)
+    assert _state_gap(student, orc.student) < 1e-4            # SGD: no sign normalisation, weights agree closely
+
+
 # ---------------------------------------------------------------------------------------------- world size 2 (gloo)
 def _dp_worker(rank, world, port, q):
     try:
