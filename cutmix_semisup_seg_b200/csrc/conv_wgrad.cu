@@ -53,7 +53,7 @@ struct UnitInfo {
   int m0, c0, tap, split, pb_begin, pb_end;
 };
 
-__device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, int u) {
+__host__ __device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, int u) {
   UnitInfo r;
   const int ot = u % a.out_tiles;
   r.split = u / a.out_tiles;
@@ -74,17 +74,17 @@ struct PbWalk {
   int w0, h0, n0;      // output-space corner of the box (dY coordinates)
   int xw, xh;          // input-space corner for the unit's tap (X coordinates; may lie in the padding)
   int wt, ht;
-  __device__ __forceinline__ void init(const WgradKArgs& a, int pb, int tap) {
+  __host__ __device__ __forceinline__ void init(const WgradKArgs& a, int pb, int tap) {
     wt = pb % a.tiles_w; const int t = pb / a.tiles_w;
     ht = t % a.tiles_h;
     w0 = wt * a.bw; h0 = ht * a.bh; n0 = (t / a.tiles_h) * a.bn;
     xw = w0 * a.istride + a.dw[tap]; xh = h0 * a.istride + a.dh[tap];
   }
   // false: every input pixel of the box lies in the padding (contributes zero)
-  __device__ __forceinline__ bool active(const WgradKArgs& a) const {
+  __host__ __device__ __forceinline__ bool active(const WgradKArgs& a) const {
     return xh + (a.bh - 1) * a.istride >= 0 && xh < a.ih && xw + (a.bw - 1) * a.istride >= 0 && xw < a.iw;
   }
-  __device__ __forceinline__ void next(const WgradKArgs& a, int tap) {
+  __host__ __device__ __forceinline__ void next(const WgradKArgs& a, int tap) {
     if (++wt < a.tiles_w) { w0 += a.bw; xw += a.bw * a.istride; return; }
     wt = 0; w0 = 0; xw = a.dw[tap];
     if (++ht < a.tiles_h) { h0 += a.bh; xh += a.bh * a.istride; return; }
@@ -94,7 +94,7 @@ struct PbWalk {
 
 // Number of pipeline stages (pixel boxes that are not all padding) of a unit, in closed form: the MMA issuer walks no
 // boxes, its loop is wait / 4 MMAs / commit.  Agrees with PbWalk::active by construction of wlo..hhi (plan_wgrad).
-__device__ __forceinline__ int active_before(const WgradKArgs& a, int tap, int pb) {   // active boxes with index < pb
+__host__ __device__ __forceinline__ int active_before(const WgradKArgs& a, int tap, int pb) {   // active boxes with index < pb
   const int nw = max(a.whi[tap] - a.wlo[tap] + 1, 0), nh = max(a.hhi[tap] - a.hlo[tap] + 1, 0);
   const int wt = pb % a.tiles_w, t = pb / a.tiles_w;
   const int ht = t % a.tiles_h, nt = t / a.tiles_h;
@@ -102,7 +102,7 @@ __device__ __forceinline__ int active_before(const WgradKArgs& a, int tap, int p
   if (ht >= a.hlo[tap] && ht <= a.hhi[tap]) f += min(max(wt - a.wlo[tap], 0), nw);
   return f;
 }
-__device__ __forceinline__ int unit_boxes(const WgradKArgs& a, const UnitInfo& ui) {
+__host__ __device__ __forceinline__ int unit_boxes(const WgradKArgs& a, const UnitInfo& ui) {
   const int n = active_before(a, ui.tap, ui.pb_end) - active_before(a, ui.tap, ui.pb_begin);
   return n > 0 ? n : 1;        // a unit with no contributing box still runs one (all-zero X) box: see the producer
 }
@@ -657,6 +657,31 @@ extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {
   WgradKArgs a;
   if (plan_wgrad(p, &a) != B2_OK) return 0;
   return a.n_splits > 1 ? (size_t)a.n_splits * a.slab_elems * sizeof(float) : 0;
+}
+
+// Host-side self check of the work decomposition (no GPU needed, no tensor is touched): for every work unit of the plan the
+// MMA issuer's closed-form stage count (unit_boxes) must equal the number of boxes the producer's walk (PbWalk) loads --
+// a disagreement would leave one of the two pipeline roles waiting forever.  out[0] = splits, out[1] = work units,
+// out[2] = pipeline stages of the whole launch, out[3] = units that disagree, out[4] = 1 if the CTA-pair kernel is chosen.
+extern "C" int b2_conv_wgrad_plan_check(const b2_wgrad_params* p, int64_t* out) {
+  B2_REQUIRE(out, "b2_conv_wgrad_plan_check: null output");
+  WgradKArgs a;
+  int rc = plan_wgrad(p, &a);
+  if (rc) return rc;
+  int64_t stages = 0, bad = 0;
+  for (int u = 0; u < a.num_units; ++u) {
+    const UnitInfo ui = decode_unit(a, u);
+    int walked = 0; bool any = false;
+    PbWalk b; b.init(a, ui.pb_begin, ui.tap);
+    for (int pb = ui.pb_begin; pb < ui.pb_end; ++pb, b.next(a, ui.tap)) {
+      if (!b.active(a) && !(pb == ui.pb_end - 1 && !any)) continue;
+      any = true; ++walked;
+    }
+    if (walked != unit_boxes(a, ui) || ui.pb_end <= ui.pb_begin) ++bad;
+    stages += (int64_t)walked * a.n_pass;
+  }
+  out[0] = a.n_splits; out[1] = a.num_units; out[2] = stages; out[3] = bad; out[4] = a.m_tile_rows == 2 * W_BLOCK_M;
+  return B2_OK;
 }
 
 extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {

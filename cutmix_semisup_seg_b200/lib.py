@@ -89,6 +89,7 @@ _SIGS = {
     'b2_conv_stats_rows': (c_i64, [ctypes.POINTER(ConvParams)]),
     'b2_conv_wgrad_workspace': (c_sz, [ctypes.POINTER(WgradParams)]),
     'b2_conv_wgrad': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
+    'b2_conv_wgrad_plan_check': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b2_transpose_w': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b2_relu_gate': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp]),

@@ -239,6 +239,9 @@ typedef struct b2_wgrad_params {
 } b2_wgrad_params;
 size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p);
 int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
+/* Host-only self check of the launch plan (no GPU, pointers are not dereferenced): out = int64[5] {splits, work units,
+ * pipeline stages, units whose two stage counts (producer walk vs closed form of the MMA issuer) disagree, CTA-pair kernel}. */
+int b2_conv_wgrad_plan_check(const b2_wgrad_params* p, int64_t* out);
 
 /* Debug knobs (tests only): key 1 = wgrad smem-descriptor variant; key 2 = 1 forces the single-CTA conv kernel. */
 void b2_debug_set(int key, int value);

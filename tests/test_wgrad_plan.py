@@ -1,0 +1,89 @@
+"""CPU: the weight-gradient kernel's launch plan, checked through the C ABI without a GPU (b2_conv_wgrad_plan_check runs the
+product's own planner and box-walk code on the host).  The TMA producer walks the pixel boxes of a work unit, the MMA issuer
+counts them in closed form: both must agree for every unit, or one pipeline role would wait forever on the device."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from cutmix_semisup_seg_b200 import lib as L
+
+
+def _taps(k, dil, pad):
+    t = []
+    for r in range(k):
+        for s in range(k):
+            t += [r * dil - pad, s * dil - pad, r * k + s]
+    return np.array(t, dtype=np.int32)
+
+
+def _check(n, oh, ow, m, c, k, dil, pad, istride=1, kchunk=0, n_split=1, max_ctas=0, ih=None, iw=None):
+    taps = _taps(k, dil, pad)
+    p = L.WgradParams()
+    fake = 0x10000                      # never dereferenced by the planner
+    p.dy, p.x, p.dw = fake, fake, fake
+    if n_split > 1:
+        p.dy_lo, p.x_lo = fake, fake
+    p.n, p.oh, p.ow, p.m, p.ldy = n, oh, ow, m, (m + 3) // 4 * 4
+    p.ih = ih if ih is not None else (oh - 1) * istride + 1
+    p.iw = iw if iw is not None else (ow - 1) * istride + 1
+    p.c, p.ldx, p.istride = c, (c + 3) // 4 * 4, istride
+    p.n_taps, p.taps, p.tw = k * k, taps.ctypes.data, k * k
+    p.accumulate, p.n_split, p.max_ctas, p.kchunk = 0, n_split, max_ctas, kchunk
+    out = (ctypes.c_int64 * 5)()
+    L.call('b2_conv_wgrad_plan_check', ctypes.byref(p), ctypes.cast(out, ctypes.c_void_p))
+    return list(out)
+
+
+HOT_PATH = [
+    # (n, oh, ow, m, c, k, dil, pad)   cfg3 / cfg2 shapes of SURVEY.md appendix A
+    (16, 64, 64, 256, 2048, 3, 12, 12), (16, 64, 64, 256, 2048, 3, 24, 24), (16, 64, 64, 256, 2048, 3, 36, 36),
+    (32, 64, 64, 256, 256, 3, 2, 2), (32, 64, 64, 512, 512, 3, 4, 4), (16, 128, 128, 256, 304, 3, 1, 1),
+    (1, 1, 131072, 1024, 256, 1, 1, 0), (1, 1, 2097152, 64, 160, 1, 1, 0), (32, 128, 128, 64, 64, 3, 1, 1),
+    (16, 41, 41, 21, 2048, 3, 12, 12), (10, 41, 41, 256, 256, 3, 2, 2), (2, 9, 9, 48, 256, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize('shape', HOT_PATH)
+def test_hot_path_shapes_have_consistent_stage_counts(shape):
+    splits, units, stages, bad, pair = _check(*shape)
+    assert bad == 0 and units >= 1 and splits >= 1 and stages >= units
+
+
+def test_cta_pair_kernel_selection_rule():
+    assert _check(16, 64, 64, 256, 2048, 3, 12, 12)[4] == 1          # M % 256 == 0 and C % 64 == 0
+    assert _check(16, 128, 128, 256, 304, 3, 1, 1)[4] == 0           # C = 304: single-CTA kernel, balanced N tiles
+    assert _check(16, 41, 41, 21, 2048, 3, 12, 12)[4] == 0           # 21 classes
+    assert _check(16, 64, 64, 256, 2048, 3, 12, 12, max_ctas=1)[4] == 0
+
+
+def test_padding_taps_are_skipped_but_every_unit_runs_a_stage():
+    # dilation 36 on a 20x20 map: most taps read only padding for most boxes; a unit with no contributing box still
+    # runs one (zero) stage so that its accumulator is written
+    splits, units, stages, bad, _ = _check(2, 20, 20, 256, 256, 3, 36, 36)
+    dense = _check(2, 20, 20, 256, 256, 3, 1, 1)
+    assert bad == 0 and dense[3] == 0
+    assert units <= stages < dense[2]
+
+
+def test_random_geometries_agree():
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        k = int(rs.choice([1, 3]))
+        dil = int(rs.randint(1, 40)) if k == 3 else 1
+        pad = dil * (k // 2) if rs.rand() < 0.7 else int(rs.randint(0, 20)) * (k // 2)
+        s = int(rs.choice([1, 1, 2]))
+        oh, ow, n = int(rs.randint(1, 70)), int(rs.randint(1, 70)), int(rs.randint(1, 6))
+        m, c = int(rs.choice([19, 64, 256, 512])), int(rs.choice([48, 64, 160, 256, 304]))
+        ih = (oh - 1) * s + dil * (k - 1) + 1 - 2 * pad
+        iw = (ow - 1) * s + dil * (k - 1) + 1 - 2 * pad
+        if ih < 1 or iw < 1:
+            continue
+        out = _check(n, oh, ow, m, c, k, dil, pad, istride=s, kchunk=int(rs.choice([0, 0, 256])),
+                     max_ctas=int(rs.choice([0, 0, 7, 40])), ih=ih, iw=iw)
+        assert out[3] == 0, (n, oh, ow, m, c, k, dil, pad, s, out)
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    with pytest.raises(L.B2Error):
+        _check(0, 8, 8, 64, 64, 3, 1, 1)
