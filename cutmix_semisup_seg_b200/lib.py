@@ -77,6 +77,9 @@ _SIGS = {
     'b2_ict_conf_mean': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_vp]),
     'b2_ict_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f32,
                                            c_int, c_vp]),
+    'b2_affine_grid_sample': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'b2_aug_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32,
+                                           c_int, c_vp]),
     'b2_consistency_num_partials': (c_i64, [c_int, c_i64]),
     'b2_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                        c_f32, c_int, c_vp]),

@@ -175,6 +175,39 @@ class CudaBackend(object):
                    int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
         return out4, dls
 
+    def affine_grid_sample(self, x, theta, out_hw=None):
+        """F.grid_sample(x, F.affine_grid(theta, ..., align_corners=True), align_corners=True), bilinear / zero padding
+        (train_seg_semisup_aug_mt.py:302-306).  x: (N,C,H,W) fp32, theta: (N,2,3) fp32."""
+        L.require_cuda(x, theta)
+        x = x.contiguous(); theta = theta.contiguous()
+        n, c, ih, iw = x.shape
+        assert theta.dtype == torch.float32 and tuple(theta.shape) == (n, 2, 3)
+        oh, ow = (ih, iw) if out_hw is None else out_hw
+        y = torch.empty((n, c, oh, ow), device=x.device, dtype=torch.float32)
+        self._call('b2_affine_grid_sample', x.data_ptr(), theta.data_ptr(), y.data_ptr(), n, c, ih, iw, oh, ow, self._s())
+        return y
+
+    def aug_consistency(self, ltea, ls, theta, um0, um1, loss_fn, conf_thresh, conf_per_pixel, ramp, cons_weight, dls=None):
+        """Fused augmentation-consistency block (train_seg_semisup_aug_mt.py:291-391): teacher logits / probabilities / valid
+        mask resampled into student space under the affine map `theta` inside the loss kernel.  Returns (out4, dls_unscaled)
+        like consistency()."""
+        L.require_cuda(ltea, ls, theta, um0, um1)
+        n, c, h, w = ls.shape
+        theta = theta.contiguous(); um0 = um0.contiguous(); um1 = um1.contiguous()
+        assert theta.dtype == torch.float32 and tuple(theta.shape) == (n, 2, 3)
+        assert tuple(ltea.shape) == tuple(ls.shape) and tuple(um0.shape) == (n, 1, h, w) and tuple(um1.shape) == (n, 1, h, w)
+        if dls is None:
+            dls = torch.empty_like(ls)
+        npart = L.call('b2_consistency_num_partials', n, h * w)
+        partials = torch.empty((npart * 3,), device=ls.device, dtype=torch.float64)
+        out4 = torch.empty((4,), device=ls.device, dtype=torch.float32)
+        self._call('b2_aug_consistency_fwd_bwd', ltea.data_ptr(), ls.data_ptr(), theta.data_ptr(), um0.data_ptr(),
+                   um1.data_ptr(), dls.data_ptr(), partials.data_ptr(), n, c, h, w, LOSS_FNS[loss_fn], float(conf_thresh),
+                   int(bool(conf_per_pixel)), self._s())
+        self._call('b2_consistency_finalize', partials.data_ptr(), npart, n * h * w, float(conf_thresh),
+                   int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
+        return out4, dls
+
     def cross_entropy(self, logits, labels, ignore_index=255, dlogits=None):
         """Returns (out3, dlogits_unscaled): out3 = [loss, n_valid, grad_scale]."""
         L.require_cuda(logits, labels)

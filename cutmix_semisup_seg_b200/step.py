@@ -192,6 +192,28 @@ class MeanTeacherStep(object):
         self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])             # ict :389-390
         return out4
 
+    def _check_aug_loss_fn(self):
+        if self.cons_loss_fn == 'logits_var':
+            # same failure as the reference: train_seg_semisup_aug_mt.py:373 reads `delta_prob`, which only the `var` branch
+            # assigns, so the first unsupervised batch raises UnboundLocalError (a NameError)
+            raise UnboundLocalError("local variable 'delta_prob' referenced before assignment "
+                                    "(train_seg_semisup_aug_mt.py:373: the reference's logits_var branch cannot run)")
+
+    def unsupervised_aug(self, ux0, um0, ux1, um1, xf0_to_1, ramp_val=1.0):
+        """Augmentation-driven consistency (train_seg_semisup_aug_mt.py:275-402): teacher on view 0, student on view 1, the
+        teacher's logits / probabilities / valid mask resampled into the student's frame under the affine map `xf0_to_1`
+        (N,2,3) inside the fused loss kernel."""
+        be = self.be
+        self._check_aug_loss_fn()
+        with torch.no_grad():                                          # aug :291-293
+            lt = self.teacher_net.b2_forward(ux0, record=False)[0]
+        ls, state = self.student_net.b2_forward(ux1, record=True)      # aug :295
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.aug_consistency(lt, ls, xf0_to_1.to(torch.float32), um0, um1, self.cons_loss_fn, self.conf_thresh,
+                                       self.conf_per_pixel, ramp, self.cons_weight)
+        self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])  # aug :397-398
+        return out4
+
     def unsupervised_cut(self, ux_tea, ux_stu, um, mask_params, ramp_val=1.0):
         """Lines 371-401 + 406-459 (cut / CutOut mode)."""
         be = self.be
@@ -221,7 +243,11 @@ class MeanTeacherStep(object):
         be = self.be
         batch_x, batch_y = sup_batch
         ict = 'ict_mix_factors' in ub
-        if ict:
+        aug = 'xf0_to_1' in ub
+        if aug:
+            self._check_aug_loss_fn()
+            ux_in = ub['ux1']                                              # aug :295 (no mixing: the views differ geometrically)
+        elif ict:
             f = ub['ict_mix_factors'].reshape(-1).to(torch.float32)
             ux_in = be.mix_per_sample(ub['ux0_stu'], ub['ux1_stu'], f)    # ict :310
             loss_mask = be.mix_per_sample(ub['um0'], ub['um1'], f)        # ict :311
@@ -237,14 +263,19 @@ class MeanTeacherStep(object):
             loss_mask = be.mix(ub['um'], None, masks)                      # :401
         (sup_logits, ls), state = self.student_net.b2_forward_multi([batch_x, ux_in], record=True)   # :299, :358 / :395
         with torch.no_grad():                                              # :354-356 / :393
-            if self.mask_mix or ict:
+            if aug:
+                l0, l1 = self.teacher_net.b2_forward(ub['ux0'], record=False)[0], None     # aug :291-293
+            elif self.mask_mix or ict:
                 (l0, l1), _ = self.teacher_net.b2_forward_multi([ub['ux0_tea'], ub['ux1_tea']], record=False)
             else:
                 l0, l1 = self.teacher_net.b2_forward(ub['ux_tea'], record=False)[0], None
         labels = batch_y[:, 0] if batch_y.dim() == 4 else batch_y
         out3, dsup = be.cross_entropy(sup_logits, labels.contiguous(), ignore_index=255)        # :300
         ramp = ramp_val if self.rampup > 0 else 1.0
-        if ict:
+        if aug:
+            out4, dls = be.aug_consistency(l0, ls, ub['xf0_to_1'].to(torch.float32), ub['um0'], ub['um1'], self.cons_loss_fn,
+                                           self.conf_thresh, self.conf_per_pixel, ramp, self.cons_weight)
+        elif ict:
             out4, dls = be.ict_consistency(l0, l1, ls, f, loss_mask, self.cons_loss_fn, self.conf_thresh, self.conf_per_pixel,
                                            ramp, self.cons_weight)
         else:
@@ -397,7 +428,9 @@ class MeanTeacherStep(object):
         cons, conf = None, None
         if self.cons_weight > 0.0:
             for ub in unsup_batches:
-                if 'ict_mix_factors' in ub:
+                if 'xf0_to_1' in ub:
+                    out4 = self.unsupervised_aug(ub['ux0'], ub['um0'], ub['ux1'], ub['um1'], ub['xf0_to_1'], ramp_val)
+                elif 'ict_mix_factors' in ub:
                     out4 = self.unsupervised_ict(ub['ux0_tea'], ub['ux0_stu'], ub['um0'], ub['ux1_tea'], ub['ux1_stu'],
                                                  ub['um1'], ub['ict_mix_factors'], ramp_val)
                 elif self.mask_mix:
@@ -421,7 +454,8 @@ class MeanTeacherStep(object):
         """One full iteration.  `sup_batch` = (image, labels); `unsup_batches` = list (length
         unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
         mode), the same with ict_mix_factors ((N,) fp32 Beta draws) instead of mask_params (ICT,
-        train_seg_semisup_ict.py), or ux_tea, ux_stu, um, mask_params (cut mode).  Returns device scalars
+        train_seg_semisup_ict.py), or ux_tea, ux_stu, um, mask_params (cut mode), or ux0, um0, ux1, um1, xf0_to_1 ((N,2,3) fp32
+        affine maps; augmentation consistency, train_seg_semisup_aug_mt.py).  Returns device scalars
         {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising.  With `use_cuda_graph` the iteration is captured
         once per (shapes, ramp value) and replayed; inputs may then be pinned host tensors (copied straight into the
         graph's static buffers).  `prefetch=(sup_batch, unsup_batches)`: the (pinned host) batch of the NEXT call; its

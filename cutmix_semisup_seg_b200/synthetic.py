@@ -83,6 +83,35 @@ def make_ict_batch(n, h, w, seed, ict_alpha, paired=False, device='cpu', pin=Fal
     return res
 
 
+def make_aug_batch(n, h, w, seed, paired=False, rot_mag=0.2, max_scale=1.2, offset=0.15, device='cpu', pin=False):
+    """Dict for MeanTeacherStep.step in augmentation-consistency mode (train_seg_semisup_aug_mt.py:275-281): two views of the
+    unlabelled images with their valid masks and `xf0_to_1` (N,2,3) fp32, the affine map from the student's (view 1)
+    normalised coordinates to the teacher's (view 0) that the reference's DataLoader derives from the two crops' transforms
+    (datapipe/seg_data.py:223-231).  Here: a random rotation (+-rot_mag rad), log-uniform scale in [1/max_scale, max_scale]
+    and translation (+-offset of the half extent) per sample, like SegCVTransformRandomCropRotateScale's ranges."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(12345 + seed)
+    out = {}
+    out['ux0'] = torch.randn((n, 3, h, w), generator=g)
+    out['ux1'] = out['ux0'] + 0.1 * torch.randn((n, 3, h, w), generator=g) if paired else torch.randn((n, 3, h, w), generator=g)
+    out['um0'], out['um1'] = make_valid_mask(n, h, w), make_valid_mask(n, h, w)
+    ang = rng.uniform(-rot_mag, rot_mag, size=(n,))
+    sc = np.exp(rng.uniform(-np.log(max_scale), np.log(max_scale), size=(n,)))
+    tx, ty = rng.uniform(-offset, offset, size=(n,)), rng.uniform(-offset, offset, size=(n,))
+    asp = float(h) / float(w)              # normalised coordinates: a rotation in pixel space is sheared by the aspect ratio
+    xf = np.zeros((n, 2, 3), dtype=np.float64)
+    xf[:, 0, 0] = sc * np.cos(ang); xf[:, 0, 1] = -sc * np.sin(ang) * asp; xf[:, 0, 2] = tx
+    xf[:, 1, 0] = sc * np.sin(ang) / asp; xf[:, 1, 1] = sc * np.cos(ang); xf[:, 1, 2] = ty
+    out['xf0_to_1'] = torch.tensor(xf.astype(np.float32))
+    res, cache = {}, {}
+    for k, v in out.items():
+        if id(v) not in cache:
+            t = v.pin_memory() if pin else v
+            cache[id(v)] = t.to(device)
+        res[k] = cache[id(v)]
+    return res
+
+
 def condition_classifier(net, gain):
     """Scale the last classification layer so that teacher soft-max confidences straddle the 0.97 threshold
     on random inputs (random-init networks give conf_rate == 0, i.e. a vacuous consistency loss)."""

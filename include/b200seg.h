@@ -134,6 +134,26 @@ int b2_ict_consistency_fwd_bwd(const float* l0, const float* l1, const float* ls
                                int64_t hw, int loss_fn, float conf_thresh, int conf_per_pixel, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Augmentation-driven consistency -- train_seg_semisup_aug_mt.py:291-391
+ *   The teacher predicts on view 0, the student on view 1; theta: DEVICE fp32 [N,2,3] = the batch's `xf0_to_1` (:281),
+ *   the affine map from student-space to teacher-space normalised coordinates.
+ *   b2_affine_grid_sample: y = F.grid_sample(x, F.affine_grid(theta, (N,C,OH,OW), align_corners=True), align_corners=True)
+ *     (bilinear, zero padding: :302-306, :312).  x: (N,C,IH,IW), y: (N,C,OH,OW), NCHW fp32.
+ *   b2_aug_consistency_fwd_bwd: the whole block in one pass -- per student pixel the sampling position, the four teacher
+ *     pixels, their soft-maxes, interpolated teacher logits / probabilities / valid mask (loss mask = sampled um0 * um1,
+ *     :306), confidence threshold on the interpolated probabilities (:345-352), the five loss functions (:366-387; the
+ *     reference's `logits_var` branch reads an unassigned variable and raises -- the host wrapper raises the same
+ *     error, the kernel itself implements the formula of the sibling scripts), un-scaled student gradient and partials.
+ *     ltea, ls, dls: (N,C,H,W); um0, um1: (N,1,H,W); outputs / partials layout as b2_consistency_fwd_bwd (count:
+ *     b2_consistency_num_partials(n, h*w)); finish with b2_consistency_finalize.
+ * ------------------------------------------------------------------------------------------ */
+int b2_affine_grid_sample(const float* x, const float* theta, float* y, int n, int c, int ih, int iw, int oh, int ow,
+                          void* stream);
+int b2_aug_consistency_fwd_bwd(const float* ltea, const float* ls, const float* theta, const float* um0,
+                               const float* um1, float* dls, double* partials, int n, int c, int h, int w, int loss_fn,
+                               float conf_thresh, int conf_per_pixel, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459
  *   Inputs (NCHW fp32): l0, l1 teacher logits of the two views (l1 == NULL → cut mode, l_t = l0),
  *   ls student logits, m mix mask (N,1,H,W) (NULL → no logit mixing), lmask per-pixel loss mask

@@ -13,6 +13,7 @@ Contents
   loss_block.json   known answers for the consistency / CE block recorded in SURVEY.md §8c
   ict_block.json    ICT loss block (train_seg_semisup_ict.py:306-387): the reference's own source lines executed on seeded
                     tensors, all five loss functions x {scalar / per-pixel confidence mask, ramp-up without threshold}
+  aug_block.json    augmentation-consistency loss block (train_seg_semisup_aug_mt.py:291-394), the same way
   entry_point.json  click surface of the reference's `train_seg_semisup_mask_mt.experiment` (option names, flags,
                     defaults, choices) and the parameter list of the job function, plus lr_schedules / sigmoid_rampup
                     known answers the entry point depends on
@@ -254,6 +255,49 @@ def gen_ict_block():
     json.dump(out, open(os.path.join(OUT, 'ict_block.json'), 'w'), indent=1)
 
 
+def gen_aug_block():
+    """Augmentation-consistency loss block: the reference's OWN source lines (train_seg_semisup_aug_mt.py, from the teacher
+    prediction to the ramp-up multiplication, :291-394) executed on small seeded tensors with stand-in networks returning
+    fixed logits.  `affine_align_corners_kw` is restated as dict(align_corners=True) (datapipe/torch_utils.py:10-12 for
+    torch >= 1.3; that module imports distutils, which Python 3.12 no longer ships).  -> tests/golden/aug_block.json, plus
+    the three resampled tensors of the block as checksums (inputs are re-created from tests/aug_recipe.py)."""
+    import textwrap
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    from aug_recipe import aug_inputs
+    lines = open(os.path.join(REF, 'train_seg_semisup_aug_mt.py')).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.strip() == '# Get teacher predictions for image0')
+    end = next(i for i, l in enumerate(lines) if l.strip() == 'consistency_loss = consistency_loss * ramp_val') + 1
+    block = textwrap.dedent('\n'.join(lines[start:end]))
+    assert 'F.affine_grid(batch_ufx0_to_1' in block and 'F.grid_sample(prob_cons_tea' in block
+    lt, ls0, x0, x1, um0, um1, theta = aug_inputs()
+    C = lt.shape[1]
+    out = dict(recipe='tests/aug_recipe.py::aug_inputs(); tau=0.6; ramp_val=0.25', ref_lines=[start + 1, end], cases={})
+    for fn in ('var', 'logits_var', 'logits_smoothl1', 'bce', 'kld'):
+        for tau, pp, rampup in ((0.6, False, -1), (0.6, True, -1), (0.0, False, 5)):
+            ls = ls0.clone().requires_grad_(True)
+            ns = dict(np=np, torch=torch, F=F, network_architectures=network_architectures,
+                      affine_align_corners_kw=dict(align_corners=True),
+                      batch_ux0=x0, batch_ux1=x1, batch_um0=um0, batch_um1=um1, batch_ufx0_to_1=theta,
+                      teacher_net=lambda x: lt, student_net=lambda x: ls,
+                      conf_thresh=tau, conf_per_pixel=pp, conf_rate_acc=0.0, rampup=rampup, ramp_val=0.25,
+                      cons_loss_fn=fn, root_n_classes=math.sqrt(C))
+            key = '%s_tau%g_pp%d_ramp%d' % (fn, tau, int(pp), rampup)
+            try:
+                exec(block, ns)
+            except NameError as e:              # the logits_var branch reads `delta_prob` before assignment (:373)
+                out['cases'][key] = dict(raises=type(e).__name__, message=str(e))
+                continue
+            loss = ns['consistency_loss']
+            loss.backward()
+            out['cases'][key] = dict(
+                loss=float(loss), grad_l1=float(ls.grad.abs().sum()), grad_max=float(ls.grad.abs().max()),
+                conf_rate_acc=float(ns['conf_rate_acc']),
+                mask_sum=float(ns['mask_tea_in_stu'].double().sum()),
+                logits_in_stu_abs_sum=float(ns['logits_cons_tea_in_stu'].double().abs().sum()),
+                prob_in_stu_sum=float(ns['prob_cons_tea_in_stu'].double().sum()))
+    json.dump(out, open(os.path.join(OUT, 'aug_block.json'), 'w'), indent=1)
+
+
 def gen_entry_point():
     """Reference CLI / job-function surface of the two drop-in scripts (train_seg_semisup_mask_mt.py:16-42, 581-650;
     train_seg_semisup_ict.py:4-14, 508-577)."""
@@ -261,7 +305,7 @@ def gen_entry_point():
     import inspect
     import click
     out = dict(scripts={}, rampup=[network_architectures.sigmoid_rampup(e, 10) for e in range(0, 12)])
-    for name in ('train_seg_semisup_mask_mt', 'train_seg_semisup_ict'):
+    for name in ('train_seg_semisup_mask_mt', 'train_seg_semisup_ict', 'train_seg_semisup_aug_mt'):
         m = importlib.import_module(name)
         assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF))
         opts = []
@@ -279,6 +323,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     gen_entry_point(); print('entry point')
     gen_ict_block(); print('ict block')
+    gen_aug_block(); print('aug block')
     gen_masks(); print('masks')
     gen_state_dicts(); print('state dicts')
     gen_loss_block(); print('loss block')

@@ -116,7 +116,13 @@ class OracleMeanTeacher(object):
         unsup_list = unsup if isinstance(unsup, (list, tuple)) else [unsup]        # :304 `for _ in range(unsup_batch_ratio)`
         for unsup in (unsup_list if self.cons_weight > 0.0 else []):
             m = unsup.get('mask_params')
-            if 'ict_mix_factors' in unsup:                                          # train_seg_semisup_ict.py:306-392
+            if 'xf0_to_1' in unsup:                                                 # train_seg_semisup_aug_mt.py:275-398
+                with torch.no_grad():                                               # aug :291-293
+                    lt = self._forward(self.teacher, unsup['ux0'], drop.get('tea0')).detach()
+                ls = self._forward(self.student, unsup['ux1'], drop.get('stu'))     # aug :295
+                loss, conf = TO.aug_consistency_loss(lt, ls, unsup['xf0_to_1'], unsup['um0'], unsup['um1'], self.cons_loss_fn,
+                                                     self.conf_thresh, self.conf_per_pixel, ramp_val, self.rampup)
+            elif 'ict_mix_factors' in unsup:                                        # train_seg_semisup_ict.py:306-392
                 f = unsup['ict_mix_factors'].reshape(-1, 1, 1, 1)
                 ux_mixed = unsup['ux0_stu'] * (1.0 - f) + unsup['ux1_stu'] * f      # ict :310
                 um_mixed = unsup['um0'] * (1.0 - f) + unsup['um1'] * f              # ict :311

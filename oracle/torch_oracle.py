@@ -224,6 +224,58 @@ def ict_consistency_loss(logits_u0_tea, logits_u1_tea, logits_cons_stu, ict_mix_
     return loss, conf_rate
 
 
+def aug_consistency_loss(logits_cons_tea, logits_cons_stu, xf0_to_1, um0, um1, cons_loss_fn='var', conf_thresh=0.97,
+                         conf_per_pixel=False, ramp_val=1.0, rampup=-1, strict_reference=True):
+    """Augmentation-driven consistency block, reference train_seg_semisup_aug_mt.py:302-391 line by line: the teacher's
+    logits, soft-max probabilities and valid mask are resampled into the student's frame with
+    F.affine_grid / F.grid_sample (align_corners=True: datapipe/torch_utils.py:10-12 on torch >= 1.3).  `xf0_to_1`: (N,2,3).
+    Returns (consistency_loss, conf_rate) like consistency_loss().
+
+    Kept on purpose: the reference's `logits_var` branch (:370-374) overwrites its result with `delta_prob * delta_prob`,
+    a variable only the `var` branch assigns, so it raises UnboundLocalError; `strict_reference=False` evaluates the
+    formula of the sibling scripts instead (used to check the kernel's loss_fn = 1 path)."""
+    kw = dict(align_corners=True)
+    grid_tea_to_stu = F.affine_grid(xf0_to_1, logits_cons_tea.shape[:1] + (3,) + logits_cons_tea.shape[2:], **kw)   # :302
+    logits_cons_tea_in_stu = F.grid_sample(logits_cons_tea, grid_tea_to_stu, **kw)                  # :304
+    mask_tea_in_stu = F.grid_sample(um0, grid_tea_to_stu, **kw) * um1                               # :306
+    prob_cons_tea = F.softmax(logits_cons_tea, dim=1)                                               # :309
+    prob_cons_stu = F.softmax(logits_cons_stu, dim=1)                                               # :310
+    prob_cons_tea_in_stu = F.grid_sample(prob_cons_tea, grid_tea_to_stu, **kw)                      # :312
+    loss_mask = mask_tea_in_stu                                                                     # :341
+    n_classes = logits_cons_stu.shape[1]
+    conf_rate = torch.tensor(float('nan'))
+    if conf_thresh > 0.0:                                                                           # :345-356
+        conf_tea = prob_cons_tea_in_stu.max(dim=1)[0]
+        conf_mask = (conf_tea >= conf_thresh).float()[:, None, :, :]
+        conf_rate = conf_mask.mean()
+        if not conf_per_pixel:
+            conf_mask = conf_mask.mean()
+        loss_mask = loss_mask * conf_mask
+    if cons_loss_fn == 'var':                                                                       # :366-369
+        d = prob_cons_stu - prob_cons_tea_in_stu
+        q = (d * d).sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'logits_var':                                                              # :370-374
+        if strict_reference:
+            raise UnboundLocalError("local variable 'delta_prob' referenced before assignment")
+        d = logits_cons_stu - logits_cons_tea_in_stu
+        q = (d * d).sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'logits_smoothl1':                                                         # :375-378
+        q = F.smooth_l1_loss(logits_cons_stu, logits_cons_tea_in_stu, reduction='none').sum(dim=1, keepdim=True) / math.sqrt(n_classes)
+    elif cons_loss_fn == 'bce':                                                                     # :379-382
+        eps = 1e-6
+        q = -(prob_cons_tea_in_stu * torch.log(prob_cons_stu + eps) +
+              (1.0 - prob_cons_tea_in_stu) * torch.log(1.0 - prob_cons_stu + eps))
+        q = q.sum(dim=1, keepdim=True)
+    elif cons_loss_fn == 'kld':                                                                     # :383-385
+        q = F.kl_div(F.log_softmax(logits_cons_stu, dim=1), prob_cons_tea_in_stu, reduction='none').sum(dim=1, keepdim=True)
+    else:
+        raise ValueError('Unknown consistency loss function {}'.format(cons_loss_fn))               # :386-387
+    loss = (q * loss_mask).mean()                                                                   # :390
+    if rampup > 0:
+        loss = loss * ramp_val                                                                      # :393-394
+    return loss, conf_rate
+
+
 def supervised_loss(logits, labels_n1hw):
     """nn.CrossEntropyLoss(ignore_index=255)(logits, y[:, 0]) — :126, :300."""
     return F.cross_entropy(logits, labels_n1hw[:, 0], ignore_index=255)

@@ -144,6 +144,65 @@ class EmuBackend(object):
         return self._finish(q, g, wmask, conf, cw, conf_thresh, conf_per_pixel, ramp, cons_weight)
 
 
+    # ------------------------------------------------------------------ augmentation consistency (aug_mt)
+    @staticmethod
+    def _affine_taps(theta, oh, ow, ih, iw):
+        """affine_bilinear_tap() of losses.cu in tensor form: flat teacher offsets (N,4,OH,OW; -1 = outside) and weights
+        in the order nw, ne, sw, se."""
+        def lin(n):
+            if n <= 1:
+                return torch.zeros((max(n, 1),))
+            i = torch.arange(n, dtype=torch.float32)
+            step = torch.tensor(2.0 / (n - 1), dtype=torch.float32)
+            return torch.where(i < n // 2, -1.0 + step * i, 1.0 - step * (n - 1 - i))
+        xb = lin(ow)[None, None, :]; yb = lin(oh)[None, :, None]
+        t = theta.reshape(-1, 6)
+        gx = xb * t[:, 0, None, None] + yb * t[:, 1, None, None] + t[:, 2, None, None]
+        gy = xb * t[:, 3, None, None] + yb * t[:, 4, None, None] + t[:, 5, None, None]
+        ix = ((gx + 1.0) * 0.5) * float(iw - 1); iy = ((gy + 1.0) * 0.5) * float(ih - 1)
+        fx, fy = torch.floor(ix), torch.floor(iy)
+        we, ws = ix - fx, iy - fy
+        ww, wn = 1.0 - we, 1.0 - ws
+        x0 = fx.clamp(-2.0, float(iw)).long(); y0 = fy.clamp(-2.0, float(ih)).long()
+        offs, wts = [], []
+        for k, wk in enumerate((wn * ww, wn * we, ws * ww, ws * we)):
+            xx, yy = x0 + (k & 1), y0 + (k >> 1)
+            inside = (xx >= 0) & (xx < iw) & (yy >= 0) & (yy < ih)
+            offs.append(torch.where(inside, yy * iw + xx, torch.full_like(xx, -1)))
+            wts.append(wk)
+        return torch.stack(offs, 1), torch.stack(wts, 1)
+
+    @staticmethod
+    def _gather_taps(x, offs, wts):
+        """sum_k x[n, :, off_k] * w_k with zero for outside taps; x: (N,C,IH,IW) -> (N,C,OH,OW)."""
+        n, c = x.shape[:2]
+        flat = x.reshape(n, c, -1)
+        out = torch.zeros((n, c) + tuple(offs.shape[2:]))
+        for k in range(4):
+            o = offs[:, k].reshape(n, 1, -1)
+            v = torch.gather(flat, 2, o.clamp_min(0).expand(n, c, -1))
+            v = torch.where(o >= 0, v, torch.zeros_like(v)).reshape(out.shape)
+            out = out + v * wts[:, k][:, None]
+        return out
+
+    def affine_grid_sample(self, x, theta, out_hw=None):
+        n, c, ih, iw = x.shape
+        oh, ow = (ih, iw) if out_hw is None else out_hw
+        offs, wts = self._affine_taps(theta, oh, ow, ih, iw)
+        self.launches += 1
+        return self._gather_taps(x, offs, wts)
+
+    def aug_consistency(self, ltea, ls, theta, um0, um1, loss_fn, conf_thresh, conf_per_pixel, ramp, cons_weight, dls=None):
+        n, c, h, w = ls.shape
+        offs, wts = self._affine_taps(theta, h, w, h, w)
+        lt = self._gather_taps(ltea, offs, wts)
+        pt = self._gather_taps(F.softmax(ltea, dim=1), offs, wts)
+        wmask = self._gather_taps(um0, offs, wts) * um1
+        conf = (pt.max(1, keepdim=True)[0] >= conf_thresh).float() if conf_thresh > 0.0 else torch.ones((n, 1, h, w))
+        q, g = self._q_and_grad(loss_fn, pt, lt, ls, c)
+        return self._finish(q, g, wmask, conf, conf, conf_thresh, conf_per_pixel, ramp, cons_weight)
+
+
 class EmuEMA(object):
     """Stand-in for optim_weight_ema.EMAWeightOptimizer.step() on CPU modules (optim_weight_ema.py:21-25 arithmetic); the
     product class refuses CPU tensors by design."""

@@ -131,6 +131,79 @@ def test_ict_loss_block_matches_the_reference_source_lines():
             assert exp['conf_rate_acc'] == 0.25           # `elif rampup > 0: conf_rate_acc += ramp_val` (:352-353)
 
 
+def test_aug_loss_block_matches_the_reference_source_lines():
+    """oracle augmentation-consistency block (torch_oracle.aug_consistency_loss) vs the reference's own lines
+    (train_seg_semisup_aug_mt.py:291-394) executed by gen_golden.py -- including the logits_var branch, which the reference
+    cannot execute -- and the kernel's algorithm (tests/_emu_backend.py: explicit four-tap gather per student pixel, soft-max
+    per tap) against the same vectors."""
+    sys.path.insert(0, HERE)
+    from aug_recipe import aug_inputs, parse_case
+    from _emu_backend import EmuBackend
+    import torch.nn.functional as F
+    gold = json.load(open(os.path.join(G, 'aug_block.json')))
+    lt, ls0, x0, x1, um0, um1, theta = aug_inputs()
+    assert len(gold['cases']) == 15
+    be = EmuBackend()
+    grid = F.affine_grid(theta, x0.shape, align_corners=True)
+    for key, exp in gold['cases'].items():
+        fn, tau, pp, rampup = parse_case(key)
+        if 'raises' in exp:
+            assert fn == 'logits_var' and exp['raises'] == 'NameError'
+            with pytest.raises(NameError):
+                TO.aug_consistency_loss(lt, ls0, theta, um0, um1, fn, tau, pp, ramp_val=0.25, rampup=rampup)
+            continue
+        assert float((F.grid_sample(um0, grid, align_corners=True) * um1).double().sum()) == pytest.approx(exp['mask_sum'], rel=1e-9)
+        ls = ls0.clone().requires_grad_(True)
+        loss, conf = TO.aug_consistency_loss(lt, ls, theta, um0, um1, fn, tau, pp, ramp_val=0.25, rampup=rampup)
+        loss.backward()
+        assert float(loss) == pytest.approx(exp['loss'], rel=1e-6), key
+        assert float(ls.grad.abs().sum()) == pytest.approx(exp['grad_l1'], rel=1e-6), key
+        assert float(ls.grad.abs().max()) == pytest.approx(exp['grad_max'], rel=1e-6), key
+        if tau > 0:
+            assert float(conf) == pytest.approx(exp['conf_rate_acc'], rel=1e-6), key
+        else:
+            assert exp['conf_rate_acc'] == 0.25           # `elif rampup > 0: conf_rate_acc += ramp_val` (:357-358)
+        # the kernel's algorithm on the CPU
+        ramp = 0.25 if rampup > 0 else 1.0
+        out4, dls = be.aug_consistency(lt, ls0, theta, um0, um1, fn, tau, pp, ramp, 1.0)
+        grad = dls * out4[2]
+        gtol = 5e-3 if fn == 'bce' else 2e-5              # bce: fp32 conditioning of 1 / (p + 1e-6), see tests/test_gpu_ict.py
+        assert float(out4[0]) == pytest.approx(exp['loss'], rel=2e-6), key
+        if tau > 0:
+            assert float(out4[1]) == pytest.approx(exp['conf_rate_acc'], rel=1e-6), key
+        assert (grad - ls.grad).abs().max().item() <= gtol * ls.grad.abs().max().item(), key
+    # the resampled tensors themselves
+    assert float(be.affine_grid_sample(lt, theta).double().abs().sum()) == pytest.approx(exp['logits_in_stu_abs_sum'], rel=1e-6)
+    assert float(be.affine_grid_sample(F.softmax(lt, dim=1), theta).double().sum()) == pytest.approx(exp['prob_in_stu_sum'], rel=1e-6)
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 9, 12), (1, 1, 1, 7), (3, 2, 16, 5), (2, 4, 33, 47)])
+def test_affine_grid_sample_algorithm_matches_torch(shape):
+    """The sampling arithmetic the CUDA kernels implement (linspace base grid, align_corners un-normalisation, four taps with
+    zero padding), stated by tests/_emu_backend.py, against F.affine_grid + F.grid_sample: identity, large shifts (everything
+    outside), rotations / anisotropic scales on non-square images, and a different output size."""
+    sys.path.insert(0, HERE)
+    from _emu_backend import EmuBackend
+    import torch.nn.functional as F
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(h * 100 + w)
+    x = torch.randn(shape, generator=g)
+    be = EmuBackend()
+    thetas = [torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]), torch.tensor([[1.0, 0.0, 5.0], [0.0, 1.0, -4.0]]),
+              torch.tensor([[0.9, -0.4, 0.1], [0.35, 1.2, -0.2]]), torch.tensor([[-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])]
+    for t in thetas:
+        theta = t[None].repeat(n, 1, 1)
+        theta[0, 0, 2] += 0.03                           # per-sample maps
+        for out_hw in (None, (h + 3, max(w - 2, 1))):
+            oh, ow = (h, w) if out_hw is None else out_hw
+            want = F.grid_sample(x, F.affine_grid(theta, (n, c, oh, ow), align_corners=True), align_corners=True)
+            got = be.affine_grid_sample(x, theta, out_hw)
+            assert got.shape == want.shape
+            assert (got - want).abs().max().item() <= 2e-5 * max(1.0, x.abs().max().item())
+    far = torch.tensor([[1.0, 0.0, 5.0], [0.0, 1.0, -4.0]])[None].repeat(n, 1, 1)
+    assert be.affine_grid_sample(x, far).abs().max().item() == 0.0
+
+
 def test_bit_exact_elementwise_oracles():
     rs = np.random.RandomState(0)
     t = rs.randn(100003).astype(np.float32); s = rs.randn(100003).astype(np.float32)

@@ -80,6 +80,9 @@ def _batches(mode, mg, seed):
     if mode == 'ict':
         uns = synthetic.make_ict_batch(N, H, W, 20 + seed, 0.4)
         uns_o = dict(uns)
+    elif mode == 'aug':
+        uns = synthetic.make_aug_batch(N, H, W, 20 + seed)
+        uns_o = dict(uns)
     else:
         uns = synthetic.make_unsup_batch(N, H, W, 20 + seed, mg, mask_mix=(mode == 'mix'), compact_masks=True)
         uns_o = dict(uns)
@@ -98,7 +101,8 @@ def _state_gap(net, ref):
 
 @pytest.mark.parametrize('mode,conf_per_pixel,batch_trunk,fn', [('mix', False, True, 'var'), ('mix', True, False, 'kld'),
                                                                ('cut', False, True, 'logits_var'), ('ict', True, True, 'var'),
-                                                               ('ict', False, False, 'bce')])
+                                                               ('ict', False, False, 'bce'), ('aug', False, True, 'var'),
+                                                               ('aug', True, False, 'kld')])
 def test_iteration_host_logic_matches_oracle(doubles, mode, conf_per_pixel, batch_trunk, fn):
     student, teacher, trainer, orc, mg = _build(mode, conf_per_pixel, batch_trunk, cons_loss_fn=fn)
     assert trainer._can_batch_trunk([None]) == batch_trunk
@@ -113,6 +117,19 @@ def test_iteration_host_logic_matches_oracle(doubles, mode, conf_per_pixel, batc
     # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr; everything else ~1e-6
     assert _state_gap(student, orc.student) < 1.5e-3
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
+@pytest.mark.parametrize('batch_trunk', [True, False])
+def test_aug_consistency_logits_var_fails_like_the_reference(doubles, batch_trunk):
+    """train_seg_semisup_aug_mt.py:373 reads `delta_prob` before assignment: the reference raises on the first unsupervised
+    batch (recorded in tests/golden/aug_block.json); so do the oracle and the iteration."""
+    student, teacher, trainer, orc, mg = _build('aug', False, batch_trunk, cons_loss_fn='logits_var')
+    sup, uns, uns_o = _batches('aug', mg, 0)
+    with pytest.raises(NameError):
+        with torch.no_grad():
+            trainer.step(sup, [uns])
+    with pytest.raises(NameError):
+        orc.step(sup[0], sup[1], uns_o)
 
 
 def test_loop_variants_pi_model_cutout_rampup_and_batch_ratio(doubles):
