@@ -174,6 +174,9 @@ def run_b200(args):
     sup_host = [synthetic.make_sup_batch(n, h, w, cfg['classes'], 100 + rank * 10 + i, pin=True) for i in range(pool)]
     if args.loss == 'ict':       # train_seg_semisup_ict.py iteration: per-sample Beta mix factors
         uns_host = [synthetic.make_ict_batch(n, h, w, 200 + rank * 10 + i, 0.1, pin=True) for i in range(pool)]
+    elif args.loss == 'aug':     # train_seg_semisup_aug_mt.py iteration: two geometrically different views + affine maps
+        uns_host = [synthetic.make_aug_batch(n, h, w, 200 + rank * 10 + i, rot_mag=10.0, max_scale=1.2, offset_range=16.0,
+                                             pin=True) for i in range(pool)]
     else:
         uns_host = [synthetic.make_unsup_batch(n, h, w, 200 + rank * 10 + i, mg, pin=True) for i in range(pool)]
     sup_dev = [(a.to(device), b.to(device)) for a, b in sup_host]
@@ -244,12 +247,14 @@ def run_b200(args):
     ms_step = ms / args.steps
     value = n * world / (ms_step / 1e3)
     F, Fs = FLOPS[args.arch]
-    flops_iter = (8 * F - 2 * Fs) * n
+    # CutMix / ICT: 4 forward + 2 backward passes; augmentation consistency runs the teacher once (3 forward passes)
+    flops_iter = ((7 if args.loss == 'aug' else 8) * F - 2 * Fs) * n
     res = {
         'metric': 'images/sec', 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-        'config': {'workload': cfg['workload'].replace('CutMix', 'ICT') if args.loss == 'ict' else cfg['workload'], 'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
+        'config': {'workload': cfg['workload'].replace('CutMix', {'ict': 'ICT', 'aug': 'augmentation-consistency'}.get(args.loss, 'CutMix')),
+                   'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
                    'freeze_bn': True, 'optimizer': trainer.optim_note,
                    'trunk_batching': 'frozen-BN backbone once per network over 2 concatenated mini-batches'
@@ -369,8 +374,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2'])
     ap.add_argument('--batch', type=int, default=0)
-    ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict'],
-                    help='unsupervised branch: CutMix (the headline workload) or ICT (train_seg_semisup_ict.py)')
+    ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict', 'aug'],
+                    help='unsupervised branch: CutMix (the headline workload), ICT (train_seg_semisup_ict.py) or augmentation '
+                         'consistency (train_seg_semisup_aug_mt.py)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -83,21 +83,24 @@ def make_ict_batch(n, h, w, seed, ict_alpha, paired=False, device='cpu', pin=Fal
     return res
 
 
-def make_aug_batch(n, h, w, seed, paired=False, rot_mag=0.2, max_scale=1.2, offset=0.15, device='cpu', pin=False):
+def make_aug_batch(n, h, w, seed, paired=False, rot_mag=10.0, max_scale=1.2, offset_range=4.0, device='cpu', pin=False):
     """Dict for MeanTeacherStep.step in augmentation-consistency mode (train_seg_semisup_aug_mt.py:275-281): two views of the
     unlabelled images with their valid masks and `xf0_to_1` (N,2,3) fp32, the affine map from the student's (view 1)
     normalised coordinates to the teacher's (view 0) that the reference's DataLoader derives from the two crops' transforms
-    (datapipe/seg_data.py:223-231).  Here: a random rotation (+-rot_mag rad), log-uniform scale in [1/max_scale, max_scale]
-    and translation (+-offset of the half extent) per sample, like SegCVTransformRandomCropRotateScale's ranges."""
+    (datapipe/seg_data.py:223-231).  Each view draws its own rotation (+-rot_mag degrees), log-uniform scale in
+    [1/max_scale, max_scale] and crop offset (+-offset_range pixels) like SegCVTransformRandomCropRotateScale
+    (datapipe/seg_transforms_cv.py:310-341, 412); the map is the difference of the two."""
     g = torch.Generator().manual_seed(seed)
     rng = np.random.RandomState(12345 + seed)
     out = {}
     out['ux0'] = torch.randn((n, 3, h, w), generator=g)
     out['ux1'] = out['ux0'] + 0.1 * torch.randn((n, 3, h, w), generator=g) if paired else torch.randn((n, 3, h, w), generator=g)
     out['um0'], out['um1'] = make_valid_mask(n, h, w), make_valid_mask(n, h, w)
-    ang = rng.uniform(-rot_mag, rot_mag, size=(n,))
-    sc = np.exp(rng.uniform(-np.log(max_scale), np.log(max_scale), size=(n,)))
-    tx, ty = rng.uniform(-offset, offset, size=(n,)), rng.uniform(-offset, offset, size=(n,))
+    rot, lms = np.radians(rot_mag), np.log(max_scale)
+    ang = rng.uniform(-rot, rot, size=(n,)) - rng.uniform(-rot, rot, size=(n,))
+    sc = np.exp(rng.uniform(-lms, lms, size=(n,)) - rng.uniform(-lms, lms, size=(n,)))
+    off = np.round(offset_range * rng.uniform(-1.0, 1.0, size=(n, 2))) - np.round(offset_range * rng.uniform(-1.0, 1.0, size=(n, 2)))
+    ty, tx = off[:, 0] * 2.0 / max(h - 1, 1), off[:, 1] * 2.0 / max(w - 1, 1)      # pixels -> normalised [-1, 1] coordinates
     asp = float(h) / float(w)              # normalised coordinates: a rotation in pixel space is sheared by the aspect ratio
     xf = np.zeros((n, 2, 3), dtype=np.float64)
     xf[:, 0, 0] = sc * np.cos(ang); xf[:, 0, 1] = -sc * np.sin(ang) * asp; xf[:, 0, 2] = tx

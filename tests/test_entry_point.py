@@ -1,5 +1,5 @@
 """CPU: the drop-in entry points keep the reference's CLI and job-function surface (train_seg_semisup_mask_mt.py:16-42,
-581-650; train_seg_semisup_ict.py:4-14, 508-577; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
+581-650; train_seg_semisup_ict.py:4-14, 508-577; train_seg_semisup_aug_mt.py:4-16, 515-577; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
 import inspect
 import json
 import os
@@ -7,6 +7,7 @@ import os
 import click
 import pytest
 
+import train_seg_semisup_aug_mt
 import train_seg_semisup_ict
 import train_seg_semisup_mask_mt
 from architectures import network_architectures
@@ -17,7 +18,8 @@ EXTRA_OPTIONS = {'no_pretrained', 'ddp', 'synthetic_classes'}
 EXTRA_CHOICES = {'dataset': {'synthetic'}}
 
 
-SCRIPTS = {'train_seg_semisup_mask_mt': train_seg_semisup_mask_mt, 'train_seg_semisup_ict': train_seg_semisup_ict}
+SCRIPTS = {'train_seg_semisup_mask_mt': train_seg_semisup_mask_mt, 'train_seg_semisup_ict': train_seg_semisup_ict,
+           'train_seg_semisup_aug_mt': train_seg_semisup_aug_mt}
 entry = train_seg_semisup_mask_mt
 
 
