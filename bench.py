@@ -288,7 +288,9 @@ def run_b200(args):
         with open(os.environ['B200SEG_SHAPE_PROFILE'], 'w') as f:
             for k, v in top:
                 f.write('{:<70s} {:8.3f} ms  n={:4d}  {:7.1f} TFLOP/s\n'.format(k, v['ms'], v['n'], v['flops'] / max(v['ms'], 1e-9) / 1e9))
-    if os.environ.get('B200SEG_SKIP_CPU_BASELINE'):
+    if world > 1:       # the host baseline is a property of the box, reported by the N = 1 run only
+        res['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': 0, 'kind': 'port', 'sample': 'reported at N=1 only'}
+    elif os.environ.get('B200SEG_SKIP_CPU_BASELINE'):
         res['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': 0, 'kind': 'port', 'sample': 'skipped (B200SEG_SKIP_CPU_BASELINE)'}
     else:
         res['cpu_baseline'] = cpu_baseline(args, sample_batch=2)
