@@ -75,3 +75,26 @@ def test_c_abi_exports_every_declared_symbol():
     l = lib.load()
     assert l.b2_version() >= 1
     assert l.b2_num_sms() == 0 or l.b2_num_sms() > 0     # no compute call without a GPU
+
+
+def test_c_abi_rejects_bad_arguments_before_any_launch():
+    """Error behaviour of the ABI (include/b200seg.h: non-zero code + b2_last_error(), no exception, no exit): argument
+    validation happens before the first CUDA call, so it can be exercised without a GPU.  Pointers below are never
+    dereferenced (every call fails validation)."""
+    from cutmix_semisup_seg_b200 import lib as L
+    fake = 0x1000
+    with pytest.raises(L.B2Error, match='bad args'):
+        L.call('b2_aug_consistency_fwd_bwd', None, fake, fake, fake, fake, fake, fake, 1, 2, 4, 4, 0, 0.5, 0, None)
+    with pytest.raises(L.B2Error, match='unknown loss_fn'):
+        L.call('b2_aug_consistency_fwd_bwd', fake, fake, fake, fake, fake, fake, fake, 1, 2, 4, 4, 9, 0.5, 0, None)
+    with pytest.raises(L.B2Error, match='unsupported'):
+        L.call('b2_aug_consistency_fwd_bwd', fake, fake, fake, fake, fake, fake, fake, 1, 65, 4, 4, 0, 0.5, 0, None)
+    with pytest.raises(L.B2Error, match='bad args'):
+        L.call('b2_affine_grid_sample', fake, None, fake, 1, 2, 4, 4, 4, 4, None)
+    with pytest.raises(L.B2Error, match='l1 given without mix mask'):
+        L.call('b2_consistency_fwd_bwd', fake, fake, fake, None, None, fake, fake, 1, 2, 16, 0, 0.5, 0, None)
+    with pytest.raises(L.B2Error, match='needs confbar'):
+        L.call('b2_ict_consistency_fwd_bwd', fake, fake, fake, fake, None, None, fake, fake, 1, 2, 16, 0, 0.5, 1, None)
+    with pytest.raises(L.B2Error, match='bad args'):
+        L.call('b2_ce_fwd_bwd', fake, None, fake, fake, 1, 2, 16, 255, None)
+    assert L.call('b2_consistency_num_partials', 3, 1000) == 3 * 4          # ceil(1000 / 256) blocks per image
