@@ -45,6 +45,13 @@ class Tape(object):
         self.K = kernels
         self.enabled = enabled
         self.nodes = []
+        # False: back-propagate to the network INPUT only (VAT's perturbation direction, torch.autograd.grad(loss, eps) in
+        # train_seg_semisup_vat_mt.py:265-268): no parameter receives a gradient, whatever its requires_grad says
+        self.param_grads = True
+
+    def wants(self, p):
+        """Does this backward pass produce a gradient for parameter p?"""
+        return self.param_grads and p.requires_grad
 
     def record(self, node, inputs):
         if not self.enabled:
@@ -82,9 +89,9 @@ class Tape(object):
         """Residual Act to subtract (or False) if the epilogue finishing d/d(t) should also emit the frozen-BN
         parameter-gradient statistics of the node that produced t; None = no statistics wanted."""
         node = t.node
-        if not isinstance(node, ConvNode) or node.bn is None or not node.bn.weight.requires_grad:
+        if not isinstance(node, ConvNode) or node.bn is None or not self.wants(node.bn.weight):
             return None
-        if node.conv.weight.requires_grad:
+        if self.wants(node.conv.weight):
             # dgamma comes from <W, dW> (ConvNode.backward): only sum_pix g is wanted, no pass over y / the residual
             return False if self.K.stats_ok(t) else None
         if not self.K.stats_ok(t) or (node.residual is not None and not self.K.stats_ok(node.residual)):
@@ -207,6 +214,8 @@ class ConvNode(object):
         self.x, self.y, self.conv, self.bn, self.residual, self.relu, self.scale = x, y, conv, bn, residual, relu, scale
         self.geom = geom          # (cout, kh, kw, cin, stride, pad, dil)
         self.col_src = col_src    # stem: (im2col matrix Act, padded K) kept for the weight gradient
+        self.stem_input = None    # stem, input gradient requested: the image Act and the zero-padded (cout, 1, kpad) weights
+        self.stem_wpad = None
 
     def backward(self, tape):
         K = tape.K
@@ -217,6 +226,8 @@ class ConvNode(object):
                 tape.skip(self.residual)
             if self.col_src is None:
                 tape.skip(self.x)
+            elif self.stem_input is not None and self.stem_input.needs_grad:
+                tape.skip(self.stem_input)
             return
         if self.y.parent is not None and self.relu:
             K.relu_gate(g, self.y)                 # slice outputs are gated here (parents carry plain sums)
@@ -224,12 +235,12 @@ class ConvNode(object):
             tape.contribute_tensor(self.residual, g)
         bn = self.bn
         w = self.conv.weight
-        bn_grads = bn is not None and bn.weight.requires_grad
+        bn_grads = bn is not None and tape.wants(bn.weight)
         st = None
         if bn_grads:
             st = getattr(self.y, 'fused_stats', None) if self.y.parent is None else None
             self.y.fused_stats = None
-        if bn_grads and not w.requires_grad:
+        if bn_grads and not tape.wants(w):
             # frozen convolution weights: recover xhat from the stored BN output
             dgam, acc = param_grad(bn.weight)
             dbet, acc2 = param_grad(bn.bias)
@@ -239,12 +250,12 @@ class ConvNode(object):
             else:
                 K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, self.residual, dgam, dbet, acc)
             bn_grads = False
-        if self.conv.bias is not None and self.conv.bias.requires_grad:
+        if self.conv.bias is not None and tape.wants(self.conv.bias):
             db, acc = param_grad(self.conv.bias)
             K.colsum(g, db, acc)
         if self.col_src is not None:
             # stem: GEMM over the (recomputed) im2col matrix; weight gradient only
-            if w.requires_grad:
+            if tape.wants(w):
                 col, kpad = self.col_src        # the forward's column matrix is kept (0.67 GB at N=16, 512^2)
                 dw_pad = K.empty((cout, 1, kpad), g.device)
                 gflat = Act(g.base, 1, 1, g.rows, g.c, g.ld, g.off)
@@ -253,8 +264,19 @@ class ConvNode(object):
                 K.copy_rows(dw, kh * kw * cin, dw_pad, kpad, cout, kh * kw * cin, acc)
                 if bn_grads:
                     self._bn_grads_from_wgrad(K, st, g, w, dw, bn)
+            x_img = self.stem_input
+            if x_img is not None and x_img.needs_grad:
+                # d/d(image) (VAT only): dcol = g . (scale * Wpad) as a 1x1 data-gradient GEMM, then the adjoint of im2col
+                col, kpad = self.col_src
+                wt, ldb = K.transpose_w(self.stem_wpad, cout, 1, kpad, scale=self.scale)
+                dcol = col.like()
+                gflat = Act(g.base, 1, 1, g.rows, g.c, g.ld, g.off)
+                K.conv_dgrad(gflat, wt, kpad, 1, 1, cout, ldb, 1, 0, 1, dcol)
+                oh, ow = self.y.h, self.y.w
+                tape.contribute_kernel(x_img, lambda dst, accumulate, addend, gate, stats: K.col2im(
+                    dcol, dst, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=accumulate), False)
             return
-        if w.requires_grad:
+        if tape.wants(w):
             dw, acc = param_grad(w)
             K.conv_wgrad(g, self.x, dw, cout, kh, kw, cin, stride, pad, dil, row_scale=self.scale, accumulate=acc)
             if bn_grads:
@@ -299,7 +321,7 @@ class BNTrainNode(object):
         bn = self.bn
         dx = self.raw.like()
         g_out = self.y.like() if self.residual is not None else None
-        if bn.weight.requires_grad:
+        if tape.wants(bn.weight):
             dgam, acc = param_grad(bn.weight)
             dbet, _ = param_grad(bn.bias)
         else:
@@ -533,8 +555,15 @@ def stem_conv(tape, x_nhwc, conv, bn):
         node = ConvNode(col, tgt, conv, bn, None, True, scale, (cout, kh, kw, cin, stride, pad, dil),
                         col_src=(col, kpad))
         tgt.node = node
-        tape.record(node, [])
+        if x_nhwc.needs_grad:          # VAT: the gradient w.r.t. the image is wanted (netbase.b2_forward(input_grad=True))
+            node.stem_input, node.stem_wpad = x_nhwc, wpad
+            tape.record(node, [x_nhwc])
+        else:
+            tape.record(node, [])
         return tgt
+    if x_nhwc.needs_grad:
+        raise NotImplementedError('input gradient through a train-mode BatchNorm stem (the reference computes the VAT '
+                                  'direction in eval mode, train_seg_semisup_vat_mt.py:237)')
     K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat)
     cnode = ConvNode(col, tgt, conv, None, None, False, None, (cout, kh, kw, cin, stride, pad, dil),
                      col_src=(col, kpad))

@@ -167,6 +167,15 @@ class ActKernels(object):
         self.be.im2col(x.ptr, col.ptr, x.n, x.h, x.w, x.c, x.ld, kh, kw, stride, pad, dil, oh, ow, kpad)
         return col
 
+    def col2im(self, dcol, dx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
+        """dx (+)= adjoint of im2col applied to dcol (input gradient of the stem; VAT only)."""
+        self.be.col2im(dcol.ptr, dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate)
+
+    def act_to_nchw(self, a):
+        out = torch.empty((a.n, a.c, a.h, a.w), device=a.device, dtype=torch.float32)
+        self.be.nhwc_to_nchw(a.ptr, out, a.n, a.c, a.h, a.w, a.ld)
+        return out
+
     def maxpool_fwd(self, x, out, idx):
         assert x.ld == x.c and out.ld == out.c
         self.be.maxpool_fwd(x.ptr, out.ptr, idx.data_ptr(), x.n, x.h, x.w, x.c, out.h, out.w)

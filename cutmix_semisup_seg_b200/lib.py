@@ -80,6 +80,11 @@ _SIGS = {
     'b2_affine_grid_sample': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_aug_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32,
                                            c_int, c_vp]),
+    'b2_col2im': (c_int, [c_vp, c_vp] + [c_int] * 14 + [c_vp]),
+    'b2_sample_reduce_blocks': (c_i64, [c_i64]),
+    'b2_sample_l2norm': (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    'b2_vat_adaptive_radius': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp]),
+    'b2_add_scaled_per_sample': (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_int, c_i64, c_vp]),
     'b2_consistency_num_partials': (c_i64, [c_int, c_i64]),
     'b2_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                        c_f32, c_int, c_vp]),
@@ -132,7 +137,7 @@ _SIGS = {
 }
 
 # Functions that return a size/count rather than an error code.
-_NON_STATUS = {'b2_version', 'b2_num_sms', 'b2_consistency_num_partials', 'b2_ce_num_partials',
+_NON_STATUS = {'b2_version', 'b2_num_sms', 'b2_consistency_num_partials', 'b2_sample_reduce_blocks', 'b2_ce_num_partials',
                'b2_conv_wgrad_workspace', 'b2_bn_workspace_doubles', 'b2_conv_stats_rows',
                'b2_bn_stats_workspace_doubles', 'b2_bilinear_bwd_nchw_workspace_floats'}
 

@@ -27,10 +27,11 @@ def set_kernels_factory(fn):
 
 class _RunState(object):
     """What the backward pass needs from one recorded forward pass."""
-    __slots__ = ('tape', 'low', 'align', 'consumed')
+    __slots__ = ('tape', 'low', 'align', 'consumed', 'xin')
 
-    def __init__(self, tape, low, align):
+    def __init__(self, tape, low, align, xin=None):
         self.tape, self.low, self.align, self.consumed = tape, low, align, False
+        self.xin = xin          # the image Act when its gradient was requested (b2_forward(input_grad=True)), else None
 
 
 class _MultiRunState(object):
@@ -100,8 +101,9 @@ class B2SegNet(nn.Module):
         return True
 
     # ---- explicit API used by the fused training step ---------------------------------------
-    def b2_forward(self, x, record):
-        """x: (N,3,H,W) fp32 CUDA tensor.  Returns (logits (N,C,H,W) fp32, state for b2_backward)."""
+    def b2_forward(self, x, record, input_grad=False):
+        """x: (N,3,H,W) fp32 CUDA tensor.  Returns (logits (N,C,H,W) fp32, state for b2_backward).  `input_grad`: also record
+        what d(loss)/d(x) needs (VAT, train_seg_semisup_vat_mt.py:247-268); b2_backward then returns that gradient."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError('expected an (N,3,H,W) image batch')
         K = get_kernels(self._n_split())
@@ -111,13 +113,13 @@ class B2SegNet(nn.Module):
         x = x.detach().to(torch.float32)
         tape = E.Tape(K, enabled=record)
         xin = K.nchw_to_act(x, 4)
-        xin.needs_grad = False
+        xin.needs_grad = bool(input_grad and record)
         low, align = self._graph(tape, xin, x.shape[2], x.shape[3])
         logits = E.to_logits_nchw(tape, low, x.shape[2], x.shape[3], align)
         if not record:
             tape.discard()
             return logits, None
-        return logits, _RunState(tape, low, align)
+        return logits, _RunState(tape, low, align, xin if xin.needs_grad else None)
 
     def b2_forward_multi(self, xs, record):
         """Several mini-batches [(N_i,3,H,W)] of the same spatial size in one pass: the batch-invariant trunk runs once
@@ -165,16 +167,27 @@ class B2SegNet(nn.Module):
             low.grad = None
         state.tape, state.lows = None, None
 
-    def b2_backward(self, state, dlogits, scale_dev=None, scale_host=1.0):
+    def b2_backward(self, state, dlogits, scale_dev=None, scale_host=1.0, param_grads=True):
         """Back-propagate d(loss)/d(logits) (NCHW, optionally to be multiplied by a device scalar) into
-        the parameters' .grad (accumulating, like autograd)."""
+        the parameters' .grad (accumulating, like autograd).  `param_grads=False`: no parameter gradient is produced
+        (torch.autograd.grad w.r.t. the input only).  Returns d(loss)/d(x) (N,3,H,W) if the pass was recorded with
+        `input_grad=True`, else None."""
         if state is None or state.consumed:
             raise RuntimeError('this forward pass was not recorded or has already been back-propagated')
         state.consumed = True
+        state.tape.param_grads = bool(param_grads)
         E.seed_output_grad(state.tape, state.low, dlogits, state.align, scale_dev=scale_dev, scale_host=scale_host)
+        K = state.tape.K
         state.tape.backward()
         state.low.grad = None
-        state.tape, state.low = None, None
+        dx = None
+        if state.xin is not None:
+            if state.xin.grad is None:
+                raise RuntimeError('the input gradient was requested but no gradient reached the image')
+            dx = K.act_to_nchw(state.xin.grad)
+            state.xin.grad = None
+        state.tape, state.low, state.xin = None, None, None
+        return dx
 
     # ---- nn.Module surface ------------------------------------------------------------------
     def forward(self, x, feature_maps=False, use_dropout=False):

@@ -208,6 +208,51 @@ class CudaBackend(object):
                    int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
         return out4, dls
 
+    # ------------------------------------------------------------------ VAT (train_seg_semisup_vat_mt.py:214-301)
+    def sample_l2norm(self, x):
+        """mag[i] = sqrt(sum of squares of sample i) (normalize_eps, :217-219).  x: (N, ...) fp32 contiguous."""
+        L.require_cuda(x)
+        x = x.contiguous()
+        n = x.shape[0]
+        per = x.numel() // n
+        blocks = L.call('b2_sample_reduce_blocks', per)
+        partials = torch.empty((n * blocks * 2,), device=x.device, dtype=torch.float64)
+        mag = torch.empty((n,), device=x.device, dtype=torch.float32)
+        self._call('b2_sample_l2norm', x.data_ptr(), n, per, partials.data_ptr(), mag.data_ptr(), self._s())
+        return mag
+
+    def vat_adaptive_radius(self, x, vat_radius):
+        """radius[i] = vat_radius * sqrt(|vertical central differences|^2 + |horizontal ...|^2) * 0.5 (:289-296)."""
+        L.require_cuda(x)
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        blocks = L.call('b2_sample_reduce_blocks', c * h * w)
+        partials = torch.empty((n * blocks * 2,), device=x.device, dtype=torch.float64)
+        radius = torch.empty((n,), device=x.device, dtype=torch.float32)
+        self._call('b2_vat_adaptive_radius', x.data_ptr(), n, c, h, w, float(vat_radius), partials.data_ptr(),
+                   radius.data_ptr(), self._s())
+        return radius
+
+    def add_scaled_per_sample(self, x, e, mag, radius, out=None):
+        """out = x + (e / (mag[i] + 1e-12)) * radius  (radius: (N,) device tensor or a python float; x None: direction only)."""
+        L.require_cuda(x, e, mag, radius if torch.is_tensor(radius) else None)
+        e = e.contiguous()
+        if x is not None:
+            x = x.contiguous()
+            assert x.shape == e.shape
+        n = e.shape[0]
+        per = e.numel() // n
+        if out is None:
+            out = torch.empty_like(e)
+        r_dev = radius if torch.is_tensor(radius) else None
+        self._call('b2_add_scaled_per_sample', L.ptr(x), e.data_ptr(), mag.data_ptr(), L.ptr(r_dev),
+                   0.0 if r_dev is not None else float(radius), out.data_ptr(), n, per, self._s())
+        return out
+
+    def col2im(self, dcol_ptr, dx_ptr, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
+        self._call('b2_col2im', dcol_ptr, dx_ptr, n, h, w, c, ldx, kh, kw, stride, pad, dil, oh, ow, kpad, int(bool(accumulate)),
+                   self._s())
+
     def cross_entropy(self, logits, labels, ignore_index=255, dlogits=None):
         """Returns (out3, dlogits_unscaled): out3 = [loss, n_valid, grad_scale]."""
         L.require_cuda(logits, labels)

@@ -154,6 +154,29 @@ int b2_aug_consistency_fwd_bwd(const float* ltea, const float* ls, const float* 
                                float conf_thresh, int conf_per_pixel, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * VAT (virtual adversarial training) -- train_seg_semisup_vat_mt.py:214-301, 392
+ *   The perturbation direction is the input gradient of a consistency loss (network passes + b2_consistency_fwd_bwd);
+ *   these entry points are the rest of the block:
+ *   b2_col2im: adjoint of b2_im2col -- dx (N,H,W,ldx; C <= 4 channels written) (+)= fold of dcol (N*OH*OW, kpad), the
+ *     input gradient of the Cin = 3 stem convolution (autograd's conv backward-data for `x_hat + eps`, :247-268).
+ *   b2_sample_l2norm: mag[i] = sqrt(sum_j x[i,j]^2) per sample (normalize_eps :217-219); per = elements per sample;
+ *     partials: DEVICE double [n * b2_sample_reduce_blocks(per) * 2] scratch.
+ *   b2_vat_adaptive_radius: radius[i] = vat_radius * sqrt(sum (x[..,y+2,x]-x[..,y,x])^2 + sum (x[..,y,x+2]-x[..,y,x])^2) * 0.5
+ *     over an (N,C,H,W) batch (:289-296); same scratch with per = C*H*W.
+ *   b2_add_scaled_per_sample: out = x + (e / (mag[i] + 1e-12)) * r_i with r_i = radius[i] (DEVICE fp32 [n]) or, when
+ *     radius == NULL, the scalar radius_host; every operation rounded to fp32 separately like the reference's tensor
+ *     expression (:220 normalize, :223 / :301 scale, :247 / :392 add).  x == NULL: out = the scaled direction only.
+ * ------------------------------------------------------------------------------------------ */
+int b2_col2im(const float* dcol, float* dx, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
+              int dil, int oh, int ow, int kpad, int accumulate, void* stream);
+int64_t b2_sample_reduce_blocks(int64_t per);
+int b2_sample_l2norm(const float* x, int n, int64_t per, double* partials, float* mag, void* stream);
+int b2_vat_adaptive_radius(const float* x, int n, int c, int h, int w, float vat_radius, double* partials, float* radius,
+                           void* stream);
+int b2_add_scaled_per_sample(const float* x, const float* e, const float* mag, const float* radius, float radius_host,
+                             float* out, int n, int64_t per, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459
  *   Inputs (NCHW fp32): l0, l1 teacher logits of the two views (l1 == NULL → cut mode, l_t = l0),
  *   ls student logits, m mix mask (N,1,H,W) (NULL → no logit mixing), lmask per-pixel loss mask

@@ -144,6 +144,30 @@ class EmuKernels(object):
         col.base.view(-1, kpad)[:, :kh * kw * x.c] = cols.to(torch.float32)
         return col
 
+    def col2im(self, dcol, dx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
+        """b2_col2im's gather loop, written out tap by tap (independent of F.fold)."""
+        self.calls.append('col2im')
+        n, h, w, c = dx.n, dx.h, dx.w, dx.c
+        cols = dcol.base.view(-1, kpad)[:, :kh * kw * c].to(DT).view(n, oh, ow, kh * kw, c)
+        acc = torch.zeros(n, h, w, c, dtype=DT)
+        for r in range(kh):
+            for s in range(kw):
+                for oy in range(oh):
+                    y = oy * stride - pad + r * dil
+                    if not 0 <= y < h:
+                        continue
+                    xs = torch.arange(ow) * stride - pad + s * dil
+                    ok = (xs >= 0) & (xs < w)
+                    acc[:, y, xs[ok]] += cols[:, oy, ok, r * kw + s]
+        v = dx.view4()
+        if accumulate:
+            v += acc.to(torch.float32)
+        else:
+            v.copy_(acc.to(torch.float32))
+
+    def act_to_nchw(self, a):
+        return a.view4().permute(0, 3, 1, 2).contiguous().clone()
+
     def maxpool_fwd(self, x, out, idx):
         y, ind = F.max_pool2d(_v(x), 3, 2, 1, ceil_mode=False, return_indices=True) if False else (None, None)
         xv = _v(x)

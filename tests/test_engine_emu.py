@@ -202,3 +202,44 @@ def test_multi_batch_needs_frozen_trunk(emu):
     net.train()
     with pytest.raises(RuntimeError):
         net.b2_forward_multi([torch.randn(1, 3, 17, 17)] * 2, record=False)
+
+
+@pytest.mark.parametrize('kind,classes,student', [('resnet101_deeplab_imagenet', 21, False),
+                                                  ('resnet101_deeplabv3plus_imagenet', 19, True)])
+def test_input_gradient_only_backward_matches_autograd(emu, kind, classes, student):
+    """VAT's direction pass (train_seg_semisup_vat_mt.py:237-268): eval-mode network, d(loss)/d(image) through the stem
+    (data-gradient GEMM over the im2col matrix + col2im), no parameter gradient -- also for a network whose parameters
+    require gradients (`--vat_dir_from_student`)."""
+    torch.manual_seed(3)
+    net = na.seg.get(kind)(classes, pretrained=False)
+    sd = TO.synth_state_dict(net.state_dict(), seed=7)
+    net.load_state_dict(sd)
+    if not student:
+        for p in net.parameters():
+            p.requires_grad = False
+    net.eval()
+    x = torch.randn(2, 3, 33, 41)
+    dy = torch.randn(2, classes, 33, 41)
+    with torch.no_grad():          # the engine never uses autograd; the torch-CPU doubles would otherwise record a graph
+        logits, state = net.b2_forward(x, record=True, input_grad=True)
+        dx = net.b2_backward(state, dy, param_grads=False)
+    assert all(p.grad is None for p in net.parameters())
+    assert emu.calls.count('col2im') == 1 and emu.calls.count('conv_wgrad') == 0
+    sd64 = OrderedDict((k, v.double().clone() if v.dtype == torch.float32 else v.clone()) for k, v in sd.items())
+    x64 = x.double().requires_grad_(True)
+    if 'v3plus' in kind:
+        yo = TO.deeplab3plus_forward(sd64, x64, backbone_bn_train=False, head_bn_train=False)
+    else:
+        yo = TO.deeplab2_forward(sd64, x64, bn_train=False)
+    yo.backward(dy.double())
+    assert (logits.double() - yo.detach()).abs().max().item() < 1e-4 * yo.abs().max().item()
+    assert dx.shape == x.shape
+    # fp32 activations against the fp64 oracle: isolated ReLU-gate / max-pool ties flip (DeepLab v2: max 3e-4 of the range),
+    # everything else agrees to ~1e-6
+    err = (dx.double() - x64.grad).abs()
+    assert err.max().item() < 1e-3 * x64.grad.abs().max().item()
+    assert err.median().item() < 1e-5 * x64.grad.abs().median().item()
+    # a recorded pass without the request keeps the old contract
+    with torch.no_grad():
+        logits, state = net.b2_forward(x, record=True)
+        assert net.b2_backward(state, dy, param_grads=False) is None
