@@ -177,6 +177,8 @@ def run_b200(args):
     elif args.loss == 'aug':     # train_seg_semisup_aug_mt.py iteration: two geometrically different views + affine maps
         uns_host = [synthetic.make_aug_batch(n, h, w, 200 + rank * 10 + i, rot_mag=10.0, max_scale=1.2, offset_range=16.0,
                                              pin=True) for i in range(pool)]
+    elif args.loss == 'vat':     # train_seg_semisup_vat_mt.py iteration: adversarial perturbation from an input-gradient pass
+        uns_host = [synthetic.make_vat_batch(n, h, w, 200 + rank * 10 + i, pin=True) for i in range(pool)]
     else:
         uns_host = [synthetic.make_unsup_batch(n, h, w, 200 + rank * 10 + i, mg, pin=True) for i in range(pool)]
     sup_dev = [(a.to(device), b.to(device)) for a, b in sup_host]
@@ -248,12 +250,13 @@ def run_b200(args):
     value = n * world / (ms_step / 1e3)
     F, Fs = FLOPS[args.arch]
     # CutMix / ICT: 4 forward + 2 backward passes; augmentation consistency runs the teacher once (3 forward passes)
-    flops_iter = ((7 if args.loss == 'aug' else 8) * F - 2 * Fs) * n
+    # VAT: 5 forward passes (direction net twice, teacher, student twice), 2 full backward passes + 1 data-gradient-only pass
+    flops_iter = ({'aug': 7, 'vat': 10}.get(args.loss, 8) * F - 2 * Fs) * n
     res = {
         'metric': 'images/sec', 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-        'config': {'workload': cfg['workload'].replace('CutMix', {'ict': 'ICT', 'aug': 'augmentation-consistency'}.get(args.loss, 'CutMix')),
+        'config': {'workload': cfg['workload'].replace('CutMix', {'ict': 'ICT', 'aug': 'augmentation-consistency', 'vat': 'VAT'}.get(args.loss, 'CutMix')),
                    'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
                    'freeze_bn': True, 'optimizer': trainer.optim_note,
@@ -376,9 +379,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2'])
     ap.add_argument('--batch', type=int, default=0)
-    ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict', 'aug'],
-                    help='unsupervised branch: CutMix (the headline workload), ICT (train_seg_semisup_ict.py) or augmentation '
-                         'consistency (train_seg_semisup_aug_mt.py)')
+    ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict', 'aug', 'vat'],
+                    help='unsupervised branch: CutMix (the headline workload), ICT (train_seg_semisup_ict.py), augmentation '
+                         'consistency (train_seg_semisup_aug_mt.py) or VAT (train_seg_semisup_vat_mt.py)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':

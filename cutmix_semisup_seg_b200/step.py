@@ -112,13 +112,16 @@ def average_gradients(flat, dist, group=None):
 class MeanTeacherStep(object):
     def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
                  cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True, use_cuda_graph=False, batch_trunk=True):
+                 unsup_batch_ratio=1, dist_group=None, use_flat_grads=True, use_cuda_graph=False, batch_trunk=True,
+                 vat_radius=0.5, adaptive_vat_radius=False, vat_dir_from_student=False):
         self.student_net, self.teacher_net = student_net, teacher_net
         self.student_optim, self.teacher_optim = student_optim, teacher_optim
         self.mask_generator = mask_generator
         self.cons_loss_fn, self.cons_weight = cons_loss_fn, cons_weight
         self.conf_thresh, self.conf_per_pixel = conf_thresh, conf_per_pixel
         self.rampup, self.mask_mix, self.unsup_batch_ratio = rampup, mask_mix, unsup_batch_ratio
+        # VAT (train_seg_semisup_vat_mt.py:624-626); used only by batches that carry the key 'vat'
+        self.vat_radius, self.adaptive_vat_radius, self.vat_dir_from_student = vat_radius, adaptive_vat_radius, vat_dir_from_student
         self.be = O.default_backend()
         self.optim_note = getattr(student_optim, 'b2_note', type(student_optim).__name__)
         self.world = 1
@@ -214,6 +217,50 @@ class MeanTeacherStep(object):
         self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])  # aug :397-398
         return out4
 
+    VAT_LOSS_FNS = ('var', 'bce', 'kld', 'logits_var')        # train_seg_semisup_vat_mt.py:251-262
+
+    def vat_perturbation(self, x, x_hat, noise=None):
+        """`vat_perburbation` + `vat_direction` of the reference (train_seg_semisup_vat_mt.py:228-301): the adversarial
+        perturbation (N,3,H,W) for the student's view `x_hat`, from the input gradient of the consistency loss between the
+        direction network's predictions on `x` and on `x_hat + eps`.  `noise`: the N(0,1) draw behind eps (reference:
+        torch.randn, :222); given explicitly by the parity tests.  Returns the perturbed images x_hat + r_adv (:392)."""
+        be = self.be
+        if self.cons_loss_fn not in self.VAT_LOSS_FNS:
+            raise ValueError('Unknown consistency loss function {}'.format(self.cons_loss_fn))      # :261-262
+        dir_net = self.student_net if self.vat_dir_from_student else self.teacher_net               # :102-105
+        dir_net.eval()                 # :237 -- and, like the reference, it STAYS in eval mode until the next epoch's .train()
+        with torch.no_grad():
+            y_logits = dir_net.b2_forward(x, record=False)[0]                                       # :238-239
+            n, c, h, w = x.shape
+            noise_scale = 1.0e-6 * h * w / 1000                                                     # :243
+            if noise is None:
+                noise = torch.randn(x.shape, dtype=torch.float32, device=x.device)                  # :222
+            x_eps = be.add_scaled_per_sample(x_hat, noise, be.sample_l2norm(noise), noise_scale)    # :223, :247
+            e_logits, state = dir_net.b2_forward(x_eps, record=True, input_grad=True)               # :247
+            # d(loss)/d(eps): the loss kernel's un-scaled gradient is that of the reference's SUMMED loss (:251-260; for
+            # logits_var up to the constant 1/sqrt(C)); positive constants cancel in the normalisation below
+            _, dle = be.consistency(y_logits, None, e_logits, None, None, self.cons_loss_fn, 0.0, False, 1.0, 1.0)
+            eps_adv = dir_net.b2_backward(state, dle, param_grads=False)                            # :265-268
+            if self.adaptive_vat_radius:
+                radius = be.vat_adaptive_radius(x_hat, self.vat_radius)                             # :277-296
+            else:
+                radius = self.vat_radius * float(c * h * w) ** 0.5                                  # :298-299
+            return be.add_scaled_per_sample(x_hat, eps_adv, be.sample_l2norm(eps_adv), radius)      # :271, :301, :392
+
+    def unsupervised_vat(self, ux_tea, ux_stu, um, ramp_val=1.0, noise=None):
+        """VAT consistency (train_seg_semisup_vat_mt.py:364-455): student on the adversarially perturbed image, teacher on
+        the clean one, the confidence-thresholded consistency loss of the CutOut branch with the valid mask as loss mask."""
+        be = self.be
+        ux_adv = self.vat_perturbation(ux_tea, ux_stu, noise)                       # vat :389-392
+        with torch.no_grad():
+            lt = self.teacher_net.b2_forward(ux_tea, record=False)[0]               # vat :395-396
+        ls, state = self.student_net.b2_forward(ux_adv, record=True)                # vat :398
+        ramp = ramp_val if self.rampup > 0 else 1.0
+        out4, dls = be.consistency(lt, None, ls, None, um, self.cons_loss_fn, self.conf_thresh, self.conf_per_pixel, ramp,
+                                   self.cons_weight)                                # vat :400-448
+        self.student_net.b2_backward(state, dls, scale_dev=out4[2:3])               # vat :451-452
+        return out4
+
     def unsupervised_cut(self, ux_tea, ux_stu, um, mask_params, ramp_val=1.0):
         """Lines 371-401 + 406-459 (cut / CutOut mode)."""
         be = self.be
@@ -230,6 +277,8 @@ class MeanTeacherStep(object):
         return out4
 
     def _can_batch_trunk(self, unsup_batches):
+        if any(ub is not None and 'vat' in ub for ub in unsup_batches):
+            return False           # VAT changes the networks' train / eval mode in the middle of the iteration: pass by pass
         return (self.batch_trunk and self.cons_weight > 0.0 and len(unsup_batches) == 1 and
                 self.teacher_net is not self.student_net and
                 hasattr(self.student_net, 'b2_forward_multi') and hasattr(self.teacher_net, 'b2_forward_multi') and
@@ -428,7 +477,9 @@ class MeanTeacherStep(object):
         cons, conf = None, None
         if self.cons_weight > 0.0:
             for ub in unsup_batches:
-                if 'xf0_to_1' in ub:
+                if 'vat' in ub:
+                    out4 = self.unsupervised_vat(ub['ux_tea'], ub['ux_stu'], ub['um'], ramp_val, ub.get('noise'))
+                elif 'xf0_to_1' in ub:
                     out4 = self.unsupervised_aug(ub['ux0'], ub['um0'], ub['ux1'], ub['um1'], ub['xf0_to_1'], ramp_val)
                 elif 'ict_mix_factors' in ub:
                     out4 = self.unsupervised_ict(ub['ux0_tea'], ub['ux0_stu'], ub['um0'], ub['ux1_tea'], ub['ux1_stu'],
@@ -455,7 +506,8 @@ class MeanTeacherStep(object):
         unsup_batch_ratio) of dicts with keys ux0_tea, ux0_stu, um0, ux1_tea, ux1_stu, um1, mask_params (mix
         mode), the same with ict_mix_factors ((N,) fp32 Beta draws) instead of mask_params (ICT,
         train_seg_semisup_ict.py), or ux_tea, ux_stu, um, mask_params (cut mode), or ux0, um0, ux1, um1, xf0_to_1 ((N,2,3) fp32
-        affine maps; augmentation consistency, train_seg_semisup_aug_mt.py).  Returns device scalars
+        affine maps; augmentation consistency, train_seg_semisup_aug_mt.py), or ux_tea, ux_stu, um, vat (any value; VAT,
+        train_seg_semisup_vat_mt.py; optional `noise` (N,3,H,W) replaces the torch.randn draw).  Returns device scalars
         {'sup_loss', 'cons_loss', 'conf_rate'} without synchronising.  With `use_cuda_graph` the iteration is captured
         once per (shapes, ramp value) and replayed; inputs may then be pinned host tensors (copied straight into the
         graph's static buffers).  `prefetch=(sup_batch, unsup_batches)`: the (pinned host) batch of the NEXT call; its

@@ -115,6 +115,28 @@ def make_aug_batch(n, h, w, seed, paired=False, rot_mag=10.0, max_scale=1.2, off
     return res
 
 
+def make_vat_batch(n, h, w, seed, paired=False, with_noise=False, device='cpu', pin=False):
+    """Dict for MeanTeacherStep.step in VAT mode (train_seg_semisup_vat_mt.py:364-380): one unlabelled view (or the weak /
+    strong pair of `--aug_strong_colour`) with its valid mask; the key 'vat' marks the batch.  `with_noise`: also carry the
+    N(0,1) draw behind the initial perturbation (reference: torch.randn on the device, :222) so that two implementations
+    can be driven with the same draw."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    out['ux_tea'] = torch.randn((n, 3, h, w), generator=g)
+    out['ux_stu'] = out['ux_tea'] + 0.1 * torch.randn((n, 3, h, w), generator=g) if paired else out['ux_tea']
+    out['um'] = make_valid_mask(n, h, w)
+    out['vat'] = torch.ones((1,))
+    if with_noise:
+        out['noise'] = torch.randn((n, 3, h, w), generator=g)
+    res, cache = {}, {}
+    for k, v in out.items():
+        if id(v) not in cache:
+            t = v.pin_memory() if pin else v
+            cache[id(v)] = t.to(device)
+        res[k] = cache[id(v)]
+    return res
+
+
 def condition_classifier(net, gain):
     """Scale the last classification layer so that teacher soft-max confidences straddle the 0.97 threshold
     on random inputs (random-init networks give conf_rate == 0, i.e. a vacuous consistency loss)."""

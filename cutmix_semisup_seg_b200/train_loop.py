@@ -1,4 +1,5 @@
-"""The training procedure shared by the drop-in entry points (`train_seg_semisup_mask_mt.py`, `train_seg_semisup_ict.py`):
+"""The training procedure shared by the drop-in entry points (`train_seg_semisup_mask_mt.py`, `train_seg_semisup_ict.py`,
+`train_seg_semisup_aug_mt.py`, `train_seg_semisup_vat_mt.py`):
 network / optimiser / EMA construction, LR schedules, the per-epoch loop around `MeanTeacherStep.step`, on-device
 evaluation and reporting -- reference train_seg_semisup_mask_mt.py:86-134, 257-530 (the ICT script's outer loop is the
 same code, train_seg_semisup_ict.py:62-110, 226-468; only the unsupervised branch of the iteration differs).
@@ -13,9 +14,10 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
                  sgd_momentum, sgd_nesterov, sgd_weight_decay, learning_rate, lr_sched, lr_step_epochs, lr_step_gamma,
                  lr_poly_power, teacher_alpha, bin_fill_holes, crop_size, cons_loss_fn, cons_weight, conf_thresh,
                  conf_per_pixel, rampup, unsup_batch_ratio, num_epochs, iters_per_epoch, batch_size, save_model,
-                 no_pretrained, ddp, synthetic_classes):
+                 no_pretrained, ddp, synthetic_classes, step_options=None):
     """`make_unsup(batch_size, h, w, seed, device)` -> one unsupervised batch dict for MeanTeacherStep.step (CutMix / CutOut
-    box parameters or ICT mix factors included)."""
+    box parameters, ICT mix factors, augmentation maps or the VAT marker included); `step_options`: extra keyword arguments of
+    MeanTeacherStep (VAT radius / direction network)."""
     import numpy as np
     import torch
     from architectures import network_architectures
@@ -83,7 +85,8 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
     trainer = step_mod.MeanTeacherStep(student_net, teacher_net, student_optim, teacher_optim, mask_generator,
                                        cons_loss_fn=cons_loss_fn, cons_weight=cons_weight, conf_thresh=conf_thresh,
                                        conf_per_pixel=conf_per_pixel, rampup=rampup, mask_mix=mask_mix,
-                                       unsup_batch_ratio=unsup_batch_ratio, dist_group=True if ddp else None)
+                                       unsup_batch_ratio=unsup_batch_ratio, dist_group=True if ddp else None,
+                                       **(step_options or {}))
 
     if rank == 0:
         print('Settings:')

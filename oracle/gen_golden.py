@@ -14,6 +14,8 @@ Contents
   ict_block.json    ICT loss block (train_seg_semisup_ict.py:306-387): the reference's own source lines executed on seeded
                     tensors, all five loss functions x {scalar / per-pixel confidence mask, ramp-up without threshold}
   aug_block.json    augmentation-consistency loss block (train_seg_semisup_aug_mt.py:291-394), the same way
+  vat_block.json    VAT perturbation (train_seg_semisup_vat_mt.py:214-301): the reference's own helper functions executed
+                    with a small seeded direction network, four loss functions x fixed / adaptive radius
   entry_point.json  click surface of the reference's `train_seg_semisup_mask_mt.experiment` (option names, flags,
                     defaults, choices) and the parameter list of the job function, plus lr_schedules / sigmoid_rampup
                     known answers the entry point depends on
@@ -298,6 +300,40 @@ def gen_aug_block():
     json.dump(out, open(os.path.join(OUT, 'aug_block.json'), 'w'), indent=1)
 
 
+def gen_vat_block():
+    """VAT perturbation: the reference's OWN helper functions (train_seg_semisup_vat_mt.py:214-301: t_dot, normalize_eps,
+    normalized_noise_like, vat_direction, vat_perburbation -- closures of the job function) are cut out of the script and
+    executed with a small seeded stand-in for `vat_dir_net`.  -> tests/golden/vat_block.json (inputs: tests/vat_recipe.py)."""
+    import textwrap
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    from vat_recipe import vat_net, vat_inputs
+    lines = open(os.path.join(REF, 'train_seg_semisup_vat_mt.py')).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.strip() == 'def t_dot(a, b):')
+    end = next(i for i, l in enumerate(lines) if l.strip() == 'return (eps_adv_nrm * adv_radius).detach(), y_pred_logits, y_pred_prob') + 1
+    block = textwrap.dedent('\n'.join(lines[start:end]))
+    assert 'def vat_direction(x, x_hat):' in block and 'torch.autograd.grad(' in block
+    net = vat_net()
+    x, x_hat = vat_inputs()
+    out = dict(recipe='tests/vat_recipe.py; torch.manual_seed(case seed) before vat_perburbation; vat_radius=0.5',
+               ref_lines=[start + 1, end], cases={})
+    seed = 100
+    for fn in ('var', 'bce', 'kld', 'logits_var'):
+        for adaptive in (False, True):
+            ns = dict(torch=torch, F=F, math=math, network_architectures=network_architectures, vat_dir_net=net,
+                      cons_loss_fn=fn, adaptive_vat_radius=adaptive, vat_radius=0.5)
+            exec(block, ns)
+            torch.manual_seed(seed)
+            x_perturb, y_logits, y_prob = ns['vat_perburbation'](x, x_hat, None)
+            assert not x_perturb.requires_grad
+            out['cases']['%s_adaptive%d' % (fn, int(adaptive))] = dict(
+                seed=seed, abs_sum=float(x_perturb.double().abs().sum()),
+                norms=[float(v) for v in x_perturb.reshape(3, -1).double().norm(dim=1)],
+                probe=[float(v) for v in x_perturb[:, :, 3, 5].reshape(-1)],
+                y_logits_abs_sum=float(y_logits.double().abs().sum()))
+            seed += 1
+    json.dump(out, open(os.path.join(OUT, 'vat_block.json'), 'w'), indent=1)
+
+
 def gen_entry_point():
     """Reference CLI / job-function surface of the two drop-in scripts (train_seg_semisup_mask_mt.py:16-42, 581-650;
     train_seg_semisup_ict.py:4-14, 508-577)."""
@@ -305,7 +341,7 @@ def gen_entry_point():
     import inspect
     import click
     out = dict(scripts={}, rampup=[network_architectures.sigmoid_rampup(e, 10) for e in range(0, 12)])
-    for name in ('train_seg_semisup_mask_mt', 'train_seg_semisup_ict', 'train_seg_semisup_aug_mt'):
+    for name in ('train_seg_semisup_mask_mt', 'train_seg_semisup_ict', 'train_seg_semisup_aug_mt', 'train_seg_semisup_vat_mt'):
         m = importlib.import_module(name)
         assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF))
         opts = []
@@ -324,6 +360,7 @@ if __name__ == '__main__':
     gen_entry_point(); print('entry point')
     gen_ict_block(); print('ict block')
     gen_aug_block(); print('aug block')
+    gen_vat_block(); print('vat block')
     gen_masks(); print('masks')
     gen_state_dicts(); print('state dicts')
     gen_loss_block(); print('loss block')

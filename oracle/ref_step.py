@@ -50,11 +50,16 @@ class OracleMeanTeacher(object):
 
     def __init__(self, arch, state_dict, learning_rate, opt_type='adam', teacher_alpha=0.99, freeze_bn=True,
                  cons_loss_fn='var', cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
-                 dtype=torch.float32, model='mean_teacher'):
+                 dtype=torch.float32, model='mean_teacher', vat_radius=0.5, adaptive_vat_radius=False,
+                 vat_dir_from_student=False):
         self.arch, self.freeze_bn = arch, freeze_bn
         self.cons_loss_fn, self.cons_weight = cons_loss_fn, cons_weight
         self.conf_thresh, self.conf_per_pixel, self.rampup, self.mask_mix = conf_thresh, conf_per_pixel, rampup, mask_mix
         self.teacher_alpha = teacher_alpha
+        self.vat_radius, self.adaptive_vat_radius, self.vat_dir_from_student = vat_radius, adaptive_vat_radius, vat_dir_from_student
+        # nn.Module.training of the two networks; VAT's direction pass switches one of them to eval mode and the reference
+        # never switches it back inside the epoch (train_seg_semisup_vat_mt.py:237 vs :326-333)
+        self.eval_mode = {'student': False, 'teacher': False}
 
         def clone(sd):
             return OrderedDict((k, (v.to(dtype) if v.dtype == torch.float32 else v).clone()) for k, v in sd.items())
@@ -84,7 +89,16 @@ class OracleMeanTeacher(object):
                 self.optim = torch.optim.SGD(groups, momentum=0.9, nesterov=False, weight_decay=5e-4, foreach=False)
 
     # ------------------------------------------------------------------------------------------
+    def start_epoch(self):
+        """student_net.train(); teacher_net.train() (+ freeze_batchnorm) at the top of every epoch (:326-333)."""
+        self.eval_mode = {'student': False, 'teacher': False}
+
     def _forward(self, sd, x, dropout_masks=None):
+        which = 'student' if sd is self.student else 'teacher'
+        if self.eval_mode[which]:                 # module in eval mode: running statistics everywhere, no dropout
+            if self.arch == 'deeplab2':
+                return TO.deeplab2_forward(sd, x, bn_train=False)
+            return TO.deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False)
         if self.arch == 'deeplab2':
             return TO.deeplab2_forward(sd, x, bn_train=not self.freeze_bn)
         # net.train() then freeze_batchnorm(): backbone BN eval, head BN train (:268-275, deeplab3plus.py:120-121)
@@ -116,7 +130,19 @@ class OracleMeanTeacher(object):
         unsup_list = unsup if isinstance(unsup, (list, tuple)) else [unsup]        # :304 `for _ in range(unsup_batch_ratio)`
         for unsup in (unsup_list if self.cons_weight > 0.0 else []):
             m = unsup.get('mask_params')
-            if 'xf0_to_1' in unsup:                                                 # train_seg_semisup_aug_mt.py:275-398
+            if 'vat' in unsup:                                                      # train_seg_semisup_vat_mt.py:364-452
+                which = 'student' if (self.vat_dir_from_student or self.model == 'pi') else 'teacher'    # :102-105
+                dir_sd = self.student if which == 'student' else self.teacher
+                self.eval_mode[which] = True                                        # vat_dir_net.eval() :237 (persists)
+                x_perturb = TO.vat_perturbation(lambda t: self._forward(dir_sd, t), unsup['ux_tea'], unsup['ux_stu'],
+                                                unsup['noise'], self.cons_loss_fn, self.vat_radius, self.adaptive_vat_radius)
+                ux_adv = unsup['ux_stu'] + x_perturb                                # :392
+                with torch.no_grad():                                               # :395-396
+                    lt = self._forward(self.teacher, unsup['ux_tea'], drop.get('tea0')).detach()
+                ls = self._forward(self.student, ux_adv, drop.get('stu'))           # :398
+                loss, conf = TO.consistency_loss(lt, None, ls, None, unsup['um'], self.cons_loss_fn, self.conf_thresh,
+                                                 self.conf_per_pixel, ramp_val, self.rampup)
+            elif 'xf0_to_1' in unsup:                                               # train_seg_semisup_aug_mt.py:275-398
                 with torch.no_grad():                                               # aug :291-293
                     lt = self._forward(self.teacher, unsup['ux0'], drop.get('tea0')).detach()
                 ls = self._forward(self.student, unsup['ux1'], drop.get('stu'))     # aug :295

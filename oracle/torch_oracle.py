@@ -276,6 +276,52 @@ def aug_consistency_loss(logits_cons_tea, logits_cons_stu, xf0_to_1, um0, um1, c
     return loss, conf_rate
 
 
+def vat_normalize_eps(x):
+    """train_seg_semisup_vat_mt.py:217-220."""
+    x_flat = x.view(len(x), -1)
+    mag = torch.sqrt((x_flat * x_flat).sum(dim=1))
+    return x / (mag[:, None, None, None] + 1e-12)
+
+
+def vat_perturbation(dir_forward, x, x_hat, noise, cons_loss_fn='kld', vat_radius=0.5, adaptive_vat_radius=False):
+    """`vat_direction` + `vat_perburbation`, reference train_seg_semisup_vat_mt.py:228-301 line by line.  `dir_forward(x)` is
+    the direction network in eval mode (:237); `noise` is the N(0,1) draw of `normalized_noise_like` (:222), passed in so that
+    the CUDA path can be driven with the same draw.  Returns x_perturb (detached), (N,3,H,W)."""
+    with torch.no_grad():
+        y_pred_logits = dir_forward(x).detach()                                            # :238-239
+    y_pred_prob = F.softmax(y_pred_logits, dim=1)                                          # :240
+    noise_scale = 1.0e-6 * x.shape[2] * x.shape[3] / 1000                                  # :243
+    eps = (vat_normalize_eps(noise) * noise_scale).clone().detach().requires_grad_(True)   # :222-225
+    eps_pred_logits = dir_forward(x_hat.detach() + eps)                                    # :247
+    eps_pred_prob = F.softmax(eps_pred_logits, dim=1)                                      # :248
+    if cons_loss_fn == 'var':                                                              # :251-253
+        delta = eps_pred_prob - y_pred_prob
+        loss = (delta * delta).sum()
+    elif cons_loss_fn == 'bce':                                                            # :254-255
+        eps_ = 1e-6
+        loss = (-(y_pred_prob * torch.log(eps_pred_prob + eps_) +
+                  (1.0 - y_pred_prob) * torch.log(1.0 - eps_pred_prob + eps_))).sum()
+    elif cons_loss_fn == 'kld':                                                            # :256-257
+        loss = F.kl_div(F.log_softmax(eps_pred_logits, dim=1), y_pred_prob, reduction='none').sum()
+    elif cons_loss_fn == 'logits_var':                                                     # :258-260
+        delta = eps_pred_logits - y_pred_logits
+        loss = (delta * delta).sum()
+    else:
+        raise ValueError('Unknown consistency loss function {}'.format(cons_loss_fn))      # :261-262
+    eps_adv = torch.autograd.grad(outputs=loss, inputs=eps)[0]                              # :265-268
+    eps_adv_nrm = vat_normalize_eps(eps_adv)                                               # :271
+    if adaptive_vat_radius:                                                                # :277-296
+        delta_v = x_hat[:, :, 2:, :] - x_hat[:, :, :-2, :]
+        delta_h = x_hat[:, :, :, 2:] - x_hat[:, :, :, :-2]
+        delta_v = delta_v.reshape(len(delta_v), -1)
+        delta_h = delta_h.reshape(len(delta_h), -1)
+        adv_radius = vat_radius * torch.sqrt((delta_v ** 2).sum(dim=1) + (delta_h ** 2).sum(dim=1))[:, None, None, None] * 0.5
+    else:                                                                                  # :298-299
+        scale = math.sqrt(float(x_hat.shape[1] * x_hat.shape[2] * x_hat.shape[3]))
+        adv_radius = vat_radius * scale
+    return (eps_adv_nrm * adv_radius).detach()                                             # :301
+
+
 def supervised_loss(logits, labels_n1hw):
     """nn.CrossEntropyLoss(ignore_index=255)(logits, y[:, 0]) — :126, :300."""
     return F.cross_entropy(logits, labels_n1hw[:, 0], ignore_index=255)

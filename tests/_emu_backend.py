@@ -203,6 +203,25 @@ class EmuBackend(object):
         return self._finish(q, g, wmask, conf, conf, conf_thresh, conf_per_pixel, ramp, cons_weight)
 
 
+    # ------------------------------------------------------------------ VAT (csrc/vat.cu)
+    def sample_l2norm(self, x):
+        self.launches += 2
+        return x.reshape(x.shape[0], -1).double().pow(2).sum(1).float().sqrt()
+
+    def vat_adaptive_radius(self, x, vat_radius):
+        self.launches += 2
+        n = x.shape[0]
+        dv = (x[:, :, 2:, :] - x[:, :, :-2, :]).reshape(n, -1).double().pow(2).sum(1).float()
+        dh = (x[:, :, :, 2:] - x[:, :, :, :-2]).reshape(n, -1).double().pow(2).sum(1).float()
+        return (torch.tensor(vat_radius, dtype=torch.float32) * torch.sqrt(dv + dh)) * 0.5
+
+    def add_scaled_per_sample(self, x, e, mag, radius, out=None):
+        self.launches += 1
+        r = radius.view(-1, 1, 1, 1) if torch.is_tensor(radius) else torch.tensor(radius, dtype=torch.float32)
+        d = (e / (mag.view(-1, 1, 1, 1) + 1e-12)) * r
+        return d if x is None else x + d
+
+
 class EmuEMA(object):
     """Stand-in for optim_weight_ema.EMAWeightOptimizer.step() on CPU modules (optim_weight_ema.py:21-25 arithmetic); the
     product class refuses CPU tensors by design."""

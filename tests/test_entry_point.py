@@ -1,5 +1,6 @@
 """CPU: the drop-in entry points keep the reference's CLI and job-function surface (train_seg_semisup_mask_mt.py:16-42,
-581-650; train_seg_semisup_ict.py:4-14, 508-577; train_seg_semisup_aug_mt.py:4-16, 515-577; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
+581-650; train_seg_semisup_ict.py:4-14, 508-577; train_seg_semisup_aug_mt.py:4-16, 515-577;
+train_seg_semisup_vat_mt.py:4-17, 589-659; golden recorded from the unmodified reference by oracle/gen_golden.py)."""
 import inspect
 import json
 import os
@@ -10,6 +11,7 @@ import pytest
 import train_seg_semisup_aug_mt
 import train_seg_semisup_ict
 import train_seg_semisup_mask_mt
+import train_seg_semisup_vat_mt
 from architectures import network_architectures
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'entry_point.json')))
@@ -19,7 +21,7 @@ EXTRA_CHOICES = {'dataset': {'synthetic'}}
 
 
 SCRIPTS = {'train_seg_semisup_mask_mt': train_seg_semisup_mask_mt, 'train_seg_semisup_ict': train_seg_semisup_ict,
-           'train_seg_semisup_aug_mt': train_seg_semisup_aug_mt}
+           'train_seg_semisup_aug_mt': train_seg_semisup_aug_mt, 'train_seg_semisup_vat_mt': train_seg_semisup_vat_mt}
 entry = train_seg_semisup_mask_mt
 
 

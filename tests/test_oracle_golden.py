@@ -204,6 +204,59 @@ def test_affine_grid_sample_algorithm_matches_torch(shape):
     assert be.affine_grid_sample(x, far).abs().max().item() == 0.0
 
 
+def test_vat_perturbation_matches_the_reference_functions():
+    """oracle VAT block (torch_oracle.vat_perturbation) vs the reference's own helper functions
+    (train_seg_semisup_vat_mt.py:214-301) executed by gen_golden.py with a small seeded direction network."""
+    sys.path.insert(0, HERE)
+    from vat_recipe import vat_net, vat_inputs, vat_noise
+    gold = json.load(open(os.path.join(G, 'vat_block.json')))
+    net = vat_net()
+    x, x_hat = vat_inputs()
+    assert len(gold['cases']) == 8
+    for key, exp in gold['cases'].items():
+        fn, adaptive = key.split('_adaptive')
+        xp = TO.vat_perturbation(net, x, x_hat, vat_noise(exp['seed'], x.shape), fn, 0.5, bool(int(adaptive)))
+        assert not xp.requires_grad and xp.shape == x.shape
+        assert float(xp.double().abs().sum()) == pytest.approx(exp['abs_sum'], rel=1e-6), key
+        assert [float(v) for v in xp.reshape(3, -1).double().norm(dim=1)] == pytest.approx(exp['norms'], rel=1e-6), key
+        assert [float(v) for v in xp[:, :, 3, 5].reshape(-1)] == pytest.approx(exp['probe'], rel=1e-5, abs=1e-7), key
+        if not int(adaptive):          # fixed radius: |r_adv| = vat_radius * sqrt(C*H*W) for every sample (:298-301)
+            assert exp['norms'] == pytest.approx([0.5 * (3 * 10 * 14) ** 0.5] * 3, rel=1e-6)
+    with pytest.raises(ValueError):
+        TO.vat_perturbation(net, x, x_hat, vat_noise(1, x.shape), 'logits_smoothl1')
+
+
+def test_vat_kernel_algorithms_match_torch():
+    """The arithmetic of csrc/vat.cu as stated by the test doubles (tests/_emu_backend.py, tests/_emu_kernels.py): per-sample
+    norm, adaptive radius, normalise-scale-add and col2im (against the adjoint identity <im2col(x), c> == <x, col2im(c)>)."""
+    sys.path.insert(0, HERE)
+    from _emu_backend import EmuBackend
+    from _emu_kernels import EmuKernels
+    from cutmix_semisup_seg_b200.acts import Act
+    be, K = EmuBackend(), EmuKernels()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((3, 3, 11, 13), generator=g); e = torch.randn((3, 3, 11, 13), generator=g)
+    mag = be.sample_l2norm(e)
+    assert torch.allclose(mag, e.reshape(3, -1).norm(dim=1), rtol=1e-6)
+    want = x + TO.vat_normalize_eps(e) * 0.37
+    assert torch.allclose(be.add_scaled_per_sample(x, e, mag, 0.37), want, rtol=1e-6, atol=1e-7)
+    dv = x[:, :, 2:, :] - x[:, :, :-2, :]; dh = x[:, :, :, 2:] - x[:, :, :, :-2]
+    rad = 0.5 * torch.sqrt((dv.reshape(3, -1) ** 2).sum(1) + (dh.reshape(3, -1) ** 2).sum(1)) * 0.5
+    assert torch.allclose(be.vat_adaptive_radius(x, 0.5), rad, rtol=1e-6)
+    assert torch.allclose(be.add_scaled_per_sample(x, e, mag, rad), x + TO.vat_normalize_eps(e) * rad.view(-1, 1, 1, 1), rtol=1e-6, atol=1e-7)
+    for kh, stride, pad, dil in ((7, 2, 3, 1), (3, 1, 1, 1), (3, 2, 2, 2)):
+        xin = K.nchw_to_act(x, 4)
+        oh = (11 + 2 * pad - dil * (kh - 1) - 1) // stride + 1; ow = (13 + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        kpad = (kh * kh * 3 + 31) // 32 * 32
+        col = K.im2col(xin, kh, kh, stride, pad, dil, oh, ow, kpad)
+        c = col.like(); c.base.copy_(torch.randn(c.base.shape, generator=g))
+        dx = xin.like(); dx.base.zero_()
+        K.col2im(c, dx, kh, kh, stride, pad, dil, oh, ow, kpad)
+        lhs = (col.base.view(-1, kpad)[:, :kh * kh * 3].double() * c.base.view(-1, kpad)[:, :kh * kh * 3].double()).sum()
+        rhs = (xin.view4().double() * dx.view4().double()).sum()
+        assert float(lhs) == pytest.approx(float(rhs), rel=1e-6)
+
+
 def test_bit_exact_elementwise_oracles():
     rs = np.random.RandomState(0)
     t = rs.randn(100003).astype(np.float32); s = rs.randn(100003).astype(np.float32)

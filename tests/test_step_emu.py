@@ -45,7 +45,7 @@ def doubles():
     _restore(saved)
 
 
-def _build(mode, conf_per_pixel, batch_trunk, dist_group=None, cons_loss_fn='var'):
+def _build(mode, conf_per_pixel, batch_trunk, dist_group=None, cons_loss_fn='var', **vat):
     import torch_oracle as TO
     import ref_step
     import mask_gen
@@ -67,9 +67,9 @@ def _build(mode, conf_per_pixel, batch_trunk, dist_group=None, cons_loss_fn='var
     mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
     trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, cons_loss_fn=cons_loss_fn, cons_weight=0.7,
                                        conf_thresh=0.5, conf_per_pixel=conf_per_pixel, mask_mix=(mode != 'cut'),
-                                       batch_trunk=batch_trunk, dist_group=dist_group)
+                                       batch_trunk=batch_trunk, dist_group=dist_group, **vat)
     orc = ref_step.OracleMeanTeacher('deeplab2', sd, LR, cons_loss_fn=cons_loss_fn, cons_weight=0.7, conf_thresh=0.5,
-                                     conf_per_pixel=conf_per_pixel, mask_mix=(mode != 'cut'))
+                                     conf_per_pixel=conf_per_pixel, mask_mix=(mode != 'cut'), **vat)
     return student, teacher, trainer, orc, mg
 
 
@@ -82,6 +82,9 @@ def _batches(mode, mg, seed):
         uns_o = dict(uns)
     elif mode == 'aug':
         uns = synthetic.make_aug_batch(N, H, W, 20 + seed)
+        uns_o = dict(uns)
+    elif mode == 'vat':
+        uns = synthetic.make_vat_batch(N, H, W, 20 + seed, paired=True, with_noise=True)
         uns_o = dict(uns)
     else:
         uns = synthetic.make_unsup_batch(N, H, W, 20 + seed, mg, mask_mix=(mode == 'mix'), compact_masks=True)
@@ -117,6 +120,40 @@ def test_iteration_host_logic_matches_oracle(doubles, mode, conf_per_pixel, batc
     # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr; everything else ~1e-6
     assert _state_gap(student, orc.student) < 1.5e-3
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
+@pytest.mark.parametrize('fn,adaptive,from_student,conf_per_pixel', [('kld', False, False, False), ('var', True, True, True),
+                                                                      ('logits_var', True, False, False)])
+def test_vat_iteration_host_logic_matches_oracle(doubles, fn, adaptive, from_student, conf_per_pixel):
+    """VAT (train_seg_semisup_vat_mt.py:228-301, 364-452): direction from the input gradient of the direction network in
+    eval mode (no parameter gradient), fixed / adaptive radius, then the CutOut-style consistency step; both implementations
+    are driven with the same N(0,1) draw."""
+    student, teacher, trainer, orc, mg = _build('vat', conf_per_pixel, True, cons_loss_fn=fn, vat_radius=0.5,
+                                                adaptive_vat_radius=adaptive, vat_dir_from_student=from_student)
+    for it in range(2):
+        sup, uns, uns_o = _batches('vat', mg, it)
+        assert not trainer._can_batch_trunk([uns])
+        with torch.no_grad():
+            out = trainer.step(sup, [uns])
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], uns_o)
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=2e-5)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-3, abs=1e-8)     # the perturbation amplifies fp32 noise
+        assert float(out['conf_rate']) == pytest.approx(r_ref, abs=2.0 / (N * H * W))
+    dir_net = student if from_student else teacher
+    assert not dir_net.training                    # vat_dir_net.eval() persists (reference :237)
+    assert (teacher if from_student else student).training
+    assert _state_gap(student, orc.student) < 1.5e-3
+    assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
+def test_vat_rejects_loss_functions_the_reference_rejects(doubles):
+    student, teacher, trainer, orc, mg = _build('vat', False, True, cons_loss_fn='logits_smoothl1')
+    sup, uns, uns_o = _batches('vat', mg, 0)
+    with pytest.raises(ValueError, match='Unknown consistency loss function'):       # train_seg_semisup_vat_mt.py:261-262
+        with torch.no_grad():
+            trainer.step(sup, [uns])
+    with pytest.raises(ValueError, match='Unknown consistency loss function'):
+        orc.step(sup[0], sup[1], uns_o)
 
 
 @pytest.mark.parametrize('batch_trunk', [True, False])

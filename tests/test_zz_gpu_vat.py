@@ -1,0 +1,221 @@
+"""-m gpu: VAT (virtual adversarial training; reference train_seg_semisup_vat_mt.py:214-301, 364-452) on
+the B200 kernels: csrc/vat.cu (col2im, per-sample norm, adaptive radius, normalise-scale-add) against torch, the
+input-gradient-only backward pass of the networks against autograd on the oracle, the perturbation and full VAT iterations
+against the oracle's CPU iterations, and the drop-in entry point.
+
+STATUS: like tests/test_zz_gpu_aug.py these kernels were written after the round's GPU budget was spent: they compile for
+sm_100a, their algorithms and the host logic are pinned on the CPU (tests/test_oracle_golden.py, test_engine_emu.py,
+test_step_emu.py), but this file has not yet run on a B200.  Until it has, every test here is a NON-STRICT expected failure
+(a pass is reported as XPASS) and the file sorts after every verified GPU test.  B200SEG_VAT_VERIFIED=1 makes them binding."""
+import math
+import os
+import re
+import sys
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(__file__)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'oracle'))
+sys.path.insert(0, HERE)
+import torch_oracle as TO  # noqa: E402
+import ref_step  # noqa: E402
+import optim_weight_ema  # noqa: E402
+from architectures import network_architectures as na  # noqa: E402
+
+pytestmark = [pytest.mark.gpu]
+if os.environ.get('B200SEG_VAT_VERIFIED', '0') != '1':
+    pytestmark.append(pytest.mark.xfail(strict=False, reason='first B200 run of the VAT kernels is pending (GPU budget of the '
+                                                              'round was spent); see module docstring'))
+dev = torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module')
+def be():
+    from cutmix_semisup_seg_b200 import ops
+    return ops.default_backend()
+
+
+def test_per_sample_norm_radius_and_perturbation_match_torch(be):
+    g = torch.Generator().manual_seed(9)
+    for shape in ((3, 3, 11, 13), (2, 3, 65, 65), (1, 3, 321, 321), (4, 3, 2, 2)):
+        x = torch.randn(shape, generator=g); e = torch.randn(shape, generator=g) * 1e-3
+        n = shape[0]
+        mag = be.sample_l2norm(e.to(dev))
+        assert torch.allclose(mag.cpu(), e.reshape(n, -1).double().norm(dim=1).float(), rtol=2e-7, atol=0)
+        want = x + TO.vat_normalize_eps(e) * 0.37                          # train_seg_semisup_vat_mt.py:220, :301, :392
+        got = be.add_scaled_per_sample(x.to(dev), e.to(dev), mag, 0.37).cpu()
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+        only = be.add_scaled_per_sample(None, e.to(dev), mag, 2.5).cpu()
+        assert torch.allclose(only, TO.vat_normalize_eps(e) * 2.5, rtol=1e-6, atol=1e-9)
+        dv = x[:, :, 2:, :] - x[:, :, :-2, :]; dh = x[:, :, :, 2:] - x[:, :, :, :-2]
+        rad = 0.5 * torch.sqrt((dv.reshape(n, -1) ** 2).sum(1) + (dh.reshape(n, -1) ** 2).sum(1)) * 0.5      # :289-296
+        rdev = be.vat_adaptive_radius(x.to(dev), 0.5)
+        assert torch.allclose(rdev.cpu(), rad, rtol=2e-6, atol=0)
+        got = be.add_scaled_per_sample(x.to(dev), e.to(dev), mag, rdev).cpu()
+        assert torch.allclose(got, x + TO.vat_normalize_eps(e) * rad.view(-1, 1, 1, 1), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('kh,stride,pad,dil,shape', [(7, 2, 3, 1, (2, 3, 33, 41)), (3, 1, 1, 1, (1, 3, 9, 7)),
+                                                    (3, 2, 2, 2, (3, 3, 16, 16)), (7, 2, 3, 1, (2, 3, 65, 65))])
+def test_col2im_is_the_adjoint_of_im2col(be, kh, stride, pad, dil, shape):
+    """Against F.fold (the adjoint of F.unfold) in the column order of b2_im2col, and through <im2col(x), c> == <x, col2im(c)>
+    with the CUDA im2col."""
+    from cutmix_semisup_seg_b200.kernels import ActKernels
+    K = ActKernels(be)
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(h * w)
+    x = torch.randn(shape, generator=g)
+    oh = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1; ow = (w + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    kreal = kh * kh * c
+    kpad = (kreal + 31) // 32 * 32
+    xin = K.nchw_to_act(x.to(dev), 4)
+    col = K.im2col(xin, kh, kh, stride, pad, dil, oh, ow, kpad)
+    cvals = torch.randn((n * oh * ow, kpad), generator=g)
+    cact = col.like(); cact.base.copy_(cvals.to(dev).view(cact.base.shape))
+    dx = xin.like(); dx.base.zero_()
+    K.col2im(cact, dx, kh, kh, stride, pad, dil, oh, ow, kpad)
+    got = K.act_to_nchw(dx).cpu()
+    cols = cvals[:, :kreal].view(n, oh * ow, kh * kh, c).permute(0, 3, 2, 1).reshape(n, c * kh * kh, oh * ow)
+    want = F.fold(cols.double(), (h, w), (kh, kh), dilation=dil, padding=pad, stride=stride).float()
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    lhs = (col.base.view(-1, kpad)[:, :kreal].double().cpu() * cvals[:, :kreal].double()).sum()
+    rhs = (x.double() * got.double()).sum()
+    assert float(lhs) == pytest.approx(float(rhs), rel=1e-5)
+    K.col2im(cact, dx, kh, kh, stride, pad, dil, oh, ow, kpad, accumulate=True)
+    assert torch.allclose(K.act_to_nchw(dx).cpu(), 2 * got, rtol=1e-6, atol=1e-7)
+
+
+def _net(kind, classes, seed, gain=4.0):
+    net = na.seg.get(kind)(classes, pretrained=False)
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    sd = TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
+    net.load_state_dict(sd)
+    return net, sd
+
+
+@pytest.mark.parametrize('kind,classes,student', [('resnet101_deeplab_imagenet', 21, False),
+                                                  ('resnet101_deeplabv3plus_imagenet', 19, True)])
+def test_input_gradient_only_backward_matches_autograd(kind, classes, student):
+    """d(loss)/d(image) through the whole network in eval mode (3xTF32), no parameter gradient (vat :237-268)."""
+    from collections import OrderedDict
+    net, sd = _net(kind, classes, 7, gain=1.0)
+    if not student:
+        for p in net.parameters():
+            p.requires_grad = False
+    net.to(dev).eval()
+    net.b2_precision = '3xtf32'
+    torch.manual_seed(3)
+    x = torch.randn(2, 3, 65, 65); dy = torch.randn(2, classes, 65, 65)
+    logits, state = net.b2_forward(x.to(dev), record=True, input_grad=True)
+    dx = net.b2_backward(state, dy.to(dev), param_grads=False)
+    assert all(p.grad is None for p in net.parameters())
+    sd64 = OrderedDict((k, v.double().clone() if v.dtype == torch.float32 else v.clone()) for k, v in sd.items())
+    x64 = x.double().requires_grad_(True)
+    if 'v3plus' in kind:
+        yo = TO.deeplab3plus_forward(sd64, x64, backbone_bn_train=False, head_bn_train=False)
+    else:
+        yo = TO.deeplab2_forward(sd64, x64, bn_train=False)
+    yo.backward(dy.double())
+    assert (logits.cpu().double() - yo.detach()).abs().max().item() < 2e-4 * yo.abs().max().item()
+    err = (dx.cpu().double() - x64.grad).abs()
+    # whole-network gradients follow the sqrt(forward error) law (Precision): isolated gate flips dominate the
+    # maximum, the bulk agrees much better
+    assert err.max().item() < 5e-2 * x64.grad.abs().max().item()
+    assert err.median().item() < 5e-3 * x64.grad.abs().median().item()
+    cos = F.cosine_similarity(dx.cpu().double().reshape(2, -1), x64.grad.reshape(2, -1), dim=1)
+    assert cos.min().item() > 0.999
+
+
+@pytest.mark.parametrize('fn,adaptive', [('kld', False), ('var', True), ('bce', False), ('logits_var', True)])
+def test_vat_perturbation_matches_oracle(fn, adaptive):
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    net, sd = _net('resnet101_deeplab_imagenet', 21, 3)
+    for p in net.parameters():
+        p.requires_grad = False
+    net.to(dev)
+    net.b2_precision = '3xtf32'
+    trainer = step_mod.MeanTeacherStep(net, net, None, None, None, cons_loss_fn=fn, use_flat_grads=False, vat_radius=0.5,
+                                       adaptive_vat_radius=adaptive)
+    b = synthetic.make_vat_batch(2, 65, 65, 5, paired=True, with_noise=True)
+    x_adv = trainer.vat_perturbation(b['ux_tea'].to(dev), b['ux_stu'].to(dev), b['noise'].to(dev)).cpu()
+    assert not net.training
+    orc = ref_step.OracleMeanTeacher('deeplab2', sd, 1e-5)
+    want = TO.vat_perturbation(lambda t: TO.deeplab2_forward(orc.teacher, t, bn_train=False), b['ux_tea'], b['ux_stu'],
+                               b['noise'], fn, 0.5, adaptive)
+    got = x_adv - b['ux_stu']
+    n = got.shape[0]
+    assert torch.allclose(got.reshape(n, -1).norm(dim=1), want.reshape(n, -1).norm(dim=1), rtol=1e-4)
+    cos = F.cosine_similarity(got.reshape(n, -1).double(), want.reshape(n, -1).double(), dim=1)
+    assert cos.min().item() > 0.995          # direction = a normalised whole-network gradient (sqrt law, see above)
+
+
+@pytest.mark.parametrize('adaptive,conf_per_pixel', [(False, False), (True, True)])
+def test_vat_iterations_match_oracle(adaptive, conf_per_pixel):
+    """Three full VAT iterations (DeepLab v2, frozen BN, Adam with the duplicated group, EMA) vs the oracle's CPU iterations,
+    both driven with the same N(0,1) draws."""
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    n, h, w, c, lr = 2, 65, 65, 21, 3e-5
+    student, sd = _net('resnet101_deeplab_imagenet', c, 3)
+    teacher = na.seg.get('resnet101_deeplab_imagenet')(c, pretrained=False)
+    student.to(dev); teacher.to(dev)
+    student.b2_precision = teacher.b2_precision = '3xtf32'
+    for p in teacher.parameters():
+        p.requires_grad = False
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'adam', lr, fused_kernel=True)
+    ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+    student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, None, cons_loss_fn='kld', cons_weight=0.7, conf_thresh=0.5,
+                                       conf_per_pixel=conf_per_pixel, vat_radius=0.5, adaptive_vat_radius=adaptive)
+    orc = ref_step.OracleMeanTeacher('deeplab2', sd, lr, cons_loss_fn='kld', cons_weight=0.7, conf_thresh=0.5,
+                                     conf_per_pixel=conf_per_pixel, vat_radius=0.5, adaptive_vat_radius=adaptive)
+    for it in range(3):
+        sup = synthetic.make_sup_batch(n, h, w, c, 10 + it)
+        uns = synthetic.make_vat_batch(n, h, w, 20 + it, paired=True, with_noise=True)
+        out = trainer.step((sup[0].to(dev), sup[1].to(dev)), [{k: v.to(dev) for k, v in uns.items()}])
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], dict(uns))
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=1e-4)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-2, abs=1e-7)      # adversarial direction: sqrt law
+        assert float(out['conf_rate']) == pytest.approx(r_ref, abs=2e-3)
+    for name, net, ref in (('teacher', teacher, orc.teacher), ('student', student, orc.student)):
+        worst = 0.0
+        for k, v in net.state_dict().items():
+            if v.dtype == torch.float32:
+                r = ref[k].detach()
+                worst = max(worst, (v.cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-12))
+        assert worst < 1.5e-3, (name, worst)
+
+
+VAT_CASES = {
+    'vat_mean_teacher_dl2': ['--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21'],
+    'vat_dl3plus_adaptive_from_student': ['--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes', '19',
+                                          '--adaptive_vat_radius', '--vat_dir_from_student', '--cons_loss_fn', 'var',
+                                          '--conf_per_pixel', '--opt_type', 'sgd', '--rampup', '2', '--aug_strong_colour'],
+    'vat_pi_model': ['--arch', 'resnet101_deeplab_imagenet', '--model', 'pi', '--vat_radius', '0.2', '--cons_loss_fn', 'logits_var'],
+}
+BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size', '65,65', '--batch_size', '2',
+        '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']
+
+
+@pytest.mark.parametrize('name', sorted(VAT_CASES))
+def test_vat_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
+    """train_seg_semisup_vat_mt.py through its click command."""
+    from click.testing import CliRunner
+    import train_seg_semisup_vat_mt
+    monkeypatch.chdir(tmp_path)
+    r = CliRunner().invoke(train_seg_semisup_vat_mt.experiment, BASE + VAT_CASES[name] + ['--job_desc', name],
+                           catch_exceptions=False)
+    assert r.exit_code == 0, r.output
+    lines = [l for l in r.output.splitlines() if l.startswith('Epoch ')]
+    assert len(lines) == 2, r.output
+    for l in lines:
+        m = re.search(r'TRAIN clf loss=([-0-9.enainf]+), consistency loss=([-0-9.enainf]+), conf rate=([-0-9.]+)%, VAL mIoU=([-0-9.]+)%', l)
+        assert m, l
+        sup, cons, conf, miou = (float(x) for x in m.groups())
+        assert math.isfinite(sup) and sup > 0.0 and math.isfinite(cons) and cons >= 0.0
+        assert 0.0 <= conf <= 100.0 and 0.0 <= miou <= 100.0
+    assert os.path.exists(os.path.join('results', 'train_seg_semisup_vat_mt', 'log_{}.txt'.format(name)))

@@ -1,0 +1,127 @@
+"""Drop-in entry point for the reference's `train_seg_semisup_vat_mt.py` (virtual adversarial training):
+mean-teacher semi-supervised segmentation where the student sees the unlabelled image plus an adversarial perturbation --
+the normalised input gradient of a consistency loss, computed through the direction network in eval mode (reference lines
+228-301) and scaled to a fixed or image-adaptive radius -- and is trained towards the teacher's prediction on the clean
+image (lines 364-452).  The iteration runs on the B200 kernels (cutmix_semisup_seg_b200.step.MeanTeacherStep.unsupervised_vat:
+input-gradient-only backward pass through the tensor-core convolutions incl. the stem, csrc/vat.cu for the norm / radius /
+perturbation arithmetic, the fused consistency kernel); the outer loop is cutmix_semisup_seg_b200.train_loop.run_training.
+
+The click surface (option names and defaults, reference lines 589-659 -- `--cons_loss_fn` defaults to `kld` and has no
+`logits_smoothl1` choice, `--sgd_nesterov` defaults to True) and the job function signature are kept; the additions
+(`--dataset synthetic`, `--no_pretrained`, `--ddp`, `--synthetic_classes`) are those of train_seg_semisup_mask_mt.py.  Kept on
+purpose: the direction network is switched to eval mode inside the iteration and stays there until the next epoch's
+`.train()` (reference line 237), which changes the DeepLab v3+ head (BatchNorm statistics, dropout) for the rest of the epoch.
+The initial perturbation noise is drawn with torch.randn on the device like the reference (line 222).
+"""
+import click
+
+import job_helper
+
+
+@job_helper.job('train_seg_semisup_vat_mt', enumerate_job_names=False)
+def train_seg_semisup_vat_mt(submit_config, dataset, model, arch, freeze_bn,
+                             opt_type, sgd_momentum, sgd_nesterov, sgd_weight_decay,
+                             learning_rate, lr_sched, lr_step_epochs, lr_step_gamma, lr_poly_power,
+                             teacher_alpha, bin_fill_holes,
+                             crop_size, aug_hflip, aug_vflip, aug_hvflip, aug_scale_hung, aug_max_scale, aug_scale_non_uniform, aug_rot_mag,
+                             aug_strong_colour, aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
+                             aug_colour_prob, aug_colour_greyscale_prob,
+                             vat_radius, adaptive_vat_radius, vat_dir_from_student,
+                             cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
+                             num_epochs, iters_per_epoch, batch_size,
+                             n_sup, n_unsup, n_val, split_seed, split_path, val_seed, save_preds, save_model, num_workers,
+                             no_pretrained=False, ddp=False, synthetic_classes=21):
+    settings = locals().copy()
+    del settings['submit_config']
+    from cutmix_semisup_seg_b200 import synthetic, train_loop
+
+    def make_unsup(n, h, w, seed, device):
+        return synthetic.make_vat_batch(n, h, w, seed, paired=aug_strong_colour, device=device)
+
+    train_loop.run_training(
+        submit_config, settings, make_unsup, None, True,
+        dataset=dataset, model=model, arch=arch, freeze_bn=freeze_bn, opt_type=opt_type, sgd_momentum=sgd_momentum,
+        sgd_nesterov=sgd_nesterov, sgd_weight_decay=sgd_weight_decay, learning_rate=learning_rate, lr_sched=lr_sched,
+        lr_step_epochs=lr_step_epochs, lr_step_gamma=lr_step_gamma, lr_poly_power=lr_poly_power, teacher_alpha=teacher_alpha,
+        bin_fill_holes=bin_fill_holes, crop_size=crop_size, cons_loss_fn=cons_loss_fn, cons_weight=cons_weight,
+        conf_thresh=conf_thresh, conf_per_pixel=conf_per_pixel, rampup=rampup, unsup_batch_ratio=unsup_batch_ratio,
+        num_epochs=num_epochs, iters_per_epoch=iters_per_epoch, batch_size=batch_size, save_model=save_model,
+        no_pretrained=no_pretrained, ddp=ddp, synthetic_classes=synthetic_classes,
+        step_options=dict(vat_radius=vat_radius, adaptive_vat_radius=adaptive_vat_radius,
+                          vat_dir_from_student=vat_dir_from_student))
+
+
+@click.command()
+@click.option('--job_desc', type=str, default='')
+@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic']),
+              default='pascal_aug')
+@click.option('--model', type=click.Choice(['mean_teacher', 'pi']), default='mean_teacher')
+@click.option('--arch', type=str, default='resnet101_deeplab_imagenet')
+@click.option('--freeze_bn', is_flag=True, default=False)
+@click.option('--opt_type', type=click.Choice(['adam', 'sgd']), default='adam')
+@click.option('--sgd_momentum', type=float, default=0.9)
+@click.option('--sgd_nesterov', is_flag=True, default=True)
+@click.option('--sgd_weight_decay', type=float, default=5e-4)
+@click.option('--learning_rate', type=float, default=1e-4)
+@click.option('--lr_sched', type=click.Choice(['none', 'stepped', 'cosine', 'poly']), default='none')
+@click.option('--lr_step_epochs', type=str, default='')
+@click.option('--lr_step_gamma', type=float, default=0.1)
+@click.option('--lr_poly_power', type=float, default=0.9)
+@click.option('--teacher_alpha', type=float, default=0.99)
+@click.option('--bin_fill_holes', is_flag=True, default=False)
+@click.option('--crop_size', type=str, default='321,321')
+@click.option('--aug_hflip', is_flag=True, default=False)
+@click.option('--aug_vflip', is_flag=True, default=False)
+@click.option('--aug_hvflip', is_flag=True, default=False)
+@click.option('--aug_scale_hung', is_flag=True, default=False)
+@click.option('--aug_max_scale', type=float, default=1.0)
+@click.option('--aug_scale_non_uniform', is_flag=True, default=False)
+@click.option('--aug_rot_mag', type=float, default=0.0)
+@click.option('--aug_strong_colour', is_flag=True, default=False)
+@click.option('--aug_colour_brightness', type=float, default=0.4)
+@click.option('--aug_colour_contrast', type=float, default=0.4)
+@click.option('--aug_colour_saturation', type=float, default=0.4)
+@click.option('--aug_colour_hue', type=float, default=0.1)
+@click.option('--aug_colour_prob', type=float, default=0.8)
+@click.option('--aug_colour_greyscale_prob', type=float, default=0.2)
+@click.option('--vat_radius', type=float, default=0.5)
+@click.option('--adaptive_vat_radius', is_flag=True, default=False)
+@click.option('--vat_dir_from_student', is_flag=True, default=False)
+@click.option('--cons_loss_fn', type=click.Choice(['var', 'bce', 'kld', 'logits_var']), default='kld')
+@click.option('--cons_weight', type=float, default=1.0)
+@click.option('--conf_thresh', type=float, default=0.97)
+@click.option('--conf_per_pixel', is_flag=True, default=False)
+@click.option('--rampup', type=int, default=-1)
+@click.option('--unsup_batch_ratio', type=int, default=1)
+@click.option('--num_epochs', type=int, default=300)
+@click.option('--iters_per_epoch', type=int, default=-1)
+@click.option('--batch_size', type=int, default=10)
+@click.option('--n_sup', type=int, default=100)
+@click.option('--n_unsup', type=int, default=-1)
+@click.option('--n_val', type=int, default=-1)
+@click.option('--split_seed', type=int, default=12345)
+@click.option('--split_path', type=click.Path(readable=True, exists=True))
+@click.option('--val_seed', type=int, default=131)
+@click.option('--save_preds', is_flag=True, default=False)
+@click.option('--save_model', is_flag=True, default=False)
+@click.option('--num_workers', type=int, default=4)
+@click.option('--no_pretrained', is_flag=True, default=False, help='[B200 build] random init instead of cached weights')
+@click.option('--ddp', is_flag=True, default=False, help='[B200 build] data parallel under torchrun (one process per GPU)')
+@click.option('--synthetic_classes', type=int, default=21, help='[B200 build] class count of --dataset synthetic')
+def experiment(job_desc, dataset, model, arch, freeze_bn,
+               opt_type, sgd_momentum, sgd_nesterov, sgd_weight_decay,
+               learning_rate, lr_sched, lr_step_epochs, lr_step_gamma, lr_poly_power,
+               teacher_alpha, bin_fill_holes,
+               crop_size, aug_hflip, aug_vflip, aug_hvflip, aug_scale_hung, aug_max_scale, aug_scale_non_uniform, aug_rot_mag,
+               aug_strong_colour, aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
+               aug_colour_prob, aug_colour_greyscale_prob,
+               vat_radius, adaptive_vat_radius, vat_dir_from_student, cons_loss_fn, cons_weight, conf_thresh, conf_per_pixel, rampup, unsup_batch_ratio,
+               num_epochs, iters_per_epoch, batch_size,
+               n_sup, n_unsup, n_val, split_seed, split_path, val_seed, save_preds, save_model, num_workers,
+               no_pretrained, ddp, synthetic_classes):
+    params = locals().copy()
+    train_seg_semisup_vat_mt.submit(**params)
+
+
+if __name__ == '__main__':
+    experiment()
