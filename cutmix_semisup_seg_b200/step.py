@@ -1,4 +1,6 @@
-"""One iteration of the CutMix / CutOut mean-teacher loop on the B200 kernels.
+"""One iteration of the CutMix / CutOut mean-teacher loop on the B200 kernels -- and of its sibling scripts, which share
+everything but the unsupervised branch: ICT (`unsupervised_ict`), augmentation consistency (`unsupervised_aug`), VAT
+(`unsupervised_vat`).
 
 This is the body of the reference's training loop (train_seg_semisup_mask_mt.py:287-476) with the
 same order of operations and the same arithmetic, restructured for the GPU:
@@ -12,7 +14,8 @@ same order of operations and the same arithmetic, restructured for the GPU:
   float(conf_mask.mean()), float(loss) host syncs    scalars stay on the device (read them when logging)
   loss.backward() through autograd                   engine tape; the 1/N, conf-rate, ramp and weight scalars
                                                      are applied by the first backward kernel from a device scalar
-  student_optim.step(); teacher_optim.step()         torch.optim (unchanged) ; fused multi-tensor EMA kernel
+  student_optim.step(); teacher_optim.step()         ONE fused optimiser + EMA launch (optim.FusedOptimizer); torch.optim +
+                                                     the multi-tensor EMA kernel when an ordinary optimiser is passed
   (single GPU)                                       optional data parallelism: ONE all-reduce(avg) of the
                                                      flat student-gradient buffer before the optimiser step
 """
