@@ -26,7 +26,7 @@ import torch_oracle as TO  # noqa: E402
 import ref_step  # noqa: E402
 import optim_weight_ema  # noqa: E402
 from architectures import network_architectures as na  # noqa: E402
-from aug_recipe import aug_inputs, parse_case, affine_thetas  # noqa: E402
+from aug_recipe import aug_inputs, parse_case  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
 if os.environ.get('B200SEG_AUG_VERIFIED', '0') != '1':
