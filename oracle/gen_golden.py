@@ -16,6 +16,8 @@ Contents
   aug_block.json    augmentation-consistency loss block (train_seg_semisup_aug_mt.py:291-394), the same way
   vat_block.json    VAT perturbation (train_seg_semisup_vat_mt.py:214-301): the reference's own helper functions executed
                     with a small seeded direction network, four loss functions x fixed / adaptive radius
+  sibling_iterations.json  two full iterations of the aug (DeepLab v2) and VAT (DeepLab v3+) loops: reference classes + the
+                    reference scripts' own unsupervised-branch lines, Adam, EMA (pins oracle/ref_step.py's aug / VAT branches)
   entry_point.json  click surface of the reference's `train_seg_semisup_mask_mt.experiment` (option names, flags,
                     defaults, choices) and the parameter list of the job function, plus lr_schedules / sigmoid_rampup
                     known answers the entry point depends on
@@ -334,6 +336,83 @@ def gen_vat_block():
     json.dump(out, open(os.path.join(OUT, 'vat_block.json'), 'w'), indent=1)
 
 
+def gen_sibling_iterations():
+    """Two full iterations of the augmentation-consistency loop (DeepLab v2) and of the VAT loop (DeepLab v3+, so that the
+    eval-mode persistence of the direction network reaches train-mode BatchNorm layers) with the reference's OWN classes
+    (networks, EMAWeightOptimizer), torch Adam on the reference's parameter groups, and the unsupervised branch executed from
+    the reference scripts' own source lines (train_seg_semisup_aug_mt.py:295-398, train_seg_semisup_vat_mt.py:214-301 +
+    397-464).  Dropout probability of the DeepLab v3+ head is set to 0 in both networks (the draw of nn.Dropout cannot be
+    shared with another implementation).  -> tests/golden/sibling_iterations.json"""
+    import textwrap
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    from aug_recipe import affine_thetas
+
+    def cut(script, first, last):
+        lines = open(os.path.join(REF, script)).read().splitlines()
+        i0 = next(i for i, l in enumerate(lines) if l.strip() == first)
+        i1 = next(i for i, l in enumerate(lines) if i > i0 and l.strip() == last) + 1
+        return textwrap.dedent('\n'.join(lines[i0:i1])), [i0 + 1, i1]
+
+    aug_block, aug_lines = cut('train_seg_semisup_aug_mt.py', '# Get teacher predictions for image0', 'unsup_loss.backward()')
+    vat_helpers, vat_hl = cut('train_seg_semisup_vat_mt.py', 'def t_dot(a, b):',
+                              'return (eps_adv_nrm * adv_radius).detach(), y_pred_logits, y_pred_prob')
+    vat_block, vat_lines = cut('train_seg_semisup_vat_mt.py', '# Compute VAT perburbation', 'unsup_loss.backward()')
+    out = dict(ref_lines=dict(aug=aug_lines, vat_helpers=vat_hl, vat=vat_lines), runs={})
+    crit = nn.CrossEntropyLoss(ignore_index=255)
+    for mode, kind, classes, lr, gain in (('aug', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0),
+                                          ('vat', 'resnet101_deeplabv3plus_imagenet', 19, 1e-5, 4.0)):
+        n, h, w = 2, 33, 33
+        student = build(kind, classes, seed=3, gain=gain)
+        teacher = network_architectures.seg.get(kind)(classes, pretrained=False)
+        for p in teacher.parameters():
+            p.requires_grad = False
+        for net in (student, teacher):
+            for m in net.modules():
+                if isinstance(m, nn.Dropout):
+                    m.p = 0.0
+        optim = torch.optim.Adam([dict(params=student.pretrained_parameters(), lr=lr * 0.1),
+                                  dict(params=student.new_parameters(), lr=lr)], foreach=False)
+        ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+        rec = dict(kind=kind, classes=classes, n=n, h=h, w=w, lr=lr, seed=3, gain=gain, conf_thresh=0.5, cons_weight=0.7,
+                   cons_loss_fn='var' if mode == 'aug' else 'kld', conf_per_pixel=(mode == 'vat'), vat_radius=0.5,
+                   adaptive_vat_radius=True, steps=[])
+        student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()      # epoch start
+        ns = dict(np=np, torch=torch, F=F, math=math, network_architectures=network_architectures,
+                  affine_align_corners_kw=dict(align_corners=True), teacher_net=teacher, student_net=student,
+                  conf_thresh=0.5, conf_per_pixel=rec['conf_per_pixel'], rampup=-1, ramp_val=1.0, cons_loss_fn=rec['cons_loss_fn'],
+                  root_n_classes=math.sqrt(classes), cons_weight=0.7, vat_dir_net=teacher, adaptive_vat_radius=True,
+                  vat_radius=0.5)
+        if mode == 'vat':
+            exec(vat_helpers, ns)
+        for it in range(2):
+            g = torch.Generator().manual_seed(300 + it)
+            sup_x = torch.randn((n, 3, h, w), generator=g)
+            sup_y = torch.randint(0, classes, (n, 1, h, w), generator=g); sup_y[:, :, :4] = 255
+            ux0 = torch.randn((n, 3, h, w), generator=g); ux1 = ux0 + 0.1 * torch.randn((n, 3, h, w), generator=g)
+            um0 = torch.ones((n, 1, h, w)); um0[:, :, :3] = 0; um1 = torch.ones((n, 1, h, w)); um1[:, :, :, 16] = 0.5
+            optim.zero_grad()
+            sup_loss = crit(student(sup_x), sup_y[:, 0]); sup_loss.backward()
+            ns['conf_rate_acc'] = 0.0
+            if mode == 'aug':
+                ns.update(batch_ux0=ux0, batch_ux1=ux1, batch_um0=um0, batch_um1=um1,
+                          batch_ufx0_to_1=affine_thetas()[it:it + 2] if it == 0 else affine_thetas()[[2, 0]])
+                exec(aug_block, ns)
+            else:
+                torch.manual_seed(500 + it)                     # the draw of normalized_noise_like (:222)
+                ns.update(batch_ux_tea=ux0, batch_ux_stu=ux1, batch_um=um0)
+                exec(vat_block, ns)
+            optim.step(); ema.step()
+            tsd, ssd = teacher.state_dict(), student.state_dict()
+            rec['steps'].append(dict(
+                sup_loss=float(sup_loss), cons_loss=float(ns['consistency_loss']), conf_rate=float(ns['conf_rate_acc']),
+                teacher_training=bool(teacher.training), student_training=bool(student.training),
+                teacher_abs_sum=float(sum(v.double().abs().sum() for v in tsd.values() if v.dtype == torch.float32)),
+                student_abs_sum=float(sum(v.double().abs().sum() for v in ssd.values() if v.dtype == torch.float32)),
+                student_conv1_sum=float(ssd['conv1.weight' if mode == 'aug' else 'deeplab.backbone.conv1.weight'].double().sum())))
+        out['runs'][mode] = rec
+    json.dump(out, open(os.path.join(OUT, 'sibling_iterations.json'), 'w'), indent=1)
+
+
 def gen_entry_point():
     """Reference CLI / job-function surface of the two drop-in scripts (train_seg_semisup_mask_mt.py:16-42, 581-650;
     train_seg_semisup_ict.py:4-14, 508-577)."""
@@ -361,6 +440,7 @@ if __name__ == '__main__':
     gen_ict_block(); print('ict block')
     gen_aug_block(); print('aug block')
     gen_vat_block(); print('vat block')
+    gen_sibling_iterations(); print('sibling iterations')
     gen_masks(); print('masks')
     gen_state_dicts(); print('state dicts')
     gen_loss_block(); print('loss block')

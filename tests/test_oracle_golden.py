@@ -257,6 +257,46 @@ def test_vat_kernel_algorithms_match_torch():
         assert float(lhs) == pytest.approx(float(rhs), rel=1e-6)
 
 
+@pytest.mark.parametrize('mode', ['aug', 'vat'])
+def test_sibling_iterations_match_reference_loops(mode):
+    """Two iterations of the oracle's augmentation-consistency / VAT loop == the reference's classes driven by the reference
+    scripts' own unsupervised-branch lines (oracle/gen_golden.py::gen_sibling_iterations): losses, confidence rate, post-step
+    student and teacher state, and the train / eval mode the reference leaves the networks in."""
+    sys.path.insert(0, HERE)
+    from aug_recipe import affine_thetas
+    from vat_recipe import vat_noise
+    gold = json.load(open(os.path.join(G, 'sibling_iterations.json')))['runs'][mode]
+    n, h, w, c = gold['n'], gold['h'], gold['w'], gold['classes']
+    net, sd = _synth(gold['kind'], c, seed=gold['seed'], gain=gold['gain'])
+    arch = 'deeplab2' if mode == 'aug' else 'deeplab3plus'
+    tr = ref_step.OracleMeanTeacher(arch, sd, gold['lr'], cons_loss_fn=gold['cons_loss_fn'], cons_weight=gold['cons_weight'],
+                                    conf_thresh=gold['conf_thresh'], conf_per_pixel=gold['conf_per_pixel'],
+                                    vat_radius=gold['vat_radius'], adaptive_vat_radius=gold['adaptive_vat_radius'])
+    tr.start_epoch()
+    conv1 = 'conv1.weight' if mode == 'aug' else 'deeplab.backbone.conv1.weight'
+    for it, exp in enumerate(gold['steps']):
+        g = torch.Generator().manual_seed(300 + it)
+        sup_x = torch.randn((n, 3, h, w), generator=g)
+        sup_y = torch.randint(0, c, (n, 1, h, w), generator=g); sup_y[:, :, :4] = 255
+        ux0 = torch.randn((n, 3, h, w), generator=g); ux1 = ux0 + 0.1 * torch.randn((n, 3, h, w), generator=g)
+        um0 = torch.ones((n, 1, h, w)); um0[:, :, :3] = 0; um1 = torch.ones((n, 1, h, w)); um1[:, :, :, 16] = 0.5
+        if mode == 'aug':
+            theta = affine_thetas()[it:it + 2] if it == 0 else affine_thetas()[[2, 0]]
+            uns = dict(ux0=ux0, ux1=ux1, um0=um0, um1=um1, xf0_to_1=theta)
+        else:
+            uns = dict(ux_tea=ux0, ux_stu=ux1, um=um0, vat=torch.ones(1), noise=vat_noise(500 + it, ux0.shape))
+        s, cl, cr = tr.step(sup_x, sup_y, uns)
+        assert s == pytest.approx(exp['sup_loss'], rel=1e-5)
+        assert cl == pytest.approx(exp['cons_loss'], rel=2e-3, abs=1e-9)
+        assert cr == pytest.approx(exp['conf_rate'], abs=1e-6)
+        assert tr.eval_mode == {'student': not exp['student_training'], 'teacher': not exp['teacher_training']}
+        assert float(tr.student[conv1].double().sum()) == pytest.approx(exp['student_conv1_sum'], rel=1e-5)
+        ssum = float(sum(v.double().abs().sum() for v in tr.student.values() if v.dtype == torch.float32))
+        tsum = float(sum(v.double().abs().sum() for v in tr.teacher.values() if v.dtype == torch.float32))
+        assert ssum == pytest.approx(exp['student_abs_sum'], rel=1e-7)
+        assert tsum == pytest.approx(exp['teacher_abs_sum'], rel=1e-7)
+
+
 def test_bit_exact_elementwise_oracles():
     rs = np.random.RandomState(0)
     t = rs.randn(100003).astype(np.float32); s = rs.randn(100003).astype(np.float32)

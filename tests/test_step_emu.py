@@ -146,6 +146,52 @@ def test_vat_iteration_host_logic_matches_oracle(doubles, fn, adaptive, from_stu
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
 
 
+def test_vat_deeplab3plus_direction_network_stays_in_eval_mode(doubles):
+    """DeepLab v3+ has train-mode BatchNorm in its head: the reference leaves the direction network (here the teacher) in
+    eval mode after the first VAT direction pass (train_seg_semisup_vat_mt.py:237), so its later forward passes use running
+    statistics.  Two iterations against the oracle (which is pinned to the reference's own classes and lines for this case,
+    tests/golden/sibling_iterations.json)."""
+    import torch_oracle as TO
+    import ref_step
+    from _emu_backend import EmuEMA
+    from architectures import network_architectures as na
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    kind, c, lr = 'resnet101_deeplabv3plus_imagenet', 19, 1e-5
+    student = na.seg.get(kind)(c, pretrained=False)
+    final = [k for k in student.state_dict() if 'classifier.classifier.6' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(student.state_dict(), seed=3, logit_gain=4.0, final_keys=final)
+    student.load_state_dict(sd)
+    teacher = na.seg.get(kind)(c, pretrained=False)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    for net in (student, teacher):
+        for m in net.modules():
+            if hasattr(m, 'next_mask'):
+                m.p = 0.0                              # the dropout draw cannot be shared with the oracle
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'adam', lr)
+    ema = EmuEMA(teacher, student, 0.99)
+    student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, None, cons_loss_fn='kld', cons_weight=0.7, conf_thresh=0.5,
+                                       conf_per_pixel=True, vat_radius=0.5, adaptive_vat_radius=True)
+    orc = ref_step.OracleMeanTeacher('deeplab3plus', sd, lr, cons_loss_fn='kld', cons_weight=0.7, conf_thresh=0.5,
+                                     conf_per_pixel=True, vat_radius=0.5, adaptive_vat_radius=True)
+    orc.start_epoch()
+    for it in range(2):
+        sup = synthetic.make_sup_batch(N, H, W, c, 10 + it)
+        uns = synthetic.make_vat_batch(N, H, W, 20 + it, paired=True, with_noise=True)
+        with torch.no_grad():
+            out = trainer.step(sup, [uns])
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], dict(uns))
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=5e-5)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=5e-3, abs=1e-8)
+        assert float(out['conf_rate']) == pytest.approx(r_ref, abs=2.0 / (N * H * W))
+        assert not teacher.training and student.training
+    assert _state_gap(student, orc.student) < 1.5e-3
+    assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
 def test_vat_rejects_loss_functions_the_reference_rejects(doubles):
     student, teacher, trainer, orc, mg = _build('vat', False, True, cons_loss_fn='logits_smoothl1')
     sup, uns, uns_o = _batches('vat', mg, 0)
