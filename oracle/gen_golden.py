@@ -337,11 +337,11 @@ def gen_vat_block():
 
 
 def gen_sibling_iterations():
-    """Two full iterations of the augmentation-consistency loop (DeepLab v2) and of the VAT loop (DeepLab v3+, so that the
+    """Two full iterations of the augmentation-consistency and ICT loops (DeepLab v2) and of the VAT loop (DeepLab v3+, so that the
     eval-mode persistence of the direction network reaches train-mode BatchNorm layers) with the reference's OWN classes
     (networks, EMAWeightOptimizer), torch Adam on the reference's parameter groups, and the unsupervised branch executed from
     the reference scripts' own source lines (train_seg_semisup_aug_mt.py:295-398, train_seg_semisup_vat_mt.py:214-301 +
-    397-464).  Dropout probability of the DeepLab v3+ head is set to 0 in both networks (the draw of nn.Dropout cannot be
+    397-464, train_seg_semisup_ict.py:305-391).  Dropout probability of the DeepLab v3+ head is set to 0 in both networks (the draw of nn.Dropout cannot be
     shared with another implementation).  -> tests/golden/sibling_iterations.json"""
     import textwrap
     sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
@@ -357,10 +357,12 @@ def gen_sibling_iterations():
     vat_helpers, vat_hl = cut('train_seg_semisup_vat_mt.py', 'def t_dot(a, b):',
                               'return (eps_adv_nrm * adv_radius).detach(), y_pred_logits, y_pred_prob')
     vat_block, vat_lines = cut('train_seg_semisup_vat_mt.py', '# Compute VAT perburbation', 'unsup_loss.backward()')
-    out = dict(ref_lines=dict(aug=aug_lines, vat_helpers=vat_hl, vat=vat_lines), runs={})
+    ict_block, ict_lines = cut('train_seg_semisup_ict.py', '# ICT mix factors', 'unsup_loss.backward()')
+    out = dict(ref_lines=dict(aug=aug_lines, vat_helpers=vat_hl, vat=vat_lines, ict=ict_lines), runs={})
     crit = nn.CrossEntropyLoss(ignore_index=255)
     for mode, kind, classes, lr, gain in (('aug', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0),
-                                          ('vat', 'resnet101_deeplabv3plus_imagenet', 19, 1e-5, 4.0)):
+                                          ('vat', 'resnet101_deeplabv3plus_imagenet', 19, 1e-5, 4.0),
+                                          ('ict', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0)):
         n, h, w = 2, 33, 33
         student = build(kind, classes, seed=3, gain=gain)
         teacher = network_architectures.seg.get(kind)(classes, pretrained=False)
@@ -374,14 +376,14 @@ def gen_sibling_iterations():
                                   dict(params=student.new_parameters(), lr=lr)], foreach=False)
         ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
         rec = dict(kind=kind, classes=classes, n=n, h=h, w=w, lr=lr, seed=3, gain=gain, conf_thresh=0.5, cons_weight=0.7,
-                   cons_loss_fn='var' if mode == 'aug' else 'kld', conf_per_pixel=(mode == 'vat'), vat_radius=0.5,
+                   cons_loss_fn={'aug': 'var', 'vat': 'kld', 'ict': 'bce'}[mode], conf_per_pixel=(mode != 'aug'), vat_radius=0.5, ict_alpha=0.4,
                    adaptive_vat_radius=True, steps=[])
         student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()      # epoch start
         ns = dict(np=np, torch=torch, F=F, math=math, network_architectures=network_architectures,
                   affine_align_corners_kw=dict(align_corners=True), teacher_net=teacher, student_net=student,
                   conf_thresh=0.5, conf_per_pixel=rec['conf_per_pixel'], rampup=-1, ramp_val=1.0, cons_loss_fn=rec['cons_loss_fn'],
                   root_n_classes=math.sqrt(classes), cons_weight=0.7, vat_dir_net=teacher, adaptive_vat_radius=True,
-                  vat_radius=0.5)
+                  vat_radius=0.5, ict_alpha=0.4, torch_device=torch.device('cpu'))
         if mode == 'vat':
             exec(vat_helpers, ns)
         for it in range(2):
@@ -397,6 +399,10 @@ def gen_sibling_iterations():
                 ns.update(batch_ux0=ux0, batch_ux1=ux1, batch_um0=um0, batch_um1=um1,
                           batch_ufx0_to_1=affine_thetas()[it:it + 2] if it == 0 else affine_thetas()[[2, 0]])
                 exec(aug_block, ns)
+            elif mode == 'ict':
+                np.random.seed(700 + it)                        # the draw of np.random.beta (:306)
+                ns.update(batch_ux0_tea=ux0, batch_ux0_stu=ux0, batch_ux1_tea=ux1, batch_ux1_stu=ux1, batch_um0=um0, batch_um1=um1)
+                exec(ict_block, ns)
             else:
                 torch.manual_seed(500 + it)                     # the draw of normalized_noise_like (:222)
                 ns.update(batch_ux_tea=ux0, batch_ux_stu=ux1, batch_um=um0)
@@ -408,7 +414,9 @@ def gen_sibling_iterations():
                 teacher_training=bool(teacher.training), student_training=bool(student.training),
                 teacher_abs_sum=float(sum(v.double().abs().sum() for v in tsd.values() if v.dtype == torch.float32)),
                 student_abs_sum=float(sum(v.double().abs().sum() for v in ssd.values() if v.dtype == torch.float32)),
-                student_conv1_sum=float(ssd['conv1.weight' if mode == 'aug' else 'deeplab.backbone.conv1.weight'].double().sum())))
+                student_conv1_sum=float(ssd['deeplab.backbone.conv1.weight' if mode == 'vat' else 'conv1.weight'].double().sum())))
+            if mode == 'ict':
+                rec['steps'][-1]['factors'] = [float(v) for v in ns['ict_mix_factors'].reshape(-1)]
         out['runs'][mode] = rec
     json.dump(out, open(os.path.join(OUT, 'sibling_iterations.json'), 'w'), indent=1)
 

@@ -257,7 +257,7 @@ def test_vat_kernel_algorithms_match_torch():
         assert float(lhs) == pytest.approx(float(rhs), rel=1e-6)
 
 
-@pytest.mark.parametrize('mode', ['aug', 'vat'])
+@pytest.mark.parametrize('mode', ['aug', 'vat', 'ict'])
 def test_sibling_iterations_match_reference_loops(mode):
     """Two iterations of the oracle's augmentation-consistency / VAT loop == the reference's classes driven by the reference
     scripts' own unsupervised-branch lines (oracle/gen_golden.py::gen_sibling_iterations): losses, confidence rate, post-step
@@ -268,12 +268,12 @@ def test_sibling_iterations_match_reference_loops(mode):
     gold = json.load(open(os.path.join(G, 'sibling_iterations.json')))['runs'][mode]
     n, h, w, c = gold['n'], gold['h'], gold['w'], gold['classes']
     net, sd = _synth(gold['kind'], c, seed=gold['seed'], gain=gold['gain'])
-    arch = 'deeplab2' if mode == 'aug' else 'deeplab3plus'
+    arch = 'deeplab3plus' if mode == 'vat' else 'deeplab2'
     tr = ref_step.OracleMeanTeacher(arch, sd, gold['lr'], cons_loss_fn=gold['cons_loss_fn'], cons_weight=gold['cons_weight'],
                                     conf_thresh=gold['conf_thresh'], conf_per_pixel=gold['conf_per_pixel'],
                                     vat_radius=gold['vat_radius'], adaptive_vat_radius=gold['adaptive_vat_radius'])
     tr.start_epoch()
-    conv1 = 'conv1.weight' if mode == 'aug' else 'deeplab.backbone.conv1.weight'
+    conv1 = 'deeplab.backbone.conv1.weight' if mode == 'vat' else 'conv1.weight'
     for it, exp in enumerate(gold['steps']):
         g = torch.Generator().manual_seed(300 + it)
         sup_x = torch.randn((n, 3, h, w), generator=g)
@@ -283,6 +283,11 @@ def test_sibling_iterations_match_reference_loops(mode):
         if mode == 'aug':
             theta = affine_thetas()[it:it + 2] if it == 0 else affine_thetas()[[2, 0]]
             uns = dict(ux0=ux0, ux1=ux1, um0=um0, um1=um1, xf0_to_1=theta)
+        elif mode == 'ict':
+            np.random.seed(700 + it)
+            f = torch.tensor(np.random.beta(0.4, 0.4, size=(n, 1, 1, 1)), dtype=torch.float)       # ict :306-307
+            assert [float(v) for v in f.reshape(-1)] == exp['factors']
+            uns = dict(ux0_tea=ux0, ux0_stu=ux0, ux1_tea=ux1, ux1_stu=ux1, um0=um0, um1=um1, ict_mix_factors=f)
         else:
             uns = dict(ux_tea=ux0, ux_stu=ux1, um=um0, vat=torch.ones(1), noise=vat_noise(500 + it, ux0.shape))
         s, cl, cr = tr.step(sup_x, sup_y, uns)
