@@ -1,4 +1,5 @@
-"""Drop-in for the reference's architectures/deeplab3plus.py: DeepLab v3+ (ResNet-101, output stride 8).
+"""Drop-in for the reference's architectures/deeplab3plus.py: DeepLab v3+ (ResNet-101, output stride 8), and the DeepLab v3
+model of torchvision that the reference wraps with the same `DeepLabv3Wrapper` (network_architectures.py:75-98).
 
 The reference composes torchvision's ResNet-101 (`replace_stride_with_dilation=[False, True, True]`),
 `IntermediateLayerGetter`, torchvision's `ASPP` and its own `DeepLabHeadV3Plus`
@@ -161,6 +162,34 @@ class DeepLabHeadV3Plus(nn.Module):
         return E.conv_bn_act(tape, t, c[6], ld_out=(c[6].out_channels + 3) // 4 * 4)
 
 
+class DeepLabHead(nn.Sequential):
+    """torchvision.models.segmentation.deeplabv3.DeepLabHead (the DeepLab v3 head the reference wraps for its
+    `resnet101_deeplabv3_*` architectures, network_architectures.py:75-98): ASPP -> 3x3 conv -> BN -> ReLU -> 1x1 conv.
+    A Sequential like torchvision's, so the state_dict keys are `classifier.0.convs...`, `classifier.1.weight`, ..."""
+
+    def __init__(self, in_channels, num_classes, aspp_dilate=(12, 24, 36)):
+        super(DeepLabHead, self).__init__(
+            ASPP(in_channels, aspp_dilate),
+            B2Conv2d(256, 256, 3, padding=1), B2BatchNorm2d(256), B2Marker('relu'),
+            B2Conv2d(256, num_classes, 1, bias=True))
+
+    def graph(self, tape, feature):
+        a = self[0].graph(tape, feature['out'])
+        t = E.conv_bn_act(tape, a, self[1], self[2], relu=True)
+        return E.conv_bn_act(tape, t, self[4], ld_out=(self[4].out_channels + 3) // 4 * 4)
+
+
+class DeepLabV3(nn.Module):
+    """torchvision.models.segmentation.DeepLabV3 without auxiliary classifier (`deeplabv3_resnet101(pretrained=False,
+    num_classes=...)`: aux_loss is off unless the COCO weights are requested)."""
+
+    def __init__(self, backbone, classifier):
+        super(DeepLabV3, self).__init__()
+        self.backbone = backbone
+        self.classifier = classifier
+        self.aux_classifier = None
+
+
 class DeepLabV3Plus(nn.Module):
     def __init__(self, backbone, classifier):
         super(DeepLabV3Plus, self).__init__()
@@ -193,10 +222,14 @@ class DeepLabv3Wrapper(B2SegNet):
 
     def _graph_trunk(self, tape, x, in_h, in_w):
         feats = self.deeplab.backbone.graph(tape, x)
+        if isinstance(self.deeplab.classifier, DeepLabHead):     # DeepLab v3: the head reads layer4 only
+            return [(feats['out'], True)]
         # layer1's output also feeds layer2; layer4's output is consumed by the head only
         return [(feats['low_level'], False), (feats['out'], True)]
 
     def _graph_head(self, tape, feats, in_h, in_w):
+        if isinstance(self.deeplab.classifier, DeepLabHead):
+            return self.deeplab.classifier.graph(tape, {'out': feats[0]}), False
         return self.deeplab.classifier.graph(tape, {'low_level': feats[0], 'out': feats[1]}), False
 
     def _trunk_module(self):
@@ -212,7 +245,12 @@ class DeepLabv3Wrapper(B2SegNet):
         return list(self.deeplab.backbone.parameters())
 
     def _classifier_end_parameters(self):
-        return list(self.deeplab.classifier.classifier[-1].parameters())
+        if isinstance(self.deeplab.classifier, DeepLabHead):
+            return list(self.deeplab.classifier[-1].parameters())
+        if isinstance(self.deeplab.classifier, DeepLabHeadV3Plus):
+            return list(self.deeplab.classifier.classifier[-1].parameters())
+        raise TypeError('Oh dear, seem to have encountered unknown classifier head type {}'.format(
+            type(self.deeplab.classifier)))
 
     def pretrained_parameters(self):
         if self.pretraining is None:
@@ -237,4 +275,32 @@ class DeepLabv3Wrapper(B2SegNet):
 
 def resnet101_deeplabv3plus_imagenet(num_classes, pretrained=True):
     deeplab = _deeplabv3plus('resnet101', num_classes, 8, pretrained)
+    return DeepLabv3Wrapper(deeplab)
+
+
+_DEEPLABV3_COCO_URL = 'https://download.pytorch.org/models/deeplabv3_resnet101_coco-586e9e4e.pth'
+
+
+def _deeplabv3(num_classes):
+    """torchvision's `deeplabv3_resnet101(pretrained=False, num_classes=num_classes)`: ResNet-101 with the strides of layer3 /
+    layer4 replaced by dilation (output stride 8), DeepLabHead, no auxiliary classifier."""
+    backbone = ResNetBackbone([3, 4, 23, 3], [False, True, True])
+    return DeepLabV3(backbone, DeepLabHead(2048, num_classes))
+
+
+def resnet101_deeplabv3_coco(num_classes=21, pretrained=True):
+    """Reference network_architectures.py:75-84 (the wrapper is built WITHOUT a `pretraining` tag there, so every parameter
+    is a "new" parameter: kept)."""
+    deeplab = _deeplabv3(num_classes)
+    if pretrained:
+        deeplab2._load_state_into_model(deeplab, deeplab2.load_pretrained_state(_DEEPLABV3_COCO_URL))
+    return DeepLabv3Wrapper(deeplab)
+
+
+def resnet101_deeplabv3_imagenet(num_classes=21, pretrained=True):
+    """Reference network_architectures.py:87-98: the DeepLab v2 ImageNet ResNet-101 weights under a `backbone.` prefix."""
+    deeplab = _deeplabv3(num_classes)
+    if pretrained:
+        state = deeplab2.load_pretrained_state(deeplab2._RESNET_101_IMAGENET_URL)
+        deeplab2._load_state_into_model(deeplab, {'backbone.{}'.format(k): v for k, v in state.items()})
     return DeepLabv3Wrapper(deeplab)

@@ -2,8 +2,8 @@
 (`seg.get(name)(num_classes, pretrained=...)`), plus `robust_binary_crossentropy` and
 `sigmoid_rampup` (network_architectures.py:15-130).
 
-Only the two architectures on the B200 hot path are built natively (DeepLab v2 and DeepLab v3+ on
-ResNet-101).  The other names of the reference registry stay registered so that `seg.names()` matches,
+The architectures on the B200 hot path are built natively (DeepLab v2 and DeepLab v3+ on ResNet-101), and so is
+torchvision's DeepLab v3, which shares every layer type with them.  The other names of the reference registry stay registered so that `seg.names()` matches,
 but constructing them raises NotImplementedError (they are outside BASELINE.json's north_star).
 """
 import sys
@@ -38,14 +38,14 @@ seg = ArchRegistry()
 
 def _not_built(name):
     def ctor(*args, **kwargs):
-        raise NotImplementedError('architecture {!r} is not part of the B200 hot path (only resnet101_deeplab_* and '
-                                  'resnet101_deeplabv3plus_imagenet are built natively)'.format(name))
+        raise NotImplementedError('architecture {!r} is not part of the B200 hot path (only the resnet101_deeplab* '
+                                  'architectures are built natively)'.format(name))
     ctor.__name__ = name
     return ctor
 
 
 for _name in ('resnet50unet_imagenet', 'resnet101unet_imagenet', 'densenet161unet', 'densenet161unet_imagenet',
-              'resnet101_deeplabv3_coco', 'resnet101_deeplabv3_imagenet', 'resnet101_pspnet_imagenet'):
+              'resnet101_pspnet_imagenet'):
     seg.register(_name)(_not_built(_name))
 
 
@@ -62,6 +62,16 @@ def resnet101_deeplab_imagenet(num_classes=21, pretrained=True):
 @seg.register('resnet101_deeplab_imagenet_mittal_std')
 def resnet101_deeplab_imagenet_mittal_std(num_classes=21, pretrained=True):
     return deeplab2.resnet101_deeplab_imagenet_mittal_std(num_classes=num_classes, pretrained=pretrained)
+
+
+@seg.register('resnet101_deeplabv3_coco')
+def resnet101_deeplabv3_coco(num_classes=21, pretrained=True):
+    return deeplab3plus.resnet101_deeplabv3_coco(num_classes=num_classes, pretrained=pretrained)
+
+
+@seg.register('resnet101_deeplabv3_imagenet')
+def resnet101_deeplabv3_imagenet(num_classes=21, pretrained=True):
+    return deeplab3plus.resnet101_deeplabv3_imagenet(num_classes=num_classes, pretrained=pretrained)
 
 
 @seg.register('resnet101_deeplabv3plus_imagenet')

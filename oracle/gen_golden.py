@@ -79,17 +79,36 @@ def gen_masks():
 
 
 def build(kind, classes, seed, gain=1.0):
-    net = network_architectures.seg.get(kind)(classes, pretrained=False)
-    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    if kind == 'resnet101_deeplabv3_imagenet':
+        net = reference_deeplabv3(classes)
+    else:
+        net = network_architectures.seg.get(kind)(classes, pretrained=False)
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'deeplab.classifier.4' in k)
+             and k.endswith('weight')]
     sd = TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
     net.load_state_dict(sd)
     return net
 
 
+def reference_deeplabv3(classes):
+    """The reference's `resnet101_deeplabv3_imagenet(num_classes, pretrained=False)` (network_architectures.py:87-98) =
+    torchvision's deeplabv3_resnet101 inside the reference's DeepLabv3Wrapper.  The factory itself cannot run offline: every
+    torchvision release downloads ImageNet backbone weights unless told otherwise, so the two constructor calls are made
+    here with the backbone download switched off."""
+    from torchvision.models.segmentation import deeplabv3_resnet101
+    from architectures import deeplab3plus as ref_dl3
+    deeplab = deeplabv3_resnet101(weights=None, weights_backbone=None, num_classes=classes)
+    return ref_dl3.DeepLabv3Wrapper(deeplab)
+
+
 def gen_state_dicts():
     out = {}
-    for kind, classes in (('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19)):
-        net = network_architectures.seg.get(kind)(classes, pretrained=False)
+    for kind, classes in (('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19),
+                          ('resnet101_deeplabv3_imagenet', 21)):
+        if kind == 'resnet101_deeplabv3_imagenet':
+            net = reference_deeplabv3(classes)
+        else:
+            net = network_architectures.seg.get(kind)(classes, pretrained=False)
         out[kind] = dict(classes=classes,
                          entries=[[k, list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in net.state_dict().items()],
                          n_pretrained=len(list(net.pretrained_parameters())),
@@ -102,7 +121,8 @@ def gen_state_dicts():
 
 def gen_nets():
     for tag, kind, classes, (n, h, w) in (('dl2', 'resnet101_deeplab_imagenet', 21, (2, 33, 41)),
-                                         ('dl3', 'resnet101_deeplabv3plus_imagenet', 19, (3, 33, 41))):
+                                         ('dl3', 'resnet101_deeplabv3plus_imagenet', 19, (3, 33, 41)),
+                                         ('dl3v3', 'resnet101_deeplabv3_imagenet', 21, (2, 33, 41))):
         net = build(kind, classes, seed=1)
         net.train()
         net.freeze_batchnorm()
@@ -118,7 +138,7 @@ def gen_nets():
         for k, p in net.named_parameters():
             if p.grad is not None:
                 names.append(k); gsum.append(float(p.grad.double().sum())); gabs.append(float(p.grad.double().abs().sum()))
-        running = {k: v.numpy() for k, v in net.state_dict().items() if 'classifier.project.1.running' in k}
+        running = {k: v.numpy() for k, v in net.state_dict().items() if 'classifier.project.1.running' in k or 'classifier.2.running' in k}
         np.savez_compressed(os.path.join(OUT, 'net_%s.npz' % tag), x=x.numpy(), dy=dy.numpy(), logits=y.detach().numpy(),
                             grad_names=np.array(names), grad_sum=np.array(gsum), grad_abs=np.array(gabs), **running)
 

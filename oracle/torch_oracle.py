@@ -76,8 +76,14 @@ _DL3_LAYERS = (('layer1', 64, 3, 1, 1, 1), ('layer2', 128, 4, 2, 1, 1), ('layer3
                ('layer4', 512, 3, 1, 2, 4))
 
 
+def deeplab3_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dropout_masks=None, pre='deeplab.'):
+    """DeepLabv3Wrapper.forward on torchvision's DeepLab v3 (`deeplabv3_resnet101`, reference network_architectures.py:75-98):
+    the same backbone and ASPP as DeepLab v3+, then DeepLabHead's 3x3 conv -> BN -> ReLU -> 1x1 conv and one bilinear resize."""
+    return deeplab3plus_forward(sd, x, backbone_bn_train, head_bn_train, dropout_masks, pre, head='v3')
+
+
 def deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dropout_masks=None, pre='deeplab.',
-                         aspp_rates=(12, 24, 36)):
+                         aspp_rates=(12, 24, 36), head='v3plus'):
     """DeepLabv3Wrapper.forward -> DeepLabV3Plus.forward -> DeepLabHeadV3Plus.forward
     (deeplab3plus.py:116-117, 73-78, 51-56) with torchvision's ASPP.  `dropout_masks`: list with one
     (N,256,h,w) keep-mask for the ASPP Dropout(0.5) (None = dropout inactive)."""
@@ -113,20 +119,26 @@ def deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dr
         y = F.conv2d(x_, sd[cp + '.weight'], **kw)
         y = F.relu(_bn(sd, bp, y, tr)); _count_bn(sd, bp, tr)
         return y
-    low = cbr(feats['layer1'], hd + 'project.0', hd + 'project.1')
+    ap = hd + ('aspp.' if head == 'v3plus' else '0.')          # DeepLabHeadV3Plus.aspp / DeepLabHead[0]
+    if head == 'v3plus':
+        low = cbr(feats['layer1'], hd + 'project.0', hd + 'project.1')
     f = feats['layer4']
-    branches = [cbr(f, hd + 'aspp.convs.0.0', hd + 'aspp.convs.0.1')]
+    branches = [cbr(f, ap + 'convs.0.0', ap + 'convs.0.1')]
     n_branches = 1 + len(aspp_rates)
     for i in range(1, n_branches):
         rate = aspp_rates[i - 1]
-        branches.append(cbr(f, hd + 'aspp.convs.{}.0'.format(i), hd + 'aspp.convs.{}.1'.format(i), padding=rate, dilation=rate))
+        branches.append(cbr(f, ap + 'convs.{}.0'.format(i), ap + 'convs.{}.1'.format(i), padding=rate, dilation=rate))
     pi = n_branches
     pooled = F.adaptive_avg_pool2d(f, 1)
-    pooled = cbr(pooled, hd + 'aspp.convs.{}.1'.format(pi), hd + 'aspp.convs.{}.2'.format(pi))
+    pooled = cbr(pooled, ap + 'convs.{}.1'.format(pi), ap + 'convs.{}.2'.format(pi))
     branches.append(F.interpolate(pooled, size=f.shape[2:4], mode='bilinear', align_corners=False))
-    a = cbr(torch.cat(branches, dim=1), hd + 'aspp.project.0', hd + 'aspp.project.1')
+    a = cbr(torch.cat(branches, dim=1), ap + 'project.0', ap + 'project.1')
     if dropout_masks is not None:
         a = a * dropout_masks[0] * 2.0            # nn.Dropout(0.5) in training mode
+    if head == 'v3':                              # torchvision DeepLabHead[1:] + DeepLabV3.forward's resize
+        c = cbr(a, hd + '1', hd + '2', padding=1)
+        c = F.conv2d(c, sd[hd + '4.weight'], sd[hd + '4.bias'])
+        return F.interpolate(c, size=in_hw, mode='bilinear', align_corners=False)
     a = F.interpolate(a, size=low.shape[2:4], mode='bilinear', align_corners=False)
     c = torch.cat([low, a], dim=1)
     c = cbr(c, hd + 'classifier.0', hd + 'classifier.1', padding=1)

@@ -51,7 +51,10 @@ def _run(kind, n, h, w, classes, freeze, seed):
     for k, p in net.named_parameters():
         if p.requires_grad:
             sd64[k].requires_grad_(True)
-    if 'v3plus' in kind:
+    if 'deeplabv3_' in kind:
+        yo = TO.deeplab3_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
+                                 dropout_masks=[dm.permute(0, 3, 1, 2).double()])
+    elif 'v3plus' in kind:
         yo = TO.deeplab3plus_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
                                      dropout_masks=[dm.permute(0, 3, 1, 2).double()])
     else:
@@ -97,6 +100,19 @@ def test_deeplab3plus_frozen_backbone_train_head(emu):
     fused, plain = emu.calls.count('bn_eval_param_grad_wdot+stats'), emu.calls.count('bn_eval_param_grad_wdot')
     assert fused == emu.calls.count('conv_dgrad+stats') and fused + plain == 104 and fused >= 90, (fused, plain)
     assert emu.calls.count('bn_eval_param_grad_from_stats') == 0 and emu.calls.count('bn_eval_param_grad') == 0
+
+
+def test_deeplab3_frozen_backbone_train_head(emu):
+    """torchvision's DeepLab v3 in the reference's wrapper (`resnet101_deeplabv3_imagenet`): same backbone and ASPP as v3+,
+    DeepLabHead, one x8 resize."""
+    lerr, errs, stat, net = _run('resnet101_deeplabv3_imagenet', 3, 33, 41, 21, True, seed=2)
+    assert lerr < 1e-4
+    assert len(errs) == 335                               # 104 backbone convs + their 2 x 104 BN affines, 23 head tensors
+    assert errs[len(errs) // 2] < 1e-3 and errs[-1] < 5e-2
+    assert stat < 1e-4
+    nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
+    assert nb['deeplab.classifier.2.num_batches_tracked'] == 1 and nb['deeplab.classifier.0.project.1.num_batches_tracked'] == 1
+    assert nb['deeplab.backbone.bn1.num_batches_tracked'] == 0
 
 
 def test_gradient_accumulation_over_two_backward_passes(emu):
