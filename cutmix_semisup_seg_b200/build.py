@@ -23,19 +23,27 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _deps_mtime():
-    m = 0.0
+def _fingerprint(src):
+    """sha256 over the source file, every header it can include and the compiler command: an object is reused only if this
+    matches the stamp written next to it (modification times do not survive checkouts / container snapshots reliably)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(' '.join([NVCC] + ARCH_FLAGS + CFLAGS).encode())
+    paths = [os.path.join(CSRC, src)]
     for root in (CSRC, os.path.join(REPO, 'include')):
-        for f in os.listdir(root):
-            if f.endswith(('.cuh', '.h')):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
-    return m
+        paths += sorted(os.path.join(root, f) for f in os.listdir(root) if f.endswith(('.cuh', '.h')))
+    for path in paths:
+        h.update(os.path.basename(path).encode())
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def _compile_one(src, verbose):
     obj = os.path.join(OBJ_DIR, src[:-3] + '.o')
     spath = os.path.join(CSRC, src)
-    if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(spath), _deps_mtime()):
+    stamp, fp = obj + '.sha256', _fingerprint(src)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
         return obj, ''
     cmd = [NVCC] + ARCH_FLAGS + CFLAGS + ['-c', spath, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -45,6 +53,8 @@ def _compile_one(src, verbose):
         sys.stderr.write(r.stderr)
     with open(obj + '.ptxas.log', 'w') as f:
         f.write(r.stderr)
+    with open(stamp, 'w') as f:
+        f.write(fp)
     return obj, r.stderr
 
 
@@ -59,12 +69,16 @@ def build_lib(force=False, verbose=False):
                 os.remove(o)
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = [o for o, _ in ex.map(lambda s: _compile_one(s, verbose), srcs)]
-    newest = max(os.path.getmtime(o) for o in objs)
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+    # the library is re-linked whenever the set of object fingerprints differs from the one it was linked from
+    link_fp = '\n'.join(open(o + '.sha256').read().strip() for o in objs)
+    link_stamp = LIB_PATH + '.sha256'
+    if force or not os.path.exists(LIB_PATH) or not os.path.exists(link_stamp) or open(link_stamp).read() != link_fp:
         cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-o', LIB_PATH] + objs + ['-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n{}\n{}'.format(r.stdout, r.stderr))
+        with open(link_stamp, 'w') as f:
+            f.write(link_fp)
     return LIB_PATH
 
 
