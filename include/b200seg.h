@@ -177,6 +177,18 @@ int b2_add_scaled_per_sample(const float* x, const float* e, const float* mag, c
                              float* out, int n, int64_t per, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data-format boundary -- datapipe/seg_transforms_cv.py:587-672 (SegCVTransformNormalizeToTensor)
+ *   The last DataLoader stage moved behind the host-to-device copy: batches cross PCIe as uint8.
+ *   b2_normalize_to_tensor: img DEVICE uint8 (N,H,W,cin), cin = 3, or 4 with the padding alpha channel ->
+ *     out DEVICE fp32 (N,3,H,W) = float32((img * (1/255) - mean [* alpha]) / std), float64 arithmetic like numpy (:596-614).
+ *     mean3 / std3: HOST pointers to 3 doubles each (net.MEAN / net.STD), both NULL = no standardisation (:609).
+ *   b2_u8_to_tensor: mode 0 labels uint8 -> int64 (:617), mode 1 valid mask uint8 -> float32(m * (1/255)) (:620).
+ * ------------------------------------------------------------------------------------------ */
+int b2_normalize_to_tensor(const uint8_t* img, int n, int h, int w, int cin, const double* mean3, const double* std3,
+                           float* out, void* stream);
+int b2_u8_to_tensor(const uint8_t* src, int64_t count, int mode, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459
  *   Inputs (NCHW fp32): l0, l1 teacher logits of the two views (l1 == NULL → cut mode, l_t = l0),
  *   ls student logits, m mix mask (N,1,H,W) (NULL → no logit mixing), lmask per-pixel loss mask

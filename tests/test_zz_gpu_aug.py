@@ -3,11 +3,12 @@ kernels: the affine grid-sample kernel against F.affine_grid + F.grid_sample, th
 against the golden vectors produced by the reference's own source lines (tests/golden/aug_block.json) and against the oracle
 on the data sets' class counts, full iterations against the oracle's CPU iterations, and the drop-in entry point.
 
-STATUS: these kernels were written after the round's GPU budget was spent: they compile for sm_100a and their algorithm is
-pinned on the CPU (tests/_emu_backend.py vs the same golden vectors, tests/test_oracle_golden.py), but this file has not yet
-run on a B200.  Until it has, every test here is a NON-STRICT expected failure (a pass is reported as XPASS, a mismatch as
-XFAIL) and the file sorts after every other GPU test, so it cannot hide or disturb a result of the verified path.  Set
-B200SEG_AUG_VERIFIED=1 (or delete the marker once a run is recorded under profiles/) to make the tests binding."""
+STATUS (profiles/r01_v15_aug_vat_kernel_probes.txt): the kernel-level tests of this file -- the grid-sample kernel, the fused
+kernel against the reference-lines golden (12 cases) and against the oracle on C = 19 / 21 / 2 / 7 for all five loss functions
+(20 cases), the ABI error paths -- ran and passed on a B200 with the last GPU seconds of round 1 and are binding.  The
+iteration-level and entry-point tests could not be run any more: they stay NON-STRICT expected failures (`pending`; a pass is
+reported as XPASS) until a run is recorded, and the file sorts after the fully verified GPU tests.  B200SEG_AUG_VERIFIED=1
+makes every test binding."""
 import json
 import math
 import os
@@ -30,8 +31,11 @@ from aug_recipe import aug_inputs, parse_case  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
 if os.environ.get('B200SEG_AUG_VERIFIED', '0') != '1':
-    pytestmark.append(pytest.mark.xfail(strict=False, reason='first B200 run of the aug-consistency kernels is pending '
-                                                              '(GPU budget of the round was spent); see module docstring'))
+    pending = pytest.mark.xfail(strict=False, reason='first B200 run of the aug-consistency ITERATION is pending (the kernels '
+                                                     'are verified; GPU budget of the round was spent); see module docstring')
+else:
+    def pending(f):
+        return f
 dev = torch.device('cuda:0')
 GOLD = json.load(open(os.path.join(HERE, 'golden', 'aug_block.json')))
 
@@ -126,6 +130,7 @@ def test_aug_kernel_rejects_bad_arguments():
                t.clone().data_ptr(), part.data_ptr(), 1, 2, 4, 4, 0, 0.5, 0, None)
 
 
+@pending
 @pytest.mark.parametrize('batch_trunk,conf_per_pixel', [(True, False), (False, True)])
 def test_aug_iterations_match_oracle(batch_trunk, conf_per_pixel):
     """Three full augmentation-consistency iterations (DeepLab v2, frozen BN, Adam with the duplicated group, EMA) vs the
@@ -167,6 +172,7 @@ def test_aug_iterations_match_oracle(batch_trunk, conf_per_pixel):
         assert worst < 1.5e-3, (name, worst)
 
 
+@pending
 def test_aug_logits_var_fails_like_the_reference():
     from cutmix_semisup_seg_b200 import step as step_mod, synthetic
     n, h, w, c = 1, 33, 33, 21
@@ -193,6 +199,7 @@ BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size
         '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']
 
 
+@pending
 @pytest.mark.parametrize('name', sorted(AUG_CASES))
 def test_aug_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
     """train_seg_semisup_aug_mt.py through its click command."""
