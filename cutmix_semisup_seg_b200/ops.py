@@ -208,6 +208,47 @@ class CudaBackend(object):
                    int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
         return out4, dls
 
+    # ------------------------------------------------------------------ data-format boundary (seg_transforms_cv.py:587-672)
+    def normalize_to_tensor(self, img_u8, mean=None, std=None, out=None):
+        """uint8 (N,H,W,3|4) pixels -> standardised fp32 (N,3,H,W) planes, bit-identical to the reference's numpy pipeline
+        (img_as_float, (v - mean [* alpha]) / std in float64, .astype(float32)).  mean / std: sequences of 3 floats or None."""
+        L.require_cuda(img_u8)
+        assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4
+        img_u8 = img_u8.contiguous()
+        n, h, w, cin = img_u8.shape
+        if cin not in (3, 4):
+            raise ValueError('image should have 3 channels, not {}'.format(cin))        # seg_transforms_cv.py:654
+        if (mean is None) != (std is None):
+            raise ValueError('mean and std must be given together')
+        if out is None:
+            out = torch.empty((n, 3, h, w), device=img_u8.device, dtype=torch.float32)
+        m = s_ = None
+        if mean is not None:
+            m = (ctypes.c_double * 3)(*[float(v) for v in mean])
+            s_ = (ctypes.c_double * 3)(*[float(v) for v in std])
+        self._call('b2_normalize_to_tensor', img_u8.data_ptr(), n, h, w, cin, m, s_, out.data_ptr(), self._s())
+        return out
+
+    def labels_to_tensor(self, labels_u8):
+        """uint8 (N,H,W) class indices (255 = ignore) -> int64 (N,1,H,W) (seg_transforms_cv.py:617)."""
+        L.require_cuda(labels_u8)
+        assert labels_u8.dtype == torch.uint8 and labels_u8.dim() == 3
+        labels_u8 = labels_u8.contiguous()
+        n, h, w = labels_u8.shape
+        out = torch.empty((n, 1, h, w), device=labels_u8.device, dtype=torch.int64)
+        self._call('b2_u8_to_tensor', labels_u8.data_ptr(), labels_u8.numel(), 0, out.data_ptr(), self._s())
+        return out
+
+    def mask_to_tensor(self, mask_u8):
+        """uint8 (N,H,W) valid mask (0..255) -> fp32 (N,1,H,W) = float32(m * (1/255)) (seg_transforms_cv.py:620)."""
+        L.require_cuda(mask_u8)
+        assert mask_u8.dtype == torch.uint8 and mask_u8.dim() == 3
+        mask_u8 = mask_u8.contiguous()
+        n, h, w = mask_u8.shape
+        out = torch.empty((n, 1, h, w), device=mask_u8.device, dtype=torch.float32)
+        self._call('b2_u8_to_tensor', mask_u8.data_ptr(), mask_u8.numel(), 1, out.data_ptr(), self._s())
+        return out
+
     # ------------------------------------------------------------------ VAT (train_seg_semisup_vat_mt.py:214-301)
     def sample_l2norm(self, x):
         """mag[i] = sqrt(sum of squares of sample i) (normalize_eps, :217-219).  x: (N, ...) fp32 contiguous."""

@@ -222,6 +222,27 @@ class EmuBackend(object):
         return d if x is None else x + d
 
 
+    # ------------------------------------------------------------------ data-format boundary (csrc/input.cu)
+    def normalize_to_tensor(self, img_u8, mean=None, std=None, out=None):
+        self.launches += 1
+        img = img_u8.numpy().astype(np.float64) * (1.0 / 255.0)
+        if img.shape[3] == 4:
+            alpha, img = img[..., 3:4], img[..., :3]
+            if mean is not None:
+                img = (img - np.asarray(mean, dtype=np.float64)[None, None, None, :] * alpha) / np.asarray(std, dtype=np.float64)
+        elif mean is not None:
+            img = (img - np.asarray(mean, dtype=np.float64)) / np.asarray(std, dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2)).astype(np.float32))
+
+    def labels_to_tensor(self, labels_u8):
+        self.launches += 1
+        return labels_u8[:, None].to(torch.int64)
+
+    def mask_to_tensor(self, mask_u8):
+        self.launches += 1
+        return torch.from_numpy((mask_u8.numpy().astype(np.float64) * (1.0 / 255.0))[:, None].astype(np.float32))
+
+
 class EmuEMA(object):
     """Stand-in for optim_weight_ema.EMAWeightOptimizer.step() on CPU modules (optim_weight_ema.py:21-25 arithmetic); the
     product class refuses CPU tensors by design."""

@@ -1,0 +1,83 @@
+"""CPU: the data-format boundary.  The reference's SegCVTransformNormalizeToTensor
+(datapipe/seg_transforms_cv.py:587-672) cannot be imported here (it needs scikit-image, pinned 0.16.2 in environment.yml),
+so its arithmetic is restated below line by line with numpy -- img_as_float for uint8 is `np.multiply(image, 1. / 255,
+dtype=float64)` (skimage/util/dtype.py, `convert`) -- and the kernels' algorithm (tests/_emu_backend.py states it a second
+time) must agree with it bit for bit; the `-m gpu` half runs the same comparison on the CUDA kernels.  parity unpinned for
+the scikit-image call (the package is absent); everything else follows the reference's own lines."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(__file__)
+sys.path.insert(0, HERE)
+MEAN = np.array([0.485, 0.456, 0.406])          # the networks' MEAN / STD (deeplab2.py, deeplab3plus.py)
+STD = np.array([0.229, 0.224, 0.225])
+
+
+def img_as_float(a):
+    return np.multiply(a, 1. / 255, dtype=np.float64)
+
+
+def reference_transform_single(sample, mean, std):
+    """seg_transforms_cv.py:592-623, verbatim arithmetic."""
+    sample = sample.copy()
+    image = img_as_float(sample['image_arr'])                                                   # :596
+    if image.shape[2] == 4:
+        alpha_channel = image[:, :, 3:4]                                                        # :601
+        image = image[:, :, :3]
+        if mean is not None and std is not None:
+            image = (image - (mean[None, None, :] * alpha_channel)) / std[None, None, :]        # :606
+    else:
+        if mean is not None and std is not None:
+            image = (image - mean[None, None, :]) / std[None, None, :]                          # :610
+    assert image.shape[2] == 3
+    sample['image'] = image.transpose(2, 0, 1).astype(np.float32)                               # :614
+    del sample['image_arr']
+    if 'labels_arr' in sample:
+        sample['labels'] = sample['labels_arr'][None, ...].astype(np.int64)                     # :617
+        del sample['labels_arr']
+    if 'mask_arr' in sample:
+        sample['mask'] = img_as_float(sample['mask_arr'])[None, ...].astype(np.float32)         # :620
+        del sample['mask_arr']
+    return sample
+
+
+def make_batch(n, h, w, cin, seed):
+    rs = np.random.RandomState(seed)
+    img = rs.randint(0, 256, size=(n, h, w, cin)).astype(np.uint8)
+    edge = np.array([[0] * cin, [255] * cin, [1] * cin, [254] * cin], dtype=np.uint8)
+    img.reshape(-1, cin)[:min(4, n * h * w)] = edge[:min(4, n * h * w)]
+    lab = rs.randint(0, 21, size=(n, h, w)).astype(np.uint8); lab[:, :2] = 255
+    mask = (rs.rand(n, h, w) > 0.2).astype(np.uint8) * 255; mask[:, :, 0] = 128
+    return img, lab, mask
+
+
+def check_backend(be, to_dev=lambda t: t):
+    for cin, h, w, norm in ((3, 9, 13, True), (4, 6, 5, True), (3, 33, 47, False), (3, 1, 1, True)):
+        img, lab, mask = make_batch(3, h, w, cin, seed=h * w + cin)
+        mean, std = (MEAN, STD) if norm else (None, None)
+        want = [reference_transform_single(dict(image_arr=img[i], labels_arr=lab[i], mask_arr=mask[i]), mean, std)
+                for i in range(len(img))]
+        got_img = be.normalize_to_tensor(to_dev(torch.from_numpy(img)), mean, std).cpu().numpy()
+        got_lab = be.labels_to_tensor(to_dev(torch.from_numpy(lab))).cpu().numpy()
+        got_mask = be.mask_to_tensor(to_dev(torch.from_numpy(mask))).cpu().numpy()
+        assert got_img.dtype == np.float32 and got_lab.dtype == np.int64 and got_mask.dtype == np.float32
+        assert np.array_equal(got_img, np.stack([s['image'] for s in want]))                   # bit-exact
+        assert np.array_equal(got_lab, np.stack([s['labels'] for s in want]))
+        assert np.array_equal(got_mask, np.stack([s['mask'] for s in want]))
+
+
+def test_kernel_algorithm_is_bit_exact_with_the_reference_arithmetic():
+    from _emu_backend import EmuBackend
+    check_backend(EmuBackend())
+
+
+def test_wrong_channel_count_is_rejected_like_the_reference():
+    from cutmix_semisup_seg_b200 import lib as L
+    with pytest.raises(L.B2Error, match='should have 3 channels'):                       # seg_transforms_cv.py:653-656
+        L.call('b2_normalize_to_tensor', 0x1000, 1, 4, 4, 2, None, None, 0x1000, None)
+    with pytest.raises(L.B2Error, match='together'):
+        L.call('b2_normalize_to_tensor', 0x1000, 1, 4, 4, 3, (L.ctypes.c_double * 3)(0, 0, 0), None, 0x1000, None)

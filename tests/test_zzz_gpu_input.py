@@ -1,0 +1,29 @@
+"""-m gpu: csrc/input.cu (device-side SegCVTransformNormalizeToTensor) bit-exact against the reference's
+numpy arithmetic restated in tests/test_input_pipeline.py.  Written after the GPU budget of round 1 was spent: non-strict
+expected failure until its first B200 run; sorts after every other GPU test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+from test_input_pipeline import MEAN, STD, check_backend, make_batch, reference_transform_single  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='csrc/input.cu was written after the GPU budget of round 1 was spent: first B200 run pending')
+def test_cuda_kernels_are_bit_exact_with_the_reference_arithmetic():
+    from cutmix_semisup_seg_b200 import ops, input_pipeline
+    dev = torch.device('cuda:0')
+    check_backend(ops.default_backend(), to_dev=lambda t: t.to(dev))
+    img, lab, mask = make_batch(2, 17, 19, 3, seed=1)
+    tf = input_pipeline.DeviceNormalizeToTensor(MEAN, STD)
+    out = tf(dict(image_arr=torch.from_numpy(img).pin_memory(), labels_arr=torch.from_numpy(lab).to(dev),
+                  mask_arr=torch.from_numpy(mask).to(dev), index=torch.arange(2)))
+    assert set(out) == {'image', 'labels', 'mask', 'index'}
+    want = reference_transform_single(dict(image_arr=img[1], labels_arr=lab[1], mask_arr=mask[1]), MEAN, STD)
+    assert np.array_equal(out['image'][1].cpu().numpy(), want['image'])
+    assert np.array_equal(out['labels'][1].cpu().numpy(), want['labels'])
+    assert np.array_equal(out['mask'][1].cpu().numpy(), want['mask'])
