@@ -338,6 +338,61 @@ class BNTrainNode(object):
             tape.contribute_tensor(self.residual, g_out)
 
 
+class UpAddNode(object):
+    """y = nearest x2 up-sampling of x [+ skip]  (DecoderBlock.forward, resunet.py:31-32; the final `up`, :87)."""
+
+    def __init__(self, x, skip, y):
+        self.x, self.skip, self.y = x, skip, y
+
+    def backward(self, tape):
+        K = tape.K
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            if self.skip is not None:
+                tape.skip(self.skip)
+            return
+        tape.contribute_kernel(self.x, lambda dst, accumulate, addend, gate, stats: K.upsample2x_bwd(
+            dy, dst, accumulate=accumulate), False)
+        if self.skip is not None:
+            tape.contribute_tensor(self.skip, dy)           # d(skip) = dy: aliased, not copied
+
+
+class ReluNode(object):
+    """y = max(x, 0) as its own layer.  The gradient of y is gated when its last consumer has contributed (gate_on_grad, like
+    the fused ReLUs), so the node only passes it on."""
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        tape.contribute_tensor(self.x, dy)
+
+
+class MulMaskNode(object):
+    """y = x * mask * scale: nn.Dropout applied to a raw convolution output (resunet.py:88)."""
+
+    def __init__(self, x, y, mask, scale):
+        self.x, self.y, self.mask, self.scale = x, y, mask, scale
+
+    def backward(self, tape):
+        K = tape.K
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        mask, scale = self.mask, self.scale
+
+        def launch(dst, accumulate, addend, gate, stats):
+            assert not accumulate, 'the dropped tensor has a single consumer'
+            K.mul_mask(dy, mask, scale, dst)
+        tape.contribute_kernel(self.x, launch, False)
+
+
 class MaxPoolNode(object):
     def __init__(self, x, y, idx):
         self.x, self.y, self.idx = x, y, idx
@@ -535,8 +590,9 @@ def bn_train(tape, raw, bn, residual=None, relu=False, out=None, dropout=None, l
     return y
 
 
-def stem_conv(tape, x_nhwc, conv, bn):
-    """Cin=3 7x7/s2 stem: explicit im2col (K = 147 padded to 160) + the same tensor-core GEMM."""
+def stem_conv(tape, x_nhwc, conv, bn, relu=True):
+    """Cin=3 7x7/s2 stem: explicit im2col (K = 147 padded to 160) + the same tensor-core GEMM.  `relu=False`: stop after
+    the BatchNorm (the U-Net decoders tap that tensor, resunet.py:69-71; eval-mode BN only)."""
     K = tape.K
     cout, kh, kw, cin, stride, pad, dil = _geom(conv)
     oh, ow = _conv_out_hw(x_nhwc.h, x_nhwc.w, kh, stride, pad, dil)
@@ -550,9 +606,9 @@ def stem_conv(tape, x_nhwc, conv, bn):
     flat = Act(tgt.base, 1, 1, tgt.rows, cout, cout, 0)
     if not train_bn:
         scale, shift = fold_bn(tape, bn)
-        K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat, scale=scale, shift=shift, relu=True)
-        tgt.gate_on_grad = True
-        node = ConvNode(col, tgt, conv, bn, None, True, scale, (cout, kh, kw, cin, stride, pad, dil),
+        K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat, scale=scale, shift=shift, relu=bool(relu))
+        tgt.gate_on_grad = bool(relu)
+        node = ConvNode(col, tgt, conv, bn, None, bool(relu), scale, (cout, kh, kw, cin, stride, pad, dil),
                         col_src=(col, kpad))
         tgt.node = node
         if x_nhwc.needs_grad:          # VAT: the gradient w.r.t. the image is wanted (netbase.b2_forward(input_grad=True))
@@ -569,7 +625,43 @@ def stem_conv(tape, x_nhwc, conv, bn):
                      col_src=(col, kpad))
     tgt.node = cnode
     tape.record(cnode, [])
-    return bn_train(tape, tgt, bn, relu=True)
+    return bn_train(tape, tgt, bn, relu=bool(relu))
+
+
+def upsample2x_add(tape, x, skip=None):
+    """nn.Upsample(scale_factor=2) (nearest) followed by the skip addition of the U-Net decoders."""
+    if skip is not None:
+        assert (skip.n, skip.h, skip.w, skip.c) == (x.n, 2 * x.h, 2 * x.w, x.c), 'skip connection shape mismatch'
+    y = Act.alloc(x.n, 2 * x.h, 2 * x.w, x.c, x.device)
+    tape.K.upsample2x_add(x, skip, y)
+    node = UpAddNode(x, skip, y)
+    y.node = node
+    tape.record(node, [x] + ([skip] if skip is not None else []))
+    return y
+
+
+def relu(tape, x):
+    y = x.like()
+    tape.K.relu(x, y)
+    y.gate_on_grad = True
+    node = ReluNode(x, y)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def dropout_raw(tape, x, dropout):
+    """Dropout on a tensor that is not the output of a fused BN/ReLU (train mode only; identity otherwise)."""
+    if dropout is None or not dropout.training or dropout.p <= 0:
+        return x
+    mask = dropout.next_mask(tape.K, x.n, x.h, x.w, x.c, x.device)
+    scale = 1.0 / (1.0 - dropout.p)
+    y = x.like()
+    tape.K.mul_mask(x, mask, scale, y)
+    node = MulMaskNode(x, y, mask, scale)
+    y.node = node
+    tape.record(node, [x])
+    return y
 
 
 def maxpool3x3s2(tape, x, ceil_mode):

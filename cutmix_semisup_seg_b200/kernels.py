@@ -176,6 +176,20 @@ class ActKernels(object):
         self.be.nhwc_to_nchw(a.ptr, out, a.n, a.c, a.h, a.w, a.ld)
         return out
 
+    # U-Net decoder operators (csrc/unet.cu)
+    def upsample2x_add(self, x, skip, out):
+        self.be.upsample2x_add(x.ptr, x.ld, None if skip is None else skip.ptr, 0 if skip is None else skip.ld, out.ptr, out.ld,
+                               x.n, x.h, x.w, x.c)
+
+    def upsample2x_bwd(self, dy, dx, accumulate=False):
+        self.be.upsample2x_bwd(dy.ptr, dy.ld, dx.ptr, dx.ld, dx.n, dx.h, dx.w, dx.c, accumulate)
+
+    def mul_mask(self, x, mask, scale, out):
+        self.be.mul_mask(x.ptr, x.ld, mask, scale, out.ptr, out.ld, x.rows, x.c)
+
+    def relu(self, x, out):
+        self.be.relu(x.ptr, x.ld, out.ptr, out.ld, x.rows, x.c)
+
     def maxpool_fwd(self, x, out, idx):
         assert x.ld == x.c and out.ld == out.c
         self.be.maxpool_fwd(x.ptr, out.ptr, idx.data_ptr(), x.n, x.h, x.w, x.c, out.h, out.w)

@@ -208,6 +208,19 @@ class CudaBackend(object):
                    int(bool(conf_per_pixel)), float(ramp), float(cons_weight), out4.data_ptr(), self._s())
         return out4, dls
 
+    # ------------------------------------------------------------------ U-Net decoder (resunet.py / denseunet.py)
+    def upsample2x_add(self, x_ptr, ldx, skip_ptr, lds, y_ptr, ldy, n, h, w, c):
+        self._call('b2_upsample2x_add', x_ptr, ldx, skip_ptr, lds, y_ptr, ldy, n, h, w, c, self._s())
+
+    def upsample2x_bwd(self, dy_ptr, lddy, dx_ptr, lddx, n, h, w, c, accumulate=False):
+        self._call('b2_upsample2x_bwd', dy_ptr, lddy, dx_ptr, lddx, n, h, w, c, int(bool(accumulate)), self._s())
+
+    def mul_mask(self, x_ptr, ldx, mask, scale, y_ptr, ldy, rows, c):
+        self._call('b2_mul_mask', x_ptr, ldx, mask.data_ptr(), float(scale), y_ptr, ldy, rows, c, self._s())
+
+    def relu(self, x_ptr, ldx, y_ptr, ldy, rows, c):
+        self._call('b2_relu', x_ptr, ldx, y_ptr, ldy, rows, c, self._s())
+
     # ------------------------------------------------------------------ data-format boundary (seg_transforms_cv.py:587-672)
     def normalize_to_tensor(self, img_u8, mean=None, std=None, out=None):
         """uint8 (N,H,W,3|4) pixels -> standardised fp32 (N,3,H,W) planes, bit-identical to the reference's numpy pipeline

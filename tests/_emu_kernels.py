@@ -144,6 +144,28 @@ class EmuKernels(object):
         col.base.view(-1, kpad)[:, :kh * kw * x.c] = cols.to(torch.float32)
         return col
 
+    # ---- U-Net decoder operators (csrc/unet.cu) ----------------------------------------------------
+    def upsample2x_add(self, x, skip, out):
+        self.calls.append('upsample2x_add')
+        y = _v(x).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        if skip is not None:
+            y = y + _v(skip)
+        _store(out, y)
+
+    def upsample2x_bwd(self, dy, dx, accumulate=False):
+        self.calls.append('upsample2x_bwd')
+        g = _v(dy)
+        n, c, h2, w2 = g.shape
+        _store(dx, g.view(n, c, h2 // 2, 2, w2 // 2, 2).sum(dim=(3, 5)), accumulate)
+
+    def mul_mask(self, x, mask, scale, out):
+        self.calls.append('mul_mask')
+        _store(out, _v(x) * mask.permute(0, 3, 1, 2).to(DT) * scale)
+
+    def relu(self, x, out):
+        self.calls.append('relu')
+        _store(out, torch.relu(_v(x)))
+
     def col2im(self, dcol, dx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
         """b2_col2im's gather loop, written out tap by tap (independent of F.fold)."""
         self.calls.append('col2im')
