@@ -2,8 +2,8 @@
 (`seg.get(name)(num_classes, pretrained=...)`), plus `robust_binary_crossentropy` and
 `sigmoid_rampup` (network_architectures.py:15-130).
 
-The architectures on the B200 hot path are built natively (DeepLab v2 and DeepLab v3+ on ResNet-101), and so is
-torchvision's DeepLab v3, which shares every layer type with them.  The other names of the reference registry stay registered so that `seg.names()` matches,
+The architectures on the B200 hot path are built natively (DeepLab v2 and DeepLab v3+ on ResNet-101), and so are
+torchvision's DeepLab v3, which shares every layer type with them, and the ResNet U-Nets (architectures/resunet.py).  The other names of the reference registry stay registered so that `seg.names()` matches,
 but constructing them raises NotImplementedError (they are outside BASELINE.json's north_star).
 """
 import sys
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-from architectures import deeplab2, deeplab3plus
+from architectures import deeplab2, deeplab3plus, resunet
 
 
 class ArchRegistry(object):
@@ -44,9 +44,18 @@ def _not_built(name):
     return ctor
 
 
-for _name in ('resnet50unet_imagenet', 'resnet101unet_imagenet', 'densenet161unet', 'densenet161unet_imagenet',
-              'resnet101_pspnet_imagenet'):
+for _name in ('densenet161unet', 'densenet161unet_imagenet', 'resnet101_pspnet_imagenet'):
     seg.register(_name)(_not_built(_name))
+
+
+@seg.register('resnet50unet_imagenet')
+def resnet50unet_imagenet(num_classes, pretrained=True):
+    return resunet.resnet50unet(num_classes, pretrained=pretrained)
+
+
+@seg.register('resnet101unet_imagenet')
+def resnet101unet_imagenet(num_classes, pretrained=True):
+    return resunet.resnet101unet(num_classes, pretrained=pretrained)
 
 
 @seg.register('resnet101_deeplab_coco')

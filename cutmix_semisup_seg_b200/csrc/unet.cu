@@ -3,8 +3,6 @@
 //   b2_upsample2x_add       y = nearest-neighbour x2 up-sampling of x (nn.Upsample(scale_factor=2)) [+ skip]   resunet.py:31-32
 //   b2_upsample2x_bwd       dx (+)= sum of the 2x2 block of dy (the adjoint); d(skip) = dy needs no kernel
 //   b2_mul_mask             y = x * mask * scale: nn.Dropout applied to a raw convolution output (resunet.py:88), fwd and bwd
-//   b2_relu                 y = max(x, 0): the stem's ReLU is a separate layer here because the decoder taps the BatchNorm
-//                           output BEFORE it (resunet.py:69-71)
 // All HBM-bound single passes; float4 paths when channels and leading dimensions allow.
 #include "common.cuh"
 
@@ -105,8 +103,7 @@ extern "C" int b2_upsample2x_bwd(const float* dy, int lddy, float* dx, int lddx,
   return B2_OK;
 }
 
-// y[r, ch] = x[r, ch] * mask[r * c + ch] * scale (mask dense (rows, c); mask == NULL: y = max(x, 0), the ReLU forward)
-template <bool RELU>
+// y[r, ch] = x[r, ch] * mask[r * c + ch] * scale (mask dense (rows, c))
 __global__ void __launch_bounds__(UN_THREADS)
 mul_mask_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mask, float scale, float* __restrict__ y,
                 int ldy, int64_t rows, int c) {
@@ -114,22 +111,14 @@ mul_mask_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * UN_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * UN_THREADS) {
     const int64_t r = i / c;
     const int ch = (int)(i - r * c);
-    const float v = __ldg(x + r * ldx + ch);
-    y[r * ldy + ch] = RELU ? fmaxf(v, 0.f) : __fmul_rn(__fmul_rn(v, __ldg(mask + i)), scale);
+    y[r * ldy + ch] = __fmul_rn(__fmul_rn(__ldg(x + r * ldx + ch), __ldg(mask + i)), scale);
   }
 }
 
 extern "C" int b2_mul_mask(const float* x, int ldx, const float* mask, float scale, float* y, int ldy, int64_t rows, int c,
                            void* stream) {
   B2_REQUIRE(x && mask && y && rows > 0 && c > 0 && ldx >= c && ldy >= c, "b2_mul_mask: bad args");
-  mul_mask_kernel<false><<<grid_for(rows * c), UN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, mask, scale, y, ldy, rows, c);
+  mul_mask_kernel<<<grid_for(rows * c), UN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, mask, scale, y, ldy, rows, c);
   B2_LAUNCH_CHECK("mul_mask_kernel");
-  return B2_OK;
-}
-
-extern "C" int b2_relu(const float* x, int ldx, float* y, int ldy, int64_t rows, int c, void* stream) {
-  B2_REQUIRE(x && y && rows > 0 && c > 0 && ldx >= c && ldy >= c, "b2_relu: bad args");
-  mul_mask_kernel<true><<<grid_for(rows * c), UN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, 1.f, y, ldy, rows, c);
-  B2_LAUNCH_CHECK("relu_kernel");
   return B2_OK;
 }

@@ -358,21 +358,6 @@ class UpAddNode(object):
             tape.contribute_tensor(self.skip, dy)           # d(skip) = dy: aliased, not copied
 
 
-class ReluNode(object):
-    """y = max(x, 0) as its own layer.  The gradient of y is gated when its last consumer has contributed (gate_on_grad, like
-    the fused ReLUs), so the node only passes it on."""
-
-    def __init__(self, x, y):
-        self.x, self.y = x, y
-
-    def backward(self, tape):
-        dy = out_grad(self.y)
-        if dy is None:
-            tape.skip(self.x)
-            return
-        tape.contribute_tensor(self.x, dy)
-
-
 class MulMaskNode(object):
     """y = x * mask * scale: nn.Dropout applied to a raw convolution output (resunet.py:88)."""
 
@@ -590,9 +575,8 @@ def bn_train(tape, raw, bn, residual=None, relu=False, out=None, dropout=None, l
     return y
 
 
-def stem_conv(tape, x_nhwc, conv, bn, relu=True):
-    """Cin=3 7x7/s2 stem: explicit im2col (K = 147 padded to 160) + the same tensor-core GEMM.  `relu=False`: stop after
-    the BatchNorm (the U-Net decoders tap that tensor, resunet.py:69-71; eval-mode BN only)."""
+def stem_conv(tape, x_nhwc, conv, bn):
+    """Cin=3 7x7/s2 stem: explicit im2col (K = 147 padded to 160) + the same tensor-core GEMM."""
     K = tape.K
     cout, kh, kw, cin, stride, pad, dil = _geom(conv)
     oh, ow = _conv_out_hw(x_nhwc.h, x_nhwc.w, kh, stride, pad, dil)
@@ -606,9 +590,9 @@ def stem_conv(tape, x_nhwc, conv, bn, relu=True):
     flat = Act(tgt.base, 1, 1, tgt.rows, cout, cout, 0)
     if not train_bn:
         scale, shift = fold_bn(tape, bn)
-        K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat, scale=scale, shift=shift, relu=bool(relu))
-        tgt.gate_on_grad = bool(relu)
-        node = ConvNode(col, tgt, conv, bn, None, bool(relu), scale, (cout, kh, kw, cin, stride, pad, dil),
+        K.conv_fwd(col, wpad, cout, 1, 1, kpad, kpad, 1, 0, 1, flat, scale=scale, shift=shift, relu=True)
+        tgt.gate_on_grad = True
+        node = ConvNode(col, tgt, conv, bn, None, True, scale, (cout, kh, kw, cin, stride, pad, dil),
                         col_src=(col, kpad))
         tgt.node = node
         if x_nhwc.needs_grad:          # VAT: the gradient w.r.t. the image is wanted (netbase.b2_forward(input_grad=True))
@@ -625,7 +609,7 @@ def stem_conv(tape, x_nhwc, conv, bn, relu=True):
                      col_src=(col, kpad))
     tgt.node = cnode
     tape.record(cnode, [])
-    return bn_train(tape, tgt, bn, relu=bool(relu))
+    return bn_train(tape, tgt, bn, relu=True)
 
 
 def upsample2x_add(tape, x, skip=None):
@@ -637,16 +621,6 @@ def upsample2x_add(tape, x, skip=None):
     node = UpAddNode(x, skip, y)
     y.node = node
     tape.record(node, [x] + ([skip] if skip is not None else []))
-    return y
-
-
-def relu(tape, x):
-    y = x.like()
-    tape.K.relu(x, y)
-    y.gate_on_grad = True
-    node = ReluNode(x, y)
-    y.node = node
-    tape.record(node, [x])
     return y
 
 

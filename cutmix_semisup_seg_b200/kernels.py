@@ -187,9 +187,6 @@ class ActKernels(object):
     def mul_mask(self, x, mask, scale, out):
         self.be.mul_mask(x.ptr, x.ld, mask, scale, out.ptr, out.ld, x.rows, x.c)
 
-    def relu(self, x, out):
-        self.be.relu(x.ptr, x.ld, out.ptr, out.ld, x.rows, x.c)
-
     def maxpool_fwd(self, x, out, idx):
         assert x.ld == x.c and out.ld == out.c
         self.be.maxpool_fwd(x.ptr, out.ptr, idx.data_ptr(), x.n, x.h, x.w, x.c, out.h, out.w)

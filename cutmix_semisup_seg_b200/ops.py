@@ -218,9 +218,6 @@ class CudaBackend(object):
     def mul_mask(self, x_ptr, ldx, mask, scale, y_ptr, ldy, rows, c):
         self._call('b2_mul_mask', x_ptr, ldx, mask.data_ptr(), float(scale), y_ptr, ldy, rows, c, self._s())
 
-    def relu(self, x_ptr, ldx, y_ptr, ldy, rows, c):
-        self._call('b2_relu', x_ptr, ldx, y_ptr, ldy, rows, c, self._s())
-
     # ------------------------------------------------------------------ data-format boundary (seg_transforms_cv.py:587-672)
     def normalize_to_tensor(self, img_u8, mean=None, std=None, out=None):
         """uint8 (N,H,W,3|4) pixels -> standardised fp32 (N,3,H,W) planes, bit-identical to the reference's numpy pipeline

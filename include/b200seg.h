@@ -193,13 +193,11 @@ int b2_u8_to_tensor(const uint8_t* src, int64_t count, int mode, void* dst, void
  *   b2_upsample2x_add: y (N,2H,2W,C; ldy) = nearest x2 up-sampling of x (N,H,W,C; ldx) [+ skip (N,2H,2W,C; lds)]   (:31-32, :87)
  *   b2_upsample2x_bwd: dx (+)= sum over each 2x2 block of dy (adjoint of the up-sampling; d(skip) = dy)
  *   b2_mul_mask: y = x * mask * scale, mask dense (rows, C): nn.Dropout on a raw convolution output (:88), forward and backward
- *   b2_relu: y = max(x, 0) (the stem's ReLU as its own layer: the decoder taps the BatchNorm output before it, :69-71)
  * ------------------------------------------------------------------------------------------ */
 int b2_upsample2x_add(const float* x, int ldx, const float* skip, int lds, float* y, int ldy, int n, int h, int w, int c,
                       void* stream);
 int b2_upsample2x_bwd(const float* dy, int lddy, float* dx, int lddx, int n, int h, int w, int c, int accumulate, void* stream);
 int b2_mul_mask(const float* x, int ldx, const float* mask, float scale, float* y, int ldy, int64_t rows, int c, void* stream);
-int b2_relu(const float* x, int ldx, float* y, int ldy, int64_t rows, int c, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459

@@ -83,8 +83,8 @@ def build(kind, classes, seed, gain=1.0):
         net = reference_deeplabv3(classes)
     else:
         net = network_architectures.seg.get(kind)(classes, pretrained=False)
-    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'deeplab.classifier.4' in k)
-             and k.endswith('weight')]
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'deeplab.classifier.4' in k
+                                              or 'final_clf' in k) and k.endswith('weight')]
     sd = TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
     net.load_state_dict(sd)
     return net
@@ -104,7 +104,8 @@ def reference_deeplabv3(classes):
 def gen_state_dicts():
     out = {}
     for kind, classes in (('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19),
-                          ('resnet101_deeplabv3_imagenet', 21)):
+                          ('resnet101_deeplabv3_imagenet', 21), ('resnet50unet_imagenet', 11),
+                          ('resnet101unet_imagenet', 11)):
         if kind == 'resnet101_deeplabv3_imagenet':
             net = reference_deeplabv3(classes)
         else:
@@ -122,7 +123,8 @@ def gen_state_dicts():
 def gen_nets():
     for tag, kind, classes, (n, h, w) in (('dl2', 'resnet101_deeplab_imagenet', 21, (2, 33, 41)),
                                          ('dl3', 'resnet101_deeplabv3plus_imagenet', 19, (3, 33, 41)),
-                                         ('dl3v3', 'resnet101_deeplabv3_imagenet', 21, (2, 33, 41))):
+                                         ('dl3v3', 'resnet101_deeplabv3_imagenet', 21, (2, 33, 41)),
+                                         ('resunet50', 'resnet50unet_imagenet', 11, (2, 32, 64))):
         net = build(kind, classes, seed=1)
         net.train()
         net.freeze_batchnorm()
@@ -138,7 +140,8 @@ def gen_nets():
         for k, p in net.named_parameters():
             if p.grad is not None:
                 names.append(k); gsum.append(float(p.grad.double().sum())); gabs.append(float(p.grad.double().abs().sum()))
-        running = {k: v.numpy() for k, v in net.state_dict().items() if 'classifier.project.1.running' in k or 'classifier.2.running' in k}
+        running = {k: v.numpy() for k, v in net.state_dict().items()
+                   if 'classifier.project.1.running' in k or 'classifier.2.running' in k or 'final_dec_bn.running' in k}
         np.savez_compressed(os.path.join(OUT, 'net_%s.npz' % tag), x=x.numpy(), dy=dy.numpy(), logits=y.detach().numpy(),
                             grad_names=np.array(names), grad_sum=np.array(gsum), grad_abs=np.array(gabs), **running)
 

@@ -147,6 +147,47 @@ def deeplab3plus_forward(sd, x, backbone_bn_train=False, head_bn_train=False, dr
     return F.interpolate(c, size=in_hw, mode='bilinear', align_corners=False)
 
 
+def resunet_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_masks=None):
+    """ResUNet.forward, reference architectures/resunet.py:66-92, on a torchvision ResNet-50 / -101 state_dict under
+    `base_model.` (stride on the 3x3 convolution of each bottleneck, no dilation).  `dropout_masks`: list with one (N,64,H,W)
+    keep-mask for `final_dec_drop` = nn.Dropout(0.3) (None = dropout inactive)."""
+    bb = 'base_model.'
+    t = F.conv2d(x, sd[bb + 'conv1.weight'], stride=2, padding=3)                                 # :67
+    t = _bn(sd, bb + 'bn1', t, backbone_bn_train); _count_bn(sd, bb + 'bn1', backbone_bn_train)   # :68 `r2 = x = bn1(x)`
+    r2 = t = F.relu(t)               # :69 base_model.relu is nn.ReLU(inplace=True): it rectifies the tapped tensor r2 too
+    t = F.max_pool2d(t, 3, 2, 1)                                                                  # :70
+    taps = []
+    for name, stride in (('layer1', 1), ('layer2', 2), ('layer3', 2), ('layer4', 2)):             # :72-75
+        b = -1
+        while '{}{}.{}.conv1.weight'.format(bb, name, b + 1) in sd:
+            b += 1
+            p = '{}{}.{}'.format(bb, name, b)
+            s_ = stride if b == 0 else 1
+            res = t
+            o = F.conv2d(t, sd[p + '.conv1.weight'])
+            o = F.relu(_bn(sd, p + '.bn1', o, backbone_bn_train)); _count_bn(sd, p + '.bn1', backbone_bn_train)
+            o = F.conv2d(o, sd[p + '.conv2.weight'], stride=s_, padding=1)
+            o = F.relu(_bn(sd, p + '.bn2', o, backbone_bn_train)); _count_bn(sd, p + '.bn2', backbone_bn_train)
+            o = F.conv2d(o, sd[p + '.conv3.weight'])
+            o = _bn(sd, p + '.bn3', o, backbone_bn_train); _count_bn(sd, p + '.bn3', backbone_bn_train)
+            if (p + '.downsample.0.weight') in sd:
+                res = F.conv2d(t, sd[p + '.downsample.0.weight'], stride=s_)
+                res = _bn(sd, p + '.downsample.1', res, backbone_bn_train); _count_bn(sd, p + '.downsample.1', backbone_bn_train)
+            t = F.relu(o + res)
+        taps.append(t)
+    r4, r8, r16, r32 = taps
+    t = F.conv2d(r32, sd['line0_conv.weight'], sd['line0_conv.bias'])                             # :78
+    for name, skip in (('decoder3', r16), ('decoder2', r8), ('decoder1', r4), ('decoder0', r2)):  # :81-84, :27-33
+        t = F.interpolate(t, scale_factor=2, mode='nearest') + skip
+        t = F.conv2d(t, sd[name + '.conv.weight'], padding=1)
+        t = F.relu(_bn(sd, name + '.conv_bn', t, head_bn_train)); _count_bn(sd, name + '.conv_bn', head_bn_train)
+    t = F.conv2d(F.interpolate(t, scale_factor=2, mode='nearest'), sd['final_dec_conv.weight'], padding=1)   # :87
+    if dropout_masks is not None:
+        t = t * dropout_masks[0] * (1.0 / (1.0 - 0.3))                                            # nn.Dropout(0.3), training
+    t = F.relu(_bn(sd, 'final_dec_bn', t, head_bn_train)); _count_bn(sd, 'final_dec_bn', head_bn_train)      # :87-88
+    return F.conv2d(t, sd['final_clf.weight'], sd['final_clf.bias'])                              # :89
+
+
 # ----------------------------------------------------------------------------------------------
 # Loss block (reference train_seg_semisup_mask_mt.py:363-367, 406-459) and CE (:126, :300)
 # ----------------------------------------------------------------------------------------------

@@ -162,10 +162,6 @@ class EmuKernels(object):
         self.calls.append('mul_mask')
         _store(out, _v(x) * mask.permute(0, 3, 1, 2).to(DT) * scale)
 
-    def relu(self, x, out):
-        self.calls.append('relu')
-        _store(out, torch.relu(_v(x)))
-
     def col2im(self, dcol, dx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
         """b2_col2im's gather loop, written out tap by tap (independent of F.fold)."""
         self.calls.append('col2im')

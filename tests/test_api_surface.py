@@ -24,7 +24,7 @@ def test_state_dict_identical_to_reference(kind):
     assert len(set(id(p) for p in net.pretrained_parameters())) == g['n_pretrained_unique']
     assert len(list(net.new_parameters())) == g['n_new']
     assert [k for k, p in net.named_parameters() if p.requires_grad] == g['trainable']
-    assert net.BLOCK_SIZE == (1, 1) and len(net.MEAN) == 3 and len(net.STD) == 3
+    assert net.BLOCK_SIZE == ((32, 32) if 'unet' in kind else (1, 1)) and len(net.MEAN) == 3 and len(net.STD) == 3
 
 
 def test_registry_names_and_unbuilt_architectures():

@@ -41,7 +41,10 @@ def _run(kind, n, h, w, classes, freeze, seed):
     dm = None
     for m in net.modules():
         if type(m).__name__ == 'B2Dropout':
-            dm = (torch.rand(n, -(-h // 8), -(-w // 8), 256) > 0.5).float()
+            if 'unet' in kind:
+                dm = (torch.rand(n, h, w, 64) > 0.3).float()           # final_dec_drop acts at the input resolution
+            else:
+                dm = (torch.rand(n, -(-h // 8), -(-w // 8), 256) > 0.5).float()
             m.inject([dm])
     x = torch.randn(n, 3, h, w)
     y = net(x)
@@ -51,7 +54,10 @@ def _run(kind, n, h, w, classes, freeze, seed):
     for k, p in net.named_parameters():
         if p.requires_grad:
             sd64[k].requires_grad_(True)
-    if 'deeplabv3_' in kind:
+    if 'unet' in kind:
+        yo = TO.resunet_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
+                                dropout_masks=[dm.permute(0, 3, 1, 2).double()])
+    elif 'deeplabv3_' in kind:
         yo = TO.deeplab3_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
                                  dropout_masks=[dm.permute(0, 3, 1, 2).double()])
     elif 'v3plus' in kind:
@@ -113,6 +119,23 @@ def test_deeplab3_frozen_backbone_train_head(emu):
     nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
     assert nb['deeplab.classifier.2.num_batches_tracked'] == 1 and nb['deeplab.classifier.0.project.1.num_batches_tracked'] == 1
     assert nb['deeplab.backbone.bn1.num_batches_tracked'] == 0
+
+
+def test_resnet50_unet_frozen_encoder_train_decoder(emu):
+    """architectures/resunet.py: nearest up-sampling + skip additions, dropout between the last conv and its BatchNorm; every
+    trainable tensor but the encoder's unused `fc` receives a gradient."""
+    lerr, errs, stat, net = _run('resnet50unet_imagenet', 2, 32, 64, 11, True, seed=2)
+    assert lerr < 1e-4
+    assert len(errs) == 180 - 2                           # base_model.fc.{weight,bias} are never used (resunet.py:66-92)
+    assert errs[len(errs) // 2] < 1e-3 and errs[-1] < 5e-2
+    assert stat < 1e-4
+    assert net.base_model.fc.weight.grad is None
+    for op in ('upsample2x_add', 'upsample2x_bwd'):
+        assert emu.calls.count(op) == 5
+    assert emu.calls.count('mul_mask') == 2
+    nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
+    assert nb['final_dec_bn.num_batches_tracked'] == 1 and nb['decoder0.conv_bn.num_batches_tracked'] == 1
+    assert nb['base_model.bn1.num_batches_tracked'] == 0
 
 
 def test_gradient_accumulation_over_two_backward_passes(emu):

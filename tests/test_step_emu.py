@@ -238,6 +238,53 @@ def test_deeplab3_cutmix_iteration_batched_trunk(doubles):
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
 
 
+def test_resnet50_unet_cutmix_iteration_batched_trunk(doubles):
+    """CutMix iteration on the ResNet-50 U-Net (architectures/resunet.py): five trunk features (the skip connections) are
+    split per mini-batch by the batched-trunk schedule; the encoder's unused `fc` layer gets no update."""
+    import torch_oracle as TO
+    import ref_step
+    import mask_gen
+    from _emu_backend import EmuEMA
+    from architectures import network_architectures as na
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    kind, c, lr, h, w = 'resnet50unet_imagenet', 11, 1e-5, 32, 64
+    student = na.seg.get(kind)(c, pretrained=False)
+    final = [k for k in student.state_dict() if 'final_clf' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(student.state_dict(), seed=3, logit_gain=4.0, final_keys=final)
+    student.load_state_dict(sd)
+    teacher = na.seg.get(kind)(c, pretrained=False)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    for net in (student, teacher):
+        for m in net.modules():
+            if hasattr(m, 'next_mask'):
+                m.p = 0.0                              # the dropout draw cannot be shared with the oracle
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'adam', lr)
+    ema = EmuEMA(teacher, student, 0.99)
+    student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+    mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, cons_weight=0.7, conf_thresh=0.5)
+    assert trainer._can_batch_trunk([None])
+    orc = ref_step.OracleMeanTeacher('resunet', sd, lr, cons_weight=0.7, conf_thresh=0.5)
+    fc0 = student.base_model.fc.weight.detach().clone()
+    for it in range(2):
+        sup = synthetic.make_sup_batch(N, h, w, c, 10 + it)
+        uns = synthetic.make_unsup_batch(N, h, w, 20 + it, mg, compact_masks=True)
+        uns_o = dict(uns)
+        uns_o['mask_params'] = torch.from_numpy(TO.box_masks(uns['mask_params'].numpy(), (h, w), invert=True))
+        with torch.no_grad():
+            out = trainer.step(sup, [uns])
+        s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], uns_o)
+        assert float(out['sup_loss']) == pytest.approx(s_ref, rel=5e-5)
+        assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-3, abs=1e-8)
+        assert float(out['conf_rate']) == pytest.approx(r_ref, abs=2.0 / (N * h * w))
+    assert torch.equal(student.base_model.fc.weight.detach(), fc0)
+    assert _state_gap(student, orc.student) < 1.5e-3
+    assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
 def test_vat_rejects_loss_functions_the_reference_rejects(doubles):
     student, teacher, trainer, orc, mg = _build('vat', False, True, cons_loss_fn='logits_smoothl1')
     sup, uns, uns_o = _batches('vat', mg, 0)
