@@ -3,7 +3,8 @@
 `sigmoid_rampup` (network_architectures.py:15-130).
 
 The architectures on the B200 hot path are built natively (DeepLab v2 and DeepLab v3+ on ResNet-101), and so are
-torchvision's DeepLab v3, which shares every layer type with them, and the ResNet U-Nets (architectures/resunet.py).  The other names of the reference registry stay registered so that `seg.names()` matches,
+torchvision's DeepLab v3, which shares every layer type with them, the ResNet U-Nets (architectures/resunet.py)
+and the DenseNet-161 U-Net (architectures/denseunet.py).  The other names of the reference registry stay registered so that `seg.names()` matches,
 but constructing them raises NotImplementedError (they are outside BASELINE.json's north_star).
 """
 import sys
@@ -11,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-from architectures import deeplab2, deeplab3plus, resunet
+from architectures import deeplab2, deeplab3plus, denseunet, resunet
 
 
 class ArchRegistry(object):
@@ -44,7 +45,7 @@ def _not_built(name):
     return ctor
 
 
-for _name in ('densenet161unet', 'densenet161unet_imagenet', 'resnet101_pspnet_imagenet'):
+for _name in ('resnet101_pspnet_imagenet',):
     seg.register(_name)(_not_built(_name))
 
 
@@ -56,6 +57,16 @@ def resnet50unet_imagenet(num_classes, pretrained=True):
 @seg.register('resnet101unet_imagenet')
 def resnet101unet_imagenet(num_classes, pretrained=True):
     return resunet.resnet101unet(num_classes, pretrained=pretrained)
+
+
+@seg.register('densenet161unet')
+def densenet161unet(num_classes):
+    return denseunet.densenet161unet(num_classes)
+
+
+@seg.register('densenet161unet_imagenet')
+def densenet161unet_imagenet(num_classes):
+    return denseunet.densenet161unet_imagenet(num_classes)
 
 
 @seg.register('resnet101_deeplab_coco')

@@ -122,3 +122,101 @@ extern "C" int b2_mul_mask(const float* x, int ldx, const float* mask, float sca
   B2_LAUNCH_CHECK("mul_mask_kernel");
   return B2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- DenseNet encoder glue
+// (architectures/denseunet.py: torchvision densenet161 `features`)
+//   b2_avgpool2x2       transition layers' nn.AvgPool2d(kernel_size=2, stride=2): y[n,h,w,c] = mean of the 2x2 block of x
+//   b2_avgpool2x2_bwd   dx[n,2h+a,2w+b,c] (+)= 0.25 * dy[n,h,w,c]
+//   b2_scale_channels   dst[r,c] (+)= g[r,c] * scale[c]: backward of a stand-alone eval-mode BatchNorm (the pre-activation
+//                       norm1 / transition norm of DenseNet act on a concatenation and cannot be folded into a producing
+//                       convolution), accumulating into a channel prefix of the concatenation's gradient
+template <int VEC>
+__global__ void __launch_bounds__(UN_THREADS)
+avgpool2x2_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int oh, int ow, int ih, int iw,
+                  int c) {
+  const int cv = c / VEC;
+  const int64_t total = (int64_t)n * oh * ow * cv;
+  for (int64_t i = (int64_t)blockIdx.x * UN_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * UN_THREADS) {
+    const int ch = (int)(i % cv) * VEC;
+    const int64_t pix = i / cv;
+    const int ox = (int)(pix % ow);
+    const int64_t t = pix / ow;
+    const int oy = (int)(t % oh);
+    const int img = (int)(t / oh);
+    const int64_t i00 = ((int64_t)img * ih + 2 * oy) * iw + 2 * ox;
+    const int64_t i10 = i00 + iw;
+    if (VEC == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + i00 * ldx + ch));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x + (i00 + 1) * ldx + ch));
+      const float4 cc = __ldg(reinterpret_cast<const float4*>(x + i10 * ldx + ch));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(x + (i10 + 1) * ldx + ch));
+      *reinterpret_cast<float4*>(y + pix * ldy + ch) = make_float4(
+          ((a.x + b.x) + (cc.x + d.x)) * 0.25f, ((a.y + b.y) + (cc.y + d.y)) * 0.25f, ((a.z + b.z) + (cc.z + d.z)) * 0.25f,
+          ((a.w + b.w) + (cc.w + d.w)) * 0.25f);
+    } else {
+      y[pix * ldy + ch] = ((__ldg(x + i00 * ldx + ch) + __ldg(x + (i00 + 1) * ldx + ch)) +
+                           (__ldg(x + i10 * ldx + ch) + __ldg(x + (i10 + 1) * ldx + ch))) * 0.25f;
+    }
+  }
+}
+
+extern "C" int b2_avgpool2x2(const float* x, int ldx, float* y, int ldy, int n, int ih, int iw, int c, void* stream) {
+  B2_REQUIRE(x && y && n > 0 && ih >= 2 && iw >= 2 && c > 0 && ldx >= c && ldy >= c, "b2_avgpool2x2: bad args");
+  const int oh = ih / 2, ow = iw / 2;                       // floor, like nn.AvgPool2d(2, 2)
+  const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16p(x) && al16p(y);
+  const int64_t total = (int64_t)n * oh * ow * (vec ? c / 4 : c);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec) avgpool2x2_kernel<4><<<grid_for(total), UN_THREADS, 0, s>>>(x, ldx, y, ldy, n, oh, ow, ih, iw, c);
+  else avgpool2x2_kernel<1><<<grid_for(total), UN_THREADS, 0, s>>>(x, ldx, y, ldy, n, oh, ow, ih, iw, c);
+  B2_LAUNCH_CHECK("avgpool2x2_kernel");
+  return B2_OK;
+}
+
+__global__ void __launch_bounds__(UN_THREADS)
+avgpool2x2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int n, int oh, int ow, int ih,
+                      int iw, int c, int accumulate) {
+  const int64_t total = (int64_t)n * ih * iw * c;
+  for (int64_t i = (int64_t)blockIdx.x * UN_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * UN_THREADS) {
+    const int ch = (int)(i % c);
+    const int64_t pix = i / c;
+    const int ix = (int)(pix % iw);
+    const int64_t t = pix / iw;
+    const int iy = (int)(t % ih);
+    const int img = (int)(t / ih);
+    float v = 0.f;                                          // an odd last row / column is not covered by any window
+    if ((iy >> 1) < oh && (ix >> 1) < ow) v = 0.25f * __ldg(dy + (((int64_t)img * oh + (iy >> 1)) * ow + (ix >> 1)) * lddy + ch);
+    float* dst = dx + pix * lddx + ch;
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
+extern "C" int b2_avgpool2x2_bwd(const float* dy, int lddy, float* dx, int lddx, int n, int ih, int iw, int c, int accumulate,
+                                 void* stream) {
+  B2_REQUIRE(dy && dx && n > 0 && ih >= 2 && iw >= 2 && c > 0 && lddy >= c && lddx >= c, "b2_avgpool2x2_bwd: bad args");
+  const int64_t total = (int64_t)n * ih * iw * c;
+  avgpool2x2_bwd_kernel<<<grid_for(total), UN_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, n, ih / 2, iw / 2, ih, iw, c,
+                                                                                 accumulate);
+  B2_LAUNCH_CHECK("avgpool2x2_bwd_kernel");
+  return B2_OK;
+}
+
+__global__ void __launch_bounds__(UN_THREADS)
+scale_channels_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ scale, float* __restrict__ dst, int ldd,
+                      int64_t rows, int c, int accumulate) {
+  const int64_t total = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * UN_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * UN_THREADS) {
+    const int64_t r = i / c;
+    const int ch = (int)(i - r * c);
+    const float v = __ldg(g + r * ldg + ch) * __ldg(scale + ch);
+    float* d = dst + r * ldd + ch;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+extern "C" int b2_scale_channels(const float* g, int ldg, const float* scale, float* dst, int ldd, int64_t rows, int c,
+                                 int accumulate, void* stream) {
+  B2_REQUIRE(g && scale && dst && rows > 0 && c > 0 && ldg >= c && ldd >= c, "b2_scale_channels: bad args");
+  scale_channels_kernel<<<grid_for(rows * c), UN_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, scale, dst, ldd, rows, c, accumulate);
+  B2_LAUNCH_CHECK("scale_channels_kernel");
+  return B2_OK;
+}

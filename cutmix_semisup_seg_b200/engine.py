@@ -151,6 +151,27 @@ class Tape(object):
             t.grad, t.grad_owned = owned, True
         self._finish(t, False)
 
+    def contribute_slice(self, t, launch):
+        """d/d(t) += one consumer's contribution where t is a channel SLICE of a wider root activation (DenseNet: every
+        dense layer reads a prefix of the block's concatenation).  launch(dst, accumulate) adds into dst, a view of the
+        root's gradient restricted to t's channels; the root's gradient is created zero-filled on first use."""
+        if t.parent is None:
+            return self.contribute_kernel(t, lambda dst, accumulate, addend, gate, stats: launch(dst, accumulate), False)
+        root, off = t, 0
+        while root.parent is not None:
+            off += root.off - root.parent.off
+            root = root.parent
+        root.pending -= 1
+        if root.grad is None:
+            root.grad, root.grad_owned = self._new_grad(root), True
+            self.K.fill_act(root.grad, 0.0)
+        elif not root.grad_owned:
+            owned = self._new_grad(root)
+            self.K.copy_act(owned, root.grad)
+            root.grad, root.grad_owned = owned, True
+        launch(root.grad.slice(off, t.c), True)
+        self._finish(root, False)
+
     def skip(self, t):
         root = t
         while root.parent is not None:
@@ -376,6 +397,59 @@ class MulMaskNode(object):
             assert not accumulate, 'the dropped tensor has a single consumer'
             K.mul_mask(dy, mask, scale, dst)
         tape.contribute_kernel(self.x, launch, False)
+
+
+class BNEvalNode(object):
+    """y = [relu]( x * scale + shift ): a stand-alone eval-mode BatchNorm (DenseNet's pre-activation norm1 / transition norm /
+    norm5 act on a concatenation, so they cannot be folded into the convolution that produced their input)."""
+
+    def __init__(self, x, y, bn, scale):
+        self.x, self.y, self.bn, self.scale = x, y, bn, scale
+
+    def backward(self, tape):
+        K = tape.K
+        g = out_grad(self.y)                      # already gated by y > 0 (gate_on_grad)
+        if g is None:
+            tape.skip(self.x)
+            return
+        bn = self.bn
+        if tape.wants(bn.weight):
+            dgam, acc = param_grad(bn.weight)
+            dbet, acc2 = param_grad(bn.bias)
+            assert acc == acc2
+            K.bn_eval_param_grad(g, self.y, bn.weight, bn.bias, None, dgam, dbet, acc)
+        scale = self.scale
+        tape.contribute_slice(self.x, lambda dst, accumulate: K.scale_channels(g, scale, dst, accumulate=accumulate))
+
+
+class AvgPoolNode(object):
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    def backward(self, tape):
+        K = tape.K
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        tape.contribute_kernel(self.x, lambda dst, accumulate, addend, gate, stats: K.avgpool2x2_bwd(
+            dy, dst, accumulate=accumulate), False)
+
+
+class CopyNode(object):
+    """dst (a slice of a concatenation buffer) = src."""
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    def backward(self, tape):
+        dy = out_grad(self.y)
+        if dy is None:
+            tape.skip(self.x)
+            return
+        tmp = self.x.like()
+        tape.K.copy_act(tmp, dy)
+        tape.contribute_tensor(self.x, tmp)
 
 
 class MaxPoolNode(object):
@@ -636,6 +710,49 @@ def dropout_raw(tape, x, dropout):
     y.node = node
     tape.record(node, [x])
     return y
+
+
+_IDENTITY_STATS = {}
+
+
+def bn_eval_act(tape, x, bn, relu=True):
+    """Stand-alone eval-mode BatchNorm (+ReLU) of an activation or of a channel slice of one; returns a dense activation."""
+    if bn.training:
+        raise NotImplementedError('stand-alone train-mode BatchNorm on a concatenation (DenseNet encoders are run with '
+                                  'freeze_batchnorm(), like the reference recipes)')
+    K = tape.K
+    scale, shift = fold_bn(tape, bn)
+    key = (K.name, x.c, str(x.device))
+    if key not in _IDENTITY_STATS:          # (x - 0) * 1 * scale + shift through the fused BN-apply kernel
+        _IDENTITY_STATS[key] = (torch.zeros(x.c, device=x.device), torch.ones(x.c, device=x.device))
+    zeros, ones = _IDENTITY_STATS[key]
+    y = Act.alloc(x.n, x.h, x.w, x.c, x.device)
+    K.bn_apply(x, zeros, ones, scale, shift, relu, None, 1.0, y)
+    y.gate_on_grad = bool(relu)
+    node = BNEvalNode(x, y, bn, scale)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def avgpool2x2(tape, x, out=None):
+    y = out if out is not None else Act.alloc(x.n, x.h // 2, x.w // 2, x.c, x.device)
+    assert (y.n, y.h, y.w, y.c) == (x.n, x.h // 2, x.w // 2, x.c)
+    tape.K.avgpool2x2(x, y)
+    node = AvgPoolNode(x, y)
+    y.node = node
+    tape.record(node, [x])
+    return y
+
+
+def copy_into(tape, x, out):
+    """out (a channel slice of a concatenation buffer) = x."""
+    assert (out.n, out.h, out.w, out.c) == (x.n, x.h, x.w, x.c)
+    tape.K.copy_act(out, x)
+    node = CopyNode(x, out)
+    out.node = node
+    tape.record(node, [x])
+    return out
 
 
 def maxpool3x3s2(tape, x, ceil_mode):

@@ -187,6 +187,15 @@ class ActKernels(object):
     def mul_mask(self, x, mask, scale, out):
         self.be.mul_mask(x.ptr, x.ld, mask, scale, out.ptr, out.ld, x.rows, x.c)
 
+    def avgpool2x2(self, x, out):
+        self.be.avgpool2x2(x.ptr, x.ld, out.ptr, out.ld, x.n, x.h, x.w, x.c)
+
+    def avgpool2x2_bwd(self, dy, dx, accumulate=False):
+        self.be.avgpool2x2_bwd(dy.ptr, dy.ld, dx.ptr, dx.ld, dx.n, dx.h, dx.w, dx.c, accumulate)
+
+    def scale_channels(self, g, scale, dst, accumulate=False):
+        self.be.scale_channels(g.ptr, g.ld, scale, dst.ptr, dst.ld, g.rows, g.c, accumulate)
+
     def maxpool_fwd(self, x, out, idx):
         assert x.ld == x.c and out.ld == out.c
         self.be.maxpool_fwd(x.ptr, out.ptr, idx.data_ptr(), x.n, x.h, x.w, x.c, out.h, out.w)

@@ -90,6 +90,9 @@ _SIGS = {
     'b2_upsample2x_add': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_upsample2x_bwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_mul_mask': (c_int, [c_vp, c_int, c_vp, c_f32, c_vp, c_int, c_i64, c_int, c_vp]),
+    'b2_avgpool2x2': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'b2_avgpool2x2_bwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'b2_scale_channels': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
     'b2_consistency_num_partials': (c_i64, [c_int, c_i64]),
     'b2_consistency_fwd_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                        c_f32, c_int, c_vp]),

@@ -218,6 +218,15 @@ class CudaBackend(object):
     def mul_mask(self, x_ptr, ldx, mask, scale, y_ptr, ldy, rows, c):
         self._call('b2_mul_mask', x_ptr, ldx, mask.data_ptr(), float(scale), y_ptr, ldy, rows, c, self._s())
 
+    def avgpool2x2(self, x_ptr, ldx, y_ptr, ldy, n, ih, iw, c):
+        self._call('b2_avgpool2x2', x_ptr, ldx, y_ptr, ldy, n, ih, iw, c, self._s())
+
+    def avgpool2x2_bwd(self, dy_ptr, lddy, dx_ptr, lddx, n, ih, iw, c, accumulate=False):
+        self._call('b2_avgpool2x2_bwd', dy_ptr, lddy, dx_ptr, lddx, n, ih, iw, c, int(bool(accumulate)), self._s())
+
+    def scale_channels(self, g_ptr, ldg, scale, dst_ptr, ldd, rows, c, accumulate=False):
+        self._call('b2_scale_channels', g_ptr, ldg, scale.data_ptr(), dst_ptr, ldd, rows, c, int(bool(accumulate)), self._s())
+
     # ------------------------------------------------------------------ data-format boundary (seg_transforms_cv.py:587-672)
     def normalize_to_tensor(self, img_u8, mean=None, std=None, out=None):
         """uint8 (N,H,W,3|4) pixels -> standardised fp32 (N,3,H,W) planes, bit-identical to the reference's numpy pipeline

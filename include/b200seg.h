@@ -198,6 +198,14 @@ int b2_upsample2x_add(const float* x, int ldx, const float* skip, int lds, float
                       void* stream);
 int b2_upsample2x_bwd(const float* dy, int lddy, float* dx, int lddx, int n, int h, int w, int c, int accumulate, void* stream);
 int b2_mul_mask(const float* x, int ldx, const float* mask, float scale, float* y, int ldy, int64_t rows, int c, void* stream);
+/* DenseNet encoder glue (architectures/denseunet.py: torchvision densenet161 features):
+ *   b2_avgpool2x2 / _bwd: nn.AvgPool2d(2, 2) of the transition layers (floor output size), NHWC with leading dimensions;
+ *   b2_scale_channels: dst[r,c] (+)= g[r,c] * scale[c], the data gradient of a stand-alone eval-mode BatchNorm (DenseNet's
+ *     pre-activation norms act on a concatenation), accumulated into a channel prefix of the concatenation's gradient. */
+int b2_avgpool2x2(const float* x, int ldx, float* y, int ldy, int n, int ih, int iw, int c, void* stream);
+int b2_avgpool2x2_bwd(const float* dy, int lddy, float* dx, int lddx, int n, int ih, int iw, int c, int accumulate, void* stream);
+int b2_scale_channels(const float* g, int ldg, const float* scale, float* dst, int ldd, int64_t rows, int c, int accumulate,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * L1  Fused CutMix consistency loss — train_seg_semisup_mask_mt.py:363-367,406-420,428-459

@@ -81,6 +81,8 @@ def gen_masks():
 def build(kind, classes, seed, gain=1.0):
     if kind == 'resnet101_deeplabv3_imagenet':
         net = reference_deeplabv3(classes)
+    elif kind == 'densenet161unet':
+        net = network_architectures.seg.get(kind)(classes)
     else:
         net = network_architectures.seg.get(kind)(classes, pretrained=False)
     final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'deeplab.classifier.4' in k
@@ -105,9 +107,11 @@ def gen_state_dicts():
     out = {}
     for kind, classes in (('resnet101_deeplab_imagenet', 21), ('resnet101_deeplabv3plus_imagenet', 19),
                           ('resnet101_deeplabv3_imagenet', 21), ('resnet50unet_imagenet', 11),
-                          ('resnet101unet_imagenet', 11)):
+                          ('resnet101unet_imagenet', 11), ('densenet161unet', 2)):
         if kind == 'resnet101_deeplabv3_imagenet':
             net = reference_deeplabv3(classes)
+        elif kind == 'densenet161unet':
+            net = network_architectures.seg.get(kind)(classes)           # the factory takes no `pretrained` argument
         else:
             net = network_architectures.seg.get(kind)(classes, pretrained=False)
         out[kind] = dict(classes=classes,
@@ -124,7 +128,8 @@ def gen_nets():
     for tag, kind, classes, (n, h, w) in (('dl2', 'resnet101_deeplab_imagenet', 21, (2, 33, 41)),
                                          ('dl3', 'resnet101_deeplabv3plus_imagenet', 19, (3, 33, 41)),
                                          ('dl3v3', 'resnet101_deeplabv3_imagenet', 21, (2, 33, 41)),
-                                         ('resunet50', 'resnet50unet_imagenet', 11, (2, 32, 64))):
+                                         ('resunet50', 'resnet50unet_imagenet', 11, (2, 32, 64)),
+                                         ('denseunet', 'densenet161unet', 2, (2, 32, 64))):
         net = build(kind, classes, seed=1)
         net.train()
         net.freeze_batchnorm()

@@ -46,7 +46,7 @@ def deeplab2_param_groups(sd):
 
 
 class OracleMeanTeacher(object):
-    """State + one-iteration function.  arch: 'deeplab2' | 'deeplab3plus' | 'deeplab3' | 'resunet'."""
+    """State + one-iteration function.  arch: 'deeplab2' | 'deeplab3plus' | 'deeplab3' | 'resunet' | 'denseunet'."""
 
     def __init__(self, arch, state_dict, learning_rate, opt_type='adam', teacher_alpha=0.99, freeze_bn=True,
                  cons_loss_fn='var', cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
@@ -98,12 +98,17 @@ class OracleMeanTeacher(object):
         if self.eval_mode[which]:                 # module in eval mode: running statistics everywhere, no dropout
             if self.arch == 'deeplab2':
                 return TO.deeplab2_forward(sd, x, bn_train=False)
+            if self.arch == 'denseunet':
+                return TO.denseunet_forward(sd, x, backbone_bn_train=False, head_bn_train=False)
             if self.arch == 'resunet':
                 return TO.resunet_forward(sd, x, backbone_bn_train=False, head_bn_train=False)
             fwd = TO.deeplab3_forward if self.arch == 'deeplab3' else TO.deeplab3plus_forward
             return fwd(sd, x, backbone_bn_train=False, head_bn_train=False)
         if self.arch == 'deeplab2':
             return TO.deeplab2_forward(sd, x, bn_train=not self.freeze_bn)
+        if self.arch == 'denseunet':              # architectures/denseunet.py: freeze_batchnorm touches the encoder only
+            return TO.denseunet_forward(sd, x, backbone_bn_train=not self.freeze_bn, head_bn_train=True,
+                                        dropout_masks=dropout_masks)
         if self.arch == 'resunet':                # architectures/resunet.py: freeze_batchnorm touches the encoder only
             return TO.resunet_forward(sd, x, backbone_bn_train=not self.freeze_bn, head_bn_train=True,
                                       dropout_masks=dropout_masks)

@@ -188,6 +188,51 @@ def resunet_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_
     return F.conv2d(t, sd['final_clf.weight'], sd['final_clf.bias'])                              # :89
 
 
+def denseunet_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_masks=None):
+    """DenseUNet.forward, reference architectures/denseunet.py:98-124, on a torchvision DenseNet-161 state_dict under
+    `base_model.features.` (pre-activation dense layers: norm1-relu-conv1(1x1)-norm2-relu-conv2(3x3), concatenated;
+    transitions norm-relu-conv(1x1)-avgpool(2)).  Taps are taken BEFORE pool0 / transition1..3 (:100-104).
+    `dropout_masks`: one (N,64,H,W) keep-mask for `final_dec_drop` = nn.Dropout(0.3) (None = inactive)."""
+    ft = 'base_model.features.'
+    tr = backbone_bn_train
+
+    def bn_relu(t, prefix):
+        y = F.relu(_bn(sd, prefix, t, tr)); _count_bn(sd, prefix, tr)
+        return y
+    t = F.conv2d(x, sd[ft + 'conv0.weight'], stride=2, padding=3)
+    t = bn_relu(t, ft + 'norm0')                       # norm0, relu0 (in place); the 'pool0' tap is this tensor
+    enc_x = [t]
+    t = F.max_pool2d(t, 3, 2, 1)
+    for b in (1, 2, 3, 4):
+        feats = [t]
+        i = 1
+        while '{}denseblock{}.denselayer{}.conv1.weight'.format(ft, b, i) in sd:
+            p = '{}denseblock{}.denselayer{}.'.format(ft, b, i)
+            o = bn_relu(torch.cat(feats, 1), p + 'norm1')
+            o = F.conv2d(o, sd[p + 'conv1.weight'])
+            o = bn_relu(o, p + 'norm2')
+            feats.append(F.conv2d(o, sd[p + 'conv2.weight'], padding=1))
+            i += 1
+        t = torch.cat(feats, 1)
+        if b < 4:
+            enc_x.append(t)                            # tap before transition b
+            p = '{}transition{}.'.format(ft, b)
+            t = F.avg_pool2d(F.conv2d(bn_relu(t, p + 'norm'), sd[p + 'conv.weight']), 2, 2)
+    t = _bn(sd, ft + 'norm5', t, tr); _count_bn(sd, ft + 'norm5', tr)
+    t = F.relu(t)                                                                                 # :108
+    enc_x[-1] = F.conv2d(enc_x[-1], sd['line0_conv.weight'], sd['line0_conv.bias'])               # :111-112
+    for k, skip in zip((3, 2, 1, 0), enc_x[::-1]):                                                # :115-116 (stored reversed, :95)
+        name = 'decoder_blocks.{}'.format(k)
+        t = F.interpolate(t, scale_factor=2, mode='nearest') + skip
+        t = F.conv2d(t, sd[name + '.conv.weight'], padding=1)
+        t = F.relu(_bn(sd, name + '.conv_bn', t, head_bn_train)); _count_bn(sd, name + '.conv_bn', head_bn_train)
+    t = F.conv2d(F.interpolate(t, scale_factor=2, mode='nearest'), sd['final_dec_conv.weight'], padding=1)   # :119
+    if dropout_masks is not None:
+        t = t * dropout_masks[0] * (1.0 / (1.0 - 0.3))
+    t = F.relu(_bn(sd, 'final_dec_bn', t, head_bn_train)); _count_bn(sd, 'final_dec_bn', head_bn_train)      # :119-120
+    return F.conv2d(t, sd['final_clf.weight'], sd['final_clf.bias'])                              # :121
+
+
 # ----------------------------------------------------------------------------------------------
 # Loss block (reference train_seg_semisup_mask_mt.py:363-367, 406-459) and CE (:126, :300)
 # ----------------------------------------------------------------------------------------------

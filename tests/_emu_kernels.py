@@ -162,6 +162,22 @@ class EmuKernels(object):
         self.calls.append('mul_mask')
         _store(out, _v(x) * mask.permute(0, 3, 1, 2).to(DT) * scale)
 
+    def avgpool2x2(self, x, out):
+        self.calls.append('avgpool2x2')
+        _store(out, F.avg_pool2d(_v(x), 2, 2))
+
+    def avgpool2x2_bwd(self, dy, dx, accumulate=False):
+        self.calls.append('avgpool2x2_bwd')
+        g = _v(dy)
+        full = torch.zeros(dx.n, dx.c, dx.h, dx.w, dtype=DT)
+        up = g.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3) * 0.25
+        full[:, :, :up.shape[2], :up.shape[3]] = up
+        _store(dx, full, accumulate)
+
+    def scale_channels(self, g, scale, dst, accumulate=False):
+        self.calls.append('scale_channels')
+        _store(dst, _v(g) * scale.to(DT).view(1, -1, 1, 1), accumulate)
+
     def col2im(self, dcol, dx, kh, kw, stride, pad, dil, oh, ow, kpad, accumulate=False):
         """b2_col2im's gather loop, written out tap by tap (independent of F.fold)."""
         self.calls.append('col2im')

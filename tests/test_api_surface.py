@@ -17,21 +17,26 @@ GOLD = json.load(open(os.path.join(HERE, 'golden', 'state_dicts.json')))
 @pytest.mark.parametrize('kind', sorted(GOLD.keys()))
 def test_state_dict_identical_to_reference(kind):
     g = GOLD[kind]
-    net = na.seg.get(kind)(g['classes'], pretrained=False)
+    # the reference's densenet161unet factory takes no `pretrained` argument (network_architectures.py:53-55)
+    net = na.seg.get(kind)(g['classes']) if kind == 'densenet161unet' else na.seg.get(kind)(g['classes'], pretrained=False)
     mine = [[k, list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in net.state_dict().items()]
     assert mine == g['entries']
     assert len(list(net.pretrained_parameters())) == g['n_pretrained']
     assert len(set(id(p) for p in net.pretrained_parameters())) == g['n_pretrained_unique']
     assert len(list(net.new_parameters())) == g['n_new']
     assert [k for k, p in net.named_parameters() if p.requires_grad] == g['trainable']
-    assert net.BLOCK_SIZE == ((32, 32) if 'unet' in kind else (1, 1)) and len(net.MEAN) == 3 and len(net.STD) == 3
+    assert net.BLOCK_SIZE == ((32, 32) if 'unet' in kind else (1, 1))
+    if kind == 'densenet161unet':            # no ImageNet statistics without ImageNet weights (denseunet.py:146-148)
+        assert net.MEAN is None and net.STD is None
+    else:
+        assert len(net.MEAN) == 3 and len(net.STD) == 3
 
 
 def test_registry_names_and_unbuilt_architectures():
     g = GOLD['resnet101_deeplab_imagenet']
     assert sorted(na.seg.names()) == g['registry_names']
     with pytest.raises(NotImplementedError):
-        na.seg.get('densenet161unet')(2)
+        na.seg.get('resnet101_pspnet_imagenet')(21)        # needs the external mit_semseg package, like the reference
 
 
 def test_freeze_batchnorm_scope():

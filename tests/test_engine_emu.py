@@ -32,7 +32,7 @@ def emu():
 
 def _run(kind, n, h, w, classes, freeze, seed):
     torch.manual_seed(seed)
-    net = na.seg.get(kind)(classes, pretrained=False)
+    net = na.seg.get(kind)(classes) if kind == 'densenet161unet' else na.seg.get(kind)(classes, pretrained=False)
     sd = TO.synth_state_dict(net.state_dict(), seed=seed)
     net.load_state_dict(sd)
     net.train()
@@ -54,7 +54,10 @@ def _run(kind, n, h, w, classes, freeze, seed):
     for k, p in net.named_parameters():
         if p.requires_grad:
             sd64[k].requires_grad_(True)
-    if 'unet' in kind:
+    if kind == 'densenet161unet':
+        yo = TO.denseunet_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
+                                  dropout_masks=[dm.permute(0, 3, 1, 2).double()])
+    elif 'unet' in kind:
         yo = TO.resunet_forward(sd64, x.double(), backbone_bn_train=not freeze, head_bn_train=True,
                                 dropout_masks=[dm.permute(0, 3, 1, 2).double()])
     elif 'deeplabv3_' in kind:
@@ -136,6 +139,22 @@ def test_resnet50_unet_frozen_encoder_train_decoder(emu):
     nb = {k: int(v) for k, v in net.state_dict().items() if k.endswith('num_batches_tracked')}
     assert nb['final_dec_bn.num_batches_tracked'] == 1 and nb['decoder0.conv_bn.num_batches_tracked'] == 1
     assert nb['base_model.bn1.num_batches_tracked'] == 0
+
+
+def test_densenet161_unet_frozen_encoder_train_decoder(emu):
+    """architectures/denseunet.py (BASELINE config 4): concatenation buffers written slice by slice, stand-alone eval-mode
+    BatchNorms on channel prefixes with their gradients accumulated into the buffer's gradient, average-pool transitions."""
+    lerr, errs, stat, net = _run('densenet161unet', 2, 32, 64, 2, True, seed=2)
+    assert lerr < 1e-5
+    assert len(errs) == 503 - 2                           # base_model.classifier.{weight,bias} are never used
+    assert errs[-1] < 1e-4
+    assert stat < 1e-4
+    assert net.base_model.classifier.weight.grad is None
+    assert emu.calls.count('scale_channels') == 78 + 3 + 1        # norm1 of 78 dense layers, 3 transition norms, norm5
+    assert emu.calls.count('avgpool2x2') == 3 and emu.calls.count('avgpool2x2_bwd') == 3
+    with pytest.raises(NotImplementedError):              # a train-mode BatchNorm over a concatenation prefix is not built
+        net.train()
+        net(torch.randn(1, 3, 32, 32))
 
 
 def test_gradient_accumulation_over_two_backward_passes(emu):

@@ -20,7 +20,7 @@ G = os.path.join(HERE, 'golden')
 
 
 def _synth(kind, classes, seed, gain=1.0):
-    net = na.seg.get(kind)(classes, pretrained=False)
+    net = na.seg.get(kind)(classes) if kind == 'densenet161unet' else na.seg.get(kind)(classes, pretrained=False)
     final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'deeplab.classifier.4' in k
                                               or 'final_clf' in k) and k.endswith('weight')]
     return net, TO.synth_state_dict(net.state_dict(), seed=seed, logit_gain=gain, final_keys=final)
@@ -55,7 +55,8 @@ def test_loss_block_known_answers():
 @pytest.mark.parametrize('tag,kind,classes', [('dl2', 'resnet101_deeplab_imagenet', 21),
                                                ('dl3', 'resnet101_deeplabv3plus_imagenet', 19),
                                                ('dl3v3', 'resnet101_deeplabv3_imagenet', 21),
-                                               ('resunet50', 'resnet50unet_imagenet', 11)])
+                                               ('resunet50', 'resnet50unet_imagenet', 11),
+                                               ('denseunet', 'densenet161unet', 2)])
 def test_functional_nets_match_reference_modules(tag, kind, classes):
     """Forward logits and parameter gradients of the functional oracle == the reference nn.Modules."""
     z = np.load(os.path.join(G, 'net_%s.npz' % tag))
@@ -66,6 +67,8 @@ def test_functional_nets_match_reference_modules(tag, kind, classes):
     x = torch.from_numpy(z['x'])
     if tag == 'dl2':
         y = TO.deeplab2_forward(sd, x)
+    elif tag == 'denseunet':
+        y = TO.denseunet_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_masks=None)
     elif tag == 'resunet50':
         y = TO.resunet_forward(sd, x, backbone_bn_train=False, head_bn_train=True, dropout_masks=None)
     elif tag == 'dl3v3':       # torchvision's deeplabv3_resnet101 inside the reference's DeepLabv3Wrapper
@@ -81,7 +84,7 @@ def test_functional_nets_match_reference_modules(tag, kind, classes):
     if tag == 'dl3':
         for k in ('deeplab.classifier.project.1.running_mean', 'deeplab.classifier.project.1.running_var'):
             assert np.allclose(sd[k].numpy(), z[k], rtol=1e-5, atol=1e-6)
-    if tag == 'resunet50':
+    if tag in ('resunet50', 'denseunet'):
         for k in ('final_dec_bn.running_mean', 'final_dec_bn.running_var'):
             assert np.allclose(sd[k].numpy(), z[k], rtol=1e-5, atol=1e-6)
     if tag == 'dl3v3':
