@@ -55,13 +55,18 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
     print('Loaded data')
 
     NetClass = network_architectures.seg.get(arch)
-    student_net = NetClass(n_classes, pretrained=not no_pretrained).to(torch_device)
+    import inspect
+    takes_pretrained = 'pretrained' in inspect.signature(NetClass).parameters      # densenet161unet*(num_classes) do not
+
+    def build_net(pretrained):
+        return NetClass(n_classes, pretrained=pretrained) if takes_pretrained else NetClass(n_classes)
+    student_net = build_net(not no_pretrained).to(torch_device)
     # one fused launch for the optimiser step + the teacher's EMA step (cutmix_semisup_seg_b200/optim.py: torch's per-tensor
     # arithmetic incl. the duplicated DeepLab v2 group); B200SEG_FUSED_OPT=0 keeps torch.optim + the EMA kernel
     student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay,
                                             fused_kernel=os.environ.get('B200SEG_FUSED_OPT', '1') != '0')
     if model == 'mean_teacher':
-        teacher_net = NetClass(n_classes, pretrained=False).to(torch_device)
+        teacher_net = build_net(False).to(torch_device)
         for p in teacher_net.parameters():
             p.requires_grad = False
         teacher_optim = optim_weight_ema.EMAWeightOptimizer(teacher_net, student_net, teacher_alpha)

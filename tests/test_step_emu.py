@@ -285,6 +285,45 @@ def test_resnet50_unet_cutmix_iteration_batched_trunk(doubles):
     assert _state_gap(teacher, orc.teacher) < 1.5e-3
 
 
+def test_densenet161_unet_aug_consistency_iteration(doubles):
+    """BASELINE config 4: DenseNet-161 U-Net, 2 classes, augmentation-driven consistency (train_seg_semisup_aug_mt.py) -- one
+    iteration of the batched-trunk schedule (five trunk features, four of them concatenation buffers) against the oracle."""
+    import torch_oracle as TO
+    import ref_step
+    from _emu_backend import EmuEMA
+    from architectures import network_architectures as na
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    kind, c, lr, h, w = 'densenet161unet', 2, 1e-5, 32, 64
+    student = na.seg.get(kind)(c)
+    final = [k for k in student.state_dict() if 'final_clf' in k and k.endswith('weight')]
+    sd = TO.synth_state_dict(student.state_dict(), seed=3, logit_gain=4.0, final_keys=final)
+    student.load_state_dict(sd)
+    teacher = na.seg.get(kind)(c)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    student.final_dec_drop.p = teacher.final_dec_drop.p = 0.0          # the dropout draw cannot be shared with the oracle
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        optim = step_mod.make_optimizer(student, 'adam', lr)
+    ema = EmuEMA(teacher, student, 0.99)
+    student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+    trainer = step_mod.MeanTeacherStep(student, teacher, optim, ema, None, cons_loss_fn='var', cons_weight=0.7, conf_thresh=0.5,
+                                       conf_per_pixel=True)
+    assert trainer._can_batch_trunk([None])
+    orc = ref_step.OracleMeanTeacher('denseunet', sd, lr, cons_loss_fn='var', cons_weight=0.7, conf_thresh=0.5,
+                                     conf_per_pixel=True)
+    sup = synthetic.make_sup_batch(N, h, w, c, 10)
+    uns = synthetic.make_aug_batch(N, h, w, 20)
+    with torch.no_grad():
+        out = trainer.step(sup, [uns])
+    s_ref, c_ref, r_ref = orc.step(sup[0], sup[1], dict(uns))
+    assert float(out['sup_loss']) == pytest.approx(s_ref, rel=5e-5)
+    assert float(out['cons_loss']) == pytest.approx(c_ref, rel=2e-3, abs=1e-8)
+    assert float(out['conf_rate']) == pytest.approx(r_ref, abs=2.0 / (N * h * w))
+    assert _state_gap(student, orc.student) < 1.5e-3
+    assert _state_gap(teacher, orc.teacher) < 1.5e-3
+
+
 def test_vat_rejects_loss_functions_the_reference_rejects(doubles):
     student, teacher, trainer, orc, mg = _build('vat', False, True, cons_loss_fn='logits_smoothl1')
     sup, uns, uns_o = _batches('vat', mg, 0)
