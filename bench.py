@@ -1,7 +1,7 @@
 """Benchmark of the CutMix mean-teacher training iteration (BASELINE.json metric: images/sec at 512x512,
 bs=16 per GPU, DeepLab v3+ ResNet-101, 19 classes, synthetic Cityscapes-shaped data).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--arch v3plus|v2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--arch v3plus|v2|denseunet] [--loss ...]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 One "step" = one full iteration of train_seg_semisup_mask_mt.py:287-476: supervised forward/backward on N
@@ -31,9 +31,13 @@ CFG = {
                    workload='DeepLab v3+ ResNet-101, synthetic Cityscapes 512x512, 19 classes, CutMix mean teacher, bs 16/GPU'),
     'v2': dict(arch='resnet101_deeplab_imagenet', classes=21, h=321, w=321, batch=16, lr=3e-5,
                workload='DeepLab v2 ResNet-101, synthetic Pascal-Aug 321x321, 21 classes, CutMix mean teacher, bs 16/GPU'),
+    # BASELINE config 4 (run it with --loss aug: train_seg_semisup_aug_mt.py on the DenseNet-161 U-Net)
+    'denseunet': dict(arch='densenet161unet', classes=2, h=224, w=224, batch=16, lr=1e-5,
+                      workload='DenseNet-161 U-Net, synthetic ISIC2017 224x224, 2 classes, CutMix mean teacher, bs 16/GPU'),
 }
 # forward conv FLOPs per image (2*MAC, dense), stem FLOPs: SURVEY.md §8 / BASELINE.md §2
-FLOPS = {'v3plus': (520.28e9, 1.233e9), 'v2': (147.67e9, 0.488e9)}
+FLOPS = {'v3plus': (520.28e9, 1.233e9), 'v2': (147.67e9, 0.488e9),
+         'denseunet': (37.15e9, 0.354e9)}      # counted from the graph's convolution launches (K un-padded), 224x224
 
 
 def committed_traffic(kernel):
@@ -120,10 +124,12 @@ def build_trainer(cfg, device, dist_on, use_graph=True):
     from cutmix_semisup_seg_b200 import step as step_mod, synthetic
     torch.manual_seed(0)
     Net = network_architectures.seg.get(cfg['arch'])
-    student = Net(cfg['classes'], pretrained=False)
+    import inspect
+    kw = dict(pretrained=False) if 'pretrained' in inspect.signature(Net).parameters else {}
+    student = Net(cfg['classes'], **kw)
     synthetic.condition_classifier(student, 40.0)
     student = student.to(device)
-    teacher = Net(cfg['classes'], pretrained=False).to(device)
+    teacher = Net(cfg['classes'], **kw).to(device)
     for p in teacher.parameters():
         p.requires_grad = False
     optim = step_mod.make_optimizer(student, 'adam', cfg['lr'], capturable=use_graph,
@@ -310,10 +316,14 @@ def _oracle_trainer(cfg, arch_key):
     import torch_oracle as TO
     from architectures import network_architectures
     import mask_gen
-    net = network_architectures.seg.get(cfg['arch'])(cfg['classes'], pretrained=False)      # shapes/keys only
-    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k) and k.endswith('weight')]
+    import inspect
+    ctor = network_architectures.seg.get(cfg['arch'])
+    kw = dict(pretrained=False) if 'pretrained' in inspect.signature(ctor).parameters else {}
+    net = ctor(cfg['classes'], **kw)                                                        # shapes/keys only
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'final_clf' in k)
+             and k.endswith('weight')]
     sd = TO.synth_state_dict(net.state_dict(), seed=0, logit_gain=40.0, final_keys=final)
-    tr = ref_step.OracleMeanTeacher('deeplab3plus' if arch_key == 'v3plus' else 'deeplab2', sd, cfg['lr'])
+    tr = ref_step.OracleMeanTeacher({'v3plus': 'deeplab3plus', 'v2': 'deeplab2', 'denseunet': 'denseunet'}[arch_key], sd, cfg['lr'])
     mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
                                    within_bounds=True, invert=True)
     return tr, mg
@@ -377,7 +387,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2'])
+    ap.add_argument('--arch', default='v3plus', choices=['v3plus', 'v2', 'denseunet'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict', 'aug', 'vat'],
                     help='unsupervised branch: CutMix (the headline workload), ICT (train_seg_semisup_ict.py), augmentation '

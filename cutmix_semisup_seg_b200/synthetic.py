@@ -142,5 +142,6 @@ def condition_classifier(net, gain):
     on random inputs (random-init networks give conf_rate == 0, i.e. a vacuous consistency loss)."""
     with torch.no_grad():
         for name, p in net.named_parameters():
-            if (name.startswith('layer5.') or 'classifier.classifier.6' in name) and p.dim() == 4:
+            if (name.startswith('layer5.') or 'classifier.classifier.6' in name or name.startswith('deeplab.classifier.4.')
+                    or name.startswith('final_clf.')) and p.dim() == 4:
                 p.mul_(gain)

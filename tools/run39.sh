@@ -18,6 +18,9 @@ for loss in cutmix aug vat; do
 import json,sys
 d=json.loads(sys.stdin.read()); print('$loss', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['clocks'])" 2>/dev/null || tail -3 gpurun_out/bench_r39_$loss.log | cut -c1-300
 done
+# 3b. BASELINE config 4: DenseNet-161 U-Net, 224x224, augmentation consistency
+B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 400 python bench.py --steps 10 --warmup 3 --arch denseunet --loss aug > gpurun_out/bench_r39_config4.log 2>&1
+echo "[bench exit $?]" >> gpurun_out/bench_r39_config4.log; tail -2 gpurun_out/bench_r39_config4.log | cut -c1-400
 # 4. one ncu --set full capture of the new loss kernel (tests drive it at C = 19 / 21)
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:aug_consistency_kernel -c 2 \
   -o gpurun_out/aug_r39 python -m pytest tests/test_zz_gpu_aug.py -m gpu -q -k "class_counts and var" > gpurun_out/ncu_aug_r39.log 2>&1
