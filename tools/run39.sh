@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/run39.sh'
 mkdir -p gpurun_out
 # 1. the binding form of the two pending test files (non-strict xfail marker off)
-B200SEG_AUG_VERIFIED=1 B200SEG_VAT_VERIFIED=1 B200SEG_DL3_VERIFIED=1 B200SEG_UNET_VERIFIED=1 timeout -s KILL 900 python -m pytest tests/test_zz_gpu_aug.py tests/test_zz_gpu_vat.py tests/test_zz_gpu_deeplab3.py tests/test_zz_gpu_resunet.py tests/test_zz_gpu_denseunet.py tests/test_zzz_gpu_input.py -m gpu -q \
+B200SEG_AUG_VERIFIED=1 B200SEG_VAT_VERIFIED=1 B200SEG_DL3_VERIFIED=1 B200SEG_UNET_VERIFIED=1 timeout -s KILL 900 python -m pytest tests/test_zz_gpu_aug.py tests/test_zz_gpu_vat.py tests/test_zzy_gpu_deeplab3.py tests/test_zzy_gpu_resunet.py tests/test_zzy_gpu_denseunet.py tests/test_zzz_gpu_input.py -m gpu -q \
   > gpurun_out/pytest_r39_aug_vat.log 2>&1; echo "[pytest exit $?]" >> gpurun_out/pytest_r39_aug_vat.log
 tail -4 gpurun_out/pytest_r39_aug_vat.log | cut -c1-200; grep -E "^E  *assert|^FAILED|Error" gpurun_out/pytest_r39_aug_vat.log | head -20 | cut -c1-250
 # 2. loss-kernel regression (the per-pixel loss tail was factored out of consistency_kernel; SASS instruction mix unchanged)
