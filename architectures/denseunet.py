@@ -12,8 +12,8 @@ parameter-group methods, and the graph on the sm_100a kernels:
   * transitions: stand-alone norm + ReLU, 1x1 convolution, 2x2 average pool written into the next block's buffer;
   * the gradient of a concatenation buffer is accumulated prefix by prefix (engine.Tape.contribute_slice).
 
-The encoder's BatchNorms must be in eval mode (`freeze_batchnorm()`, or `.eval()`): a train-mode BatchNorm over a
-concatenation prefix is not built.  Input sizes must be multiples of 32 (BLOCK_SIZE), like the reference."""
+Without `freeze_batchnorm()` the encoder's norms run in train mode through the batch-statistics kernels (one statistics pass
+per norm over its concatenation prefix).  Input sizes must be multiples of 32 (BLOCK_SIZE), like the reference."""
 from collections import OrderedDict
 
 import numpy as np

@@ -354,7 +354,10 @@ class BNTrainNode(object):
             K.copy_act(dyd, dy)
         K.bn_bwd(dyd, self.raw, self.y, self.mean, self.rstd, bn.weight, self.relu, self.dropmask, self.drop_scale, dx,
                  dgam, dbet, acc, g_out=g_out)
-        tape.contribute_tensor(self.raw, dx)
+        if self.raw.parent is not None:      # input = a channel prefix of a concatenation buffer (DenseNet norm1, train mode)
+            tape.contribute_slice(self.raw, lambda dst, accumulate: K.copy_act(dst, dx, accumulate=accumulate))
+        else:
+            tape.contribute_tensor(self.raw, dx)
         if self.residual is not None:
             tape.contribute_tensor(self.residual, g_out)
 
@@ -716,10 +719,10 @@ _IDENTITY_STATS = {}
 
 
 def bn_eval_act(tape, x, bn, relu=True):
-    """Stand-alone eval-mode BatchNorm (+ReLU) of an activation or of a channel slice of one; returns a dense activation."""
-    if bn.training:
-        raise NotImplementedError('stand-alone train-mode BatchNorm on a concatenation (DenseNet encoders are run with '
-                                  'freeze_batchnorm(), like the reference recipes)')
+    """Stand-alone BatchNorm (+ReLU) of an activation or of a channel slice of one (DenseNet's pre-activation norms); returns a
+    dense activation.  Eval mode: folded scale / shift in one pass; train mode: the statistics + apply kernels."""
+    if bn.training:          # batch statistics over the (slice of the) concatenation: the train-mode BN path, dense output
+        return bn_train(tape, x, bn, relu=relu)
     K = tape.K
     scale, shift = fold_bn(tape, bn)
     key = (K.name, x.c, str(x.device))
