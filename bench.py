@@ -237,6 +237,44 @@ def run_b200(args):
     sync_all()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- optional: the same end-to-end loop with uint8 batches crossing PCIe: images as HWC uint8, labels
+    # and valid masks as uint8, standardised / widened on the device by csrc/input.cu (DeviceNormalizeToTensor)
+    e2e_u8 = None
+    if args.u8_inputs and args.loss == 'cutmix':
+        from cutmix_semisup_seg_b200 import input_pipeline
+        norm = input_pipeline.DeviceNormalizeToTensor([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+
+        def to_u8_img(t):        # synthetic standardised images -> plausible uint8 pixels (HWC), pinned
+            return (t * 58.0 + 116.0).clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+        u8_pool = []
+        for i in range(pool):
+            sx, sy = sup_host[i]
+            ub = uns_host[i]
+            u8_pool.append(dict(sup=dict(image_arr=to_u8_img(sx), labels_arr=sy[:, 0].to(torch.uint8).pin_memory()),
+                                v0=dict(image_arr=to_u8_img(ub['ux0_tea']), mask_arr=(ub['um0'][:, 0] * 255).to(torch.uint8).pin_memory()),
+                                v1=dict(image_arr=to_u8_img(ub['ux1_tea']), mask_arr=(ub['um1'][:, 0] * 255).to(torch.uint8).pin_memory()),
+                                mask_params=ub['mask_params']))
+        h2d_u8 = sum(t.numel() * t.element_size() for d in (u8_pool[0]['sup'], u8_pool[0]['v0'], u8_pool[0]['v1']) for t in d.values()) \
+            + u8_pool[0]['mask_params'].numel() * u8_pool[0]['mask_params'].element_size()
+
+        def u8_step(b):
+            s_ = norm(b['sup']); a0 = norm(b['v0']); a1 = norm(b['v1'])
+            uns = dict(ux0_tea=a0['image'], ux0_stu=a0['image'], um0=a0['mask'], ux1_tea=a1['image'], ux1_stu=a1['image'],
+                       um1=a1['mask'], mask_params=b['mask_params'].to(device, non_blocking=True))
+            return trainer.step((s_['image'], s_['labels']), [uns])
+        for i in range(2):
+            u8_step(u8_pool[i % pool])
+        sync_all()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for i in range(args.steps):
+            o = u8_step(u8_pool[i % pool])
+            torch.stack([o['sup_loss'], o['cons_loss'], o['conf_rate']]).cpu()
+        u1.record()
+        sync_all()
+        e2e_u8 = {'value': round(n * world / (u0.elapsed_time(u1) / args.steps / 1e3), 3), 'unit': 'images/s',
+                  'h2d_bytes_per_step': int(h2d_u8), 'note': 'uint8 batches, normalise-to-tensor on the device; no prefetch overlap'}
+
     # ---- per-kernel roofline (instrumented iteration outside the timed regions)
     # every rank runs it (the iteration contains the gradient all-reduce); only rank 0 reports
     prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0])
@@ -274,6 +312,7 @@ def run_b200(args):
         'e2e': {'value': round(n * world / (ms_e2e / args.steps / 1e3), 3), 'unit': 'images/s',
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
         'gpu_launches': int(launches),
+        **({'e2e_u8': e2e_u8} if e2e_u8 is not None else {}),
         'last_step': last,
     }
     if prof:
@@ -392,6 +431,8 @@ def main():
     ap.add_argument('--loss', default='cutmix', choices=['cutmix', 'ict', 'aug', 'vat'],
                     help='unsupervised branch: CutMix (the headline workload), ICT (train_seg_semisup_ict.py), augmentation '
                          'consistency (train_seg_semisup_aug_mt.py) or VAT (train_seg_semisup_vat_mt.py)')
+    ap.add_argument('--u8-inputs', dest='u8_inputs', action='store_true',
+                    help='also time the end-to-end loop with uint8 batches normalised on the device (extra key e2e_u8)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -21,6 +21,8 @@ done
 # 3b. BASELINE config 4: DenseNet-161 U-Net, 224x224, augmentation consistency
 B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 400 python bench.py --steps 10 --warmup 3 --arch denseunet --loss aug > gpurun_out/bench_r39_config4.log 2>&1
 echo "[bench exit $?]" >> gpurun_out/bench_r39_config4.log; tail -2 gpurun_out/bench_r39_config4.log | cut -c1-400
+# 3c. uint8 batches across PCIe (extra key e2e_u8)
+B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 400 python bench.py --steps 10 --warmup 3 --u8-inputs > gpurun_out/bench_r39_u8.log 2>&1; tail -1 gpurun_out/bench_r39_u8.log | cut -c1-200
 # 4. one ncu --set full capture of the new loss kernel (tests drive it at C = 19 / 21)
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:aug_consistency_kernel -c 2 \
   -o gpurun_out/aug_r39 python -m pytest tests/test_zz_gpu_aug.py -m gpu -q -k "class_counts and var" > gpurun_out/ncu_aug_r39.log 2>&1
