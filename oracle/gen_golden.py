@@ -390,10 +390,14 @@ def gen_sibling_iterations():
     crit = nn.CrossEntropyLoss(ignore_index=255)
     for mode, kind, classes, lr, gain in (('aug', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0),
                                           ('vat', 'resnet101_deeplabv3plus_imagenet', 19, 1e-5, 4.0),
-                                          ('ict', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0)):
-        n, h, w = 2, 33, 33
+                                          ('ict', 'resnet101_deeplab_imagenet', 21, 3e-5, 4.0),
+                                          ('aug_config4', 'densenet161unet', 2, 1e-5, 4.0)):      # BASELINE config 4
+        run = mode
+        mode = mode.split('_')[0]
+        n, h, w = (2, 32, 64) if run == 'aug_config4' else (2, 33, 33)
         student = build(kind, classes, seed=3, gain=gain)
-        teacher = network_architectures.seg.get(kind)(classes, pretrained=False)
+        teacher = (network_architectures.seg.get(kind)(classes) if kind == 'densenet161unet'
+                   else network_architectures.seg.get(kind)(classes, pretrained=False))
         for p in teacher.parameters():
             p.requires_grad = False
         for net in (student, teacher):
@@ -442,10 +446,11 @@ def gen_sibling_iterations():
                 teacher_training=bool(teacher.training), student_training=bool(student.training),
                 teacher_abs_sum=float(sum(v.double().abs().sum() for v in tsd.values() if v.dtype == torch.float32)),
                 student_abs_sum=float(sum(v.double().abs().sum() for v in ssd.values() if v.dtype == torch.float32)),
-                student_conv1_sum=float(ssd['deeplab.backbone.conv1.weight' if mode == 'vat' else 'conv1.weight'].double().sum())))
+                student_conv1_sum=float(ssd[{'vat': 'deeplab.backbone.conv1.weight', 'aug_config4': 'base_model.features.conv0.weight'}
+                                            .get(run, 'conv1.weight')].double().sum())))
             if mode == 'ict':
                 rec['steps'][-1]['factors'] = [float(v) for v in ns['ict_mix_factors'].reshape(-1)]
-        out['runs'][mode] = rec
+        out['runs'][run] = rec
     json.dump(out, open(os.path.join(OUT, 'sibling_iterations.json'), 'w'), indent=1)
 
 

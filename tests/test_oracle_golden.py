@@ -273,23 +273,24 @@ def test_vat_kernel_algorithms_match_torch():
         assert float(lhs) == pytest.approx(float(rhs), rel=1e-6)
 
 
-@pytest.mark.parametrize('mode', ['aug', 'vat', 'ict'])
-def test_sibling_iterations_match_reference_loops(mode):
+@pytest.mark.parametrize('run', ['aug', 'vat', 'ict', 'aug_config4'])
+def test_sibling_iterations_match_reference_loops(run):
     """Two iterations of the oracle's augmentation-consistency / VAT loop == the reference's classes driven by the reference
     scripts' own unsupervised-branch lines (oracle/gen_golden.py::gen_sibling_iterations): losses, confidence rate, post-step
     student and teacher state, and the train / eval mode the reference leaves the networks in."""
     sys.path.insert(0, HERE)
     from aug_recipe import affine_thetas
     from vat_recipe import vat_noise
-    gold = json.load(open(os.path.join(G, 'sibling_iterations.json')))['runs'][mode]
+    mode = run.split('_')[0]          # 'aug_config4': BASELINE config 4, the aug loop on the DenseNet-161 U-Net
+    gold = json.load(open(os.path.join(G, 'sibling_iterations.json')))['runs'][run]
     n, h, w, c = gold['n'], gold['h'], gold['w'], gold['classes']
     net, sd = _synth(gold['kind'], c, seed=gold['seed'], gain=gold['gain'])
-    arch = 'deeplab3plus' if mode == 'vat' else 'deeplab2'
+    arch = {'vat': 'deeplab3plus', 'aug_config4': 'denseunet'}.get(run, 'deeplab2')
     tr = ref_step.OracleMeanTeacher(arch, sd, gold['lr'], cons_loss_fn=gold['cons_loss_fn'], cons_weight=gold['cons_weight'],
                                     conf_thresh=gold['conf_thresh'], conf_per_pixel=gold['conf_per_pixel'],
                                     vat_radius=gold['vat_radius'], adaptive_vat_radius=gold['adaptive_vat_radius'])
     tr.start_epoch()
-    conv1 = 'deeplab.backbone.conv1.weight' if mode == 'vat' else 'conv1.weight'
+    conv1 = {'vat': 'deeplab.backbone.conv1.weight', 'aug_config4': 'base_model.features.conv0.weight'}.get(run, 'conv1.weight')
     for it, exp in enumerate(gold['steps']):
         g = torch.Generator().manual_seed(300 + it)
         sup_x = torch.randn((n, 3, h, w), generator=g)
