@@ -274,21 +274,23 @@ def test_multi_batch_needs_frozen_trunk(emu):
 
 
 @pytest.mark.parametrize('kind,classes,student', [('resnet101_deeplab_imagenet', 21, False),
-                                                  ('resnet101_deeplabv3plus_imagenet', 19, True)])
+                                                  ('resnet101_deeplabv3plus_imagenet', 19, True),
+                                                  ('densenet161unet', 2, True)])
 def test_input_gradient_only_backward_matches_autograd(emu, kind, classes, student):
     """VAT's direction pass (train_seg_semisup_vat_mt.py:237-268): eval-mode network, d(loss)/d(image) through the stem
     (data-gradient GEMM over the im2col matrix + col2im), no parameter gradient -- also for a network whose parameters
     require gradients (`--vat_dir_from_student`)."""
     torch.manual_seed(3)
-    net = na.seg.get(kind)(classes, pretrained=False)
+    net = na.seg.get(kind)(classes) if kind == 'densenet161unet' else na.seg.get(kind)(classes, pretrained=False)
     sd = TO.synth_state_dict(net.state_dict(), seed=7)
     net.load_state_dict(sd)
     if not student:
         for p in net.parameters():
             p.requires_grad = False
     net.eval()
-    x = torch.randn(2, 3, 33, 41)
-    dy = torch.randn(2, classes, 33, 41)
+    hw = (32, 64) if 'unet' in kind else (33, 41)
+    x = torch.randn(2, 3, *hw)
+    dy = torch.randn(2, classes, *hw)
     with torch.no_grad():          # the engine never uses autograd; the torch-CPU doubles would otherwise record a graph
         logits, state = net.b2_forward(x, record=True, input_grad=True)
         dx = net.b2_backward(state, dy, param_grads=False)
@@ -296,7 +298,9 @@ def test_input_gradient_only_backward_matches_autograd(emu, kind, classes, stude
     assert emu.calls.count('col2im') == 1 and emu.calls.count('conv_wgrad') == 0
     sd64 = OrderedDict((k, v.double().clone() if v.dtype == torch.float32 else v.clone()) for k, v in sd.items())
     x64 = x.double().requires_grad_(True)
-    if 'v3plus' in kind:
+    if kind == 'densenet161unet':
+        yo = TO.denseunet_forward(sd64, x64, backbone_bn_train=False, head_bn_train=False)
+    elif 'v3plus' in kind:
         yo = TO.deeplab3plus_forward(sd64, x64, backbone_bn_train=False, head_bn_train=False)
     else:
         yo = TO.deeplab2_forward(sd64, x64, bn_train=False)
