@@ -44,6 +44,29 @@ HOT_PATH = [
 ]
 
 
+# weight-gradient shapes of the architectures added after the last GPU run (DeepLab v3 head, ResNet U-Net decoder, DenseNet-161
+# U-Net at 224x224 / batch 16 or 32 in the batched trunk): Cin = 96 + 48 k is not a multiple of 32, Cout = 48 / 192 / 1056 / 2208
+NEW_ARCH = [
+    (16, 64, 64, 256, 256, 3, 1, 1), (16, 64, 64, 21, 256, 1, 1, 0),                                   # DeepLab v3 head
+    (16, 16, 16, 1024, 2048, 1, 1, 0), (16, 32, 32, 512, 1024, 3, 1, 1), (16, 64, 64, 256, 512, 3, 1, 1),      # ResNet U-Net
+    (16, 128, 128, 64, 256, 3, 1, 1), (16, 256, 256, 64, 64, 3, 1, 1), (16, 512, 512, 64, 64, 3, 1, 1), (16, 512, 512, 11, 64, 1, 1, 0),
+    (1, 1, 32 * 56 * 56, 192, 96, 1, 1, 0), (1, 1, 32 * 56 * 56, 192, 336, 1, 1, 0), (32, 56, 56, 48, 192, 3, 1, 1),       # dense block 1
+    (1, 1, 32 * 56 * 56, 192, 384, 1, 1, 0), (1, 1, 32 * 28 * 28, 192, 720, 1, 1, 0), (32, 28, 28, 48, 192, 3, 1, 1),      # transition 1, block 2
+    (1, 1, 32 * 14 * 14, 192, 2064, 1, 1, 0), (1, 1, 32 * 14 * 14, 1056, 2112, 1, 1, 0), (32, 14, 14, 48, 192, 3, 1, 1),   # block 3, transition 3
+    (1, 1, 32 * 7 * 7, 192, 2160, 1, 1, 0), (32, 7, 7, 48, 192, 3, 1, 1),                              # block 4
+    (1, 1, 16 * 14 * 14, 2208, 2112, 1, 1, 0), (16, 14, 14, 768, 2208, 3, 1, 1), (16, 28, 28, 384, 768, 3, 1, 1),          # line0, decoder
+    (16, 56, 56, 96, 384, 3, 1, 1), (16, 112, 112, 96, 96, 3, 1, 1), (16, 224, 224, 64, 96, 3, 1, 1), (16, 224, 224, 2, 64, 1, 1, 0),
+    (1, 1, 32 * 112 * 112, 96, 160, 1, 1, 0),                                                          # DenseNet stem (im2col, K padded to 160)
+]
+
+
+@pytest.mark.parametrize('shape', NEW_ARCH)
+def test_new_architecture_shapes_have_consistent_stage_counts(shape):
+    for n_split, kchunk in ((1, 0), (3, 1024)):                      # throughput mode and the 3xTF32 parity mode
+        splits, units, stages, bad, pair = _check(*shape, n_split=n_split, kchunk=kchunk)
+        assert bad == 0 and units >= 1 and splits >= 1 and stages >= units, (shape, n_split)
+
+
 @pytest.mark.parametrize('shape', HOT_PATH)
 def test_hot_path_shapes_have_consistent_stage_counts(shape):
     splits, units, stages, bad, pair = _check(*shape)
