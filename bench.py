@@ -117,7 +117,7 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def build_trainer(cfg, device, dist_on, use_graph=True):
+def build_trainer(cfg, device, dist_on, use_graph=True, precision='tf32'):
     from architectures import network_architectures
     import mask_gen
     import optim_weight_ema
@@ -130,6 +130,7 @@ def build_trainer(cfg, device, dist_on, use_graph=True):
     synthetic.condition_classifier(student, 40.0)
     student = student.to(device)
     teacher = Net(cfg['classes'], **kw).to(device)
+    student.b2_precision = teacher.b2_precision = precision        # 'tf32' (one tensor-core pass) | '3xtf32' (parity mode)
     for p in teacher.parameters():
         p.requires_grad = False
     optim = step_mod.make_optimizer(student, 'adam', cfg['lr'], capturable=use_graph,
@@ -156,6 +157,157 @@ def timed_conv_profile(trainer, sup, unsup):
     return be.stop_profile()
 
 
+def _release():
+    """After the caller dropped its trainer (CUDA graphs, tens of GB of graph-private activations): return the memory before
+    the next leg builds its own."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def timed_steps(trainer, sup_dev, uns_dev, steps, warmup, sync_all):
+    """W untimed + K timed iterations with inputs resident in HBM; CUDA events on the launching stream."""
+    pool = len(sup_dev)
+    for i in range(warmup):
+        out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = trainer.be.launches
+    t_start = time.time()
+    ev0.record()
+    for i in range(steps):
+        out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
+    ev1.record()
+    t_enq = time.time()
+    sync_all()
+    return ev0.elapsed_time(ev1), trainer.be.launches - launches0, out, (t_enq - t_start)
+
+
+def parity_block(device):
+    """Losses of the full-size cfg3 parity iterations (tests/fullsize_recipe.py: DeepLab v3+, N = 16, 512 x 512, seeded weights /
+    batches / dropout masks) in the precision this bench times (single-pass TF32) and in the parity mode (3xTF32), next to the
+    values the UNMODIFIED reference modules produced on the CPU (tests/golden/fullsize_cfg3.npz, committed fixture written by
+    oracle/gen_golden_fullsize.py).  Eager iterations outside every timed region."""
+    import warnings
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import fullsize_recipe as R
+    from architectures import network_architectures
+    import mask_gen
+    import optim_weight_ema
+    from cutmix_semisup_seg_b200 import step as step_mod, synthetic
+    name = 'cfg3'
+    path = os.path.join(ROOT, 'tests', 'golden', 'fullsize_%s.npz' % name)
+    if not os.path.exists(path):
+        return {'unavailable': 'tests/golden/fullsize_%s.npz missing' % name}
+    gold = np.load(path)
+    cfg = R.CONFIGS[name]
+    ref = {k: [float(v) for v in np.atleast_1d(gold[k])] for k in ('sup_loss', 'cons_loss', 'conf_rate')}
+    out = {'config': 'DeepLab v3+ ResNet-101, N = {n}, {h}x{w}, {classes} classes, conf_thresh {conf_thresh}, Adam lr {lr}, '
+                     '{iters} consecutive iterations, injected dropout masks'.format(**cfg),
+           'reference': dict(ref, source='tests/golden/fullsize_cfg3.npz: unmodified reference modules, torch CPU fp32')}
+    runs = {}
+    for precision in ('tf32', '3xtf32'):
+        Net = network_architectures.seg.get(cfg['kind'])
+        student = Net(cfg['classes'], pretrained=False)
+        sd = synthetic.synth_state_dict(student.state_dict(), seed=cfg['seed'], logit_gain=cfg['gain'],
+                                        final_keys=R.final_keys(student.state_dict(), cfg))
+        student.load_state_dict(sd)
+        teacher = Net(cfg['classes'], pretrained=False)
+        student.to(device); teacher.to(device)
+        student.b2_precision = teacher.b2_precision = precision
+        for p in teacher.parameters():
+            p.requires_grad = False
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            optim = step_mod.make_optimizer(student, 'adam', cfg['lr'], fused_kernel=True)
+        ema = optim_weight_ema.EMAWeightOptimizer(teacher, student, 0.99)
+        student.train(); teacher.train(); student.freeze_batchnorm(); teacher.freeze_batchnorm()
+        mg = mask_gen.BoxMaskGenerator(0.5, invert=True)
+        tr = step_mod.MeanTeacherStep(student, teacher, optim, ema, mg, conf_thresh=cfg['conf_thresh'])
+        vals = {'sup_loss': [], 'cons_loss': [], 'conf_rate': []}
+        for it in range(cfg['iters']):
+            (sx, sy), uns = R.batches(cfg, mg, compact_masks=True, it=it)
+            dm = R.dropout_masks(cfg, it)
+            for net, keys in ((student, ('sup', 'stu')), (teacher, ('tea0', 'tea1'))):
+                drop = [m for m in net.modules() if type(m).__name__ == 'B2Dropout'][0]
+                drop.inject([dm[k] for k in keys])
+            o = tr.step((sx.to(device), sy.to(device)), [{k: v.to(device) for k, v in uns.items()}])
+            for k in vals:
+                vals[k].append(float(o[k]))
+        runs[precision] = vals
+        tr = student = teacher = optim = ema = None
+        _release()
+
+    def dev(a, b):
+        return {'sup_loss_rel': max(abs(x - y) / abs(y) for x, y in zip(a['sup_loss'], b['sup_loss'])),
+                'cons_loss_rel': max(abs(x - y) / abs(y) for x, y in zip(a['cons_loss'], b['cons_loss'])),
+                'conf_rate_abs': max(abs(x - y) for x, y in zip(a['conf_rate'], b['conf_rate']))}
+    for precision in runs:
+        out[precision] = dict(runs[precision], max_dev_vs_reference=dev(runs[precision], ref))
+    out['tf32_vs_3xtf32'] = dev(runs['tf32'], runs['3xtf32'])
+    return out
+
+
+def incumbent_cudnn(args, cfg, device, n, steps):
+    """The honest incumbent (BASELINE.md section 3 "Also reported"): the reference's own path -- ATen / cuDNN convolutions under
+    torch.autograd, torch.optim.Adam, the EMA loop -- on THIS GPU: oracle/ref_step.py (the line-for-line restatement of
+    train_seg_semisup_mask_mt.py:287-476 on functional torch networks, pinned to the reference by tests/golden/) with its
+    state on the device.  Reported next to `value`; none of this repository's kernels run in it.  Three settings: the stock
+    one (cudnn.allow_tf32 = True, PyTorch's default, cudnn.benchmark = False as the reference never sets it), full fp32
+    (allow_tf32 = False) and stock + cudnn.benchmark = True (cuDNN's autotuned best)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_step
+    import inspect
+    from architectures import network_architectures
+    import mask_gen
+    from cutmix_semisup_seg_b200 import synthetic
+    ctor = network_architectures.seg.get(cfg['arch'])
+    kw = dict(pretrained=False) if 'pretrained' in inspect.signature(ctor).parameters else {}
+    net = ctor(cfg['classes'], **kw)
+    final = [k for k in net.state_dict() if ('layer5' in k or 'classifier.classifier.6' in k or 'final_clf' in k) and k.endswith('weight')]
+    sd = synthetic.synth_state_dict(net.state_dict(), seed=0, logit_gain=12.0, final_keys=final)
+    del net
+    arch = {'v3plus': 'deeplab3plus', 'v2': 'deeplab2', 'denseunet': 'denseunet'}[args.arch]
+    mg = mask_gen.BoxMaskGenerator(prop_range=0.5, n_boxes=1, random_aspect_ratio=True, prop_by_area=True,
+                                   within_bounds=True, invert=True)
+    h, w = cfg['h'], cfg['w']
+    sup = synthetic.make_sup_batch(n, h, w, cfg['classes'], 100, device=device)
+    uns = synthetic.make_unsup_batch(n, h, w, 200, mg, compact_masks=False, device=device)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    res = {'what': 'reference path (ATen/cuDNN + autograd + torch.optim.Adam(foreach=False) + EMA loop, NCHW fp32 tensors) on the same '
+                   'B200, batch {} at {}x{}'.format(n, h, w), 'unit': 'images/s', 'steps': steps}
+    try:
+        for tag, tf32, bench in (('tf32_stock', True, False), ('fp32', False, False), ('tf32_cudnn_benchmark', True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = bench
+            tr = ref_step.OracleMeanTeacher(arch, {k: v.to(device) for k, v in sd.items()}, cfg['lr'])
+
+            def drop():
+                if arch != 'deeplab3plus':
+                    return None
+                mk = lambda: [(torch.rand((n, 256, -(-h // 8), -(-w // 8)), device=device) > 0.5).float()]   # noqa: E731
+                return {'sup': mk(), 'tea0': mk(), 'tea1': mk(), 'stu': mk()}
+            for _ in range(2):
+                tr.step(sup[0], sup[1], uns, drop=drop())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                last = tr.step(sup[0], sup[1], uns, drop=drop())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[tag] = {'value': round(n / (ms / 1e3), 3), 'ms_per_step': round(ms, 2), 'last_losses': [round(float(v), 6) for v in last]}
+            tr = None
+            _release()
+    except Exception as e:      # keep the bench line if torch's own path fails (e.g. out of memory)
+        res['failed'] = repr(e)[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return res
+
+
 def run_b200(args):
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -173,7 +325,7 @@ def run_b200(args):
     from cutmix_semisup_seg_b200 import synthetic
     cfg = CFG[args.arch]
     n, h, w = args.batch or cfg['batch'], cfg['h'], cfg['w']
-    trainer, mg = build_trainer(cfg, device, dist_on, use_graph=not args.eager)
+    trainer, mg = build_trainer(cfg, device, dist_on, use_graph=not args.eager, precision=args.precision)
     be = trainer.be
     # a small pool of distinct batches (per-iteration working set >> 126 MB L2: activations alone are ~20 GB)
     pool = 3
@@ -202,19 +354,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = be.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_start = time.time()
-    ev0.record()
-    for i in range(args.steps):
-        out = trainer.step(sup_dev[i % pool], [uns_dev[i % pool]])
-    ev1.record()
-    t_enq = time.time()
-    sync_all()
-    t_done = time.time()
-    ms = ev0.elapsed_time(ev1)
-    launches = be.launches - launches0
+    ms, launches, out, enq_s = timed_steps(trainer, sup_dev, uns_dev, args.steps, 0, sync_all)
     clocks = sampler.stop() if rank == 0 else None
     last = {k: float(v) for k, v in out.items() if v is not None}
 
@@ -280,6 +420,22 @@ def run_b200(args):
     prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0])
     if rank != 0:
         prof = None
+    shape_profile = getattr(be, 'last_shape_profile', None)
+    optim_note = trainer.optim_note
+    trunk_batched = trainer._can_batch_trunk([None])
+    trainer = None
+    _release()
+
+    # ---- the other precision mode on the same workload (fewer steps: it only has to place the parity mode's cost)
+    other = None
+    other_mode = '3xtf32' if args.precision == 'tf32' else 'tf32'
+    if not args.no_second_precision and world == 1:
+        tr2, _ = build_trainer(cfg, device, dist_on, use_graph=not args.eager, precision=other_mode)
+        k2 = max(3, min(args.steps, 5))
+        ms2, _, out2, _ = timed_steps(tr2, sup_dev, uns_dev, k2, 3, sync_all)
+        other = (ms2 / k2, k2, {k: float(v) for k, v in out2.items() if v is not None})
+        tr2 = None
+        _release()
 
     if dist_on:
         t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
@@ -299,14 +455,18 @@ def run_b200(args):
     res = {
         'metric': 'images/sec', 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
         'config': {'workload': cfg['workload'].replace('CutMix', {'ict': 'ICT', 'aug': 'augmentation-consistency', 'vat': 'VAT'}.get(args.loss, 'CutMix')),
                    'global_batch': n * world, 'crop': [h, w], 'parallelism': 'dp%d' % world,
+                   'precision': {'tf32': 'single-pass kind::tf32 tensor-core products, fp32 accumulate (PyTorch / cuDNN default for '
+                                         'convolutions); parity of this mode: see `parity`',
+                                 '3xtf32': 'three tensor-core passes over hi/lo operand splits (~fp32 products): the mode the tight '
+                                           'parity tests run in'}[args.precision],
                    'l2': 'per-iteration working set (activations ~GBs) far exceeds the 126 MB L2; 3 distinct batches rotate',
-                   'freeze_bn': True, 'optimizer': trainer.optim_note,
+                   'freeze_bn': True, 'optimizer': optim_note,
                    'trunk_batching': 'frozen-BN backbone once per network over 2 concatenated mini-batches'
-                                     if trainer._can_batch_trunk([None]) else 'pass by pass', 'launch_mode': 'eager' if args.eager else 'cuda-graph replay (2 graphs/step)',
-                   'host_enqueue_ms_per_step': round((t_enq - t_start) * 1e3 / args.steps, 2),
+                                     if trunk_batched else 'pass by pass', 'launch_mode': 'eager' if args.eager else 'cuda-graph replay (2 graphs/step)',
+                   'host_enqueue_ms_per_step': round(enq_s * 1e3 / args.steps, 2),
                    'conv_tflops_per_s_whole_step': round(flops_iter / (ms_step / 1e3) / 1e12, 2)},
         'clocks': clocks,
         'e2e': {'value': round(n * world / (ms_e2e / args.steps / 1e3), 3), 'unit': 'images/s',
@@ -315,27 +475,44 @@ def run_b200(args):
         **({'e2e_u8': e2e_u8} if e2e_u8 is not None else {}),
         'last_step': last,
     }
+    modes = {args.precision: {'value': round(value, 3), 'ms_per_step': round(ms_step, 3), 'steps': args.steps}}
+    if other:
+        modes[other_mode] = {'value': round(n * world / (other[0] / 1e3), 3), 'ms_per_step': round(other[0], 3), 'steps': other[1],
+                             'last_step': other[2]}
+    res['precision_modes'] = modes
     if prof:
         dom = max(((k, v) for k, v in prof.items() if v['flops'] > 0), key=lambda kv: kv[1]['ms'])
         name, d = dom
         ach = d['flops'] / (d['ms'] / 1e3) / 1e12
         traffic, traffic_src = committed_traffic(name)
+        tf32_peak = peaks.get('tf32_sustained')
         res['roofline'] = {'kernel': name, 'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peaks['bf16_sustained'],
                            'unit': 'TFLOP/s', 'frac': round(ach / peaks['bf16_sustained'], 4), 'traffic': traffic,
                            'traffic_source': traffic_src,
-                           'peak_source': peaks['source'] + ' cuBLAS bf16 sustained; kind::tf32 runs at half the bf16 rate',
-                           'frac_of_tf32_rate': round(ach / (peaks['bf16_sustained'] / 2), 4),
+                           'peak_source': peaks['source'] + ' cuBLAS bf16 sustained (MEASURED_PEAKS.json holds no tf32 figure; kind::tf32 '
+                                          'issues at half the bf16 rate, so 0.5 is this kernel family\'s ceiling on this scale)',
+                           'frac_of_half_bf16_rate': round(ach / (peaks['bf16_sustained'] / 2), 4),
                            'launches': d['n'], 'kernel_ms_per_step': round(d['ms'], 3),
                            'share_of_step': round(d['ms'] / ms_step, 4),
                            'profiled_step_kernel_ms_total': round(sum(v['ms'] for v in prof.values()), 3),
                            'per_kernel': {k: {'ms': round(v['ms'], 3), 'n': v['n'],
                                               'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)}
                                           for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:24]}}
-    if prof and os.environ.get('B200SEG_SHAPE_PROFILE'):
-        top = sorted(be.last_shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:70]
+        if args.measure_tf32_peak:
+            res['roofline']['tf32_matmul_measured'] = measure_tf32_matmul(device)
+    if prof and os.environ.get('B200SEG_SHAPE_PROFILE') and shape_profile:
+        top = sorted(shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:70]
         with open(os.environ['B200SEG_SHAPE_PROFILE'], 'w') as f:
             for k, v in top:
                 f.write('{:<70s} {:8.3f} ms  n={:4d}  {:7.1f} TFLOP/s\n'.format(k, v['ms'], v['n'], v['flops'] / max(v['ms'], 1e-9) / 1e9))
+    extras = world == 1 and not os.environ.get('B200SEG_SKIP_EXTRAS')
+    if extras and args.arch == 'v3plus' and args.loss == 'cutmix':
+        try:
+            res['parity'] = parity_block(device)
+        except Exception as e:
+            res['parity'] = {'failed': repr(e)[:300]}
+    if extras and args.loss == 'cutmix':
+        res['incumbent_cudnn'] = incumbent_cudnn(args, cfg, device, n, max(2, min(args.steps, 5)))
     if world > 1:       # the host baseline is a property of the box, reported by the N = 1 run only
         res['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': 0, 'kind': 'port', 'sample': 'reported at N=1 only'}
     elif os.environ.get('B200SEG_SKIP_CPU_BASELINE'):
@@ -345,6 +522,32 @@ def run_b200(args):
     print(json.dumps(res))
     if dist_on:
         dist.destroy_process_group()
+
+
+def measure_tf32_matmul(device):
+    """cuBLAS fp32 matmul with TF32 tensor cores allowed, 8192^3, sustained for ~2 s: the library's tf32 rate on this GPU at the
+    clock it settles to (MEASURED_PEAKS.json has bf16 only)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=device); b = torch.randn((8192, 8192), device=device)
+        for _ in range(5):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best, n_it, t_end = 0.0, 0, time.time() + 2.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.time() < t_end:
+            for _ in range(20):
+                torch.matmul(a, b)
+            n_it += 20
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = 2 * 8192 ** 3 * n_it / (e0.elapsed_time(e1) / 1e3) / 1e12
+        return {'tflops_sustained': round(sustained, 1), 'how': 'torch.matmul fp32 8192^3, allow_tf32=True, back to back for 2 s'}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -434,6 +637,13 @@ def main():
     ap.add_argument('--u8-inputs', dest='u8_inputs', action='store_true',
                     help='also time the end-to-end loop with uint8 batches normalised on the device (extra key e2e_u8)')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
+    ap.add_argument('--precision', default='tf32', choices=['tf32', '3xtf32'],
+                    help='tensor-core mode of the timed iteration: single-pass TF32 (PyTorch/cuDNN default conv precision) or 3xTF32 '
+                         '(the mode the tight parity tests run in); the other mode is timed as well on a few steps (precision_modes)')
+    ap.add_argument('--no-second-precision', dest='no_second_precision', action='store_true',
+                    help='skip the short run in the other precision mode')
+    ap.add_argument('--no-tf32-peak', dest='measure_tf32_peak', action='store_false',
+                    help='skip the 2 s cuBLAS tf32 matmul that places the tf32 library rate next to the roofline')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -220,11 +220,30 @@ def out_grad(act):
 
 
 def param_grad(p):
-    """(grad tensor laid out like p, accumulate?)  Creates p.grad on first use."""
+    """(grad tensor laid out like p, accumulate?)  Creates p.grad on first use.  The gradient kernels write through raw
+    pointers in the PARAMETER's storage order, so an existing .grad with other strides (a user-assigned NCHW-contiguous
+    tensor) is refused instead of being filled in the wrong order."""
     if p.grad is None:
         p.grad = torch.empty_like(p)
         return p.grad, False
+    if p.grad.stride() != p.stride() or p.grad.dtype != torch.float32:
+        raise RuntimeError('parameter gradient of shape {} has strides {} / dtype {}, the parameter has strides {}: the B200 '
+                           'kernels need .grad laid out like the parameter (set it to None and let the backward pass create it)'
+                           .format(tuple(p.shape), p.grad.stride(), p.grad.dtype, p.stride()))
     return p.grad, True
+
+
+def check_weight_layout(w):
+    """Convolution weights are logical (Cout, Cin, kh, kw) tensors STORED channels-last = physically (Cout, kh, kw, Cin), the
+    K-major operand the GEMMs read through TMA (architectures/layers.py).  `load_state_dict(assign=True)`, `p.data = t` or a
+    `memory_format` conversion can silently replace the storage by an NCHW-contiguous one; the kernels would then read the
+    taps and channels in the wrong order.  Fail loudly instead."""
+    if w.dim() == 4 and not w.permute(0, 2, 3, 1).is_contiguous():
+        raise RuntimeError('convolution weight of shape {} has strides {}: the B200 kernels need channels-last storage '
+                           '(p.data = p.data.contiguous(memory_format=torch.channels_last)); load_state_dict() without '
+                           'assign=True keeps it'.format(tuple(w.shape), w.stride()))
+    if w.dtype != torch.float32:
+        raise RuntimeError('convolution weight has dtype {}, the B200 kernels compute on fp32 storage'.format(w.dtype))
 
 
 # ====================================================================================== nodes
@@ -607,6 +626,7 @@ def conv_bn_act(tape, x, conv, bn=None, residual=None, relu=False, out=None, dro
     assert x.c == cin, 'channel mismatch: {} vs {}'.format(x.c, cin)
     oh, ow = _conv_out_hw(x.h, x.w, kh, stride, pad, dil)
     w = conv.weight
+    check_weight_layout(w)
     bias = conv.bias
     train_bn = bn is not None and bn.training
     if not train_bn:
@@ -659,6 +679,7 @@ def stem_conv(tape, x_nhwc, conv, bn):
     oh, ow = _conv_out_hw(x_nhwc.h, x_nhwc.w, kh, stride, pad, dil)
     kreal = kh * kw * cin
     kpad = (kreal + 31) // 32 * 32
+    check_weight_layout(conv.weight)
     col = K.im2col(x_nhwc, kh, kw, stride, pad, dil, oh, ow, kpad)
     wpad = torch.zeros((cout, 1, kpad), device=x_nhwc.device, dtype=torch.float32)
     K.copy_rows(wpad, kpad, conv.weight, kreal, cout, kreal, False)

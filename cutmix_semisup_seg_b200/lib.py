@@ -207,3 +207,16 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise B2Error('B200 hot path received a non-CUDA tensor; there is no CPU fallback')
+
+
+def require_dense(dtype, *tensors):
+    """The C ABI takes raw pointers: a tensor of another dtype or a non-contiguous view would be silently reinterpreted.
+    Raises B2Error naming the offending argument position instead."""
+    for i, t in enumerate(tensors):
+        if t is None:
+            continue
+        if t.dtype != dtype:
+            raise B2Error('B200 hot path: argument {} has dtype {}, expected {} (cast it; the kernels read raw pointers)'
+                          .format(i, t.dtype, dtype))
+        if not t.is_contiguous():
+            raise B2Error('B200 hot path: argument {} is not contiguous (shape {}, strides {})'.format(i, tuple(t.shape), t.stride()))

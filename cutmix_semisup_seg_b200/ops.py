@@ -83,6 +83,7 @@ class CudaBackend(object):
     # ------------------------------------------------------------------ elementwise hot-path ops
     def ema_step_flat(self, tgt, src, alpha):
         L.require_cuda(tgt, src)
+        L.require_dense(torch.float32, tgt, src)
         one_minus_alpha = 1.0 - alpha   # double, rounded to fp32 by ctypes like torch does (optim_weight_ema.py:22)
         self._call('b2_ema_step_flat', tgt.data_ptr(), src.data_ptr(), tgt.numel(), alpha, one_minus_alpha, self._s())
 
@@ -95,6 +96,8 @@ class CudaBackend(object):
         L.require_cuda(logits, labels, cm)
         n, c, h, w = logits.shape
         logits = logits.contiguous()
+        L.require_dense(torch.float32, logits)
+        L.require_dense(torch.int64, cm)
         if labels is not None:
             labels = labels.reshape(n, h, w).contiguous()
             assert labels.dtype == torch.int64
@@ -106,6 +109,7 @@ class CudaBackend(object):
     def box_mask_rasterize(self, boxes, h, w, init):
         """boxes: int32 CUDA tensor (N, B, 4) [y0,y1,x0,x1) -> (N,1,H,W) fp32."""
         L.require_cuda(boxes)
+        L.require_dense(torch.int32, boxes)
         n, nb = boxes.shape[0], boxes.shape[1]
         out = torch.empty((n, 1, h, w), device=boxes.device, dtype=torch.float32)
         self._call('b2_box_mask_rasterize', boxes.data_ptr(), n, nb, h, w, float(init), out.data_ptr(), self._s())
@@ -118,8 +122,12 @@ class CudaBackend(object):
         if b is not None:
             b = b.contiguous()
         n, c, h, w = a.shape
+        if tuple(m.shape) != (n, 1, h, w) or (b is not None and b.shape != a.shape):
+            raise L.B2Error('mix: a/b must be (N,C,H,W) and the mask (N,1,H,W); got {} {} {}'.format(
+                tuple(a.shape), None if b is None else tuple(b.shape), tuple(m.shape)))
         if out is None:
             out = torch.empty_like(a)
+        L.require_dense(torch.float32, a, b, m, out)
         self._call('b2_mix', a.data_ptr(), L.ptr(b), m.data_ptr(), out.data_ptr(), n, c, h * w, self._s())
         return out
 
@@ -130,6 +138,10 @@ class CudaBackend(object):
         hw = h * w
         if dls is None:
             dls = torch.empty_like(ls)
+        L.require_dense(torch.float32, l0, l1, ls, m, lmask, dls)
+        for t, shp in ((l0, ls.shape), (l1, ls.shape), (m, (n, 1, h, w)), (lmask, (n, 1, h, w)), (dls, ls.shape)):
+            if t is not None and tuple(t.shape) != tuple(shp):
+                raise L.B2Error('consistency: operand of shape {} where {} is expected'.format(tuple(t.shape), tuple(shp)))
         npart = L.call('b2_consistency_num_partials', n, hw)
         partials = torch.empty((npart * 3,), device=ls.device, dtype=torch.float64)
         out4 = torch.empty((4,), device=ls.device, dtype=torch.float32)
@@ -148,6 +160,7 @@ class CudaBackend(object):
         assert factors.dtype == torch.float32 and factors.numel() == n
         if out is None:
             out = torch.empty_like(a)
+        L.require_dense(torch.float32, a, b, factors, out)
         self._call('b2_mix_per_sample', a.data_ptr(), b.data_ptr(), factors.data_ptr(), out.data_ptr(), n, c, h * w, self._s())
         return out
 
@@ -160,6 +173,7 @@ class CudaBackend(object):
         assert factors.dtype == torch.float32 and factors.numel() == n
         if dls is None:
             dls = torch.empty_like(ls)
+        L.require_dense(torch.float32, l0, l1, ls, lmask, dls)
         confbar = None
         if conf_per_pixel and conf_thresh > 0.0:      # the reference's (N,N,1,H,W) broadcast: see include/b200seg.h
             confbar = torch.empty((hw,), device=ls.device, dtype=torch.float32)
@@ -184,6 +198,7 @@ class CudaBackend(object):
         assert theta.dtype == torch.float32 and tuple(theta.shape) == (n, 2, 3)
         oh, ow = (ih, iw) if out_hw is None else out_hw
         y = torch.empty((n, c, oh, ow), device=x.device, dtype=torch.float32)
+        L.require_dense(torch.float32, x, theta)
         self._call('b2_affine_grid_sample', x.data_ptr(), theta.data_ptr(), y.data_ptr(), n, c, ih, iw, oh, ow, self._s())
         return y
 
@@ -198,6 +213,7 @@ class CudaBackend(object):
         assert tuple(ltea.shape) == tuple(ls.shape) and tuple(um0.shape) == (n, 1, h, w) and tuple(um1.shape) == (n, 1, h, w)
         if dls is None:
             dls = torch.empty_like(ls)
+        L.require_dense(torch.float32, ltea, ls, theta, um0, um1, dls)
         npart = L.call('b2_consistency_num_partials', n, h * w)
         partials = torch.empty((npart * 3,), device=ls.device, dtype=torch.float64)
         out4 = torch.empty((4,), device=ls.device, dtype=torch.float32)
@@ -273,6 +289,7 @@ class CudaBackend(object):
         """mag[i] = sqrt(sum of squares of sample i) (normalize_eps, :217-219).  x: (N, ...) fp32 contiguous."""
         L.require_cuda(x)
         x = x.contiguous()
+        L.require_dense(torch.float32, x)
         n = x.shape[0]
         per = x.numel() // n
         blocks = L.call('b2_sample_reduce_blocks', per)
@@ -305,6 +322,7 @@ class CudaBackend(object):
         if out is None:
             out = torch.empty_like(e)
         r_dev = radius if torch.is_tensor(radius) else None
+        L.require_dense(torch.float32, x, e, mag, r_dev, out)
         self._call('b2_add_scaled_per_sample', L.ptr(x), e.data_ptr(), mag.data_ptr(), L.ptr(r_dev),
                    0.0 if r_dev is not None else float(radius), out.data_ptr(), n, per, self._s())
         return out
@@ -320,6 +338,10 @@ class CudaBackend(object):
         hw = h * w
         if dlogits is None:
             dlogits = torch.empty_like(logits)
+        L.require_dense(torch.float32, logits, dlogits)
+        L.require_dense(torch.int64, labels)
+        if tuple(labels.shape) != (n, h, w):
+            raise L.B2Error('cross_entropy: labels must be (N,H,W) int64, got {}'.format(tuple(labels.shape)))
         npart = L.call('b2_ce_num_partials', n, hw)
         partials = torch.empty((npart * 2,), device=logits.device, dtype=torch.float64)
         out3 = torch.empty((3,), device=logits.device, dtype=torch.float32)

@@ -19,6 +19,7 @@ from . import lib as L
 
 _CHUNK = 8192           # B2_OPT_CHUNK in include/b200seg.h
 _MAX_K = 8              # B2_OPT_MAX_K
+_LR_SLOTS = 8           # pinned staging slots of the learning-rate upload (see FusedOptimizer.upload_lr)
 
 
 class FusedOptimizer(torch.optim.Optimizer):
@@ -78,7 +79,13 @@ class FusedOptimizer(torch.optim.Optimizer):
                 st['b2_steps_done'] = self._iter          # shared step counter (every tensor steps every iteration)
             self._off[id(p)] = off
             off += n
-        self._lr_host = torch.zeros(len(self.param_groups), dtype=torch.float64).pin_memory()
+        # Learning rates reach the kernel through a RING of pinned host slots: the host-to-device copy is asynchronous, so a
+        # single staging buffer could be overwritten with iteration i+1's rate (poly / cosine schedules change it every
+        # iteration) before iteration i's copy has executed.  Each slot carries an event recorded after its copy; a slot is
+        # rewritten only once that event has completed (the host blocks only if the GPU is _LR_SLOTS iterations behind).
+        self._lr_ring = [torch.zeros(len(self.param_groups), dtype=torch.float64).pin_memory() for _ in range(_LR_SLOTS)]
+        self._lr_events = [None] * _LR_SLOTS
+        self._lr_next = 0
         self._lr_dev = torch.zeros(len(self.param_groups), device=dev, dtype=torch.float64)
         self._table = None
         self._table_key = None
@@ -89,12 +96,23 @@ class FusedOptimizer(torch.optim.Optimizer):
             opt_type, ', k sequential updates for the duplicated reference group' if dup else '')
 
     # ------------------------------------------------------------------------------------------
-    def refresh_lr(self):
-        """Publish the groups' current learning rates to the pinned host buffer the step copies from (call before
-        replaying a CUDA graph that contains step())."""
-        lr = self._lr_host.numpy()
+    def upload_lr(self):
+        """Copy the groups' current learning rates to the device buffer the kernel reads, ordered on the current stream
+        before the next step launch / CUDA-graph replay (the captured step contains no copy of its own: call this before
+        every replay)."""
+        j = self._lr_next
+        self._lr_next = (j + 1) % _LR_SLOTS
+        ev = self._lr_events[j]
+        if ev is not None:
+            ev.synchronize()                   # the copy that last read this slot has executed
+        lr = self._lr_ring[j].numpy()
         for i, g in enumerate(self.param_groups):
             lr[i] = float(g['lr'])
+        with torch.cuda.device(self._dev):
+            self._lr_dev.copy_(self._lr_ring[j], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._lr_events[j] = ev
 
     @staticmethod
     def _dense(t):
@@ -157,10 +175,10 @@ class FusedOptimizer(torch.optim.Optimizer):
             raise RuntimeError('closures are not supported by the fused optimiser')
         from . import engine, ops
         self._build_table(ema)
-        self.refresh_lr()
+        if not torch.cuda.is_current_stream_capturing():
+            self.upload_lr()            # (a captured step reads what upload_lr() delivered before the replay)
         g = self.param_groups[0]
         with torch.cuda.device(self._dev):
-            self._lr_dev.copy_(self._lr_host, non_blocking=True)
             alpha = float(ema.ema_alpha) if ema is not None else 0.0
             ops.default_backend()._call('b2_opt_ema_step', self._table.data_ptr(), self._n_chunks, self._lr_dev.data_ptr(), self._iter.data_ptr(),
                    0 if self.opt_type == 'adam' else 1, float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),

@@ -86,6 +86,11 @@ def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_n
     kw = dict(foreach=False) if (dup or not on_cuda) else dict(fused=True)
     if capturable and opt_type == 'adam' and on_cuda:
         kw['capturable'] = True          # step counters live on the device: the step can be replayed from a CUDA graph
+        # ... and so must the learning rates: a python float would be baked into the captured kernels and every LR schedule
+        # silently ignored on replay.  torch's schedulers update tensor learning rates in place (`fill_`).
+        dev = (g0 + g1)[0].device
+        for g in groups:
+            g['lr'] = torch.tensor(float(g['lr']), device=dev, dtype=torch.float32)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         if opt_type == 'adam':
@@ -527,8 +532,8 @@ class MeanTeacherStep(object):
             g1, g2, out = self._graph[0], self._graph[1], self._graph[2]
             g1.replay()
             self._allreduce()
-            if hasattr(self.student_optim, 'refresh_lr'):
-                self.student_optim.refresh_lr()        # the captured step re-reads the learning rates from pinned memory
+            if hasattr(self.student_optim, 'upload_lr'):
+                self.student_optim.upload_lr()         # this iteration's learning rates -> device, ahead of the captured step
             g2.replay()
             self.be.launches += self.launches_per_replay
             if prefetch is not None:

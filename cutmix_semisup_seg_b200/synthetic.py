@@ -3,6 +3,9 @@ image fp32 (N,3,H,W) ~ N(0,1) (standardised images), labels int64 (N,1,H,W) with
 valid masks fp32 (N,1,H,W) in [0,1] with a zero border and a fractional ramp column, and CutMix box
 parameters from `mask_gen.BoxMaskGenerator` with a seeded numpy RandomState.  Used by bench.py, the smoke
 test and the `--dataset synthetic` mode of the entry point (there is no network access for real data)."""
+import math
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
@@ -145,3 +148,32 @@ def condition_classifier(net, gain):
             if (name.startswith('layer5.') or 'classifier.classifier.6' in name or name.startswith('deeplab.classifier.4.')
                     or name.startswith('final_clf.')) and p.dim() == 4:
                 p.mul_(gain)
+
+
+def synth_state_dict(template, seed=0, logit_gain=1.0, final_keys=()):
+    """Deterministic, well-conditioned synthetic weights for a state_dict-shaped mapping (random-init or
+    checkpoint weights cannot be downloaded here): conv weights ~ N(0, 2/fan_in); BatchNorm gamma ~ U(0.5, 1.5) (U(0.15, 0.35)
+    for the last BatchNorm of a residual unit and for down-sample BatchNorms, so that activations stay O(1) through 33
+    residual units), beta ~ N(0, 0.1), running_mean ~ N(0, 0.1), running_var ~ U(0.5, 1.5), biases ~ N(0, 0.1); the weights
+    named in `final_keys` are multiplied by `logit_gain`.  One CPU generator per tensor, seeded by (seed, position): the same
+    values on every machine.  (oracle/torch_oracle.py carries an identical statement for the CPU side;
+    tests/test_fullsize_recipe.py checks that the two agree bit for bit.)"""
+    out = OrderedDict()
+    for i, (k, v) in enumerate(template.items()):
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        shape = tuple(v.shape)
+        if v.dtype != torch.float32:
+            out[k] = torch.zeros(shape, dtype=v.dtype)
+        elif k.endswith('running_mean'):
+            out[k] = torch.randn(shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            out[k] = torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 4:
+            w = torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[1] * shape[2] * shape[3]))
+            out[k] = w * logit_gain if k in final_keys else w
+        elif k.endswith('.weight'):
+            small = k.endswith('bn3.weight') or k.endswith('downsample.1.weight')
+            out[k] = torch.rand(shape, generator=g) * 0.2 + 0.15 if small else torch.rand(shape, generator=g) + 0.5
+        else:
+            out[k] = torch.randn(shape, generator=g) * 0.1
+    return out

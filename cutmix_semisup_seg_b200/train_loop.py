@@ -9,15 +9,50 @@ Differences from the reference, forced by the offline / GPU-native setting, are 
 import os
 import time
 
+# Options of the reference's click surface that configure its CPU data pipeline (dataset splits, DataLoader workers, geometric /
+# colour augmentation of real images, prediction dumps).  `--dataset synthetic` has no such pipeline: a non-default value cannot
+# take effect, which the run says out loud instead of silently accepting it.  {option: reference default}
+DATA_PIPELINE_OPTIONS = dict(
+    n_sup=100, n_unsup=-1, n_val=-1, split_seed=12345, split_path=None, val_seed=131, save_preds=False, num_workers=4,
+    aug_hflip=False, aug_vflip=False, aug_hvflip=False, aug_scale_hung=False, aug_max_scale=1.0, aug_scale_non_uniform=False,
+    aug_rot_mag=0.0, aug_colour_brightness=0.4, aug_colour_contrast=0.4, aug_colour_saturation=0.4, aug_colour_hue=0.1,
+    aug_colour_prob=0.8, aug_colour_greyscale_prob=0.2, aug_offset_range=16)
+NAN_CHECK_EVERY = 32        # iterations between two host reads of the running supervised loss (NaN bail-out)
+
+
+def check_dataset(dataset):
+    """Fail before any device / process-group initialisation: only `--dataset synthetic` can train in this build (the real
+    datasets need the reference's CPU data pipeline `datapipe/` -- scikit-image, OpenCV, the image archives -- which is outside
+    the B200 hot path, SURVEY.md 8 'out of scope')."""
+    if dataset != 'synthetic':
+        import click
+        raise click.UsageError(
+            "--dataset {!r} is not available in the B200 build: the reference's CPU data pipeline (datapipe/, real image archives) "
+            "is not part of the hot path.  Use --dataset synthetic (seeded tensors with the DataLoader's tensor contract); the "
+            "reference CLI default 'pascal_aug' has to be overridden explicitly.".format(dataset))
+
+
+def ignored_options(settings, used=()):
+    """Names of data-pipeline options given a non-default value although nothing consumes them on synthetic data."""
+    out = []
+    for key, default in DATA_PIPELINE_OPTIONS.items():
+        if key in used or key not in settings:
+            continue
+        if settings[key] != default:
+            out.append(key)
+    return out
+
 
 def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, *, dataset, model, arch, freeze_bn, opt_type,
                  sgd_momentum, sgd_nesterov, sgd_weight_decay, learning_rate, lr_sched, lr_step_epochs, lr_step_gamma,
                  lr_poly_power, teacher_alpha, bin_fill_holes, crop_size, cons_loss_fn, cons_weight, conf_thresh,
                  conf_per_pixel, rampup, unsup_batch_ratio, num_epochs, iters_per_epoch, batch_size, save_model,
-                 no_pretrained, ddp, synthetic_classes, step_options=None):
+                 no_pretrained, ddp, synthetic_classes, step_options=None, used_options=()):
     """`make_unsup(batch_size, h, w, seed, device)` -> one unsupervised batch dict for MeanTeacherStep.step (CutMix / CutOut
     box parameters, ICT mix factors, augmentation maps or the VAT marker included); `step_options`: extra keyword arguments of
-    MeanTeacherStep (VAT radius / direction network)."""
+    MeanTeacherStep (VAT radius / direction network); `used_options`: data-pipeline options the calling script does consume
+    on synthetic data (e.g. the aug script's rotation / scale magnitudes)."""
+    check_dataset(dataset)
     import numpy as np
     import torch
     from architectures import network_architectures
@@ -37,15 +72,9 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
     torch_device = torch.device('cuda', local)
     torch.cuda.set_device(torch_device)
 
-    if dataset != 'synthetic':
-        try:
-            from datapipe import datasets  # noqa: F401  (the reference's CPU data pipeline, if the user provides it)
-        except ImportError:
-            raise NotImplementedError(
-                'dataset {!r} needs the reference data pipeline (datapipe/, CPU, out of scope of the B200 hot path); put '
-                'the reference repository on PYTHONPATH or use --dataset synthetic'.format(dataset))
-        raise NotImplementedError('real-dataset loaders are wired through the reference datapipe in a later round; '
-                                  'use --dataset synthetic')
+    ign = ignored_options(settings, used_options)
+    if ign and rank == 0:
+        print('WARNING: --dataset synthetic has no data pipeline; these options have no effect: {}'.format(', '.join(sorted(ign))))
     n_classes = synthetic_classes
     if bin_fill_holes and n_classes != 2:
         print('Binary hole filling can only be used with binary (2-class) segmentation datasets')
@@ -61,6 +90,12 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
     def build_net(pretrained):
         return NetClass(n_classes, pretrained=pretrained) if takes_pretrained else NetClass(n_classes)
     student_net = build_net(not no_pretrained).to(torch_device)
+    if ddp:
+        # identical replicas must not depend on every rank drawing the same initial weights (RNG state, cached files):
+        # rank 0's parameters AND buffers are the model, before the EMA teacher copies them
+        with torch.no_grad():
+            for t in student_net.state_dict().values():
+                dist.broadcast(t, src=0)
     # one fused launch for the optimiser step + the teacher's EMA step (cutmix_semisup_seg_b200/optim.py: torch's per-tensor
     # arithmetic incl. the duplicated DeepLab v2 group); B200SEG_FUSED_OPT=0 keeps torch.optim + the EMA kernel
     student_optim = step_mod.make_optimizer(student_net, opt_type, learning_rate, sgd_momentum, sgd_nesterov, sgd_weight_decay,
@@ -115,6 +150,7 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
         sup_acc = torch.zeros((), device=torch_device)
         cons_acc = torch.zeros((), device=torch_device)
         conf_acc = torch.zeros((), device=torch_device)
+        conf_ramp_acc = 0.0
         n_unsup_batches = 0
         for it in range(iters_per_epoch):
             if lr_iter_scheduler is not None:
@@ -129,15 +165,25 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
             sup_acc += out['sup_loss']
             if out['cons_loss'] is not None:
                 cons_acc += out['cons_loss']
-                conf_acc += out['conf_rate'] if conf_thresh > 0.0 else ramp_val
+                # reference :406-420: the confidence rate is accumulated per unsupervised batch when thresholding is on;
+                # without a threshold the ramp value stands in, but only `elif rampup > 0` -- otherwise nothing is added
+                if conf_thresh > 0.0:
+                    conf_acc += out['conf_rate']             # (already the sum over this iteration's unsup batches)
+                elif rampup > 0:
+                    conf_ramp_acc += ramp_val * len(unsup)
                 n_unsup_batches += len(unsup)
             iter_i += 1
-        sup_loss_val = float(sup_acc) / iters_per_epoch                # the only host sync of the epoch
+            # reference :468-471 reads the loss back every iteration to bail out on NaN; here the running sum is read every
+            # NAN_CHECK_EVERY iterations (a NaN term makes the sum NaN), so a dead network stops within that many iterations
+            if (it + 1) % NAN_CHECK_EVERY == 0 and it + 1 < iters_per_epoch and bool(torch.isnan(sup_acc)):
+                print('NaN detected; network dead, bailing.')
+                return
+        sup_loss_val = float(sup_acc) / iters_per_epoch
         if np.isnan(sup_loss_val):
             print('NaN detected; network dead, bailing.')
             return
         cons_val = float(cons_acc) / max(n_unsup_batches, 1)
-        conf_val = float(conf_acc) / max(n_unsup_batches, 1)
+        conf_val = (float(conf_acc) + conf_ramp_acc) / max(n_unsup_batches, 1)
 
         eval_net.eval()
         iou_eval = evaluation.EvaluatorIoU(n_classes, bin_fill_holes)

@@ -127,9 +127,12 @@ class BoxMaskGenerator(MaskGenerator):
 
     # -- device side --------------------------------------------------------------------------
     def torch_masks_from_params(self, t_params, mask_shape, torch_device):
-        """Dense params (N,1,H,W) pass through unchanged (reference mask_gen.py:119-120); compact
-        int32 box params (N,B,4) are rasterised on the GPU."""
+        """Dense params (N,1,H,W) pass through (reference mask_gen.py:119-120; the collate hook already made them float32,
+        :141 -- a float64 array straight from `generate_params` is cast here, because the mix / loss kernels read raw fp32
+        pointers); compact int32 box params (N,B,4) are rasterised on the GPU."""
         if t_params.dim() == 4:
+            if t_params.dtype != torch.float32 or t_params.device != torch.device(torch_device):
+                t_params = t_params.to(device=torch_device, dtype=torch.float32)
             return t_params
         if t_params.dim() != 3 or t_params.shape[-1] != 4:
             raise ValueError('mask params must be (N,1,H,W) masks or (N,n_boxes,4) boxes')

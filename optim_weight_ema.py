@@ -4,12 +4,9 @@
 (`target_params`, `source_params`: every float32 `state_dict()` tensor, i.e. parameters AND BatchNorm
 running statistics; int64 `num_batches_tracked` is skipped) and semantics (constructor copies
 source -> target and checks the key sets; `step()` does `t = t*alpha + s*(1-alpha)`), but `step()`
-is ONE fused multi-tensor CUDA kernel (`b2_ema_step`, or `b2_ema_step_flat` when both networks keep
-their float state in one flat buffer) instead of 3 launches x ~567 tensors.  The arithmetic is
+is ONE fused multi-tensor CUDA kernel (`b2_ema_step` over a device table of chunks) instead of 3 launches x ~567 tensors.  The arithmetic is
 bit-exact with the reference: three separate fp32 roundings, no FMA.
 """
-import ctypes
-
 import numpy as np
 import torch
 
@@ -37,20 +34,6 @@ class EMAWeightOptimizer(object):
         self._n_chunks = 0
 
     # ------------------------------------------------------------------------------------------
-    def _flat_pair(self):
-        """(teacher_flat, student_flat) if both networks expose one flat fp32 state buffer that is
-        exactly the union of the tensors in target_params / source_params."""
-        tf = getattr(self.target_net, 'b2_flat_state', None)
-        sf = getattr(self.source_net, 'b2_flat_state', None)
-        if tf is None or sf is None:
-            return None
-        t, s = tf(), sf()
-        if t is None or s is None or t.numel() != s.numel():
-            return None
-        if t.numel() != sum(p.numel() for p in self.target_params):
-            return None
-        return t, s
-
     def _build_table(self, backend_device):
         ptr_key = tuple(p.data_ptr() for p in self.target_params) + tuple(p.data_ptr() for p in self.source_params)
         if self._table is not None and ptr_key == self._table_key:
@@ -81,12 +64,8 @@ class EMAWeightOptimizer(object):
         be = ops.default_backend()
         engine.invalidate_caches()      # the kernel writes the teacher through raw pointers (no torch version bump)
         with torch.cuda.device(dev):
-            flat = self._flat_pair()
-            if flat is not None:
-                be.ema_step_flat(flat[0], flat[1], self.ema_alpha)
-            else:
-                self._build_table(dev)
-                be.ema_step_table(self._table, self._n_chunks, self.ema_alpha)
+            self._build_table(dev)
+            be.ema_step_table(self._table, self._n_chunks, self.ema_alpha)
 
 
 def _dense(t):

@@ -79,3 +79,20 @@ def test_bad_mask_mode_is_rejected_before_any_gpu_work():
     from click.testing import CliRunner
     r = CliRunner().invoke(entry.experiment, ['--mask_mode', 'blend'])
     assert r.exit_code == 2
+
+
+def test_real_datasets_fail_fast_with_a_usage_error_and_ignored_options_are_reported(tmp_path, monkeypatch):
+    """the CLI default `pascal_aug` (and every real dataset) needs the reference's CPU data pipeline, which is not part
+    of this build -> a click usage error before any device / process-group initialisation (this test runs without a GPU);
+    data-pipeline options that cannot take effect on synthetic data are listed, not silently swallowed."""
+    from click.testing import CliRunner
+    import train_seg_semisup_mask_mt as entry
+    from cutmix_semisup_seg_b200 import train_loop
+    monkeypatch.chdir(tmp_path)
+    r = CliRunner().invoke(entry.experiment, ['--num_epochs', '1'])
+    assert r.exit_code == 2 and 'pascal_aug' in r.output and '--dataset synthetic' in r.output, r.output
+    settings = dict(train_loop.DATA_PIPELINE_OPTIONS)
+    assert train_loop.ignored_options(settings) == []
+    settings.update(n_sup=372, aug_hflip=True, aug_rot_mag=10.0)
+    assert sorted(train_loop.ignored_options(settings)) == ['aug_hflip', 'aug_rot_mag', 'n_sup']
+    assert sorted(train_loop.ignored_options(settings, used=('aug_rot_mag',))) == ['aug_hflip', 'n_sup']

@@ -3,12 +3,7 @@ kernels: the affine grid-sample kernel against F.affine_grid + F.grid_sample, th
 against the golden vectors produced by the reference's own source lines (tests/golden/aug_block.json) and against the oracle
 on the data sets' class counts, full iterations against the oracle's CPU iterations, and the drop-in entry point.
 
-STATUS (profiles/r01_v15_aug_vat_kernel_probes.txt): the kernel-level tests of this file -- the grid-sample kernel, the fused
-kernel against the reference-lines golden (12 cases) and against the oracle on C = 19 / 21 / 2 / 7 for all five loss functions
-(20 cases), the ABI error paths -- ran and passed on a B200 with the last GPU seconds of round 1 and are binding.  The
-iteration-level and entry-point tests could not be run any more: they stay NON-STRICT expected failures (`pending`; a pass is
-reported as XPASS) until a run is recorded, and the file sorts after the fully verified GPU tests.  B200SEG_AUG_VERIFIED=1
-makes every test binding."""
+Every test of this file is binding (round 2: the non-strict xfail gates of round 1 are gone)."""
 import json
 import math
 import os
@@ -30,12 +25,6 @@ from architectures import network_architectures as na  # noqa: E402
 from aug_recipe import aug_inputs, parse_case  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-if os.environ.get('B200SEG_AUG_VERIFIED', '0') != '1':
-    pending = pytest.mark.xfail(strict=False, reason='first B200 run of the aug-consistency ITERATION is pending (the kernels '
-                                                     'are verified; GPU budget of the round was spent); see module docstring')
-else:
-    def pending(f):
-        return f
 dev = torch.device('cuda:0')
 GOLD = json.load(open(os.path.join(HERE, 'golden', 'aug_block.json')))
 
@@ -130,7 +119,6 @@ def test_aug_kernel_rejects_bad_arguments():
                t.clone().data_ptr(), part.data_ptr(), 1, 2, 4, 4, 0, 0.5, 0, None)
 
 
-@pending
 @pytest.mark.parametrize('batch_trunk,conf_per_pixel', [(True, False), (False, True)])
 def test_aug_iterations_match_oracle(batch_trunk, conf_per_pixel):
     """Two full augmentation-consistency iterations (DeepLab v2, frozen BN, Adam with the duplicated group, EMA) vs the
@@ -172,7 +160,6 @@ def test_aug_iterations_match_oracle(batch_trunk, conf_per_pixel):
         assert worst < 1.5e-3, (name, worst)
 
 
-@pending
 def test_aug_logits_var_fails_like_the_reference():
     from cutmix_semisup_seg_b200 import step as step_mod, synthetic
     n, h, w, c = 1, 33, 33, 21
@@ -199,7 +186,6 @@ BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size
         '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']
 
 
-@pending
 @pytest.mark.parametrize('name', sorted(AUG_CASES))
 def test_aug_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
     """train_seg_semisup_aug_mt.py through its click command."""

@@ -3,13 +3,7 @@ the B200 kernels: csrc/vat.cu (col2im, per-sample norm, adaptive radius, normali
 input-gradient-only backward pass of the networks against autograd on the oracle, the perturbation and full VAT iterations
 against the oracle's CPU iterations, and the drop-in entry point.
 
-STATUS (profiles/r01_v15_aug_vat_kernel_probes.txt): with the last GPU seconds of round 1 the kernel-level tests ran on a
-B200 -- per-sample norm / adaptive radius / normalise-scale-add and col2im (vs F.fold and the adjoint identity) passed and
-are binding; the input-gradient pass of the full DeepLab v2 produced correct logits and a gradient within the 5e-2 maximum
-bound, median error 1.1e-2 of the median magnitude (the sqrt(forward error) law of whole-network gradients in 3xTF32; the
-5e-3 first written here was too tight and is now 3e-2).  Everything else (input gradient re-run, perturbation, iterations,
-entry point) could not be run any more and stays a NON-STRICT expected failure (`pending`) until a run is recorded.
-B200SEG_VAT_VERIFIED=1 makes every test binding."""
+Every test of this file is binding (round 2: the non-strict xfail gates of round 1 are gone)."""
 import math
 import os
 import re
@@ -29,12 +23,6 @@ import optim_weight_ema  # noqa: E402
 from architectures import network_architectures as na  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-if os.environ.get('B200SEG_VAT_VERIFIED', '0') != '1':
-    pending = pytest.mark.xfail(strict=False, reason='first complete B200 run of the VAT path is pending (its kernels are '
-                                                     'verified; GPU budget of the round was spent); see module docstring')
-else:
-    def pending(f):
-        return f
 dev = torch.device('cuda:0')
 
 
@@ -102,7 +90,6 @@ def _net(kind, classes, seed, gain=4.0):
     return net, sd
 
 
-@pending
 @pytest.mark.parametrize('kind,classes,student', [('resnet101_deeplab_imagenet', 21, False),
                                                   ('resnet101_deeplabv3plus_imagenet', 19, True)])
 def test_input_gradient_only_backward_matches_autograd(kind, classes, student):
@@ -137,7 +124,6 @@ def test_input_gradient_only_backward_matches_autograd(kind, classes, student):
     assert cos.min().item() > 0.999
 
 
-@pending
 @pytest.mark.parametrize('fn,adaptive', [('kld', False), ('var', True)])      # bce / logits_var: CPU tests (test_step_emu.py)
 def test_vat_perturbation_matches_oracle(fn, adaptive):
     from cutmix_semisup_seg_b200 import step as step_mod, synthetic
@@ -161,7 +147,6 @@ def test_vat_perturbation_matches_oracle(fn, adaptive):
     assert cos.min().item() > 0.995          # direction = a normalised whole-network gradient (sqrt law, see above)
 
 
-@pending
 @pytest.mark.parametrize('adaptive,conf_per_pixel', [(False, False), (True, True)])
 def test_vat_iterations_match_oracle(adaptive, conf_per_pixel):
     """Two full VAT iterations (DeepLab v2, frozen BN, Adam with the duplicated group, EMA) vs the oracle's CPU iterations,
@@ -211,7 +196,6 @@ BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size
         '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']
 
 
-@pending
 @pytest.mark.parametrize('name', sorted(VAT_CASES))
 def test_vat_entry_point_runs_on_synthetic_data(name, tmp_path, monkeypatch):
     """train_seg_semisup_vat_mt.py through its click command."""

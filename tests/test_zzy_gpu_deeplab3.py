@@ -2,10 +2,7 @@
 network_architectures.py:75-98) on the B200 kernels: shallow and full networks against the fp64 oracle (3xTF32), the golden
 logits of the real module (tests/golden/net_dl3v3.npz), CutMix iterations against the oracle, the entry point.
 
-STATUS: this architecture only re-arranges layers whose kernels are verified (backbone, ASPP and head layers of DeepLab v3+,
-one x8 resize as in DeepLab v2), but the file was written after the round's GPU budget was spent and has not yet run on a
-B200: non-strict expected failures (a pass is reported as XPASS), sorted after the verified GPU tests.
-B200SEG_DL3_VERIFIED=1 makes them binding."""
+Every test of this file is binding (round 2: the non-strict xfail gates of round 1 are gone)."""
 import math
 import os
 import re
@@ -26,9 +23,6 @@ import optim_weight_ema  # noqa: E402
 from architectures import network_architectures as na, deeplab3plus  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-if os.environ.get('B200SEG_DL3_VERIFIED', '0') != '1':
-    pytestmark.append(pytest.mark.xfail(strict=False, reason='first B200 run of the DeepLab v3 graph is pending (GPU budget of '
-                                                              'the round was spent); see module docstring'))
 dev = torch.device('cuda:0')
 
 

@@ -3,9 +3,7 @@ augmentation-consistency loop) on the B200 kernels: the encoder glue of csrc/une
 per-channel gradient scaling into a strided prefix) against torch, the network against the fp64 oracle and the golden logits
 of the real module (tests/golden/net_denseunet.npz), an augmentation-consistency iteration against the oracle, the entry point.
 
-STATUS: written after the GPU budget of round 1 was spent; not yet run on a B200 (new: the glue kernels; GEMM shapes with
-K = 96 + 48 k input channels and N = 48 / 192 output channels into concatenation slices).  NON-STRICT expected failures (a pass
-is reported as XPASS), sorted after the verified GPU tests; B200SEG_UNET_VERIFIED=1 makes them binding."""
+Every test of this file is binding (round 2: the non-strict xfail gates of round 1 are gone)."""
 import math
 import os
 import re
@@ -26,9 +24,6 @@ import optim_weight_ema  # noqa: E402
 from architectures import network_architectures as na, denseunet  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-if os.environ.get('B200SEG_UNET_VERIFIED', '0') != '1':
-    pytestmark.append(pytest.mark.xfail(strict=False, reason='first B200 run of the DenseNet U-Net graph is pending (GPU budget '
-                                                              'of the round was spent); see module docstring'))
 dev = torch.device('cuda:0')
 
 

@@ -3,9 +3,7 @@ B200 kernels: csrc/unet.cu (nearest x2 up-sampling + skip addition forward / bac
 torch, the network against the fp64 oracle and the golden logits of the real module (tests/golden/net_resunet50.npz), CutMix
 iterations against the oracle, the entry point.
 
-STATUS: written after the GPU budget of round 1 was spent; csrc/unet.cu has not run on a B200 yet (the rest of the graph uses
-verified kernels).  NON-STRICT expected failures (a pass is reported as XPASS), sorted after the verified GPU tests;
-B200SEG_UNET_VERIFIED=1 makes them binding."""
+Every test of this file is binding (round 2: the non-strict xfail gates of round 1 are gone)."""
 import math
 import os
 import re
@@ -27,9 +25,6 @@ import optim_weight_ema  # noqa: E402
 from architectures import network_architectures as na, resunet  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-if os.environ.get('B200SEG_UNET_VERIFIED', '0') != '1':
-    pytestmark.append(pytest.mark.xfail(strict=False, reason='first B200 run of csrc/unet.cu and the U-Net graph is pending (GPU '
-                                                              'budget of the round was spent); see module docstring'))
 dev = torch.device('cuda:0')
 
 

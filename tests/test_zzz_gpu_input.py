@@ -1,6 +1,5 @@
 """-m gpu: csrc/input.cu (device-side SegCVTransformNormalizeToTensor) bit-exact against the reference's
-numpy arithmetic restated in tests/test_input_pipeline.py.  Written after the GPU budget of round 1 was spent: non-strict
-expected failure until its first B200 run; sorts after every other GPU test."""
+numpy arithmetic restated in tests/test_input_pipeline.py."""
 import os
 import sys
 
@@ -13,7 +12,6 @@ from test_input_pipeline import MEAN, STD, check_backend, make_batch, reference_
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason='csrc/input.cu was written after the GPU budget of round 1 was spent: first B200 run pending')
 def test_cuda_kernels_are_bit_exact_with_the_reference_arithmetic():
     from cutmix_semisup_seg_b200 import ops, input_pipeline
     dev = torch.device('cuda:0')

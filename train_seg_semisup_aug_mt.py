@@ -47,7 +47,8 @@ def train_seg_semisup_aug_mt(submit_config, dataset, model, arch, freeze_bn,
         bin_fill_holes=bin_fill_holes, crop_size=crop_size, cons_loss_fn=cons_loss_fn, cons_weight=cons_weight,
         conf_thresh=conf_thresh, conf_per_pixel=conf_per_pixel, rampup=rampup, unsup_batch_ratio=unsup_batch_ratio,
         num_epochs=num_epochs, iters_per_epoch=iters_per_epoch, batch_size=batch_size, save_model=save_model,
-        no_pretrained=no_pretrained, ddp=ddp, synthetic_classes=synthetic_classes)
+        no_pretrained=no_pretrained, ddp=ddp, synthetic_classes=synthetic_classes,
+        used_options=('aug_rot_mag', 'aug_max_scale', 'aug_offset_range'))
 
 
 @click.command()
