@@ -49,6 +49,7 @@ struct ConvKArgs {
   short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
   int kblocks;
   int n_pass;
+  int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
 };
 
@@ -118,14 +119,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer (converged warp, one elected lane issues; tc_common.cuh) =====================
     const uint32_t el = tc::elect_one();
     int stage = 0; uint32_t phase = 0;
+    // K-block outer / tap inner: the shifted boxes of one 32-channel slab are served from L2 (see conv_gemm2.cu)
+    const int n_outer = a.tap_outer ? a.n_taps : a.kblocks;
+    const int n_inner = a.tap_outer ? a.kblocks : a.n_taps;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(a, tile);
-      for (int tap = 0; tap < a.n_taps; ++tap) {
-        if (!(t.tap_mask >> tap & 1)) continue;
-        const int cw = t.w0 * a.istride + a.dw[tap];
-        const int ch = t.h0 * a.istride + a.dh[tap];
-        const int bt = a.btap[tap];
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+      const int w_base = t.w0 * a.istride, h_base = t.h0 * a.istride;
+      for (int o = 0; o < n_outer; ++o) {
+        for (int i = 0; i < n_inner; ++i) {
+          const int tap = a.tap_outer ? o : i;
+          const int kb = a.tap_outer ? i : o;
+          if (!(t.tap_mask >> tap & 1)) continue;
+          const int cw = w_base + a.dw[tap];
+          const int ch = h_base + a.dh[tap];
+          const int bt = a.btap[tap];
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (el) {
@@ -292,6 +299,7 @@ extern "C" int64_t b2_conv_stats_rows(const b2_conv_params* p) {
 }
 int g_conv_force_1cta = 0;
 int g_conv_epi_debug = 0;
+int g_conv_tap_outer = 0;         // b2_debug_set(7, 1): producer loops tap-outer / K-block-inner (the round-1 order)
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   B2_REQUIRE(p && p->a && p->b && p->d, "b2_conv_gemm: null tensor");
@@ -338,6 +346,7 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
+  a.tap_outer = g_conv_tap_outer;
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;

@@ -53,6 +53,7 @@ struct Conv2KArgs {
   short dh[MAX_TAPS], dw[MAX_TAPS], btap[MAX_TAPS];
   int kblocks;
   int n_pass;
+  int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
   long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
 };
@@ -193,14 +194,25 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t el = tc::elect_one();
     int stage = 0; uint32_t phase = 0;
     int tr_n = 0;
+    // Loop order: K-block OUTER, tap INNER.  All CTAs of the grid walk the K blocks roughly in step, so at any moment the
+    // chip's working set is ONE 32-channel slab of the few images in flight (a few MB): the 9 shifted boxes of that slab
+    // (and the neighbouring tiles' halos) are served from L2.  With the taps outside, every tap streamed all channels of
+    // those images (~150 MB at 2048 channels, more than the 126 MB L2) before the next tap could reuse anything: the ASPP
+    // fprop read 2.49 GB from DRAM for 0.62 GB of tensors (profiles/r01_v11_ncu_full_aspp_*).  The MMA issuer only counts
+    // stages, so the order is the producer's alone.  (Debug knob 7 = 1 restores the old order for A/B timing.)
+    const int n_outer = a.tap_outer ? a.n_taps : a.kblocks;
+    const int n_inner = a.tap_outer ? a.kblocks : a.n_taps;
     for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
       const TileInfo t = decode_tile(a, pair, (int)rank);
-      for (int tap = 0; tap < a.n_taps; ++tap) {
-        if (!(t.tap_mask >> tap & 1)) continue;
-        const int cw = t.w0 * a.istride + a.dw[tap];
-        const int ch = t.h0 * a.istride + a.dh[tap];
-        const int bt = a.btap[tap];
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+      const int w_base = t.w0 * a.istride, h_base = t.h0 * a.istride;
+      for (int o = 0; o < n_outer; ++o) {
+        for (int i = 0; i < n_inner; ++i) {
+          const int tap = a.tap_outer ? o : i;
+          const int kb = a.tap_outer ? i : o;
+          if (!(t.tap_mask >> tap & 1)) continue;
+          const int cw = w_base + a.dw[tap];
+          const int ch = h_base + a.dh[tap];
+          const int bt = a.btap[tap];
           for (int p = 0; p < a.n_pass; ++p) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (a.trace && blockIdx.x == 0 && tr_n < 512) { if (el) a.trace[tr_n] = clock64(); ++tr_n; }
@@ -325,6 +337,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // choose_box is defined in conv_gemm.cu
 extern int g_conv_epi_debug;
+extern int g_conv_tap_outer;
 // PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never).  Measured on B200
 // (profiles/r01_v7_pf_microbench.log): faster up to K = 512 (HBM-bound 1x1 layers, 0.231 -> 0.163 ms for 256 -> 1024 with
 // addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
@@ -353,6 +366,7 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
+  a.tap_outer = g_conv_tap_outer;
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;

@@ -644,6 +644,7 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
 extern int g_conv_force_1cta;
 extern int g_conv_epi_debug;
 extern int g_conv_pf_max_k;
+extern int g_conv_tap_outer;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 5) g_wgrad_force_1cta = value;
   if (key == 6) g_wgrad_dbg = value;
@@ -651,6 +652,7 @@ extern "C" void b2_debug_set(int key, int value) {
   if (key == 2) g_conv_force_1cta = value;
   if (key == 3) g_conv_epi_debug = value;
   if (key == 4) g_conv_pf_max_k = value;
+  if (key == 7) g_conv_tap_outer = value;
 }
 
 extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {

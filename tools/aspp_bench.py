@@ -44,6 +44,10 @@ def conv_case(n, h, w, cin, cout, k, dil, name):
 
 if __name__ == '__main__':
     which = sys.argv[2] if len(sys.argv) > 2 else 'all'
+    if os.environ.get('B200SEG_TAP_OUTER'):          # A/B of the producer loop order (debug knob 7)
+        from cutmix_semisup_seg_b200 import lib as _lib0
+        _lib0.load().b2_debug_set(7, int(os.environ['B200SEG_TAP_OUTER']))
+        print('debug knob 7 (tap-outer producer order) =', os.environ['B200SEG_TAP_OUTER'])
     if which in ('all', 'aspp'):
         conv_case(16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N16')
     if which == 'l3':

@@ -1,0 +1,40 @@
+#!/bin/bash
+# One parametrised launcher for the GPU calls of a round (replaces the per-call scratch scripts of round 1):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh <stage> [tag]'
+# Every stage writes its logs under gpurun_out/ with the given tag; nothing here is a bench value unless bench.py printed it
+# outside a profiler.
+stage=${1:-tests}; tag=${2:-r02}
+mkdir -p gpurun_out
+run_tests() {   # $1 = log tag, rest = pytest args
+  local t=$1; shift
+  B200SEG_PARITY_LOG=gpurun_out/parity_$t.txt timeout -s KILL 1500 python -m pytest "$@" -m gpu -q --tb=short -p no:cacheprovider \
+    > gpurun_out/pytest_$t.log 2>&1
+  echo "[pytest exit $?]" >> gpurun_out/pytest_$t.log
+  tail -5 gpurun_out/pytest_$t.log | cut -c1-220
+  grep -E "^(FAILED|ERROR)" gpurun_out/pytest_$t.log | head -40 | cut -c1-220
+}
+bench_line() {  # $1 = log name, rest = bench args
+  local n=$1; shift
+  timeout -s KILL 900 python bench.py "$@" > gpurun_out/bench_$n.log 2>&1
+  echo "[bench exit $?]" >> gpurun_out/bench_$n.log
+  grep '^{' gpurun_out/bench_$n.log | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print('$n', d.get('value'), 'img/s', d.get('ms_per_step'), 'ms e2e', d.get('e2e',{}).get('value'), d.get('clocks'), 'modes', d.get('precision_modes'))
+    for k in ('parity','incumbent_cudnn'):
+        if k in d: print(' ', k, json.dumps(d[k])[:1500])
+    r=d.get('roofline',{}); print('  roofline', r.get('kernel'), r.get('achieved'), r.get('frac'), r.get('share_of_step'), r.get('tf32_matmul_measured'))
+" 2>/dev/null || tail -5 gpurun_out/bench_$n.log | cut -c1-300
+}
+case $stage in
+  tests)      run_tests $tag tests ;;
+  first)      # first call of the round: whole suite (binding), producer-order A/B, headline bench with parity + incumbent
+    run_tests $tag tests
+    for v in 0 1; do B200SEG_TAP_OUTER=$v timeout -s KILL 300 python tools/aspp_bench.py 3 all > gpurun_out/micro_${tag}_tapouter$v.log 2>&1; done
+    paste -d'|' <(cut -c1-75 gpurun_out/micro_${tag}_tapouter0.log) <(cut -c46-75 gpurun_out/micro_${tag}_tapouter1.log) | head -40
+    B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3
+    ;;
+  micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
+  bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
+  *) echo "unknown stage $stage"; exit 2 ;;
+esac
