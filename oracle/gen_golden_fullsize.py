@@ -132,7 +132,7 @@ def run(name):
                student_abs_sum=float(sum(v.double().abs().sum() for v in ssd.values() if v.dtype == torch.float32)),
                student_first_sum=float(ssd[first].double().sum()), student_last_sum=float(ssd[last].double().sum()),
                teacher_last_sum=float(tsd[last].double().sum()),
-               student_last=ssd[last].detach().numpy().copy(), teacher_last=tsd[last].detach().numpy().copy(),
+               student_last=ssd[last].detach()[:, :64].numpy().copy(), teacher_last=tsd[last].detach()[:, :64].numpy().copy(),     # first 64 input channels
                bn_running={k: v.numpy().copy() for k, v in ssd.items() if 'classifier.classifier.1.running' in k},
                torch_version=torch.__version__, seconds=time.time() - t0)
     bn = rec.pop('bn_running')

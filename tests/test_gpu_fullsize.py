@@ -325,8 +325,8 @@ def test_fullsize_iterations_match_reference_golden(name, precision):
         assert got[1] == pytest.approx(ref[1], rel=t_cons)
         assert got[2] == pytest.approx(ref[2], abs=t_conf)
     last = R.final_keys(student.state_dict(), cfg)[0]
-    s_last = student.state_dict()[last].detach().cpu().numpy()
-    t_last = teacher.state_dict()[last].detach().cpu().numpy()
+    s_last = student.state_dict()[last].detach().cpu().numpy()[:, :64]        # the fixture keeps the first 64 input channels
+    t_last = teacher.state_dict()[last].detach().cpu().numpy()[:, :64]
     rng = np.abs(gold['student_last']).max()
     e_s = np.abs(s_last - gold['student_last']).max() / rng
     e_t = np.abs(t_last - gold['teacher_last']).max() / rng
