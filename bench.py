@@ -499,7 +499,11 @@ def run_b200(args):
                                               'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)}
                                           for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:24]}}
         if args.measure_tf32_peak:
-            res['roofline']['tf32_matmul_measured'] = measure_tf32_matmul(device)
+            # MEASURED_PEAKS.json carries bf16 only; the tf32 library rate on THIS box at the clock it settles to, measured
+            # here (outside the timed regions), is the like-for-like denominator of a kind::tf32 kernel
+            m = measure_tf32_matmul(device)
+            res['roofline']['tf32_matmul_measured'] = m
+            res['roofline']['frac_of_measured_tf32_matmul'] = round(ach / m['tflops_sustained'], 4)
     if prof and os.environ.get('B200SEG_SHAPE_PROFILE') and shape_profile:
         top = sorted(shape_profile.items(), key=lambda kv: -kv[1]['ms'])[:70]
         with open(os.environ['B200SEG_SHAPE_PROFILE'], 'w') as f:

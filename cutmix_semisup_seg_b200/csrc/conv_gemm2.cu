@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_epilogue_tma.cuh"
 
 namespace {
 
@@ -31,8 +32,11 @@ constexpr int STAGES_PF = 3;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB
 constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;      // 16 KB: this CTA's half of the weight tile
 constexpr int EPI_BYTES = epi::BYTES;
+// PF build: the region behind the barriers holds EITHER the register epilogue's staging tiles + cp.async slots OR the TMA
+// epilogue's per-warp tiles (1024 B aligned: they start 1 KB behind the operand ring) + tables
+constexpr int PF_REGION = EPI_BYTES + epi::PF_BYTES > 768 + epi2::BYTES ? EPI_BYTES + epi::PF_BYTES : 768 + epi2::BYTES;
 constexpr int smem_bytes(int stages, bool pf) {
-  return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + EPI_BYTES + (pf ? epi::PF_BYTES : 0);
+  return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256 + (pf ? PF_REGION : EPI_BYTES);
 }
 static_assert(smem_bytes(STAGES_MAIN, false) <= 232448 && smem_bytes(STAGES_PF, true) <= 232448, "shared memory budget");
 constexpr int MAX_TAPS = 16;
@@ -55,6 +59,7 @@ struct Conv2KArgs {
   int n_pass;
   int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
+  epi2::Geo tma;              // TMA epilogue (conv_epilogue_tma.cuh; PF build only)
   long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
 };
 
@@ -151,7 +156,8 @@ template <int STAGES, bool PF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-                  const __grid_constant__ Conv2KArgs a) {
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
+                  const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ Conv2KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -175,6 +181,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 16); }   // 8 warps x 2 CTAs
+    if (PF && a.tma.on) {
+      uint8_t* aux = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + epi2::NUM_WARPS * epi2::WARP_BYTES;
+      for (int i = 0; i < epi2::NUM_WARPS; ++i)
+        tc::mbar_init(reinterpret_cast<uint64_t*>(aux + i * epi2::WARP_AUX_BYTES + 384), 1);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -277,6 +288,48 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp >= 4 && PF && a.tma.on) {
+    // ===================== TMA epilogue (both CTAs, own 128 rows; conv_epilogue_tma.cuh) =====================
+    const int ew = (warp - 4) & 3;        // TMEM lane quarter
+    const int eh = (warp - 4) >> 2;       // even / odd chunks
+    const int ewi = warp - 4;
+    const epi::Params& ep = a.ep;
+    uint8_t* tiles = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + ewi * epi2::WARP_BYTES;
+    uint8_t* aux = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + epi2::NUM_WARPS * epi2::WARP_BYTES + ewi * epi2::WARP_AUX_BYTES;
+    epi2::WarpState ws;
+    ws.stage = tc::smem_u32(tiles); ws.slot_add = ws.stage + epi2::TILE_BYTES; ws.slot_gate = ws.stage + 2 * epi2::TILE_BYTES;
+    ws.tab = tc::smem_u32(aux); ws.bar = ws.tab + 384; ws.phase = 0; ws.requested = 0;
+    const int lin = ew * 32;              // first accumulator row of this warp's quarter
+    const int bwbh = a.bw * a.bh;
+    const int q_dn = lin / bwbh, q_dh = (lin - q_dn * bwbh) / a.bw, q_dw = lin - q_dn * bwbh - q_dh * a.bw;
+    auto quarter = [&](const TileInfo& ti) -> epi2::Quarter {
+      epi2::Quarter q;
+      q.x = ti.w0 + q_dw; q.y = ti.h0 + q_dh; q.z = ti.n0 + q_dn;
+      q.active = ((uint32_t)lin < rows_a && q.x < a.ow && q.y < a.oh && q.z < a.n) ? 1 : 0;
+      return q;
+    };
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int pair = cluster_id; pair < a.num_pairs; pair += num_clusters) {
+      const TileInfo t = decode_tile(a, pair, (int)rank);
+      const epi2::Quarter q = quarter(t);
+      const bool have_next = pair + num_clusters < a.num_pairs;
+      TileInfo tn = t;
+      if (have_next) tn = decode_tile(a, pair + num_clusters, (int)rank);
+      const epi2::Quarter qn = quarter(tn);
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+      const int m_idx = (pair / a.n_tiles_n) * 2 + (int)rank;
+      const int stat_row = m_idx < a.tiles_w * a.tiles_h * a.tiles_n ? m_idx * 4 + ew : -1;   // phantom tile: none
+      epi2::drain_tile(ep, &tmD, &tmAdd, &tmGate, ws, taddr, BLOCK_N, t.n_idx * BLOCK_N, q, have_next, tn.n_idx * BLOCK_N, qn,
+                       lane, eh, stat_row, [&]() {
+        tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) epi2::bulk_wait0();    // the last stores have left shared memory (and completed) before the CTA exits
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows; conv_epilogue.cuh) =====================
     const int ew = (warp - 4) & 3;        // TMEM lane quarter
@@ -343,6 +396,9 @@ extern int g_conv_tap_outer;
 // addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
 // Override: environment B200SEG_PF_MAX_K or b2_debug_set(4, v).
 int g_conv_pf_max_k = -1;
+// TMA epilogue of the PF build (conv_epilogue_tma.cuh): 1 = on where usable (default), 0 = register epilogue everywhere.
+// Override: environment B200SEG_TMA_EPI or b2_debug_set(8, v).
+int g_conv_tma_epi = -1;
 static long long* g_conv_trace = nullptr;
 extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
@@ -402,8 +458,38 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
     const char* e = getenv("B200SEG_PF_MAX_K");
     g_conv_pf_max_k = e ? atoi(e) : 512;
   }
-  const bool use_pf = g_conv_pf_max_k > 0 && (p->addend || p->gate) && a.ep.vec_ok && p->n_split == 1 &&
-                      (int64_t)p->k * p->n_taps <= g_conv_pf_max_k;
+  if (g_conv_tma_epi < 0) {
+    const char* e = getenv("B200SEG_TMA_EPI");
+    g_conv_tma_epi = e ? atoi(e) : 1;
+  }
+  const bool small_k = g_conv_pf_max_k > 0 && (int64_t)p->k * p->n_taps <= g_conv_pf_max_k;
+  // TMA epilogue (conv_epilogue_tma.cuh): the 32 accumulator rows of a TMEM lane quarter must be one rectangular pixel box
+  // of the output tensor, written densely (unit output stride, no phase offset) through 16 B aligned pointers / pitches.
+  CUtensorMap tmD = tmA, tmAdd = tmA, tmGate = tmA;        // placeholders unless the TMA epilogue is on
+  {
+    int ex = 0, ey = 0, ez = 0;
+    const int rows_a = a.bw * a.bh * a.bn;
+    if (a.bw % 32 == 0) { ex = 32; ey = 1; ez = 1; }
+    else if (32 % a.bw == 0 && a.bh % (32 / a.bw) == 0) { ex = a.bw; ey = 32 / a.bw; ez = 1; }
+    else if (32 % (a.bw * a.bh) == 0) { ex = a.bw; ey = a.bh; ez = 32 / (a.bw * a.bh); }
+    const bool tma_ok = g_conv_tma_epi > 0 && small_k && ex > 0 && rows_a % 32 == 0 && a.ep.vec_ok && p->ostride == 1 &&
+                        p->ooh == 0 && p->oow == 0 && p->oh == p->fh && p->ow == p->fw && !p->stats_sub &&
+                        !(g_conv_epi_debug & 3);
+    if (tma_ok) {
+      const uint32_t box[4] = {32, (uint32_t)ex, (uint32_t)ey, (uint32_t)ez};
+      const uint32_t es[4] = {1, 1, 1, 1};
+      auto out_map = [&](CUtensorMap* m, const void* ptr, int ld) -> int {
+        const uint64_t dims[4] = {(uint64_t)p->nb, (uint64_t)p->ow, (uint64_t)p->oh, (uint64_t)p->n};
+        const uint64_t strides[3] = {(uint64_t)ld * 4, (uint64_t)p->ow * ld * 4, (uint64_t)p->oh * p->ow * ld * 4};
+        return tc::make_tmap_f32(m, ptr, 4, dims, strides, box, es);
+      };
+      int rc = out_map(&tmD, p->d, p->ldd); if (rc) return rc;
+      if (p->addend) { rc = out_map(&tmAdd, p->addend, p->ld_add); if (rc) return rc; }
+      if (p->gate) { rc = out_map(&tmGate, p->gate, p->ld_gate); if (rc) return rc; }
+      a.tma.on = 1; a.tma.ex = ex; a.tma.ey = ey; a.tma.ez = ez;
+    }
+  }
+  const bool use_pf = a.tma.on || (small_k && (p->addend || p->gate) && a.ep.vec_ok && p->n_split == 1);
   int sms = b2_sm_count_cached();
   if (sms <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_gemm: no CUDA device");
   if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
@@ -411,9 +497,9 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   if (clusters < 1) clusters = 1;
   if (clusters > a.num_pairs) clusters = a.num_pairs;
   if (use_pf)
-    conv_gemm2_kernel<STAGES_PF, true><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+    conv_gemm2_kernel<STAGES_PF, true><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   else
-    conv_gemm2_kernel<STAGES_MAIN, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+    conv_gemm2_kernel<STAGES_MAIN, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   B2_LAUNCH_CHECK("conv_gemm2_kernel");
   return B2_OK;
 }

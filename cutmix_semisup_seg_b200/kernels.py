@@ -19,6 +19,7 @@ def _pad4(v):
 
 class ActKernels(object):
     name = 'cuda'
+    KCHUNK_FWD = 2304       # parity mode (3xTF32): reduction terms per TMEM accumulation of a forward convolution
 
     def __init__(self, backend=None, n_split=1):
         self.be = backend if backend is not None else O.default_backend()
@@ -72,9 +73,25 @@ class ActKernels(object):
             npix = x.rows
             be.conv_gemm(xa.ptr, 1, 1, npix, cin, xa.ld, wb.data_ptr(), cout, 1, ldb, out.ptr, 1, npix, 1, npix, out.ld,
                          taps, **kwargs)
-        else:
+            return
+        if self.n_split > 1 and cin * len(taps) > self.KCHUNK_FWD and scale is None and addend is None and gate is None:
+            # Parity mode, long reductions (ASPP / DeepLab v2 classifier: K = 2048 x 9 = 18432): tcgen05 accumulates in fp32
+            # with TRUNCATION, so the error of one TMEM accumulation grows linearly with K (1.4e-4 of the output range at
+            # K = 18432, measured).  Run the taps in groups of <= KCHUNK_FWD reduction terms: partial sums are combined by the
+            # epilogue's round-to-nearest fp32 adds (accumulate / addend), which brings the error back to the K = 2048 level.
+            per = max(1, self.KCHUNK_FWD // cin)
+            groups = [taps[i:i + per] for i in range(0, len(taps), per)]
+            part = Act.alloc(out.n, out.h, out.w, cout, out.device)
+            raw = dict(a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
+            for gi, grp in enumerate(groups[:-1]):
+                be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, part.ptr, out.h, out.w,
+                             out.h, out.w, part.ld, grp, istride=stride, accumulate=gi > 0, **raw)
+            kwargs['addend'] = part.ptr; kwargs['ld_add'] = part.ld
             be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
-                         out.h, out.w, out.ld, taps, istride=stride, **kwargs)
+                         out.h, out.w, out.ld, groups[-1], istride=stride, **kwargs)
+            return
+        be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
+                     out.h, out.w, out.ld, taps, istride=stride, **kwargs)
 
     def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False,
                    want_stats=False, stats_sub=None):

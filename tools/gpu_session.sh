@@ -34,6 +34,13 @@ case $stage in
     paste -d'|' <(cut -c1-75 gpurun_out/micro_${tag}_tapouter0.log) <(cut -c46-75 gpurun_out/micro_${tag}_tapouter1.log) | head -40
     B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3
     ;;
+  second)     # TMA epilogue A/B + bit-exactness, the tests that failed in the first call, a bench line
+    timeout -s KILL 600 python tools/aspp_bench.py 3 tma > gpurun_out/micro_${tag}_tma.log 2>&1; cut -c1-200 gpurun_out/micro_${tag}_tma.log
+    run_tests $tag tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_zzy_gpu_deeplab3.py tests/test_zzy_gpu_denseunet.py tests/test_gpu_nets.py tests/test_gpu_netops.py
+    grep -h "denseunet\|dl3 (v3)" gpurun_out/pytest_$tag.log | head; cat gpurun_out/parity_$tag.txt | grep -v "^conv cfg3" | cut -c1-250
+    B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    head -30 gpurun_out/shape_profile_$tag.txt
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
