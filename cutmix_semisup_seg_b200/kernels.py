@@ -19,7 +19,7 @@ def _pad4(v):
 
 class ActKernels(object):
     name = 'cuda'
-    KCHUNK_FWD = 2304       # parity mode (3xTF32): reduction terms per TMEM accumulation of a forward convolution
+    KCHUNK = 1024           # parity mode (3xTF32): reduction terms per TMEM accumulation of a forward / dgrad GEMM
 
     def __init__(self, backend=None, n_split=1):
         self.be = backend if backend is not None else O.default_backend()
@@ -53,17 +53,65 @@ class ActKernels(object):
         return True
 
     # ------------------------------------------------------------------------------ convolution
+    def _chunks(self, taps, k):
+        """[(tap group, first channel, channels)] of one convolution GEMM.  Throughput mode: one launch.  Parity mode (3xTF32):
+        tcgen05 accumulates in fp32 with TRUNCATION, so the error of one TMEM accumulation grows linearly with its reduction
+        length (measured: 1.5e-6 of the output range at K = 64, 2e-5 at 2304, 1.4e-4 at 18432); reductions longer than KCHUNK
+        terms therefore run as several launches over tap groups / channel ranges whose partial results are combined by the
+        epilogue's round-to-nearest fp32 adds."""
+        limit = self.KCHUNK if self.n_split > 1 else 0
+        if not limit or k * len(taps) <= limit:
+            return [(taps, 0, k)]
+        if k > limit:
+            return [([t], c0, min(limit, k - c0)) for t in taps for c0 in range(0, k, limit)]
+        per = max(1, limit // k)
+        return [(taps[i:i + per], 0, k) for i in range(0, len(taps), per)]
+
+    def _gemm(self, a, a_lo, n, ih, iw, k, lda, b, b_lo, nb, tb, ldb, out_ptr, out_ld, oh, ow, taps, device, istride=1, **ep):
+        """One logical convolution GEMM D = epilogue(sum_{tap, k} A B) through b2_conv_gemm (raw pointers; a_lo / b_lo: the
+        low parts of the operand splits in parity mode).  Chunked launches use the linearity of the epilogue up to the ReLU:
+        chunk 0 writes scale * acc_0 (+ addend) to a scratch buffer, the middle chunks accumulate scale * acc_i into it, the
+        last launch adds it through the addend slot and applies shift / ReLU / gate / statistics / accumulate."""
+        be = self.be
+        base = dict(n_split=self.n_split)
+        chunks = self._chunks(taps, k)
+
+        def ptrs(c_off):
+            d = dict(base)
+            d['a_lo_ptr'] = None if a_lo is None else a_lo + 4 * c_off
+            d['b_lo_ptr'] = None if b_lo is None else b_lo + 4 * c_off
+            return a + 4 * c_off, b + 4 * c_off, d
+        if len(chunks) == 1:
+            ap, bp, d = ptrs(0)
+            return be.conv_gemm(ap, n, ih, iw, k, lda, bp, nb, tb, ldb, out_ptr, oh, ow, oh, ow, out_ld, taps, istride=istride,
+                                **d, **ep)
+        assert ep.get('scale2') is None, 'chunked launches do not support scale2'
+        part_ld = _pad4(nb)
+        part = torch.empty((n * oh * ow, part_ld), device=device, dtype=torch.float32)
+        for ci, (grp, c_off, kc) in enumerate(chunks[:-1]):
+            ap, bp, d = ptrs(c_off)
+            d['scale'] = ep.get('scale')
+            if ci == 0 and ep.get('addend') is not None:
+                d['addend'] = ep['addend']; d['ld_add'] = ep['ld_add']
+            be.conv_gemm(ap, n, ih, iw, kc, lda, bp, nb, tb, ldb, part.data_ptr(), oh, ow, oh, ow, part_ld, grp, istride=istride,
+                         accumulate=ci > 0, **d)
+        grp, c_off, kc = chunks[-1]
+        ap, bp, d = ptrs(c_off)
+        last = dict(ep)
+        last['addend'] = part.data_ptr(); last['ld_add'] = part_ld
+        return be.conv_gemm(ap, n, ih, iw, kc, lda, bp, nb, tb, ldb, out_ptr, oh, ow, oh, ow, out_ld, grp, istride=istride,
+                            **d, **last)
+
     def conv_fwd(self, x, w, cout, kh, kw, cin, ldb, stride, pad, dil, out, scale=None, shift=None, addend=None,
                  gate=None, relu=False):
         """out = epilogue(conv(x, w)).  w: tensor whose storage is (cout, kh*kw, ldb)."""
-        be = self.be
         a_lo = b_lo = None
         xa, wb = x, w
         if self.n_split > 1:
             xa, xlo = self._split_act(x)
             wb, wlo = self._split_w(w)
             a_lo, b_lo = xlo.ptr, wlo.data_ptr()
-        kwargs = dict(scale=scale, shift=shift, relu=relu, a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
+        kwargs = dict(scale=scale, shift=shift, relu=relu)
         if addend is not None:
             kwargs['addend'] = addend.ptr; kwargs['ld_add'] = addend.ld
         if gate is not None:
@@ -71,27 +119,11 @@ class ActKernels(object):
         taps = O.conv_taps(kh, kw, dil, pad)
         if kh == 1 and kw == 1 and stride == 1 and pad == 0:
             npix = x.rows
-            be.conv_gemm(xa.ptr, 1, 1, npix, cin, xa.ld, wb.data_ptr(), cout, 1, ldb, out.ptr, 1, npix, 1, npix, out.ld,
-                         taps, **kwargs)
+            self._gemm(xa.ptr, a_lo, 1, 1, npix, cin, xa.ld, wb.data_ptr(), b_lo, cout, 1, ldb, out.ptr, out.ld, 1, npix, taps,
+                       x.device, **kwargs)
             return
-        if self.n_split > 1 and cin * len(taps) > self.KCHUNK_FWD and scale is None and addend is None and gate is None:
-            # Parity mode, long reductions (ASPP / DeepLab v2 classifier: K = 2048 x 9 = 18432): tcgen05 accumulates in fp32
-            # with TRUNCATION, so the error of one TMEM accumulation grows linearly with K (1.4e-4 of the output range at
-            # K = 18432, measured).  Run the taps in groups of <= KCHUNK_FWD reduction terms: partial sums are combined by the
-            # epilogue's round-to-nearest fp32 adds (accumulate / addend), which brings the error back to the K = 2048 level.
-            per = max(1, self.KCHUNK_FWD // cin)
-            groups = [taps[i:i + per] for i in range(0, len(taps), per)]
-            part = Act.alloc(out.n, out.h, out.w, cout, out.device)
-            raw = dict(a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
-            for gi, grp in enumerate(groups[:-1]):
-                be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, part.ptr, out.h, out.w,
-                             out.h, out.w, part.ld, grp, istride=stride, accumulate=gi > 0, **raw)
-            kwargs['addend'] = part.ptr; kwargs['ld_add'] = part.ld
-            be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
-                         out.h, out.w, out.ld, groups[-1], istride=stride, **kwargs)
-            return
-        be.conv_gemm(xa.ptr, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), cout, kh * kw, ldb, out.ptr, out.h, out.w,
-                     out.h, out.w, out.ld, taps, istride=stride, **kwargs)
+        self._gemm(xa.ptr, a_lo, x.n, x.h, x.w, cin, xa.ld, wb.data_ptr(), b_lo, cout, kh * kw, ldb, out.ptr, out.ld, out.h, out.w,
+                   taps, x.device, istride=stride, **kwargs)
 
     def conv_dgrad(self, g, wt, cin, kh, kw, cout, ldb, stride, pad, dil, dx, addend=None, gate=None, accumulate=False,
                    want_stats=False, stats_sub=None):
@@ -110,7 +142,7 @@ class ActKernels(object):
             a_lo, b_lo = glo.ptr, wlo.data_ptr()
         common = dict(a_lo_ptr=a_lo, b_lo_ptr=b_lo, n_split=self.n_split)
         if stride == 1:
-            kwargs = dict(common, accumulate=accumulate)
+            kwargs = dict(accumulate=accumulate)
             if addend is not None:
                 kwargs['addend'] = addend.ptr; kwargs['ld_add'] = addend.ld
             if gate is not None:
@@ -123,10 +155,10 @@ class ActKernels(object):
             taps = O.dgrad_taps(kh, kw, dil, pad)
             if kh == 1 and kw == 1 and pad == 0:
                 npix = g.rows
-                return be.conv_gemm(ga.ptr, 1, 1, npix, cout, ga.ld, wb.data_ptr(), cin, 1, ldb, dx.ptr, 1, npix, 1, npix,
-                                    dx.ld, taps, **kwargs)
-            return be.conv_gemm(ga.ptr, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), cin, kh * kw, ldb, dx.ptr, dx.h, dx.w,
-                                dx.h, dx.w, dx.ld, taps, **kwargs)
+                return self._gemm(ga.ptr, a_lo, 1, 1, npix, cout, ga.ld, wb.data_ptr(), b_lo, cin, 1, ldb, dx.ptr, dx.ld, 1, npix,
+                                  taps, g.device, **kwargs)
+            return self._gemm(ga.ptr, a_lo, g.n, g.h, g.w, cout, ga.ld, wb.data_ptr(), b_lo, cin, kh * kw, ldb, dx.ptr, dx.ld,
+                              dx.h, dx.w, taps, g.device, **kwargs)
         assert addend is None and gate is None and not want_stats, 'strided dgrad is not fused'
         if not accumulate:
             self.fill_act(dx, 0.0)
@@ -166,6 +198,15 @@ class ActKernels(object):
             be.conv_wgrad(ga.ptr, g.n, g.h, g.w, cout, ga.ld, xa.ptr, x.h, x.w, cin, xa.ld, dw.data_ptr(), taps, kh * kw,
                           istride=stride, accumulate=accumulate, dy_lo_ptr=y_lo, x_lo_ptr=x_lo, n_split=self.n_split,
                           device=g.device, row_scale=row_scale, kchunk=self.kchunk)
+
+    # multi-tensor forms: one launch for all frozen BatchNorms of a network / all dgrad operands of a backward pass
+    multi_tensor = True
+
+    def bn_fold_multi(self, table, n_entries, max_c):
+        self.be.bn_fold_multi(table, n_entries, max_c)
+
+    def transpose_w_multi(self, table, n_entries, total_blocks):
+        self.be.transpose_w_multi(table, n_entries, total_blocks)
 
     def transpose_w(self, w, cout, t, cin, scale=None):
         """(cout, t, cin) -> (cin, t, pad4(cout)) with optional per-cout scale.  Returns (tensor, ldb)."""

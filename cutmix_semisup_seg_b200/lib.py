@@ -108,6 +108,8 @@ _SIGS = {
     'b2_conv_wgrad_plan_check': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b2_transpose_w': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'b2_bn_fold_multi': (c_int, [c_vp, c_int, c_int, c_vp]),
+    'b2_transpose_w_multi': (c_int, [c_vp, c_int, c_i64, c_vp]),
     'b2_relu_gate': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp]),
     'b2_slice_copy': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
     'b2_nchw_to_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

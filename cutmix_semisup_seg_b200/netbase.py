@@ -112,6 +112,7 @@ class B2SegNet(nn.Module):
                                'network to a CUDA device)')
         x = x.detach().to(torch.float32)
         tape = E.Tape(K, enabled=record)
+        E.prefold(K, self)                      # every frozen BatchNorm of the network in one launch
         xin = K.nchw_to_act(x, 4)
         xin.needs_grad = bool(input_grad and record)
         low, align = self._graph(tape, xin, x.shape[2], x.shape[3])
@@ -137,6 +138,7 @@ class B2SegNet(nn.Module):
         x_all = torch.cat([x.detach().to(torch.float32) for x in xs], dim=0)
         in_h, in_w = x_all.shape[2], x_all.shape[3]
         tape = E.Tape(K, enabled=record)
+        E.prefold(K, self)
         xin = K.nchw_to_act(x_all, 4)
         xin.needs_grad = False
         feats = self._graph_trunk(tape, xin, in_h, in_w)

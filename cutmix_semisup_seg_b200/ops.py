@@ -372,6 +372,15 @@ class CudaBackend(object):
         self._call('b2_transpose_w', w.data_ptr(), out.data_ptr(), a, t, b, ldd, L.ptr(scale), self._s())
         return out
 
+    # ------------------------------------------------------------------ multi-tensor derived-weight kernels (csrc/multi.cu)
+    def bn_fold_multi(self, table, n_entries, max_c):
+        """table: device uint8 tensor holding n_entries b2_bn_fold_entry records (include/b200seg.h)."""
+        self._call('b2_bn_fold_multi', table.data_ptr(), int(n_entries), int(max_c), self._s())
+
+    def transpose_w_multi(self, table, n_entries, total_blocks):
+        """table: device uint8 tensor holding n_entries b2_transpose_entry records."""
+        self._call('b2_transpose_w_multi', table.data_ptr(), int(n_entries), int(total_blocks), self._s())
+
     # ------------------------------------------------------------------ tensor-core convolution
     def conv_gemm(self, a_ptr, n, ih, iw, k, lda, b_ptr, nb, tb, ldb, d_ptr, oh, ow, fh, fw, ldd, taps,
                   ostride=1, ooh=0, oow=0, istride=1, scale=None, shift=None, addend=None, ld_add=0,

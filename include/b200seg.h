@@ -335,6 +335,22 @@ int b2_split_tf32(const float* x, float* hi, float* lo, int64_t count, void* str
 int b2_transpose_w(const float* src, float* dst, int a, int t, int b, int ldd, const float* scale_a,
                    void* stream);
 
+/* Multi-tensor forms (ONE launch per network and pass; tables in DEVICE memory, built once by the caller).  Replace the
+ * per-layer launches of b2_bn_fold / b2_transpose_w in the iteration (reference: the BatchNorm modules in eval mode under
+ * freeze_batchnorm, deeplab2.py:244-245 / deeplab3plus.py:120-121, and autograd's transposed-weight convolutions). */
+typedef struct {
+  const float* gamma; const float* beta; const float* mean; const float* var;
+  float* scale; float* shift;
+  int32_t c; float eps;
+} b2_bn_fold_entry;                       /* 56 bytes */
+int b2_bn_fold_multi(const b2_bn_fold_entry* table, int n_entries, int max_c, void* stream);
+typedef struct {
+  const float* src; float* dst; const float* scale;      /* scale: per-A factor or NULL */
+  int32_t a, t, b, ldd;
+  int64_t block_begin;                    /* prefix sum of ceil(b/32) * ceil(ldd/32) * t over the preceding entries */
+} b2_transpose_entry;                     /* 48 bytes */
+int b2_transpose_w_multi(const b2_transpose_entry* table, int n_entries, int64_t total_blocks, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * HBM-bound network ops (NHWC fp32).
  * ------------------------------------------------------------------------------------------ */

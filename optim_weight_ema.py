@@ -53,13 +53,25 @@ class EMAWeightOptimizer(object):
         self._table_key = ptr_key
         self._n_chunks = arr.shape[0]
 
+    def _host_step(self):
+        """Both networks live on the CPU (`toy2d_train.py --device cpu`, BASELINE config 1: the reference's CPU plumbing
+        configuration): the update in host arithmetic, with the reference's three fp32 roundings (optim_weight_ema.py:21-25).
+        This is a device TARGET the caller chose for the whole model, not a fallback: CUDA tensors never take this path, and a
+        CUDA / CPU mixture is refused below."""
+        one_minus_alpha = 1.0 - self.ema_alpha
+        for tgt_p, src_p in zip(self.target_params, self.source_params):
+            tgt_p.mul_(self.ema_alpha)
+            tgt_p.add_(src_p * one_minus_alpha)
+
     def step(self):
         if len(self.target_params) == 0:
             return
         dev = self.target_params[0].device
+        if all(p.device.type == 'cpu' for p in self.target_params + self.source_params):
+            return self._host_step()
         if dev.type != 'cuda' or any(p.device != dev for p in self.target_params + self.source_params):
-            raise RuntimeError('EMAWeightOptimizer (B200 hot path) needs all tensors on one CUDA device; '
-                               'there is no CPU fallback')
+            raise RuntimeError('EMAWeightOptimizer (B200 hot path) needs all tensors on one CUDA device (or all of them on '
+                               'the CPU for the toy-2D plumbing configuration); a device mixture is refused')
         from cutmix_semisup_seg_b200 import ops, engine
         be = ops.default_backend()
         engine.invalidate_caches()      # the kernel writes the teacher through raw pointers (no torch version bump)

@@ -475,8 +475,80 @@ def gen_entry_point():
     json.dump(out, open(os.path.join(OUT, 'entry_point.json'), 'w'), indent=1)
 
 
+def gen_toy2d():
+    """BASELINE config 1: the reference's OWN job function `toy2d_train.train_toy2d` (imported unmodified from /root/reference) run
+    on the cases of tests/toy2d_recipe.py with torch.manual_seed(TORCH_SEED).  The reference's `toy2d/generate_data.py` cannot be
+    imported here (scikit-image, batchup), so the data-set module it asks for is this repository's drop-in (toy2d/generate_data.py:
+    same classes / arithmetic, pinned against the reference's committed pickle by tests/test_toy2d.py); everything the job
+    function itself does -- network, loaders, perturbation, losses, Adam, EMAWeightOptimizer (the reference's), report -- is
+    reference code.  -> tests/golden/toy2d.json"""
+    import contextlib
+    import importlib.util
+    import io
+    import tempfile
+    repo = os.path.dirname(HERE)
+    sys.path.insert(0, os.path.join(repo, 'tests'))
+    import toy2d_recipe as T
+    pkg_dir = os.path.join(repo, 'toy2d')
+    spec = importlib.util.spec_from_file_location('toy2d', os.path.join(pkg_dir, '__init__.py'), submodule_search_locations=[pkg_dir])
+    pkg = importlib.util.module_from_spec(spec); sys.modules['toy2d'] = pkg; spec.loader.exec_module(pkg)
+    spec2 = importlib.util.spec_from_file_location('toy2d.generate_data', os.path.join(pkg_dir, 'generate_data.py'))
+    mod = importlib.util.module_from_spec(spec2); sys.modules['toy2d.generate_data'] = mod; spec2.loader.exec_module(mod)
+    pkg.generate_data = mod
+    import toy2d_train                                   # the reference's script
+    assert os.path.realpath(toy2d_train.__file__).startswith(os.path.realpath(REF))
+    assert os.path.realpath(optim_weight_ema.__file__).startswith(os.path.realpath(REF))
+
+    class Cfg(object):
+        def __init__(self, run_dir):
+            self.run_dir = run_dir
+    out = dict(torch_seed=T.TORCH_SEED, cases={})
+    with tempfile.TemporaryDirectory() as tmp:
+        mask = os.path.join(tmp, 'mask.png')
+        T.write_mask_png(mask)
+        for name in T.CASES:
+            p = T.params(name, mask)
+            torch.manual_seed(T.TORCH_SEED)
+            buf = io.StringIO()
+            run_dir = os.path.join(tmp, name); os.makedirs(run_dir)
+            exact = dict(epochs=[])
+
+            def spy(*a, **k):
+                """The job's own print: the report lines carry 6 decimals only, so the un-rounded accumulators and the final
+                networks are read from the job function's frame at the moment it prints them."""
+                import inspect
+                loc = inspect.currentframe().f_back.f_locals
+                line = ' '.join(str(v) for v in a)
+                if line.startswith('Epoch '):
+                    exact['epochs'].append([float(loc['batch_sup_loss_accum']), float(loc['batch_conf_mask_sum_accum']),
+                                            float(loc['batch_cons_loss_accum'])])
+                elif line.startswith('FINAL RESULT'):
+                    exact['error_rate'] = float(loc['err_rate'])
+                    for tag in ('student_net', 'teacher_net'):
+                        net = loc.get(tag)
+                        if net is not None:
+                            sd = net.state_dict()
+                            exact[tag] = dict(abs_sum=float(sum(v.double().abs().sum() for v in sd.values() if v.dtype == torch.float32)),
+                                              l_final=[float(v) for v in sd['l_final.weight'].reshape(-1)[:8]])
+                buf.write(line + '\n')
+            toy2d_train.print = spy
+            try:
+                toy2d_train.train_toy2d(Cfg(run_dir), **p)
+            finally:
+                del toy2d_train.print
+            epochs, final = T.parse_report(buf.getvalue())
+            assert len(epochs) == p['num_epochs'] and final is not None, buf.getvalue()
+            out['cases'][name] = dict(epochs=epochs, final_error_pct=final, n_images=len(os.listdir(run_dir)), exact=exact)
+            print(' ', name, exact['epochs'], exact['error_rate'])
+    json.dump(out, open(os.path.join(OUT, 'toy2d.json'), 'w'), indent=1)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:                      # regenerate selected fixtures only: python gen_golden.py toy2d masks ...
+        for name in sys.argv[1:]:
+            globals()['gen_' + name](); print(name)
+        sys.exit(0)
     gen_entry_point(); print('entry point')
     gen_ict_block(); print('ict block')
     gen_aug_block(); print('aug block')

@@ -297,8 +297,9 @@ def test_deeplab3plus_cutmix_iterations_match_oracle():
                 r = ref[k].detach()
                 worst = max(worst, (v.cpu() - r).abs().max().item() / (r.abs().max().item() + 1e-12))
         _log('dl3+ cutmix iterations: %s state max rel diff after 3 steps %.2e' % (name, worst))
-        # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr per step
-        assert worst < 1.5e-3, (name, worst)
+        # Adam normalises gradients: a weight whose tiny gradient changes sign moves by up to +-lr per step, relative to a
+        # tensor range that can be as small as ~1e-2 (BatchNorm shifts): 1e-3 of the range per step
+        assert worst < 3e-3, (name, worst)
 
 
 FULLSIZE_TOL = {
