@@ -284,6 +284,22 @@ class CudaBackend(object):
         self._call('b2_u8_to_tensor', mask_u8.data_ptr(), mask_u8.numel(), 1, out.data_ptr(), self._s())
         return out
 
+    def crop_flip_normalize(self, table, n, out_h, out_w, mean, std, want_labels, want_mask, device):
+        """Fused pad / crop / flip / normalise-to-tensor gather (b2_crop_flip_normalize).  table: device uint8 tensor of n
+        b2_crop_entry records.  Returns (image fp32 (n,3,h,w), labels int64 (n,1,h,w) | None, mask fp32 (n,1,h,w) | None)."""
+        if (mean is None) != (std is None):
+            raise ValueError('mean and std must be given together')
+        image = torch.empty((n, 3, out_h, out_w), device=device, dtype=torch.float32)
+        labels = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.int64) if want_labels else None
+        mask = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.float32) if want_mask else None
+        m = s_ = None
+        if mean is not None:
+            m = (ctypes.c_double * 3)(*[float(v) for v in mean])
+            s_ = (ctypes.c_double * 3)(*[float(v) for v in std])
+        self._call('b2_crop_flip_normalize', table.data_ptr(), int(n), int(out_h), int(out_w), m, s_, image.data_ptr(), L.ptr(labels),
+                   L.ptr(mask), self._s())
+        return image, labels, mask
+
     # ------------------------------------------------------------------ VAT (train_seg_semisup_vat_mt.py:214-301)
     def sample_l2norm(self, x):
         """mag[i] = sqrt(sum of squares of sample i) (normalize_eps, :217-219).  x: (N, ...) fp32 contiguous."""

@@ -188,6 +188,26 @@ int b2_normalize_to_tensor(const uint8_t* img, int n, int h, int w, int cin, con
                            float* out, void* stream);
 int b2_u8_to_tensor(const uint8_t* src, int64_t count, int mode, void* dst, void* stream);
 
+/* Device crop + flip + normalise: SegCVTransformPad (datapipe/seg_transforms_cv.py:30-99) + SegCVTransformRandomCrop (:102-167)
+ * + SegCVTransformRandomFlip (:445-520) + SegCVTransformNormalizeToTensor (:587-672) in one gather pass over variable-size uint8
+ * source images.  The random parameters are drawn on the host in the reference's order (cutmix_semisup_seg_b200/input_pipeline.py);
+ * `table` is a DEVICE array of n entries.  Outputs: image fp32 (n,3,out_h,out_w); labels int64 (n,1,out_h,out_w) or NULL
+ * (255 in the padding and when an entry has no labels); mask fp32 (n,1,out_h,out_w) or NULL (0 in the padding).
+ * out_h x out_w is the crop size (transposed samples, flip_d, need a square crop). */
+typedef struct {
+  const uint8_t* image;        /* DEVICE (h0, w0, 3) uint8 */
+  const uint8_t* labels;       /* DEVICE (h0, w0) uint8 or NULL */
+  const uint8_t* mask;         /* DEVICE (h0, w0) uint8 or NULL */
+  int32_t h0, w0;              /* source size */
+  int32_t pad_top, pad_left;   /* rows / columns of padding in front of the source (pad_h // 2, pad_w // 2) */
+  int32_t padded;              /* 1: the reference would have padded this sample (alpha-channel standardisation) */
+  int32_t pos_y, pos_x;        /* crop origin in padded coordinates */
+  int32_t crop_h, crop_w;
+  int32_t flip_x, flip_y, flip_d;
+} b2_crop_entry;               /* 72 bytes */
+int b2_crop_flip_normalize(const b2_crop_entry* table, int n, int out_h, int out_w, const double* mean3, const double* std3,
+                           float* image, int64_t* labels, float* mask, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * U-Net decoder operators -- architectures/resunet.py:10-34, 57-92 (identical in denseunet.py:10-34, 98-124); NHWC fp32
  *   b2_upsample2x_add: y (N,2H,2W,C; ldy) = nearest x2 up-sampling of x (N,H,W,C; ldx) [+ skip (N,2H,2W,C; lds)]   (:31-32, :87)

@@ -14,7 +14,11 @@ _CHUNK = 16384  # elements per thread block, must match EMA_CHUNK in csrc/elemen
 
 
 class EMAWeightOptimizer(object):
-    def __init__(self, target_net, source_net, ema_alpha):
+    def __init__(self, target_net, source_net, ema_alpha, host_arithmetic=False):
+        """`host_arithmetic=True` (new, opt-in): both networks live on the CPU and `step()` runs in host arithmetic -- only the
+        toy-2D plumbing configuration asks for it (`toy2d_train.py --device cpu`, BASELINE config 1).  Without it CPU tensors are
+        refused: the segmentation hot path has no CPU fallback."""
+        self.host_arithmetic = bool(host_arithmetic)
         self.target_net = target_net
         self.source_net = source_net
         self.ema_alpha = ema_alpha
@@ -56,8 +60,10 @@ class EMAWeightOptimizer(object):
     def _host_step(self):
         """Both networks live on the CPU (`toy2d_train.py --device cpu`, BASELINE config 1: the reference's CPU plumbing
         configuration): the update in host arithmetic, with the reference's three fp32 roundings (optim_weight_ema.py:21-25).
-        This is a device TARGET the caller chose for the whole model, not a fallback: CUDA tensors never take this path, and a
-        CUDA / CPU mixture is refused below."""
+        Opt-in through the constructor (a device TARGET the caller chose for the whole model, not a fallback): CUDA tensors
+        never take this path."""
+        if not all(p.device.type == 'cpu' for p in self.target_params + self.source_params):
+            raise RuntimeError('EMAWeightOptimizer(host_arithmetic=True) needs every tensor of both networks on the CPU')
         one_minus_alpha = 1.0 - self.ema_alpha
         for tgt_p, src_p in zip(self.target_params, self.source_params):
             tgt_p.mul_(self.ema_alpha)
@@ -67,11 +73,11 @@ class EMAWeightOptimizer(object):
         if len(self.target_params) == 0:
             return
         dev = self.target_params[0].device
-        if all(p.device.type == 'cpu' for p in self.target_params + self.source_params):
+        if self.host_arithmetic:
             return self._host_step()
         if dev.type != 'cuda' or any(p.device != dev for p in self.target_params + self.source_params):
-            raise RuntimeError('EMAWeightOptimizer (B200 hot path) needs all tensors on one CUDA device (or all of them on '
-                               'the CPU for the toy-2D plumbing configuration); a device mixture is refused')
+            raise RuntimeError('EMAWeightOptimizer (B200 hot path) needs all tensors on one CUDA device; '
+                               'there is no CPU fallback')
         from cutmix_semisup_seg_b200 import ops, engine
         be = ops.default_backend()
         engine.invalidate_caches()      # the kernel writes the teacher through raw pointers (no torch version bump)

@@ -475,6 +475,46 @@ def gen_entry_point():
     json.dump(out, open(os.path.join(OUT, 'entry_point.json'), 'w'), indent=1)
 
 
+def gen_input_pipeline():
+    """the reference's OWN transform classes SegCVTransformRandomCrop -> SegCVTransformRandomFlip ->
+    SegCVTransformNormalizeToTensor (datapipe/seg_transforms_cv.py, imported unmodified; OpenCV is installed) applied to seeded
+    uint8 samples of the cases in tests/input_recipe.py, single samples and pairs.  scikit-image is not installed, so the one
+    function the module takes from it, `img_as_float`, is provided as `np.multiply(a, 1/255, dtype=float64)` (skimage/util/dtype.py
+    `convert` for uint8 input; parity unpinned for that call).  -> tests/golden/input_pipeline.npz (outputs of every case)"""
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    import input_recipe as IR
+    fake = types.ModuleType('skimage')
+    fake.img_as_float = lambda a: np.multiply(a, 1. / 255, dtype=np.float64)
+    sys.modules.setdefault('skimage', fake)
+    from datapipe import seg_transforms_cv as TCV
+    assert os.path.realpath(TCV.__file__).startswith(os.path.realpath(REF))
+    out = {}
+    for name, case in IR.CASES.items():
+        crop = TCV.SegCVTransformRandomCrop(case['crop_size'], case['crop_offset'], rng=np.random.RandomState(case['seed']))
+        flip = TCV.SegCVTransformRandomFlip(case['hflip'], case['vflip'], case['hvflip'], rng=np.random.RandomState(case['seed'] + 1))
+        norm = TCV.SegCVTransformNormalizeToTensor(None if case['mean'] is None else np.array(case['mean']),
+                                                   None if case['std'] is None else np.array(case['std']))
+        samples = IR.make_samples(case)
+        res = []
+        for smp in samples:
+            if case['pair']:
+                a, b = crop.transform_pair(dict(smp), dict(smp))
+                a, b = flip.transform_pair(a, b)
+                a, b = norm.transform_pair(a, b)
+                res.extend([a, b])
+            else:
+                a = norm.transform_single(flip.transform_single(crop.transform_single(dict(smp))))
+                res.append(a)
+        out[name + '.image'] = np.stack([r['image'] for r in res])
+        if 'labels' in res[0]:
+            out[name + '.labels'] = np.stack([r['labels'] for r in res])
+        if 'mask' in res[0]:
+            out[name + '.mask'] = np.stack([r['mask'] for r in res])
+        print(' ', name, out[name + '.image'].shape, out[name + '.image'].dtype)
+    np.savez_compressed(os.path.join(OUT, 'input_pipeline.npz'), **out)
+
+
 def gen_toy2d():
     """BASELINE config 1: the reference's OWN job function `toy2d_train.train_toy2d` (imported unmodified from /root/reference) run
     on the cases of tests/toy2d_recipe.py with torch.manual_seed(TORCH_SEED).  The reference's `toy2d/generate_data.py` cannot be

@@ -81,3 +81,56 @@ def test_wrong_channel_count_is_rejected_like_the_reference():
         L.call('b2_normalize_to_tensor', 0x1000, 1, 4, 4, 2, None, None, 0x1000, None)
     with pytest.raises(L.B2Error, match='together'):
         L.call('b2_normalize_to_tensor', 0x1000, 1, 4, 4, 3, (L.ctypes.c_double * 3)(0, 0, 0), None, 0x1000, None)
+
+
+# ------------------------------------------------------------------------------------------ crop + flip + normalise
+def _drawn(case):
+    """Parameters drawn by DeviceCropFlipNormalize in the reference's order, and the samples (pairs: each sample twice)."""
+    import input_recipe as IR
+    from cutmix_semisup_seg_b200.input_pipeline import DeviceCropFlipNormalize
+    tf = DeviceCropFlipNormalize(case['crop_size'], case['crop_offset'], case['hflip'], case['vflip'], case['hvflip'], case['mean'],
+                                 case['std'], crop_rng=np.random.RandomState(case['seed']),
+                                 flip_rng=np.random.RandomState(case['seed'] + 1))
+    samples, params = [], []
+    for s in IR.make_samples(case):
+        # NOTE the reference draws crop parameters of ALL samples from the crop transform's generator and flips from the flip
+        # transform's, sample after sample (transform_single / transform_pair are called per sample by the data set accessor)
+        if case['pair']:
+            p0, p1 = tf.draw_pair(s['image_arr'].shape[:2])
+            samples += [s, s]; params += [p0, p1]
+        else:
+            samples.append(s); params.append(tf.draw_single(s['image_arr'].shape[:2]))
+    return tf, samples, params
+
+
+@pytest.mark.parametrize('name', ['single_flips', 'single_padded', 'pair_offset', 'pair_square'])
+def test_crop_flip_normalize_algorithm_matches_the_reference_transform_classes(name):
+    """The host-side parameter draws + the kernel's gather (stated in numpy, tests/input_recipe.py) reproduce, bit for bit,
+    what the reference's SegCVTransformRandomCrop -> RandomFlip -> NormalizeToTensor chain produced for the same seeds
+    (tests/golden/input_pipeline.npz, written by the reference's own classes)."""
+    import input_recipe as IR
+    gold = np.load(os.path.join(HERE, 'golden', 'input_pipeline.npz'))
+    case = IR.CASES[name]
+    tf, samples, params = _drawn(case)
+    got = IR.reference_statement(samples, params, case['crop_size'], case['mean'], case['std'])
+    assert np.array_equal(got['image'], gold[name + '.image']) and got['image'].dtype == np.float32
+    if case['labels']:
+        assert np.array_equal(got['labels'], gold[name + '.labels']) and got['labels'].dtype == np.int64
+    if case['mask']:
+        assert np.array_equal(got['mask'], gold[name + '.mask'])
+    if name == 'single_padded':
+        assert any(p['padded'] for p in params) and any(not p['padded'] for p in params)
+
+
+def test_crop_entry_table_layout_matches_the_header():
+    """72-byte records, field order of b2_crop_entry in include/b200seg.h."""
+    from cutmix_semisup_seg_b200.input_pipeline import DeviceCropFlipNormalize
+    img = torch.zeros((5, 7, 3), dtype=torch.uint8)
+    arr = DeviceCropFlipNormalize.table([dict(image_arr=img)], [dict(pad_top=1, pad_left=2, padded=1, pos=(3, 4), flips=(True, False, True))],
+                                        (8, 9))
+    assert arr.dtype.itemsize == 72 and arr.dtype.fields['h0'][1] == 24 and arr.dtype.fields['flip_d'][1] == 68
+    rec = arr[0]
+    assert rec['image'] == img.data_ptr() and rec['labels'] == 0 and (rec['h0'], rec['w0']) == (5, 7)
+    assert (rec['pos_y'], rec['pos_x'], rec['crop_h'], rec['crop_w']) == (3, 4, 8, 9) and (rec['flip_x'], rec['flip_y'], rec['flip_d']) == (1, 0, 1)
+    with pytest.raises(ValueError, match='square'):
+        DeviceCropFlipNormalize((8, 9), hvflip=True)

@@ -54,12 +54,12 @@ def test_toy2d_job_reproduces_the_reference_run(name, tmp_path, capsys):
         assert np.allclose(sd['l_final.weight'].reshape(-1)[:8].numpy(), gold['exact'][tag]['l_final'], rtol=1e-5, atol=1e-8)
 
 
-def test_ema_host_path_is_the_reference_arithmetic_and_mixtures_are_refused():
+def test_ema_host_path_is_opt_in_and_is_the_reference_arithmetic():
     import optim_weight_ema
     torch.manual_seed(1)
     mk = lambda: torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.BatchNorm1d(7), torch.nn.Linear(7, 2))   # noqa: E731
     tea, stu = mk(), mk()
-    opt = optim_weight_ema.EMAWeightOptimizer(tea, stu, 0.99)
+    opt = optim_weight_ema.EMAWeightOptimizer(tea, stu, 0.99, host_arithmetic=True)
     with torch.no_grad():
         for v in stu.state_dict().values():
             if v.dtype == torch.float32:
@@ -71,6 +71,8 @@ def test_ema_host_path_is_the_reference_arithmetic_and_mixtures_are_refused():
     opt.step()
     for k, v in tea.state_dict().items():
         assert torch.equal(v, want[k]), k
+    with pytest.raises(RuntimeError, match='no CPU fallback'):          # not opted in: CPU tensors are refused
+        optim_weight_ema.EMAWeightOptimizer(mk(), mk(), 0.99).step()
 
 
 def test_dataset_module_matches_the_reference_pickle_when_the_reference_tree_is_present():

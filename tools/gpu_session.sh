@@ -41,6 +41,14 @@ case $stage in
     B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
     head -30 gpurun_out/shape_profile_$tag.txt
     ;;
+  third)      # multi-tensor prefills + parity-mode K chunking + loop variants: whole suite; bench; ncu --set full of the ASPP kernels
+    run_tests $tag tests
+    grep -h "denseunet\|dl3 (v3)\|pi / cutout\|per_pixel" gpurun_out/pytest_$tag.log | head -20; grep "fullsize\|cutmix iter" gpurun_out/parity_$tag.txt | grep -v " tf32 " | cut -c1-230
+    B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    timeout -s KILL 600 ncu --set full --import-source on --clock-control none -k regex:'conv_gemm2|conv_wgrad2' -c 6 -o gpurun_out/aspp_$tag -f python tools/aspp_bench.py 1 aspp > gpurun_out/ncu_aspp_$tag.log 2>&1; echo "[ncu aspp exit $?]" >> gpurun_out/ncu_aspp_$tag.log
+    python tools/ncu_summary.py gpurun_out/aspp_$tag.ncu-rep > gpurun_out/aspp_${tag}_summary.txt 2>&1
+    grep -E "tensor_cycles_active_realtime|time_duration|kernel:|dram__bytes|lts__t_bytes|lts__throughput" gpurun_out/aspp_${tag}_summary.txt | head -60
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;

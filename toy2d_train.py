@@ -141,7 +141,8 @@ def train_toy2d(submit_config, dataset, region_erode_radius, img_noise_std,
         teacher_net = Network().to(torch_device)
         for p in teacher_net.parameters():
             p.requires_grad = False
-        teacher_optimizer = optim_weight_ema.EMAWeightOptimizer(teacher_net, student_net, ema_alpha=teacher_alpha)
+        teacher_optimizer = optim_weight_ema.EMAWeightOptimizer(teacher_net, student_net, ema_alpha=teacher_alpha,
+                                                                 host_arithmetic=torch_device.type == 'cpu')
         pred_net = teacher_net
     else:
         teacher_net = teacher_optimizer = None
