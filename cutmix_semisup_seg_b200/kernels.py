@@ -75,6 +75,8 @@ class ActKernels(object):
         be = self.be
         base = dict(n_split=self.n_split)
         chunks = self._chunks(taps, k)
+        if ep.get('want_stats'):
+            ep = dict(ep, device=device)          # the statistics buffer is allocated by the (last) launch
 
         def ptrs(c_off):
             d = dict(base)
@@ -149,7 +151,7 @@ class ActKernels(object):
                 kwargs['gate'] = gate.ptr; kwargs['ld_gate'] = gate.ld
             if want_stats:
                 assert gate is not None and not accumulate
-                kwargs['want_stats'] = True; kwargs['device'] = g.device
+                kwargs['want_stats'] = True
                 if stats_sub is not None:
                     kwargs['stats_sub'] = stats_sub.ptr; kwargs['ld_stats_sub'] = stats_sub.ld
             taps = O.dgrad_taps(kh, kw, dil, pad)
