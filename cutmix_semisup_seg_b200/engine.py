@@ -285,15 +285,35 @@ class Tape(object):
         root.pending -= 1
         self._finish(root, False)
 
-    def backward(self):
+    def param_ready_index(self):
+        """{id(parameter): index of the EARLIEST recorded node that contributes to its gradient}.  The backward pass runs
+        the nodes from the last to the first, so a parameter's gradient is final once the node with that index has run
+        (parameters of layers applied to several mini-batches of one pass are accumulated by several nodes)."""
+        ready = {}
+        for i, node in enumerate(self.nodes):
+            mods = [getattr(node, 'conv', None), getattr(node, 'bn', None)]
+            for m in mods:
+                if m is None:
+                    continue
+                for p in (getattr(m, 'weight', None), getattr(m, 'bias', None)):
+                    if p is not None and id(p) not in ready:
+                        ready[id(p)] = i
+        return ready
+
+    def backward(self, cuts=None):
         """Run the recorded nodes in reverse.  Each node is released as soon as it has run: its output's
         gradient and its saved activations are dropped (Act <-> node reference cycles are broken explicitly so
-        tens of GB of activations are freed by reference counting, not by the cyclic GC)."""
+        tens of GB of activations are freed by reference counting, not by the cyclic GC).
+        `cuts`: {node index: callable} -- called right after the node with that index has run (the training step launches
+        the all-reduce of a gradient bucket there, see step.MeanTeacherStep)."""
         nodes, self.nodes = self.nodes, []
         pretranspose(self.K, nodes)              # all dgrad operands of this pass in one launch
         while nodes:
             node = nodes.pop()
+            index = len(nodes)
             node.backward(self)
+            if cuts and index in cuts:
+                cuts[index]()
             y = getattr(node, 'y', None)
             if y is not None:
                 y.node = None
@@ -301,6 +321,8 @@ class Tape(object):
                     y.grad = None
             for k in list(vars(node).keys()):
                 setattr(node, k, None)
+        if cuts and -1 in cuts:
+            cuts[-1]()                           # "after the whole pass"
 
     def discard(self):
         for node in self.nodes:

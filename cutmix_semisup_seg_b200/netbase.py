@@ -153,9 +153,11 @@ class B2SegNet(nn.Module):
             return logits, None
         return logits, _MultiRunState(tape, lows)
 
-    def b2_backward_multi(self, state, dlogits_list, scale_devs=None):
+    def b2_backward_multi(self, state, dlogits_list, scale_devs=None, cuts_for=None):
         """Backward of b2_forward_multi: one d(loss_i)/d(logits_i) (NCHW, optionally times a device scalar) per
-        mini-batch; parameter gradients accumulate into .grad as the sum over the mini-batches."""
+        mini-batch; parameter gradients accumulate into .grad as the sum over the mini-batches.
+        `cuts_for(ready)`: optional; given {id(parameter): node index at which its gradient is final} it returns the
+        {node index: callable} hooks of Tape.backward (gradient-bucket all-reduces overlapped with the pass)."""
         if state is None or state.consumed:
             raise RuntimeError('this forward pass was not recorded or has already been back-propagated')
         state.consumed = True
@@ -164,7 +166,8 @@ class B2SegNet(nn.Module):
         assert len(dlogits_list) == len(state.lows) == len(scale_devs)
         for (low, align), dl, sc in zip(state.lows, dlogits_list, scale_devs):
             E.seed_output_grad(state.tape, low, dl, align, scale_dev=sc)
-        state.tape.backward()
+        cuts = cuts_for(state.tape.param_ready_index()) if cuts_for is not None else None
+        state.tape.backward(cuts)
         for low, _ in state.lows:
             low.grad = None
         state.tape, state.lows = None, None

@@ -58,6 +58,26 @@ class FlatGrads(object):
         self.attach()
         backend.fill(self.flat, 0.0)
 
+    def buckets(self, n_buckets):
+        """The flat buffer cut into `n_buckets` contiguous ranges at parameter boundaries, LAST range first (parameters are laid
+        out in forward order, the backward pass finishes them back to front): [(first element, one-past-last element,
+        [parameters])].  Sizes shrink towards the front (each bucket takes half of what is left, the final one the rest): the
+        bucket that is ready last -- the first layers, whose all-reduce cannot hide under any remaining kernel -- is the
+        smallest."""
+        total = self.numel
+        out, params, hi, off = [], [], total, total
+        target = max(1, total // 2)
+        for p in reversed(self.params):
+            off -= p.numel()
+            params.append(p)
+            if hi - off >= target and len(out) < n_buckets - 1:
+                out.append((off, hi, params))
+                params, hi = [], off
+                target = max(1, off // 2)
+        if hi > 0 or params:
+            out.append((0, hi, params))
+        return out
+
 
 def make_optimizer(student_net, opt_type, learning_rate, sgd_momentum=0.9, sgd_nesterov=False, sgd_weight_decay=5e-4,
                    capturable=False, fused_kernel=False):
@@ -117,6 +137,53 @@ def average_gradients(flat, dist, group=None):
         flat.div_(world)
 
 
+class BucketedAllReduce(object):
+    """The iteration's ONE exchange step (average of the flat student-gradient buffer over the data-parallel ranks, SURVEY.md
+    8e), issued as a few bucket all-reduces WHILE the backward pass is still running: a bucket (a contiguous range at the end of
+    the flat buffer = the layers whose gradients are final first) is handed to NCCL as soon as the backward pass has produced
+    it; NCCL runs on its own stream, ordered after the producing kernels, under the remaining backward kernels.  Rank skew and
+    the transfer itself are hidden up to the last bucket (237 MB over NVLink is ~0.6 ms of an ~147 ms iteration; the exposed
+    single all-reduce cost ~3.5 ms at 8 GPUs including skew, SCALE_r01).  `finish()` makes the current stream wait for all of
+    them (before the optimiser step).  Other backends (gloo, CPU tests of this host logic): the same calls, summed and divided."""
+
+    def __init__(self, flat, dist, group, n_buckets=4):
+        self.flat, self.dist, self.group = flat, dist, group
+        self.world = dist.get_world_size(group)
+        self.nccl = dist.get_backend(group) == 'nccl'
+        self.spans = flat.buckets(n_buckets)
+        self.pending = []
+        self.launched = 0
+
+    def ready_cuts(self, ready):
+        """{tape node index: launch bucket b}: bucket b may go once the earliest node owning one of its parameters has run."""
+        cuts = {}
+        for b, (lo, hi, params) in enumerate(self.spans):
+            idx = [ready[id(p)] for p in params if id(p) in ready]
+            at = min(idx) if idx else -1            # no layer of the pass uses these parameters: zero gradients, ready at once
+            prev = cuts.get(at)
+            cuts[at] = (lambda b=b, prev=prev: ((prev() if prev else None), self.launch(b)))
+        return cuts
+
+    def launch(self, b):
+        lo, hi, _ = self.spans[b]
+        view = self.flat.flat[lo:hi]
+        if self.nccl:
+            work = self.dist.all_reduce(view, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            work = self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((work, view))
+        self.launched += 1
+
+    def finish(self):
+        """All buckets launched so far are complete as far as the current stream is concerned."""
+        for work, view in self.pending:
+            work.wait()
+            if not self.nccl:
+                view.div_(self.world)
+        done, self.pending = len(self.pending), []
+        return done
+
+
 class MeanTeacherStep(object):
     def __init__(self, student_net, teacher_net, student_optim, teacher_optim, mask_generator, cons_loss_fn='var',
                  cons_weight=1.0, conf_thresh=0.97, conf_per_pixel=False, rampup=-1, mask_mix=True,
@@ -140,6 +207,13 @@ class MeanTeacherStep(object):
             self.group = dist_group if dist_group is not True else None
             self.world = dist.get_world_size(self.group)
         self.flat = FlatGrads(list(student_net.parameters())) if (use_flat_grads or self.world > 1) else None
+        # gradient exchange overlapped with the backward pass (batched-trunk iterations: ONE backward pass produces every
+        # gradient); B200SEG_GRAD_BUCKETS=1 restores the single all-reduce after the pass
+        import os as _os
+        self.grad_buckets = int(_os.environ.get('B200SEG_GRAD_BUCKETS', '4'))
+        self._bucketed = BucketedAllReduce(self.flat, self.dist, self.group, self.grad_buckets) \
+            if (self.world > 1 and self.grad_buckets > 1) else None
+        self._overlapped = False         # this iteration's buckets were launched during the backward pass
         # CUDA-graph replay of the iteration (the eager path issues ~6000 launches per iteration from Python and is
         # host-bound: profiles/r01_v2_*).  Two graphs: forward/backward/losses, and optimiser + EMA, with the
         # gradient all-reduce between them.
@@ -148,6 +222,7 @@ class MeanTeacherStep(object):
         # netbase.B2SegNet.b2_forward_multi); falls back to the reference's pass-by-pass order when BatchNorm is not frozen
         self.batch_trunk = batch_trunk
         self._graph = None
+        self._segmenter = None           # set while capturing: turns bucket-ready points into CUDA-graph boundaries
         self.launches_per_replay = 0
 
     # ------------------------------------------------------------------------------------------
@@ -159,7 +234,11 @@ class MeanTeacherStep(object):
 
     def _allreduce(self):
         if self.world > 1:
-            average_gradients(self.flat.flat, self.dist, self.group)
+            if self._overlapped:                     # launched bucket by bucket under the backward pass: wait for them
+                self._bucketed.finish()
+                self._overlapped = False
+            else:
+                average_gradients(self.flat.flat, self.dist, self.group)
 
     def supervised(self, batch_x, batch_y):
         """Lines 296-301: student forward, CE(ignore 255), backward.  Returns the loss as a device scalar."""
@@ -338,7 +417,13 @@ class MeanTeacherStep(object):
         else:
             out4, dls = be.consistency(l0, l1, ls, masks if self.mask_mix else None, loss_mask, self.cons_loss_fn,
                                        self.conf_thresh, self.conf_per_pixel, ramp, self.cons_weight)
-        self.student_net.b2_backward_multi(state, [dsup, dls], [out3[2:3], out4[2:3]])          # :301, :459
+        cuts_for = None
+        if self._bucketed is not None and self._segmenter is None:
+            cuts_for = self._bucketed.ready_cuts              # eager: bucket all-reduces launched from inside the pass
+            self._overlapped = True
+        elif self._bucketed is not None:
+            cuts_for = self._segmenter                        # graph capture: the pass is cut into one graph per bucket
+        self.student_net.b2_backward_multi(state, [dsup, dls], [out3[2:3], out4[2:3]], cuts_for=cuts_for)   # :301, :459
         return {'sup_loss': out3[0], 'cons_loss': out4[0], 'conf_rate': out4[1]}
 
     def _capture(self, sup_batch, unsup_batches, ramp_val):
@@ -366,15 +451,55 @@ class MeanTeacherStep(object):
         cur.wait_stream(side)
         torch.cuda.synchronize()
         l0 = self.be.launches
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            out = self._fwd_bwd(st_sup, st_uns, ramp_val)
+        segs, plan = [], []
+        if self._bucketed is not None and self._can_batch_trunk(st_uns):
+            # Data parallel: the forward / backward capture is cut into one CUDA graph per gradient bucket, at the points of
+            # the backward pass where a bucket's gradients are final; between two replays the bucket's all-reduce is handed to
+            # NCCL (eagerly, on NCCL's stream), so it runs under the next segment's kernels.  Manual capture_begin / capture_end
+            # (torch.cuda.graph cannot be left from inside the pass); all segments share one memory pool and replay in
+            # capture order.
+            import gc
+            torch.cuda.synchronize(); gc.collect(); torch.cuda.empty_cache()
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                g = torch.cuda.CUDAGraph()
+                g.capture_begin()
+                segs.append(g)
+                pool = g.pool()
+
+                def cut(buckets):
+                    segs[-1].capture_end()
+                    plan.append(buckets)
+                    nxt = torch.cuda.CUDAGraph()
+                    nxt.capture_begin(pool=pool)
+                    segs.append(nxt)
+
+                def segmenter(ready):
+                    at = {}
+                    for b, (lo, hi, params) in enumerate(self._bucketed.spans):
+                        idx = [ready[id(p)] for p in params if id(p) in ready]
+                        at.setdefault(min(idx) if idx else -1, []).append(b)
+                    return {i: (lambda bs=bs: cut(bs)) for i, bs in at.items()}
+                self._segmenter = segmenter
+                try:
+                    out = self._fwd_bwd(st_sup, st_uns, ramp_val)
+                finally:
+                    self._segmenter = None
+                segs[-1].capture_end()
+            torch.cuda.current_stream().wait_stream(cap)
+            plan.append([])
+        else:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                out = self._fwd_bwd(st_sup, st_uns, ramp_val)
+            segs, plan, pool = [g1], [None], g1.pool()
         g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g2, pool=g1.pool()):
+        with torch.cuda.graph(g2, pool=pool):
             self._opt_ema()
         self.launches_per_replay = self.be.launches - l0
         self._restore(snap)
-        self._graph = (g1, g2, out, float(ramp_val), tuple(tuple(t.shape) for t in sup_batch))
+        self._graph = (segs, g2, out, float(ramp_val), tuple(tuple(t.shape) for t in sup_batch), plan)
 
     def _state_tensors(self):
         ts = list(self.student_net.state_dict().values())
@@ -529,8 +654,13 @@ class MeanTeacherStep(object):
                 self._load_staged()                    # prefetched during the previous call: device-to-device only
             else:
                 self._load_static(sup_batch, unsup_batches)
-            g1, g2, out = self._graph[0], self._graph[1], self._graph[2]
-            g1.replay()
+            segs, g2, out, plan = self._graph[0], self._graph[1], self._graph[2], self._graph[5]
+            for seg, buckets in zip(segs, plan):
+                seg.replay()
+                if buckets:                            # this segment completed these gradient buckets: all-reduce them under
+                    for b in buckets:                  # the next segment
+                        self._bucketed.launch(b)
+                    self._overlapped = True
             self._allreduce()
             if hasattr(self.student_optim, 'upload_lr'):
                 self.student_optim.upload_lr()         # this iteration's learning rates -> device, ahead of the captured step

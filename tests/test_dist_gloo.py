@@ -33,6 +33,21 @@ def _worker(rank, world, port, q):
     fg.attach()
     ok = ok and all(p.grad is not None and p.grad.data_ptr() >= fg.flat.data_ptr() for p in fg.params)
     ok = ok and net[1].weight.grad is None
+    # bucketed form (overlapped with the backward pass on the GPU): contiguous spans, last parameters first, shrinking towards
+    # the front, covering the buffer exactly once; launching them in any grouping + finish() == the single all-reduce
+    from cutmix_semisup_seg_b200.step import BucketedAllReduce
+    for i, p in enumerate(fg.params):
+        p.grad.fill_(float(rank + 1) * (i + 1))
+    bar = BucketedAllReduce(fg, dist, None, n_buckets=3)
+    spans = bar.spans
+    ok = ok and spans[0][1] == fg.numel and spans[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(spans, spans[1:]))
+    ok = ok and sum(len(s[2]) for s in spans) == len(fg.params) and spans[0][2][0] is fg.params[-1]
+    cuts = bar.ready_cuts({id(p): 10 - i for i, p in enumerate(fg.params)})
+    for k in sorted(cuts, reverse=True):
+        cuts[k]()
+    ok = ok and bar.launched == len(spans) and bar.finish() == len(spans)
+    for i, p in enumerate(fg.params):
+        ok = ok and bool(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -49,6 +49,23 @@ case $stage in
     python tools/ncu_summary.py gpurun_out/aspp_$tag.ncu-rep > gpurun_out/aspp_${tag}_summary.txt 2>&1
     grep -E "tensor_cycles_active_realtime|time_duration|kernel:|dram__bytes|lts__t_bytes|lts__throughput" gpurun_out/aspp_${tag}_summary.txt | head -60
     ;;
+  fourth)     # whole suite + bench (no extras)
+    run_tests $tag tests
+    grep -h "denseunet\|dl3 (v3)\|pi / cutout\|per_pixel" gpurun_out/pytest_$tag.log | head -20; grep "fullsize\|cutmix iter" gpurun_out/parity_$tag.txt | grep -v " tf32 " | cut -c1-230
+    B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    head -12 gpurun_out/shape_profile_$tag.txt
+    ;;
+  ddp2)       # 2 GPUs: correctness of the bucketed / overlapped all-reduce, then bench A/B (buckets 4 vs 1)
+    timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_check.py > gpurun_out/ddp_check_$tag.log 2>&1
+    grep -E "buckets=|overlapped|DDP_CHECK|Error|error" gpurun_out/ddp_check_$tag.log | head -20
+    for b in 4 1; do
+      B200SEG_GRAD_BUCKETS=$b B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_${tag}_2gpu_buckets$b.log 2>&1
+      grep '^{' gpurun_out/bench_${tag}_2gpu_buckets$b.log | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print('buckets $b', d['value'], 'img/s', d['ms_per_step'], 'ms e2e', d['e2e']['value'], d['clocks'])" || tail -5 gpurun_out/bench_${tag}_2gpu_buckets$b.log
+    done
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
