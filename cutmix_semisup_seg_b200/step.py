@@ -463,10 +463,10 @@ class MeanTeacherStep(object):
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(cap):
+                pool = torch.cuda.graph_pool_handle()
                 g = torch.cuda.CUDAGraph()
-                g.capture_begin()
+                g.capture_begin(pool=pool)
                 segs.append(g)
-                pool = g.pool()
 
                 def cut(buckets):
                     segs[-1].capture_end()

@@ -66,6 +66,17 @@ for l in sys.stdin:
     d=json.loads(l); print('buckets $b', d['value'], 'img/s', d['ms_per_step'], 'ms e2e', d['e2e']['value'], d['clocks'])" || tail -5 gpurun_out/bench_${tag}_2gpu_buckets$b.log
     done
     ;;
+  evidence)   # bench lines of the sibling loops / BASELINE config 4, ncu --set full of the aug-consistency kernel, ncu launch list of one step
+    for spec in "aug:--loss aug" "vat:--loss vat" "ict:--loss ict" "config4:--arch denseunet --loss aug" "cfg2:--arch v2"; do
+      n=${spec%%:*}; a=${spec#*:}
+      B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 bench_line ${tag}_$n --steps 10 --warmup 3 --no-second-precision --no-tf32-peak $a
+    done
+    timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:aug_consistency_kernel -c 2 -o gpurun_out/aug_$tag -f python -m pytest tests/test_zz_gpu_aug.py -m gpu -q -k "class_counts and var" > gpurun_out/ncu_aug_$tag.log 2>&1
+    python tools/ncu_summary.py gpurun_out/aug_$tag.ncu-rep > gpurun_out/aug_${tag}_summary.txt 2>&1; grep -E "kernel:|time_duration|dram__bytes|dram_throughput" gpurun_out/aug_${tag}_summary.txt | head -12
+    timeout -s KILL 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python tools/ncu_step.py > gpurun_out/ncu_step_$tag.log 2>&1; echo "[ncu step exit $?]" >> gpurun_out/ncu_step_$tag.log
+    python tools/launch_list_summary.py gpurun_out/launches_$tag.csv > gpurun_out/launch_list_summary_$tag.txt 2>&1; head -25 gpurun_out/launch_list_summary_$tag.txt
+    gzip -f gpurun_out/launches_$tag.csv
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
