@@ -125,3 +125,174 @@ extern "C" int b2_crop_flip_normalize(const b2_crop_entry* table, int n, int out
   B2_LAUNCH_CHECK("crop_flip_normalize_kernel");
   return B2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Crop + flip to uint8 RGBA (the strong-colour branch keeps the crop as pixels for the colour jitter below; alpha = 255 inside
+// the source image, 0 in the padding: b2_normalize_to_tensor(cin = 4) then reproduces the reference's alpha standardisation).
+__global__ void __launch_bounds__(IN_THREADS)
+crop_flip_u8_kernel(const b2_crop_entry* __restrict__ table, int out_h, int out_w, uint8_t* __restrict__ image,
+                    int64_t* __restrict__ labels, float* __restrict__ mask) {
+  const int n = blockIdx.y;
+  const int64_t hw = (int64_t)out_h * out_w;
+  const int64_t p = (int64_t)blockIdx.x * IN_THREADS + threadIdx.x;
+  if (p >= hw) return;
+  const b2_crop_entry e = table[n];
+  const int oy = (int)(p / out_w), ox = (int)(p % out_w);
+  int cy = oy, cx = ox;
+  if (e.flip_d) { cy = ox; cx = oy; }
+  if (e.flip_y) cy = e.crop_h - 1 - cy;
+  if (e.flip_x) cx = e.crop_w - 1 - cx;
+  const int sy = e.pos_y + cy - e.pad_top, sx = e.pos_x + cx - e.pad_left;
+  const bool inside = sy >= 0 && sy < e.h0 && sx >= 0 && sx < e.w0;
+  const int64_t sp = (int64_t)sy * e.w0 + sx;
+  uchar4 px = make_uchar4(0, 0, 0, 0);
+  if (inside) px = make_uchar4(e.image[sp * 3], e.image[sp * 3 + 1], e.image[sp * 3 + 2], 255);
+  reinterpret_cast<uchar4*>(image)[(int64_t)n * hw + p] = px;
+  if (labels) labels[(int64_t)n * hw + p] = (e.labels && inside) ? (int64_t)e.labels[sp] : 255;
+  if (mask) mask[(int64_t)n * hw + p] = (e.mask && inside) ? (float)__dmul_rn((double)e.mask[sp], 1.0 / 255.0) : 0.0f;
+}
+
+extern "C" int b2_crop_flip_u8(const b2_crop_entry* table, int n, int out_h, int out_w, uint8_t* image_rgba, int64_t* labels,
+                               float* mask, void* stream) {
+  B2_REQUIRE(table && image_rgba && n > 0 && n <= 65535 && out_h > 0 && out_w > 0, "b2_crop_flip_u8: bad args");
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(image_rgba) & 3) == 0, "b2_crop_flip_u8: output must be 4-byte aligned");
+  dim3 grid((unsigned)ceil_div64((int64_t)out_h * out_w, IN_THREADS), n);
+  crop_flip_u8_kernel<<<grid, IN_THREADS, 0, (cudaStream_t)stream>>>(table, out_h, out_w, image_rgba, labels, mask);
+  B2_LAUNCH_CHECK("crop_flip_u8_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Colour jitter on uint8 pixels: torchvision ColorJitter + RandomGrayscale on PIL images (the reference's strong colour
+// augmentation, train_seg_semisup_mask_mt.py:169-179 -> datapipe/seg_transforms_cv.py:541-586), i.e. Pillow's C arithmetic
+// (libImaging/Blend.c, Convert.c; ImageEnhance.py), restated with its float / double mixing and explicit roundings so that the
+// bytes are identical (tests/colour_recipe.py states the same algorithm in numpy; pinned against the installed Pillow /
+// torchvision, exhaustively for the HSV conversions).  Up to four operations per image in a per-image random order:
+//   brightness  blend(0, x, a);  contrast  blend(mean L, x, a) (mean over the image: a reduction pass);  saturation
+//   blend(L(x), x, a);  hue  RGB -> HSV, H += shift (mod 256), HSV -> RGB;  then optionally grey = L(x).
+__device__ __forceinline__ int colour_lum(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
+
+__device__ __forceinline__ int colour_blend(int d, int x, float a) {
+  const float t = __fadd_rn((float)d, __fmul_rn(a, (float)(x - d)));
+  if (a >= 0.0f && a <= 1.0f) return (int)t;                 // (UINT8) cast of a value in [0, 255]: truncation
+  return t <= 0.0f ? 0 : (t >= 255.0f ? 255 : (int)t);
+}
+
+__device__ __forceinline__ void colour_rgb2hsv(int r, int g, int b, int* uh, int* us, int* uv) {
+  const int maxc = max(r, max(g, b)), minc = min(r, min(g, b));
+  *uv = maxc;
+  if (minc == maxc) { *uh = 0; *us = 0; return; }
+  const float cr = (float)(maxc - minc);
+  const float s = __fdiv_rn(cr, (float)maxc);
+  const float rc = __fdiv_rn((float)(maxc - r), cr), gc = __fdiv_rn((float)(maxc - g), cr), bc = __fdiv_rn((float)(maxc - b), cr);
+  float h;
+  if (r == maxc) h = __fsub_rn(bc, gc);
+  else if (g == maxc) h = (float)__dsub_rn(__dadd_rn(2.0, (double)rc), (double)bc);
+  else h = (float)__dsub_rn(__dadd_rn(4.0, (double)gc), (double)rc);
+  const double hh = __dadd_rn(__ddiv_rn((double)h, 6.0), 1.0);
+  h = (float)(hh - floor(hh));                                // fmod(x, 1.0) for x >= 0: exact
+  int ih = (int)__dmul_rn((double)h, 255.0), is = (int)__dmul_rn((double)s, 255.0);
+  *uh = min(max(ih, 0), 255); *us = min(max(is, 0), 255);
+}
+
+__device__ __forceinline__ void colour_hsv2rgb(int h, int s, int v, int* r, int* g, int* b) {
+  if (s == 0) { *r = *g = *b = v; return; }
+  const double h6 = __ddiv_rn(__dmul_rn((double)(float)h, 6.0), 255.0);
+  const int i = (int)floor(h6);
+  const float f = (float)__dsub_rn(h6, (double)(float)i);
+  const float fs = (float)__ddiv_rn((double)(float)s, 255.0);
+  const double vf = (double)(float)v;
+  const int p = (int)round(__dmul_rn(vf, __dsub_rn(1.0, (double)fs)));
+  const int q = (int)round(__dmul_rn(vf, __dsub_rn(1.0, (double)__fmul_rn(fs, f))));
+  const int t = (int)round(__dmul_rn(vf, __dsub_rn(1.0, __dmul_rn((double)fs, __dsub_rn(1.0, (double)f)))));
+  const int up = min(max(p, 0), 255), uq = min(max(q, 0), 255), ut = min(max(t, 0), 255);
+  switch (i % 6) {
+    case 0: *r = v; *g = ut; *b = up; break;
+    case 1: *r = uq; *g = v; *b = up; break;
+    case 2: *r = up; *g = v; *b = ut; break;
+    case 3: *r = up; *g = uq; *b = v; break;
+    case 4: *r = ut; *g = up; *b = v; break;
+    default: *r = v; *g = up; *b = uq; break;
+  }
+}
+
+// sums[n] += sum of L over the pixels of image n, for the images whose k-th operation is a contrast change
+__global__ void __launch_bounds__(IN_THREADS)
+colour_lum_sum_kernel(const uint8_t* __restrict__ img, int cstride, int64_t hw, const b2_colour_entry* __restrict__ table, int k,
+                      unsigned long long* __restrict__ sums) {
+  const int n = blockIdx.y;
+  if (k >= table[n].n_ops || table[n].op[k] != 1) return;
+  unsigned long long acc = 0;
+  for (int64_t p = (int64_t)blockIdx.x * IN_THREADS + threadIdx.x; p < hw; p += (int64_t)gridDim.x * IN_THREADS) {
+    const uint8_t* px = img + ((int64_t)n * hw + p) * cstride;
+    acc += (unsigned long long)colour_lum(px[0], px[1], px[2]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sums[n], acc);          // integer sum: order-independent
+}
+
+__global__ void __launch_bounds__(IN_THREADS)
+colour_apply_kernel(uint8_t* __restrict__ img, int cstride, int64_t hw, const b2_colour_entry* __restrict__ table, int k,
+                    const unsigned long long* __restrict__ sums, int last) {
+  const int n = blockIdx.y;
+  const b2_colour_entry e = table[n];
+  const int64_t p = (int64_t)blockIdx.x * IN_THREADS + threadIdx.x;
+  if (p >= hw) return;
+  const int op = k < e.n_ops ? e.op[k] : -1;
+  const bool grey = last && e.grey;
+  if (op < 0 && !grey) return;
+  uint8_t* px = img + ((int64_t)n * hw + p) * cstride;
+  int r = px[0], g = px[1], b = px[2];
+  if (op == 0) {
+    const float a = e.factor[k];
+    r = colour_blend(0, r, a); g = colour_blend(0, g, a); b = colour_blend(0, b, a);
+  } else if (op == 1) {
+    const float a = e.factor[k];
+    const int m = (int)__dadd_rn(__ddiv_rn((double)sums[n], (double)hw), 0.5);
+    r = colour_blend(m, r, a); g = colour_blend(m, g, a); b = colour_blend(m, b, a);
+  } else if (op == 2) {
+    const float a = e.factor[k];
+    const int l = colour_lum(r, g, b);
+    r = colour_blend(l, r, a); g = colour_blend(l, g, a); b = colour_blend(l, b, a);
+  } else if (op == 3) {
+    int h, s, v;
+    colour_rgb2hsv(r, g, b, &h, &s, &v);
+    h = (h + e.hue_shift[k]) & 255;
+    colour_hsv2rgb(h, s, v, &r, &g, &b);
+  }
+  if (grey) { const int l = colour_lum(r, g, b); r = g = b = l; }
+  px[0] = (uint8_t)r; px[1] = (uint8_t)g; px[2] = (uint8_t)b;
+}
+
+extern "C" int b2_colour_jitter(uint8_t* img, int n, int h, int w, int cstride, const b2_colour_entry* table_dev,
+                                const b2_colour_entry* table_host, unsigned long long* workspace, void* stream) {
+  B2_REQUIRE(img && table_dev && table_host && workspace && n > 0 && n <= 65535 && h > 0 && w > 0, "b2_colour_jitter: bad args");
+  B2_REQUIRE(cstride == 3 || cstride == 4, "b2_colour_jitter: pixel stride must be 3 (RGB) or 4 (RGBA)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t hw = (int64_t)h * w;
+  int max_ops = 0; bool any_grey = false;
+  for (int i = 0; i < n; ++i) {
+    B2_REQUIRE(table_host[i].n_ops >= 0 && table_host[i].n_ops <= 4, "b2_colour_jitter: n_ops out of range");
+    for (int k = 0; k < table_host[i].n_ops; ++k)
+      B2_REQUIRE(table_host[i].op[k] >= 0 && table_host[i].op[k] <= 3, "b2_colour_jitter: unknown operation %d", table_host[i].op[k]);
+    if (table_host[i].n_ops > max_ops) max_ops = table_host[i].n_ops;
+    any_grey = any_grey || table_host[i].grey;
+  }
+  if (max_ops == 0 && !any_grey) return B2_OK;
+  const int passes = max_ops > 0 ? max_ops : 1;
+  dim3 grid((unsigned)ceil_div64(hw, IN_THREADS), n);
+  for (int k = 0; k < passes; ++k) {
+    bool contrast = false;
+    for (int i = 0; i < n; ++i) contrast = contrast || (k < table_host[i].n_ops && table_host[i].op[k] == 1);
+    if (contrast) {
+      B2_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * n, s));
+      int64_t bx = ceil_div64(hw, IN_THREADS * 8); if (bx > 1024) bx = 1024; if (bx < 1) bx = 1;
+      colour_lum_sum_kernel<<<dim3((unsigned)bx, n), IN_THREADS, 0, s>>>(img, cstride, hw, table_dev, k, workspace);
+      B2_LAUNCH_CHECK("colour_lum_sum_kernel");
+    }
+    colour_apply_kernel<<<grid, IN_THREADS, 0, s>>>(img, cstride, hw, table_dev, k, workspace, k == passes - 1);
+    B2_LAUNCH_CHECK("colour_apply_kernel");
+  }
+  return B2_OK;
+}

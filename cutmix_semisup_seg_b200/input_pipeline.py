@@ -114,10 +114,13 @@ class DeviceCropFlipNormalize(object):
                       int(crop_size[1]), int(p['flips'][0]), int(p['flips'][1]), int(p['flips'][2]))
         return arr
 
-    def __call__(self, samples, params):
+    def __call__(self, samples, params, colour=None, colour_params=None):
         """samples: list of dicts with `image_arr` uint8 (H_i, W_i, 3) and optionally `labels_arr` / `mask_arr` uint8 (H_i, W_i),
         contiguous CUDA tensors (or host tensors, copied first); params: one `draw_*` dict per sample.  Returns a dict with
-        `image` fp32 (N,3,h,w) and, if every sample has them, `labels` int64 (N,1,h,w) / `mask` fp32 (N,1,h,w)."""
+        `image` fp32 (N,3,h,w) and, if every sample has them, `labels` int64 (N,1,h,w) / `mask` fp32 (N,1,h,w).
+        `colour` (a DeviceColourJitter) + `colour_params` (one `draw()` dict per sample): the strong-colour branch -- the crops
+        stay uint8 RGBA, are jittered in place and standardised afterwards (crop -> flip -> colour -> normalise, the reference's
+        order)."""
         if self.be is None:
             self.be = O.default_backend()
         dev = torch.device('cuda', torch.cuda.current_device())
@@ -137,7 +140,12 @@ class DeviceCropFlipNormalize(object):
         want_labels = all('labels_arr' in d for d in moved)
         want_mask = all('mask_arr' in d for d in moved)
         h, w = int(self.crop_size[0]), int(self.crop_size[1])
-        image, labels, mask = self.be.crop_flip_normalize(tab, len(moved), h, w, self.mean, self.std, want_labels, want_mask, dev)
+        if colour is not None:
+            rgba, labels, mask = self.be.crop_flip_u8(tab, len(moved), h, w, want_labels, want_mask, dev)
+            colour(rgba, colour_params)
+            image = self.be.normalize_to_tensor(rgba, self.mean, self.std)
+        else:
+            image, labels, mask = self.be.crop_flip_normalize(tab, len(moved), h, w, self.mean, self.std, want_labels, want_mask, dev)
         self._keep = (moved, tab)          # inputs of the asynchronous launch stay alive until the next call
         out = {'image': image}
         if labels is not None:
@@ -145,3 +153,66 @@ class DeviceCropFlipNormalize(object):
         if mask is not None:
             out['mask'] = mask
         return out
+
+
+class DeviceColourJitter(object):
+    """The reference's strong colour augmentation on the device: `tvt.Compose([tvt.RandomApply([tvt.ColorJitter(
+    brightness, contrast, saturation, hue)], p), tvt.RandomGrayscale(grey_p)])` applied to the second sample of every unsupervised
+    pair by SegCVTransformTVT (train_seg_semisup_mask_mt.py:169-179, datapipe/seg_transforms_cv.py:541-586).
+
+    `draw()` consumes torch's global generator exactly like torchvision 0.26 does for one image -- RandomApply `torch.rand(1)`;
+    ColorJitter.get_params `torch.randperm(4)` then one `uniform_` per enabled factor in the order brightness, contrast,
+    saturation, hue; RandomGrayscale `torch.rand(1)` -- so a seeded run jitters the same way; `__call__` applies the drawn
+    parameters to uint8 crops (N,H,W,3|4) in place with csrc/input.cu's kernels, byte-identical to Pillow."""
+    BRIGHTNESS, CONTRAST, SATURATION, HUE = 0, 1, 2, 3
+
+    def __init__(self, brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, p=0.8, grey_p=0.2):
+        def rng_of(value, center=1.0, bound=(0.0, float('inf')), clip_first=True):
+            # torchvision ColorJitter._check_input for a scalar
+            if value < 0:
+                raise ValueError('colour-jitter magnitudes must be non-negative')
+            lo, hi = center - float(value), center + float(value)
+            if clip_first:
+                lo = max(lo, 0.0)
+            if not bound[0] <= lo <= hi <= bound[1]:
+                raise ValueError('colour-jitter range out of bounds')
+            return None if lo == hi == center else (lo, hi)
+        self.ranges = [rng_of(brightness), rng_of(contrast), rng_of(saturation),
+                       rng_of(hue, center=0.0, bound=(-0.5, 0.5), clip_first=False)]
+        self.p, self.grey_p = float(p), float(grey_p)
+        self.be = None
+
+    def draw(self):
+        """Parameters for ONE image: dict(ops=[(op, factor), ...] in application order, grey=bool)."""
+        ops = []
+        if not (self.p < float(torch.rand(1))):                      # RandomApply.forward: `if self.p < torch.rand(1): return img`
+            order = torch.randperm(4)                                 # ColorJitter.get_params
+            fac = [None if r is None else float(torch.empty(1).uniform_(r[0], r[1])) for r in self.ranges]
+            for fn_id in order.tolist():                              # ColorJitter.forward
+                if fac[fn_id] is not None:
+                    ops.append((fn_id, fac[fn_id]))
+        grey = bool(float(torch.rand(1)) < self.grey_p)               # RandomGrayscale.forward
+        return dict(ops=ops, grey=grey)
+
+    @staticmethod
+    def table(params):
+        """numpy structured array of b2_colour_entry records (include/b200seg.h)."""
+        import numpy as np
+        dt = np.dtype([('n_ops', 'i4'), ('op', 'i4', (4,)), ('factor', 'f4', (4,)), ('hue_shift', 'i4', (4,)), ('grey', 'i4')])
+        assert dt.itemsize == 56
+        arr = np.zeros(len(params), dtype=dt)
+        for i, p in enumerate(params):
+            arr[i]['n_ops'] = len(p['ops'])
+            for k, (op, fac) in enumerate(p['ops']):
+                arr[i]['op'][k] = op
+                if op == DeviceColourJitter.HUE:
+                    arr[i]['hue_shift'][k] = int(np.int32(fac * 255).astype(np.uint8))      # _functional_pil.adjust_hue
+                else:
+                    arr[i]['factor'][k] = np.float32(fac)                                    # Image.blend takes a C float
+            arr[i]['grey'] = int(p['grey'])
+        return arr
+
+    def __call__(self, images_u8, params):
+        if self.be is None:
+            self.be = O.default_backend()
+        return self.be.colour_jitter(images_u8, self.table(params))

@@ -300,6 +300,29 @@ class CudaBackend(object):
                    L.ptr(mask), self._s())
         return image, labels, mask
 
+    def crop_flip_u8(self, table, n, out_h, out_w, want_labels, want_mask, device):
+        """b2_crop_flip_u8: the crop / flip gather with uint8 RGBA output (n, h, w, 4) for the colour-jitter branch."""
+        image = torch.empty((n, out_h, out_w, 4), device=device, dtype=torch.uint8)
+        labels = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.int64) if want_labels else None
+        mask = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.float32) if want_mask else None
+        self._call('b2_crop_flip_u8', table.data_ptr(), int(n), int(out_h), int(out_w), image.data_ptr(), L.ptr(labels), L.ptr(mask),
+                   self._s())
+        return image, labels, mask
+
+    def colour_jitter(self, img_u8, table_np):
+        """In-place colour jitter of uint8 (N,H,W,3|4) pixels (b2_colour_jitter).  table_np: numpy structured array of N
+        b2_colour_entry records (host); its device copy is made here."""
+        L.require_cuda(img_u8)
+        assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] in (3, 4) and img_u8.is_contiguous()
+        n, h, w, cs = img_u8.shape
+        assert table_np.shape[0] == n and table_np.dtype.itemsize == 56
+        host = np.ascontiguousarray(table_np)
+        dev_tab = torch.from_numpy(host.view(np.uint8).copy()).to(img_u8.device)
+        ws = torch.empty((n,), device=img_u8.device, dtype=torch.int64)
+        self._call('b2_colour_jitter', img_u8.data_ptr(), n, h, w, cs, dev_tab.data_ptr(), host.ctypes.data, ws.data_ptr(), self._s())
+        self.launches += 1
+        return img_u8
+
     # ------------------------------------------------------------------ VAT (train_seg_semisup_vat_mt.py:214-301)
     def sample_l2norm(self, x):
         """mag[i] = sqrt(sum of squares of sample i) (normalize_eps, :217-219).  x: (N, ...) fp32 contiguous."""

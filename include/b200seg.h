@@ -207,6 +207,26 @@ typedef struct {
 } b2_crop_entry;               /* 72 bytes */
 int b2_crop_flip_normalize(const b2_crop_entry* table, int n, int out_h, int out_w, const double* mean3, const double* std3,
                            float* image, int64_t* labels, float* mask, void* stream);
+/* The same gather with uint8 RGBA pixels as output (n, out_h, out_w, 4): alpha = 255 inside the source image, 0 in the padding
+ * (the strong-colour branch: b2_crop_flip_u8 -> b2_colour_jitter -> b2_normalize_to_tensor with cin = 4). */
+int b2_crop_flip_u8(const b2_crop_entry* table, int n, int out_h, int out_w, uint8_t* image_rgba, int64_t* labels, float* mask,
+                    void* stream);
+
+/* Colour jitter on uint8 pixels, in place: torchvision ColorJitter + RandomGrayscale on PIL images as applied by the reference's
+ * SegCVTransformTVT (datapipe/seg_transforms_cv.py:541-586; assembled in train_seg_semisup_mask_mt.py:169-179), byte-identical to
+ * Pillow's arithmetic.  Per image up to 4 operations in the drawn order -- op 0 brightness, 1 contrast, 2 saturation (factor =
+ * blend alpha), 3 hue (hue_shift = np.int32(hue_factor * 255).astype(uint8)) -- then grey = luma if `grey`.
+ * img: DEVICE uint8 (n, h, w, cstride), cstride 3 or 4 (alpha untouched); table_dev / table_host: the same n entries in DEVICE and
+ * HOST memory (the host copy plans the passes); workspace: DEVICE n x uint64. */
+typedef struct {
+  int32_t n_ops;
+  int32_t op[4];
+  float factor[4];
+  int32_t hue_shift[4];
+  int32_t grey;
+} b2_colour_entry;             /* 56 bytes */
+int b2_colour_jitter(uint8_t* img, int n, int h, int w, int cstride, const b2_colour_entry* table_dev,
+                     const b2_colour_entry* table_host, unsigned long long* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * U-Net decoder operators -- architectures/resunet.py:10-34, 57-92 (identical in denseunet.py:10-34, 98-124); NHWC fp32

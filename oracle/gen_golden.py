@@ -497,10 +497,20 @@ def gen_input_pipeline():
                                                    None if case['std'] is None else np.array(case['std']))
         samples = IR.make_samples(case)
         res = []
+        tvt_xf = None
+        if case.get('colour'):
+            import torchvision.transforms as tvt
+            c = case['colour']
+            tvt_xf = TCV.SegCVTransformTVT(tvt.Compose([                                     # train_seg_semisup_mask_mt.py:169-179
+                tvt.RandomApply([tvt.ColorJitter(c['brightness'], c['contrast'], c['saturation'], c['hue'])], p=c['p']),
+                tvt.RandomGrayscale(p=c['grey_p'])]))
+            torch.manual_seed(case['torch_seed'])
         for smp in samples:
             if case['pair']:
                 a, b = crop.transform_pair(dict(smp), dict(smp))
                 a, b = flip.transform_pair(a, b)
+                if tvt_xf is not None:
+                    a, b = tvt_xf.transform_pair(a, b)
                 a, b = norm.transform_pair(a, b)
                 res.extend([a, b])
             else:

@@ -17,6 +17,11 @@ CASES = {
     # pairs with labels, square crop with transposition
     'pair_square': dict(crop_size=(20, 20), crop_offset=(4, 4), hflip=False, vflip=True, hvflip=True, mean=MEAN, std=STD, pair=True,
                         seed=41, sizes=[(28, 36), (19, 33), (50, 21)], labels=True, mask=True),
+    # the strong-colour branch of the unsupervised pairs: crop -> flip -> ColorJitter / RandomGrayscale on sample 1 -> normalise
+    'pair_colour': dict(crop_size=(24, 28), crop_offset=(3, 5), hflip=True, vflip=False, hvflip=False, mean=MEAN, std=STD, pair=True,
+                        seed=51, sizes=[(30, 45), (24, 28), (20, 50), (41, 26), (33, 33), (64, 40), (25, 29), (28, 31), (50, 50), (26, 30)],
+                        labels=False, mask=True,
+                        colour=dict(brightness=0.4, contrast=0.4, saturation=0.4, hue=0.1, p=0.8, grey_p=0.2), torch_seed=7),
 }
 
 

@@ -92,18 +92,49 @@ def _drawn(case):
                                  case['std'], crop_rng=np.random.RandomState(case['seed']),
                                  flip_rng=np.random.RandomState(case['seed'] + 1))
     samples, params = [], []
+    colour, cparams = None, []
+    if case.get('colour'):
+        from cutmix_semisup_seg_b200.input_pipeline import DeviceColourJitter
+        colour = DeviceColourJitter(**case['colour'])
+        torch.manual_seed(case['torch_seed'])
+    tf.colour, tf.cparams = colour, cparams
     for s in IR.make_samples(case):
         # NOTE the reference draws crop parameters of ALL samples from the crop transform's generator and flips from the flip
         # transform's, sample after sample (transform_single / transform_pair are called per sample by the data set accessor)
         if case['pair']:
             p0, p1 = tf.draw_pair(s['image_arr'].shape[:2])
             samples += [s, s]; params += [p0, p1]
+            if colour is not None:                  # SegCVTransformTVT(apply_pair0=False, apply_pair1=True)
+                cparams += [dict(ops=[], grey=False), colour.draw()]
         else:
             samples.append(s); params.append(tf.draw_single(s['image_arr'].shape[:2]))
     return tf, samples, params
 
 
-@pytest.mark.parametrize('name', ['single_flips', 'single_padded', 'pair_offset', 'pair_square'])
+def _statement(case, samples, params, cparams):
+    """numpy statement of the device pipeline: crop / flip gather, optional colour jitter on the uint8 crop, normalise."""
+    import input_recipe as IR
+    import colour_recipe as CR
+    if not case.get('colour'):
+        return IR.reference_statement(samples, params, case['crop_size'], case['mean'], case['std'])
+    raw = IR.reference_statement(samples, params, case['crop_size'], None, None)            # crops as [0,1] floats = u8 / 255
+    u8 = np.rint(raw['image'].transpose(0, 2, 3, 1).astype(np.float64) * 255.0).astype(np.uint8)
+    alpha = []
+    for s, p in zip(samples, params):                      # alpha plane of padded samples: where the gather left the source
+        probe = dict(image_arr=np.full(s['image_arr'].shape, 255, np.uint8))
+        a = IR.reference_statement([probe], [p], case['crop_size'], None, None)['image'][0, 0]
+        alpha.append(a)
+    out = []
+    for img, cp, a in zip(u8, cparams, alpha):
+        j = CR.apply(img, cp)
+        v = np.multiply(j, 1. / 255, dtype=np.float64)
+        v = (v - np.array(case['mean'])[None, None, :] * a.astype(np.float64)[..., None]) / np.array(case['std'])[None, None, :]
+        out.append(v.transpose(2, 0, 1).astype(np.float32))
+    raw['image'] = np.stack(out)
+    return raw
+
+
+@pytest.mark.parametrize('name', ['single_flips', 'single_padded', 'pair_offset', 'pair_square', 'pair_colour'])
 def test_crop_flip_normalize_algorithm_matches_the_reference_transform_classes(name):
     """The host-side parameter draws + the kernel's gather (stated in numpy, tests/input_recipe.py) reproduce, bit for bit,
     what the reference's SegCVTransformRandomCrop -> RandomFlip -> NormalizeToTensor chain produced for the same seeds
@@ -112,8 +143,11 @@ def test_crop_flip_normalize_algorithm_matches_the_reference_transform_classes(n
     gold = np.load(os.path.join(HERE, 'golden', 'input_pipeline.npz'))
     case = IR.CASES[name]
     tf, samples, params = _drawn(case)
-    got = IR.reference_statement(samples, params, case['crop_size'], case['mean'], case['std'])
+    got = _statement(case, samples, params, tf.cparams)
     assert np.array_equal(got['image'], gold[name + '.image']) and got['image'].dtype == np.float32
+    if name == 'pair_colour':
+        kinds = [tuple(op for op, _ in c['ops']) for c in tf.cparams]
+        assert any(len(k) == 4 for k in kinds) and any(c['grey'] for c in tf.cparams) and any(len(k) == 0 for k in kinds[1::2])
     if case['labels']:
         assert np.array_equal(got['labels'], gold[name + '.labels']) and got['labels'].dtype == np.int64
     if case['mask']:

@@ -50,3 +50,50 @@ def test_crop_flip_normalize_kernel_matches_the_reference_transform_classes(name
     # host (pinned) samples are copied first: same result
     out2 = tf([{k: torch.from_numpy(v).pin_memory() for k, v in s.items()} for s in samples], params)
     assert torch.equal(out2['image'], out['image'])
+
+
+@pytest.mark.gpu
+def test_strong_colour_branch_matches_the_reference_transform_chain():
+    """crop -> flip -> ColorJitter / RandomGrayscale -> normalise on the device (b2_crop_flip_u8, b2_colour_jitter,
+    b2_normalize_to_tensor) against the reference's SegCVTransformRandomCrop -> RandomFlip -> SegCVTransformTVT(torchvision) ->
+    NormalizeToTensor chain on the same seeds (tests/golden/input_pipeline.npz, case pair_colour)."""
+    import input_recipe as IR
+    from test_input_pipeline import _drawn
+    dev = torch.device('cuda:0')
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'input_pipeline.npz'))
+    case = IR.CASES['pair_colour']
+    tf, samples, params = _drawn(case)
+    dev_samples = [{k: torch.from_numpy(v).to(dev) for k, v in s.items()} for s in samples]
+    out = tf(dev_samples, params, colour=tf.colour, colour_params=tf.cparams)
+    assert np.array_equal(out['image'].cpu().numpy(), gold['pair_colour.image'])
+    assert np.array_equal(out['mask'].cpu().numpy(), gold['pair_colour.mask'])
+
+
+@pytest.mark.gpu
+def test_colour_kernels_match_the_pillow_arithmetic_on_all_colours():
+    """Every operation of b2_colour_jitter on all 2^24 colours (a 4096 x 4096 image) against the numpy statement that
+    tests/test_colour_jitter.py pins to Pillow: hue shifts (RGB -> HSV -> RGB), brightness / saturation inside and outside
+    [0, 1], contrast (image-wide mean), grey, and a four-operation chain."""
+    import colour_recipe as CR
+    from cutmix_semisup_seg_b200.input_pipeline import DeviceColourJitter
+    dev = torch.device('cuda:0')
+    a = np.arange(256, dtype=np.uint8)
+    x, y, z = np.meshgrid(a, a, a, indexing='ij')
+    cube = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).reshape(4096, 4096, 3)
+    cj = DeviceColourJitter()
+    cases = [dict(ops=[(CR.HUE, 0.0)], grey=False), dict(ops=[(CR.HUE, 0.1)], grey=False), dict(ops=[(CR.HUE, -0.37)], grey=False),
+             dict(ops=[(CR.BRIGHTNESS, 0.6)], grey=False), dict(ops=[(CR.BRIGHTNESS, 1.4)], grey=False),
+             dict(ops=[(CR.SATURATION, 0.77)], grey=False), dict(ops=[(CR.SATURATION, 1.31)], grey=True),
+             dict(ops=[(CR.CONTRAST, 0.61)], grey=False), dict(ops=[(CR.CONTRAST, 1.39)], grey=False), dict(ops=[], grey=True),
+             dict(ops=[(CR.SATURATION, 1.2), (CR.HUE, 0.05), (CR.CONTRAST, 0.8), (CR.BRIGHTNESS, 1.1)], grey=False)]
+    for start in range(0, len(cases), 4):
+        chunk = cases[start:start + 4]
+        img = torch.from_numpy(np.stack([cube] * len(chunk))).to(dev)
+        cj(img, chunk)
+        got = img.cpu().numpy()
+        for i, p in enumerate(chunk):
+            assert np.array_equal(got[i], CR.apply(cube, p)), p
+    # RGBA pixels: the alpha plane is left alone
+    rgba = torch.from_numpy(np.concatenate([cube[:64], np.full((64, 4096, 1), 200, np.uint8)], axis=2)[None]).to(dev).contiguous()
+    cj(rgba, [cases[-1]])
+    assert np.array_equal(rgba.cpu().numpy()[0, ..., :3], CR.apply(cube[:64], cases[-1])) and int(rgba[..., 3].min()) == 200
