@@ -77,6 +77,12 @@ for l in sys.stdin:
     python tools/launch_list_summary.py gpurun_out/launches_$tag.csv > gpurun_out/launch_list_summary_$tag.txt 2>&1; head -25 gpurun_out/launch_list_summary_$tag.txt
     gzip -f gpurun_out/launches_$tag.csv
     ;;
+  fifth)      # colour-jitter / input kernels + whole suite, pipeline isolation of the conv kernels, ncu of the aug loss kernel at full size
+    run_tests $tag tests
+    timeout -s KILL 300 python tools/aspp_bench.py 3 iso > gpurun_out/iso_$tag.log 2>&1; cut -c1-110 gpurun_out/iso_$tag.log
+    B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:aug_consistency_kernel -c 2 -o gpurun_out/aug_$tag -f python bench.py --steps 1 --warmup 3 --loss aug --eager --no-second-precision --no-tf32-peak > gpurun_out/ncu_aug_$tag.log 2>&1
+    python tools/ncu_summary.py gpurun_out/aug_$tag.ncu-rep > gpurun_out/aug_${tag}_summary.txt 2>&1; grep -E "kernel:|time_duration|dram__bytes|dram_throughput|registers" gpurun_out/aug_${tag}_summary.txt | head -12
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
