@@ -83,6 +83,12 @@ for l in sys.stdin:
     B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:aug_consistency_kernel -c 2 -o gpurun_out/aug_$tag -f python bench.py --steps 1 --warmup 3 --loss aug --eager --no-second-precision --no-tf32-peak > gpurun_out/ncu_aug_$tag.log 2>&1
     python tools/ncu_summary.py gpurun_out/aug_$tag.ncu-rep > gpurun_out/aug_${tag}_summary.txt 2>&1; grep -E "kernel:|time_duration|dram__bytes|dram_throughput|registers" gpurun_out/aug_${tag}_summary.txt | head -12
     ;;
+  timeline)   # device timeline of the graph-replayed iteration (CUPTI via torch.profiler) + the vendor's TF32 GEMM under ncu
+    timeout -s KILL 600 python tools/timeline.py v3plus gpurun_out/timeline_$tag.txt > gpurun_out/timeline_$tag.log 2>&1; head -75 gpurun_out/timeline_$tag.txt | cut -c1-200 || tail -20 gpurun_out/timeline_$tag.log
+    timeout -s KILL 300 python tools/cublas_tf32_probe.py --time > gpurun_out/cublas_tf32_$tag.log 2>&1; cat gpurun_out/cublas_tf32_$tag.log | tail -4
+    timeout -s KILL 400 ncu --set full --clock-control none --profile-from-start off -o gpurun_out/cublas_tf32_$tag -f python tools/cublas_tf32_probe.py > gpurun_out/ncu_cublas_$tag.log 2>&1
+    python tools/ncu_summary.py gpurun_out/cublas_tf32_$tag.ncu-rep > gpurun_out/cublas_tf32_${tag}_summary.txt 2>&1; grep -E "kernel:|time_duration|tensor_cycles|mem_tensor|dram__bytes|lts__throughput|shared_mem_per_block|grid_size|block_size" gpurun_out/cublas_tf32_${tag}_summary.txt | head -40
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
