@@ -163,6 +163,151 @@ extern "C" int b2_crop_flip_u8(const b2_crop_entry* table, int n, int out_h, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
+// Scale / rotation crops on uint8 pixels: SegCVTransformRandomCropScaleHung (datapipe/seg_transforms_cv.py:
+// 169-303: pad, crop a scaled window, cv2.resize to the crop size) and SegCVTransformRandomCropRotateScale (:305-449: cv2.warpAffine
+// of the whole image into the crop) followed by SegCVTransformRandomFlip.flip_image (:467-474), as ONE gather per output pixel.
+// OpenCV's uint8 paths are integer algorithms (imgproc/resize.cpp, imgwarp.cpp; pinned 3.4.2, same results from the installed
+// 4.13), restated here; the host (input_pipeline.resize_tables / warp_tables) prepares the per-sample integer tables:
+//   mode 0  resize of the window [pos, pos + src) of the virtually padded image.  tables (int32, W = out_w, H = out_h):
+//           [0,W) nearest source column, [W,2W) left column of the linear filter, [2W,3W) its coefficients a0 | a1 << 16 (11 bit),
+//           [3W,3W+H) nearest row, [3W+H,3W+2H) upper row (clipped at use), [3W+2H,3W+3H) b0 | b1 << 16.
+//           linear: rows are filtered horizontally into ints (S[x0]*a0 + S[x1]*a1), then
+//           (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;  interp 2 = exact 2x decimation = (sum of 2x2 + 2) >> 2.
+//   mode 1  warpAffine.  tables: [0,W) adelta, [W,2W) bdelta, [3W,3W+H) X0, [3W+H,3W+2H) Y0 (10-bit fixed point of the inverted
+//           matrix).  nearest: X = (X0 + 512 + adelta) >> 10; linear: X = (X0 + 16 + adelta) >> 5, pixel X >> 5, 5-bit fractions,
+//           weights (32-fy)(32-fx)*32 ... (sum 2^15), (acc + 2^14) >> 15.  Borders: image BORDER_REFLECT_101, labels
+//           BORDER_CONSTANT 255, mask BORDER_CONSTANT 0.
+// Output: RGBA uint8 (alpha = 255 inside the image, 0 in the padding, interpolated like a colour channel: the reference resizes
+// the 4-channel padded image), labels int64, mask float32(m * (1/255)).
+__device__ __forceinline__ int geom_reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+__device__ __forceinline__ int geom_sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+struct GeomSrc {
+  const b2_geom_entry* e;
+  // pixel (y, x) of the window of the virtually padded image (mode 0): channel c of RGBA / labels / mask
+  __device__ __forceinline__ bool inside(int y, int x, int64_t* sp) const {
+    const int sy = e->pos_y + y - e->pad_top, sx = e->pos_x + x - e->pad_left;
+    *sp = (int64_t)sy * e->w0 + sx;
+    return sy >= 0 && sy < e->h0 && sx >= 0 && sx < e->w0;
+  }
+  __device__ __forceinline__ void rgba(int y, int x, int (&v)[4]) const {
+    int64_t sp;
+    if (inside(y, x, &sp)) { v[0] = e->image[sp * 3]; v[1] = e->image[sp * 3 + 1]; v[2] = e->image[sp * 3 + 2]; v[3] = 255; }
+    else { v[0] = v[1] = v[2] = v[3] = 0; }
+  }
+  __device__ __forceinline__ int plane(const uint8_t* p, int y, int x, int outside) const {
+    int64_t sp;
+    return inside(y, x, &sp) ? (int)p[sp] : outside;
+  }
+};
+
+__device__ __forceinline__ int geom_vresize(int r0, int r1, int b0, int b1) {
+  return (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+}
+
+__global__ void __launch_bounds__(IN_THREADS)
+geom_u8_kernel(const b2_geom_entry* __restrict__ table, const int32_t* __restrict__ tables, int out_h, int out_w,
+               uint8_t* __restrict__ image, int64_t* __restrict__ labels, float* __restrict__ mask) {
+  const int n = blockIdx.y;
+  const int64_t hw = (int64_t)out_h * out_w;
+  const int64_t p = (int64_t)blockIdx.x * IN_THREADS + threadIdx.x;
+  if (p >= hw) return;
+  const b2_geom_entry e = table[n];
+  const int32_t* t = tables + e.tab_off;
+  const int W = out_w, H = out_h;
+  const int oy = (int)(p / out_w), ox = (int)(p % out_w);
+  int ry = oy, rx = ox;                                   // pixel of the un-flipped crop
+  if (e.flip_d) { ry = ox; rx = oy; }
+  if (e.flip_y) ry = H - 1 - ry;
+  if (e.flip_x) rx = W - 1 - rx;
+  int px[4] = {0, 0, 0, 255};
+  int lab = 255, msk = 0;
+  if (e.mode == 0) {
+    GeomSrc s{&e};
+    const int xn = t[rx], yn = t[3 * W + ry];
+    const int xl = t[W + rx], xa = t[2 * W + rx], yl = t[3 * W + H + ry], yb = t[3 * W + 2 * H + ry];
+    const int x1 = min(xl + 1, e.src_w - 1);
+    const int y0 = min(max(yl, 0), e.src_h - 1), y1 = min(max(yl + 1, 0), e.src_h - 1);
+    const int a0 = xa & 0xffff, a1 = (xa >> 16) & 0xffff, b0 = yb & 0xffff, b1 = (yb >> 16) & 0xffff;
+    if (e.image_interp == 0) {
+      s.rgba(yn, xn, px);
+    } else if (e.image_interp == 1) {
+      int v00[4], v01[4], v10[4], v11[4];
+      s.rgba(y0, xl, v00); s.rgba(y0, x1, v01); s.rgba(y1, xl, v10); s.rgba(y1, x1, v11);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) px[c] = geom_vresize(v00[c] * a0 + v01[c] * a1, v10[c] * a0 + v11[c] * a1, b0, b1);
+    } else {
+      int v00[4], v01[4], v10[4], v11[4];
+      s.rgba(2 * ry, 2 * rx, v00); s.rgba(2 * ry, 2 * rx + 1, v01); s.rgba(2 * ry + 1, 2 * rx, v10); s.rgba(2 * ry + 1, 2 * rx + 1, v11);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) px[c] = (v00[c] + v01[c] + v10[c] + v11[c] + 2) >> 2;
+    }
+    if (labels && e.labels) lab = s.plane(e.labels, yn, xn, 255);
+    if (mask && e.mask) {
+      if (e.mask_interp == 0) msk = s.plane(e.mask, yn, xn, 0);
+      else if (e.mask_interp == 1)
+        msk = geom_vresize(s.plane(e.mask, y0, xl, 0) * a0 + s.plane(e.mask, y0, x1, 0) * a1,
+                           s.plane(e.mask, y1, xl, 0) * a0 + s.plane(e.mask, y1, x1, 0) * a1, b0, b1);
+      else
+        msk = (s.plane(e.mask, 2 * ry, 2 * rx, 0) + s.plane(e.mask, 2 * ry, 2 * rx + 1, 0) + s.plane(e.mask, 2 * ry + 1, 2 * rx, 0) +
+               s.plane(e.mask, 2 * ry + 1, 2 * rx + 1, 0) + 2) >> 2;
+    }
+  } else {
+    const int ad = t[rx], bd = t[W + rx], X0 = t[3 * W + ry], Y0 = t[3 * W + H + ry];
+    const int h0 = e.h0, w0 = e.w0;
+    // nearest coordinates (labels always; image / mask when their interpolation is nearest)
+    const int nx = geom_sat_short((X0 + 512 + ad) >> 10), ny = geom_sat_short((Y0 + 512 + bd) >> 10);
+    const bool n_in = (unsigned)nx < (unsigned)w0 && (unsigned)ny < (unsigned)h0;
+    // linear coordinates
+    const int LX = (X0 + 16 + ad) >> 5, LY = (Y0 + 16 + bd) >> 5;
+    const int sx = geom_sat_short(LX >> 5), sy = geom_sat_short(LY >> 5);
+    const int fx = LX & 31, fy = LY & 31;
+    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    if (e.image_interp == 0) {
+      const int yy = geom_reflect101(ny, h0), xx = geom_reflect101(nx, w0);
+      const int64_t sp = (int64_t)yy * w0 + xx;
+      px[0] = e.image[sp * 3]; px[1] = e.image[sp * 3 + 1]; px[2] = e.image[sp * 3 + 2];
+    } else {
+      const int xa = geom_reflect101(sx, w0), xb = geom_reflect101(sx + 1, w0);
+      const int ya = geom_reflect101(sy, h0), yb = geom_reflect101(sy + 1, h0);
+      const uint8_t* p00 = e.image + ((int64_t)ya * w0 + xa) * 3; const uint8_t* p01 = e.image + ((int64_t)ya * w0 + xb) * 3;
+      const uint8_t* p10 = e.image + ((int64_t)yb * w0 + xa) * 3; const uint8_t* p11 = e.image + ((int64_t)yb * w0 + xb) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[c] = (p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11 + (1 << 14)) >> 15;
+    }
+    if (labels && e.labels) lab = n_in ? (int)e.labels[(int64_t)ny * w0 + nx] : 255;
+    if (mask && e.mask) {
+      if (e.mask_interp == 0) msk = n_in ? (int)e.mask[(int64_t)ny * w0 + nx] : 0;
+      else if (sx >= w0 || sx + 1 < 0 || sy >= h0 || sy + 1 < 0) msk = 0;
+      else {
+        auto tap = [&](int yy, int xx) -> int {
+          return ((unsigned)xx < (unsigned)w0 && (unsigned)yy < (unsigned)h0) ? (int)e.mask[(int64_t)yy * w0 + xx] : 0;
+        };
+        msk = (tap(sy, sx) * w00 + tap(sy, sx + 1) * w01 + tap(sy + 1, sx) * w10 + tap(sy + 1, sx + 1) * w11 + (1 << 14)) >> 15;
+      }
+    }
+  }
+  reinterpret_cast<uchar4*>(image)[(int64_t)n * hw + p] = make_uchar4((unsigned char)px[0], (unsigned char)px[1], (unsigned char)px[2],
+                                                                      (unsigned char)px[3]);
+  if (labels) labels[(int64_t)n * hw + p] = e.labels ? (int64_t)lab : 255;
+  if (mask) mask[(int64_t)n * hw + p] = e.mask ? (float)__dmul_rn((double)msk, 1.0 / 255.0) : 0.0f;
+}
+
+extern "C" int b2_geom_u8(const b2_geom_entry* table, const int32_t* tables, int n, int out_h, int out_w, uint8_t* image_rgba,
+                          int64_t* labels, float* mask, void* stream) {
+  B2_REQUIRE(table && tables && image_rgba && n > 0 && n <= 65535 && out_h > 0 && out_w > 0, "b2_geom_u8: bad args");
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(image_rgba) & 3) == 0, "b2_geom_u8: output must be 4-byte aligned");
+  dim3 grid((unsigned)ceil_div64((int64_t)out_h * out_w, IN_THREADS), n);
+  geom_u8_kernel<<<grid, IN_THREADS, 0, (cudaStream_t)stream>>>(table, tables, out_h, out_w, image_rgba, labels, mask);
+  B2_LAUNCH_CHECK("geom_u8_kernel");
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
 // Colour jitter on uint8 pixels: torchvision ColorJitter + RandomGrayscale on PIL images (the reference's strong colour
 // augmentation, train_seg_semisup_mask_mt.py:169-179 -> datapipe/seg_transforms_cv.py:541-586), i.e. Pillow's C arithmetic
 // (libImaging/Blend.c, Convert.c; ImageEnhance.py), restated with its float / double mixing and explicit roundings so that the

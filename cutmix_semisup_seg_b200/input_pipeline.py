@@ -216,3 +216,351 @@ class DeviceColourJitter(object):
         if self.be is None:
             self.be = O.default_backend()
         return self.be.colour_jitter(images_u8, self.table(params))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Scale / rotation crops: SegCVTransformRandomCropScaleHung (datapipe/seg_transforms_cv.py:169-303, the
+# Pascal recipes' --aug_scale_hung) and SegCVTransformRandomCropRotateScale (:305-449, the ISIC recipes' --aug_max_scale /
+# --aug_rot_mag).  The reference calls cv2.resize / cv2.warpAffine on uint8 arrays; OpenCV's uint8 paths are fixed-point integer
+# algorithms (pinned 3.4.2, unchanged in the installed 4.13: tests/test_geom_pipeline.py compares the restatement with cv2 itself),
+# so the host only prepares small integer tables per sample -- coefficient tables of the resize, the inverted matrix in 10-bit
+# fixed point of the warp -- and csrc/input.cu (geom_u8_kernel) does the gather + interpolation in integer arithmetic.
+
+def _mat_translation(xlats_xy):
+    """datapipe/affine.py:73-84: (N,2,3) float32 translation matrices."""
+    import numpy as np
+    xf = np.zeros((len(xlats_xy), 2, 3), dtype=np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = 1.0
+    xf[:, :, 2] = xlats_xy
+    return xf
+
+
+def _mat_scale(scale_xy):
+    """datapipe/affine.py:86-97."""
+    import numpy as np
+    xf = np.zeros((len(scale_xy), 2, 3), dtype=np.float32)
+    xf[:, 0, 0] = scale_xy[:, 0]
+    xf[:, 1, 1] = scale_xy[:, 1]
+    return xf
+
+
+def _mat_rotation(thetas):
+    """datapipe/affine.py:99-121: counter-clockwise, +y down."""
+    import numpy as np
+    c, s = np.cos(thetas), np.sin(thetas)
+    xf = np.zeros((len(thetas), 2, 3), dtype=np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = c
+    xf[:, 1, 0] = -s
+    xf[:, 0, 1] = s
+    return xf
+
+
+def _mat_cat(*x):
+    """datapipe/affine.py:43-71: x[0] . x[1] . ... (same numpy calls on the same dtypes, so the float32 products round alike)."""
+    import numpy as np
+    y = x[0]
+    for b in x[1:]:
+        a2, b2 = y[:, :, :2], b[:, :, :2]
+        y = np.append(np.matmul(a2, b2), y[:, :, 2:3] + np.matmul(a2, b[:, :, 2:3]), axis=2)
+    return y
+
+
+NEAREST, LINEAR, AREA2 = 0, 1, 2
+
+
+def resize_tables(src_hw, dst_hw):
+    """Integer tables of cv2.resize for uint8 (OpenCV imgproc/resize.cpp): per destination column / row the nearest source index
+    (INTER_NEAREST: min(floor(d * scale), n - 1), scale = 1 / (dst / src) in double), the left / upper source index of the linear
+    filter and its two 11-bit coefficients packed as a0 | a1 << 16 ((float)((d + 0.5) * scale - 0.5), floor, float remainder,
+    saturate_cast<short>(c * 2048); columns clamp the index and zero the remainder at the borders, rows keep the remainder and clip
+    the row index at use).  Returns (xn, xl, xa, yn, yl, yb) int32 arrays and `area2` (INTER_LINEAR of an exact 2 x decimation is
+    computed as a 2 x 2 box average)."""
+    import numpy as np
+    (sh, sw), (dh, dw) = src_hw, dst_hw
+    scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)
+    eps = np.finfo(np.float64).eps
+    area2 = bool(abs(scale_x - 2) < eps and abs(scale_y - 2) < eps)
+
+    def axis(n_dst, n_src, scale, clamp):
+        d = np.arange(n_dst, dtype=np.float64)
+        near = np.minimum(np.floor(d * scale).astype(np.int64), n_src - 1)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        si = np.floor(f).astype(np.int64)
+        f = f - si.astype(np.float32)
+        if clamp:
+            lo = si < 0
+            f = np.where(lo, np.float32(0), f); si = np.where(lo, 0, si)
+            hi = si >= n_src - 1
+            f = np.where(hi, np.float32(0), f); si = np.where(hi, n_src - 1, si)
+        a0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64)
+        a1 = np.rint(f * np.float32(2048)).astype(np.int64)
+        return near.astype(np.int32), si.astype(np.int32), (a0 | (a1 << 16)).astype(np.int32)
+    xn, xl, xa = axis(dw, sw, scale_x, True)
+    yn, yl, yb = axis(dh, sh, scale_y, False)
+    return (xn, xl, xa, yn, yl, yb), area2
+
+
+def warp_tables(matrix_2x3, dst_hw):
+    """Integer tables of cv2.warpAffine (OpenCV imgproc/imgwarp.cpp): the forward matrix is inverted in double, then
+    adelta[x] = round(M00 * x * 1024), bdelta[x] = round(M10 * x * 1024), X0[y] = round((M01 * y + M02) * 1024), Y0[y] likewise
+    (saturate_cast<int> = round half to even); the kernel adds the interpolation's rounding constant and shifts."""
+    import numpy as np
+    dh, dw = dst_hw
+    m = np.asarray(matrix_2x3, dtype=np.float64).copy().ravel()
+    det = m[0] * m[4] - m[1] * m[3]
+    det = 1.0 / det if det != 0 else 0.0
+    a11, a22 = m[4] * det, m[0] * det
+    m[0] = a11; m[1] *= -det; m[3] *= -det; m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2] = b1; m[5] = b2
+    xs, ys = np.arange(dw, dtype=np.float64), np.arange(dh, dtype=np.float64)
+
+    def sat(v):
+        return np.clip(np.rint(v), -2147483648, 2147483647).astype(np.int64).astype(np.int32)
+    return sat(m[0] * xs * 1024), sat(m[3] * xs * 1024), sat((m[1] * ys + m[2]) * 1024), sat((m[4] * ys + m[5]) * 1024)
+
+
+class _DeviceGeomBase(object):
+    """Shared device side: table upload, geom_u8_kernel, optional colour jitter, normalise-to-tensor."""
+
+    def _init_common(self, crop_size, crop_offset, hflip, vflip, hvflip, mean, std, rng, flip_rng):
+        import numpy as np
+        if (mean is None) != (std is None):
+            raise ValueError('mean and std must be given together')
+        self.crop_size = tuple(int(v) for v in crop_size)
+        self.crop_size_arr = np.array(crop_size)
+        self.crop_offset = np.array([0, 0] if crop_offset is None else crop_offset)
+        self.hflip, self.vflip, self.hvflip = bool(hflip), bool(vflip), bool(hvflip)
+        if self.hvflip and self.crop_size[0] != self.crop_size[1]:
+            raise ValueError('hvflip (transposition) needs a square crop')
+        self.mean = None if mean is None else [float(v) for v in mean]
+        self.std = None if std is None else [float(v) for v in std]
+        self.rng = rng if rng is not None else np.random.RandomState()
+        self.flip_rng = flip_rng if flip_rng is not None else np.random.RandomState()
+        self.be = None
+
+    def _flips(self, pair):
+        """SegCVTransformRandomFlip.transform_single / transform_pair (:478-481, :500-504)."""
+        import numpy as np
+        on = np.array([self.hflip, self.vflip, self.hvflip])
+        if not pair:
+            return tuple(bool(f) for f in ((self.flip_rng.binomial(1, 0.5, size=(3,)) != 0) & on))
+        fl = (self.flip_rng.binomial(1, 0.5, size=(2, 3)) != 0) & on[None]
+        return tuple(bool(f) for f in fl[0]), tuple(bool(f) for f in fl[1])
+
+    @staticmethod
+    def entry_dtype():
+        import numpy as np
+        dt = np.dtype([('image', 'u8'), ('labels', 'u8'), ('mask', 'u8'), ('h0', 'i4'), ('w0', 'i4'), ('mode', 'i4'),
+                       ('pad_top', 'i4'), ('pad_left', 'i4'), ('padded', 'i4'), ('pos_y', 'i4'), ('pos_x', 'i4'), ('src_h', 'i4'),
+                       ('src_w', 'i4'), ('image_interp', 'i4'), ('mask_interp', 'i4'), ('tab_off', 'i4'), ('flip_x', 'i4'),
+                       ('flip_y', 'i4'), ('flip_d', 'i4')], align=True)
+        assert dt.itemsize == 88
+        return dt
+
+    def tables(self, samples, params):
+        """(entries: structured array of b2_geom_entry records, tables: int32 array) for device-resident samples."""
+        import numpy as np
+        h, w = self.crop_size
+        per = 3 * (h + w)
+        ent = np.zeros(len(samples), dtype=self.entry_dtype())
+        tab = np.zeros(len(samples) * per, dtype=np.int32)
+        for i, (s, p) in enumerate(zip(samples, params)):
+            img, lab, msk = s['image_arr'], s.get('labels_arr'), s.get('mask_arr')
+            e = ent[i]
+            e['image'] = img.data_ptr(); e['labels'] = 0 if lab is None else lab.data_ptr(); e['mask'] = 0 if msk is None else msk.data_ptr()
+            e['h0'], e['w0'] = int(img.shape[0]), int(img.shape[1])
+            e['mode'] = p['mode']
+            e['tab_off'] = i * per
+            e['flip_x'], e['flip_y'], e['flip_d'] = (int(f) for f in p['flips'])
+            t = tab[i * per:(i + 1) * per]
+            if p['mode'] == 0:
+                e['pad_top'], e['pad_left'], e['padded'] = p['pad_top'], p['pad_left'], p['padded']
+                e['pos_y'], e['pos_x'] = p['pos']
+                e['src_h'], e['src_w'] = p['src_size']
+                (xn, xl, xa, yn, yl, yb), area2 = resize_tables(p['src_size'], (h, w))
+                t[0:w] = xn; t[w:2 * w] = xl; t[2 * w:3 * w] = xa
+                t[3 * w:3 * w + h] = yn; t[3 * w + h:3 * w + 2 * h] = yl; t[3 * w + 2 * h:3 * w + 3 * h] = yb
+                e['image_interp'] = AREA2 if (p['image_interp'] == LINEAR and area2) else p['image_interp']
+                e['mask_interp'] = AREA2 if (p['mask_interp'] == LINEAR and area2) else p['mask_interp']
+            else:
+                ad, bd, x0, y0 = warp_tables(p['matrix'], (h, w))
+                t[0:w] = ad; t[w:2 * w] = bd; t[3 * w:3 * w + h] = x0; t[3 * w + h:3 * w + 2 * h] = y0
+                e['image_interp'], e['mask_interp'] = p['image_interp'], p['mask_interp']
+        return ent, tab
+
+    def __call__(self, samples, params, colour=None, colour_params=None):
+        """samples: list of dicts with `image_arr` uint8 (H_i, W_i, 3) [+ `labels_arr` / `mask_arr` uint8 (H_i, W_i)] (CUDA tensors,
+        or host tensors that are copied first); params: one `draw_*` dict per sample.  Returns `image` fp32 (N,3,h,w) [+ `labels`
+        int64 (N,1,h,w), `mask` fp32 (N,1,h,w)] as the reference's collate function would have produced them after
+        scale / rotate crop -> flip -> [colour jitter] -> normalise."""
+        if self.be is None:
+            self.be = O.default_backend()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        moved = []
+        for s in samples:
+            d = {}
+            for k in ('image_arr', 'labels_arr', 'mask_arr'):
+                if s.get(k) is not None:
+                    t = s[k]
+                    if t.dtype != torch.uint8:
+                        raise ValueError('{} must be uint8'.format(k))
+                    d[k] = (t if t.is_cuda else t.to(dev, non_blocking=True)).contiguous()
+            if d['image_arr'].dim() != 3 or d['image_arr'].shape[2] != 3:
+                raise ValueError('image should have 3 channels, not {}'.format(tuple(d['image_arr'].shape)))
+            moved.append(d)
+        ent, tab = self.tables(moved, params)
+        ent_dev = torch.from_numpy(ent.view('u1').copy()).to(dev, non_blocking=True)
+        tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
+        want_labels = all('labels_arr' in d for d in moved)
+        want_mask = all('mask_arr' in d for d in moved)
+        h, w = self.crop_size
+        rgba, labels, mask = self.be.geom_u8(ent_dev, tab_dev, len(moved), h, w, want_labels, want_mask, dev)
+        if colour is not None:
+            colour(rgba, colour_params)
+        image = self.be.normalize_to_tensor(rgba, self.mean, self.std)
+        self._keep = (moved, ent_dev, tab_dev)
+        out = {'image': image}
+        if labels is not None:
+            out['labels'] = labels
+        if mask is not None:
+            out['mask'] = mask
+        return out
+
+
+class DeviceRandomCropScaleHung(_DeviceGeomBase):
+    """`SegCVTransformRandomCropScaleHung(crop_size, crop_offset, uniform_scale)` -> `SegCVTransformRandomFlip` ->
+    [`SegCVTransformTVT`] -> `SegCVTransformNormalizeToTensor` on the device.  Parameters are drawn on the host in the reference's
+    order (`rng.randint(0, 11, (scale_dim,))`, `rng.uniform(0, 1, (2,))` [pairs: `rng.uniform(-1, 1, (2,))`]; flips from the flip
+    transform's own generator)."""
+
+    def __init__(self, crop_size, crop_offset=None, uniform_scale=True, hflip=False, vflip=False, hvflip=False, mean=None, std=None,
+                 rng=None, flip_rng=None):
+        self._init_common(crop_size, crop_offset, hflip, vflip, hvflip, mean, std, rng, flip_rng)
+        self.uniform_scale = bool(uniform_scale)
+
+    @staticmethod
+    def _pad_to(img_hw, min_size):
+        """SegCVTransformPad.pad_single / pad_pair (:30-100): (pad_top, pad_left, padded, padded size)."""
+        import numpy as np
+        h, w = int(img_hw[0]), int(img_hw[1])
+        if h < min_size[0] or w < min_size[1]:
+            pad_h, pad_w = max(int(min_size[0]) - h, 0), max(int(min_size[1]) - w, 0)
+            return pad_h // 2, pad_w // 2, 1, np.array([h + pad_h, w + pad_w])
+        return 0, 0, 0, np.array([h, w])
+
+    def _xf(self, pos, sc_size, pad_top, pad_left, padded):
+        """The `xf_cv` entry the reference would leave in the sample for an identity input transform (:216-229, :272-298)."""
+        import numpy as np
+        scale_yx = self.crop_size_arr / sc_size
+        xlat_yx = (scale_yx - 1.0) * 0.5
+        parts = [_mat_translation(xlat_yx[None, ::-1].astype(float)), _mat_scale(scale_yx[None, ::-1]),
+                 _mat_translation(-np.array(pos)[None, ::-1].astype(float))]
+        if padded:
+            parts.append(_mat_translation(np.array([[pad_left, pad_top]])))
+        return _mat_cat(*parts)[0]
+
+    def draw_single(self, img_hw):
+        import numpy as np
+        scale_dim = 1 if self.uniform_scale else 2
+        f_scale = 0.5 + self.rng.randint(0, 11, size=(scale_dim,)) / 10.0                                    # :199
+        sc_size = np.round(self.crop_size_arr / f_scale).astype(int)                                         # :202
+        top, left, padded, size = self._pad_to(img_hw, sc_size)                                              # :204
+        extra = size - sc_size
+        pos = np.round(extra * self.rng.uniform(0.0, 1.0, size=(2,))).astype(int)                            # :208-209
+        return dict(mode=0, pad_top=top, pad_left=left, padded=padded, pos=(int(pos[0]), int(pos[1])),
+                    src_size=(int(sc_size[0]), int(sc_size[1])), image_interp=LINEAR, mask_interp=LINEAR,   # :213-221
+                    flips=self._flips(False), xf_cv=self._xf(pos, sc_size, top, left, padded))
+
+    def draw_pair(self, img_hw):
+        import numpy as np
+        scale_dim = 1 if self.uniform_scale else 2
+        f_scale1 = 0.5 + self.rng.randint(0, 11, size=(scale_dim,)) / 10.0                                   # :240
+        sc_size1 = np.round(self.crop_size_arr / f_scale1).astype(int)                                       # :243
+        max_sc = np.maximum(self.crop_size_arr, sc_size1)                                                    # :245
+        top, left, padded, size = self._pad_to(img_hw, max_sc)                                               # :248
+        extra = size - max_sc
+        pos0 = np.round(extra * self.rng.uniform(0.0, 1.0, size=(2,))).astype(int)                           # :252
+        pos1 = pos0 + np.round(self.crop_offset * self.rng.uniform(-1.0, 1.0, size=(2,))).astype(int)        # :253
+        pos1 = np.clip(pos1, np.array([0, 0]), extra)                                                        # :255
+        centre0, centre1 = pos0 + max_sc * 0.5, pos1 + max_sc * 0.5
+        pos0 = np.round(centre0 - self.crop_size_arr * 0.5).astype(int)                                      # :260
+        pos1 = np.round(centre1 - sc_size1 * 0.5).astype(int)                                                # :261
+        f0, f1 = self._flips(True)
+        crop = (int(self.crop_size_arr[0]), int(self.crop_size_arr[1]))
+        p0 = dict(mode=0, pad_top=top, pad_left=left, padded=padded, pos=(int(pos0[0]), int(pos0[1])), src_size=crop,
+                  image_interp=NEAREST, mask_interp=NEAREST, flips=f0,                                       # plain crop (:264)
+                  xf_cv=self._xf(pos0, self.crop_size_arr, top, left, padded))
+        p1 = dict(mode=0, pad_top=top, pad_left=left, padded=padded, pos=(int(pos1[0]), int(pos1[1])),
+                  src_size=(int(sc_size1[0]), int(sc_size1[1])), image_interp=LINEAR, mask_interp=NEAREST, flips=f1,   # :267, :273
+                  xf_cv=self._xf(pos1, sc_size1, top, left, padded))
+        return p0, p1
+
+
+class DeviceRandomCropRotateScale(_DeviceGeomBase):
+    """`SegCVTransformRandomCropRotateScale(crop_size, crop_offset, rot_mag, max_scale, uniform_scale, constrain_rot_scale)` ->
+    `SegCVTransformRandomFlip` -> [`SegCVTransformTVT`] -> `SegCVTransformNormalizeToTensor` on the device: cv2.warpAffine with
+    BORDER_REFLECT_101 for the image and BORDER_CONSTANT for labels (255) / mask (0); nearest-neighbour sampling whenever the
+    sample carries labels (:361-364, :424)."""
+
+    def __init__(self, crop_size, crop_offset=None, rot_mag=0.0, max_scale=1.0, uniform_scale=True, constrain_rot_scale=True,
+                 hflip=False, vflip=False, hvflip=False, mean=None, std=None, rng=None, flip_rng=None):
+        import math
+        import numpy as np
+        self._init_common(crop_size, crop_offset, hflip, vflip, hvflip, mean, std, rng, flip_rng)
+        self.rot_mag_rad = math.radians(rot_mag)
+        self.log_max_scale = np.log(max_scale)
+        self.uniform_scale, self.constrain_rot_scale = bool(uniform_scale), bool(constrain_rot_scale)
+
+    def draw_single(self, img_hw, has_labels):
+        import numpy as np
+        lms = self.log_max_scale
+        if self.uniform_scale:
+            scale_yx = np.repeat(np.exp(self.rng.uniform(-lms, lms, size=(1,))), 2, axis=0)                  # :335-337
+        else:
+            scale_yx = np.exp(self.rng.uniform(-lms, lms, size=(2,)))                                        # :339
+        theta = self.rng.uniform(-self.rot_mag_rad, self.rot_mag_rad, size=(1,))                             # :340
+        sc_size = self.crop_size_arr / scale_yx                                                              # :343
+        img_size = np.array([int(img_hw[0]), int(img_hw[1])])
+        extra = np.maximum(img_size - sc_size, 0.0)
+        centre = extra * self.rng.uniform(0.0, 1.0, size=(2,)) + np.minimum(sc_size, img_size) * 0.5         # :346-348
+        xf = _mat_cat(_mat_translation(self.crop_size_arr[None, ::-1] * 0.5), _mat_rotation(theta),
+                      _mat_scale(scale_yx[None, ::-1]), _mat_translation(-centre[None, ::-1]))               # :351-356
+        if has_labels:
+            interp = NEAREST                                                                                 # :361-362
+        else:
+            interp = int(self.rng.choice([NEAREST, LINEAR]))          # cv2.INTER_NEAREST = 0, cv2.INTER_LINEAR = 1 (:364)
+        return dict(mode=1, matrix=xf[0], image_interp=interp, mask_interp=interp, flips=self._flips(False), xf_cv=xf[0])
+
+    def draw_pair(self, img_hw, has_labels):
+        import numpy as np
+        lms, rot = self.log_max_scale, self.rot_mag_rad
+        if self.constrain_rot_scale:                                                                         # :385-395
+            if self.uniform_scale:
+                scales = np.repeat(np.exp(self.rng.uniform(-lms, lms, size=(1, 1))), 2, axis=1)
+            else:
+                scales = np.exp(self.rng.uniform(-lms, lms, size=(1, 2)))
+            thetas = self.rng.uniform(-rot, rot, size=(1,))
+            scales = np.repeat(scales, 2, axis=0)
+            thetas = np.repeat(thetas, 2, axis=0)
+        else:                                                                                                # :396-402
+            if self.uniform_scale:
+                scales = np.repeat(np.exp(self.rng.uniform(-lms, lms, size=(2, 1))), 2, axis=1)
+            else:
+                scales = np.exp(self.rng.uniform(-lms, lms, size=(2, 2)))
+            thetas = self.rng.uniform(-rot, rot, size=(2,))
+        img_size = np.array([int(img_hw[0]), int(img_hw[1])])
+        sc_size = self.crop_size_arr / scales.min(axis=0)                                                    # :407
+        crop_centre = np.minimum(sc_size, img_size) * 0.5
+        extra = np.maximum(img_size - sc_size, 0.0)
+        centre0 = extra * self.rng.uniform(0.0, 1.0, size=(2,)) + crop_centre                                # :412
+        offset1 = np.round(self.crop_offset * self.rng.uniform(-1.0, 1.0, size=(2,)))                        # :413
+        centre_xlat = np.stack([centre0, centre0], axis=0)
+        offset1_xlat = np.stack([np.zeros((2,)), offset1], axis=0)
+        xfs = _mat_cat(_mat_translation(self.crop_size_arr[None, ::-1] * 0.5), _mat_translation(offset1_xlat[:, ::-1]),
+                       _mat_rotation(thetas), _mat_scale(scales[:, ::-1]), _mat_translation(-centre_xlat[:, ::-1]))   # :418-424
+        interp = NEAREST if has_labels else LINEAR                                                           # :427
+        f0, f1 = self._flips(True)
+        return tuple(dict(mode=1, matrix=xfs[i], image_interp=interp, mask_interp=interp, flips=f, xf_cv=xfs[i])
+                     for i, f in ((0, f0), (1, f1)))

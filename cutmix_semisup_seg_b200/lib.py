@@ -89,6 +89,7 @@ _SIGS = {
     'b2_u8_to_tensor': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'b2_crop_flip_normalize': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b2_crop_flip_u8': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'b2_geom_u8': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     'b2_colour_jitter': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     'b2_upsample2x_add': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b2_upsample2x_bwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),

@@ -309,6 +309,19 @@ class CudaBackend(object):
                    self._s())
         return image, labels, mask
 
+    def geom_u8(self, entries, tables, n, out_h, out_w, want_labels, want_mask, device):
+        """b2_geom_u8: scale / rotation crop (cv2.resize / cv2.warpAffine in OpenCV's fixed-point arithmetic) + flip of n
+        variable-size uint8 samples -> RGBA uint8 (n, h, w, 4), labels int64 (n,1,h,w) | None, mask fp32 (n,1,h,w) | None.
+        entries: device uint8 tensor of n b2_geom_entry records; tables: device int32 tensor."""
+        assert entries.dtype == torch.uint8 and entries.numel() == n * 88 and tables.dtype == torch.int32
+        assert tables.numel() >= n * 3 * (out_h + out_w)
+        image = torch.empty((n, out_h, out_w, 4), device=device, dtype=torch.uint8)
+        labels = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.int64) if want_labels else None
+        mask = torch.empty((n, 1, out_h, out_w), device=device, dtype=torch.float32) if want_mask else None
+        self._call('b2_geom_u8', entries.data_ptr(), tables.data_ptr(), int(n), int(out_h), int(out_w), image.data_ptr(), L.ptr(labels),
+                   L.ptr(mask), self._s())
+        return image, labels, mask
+
     def colour_jitter(self, img_u8, table_np):
         """In-place colour jitter of uint8 (N,H,W,3|4) pixels (b2_colour_jitter).  table_np: numpy structured array of N
         b2_colour_entry records (host); its device copy is made here."""

@@ -212,6 +212,26 @@ int b2_crop_flip_normalize(const b2_crop_entry* table, int n, int out_h, int out
 int b2_crop_flip_u8(const b2_crop_entry* table, int n, int out_h, int out_w, uint8_t* image_rgba, int64_t* labels, float* mask,
                     void* stream);
 
+/* Scale / rotation crops on uint8 pixels -- SegCVTransformRandomCropScaleHung (datapipe/seg_transforms_cv.py:169-303: cv2.resize
+ * INTER_LINEAR / INTER_NEAREST of a window of the padded image) and SegCVTransformRandomCropRotateScale (:305-449: cv2.warpAffine,
+ * BORDER_REFLECT_101 image, BORDER_CONSTANT labels 255 / mask 0), then SegCVTransformRandomFlip.flip_image (:467-474): one gather
+ * per output pixel in OpenCV's fixed-point arithmetic (byte-identical to cv2).  `tables`: DEVICE int32, 3 * (out_h + out_w) entries
+ * per sample at tab_off (layout: csrc/input.cu; built by input_pipeline.resize_tables / warp_tables).  Outputs as b2_crop_flip_u8. */
+typedef struct {
+  const uint8_t* image;        /* (h0, w0, 3) */
+  const uint8_t* labels;       /* (h0, w0) or NULL */
+  const uint8_t* mask;         /* (h0, w0) or NULL */
+  int32_t h0, w0;
+  int32_t mode;                /* 0: crop window + resize, 1: warpAffine */
+  int32_t pad_top, pad_left, padded;          /* mode 0: virtual padding (SegCVTransformPad) */
+  int32_t pos_y, pos_x, src_h, src_w;         /* mode 0: window in padded coordinates */
+  int32_t image_interp, mask_interp;          /* 0 nearest, 1 linear, 2 exact 2x decimation (2x2 average); labels: nearest */
+  int32_t tab_off;
+  int32_t flip_x, flip_y, flip_d;
+} b2_geom_entry;               /* 88 bytes */
+int b2_geom_u8(const b2_geom_entry* table, const int32_t* tables, int n, int out_h, int out_w, uint8_t* image_rgba, int64_t* labels,
+               float* mask, void* stream);
+
 /* Colour jitter on uint8 pixels, in place: torchvision ColorJitter + RandomGrayscale on PIL images as applied by the reference's
  * SegCVTransformTVT (datapipe/seg_transforms_cv.py:541-586; assembled in train_seg_semisup_mask_mt.py:169-179), byte-identical to
  * Pillow's arithmetic.  Per image up to 4 operations in the drawn order -- op 0 brightness, 1 contrast, 2 saturation (factor =

@@ -525,6 +525,54 @@ def gen_input_pipeline():
     np.savez_compressed(os.path.join(OUT, 'input_pipeline.npz'), **out)
 
 
+def gen_geom_pipeline():
+    """SURVEY.md 8f row 4, scale / rotation crops: the reference's OWN SegCVTransformRandomCropScaleHung / SegCVTransformRandomCropRotateScale
+    (datapipe/seg_transforms_cv.py:169-449, imported unmodified; they call cv2.resize / cv2.warpAffine of the installed OpenCV) ->
+    SegCVTransformRandomFlip -> SegCVTransformNormalizeToTensor on the seeded uint8 samples of tests/geom_recipe.py, single samples
+    and pairs, each sample entering with an identity `xf_cv` so that the transform's matrix is recorded as well (after the crop
+    stage, before the flips).  `img_as_float` substituted as in gen_input_pipeline.  -> tests/golden/geom_pipeline.npz"""
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    import geom_recipe as GR
+    fake = types.ModuleType('skimage')
+    fake.img_as_float = lambda a: np.multiply(a, 1. / 255, dtype=np.float64)
+    sys.modules.setdefault('skimage', fake)
+    from datapipe import seg_transforms_cv as TCV, affine
+    assert os.path.realpath(TCV.__file__).startswith(os.path.realpath(REF))
+    out = {}
+    for name, case in GR.CASES.items():
+        rng = np.random.RandomState(case['seed'])
+        if case['kind'] == 'hung':
+            crop = TCV.SegCVTransformRandomCropScaleHung(case['crop_size'], case['crop_offset'], uniform_scale=case['uniform_scale'], rng=rng)
+        else:
+            crop = TCV.SegCVTransformRandomCropRotateScale(case['crop_size'], case['crop_offset'], case['rot_mag'], case['max_scale'],
+                                                           uniform_scale=case['uniform_scale'],
+                                                           constrain_rot_scale=case['constrain_rot_scale'], rng=rng)
+        flip = TCV.SegCVTransformRandomFlip(case['hflip'], case['vflip'], case['hvflip'], rng=np.random.RandomState(case['seed'] + 1))
+        norm = TCV.SegCVTransformNormalizeToTensor(None if case['mean'] is None else np.array(case['mean']),
+                                                   None if case['std'] is None else np.array(case['std']))
+        res, xfs = [], []
+        for smp in GR.make_samples(case):
+            smp = dict(smp, xf_cv=affine.identity_xf(1)[0])
+            if case['pair']:
+                a, b = crop.transform_pair(dict(smp), dict(smp))
+                xfs.extend([a['xf_cv'], b['xf_cv']])
+                a, b = norm.transform_pair(*flip.transform_pair(a, b))
+                res.extend([a, b])
+            else:
+                a = crop.transform_single(dict(smp))
+                xfs.append(a.pop('xf_cv'))      # (the reference's single-sample flip cannot take a sample that carries xf_cv)
+                res.append(norm.transform_single(flip.transform_single(a)))
+        out[name + '.image'] = np.stack([r['image'] for r in res])
+        out[name + '.xf_cv'] = np.stack(xfs)
+        if 'labels' in res[0]:
+            out[name + '.labels'] = np.stack([r['labels'] for r in res])
+        if 'mask' in res[0]:
+            out[name + '.mask'] = np.stack([r['mask'] for r in res])
+        print(' ', name, out[name + '.image'].shape, out[name + '.image'].dtype, out[name + '.xf_cv'].dtype)
+    np.savez_compressed(os.path.join(OUT, 'geom_pipeline.npz'), **out)
+
+
 def gen_toy2d():
     """BASELINE config 1: the reference's OWN job function `toy2d_train.train_toy2d` (imported unmodified from /root/reference) run
     on the cases of tests/toy2d_recipe.py with torch.manual_seed(TORCH_SEED).  The reference's `toy2d/generate_data.py` cannot be

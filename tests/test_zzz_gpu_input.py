@@ -97,3 +97,87 @@ def test_colour_kernels_match_the_pillow_arithmetic_on_all_colours():
     rgba = torch.from_numpy(np.concatenate([cube[:64], np.full((64, 4096, 1), 200, np.uint8)], axis=2)[None]).to(dev).contiguous()
     cj(rgba, [cases[-1]])
     assert np.array_equal(rgba.cpu().numpy()[0, ..., :3], CR.apply(cube[:64], cases[-1])) and int(rgba[..., 3].min()) == 200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['hung_single', 'hung_single_nonuniform', 'hung_pair', 'hung_pair_labels', 'rot_single_labels',
+                                  'rot_single_nolabels', 'rot_pair', 'rot_pair_free'])
+def test_scale_rotation_crop_kernel_matches_the_reference_transform_classes(name):
+    """b2_geom_u8 (cv2.resize / cv2.warpAffine in OpenCV's fixed-point arithmetic + flips, one gather over variable-size uint8 images)
+    -> b2_normalize_to_tensor against the outputs of the reference's own SegCVTransformRandomCropScaleHung /
+    SegCVTransformRandomCropRotateScale -> RandomFlip -> NormalizeToTensor classes (tests/golden/geom_pipeline.npz), and the raw
+    RGBA / label / mask bytes against the numpy statement of the kernel."""
+    import geom_recipe as GR
+    dev = torch.device('cuda:0')
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'geom_pipeline.npz'))
+    case = GR.CASES[name]
+    tf, samples, params = GR.drawn(case)
+    dev_samples = [{k: torch.from_numpy(v).to(dev) for k, v in s.items()} for s in samples]
+    out = tf(dev_samples, params)
+    assert np.array_equal(out['image'].cpu().numpy(), gold[name + '.image'])
+    if case['labels']:
+        assert out['labels'].dtype == torch.int64 and np.array_equal(out['labels'].cpu().numpy(), gold[name + '.labels'])
+    else:
+        assert 'labels' not in out
+    if case['mask']:
+        assert np.array_equal(out['mask'].cpu().numpy(), gold[name + '.mask'])
+    # the un-normalised bytes of the kernel itself
+    ent, tab = tf.tables(dev_samples, params)
+    from cutmix_semisup_seg_b200 import ops
+    h, w = case['crop_size']
+    rgba, _, _ = ops.default_backend().geom_u8(torch.from_numpy(ent.view('u1').copy()).to(dev), torch.from_numpy(tab).to(dev),
+                                               len(samples), h, w, False, False, dev)
+    rgba = rgba.cpu().numpy()
+    for i, (s, p) in enumerate(zip(samples, params)):
+        assert np.array_equal(rgba[i], GR.flip(GR.geom_u8(s, p, case['crop_size'])[0], p['flips'])), i
+    # host (pinned) samples are copied first: same result
+    out2 = tf([{k: torch.from_numpy(v).pin_memory() for k, v in s.items()} for s in samples], params)
+    assert torch.equal(out2['image'], out['image'])
+
+
+@pytest.mark.gpu
+def test_scale_crop_full_size_against_cv2_and_colour_chain():
+    """Pascal-recipe sizes (321 x 321 crops of ~500 x 375 images, every scale factor 0.5 ... 1.5): the kernel's RGBA bytes against
+    cv2.resize itself; then the colour-jitter branch on top of the scaled crops runs through the same kernels as the plain-crop
+    pipeline (bytes = numpy statement of geom + tests/colour_recipe.py)."""
+    cv2 = pytest.importorskip('cv2')
+    cv2.setNumThreads(0)
+    import colour_recipe as CR
+    import geom_recipe as GR
+    from cutmix_semisup_seg_b200 import input_pipeline as IP, ops
+    dev = torch.device('cuda:0')
+    rng = np.random.RandomState(5)
+    crop = (321, 321)
+    tf = IP.DeviceRandomCropScaleHung(crop, (0, 0), hflip=True, rng=np.random.RandomState(1), flip_rng=np.random.RandomState(2))
+    samples, params = [], []
+    for f10 in range(5, 16):
+        sc = int(np.round(321 / (f10 / 10.0)))
+        h0, w0 = sc + int(rng.randint(0, 40)), sc + int(rng.randint(0, 60))
+        s = dict(image_arr=rng.randint(0, 256, size=(h0, w0, 3)).astype(np.uint8), mask_arr=rng.randint(0, 256, size=(h0, w0)).astype(np.uint8))
+        pos = (int(rng.randint(0, h0 - sc + 1)), int(rng.randint(0, w0 - sc + 1)))
+        samples.append(s)
+        params.append(dict(mode=0, pad_top=0, pad_left=0, padded=0, pos=pos, src_size=(sc, sc), image_interp=IP.LINEAR,
+                           mask_interp=IP.LINEAR, flips=(False, False, False)))
+    dev_samples = [{k: torch.from_numpy(v).to(dev) for k, v in s.items()} for s in samples]
+    ent, tab = tf.tables(dev_samples, params)
+    be = ops.default_backend()
+    rgba, _, mask = be.geom_u8(torch.from_numpy(ent.view('u1').copy()).to(dev), torch.from_numpy(tab).to(dev), len(samples), 321, 321,
+                               False, True, dev)
+    got, got_m = rgba.cpu().numpy(), mask.cpu().numpy()
+    for i, (s, p) in enumerate(zip(samples, params)):
+        (y, x), (sh, sw) = p['pos'], p['src_size']
+        want = cv2.resize(s['image_arr'][y:y + sh, x:x + sw], (321, 321), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(got[i, ..., :3], want), i
+        want_m = cv2.resize(s['mask_arr'][y:y + sh, x:x + sw], (321, 321), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(got_m[i, 0], np.multiply(want_m, 1. / 255, dtype=np.float64).astype(np.float32)), i
+    # colour jitter on the scaled crops (strong-colour branch of the Pascal recipe)
+    cj = IP.DeviceColourJitter()
+    torch.manual_seed(3)
+    cparams = [cj.draw() for _ in samples]
+    tf.mean, tf.std = GR.MEAN, GR.STD
+    out = tf(dev_samples, params, colour=cj, colour_params=cparams)
+    for i, (s, p, cp) in enumerate(zip(samples, params, cparams)):
+        u8 = GR.geom_u8(s, p, crop)[0]
+        j = CR.apply(u8[..., :3], cp)
+        v = (np.multiply(j, 1. / 255, dtype=np.float64) - np.array(GR.MEAN)[None, None, :]) / np.array(GR.STD)[None, None, :]
+        assert np.array_equal(out['image'][i].cpu().numpy(), v.transpose(2, 0, 1).astype(np.float32)), i

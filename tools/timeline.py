@@ -101,6 +101,14 @@ for g, a, b in gaps:
 P('idle time by preceding kernel:')
 for k, (c, t) in sorted(by.items(), key=lambda kv: -kv[1][1])[:15]:
     P('  %-60s n=%4d  %8.3f ms  (%.2f us each)' % (k, c, t / 1e3, t / c))
+# in-graph duration per kernel name (the eager per-launch profile of bench.py runs with gaps between launches, i.e. cooler)
+tot = {}
+for s_, e_, name in it:
+    k = short(name)
+    tot.setdefault(k, [0, 0.0]); tot[k][0] += 1; tot[k][1] += e_ - s_
+P('in-graph time by kernel (one iteration):')
+for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    P('  %-60s n=%4d  %9.3f ms  %5.1f %%  (%.1f us each)' % (k, c, t / 1e3, 100.0 * t / ksum, t / c))
 txt = '\n'.join(lines)
 print(txt)
 if out_path:
