@@ -82,7 +82,9 @@ class DeviceCropFlipNormalize(object):
         top, left, padded, size = self._pad(img_hw)
         extra = size - self.crop_size
         pos = np.round(extra * self.crop_rng.uniform(0.0, 1.0, size=(2,))).astype(int)                       # :124-125
-        flags = (self.flip_rng.binomial(1, 0.5, size=(3,)) != 0) & np.array([self.hflip, self.vflip, self.hvflip])   # :480-481
+        on = np.array([self.hflip, self.vflip, self.hvflip])
+        # the entry points add the flip transform only if a flip is enabled (train_seg_semisup_mask_mt.py:163-165)
+        flags = ((self.flip_rng.binomial(1, 0.5, size=(3,)) != 0) & on) if on.any() else np.zeros(3, bool)              # :480-481
         return dict(pad_top=top, pad_left=left, padded=padded, pos=(int(pos[0]), int(pos[1])), flips=tuple(bool(f) for f in flags))
 
     def draw_pair(self, img_hw):
@@ -92,7 +94,8 @@ class DeviceCropFlipNormalize(object):
         pos0 = np.round(extra * self.crop_rng.uniform(0.0, 1.0, size=(2,))).astype(int)                      # :143-144
         pos1 = pos0 + np.round(self.crop_offset * self.crop_rng.uniform(-1.0, 1.0, size=(2,))).astype(int)   # :145
         pos1 = np.clip(pos1, np.array([0, 0]), extra)                                                        # :147
-        flags = (self.flip_rng.binomial(1, 0.5, size=(2, 3)) != 0) & np.array([[self.hflip, self.vflip, self.hvflip]])   # :503-504
+        on = np.array([[self.hflip, self.vflip, self.hvflip]])
+        flags = ((self.flip_rng.binomial(1, 0.5, size=(2, 3)) != 0) & on) if on.any() else np.zeros((2, 3), bool)       # :503-504
         return tuple(dict(pad_top=top, pad_left=left, padded=padded, pos=(int(p[0]), int(p[1])), flips=tuple(bool(f) for f in fl))
                      for p, fl in ((pos0, flags[0]), (pos1, flags[1])))
 
@@ -114,7 +117,11 @@ class DeviceCropFlipNormalize(object):
                       int(crop_size[1]), int(p['flips'][0]), int(p['flips'][1]), int(p['flips'][2]))
         return arr
 
-    def __call__(self, samples, params, colour=None, colour_params=None):
+    def crops_u8(self, samples, params):
+        """The cropped / flipped samples as pixels: (RGBA uint8 (N,h,w,4), labels int64 (N,1,h,w) | None, mask fp32 (N,1,h,w) | None)."""
+        return self(samples, params, raw=True)
+
+    def __call__(self, samples, params, colour=None, colour_params=None, raw=False):
         """samples: list of dicts with `image_arr` uint8 (H_i, W_i, 3) and optionally `labels_arr` / `mask_arr` uint8 (H_i, W_i),
         contiguous CUDA tensors (or host tensors, copied first); params: one `draw_*` dict per sample.  Returns a dict with
         `image` fp32 (N,3,h,w) and, if every sample has them, `labels` int64 (N,1,h,w) / `mask` fp32 (N,1,h,w).
@@ -140,8 +147,11 @@ class DeviceCropFlipNormalize(object):
         want_labels = all('labels_arr' in d for d in moved)
         want_mask = all('mask_arr' in d for d in moved)
         h, w = int(self.crop_size[0]), int(self.crop_size[1])
-        if colour is not None:
+        if colour is not None or raw:
             rgba, labels, mask = self.be.crop_flip_u8(tab, len(moved), h, w, want_labels, want_mask, dev)
+            self._keep = (moved, tab)
+            if raw:
+                return rgba, labels, mask
             colour(rgba, colour_params)
             image = self.be.normalize_to_tensor(rgba, self.mean, self.std)
         else:
@@ -344,6 +354,8 @@ class _DeviceGeomBase(object):
         """SegCVTransformRandomFlip.transform_single / transform_pair (:478-481, :500-504)."""
         import numpy as np
         on = np.array([self.hflip, self.vflip, self.hvflip])
+        if not on.any():              # the entry points add the flip transform only if a flip is enabled (:163-165): nothing is drawn
+            return ((False,) * 3, (False,) * 3) if pair else (False,) * 3
         if not pair:
             return tuple(bool(f) for f in ((self.flip_rng.binomial(1, 0.5, size=(3,)) != 0) & on))
         fl = (self.flip_rng.binomial(1, 0.5, size=(2, 3)) != 0) & on[None]
@@ -390,7 +402,11 @@ class _DeviceGeomBase(object):
                 e['image_interp'], e['mask_interp'] = p['image_interp'], p['mask_interp']
         return ent, tab
 
-    def __call__(self, samples, params, colour=None, colour_params=None):
+    def crops_u8(self, samples, params):
+        """The scaled / rotated / flipped crops as pixels: (RGBA uint8 (N,h,w,4), labels int64 | None, mask fp32 | None)."""
+        return self(samples, params, raw=True)
+
+    def __call__(self, samples, params, colour=None, colour_params=None, raw=False):
         """samples: list of dicts with `image_arr` uint8 (H_i, W_i, 3) [+ `labels_arr` / `mask_arr` uint8 (H_i, W_i)] (CUDA tensors,
         or host tensors that are copied first); params: one `draw_*` dict per sample.  Returns `image` fp32 (N,3,h,w) [+ `labels`
         int64 (N,1,h,w), `mask` fp32 (N,1,h,w)] as the reference's collate function would have produced them after
@@ -417,6 +433,9 @@ class _DeviceGeomBase(object):
         want_mask = all('mask_arr' in d for d in moved)
         h, w = self.crop_size
         rgba, labels, mask = self.be.geom_u8(ent_dev, tab_dev, len(moved), h, w, want_labels, want_mask, dev)
+        self._keep = (moved, ent_dev, tab_dev)
+        if raw:
+            return rgba, labels, mask
         if colour is not None:
             colour(rgba, colour_params)
         image = self.be.normalize_to_tensor(rgba, self.mean, self.std)
@@ -564,3 +583,70 @@ class DeviceRandomCropRotateScale(_DeviceGeomBase):
         f0, f1 = self._flips(True)
         return tuple(dict(mode=1, matrix=xfs[i], image_interp=interp, mask_interp=interp, flips=f, xf_cv=xfs[i])
                      for i, f in ((0, f0), (1, f1)))
+
+
+class DeviceTrainPipeline(object):
+    """The train-time transform lists of the entry points (train_seg_semisup_mask_mt.py:147-179) assembled from the device
+    transforms above: geometric stage by option -- `aug_scale_hung` -> SegCVTransformRandomCropScaleHung, `aug_max_scale != 1` or
+    `aug_rot_mag != 0` -> SegCVTransformRandomCropRotateScale(constrain_rot_scale=True), else SegCVTransformRandomCrop (crop offset
+    (0, 0)) --, SegCVTransformRandomFlip if any flip is enabled, and for the unsupervised samples with `aug_strong_colour`
+    SegTransformToPair + SegCVTransformTVT(ColorJitter / RandomGrayscale) on the second member (`unsup_paired`), then
+    SegCVTransformNormalizeToTensor(NET_MEAN, NET_STD).  As in the reference the supervised and the unsupervised list SHARE the
+    geometric and flip transform objects (`train_unsup_transforms = train_transforms.copy()`, :167), i.e. their generators.
+
+    The DataLoader side shrinks to decoding: `sup_batch` / `unsup_batch` take lists of uint8 samples (`image_arr` (H,W,3) +
+    `labels_arr` for supervised, + `mask_arr` for unsupervised samples, as `ds_src.dataset(labels=..., mask=...)` yields them,
+    :181-189) and return the tensors `seg_data.SegCollate` would have stacked."""
+
+    def __init__(self, crop_size, mean, std, aug_hflip=False, aug_vflip=False, aug_hvflip=False, aug_scale_hung=False,
+                 aug_max_scale=1.0, aug_scale_non_uniform=False, aug_rot_mag=0.0, aug_strong_colour=False,
+                 aug_colour_brightness=0.4, aug_colour_contrast=0.4, aug_colour_saturation=0.4, aug_colour_hue=0.1,
+                 aug_colour_prob=0.8, aug_colour_greyscale_prob=0.2, rng=None, flip_rng=None):
+        if crop_size is None:
+            raise NotImplementedError('the device pipeline needs a crop_size (fixed-size batches)')
+        any_flip = aug_hflip or aug_vflip or aug_hvflip
+        common = dict(hflip=aug_hflip, vflip=aug_vflip, hvflip=aug_hvflip, mean=mean, std=std, flip_rng=flip_rng)
+        if aug_scale_hung:                                                                                   # :151-152
+            self.geom = DeviceRandomCropScaleHung(crop_size, (0, 0), uniform_scale=not aug_scale_non_uniform, rng=rng, **common)
+            self.kind = 'hung'
+        elif aug_max_scale != 1.0 or aug_rot_mag != 0.0:                                                     # :153-155
+            self.geom = DeviceRandomCropRotateScale(crop_size, (0, 0), rot_mag=aug_rot_mag, max_scale=aug_max_scale,
+                                                    uniform_scale=not aug_scale_non_uniform, constrain_rot_scale=True, rng=rng, **common)
+            self.kind = 'rot'
+        else:                                                                                                # :156-157
+            self.geom = DeviceCropFlipNormalize(crop_size, (0, 0), crop_rng=rng, **common)
+            self.kind = 'crop'
+        self.any_flip = bool(any_flip)
+        self.colour = DeviceColourJitter(aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
+                                         aug_colour_prob, aug_colour_greyscale_prob) if aug_strong_colour else None
+        self.unsup_paired = bool(aug_strong_colour)                                                          # :170-179
+        self.mean, self.std = self.geom.mean, self.geom.std
+
+    def _draw(self, sample):
+        hw = sample['image_arr'].shape[:2]
+        if self.kind == 'rot':
+            return self.geom.draw_single(hw, sample.get('labels_arr') is not None)
+        return self.geom.draw_single(hw)
+
+    def _crops(self, samples):
+        params = [self._draw(s) for s in samples]
+        return self.geom.crops_u8(samples, params)
+
+    def sup_batch(self, samples):
+        """-> dict(image fp32 (N,3,h,w), labels int64 (N,1,h,w))"""
+        rgba, labels, _ = self._crops([{k: v for k, v in s.items() if k != 'mask_arr'} for s in samples])
+        be = self.geom.be
+        return dict(image=be.normalize_to_tensor(rgba, self.mean, self.std), labels=labels)
+
+    def unsup_batch(self, samples):
+        """-> dict(image, mask), or with aug_strong_colour dict(sample0=dict(image, mask), sample1=dict(image, mask)) where sample1 is
+        the colour-jittered copy of the same crop (SegTransformToPair, then SegCVTransformTVT on the second member only)."""
+        rgba, _, mask = self._crops([{k: v for k, v in s.items() if k != 'labels_arr'} for s in samples])
+        be = self.geom.be
+        image0 = be.normalize_to_tensor(rgba, self.mean, self.std)
+        if not self.unsup_paired:
+            return dict(image=image0, mask=mask)
+        cparams = [self.colour.draw() for _ in samples]
+        rgba1 = rgba.clone()
+        self.colour(rgba1, cparams)
+        return dict(sample0=dict(image=image0, mask=mask), sample1=dict(image=be.normalize_to_tensor(rgba1, self.mean, self.std), mask=mask))

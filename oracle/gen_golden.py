@@ -573,6 +573,69 @@ def gen_geom_pipeline():
     np.savez_compressed(os.path.join(OUT, 'geom_pipeline.npz'), **out)
 
 
+def gen_train_pipeline():
+    """the train-time transform lists exactly as train_seg_semisup_mask_mt.py:147-179 assembles them from the
+    reference's OWN classes (SegCVTransformRandomCropScaleHung | RandomCropRotateScale | RandomCrop, RandomFlip, SegTransformToPair,
+    SegCVTransformTVT, NormalizeToTensor; SegTransformCompose), with seeded generators handed to the crop and flip transforms
+    (shared by the supervised and unsupervised list like in the script), applied sample by sample to the seeded uint8 samples of
+    tests/pipeline_recipe.py in the order sup_a, unsup, sup_b.  -> tests/golden/train_pipeline.npz"""
+    import types
+    import torchvision.transforms as tvt
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    import pipeline_recipe as PR
+    fake = types.ModuleType('skimage')
+    fake.img_as_float = lambda a: np.multiply(a, 1. / 255, dtype=np.float64)
+    sys.modules.setdefault('skimage', fake)
+    from datapipe import seg_transforms, seg_transforms_cv
+    assert os.path.realpath(seg_transforms_cv.__file__).startswith(os.path.realpath(REF))
+    NET_MEAN, NET_STD = np.array(PR.MEAN), np.array(PR.STD)
+    out = {}
+    for name, case in PR.CASES.items():
+        o = PR.options(case)
+        crop_size = case['crop_size']
+        rng, flip_rng = np.random.RandomState(case['seed']), np.random.RandomState(case['seed'] + 1)
+        # ---- train_seg_semisup_mask_mt.py:147-179 (the script's lines; only `rng=` added to the constructors)
+        train_transforms = []
+        if o['aug_scale_hung']:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCropScaleHung(crop_size, (0, 0), uniform_scale=not o['aug_scale_non_uniform'], rng=rng))
+        elif o['aug_max_scale'] != 1.0 or o['aug_rot_mag'] != 0.0:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCropRotateScale(
+                crop_size, (0, 0), rot_mag=o['aug_rot_mag'], max_scale=o['aug_max_scale'], uniform_scale=not o['aug_scale_non_uniform'],
+                constrain_rot_scale=True, rng=rng))
+        else:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCrop(crop_size, (0, 0), rng=rng))
+        if o['aug_hflip'] or o['aug_vflip'] or o['aug_hvflip']:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomFlip(o['aug_hflip'], o['aug_vflip'], o['aug_hvflip'], rng=flip_rng))
+        train_unsup_transforms = train_transforms.copy()
+        if o['aug_strong_colour']:
+            colour_xforms = tvt.Compose([
+                tvt.RandomApply([tvt.ColorJitter(o['aug_colour_brightness'], o['aug_colour_contrast'], o['aug_colour_saturation'],
+                                                 o['aug_colour_hue'])], p=o['aug_colour_prob']),
+                tvt.RandomGrayscale(p=o['aug_colour_greyscale_prob']),
+            ])
+            train_unsup_transforms.append(seg_transforms.SegTransformToPair())
+            train_unsup_transforms.append(seg_transforms_cv.SegCVTransformTVT(colour_xforms))
+        train_transforms.append(seg_transforms_cv.SegCVTransformNormalizeToTensor(NET_MEAN, NET_STD))
+        train_unsup_transforms.append(seg_transforms_cv.SegCVTransformNormalizeToTensor(NET_MEAN, NET_STD))
+        sup = seg_transforms.SegTransformCompose(train_transforms)
+        unsup = seg_transforms.SegTransformCompose(train_unsup_transforms)
+        # ----
+        torch.manual_seed(case['torch_seed'])
+        for part, xf in (('sup_a', sup), ('unsup', unsup), ('sup_b', sup)):
+            res = [xf.apply(dict(smp)) for smp in PR.make_samples(case, part)]
+            key = name + '.' + part
+            if part == 'unsup' and o['aug_strong_colour']:
+                for m in ('sample0', 'sample1'):
+                    out[key + '.' + m + '.image'] = np.stack([r[m]['image'] for r in res])
+                    out[key + '.' + m + '.mask'] = np.stack([r[m]['mask'] for r in res])
+            elif part == 'unsup':
+                out[key + '.image'] = np.stack([r['image'] for r in res]); out[key + '.mask'] = np.stack([r['mask'] for r in res])
+            else:
+                out[key + '.image'] = np.stack([r['image'] for r in res]); out[key + '.labels'] = np.stack([r['labels'] for r in res])
+        print(' ', name, sorted(k for k in out if k.startswith(name + '.unsup')))
+    np.savez_compressed(os.path.join(OUT, 'train_pipeline.npz'), **out)
+
+
 def gen_toy2d():
     """BASELINE config 1: the reference's OWN job function `toy2d_train.train_toy2d` (imported unmodified from /root/reference) run
     on the cases of tests/toy2d_recipe.py with torch.manual_seed(TORCH_SEED).  The reference's `toy2d/generate_data.py` cannot be

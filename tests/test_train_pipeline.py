@@ -1,0 +1,107 @@
+"""CPU: the assembled train-time input pipeline (cutmix_semisup_seg_b200.input_pipeline.DeviceTrainPipeline; reference
+train_seg_semisup_mask_mt.py:147-179).  The pipeline's parameter draws (geometry and flips from generators SHARED by the supervised
+and unsupervised list, colour jitter from torch's generator) combined with the numpy statements of the kernels reproduce bit for bit
+what the reference's own transform classes, composed by the script's own lines, produced (tests/golden/train_pipeline.npz).  The
+`-m gpu` half runs DeviceTrainPipeline itself on the B200 against the same bytes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(__file__)
+sys.path.insert(0, HERE)
+import pipeline_recipe as PR  # noqa: E402
+
+
+def make_pipeline(case):
+    from cutmix_semisup_seg_b200.input_pipeline import DeviceTrainPipeline
+    return DeviceTrainPipeline(case['crop_size'], PR.MEAN, PR.STD, rng=np.random.RandomState(case['seed']),
+                               flip_rng=np.random.RandomState(case['seed'] + 1), **PR.options(case))
+
+
+def crops_statement(pipe, samples, params):
+    """RGBA uint8 crops + labels / mask planes from the numpy statements of the kernels (geom_recipe / input_recipe)."""
+    import geom_recipe as GR
+    import input_recipe as IR
+    out = []
+    for s, p in zip(samples, params):
+        if pipe.kind == 'crop':
+            r = IR.reference_statement([s], [p], pipe.geom.crop_size, None, None)
+            rgb = np.rint(r['image'][0].transpose(1, 2, 0).astype(np.float64) * 255.0).astype(np.uint8)
+            probe = IR.reference_statement([dict(image_arr=np.full(s['image_arr'].shape, 255, np.uint8))], [p], pipe.geom.crop_size, None, None)
+            alpha = np.rint(probe['image'][0, 0].astype(np.float64) * 255.0).astype(np.uint8)
+            out.append((np.concatenate([rgb, alpha[..., None]], axis=2), r.get('labels', [None])[0], r.get('mask', [None])[0]))
+        else:
+            rgba, lab, msk = GR.geom_u8(s, p, pipe.geom.crop_size)
+            f = p['flips']
+            out.append((GR.flip(rgba, f), None if lab is None else GR.flip(lab, f)[None].astype(np.int64),
+                        None if msk is None else np.multiply(GR.flip(msk, f), 1. / 255, dtype=np.float64)[None].astype(np.float32)))
+    return out
+
+
+def normalise(rgba):
+    v = np.multiply(rgba[..., :3], 1. / 255, dtype=np.float64)
+    alpha = np.multiply(rgba[..., 3:4], 1. / 255, dtype=np.float64)
+    v = (v - np.array(PR.MEAN)[None, None, :] * alpha) / np.array(PR.STD)[None, None, :]
+    return v.transpose(2, 0, 1).astype(np.float32)
+
+
+@pytest.mark.parametrize('name', sorted(PR.CASES))
+def test_pipeline_draws_and_kernel_statements_match_the_reference_composition(name):
+    import colour_recipe as CR
+    gold = np.load(os.path.join(HERE, 'golden', 'train_pipeline.npz'))
+    case = PR.CASES[name]
+    pipe = make_pipeline(case)
+    assert pipe.unsup_paired == PR.options(case)['aug_strong_colour']
+    assert pipe.kind == dict(cityscapes='crop', pascal='hung', isic='rot', plain='crop')[name]
+    torch.manual_seed(case['torch_seed'])
+    for part in ('sup_a', 'unsup', 'sup_b'):
+        samples = PR.make_samples(case, part)
+        use = [{k: v for k, v in s.items() if k != ('mask_arr' if part != 'unsup' else 'labels_arr')} for s in samples]
+        params = [pipe._draw(s) for s in use]
+        crops = crops_statement(pipe, use, params)
+        key = name + '.' + part
+        if part != 'unsup':
+            assert np.array_equal(np.stack([normalise(c[0]) for c in crops]), gold[key + '.image'])
+            assert np.array_equal(np.stack([c[1] for c in crops]), gold[key + '.labels'])
+        elif not pipe.unsup_paired:
+            assert np.array_equal(np.stack([normalise(c[0]) for c in crops]), gold[key + '.image'])
+            assert np.array_equal(np.stack([c[2] for c in crops]), gold[key + '.mask'])
+        else:
+            cparams = [pipe.colour.draw() for _ in use]
+            assert np.array_equal(np.stack([normalise(c[0]) for c in crops]), gold[key + '.sample0.image'])
+            jit = [np.concatenate([CR.apply(c[0][..., :3], cp), c[0][..., 3:]], axis=2) for c, cp in zip(crops, cparams)]
+            assert np.array_equal(np.stack([normalise(j) for j in jit]), gold[key + '.sample1.image'])
+            for m in ('sample0', 'sample1'):
+                assert np.array_equal(np.stack([c[2] for c in crops]), gold[key + '.' + m + '.mask'])
+            assert any(cp['ops'] for cp in cparams)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(PR.CASES))
+def test_device_train_pipeline_matches_the_reference_composition(name):
+    """DeviceTrainPipeline on the B200 (crop / scale / rotation gather, flips, colour jitter, normalise-to-tensor kernels) against the
+    reference's composed transform lists on the same seeds."""
+    gold = np.load(os.path.join(HERE, 'golden', 'train_pipeline.npz'))
+    case = PR.CASES[name]
+    dev = torch.device('cuda:0')
+    pipe = make_pipeline(case)
+    torch.manual_seed(case['torch_seed'])
+    for part in ('sup_a', 'unsup', 'sup_b'):
+        samples = [{k: torch.from_numpy(v).to(dev) for k, v in s.items()} for s in PR.make_samples(case, part)]
+        key = name + '.' + part
+        if part != 'unsup':
+            out = pipe.sup_batch(samples)
+            assert np.array_equal(out['image'].cpu().numpy(), gold[key + '.image'])
+            assert out['labels'].dtype == torch.int64 and np.array_equal(out['labels'].cpu().numpy(), gold[key + '.labels'])
+        else:
+            out = pipe.unsup_batch(samples)
+            if pipe.unsup_paired:
+                for m in ('sample0', 'sample1'):
+                    assert np.array_equal(out[m]['image'].cpu().numpy(), gold[key + '.' + m + '.image']), m
+                    assert np.array_equal(out[m]['mask'].cpu().numpy(), gold[key + '.' + m + '.mask'])
+            else:
+                assert np.array_equal(out['image'].cpu().numpy(), gold[key + '.image'])
+                assert np.array_equal(out['mask'].cpu().numpy(), gold[key + '.mask'])
