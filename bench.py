@@ -157,6 +157,31 @@ def timed_conv_profile(trainer, sup, unsup):
     return be.stop_profile()
 
 
+def in_graph_profile(trainer, sup, unsup, iters=3):
+    """Device timeline of graph-replayed iterations through CUPTI (torch.profiler; outside the timed regions): per-kernel time
+    INSIDE the replay, where kernels run back to back at the sustained (power-capped) clock, and the device idle time between
+    them.  Returns {'kernels': {short name: [launches, ms]} per iteration, 'span_ms', 'idle_ms'} of the middle iteration."""
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            trainer.step(sup, [unsup])
+        torch.cuda.synchronize()
+    evs = sorted((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                 if e.device_type == torch.autograd.DeviceType.CUDA)
+    per = len(evs) // iters
+    if per == 0:
+        return None
+    it = evs[per:2 * per] if iters >= 3 else evs[:per]
+    kernels, busy_end, idle = {}, it[0][0], 0.0
+    for s, e, name in it:
+        short = name.replace('void ', '').replace('(anonymous namespace)::', '').split('(')[0].split('<')[0]
+        k = kernels.setdefault(short, [0, 0.0]); k[0] += 1; k[1] += (e - s) / 1e3
+        if s > busy_end:
+            idle += (s - busy_end) / 1e3
+        busy_end = max(busy_end, e)
+    return {'kernels': kernels, 'span_ms': (busy_end - it[0][0]) / 1e3, 'idle_ms': idle, 'activities': per}
+
+
 def _release():
     """After the caller dropped its trainer (CUDA graphs, tens of GB of graph-private activations): return the memory before
     the next leg builds its own."""
@@ -418,6 +443,14 @@ def run_b200(args):
     # ---- per-kernel roofline (instrumented iteration outside the timed regions)
     # every rank runs it (the iteration contains the gradient all-reduce); only rank 0 reports
     prof = timed_conv_profile(trainer, sup_dev[0], uns_dev[0])
+    in_graph = None
+    if not args.eager and not os.environ.get('B200SEG_SKIP_IN_GRAPH'):
+        try:
+            for _ in range(2):
+                trainer.step(sup_dev[0], [uns_dev[0]])
+            in_graph = in_graph_profile(trainer, sup_dev[0], uns_dev[0])
+        except Exception as e:          # CUPTI unavailable: the eager per-launch profile stands alone
+            in_graph = {'failed': repr(e)[:200]}
     if rank != 0:
         prof = None
     shape_profile = getattr(be, 'last_shape_profile', None)
@@ -498,6 +531,19 @@ def run_b200(args):
                            'per_kernel': {k: {'ms': round(v['ms'], 3), 'n': v['n'],
                                               'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 2)}
                                           for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:24]}}
+        if in_graph and 'kernels' in in_graph:
+            # the same kernel INSIDE the graph replay (CUPTI durations): back to back at the sustained clock, i.e. what the timed
+            # region actually contains; `achieved` above comes from event-timed eager launches that run cooler
+            ig = in_graph['kernels'].get(name)
+            if ig:
+                res['roofline']['in_graph'] = {
+                    'kernel_ms_per_step': round(ig[1], 3), 'launches': ig[0], 'achieved': round(d['flops'] / (ig[1] / 1e3) / 1e12, 2),
+                    'frac': round(d['flops'] / (ig[1] / 1e3) / 1e12 / peaks['bf16_sustained'], 4),
+                    'share_of_step': round(ig[1] / in_graph['span_ms'], 4), 'iteration_span_ms': round(in_graph['span_ms'], 3),
+                    'device_idle_ms': round(in_graph['idle_ms'], 3), 'device_activities': in_graph['activities'],
+                    'how': 'CUPTI kernel durations of one graph-replayed iteration (torch.profiler), outside the timed region'}
+        elif in_graph:
+            res['roofline']['in_graph'] = in_graph
         if args.measure_tf32_peak:
             # MEASURED_PEAKS.json carries bf16 only; the tf32 library rate on THIS box at the clock it settles to, measured
             # here (outside the timed regions), is the like-for-like denominator of a kind::tf32 kernel
