@@ -177,3 +177,59 @@ def synth_state_dict(template, seed=0, logit_gain=1.0, final_keys=()):
         else:
             out[k] = torch.randn(shape, generator=g) * 0.1
     return out
+
+
+class U8ImageSource(object):
+    """`--dataset synthetic_u8`: a seeded stand-in for a DECODED image data set -- uint8 images of assorted sizes around the crop
+    size (some smaller than the crop: they get padded), uint8 label maps with a 255 = ignore band, and the all-valid 255 mask
+    the reference's data sets hand out for unlabelled samples -- kept resident on the device.  The samples have the format of
+    `ds_src.dataset(...)[i]` before the transform list (train_seg_semisup_mask_mt.py:181-189: `image_arr`, `labels_arr`,
+    `mask_arr`), so the train-time pipeline (input_pipeline.DeviceTrainPipeline) runs on them exactly as it would on real decoded
+    images.  The semi-supervised split follows the reference's scheme: a seeded permutation whose first `n_sup` indices are the
+    supervised subset, the unsupervised subset is every sample (`n_unsup == -1`) or the first `n_unsup` (:103-118)."""
+
+    def __init__(self, n_images, crop_hw, num_classes, seed, device, n_sup=100, n_unsup=-1, split_seed=12345):
+        rs = np.random.RandomState(seed)
+        h, w = int(crop_hw[0]), int(crop_hw[1])
+        self.samples = []
+        for i in range(n_images):
+            f_h, f_w = rs.uniform(0.8, 1.7, size=2)
+            ih, iw = max(8, int(round(h * f_h))), max(8, int(round(w * f_w)))
+            # smooth-ish content (blocks of 8 x 8) so that interpolation and colour jitter act on structure, not on white noise
+            coarse = rs.randint(0, 256, size=((ih + 7) // 8, (iw + 7) // 8, 3)).astype(np.uint8)
+            img = np.repeat(np.repeat(coarse, 8, axis=0), 8, axis=1)[:ih, :iw]
+            img = np.clip(img.astype(np.int16) + rs.randint(-12, 13, size=img.shape), 0, 255).astype(np.uint8)
+            lab = np.repeat(np.repeat(rs.randint(0, num_classes, size=((ih + 15) // 16, (iw + 15) // 16)), 16, axis=0), 16, axis=1)[:ih, :iw]
+            lab = lab.astype(np.uint8)
+            lab[:max(1, ih // 16)] = 255
+            self.samples.append(dict(image_arr=torch.from_numpy(np.ascontiguousarray(img)).to(device),
+                                     labels_arr=torch.from_numpy(np.ascontiguousarray(lab)).to(device),
+                                     mask_arr=torch.full((ih, iw), 255, dtype=torch.uint8, device=device)))
+        perm = np.random.RandomState(split_seed).permutation(n_images)
+        n_sup = n_images if n_sup == -1 else min(int(n_sup), n_images)
+        self.sup_ndx = perm[:n_sup]
+        self.unsup_ndx = perm if n_unsup == -1 else perm[:min(int(n_unsup), n_images)]
+
+    def __len__(self):
+        return len(self.samples)
+
+    def sampler(self, indices, batch_size, generator):
+        """RepeatSampler(SubsetRandomSampler(indices)) in batches (seg_data.py RepeatSampler, :199-205 of the script): an endless
+        stream of index batches, every pass a fresh random permutation drawn from `generator`."""
+        indices = np.asarray(indices)
+
+        def gen():
+            buf = []
+            while True:
+                for j in torch.randperm(len(indices), generator=generator).tolist():
+                    buf.append(int(indices[j]))
+                    if len(buf) == batch_size:
+                        yield buf
+                        buf = []
+        return gen()
+
+    def sup(self, idx):
+        return [dict(image_arr=self.samples[i]['image_arr'], labels_arr=self.samples[i]['labels_arr']) for i in idx]
+
+    def unsup(self, idx):
+        return [dict(image_arr=self.samples[i]['image_arr'], mask_arr=self.samples[i]['mask_arr']) for i in idx]

@@ -20,16 +20,25 @@ DATA_PIPELINE_OPTIONS = dict(
 NAN_CHECK_EVERY = 32        # iterations between two host reads of the running supervised loss (NaN bail-out)
 
 
-def check_dataset(dataset):
-    """Fail before any device / process-group initialisation: only `--dataset synthetic` can train in this build (the real
-    datasets need the reference's CPU data pipeline `datapipe/` -- scikit-image, OpenCV, the image archives -- which is outside
-    the B200 hot path, SURVEY.md 8 'out of scope')."""
-    if dataset != 'synthetic':
-        import click
+def check_dataset(dataset, u8_supported=False):
+    """Fail before any device / process-group initialisation: `--dataset synthetic` (seeded tensors) and, where the entry point
+    supports it, `--dataset synthetic_u8` (seeded uint8 images through the device input pipeline) can train in this build; the real
+    data sets need the reference's image archives and decoders, which are outside the B200 hot path (SURVEY.md 8 'out of scope')."""
+    import click
+    if dataset == 'synthetic_u8' and not u8_supported:
+        raise click.UsageError("--dataset 'synthetic_u8' is wired into train_seg_semisup_mask_mt.py only; use --dataset synthetic here.")
+    if dataset not in ('synthetic', 'synthetic_u8'):
         raise click.UsageError(
             "--dataset {!r} is not available in the B200 build: the reference's CPU data pipeline (datapipe/, real image archives) "
-            "is not part of the hot path.  Use --dataset synthetic (seeded tensors with the DataLoader's tensor contract); the "
+            "is not part of the hot path.  Use --dataset synthetic (seeded tensors with the DataLoader's tensor contract) or "
+            "--dataset synthetic_u8 (seeded uint8 images through the device input pipeline, honours the aug_* options); the "
             "reference CLI default 'pascal_aug' has to be overridden explicitly.".format(dataset))
+
+
+# data-pipeline options that `--dataset synthetic_u8` consumes (split + every augmentation option of the mask_mt script)
+U8_USED_OPTIONS = ('n_sup', 'n_unsup', 'split_seed', 'aug_hflip', 'aug_vflip', 'aug_hvflip', 'aug_scale_hung', 'aug_max_scale',
+                   'aug_scale_non_uniform', 'aug_rot_mag', 'aug_colour_brightness', 'aug_colour_contrast', 'aug_colour_saturation',
+                   'aug_colour_hue', 'aug_colour_prob', 'aug_colour_greyscale_prob')
 
 
 def ignored_options(settings, used=()):
@@ -47,12 +56,15 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
                  sgd_momentum, sgd_nesterov, sgd_weight_decay, learning_rate, lr_sched, lr_step_epochs, lr_step_gamma,
                  lr_poly_power, teacher_alpha, bin_fill_holes, crop_size, cons_loss_fn, cons_weight, conf_thresh,
                  conf_per_pixel, rampup, unsup_batch_ratio, num_epochs, iters_per_epoch, batch_size, save_model,
-                 no_pretrained, ddp, synthetic_classes, step_options=None, used_options=()):
+                 no_pretrained, ddp, synthetic_classes, step_options=None, used_options=(), u8_unsup=None):
     """`make_unsup(batch_size, h, w, seed, device)` -> one unsupervised batch dict for MeanTeacherStep.step (CutMix / CutOut
     box parameters, ICT mix factors, augmentation maps or the VAT marker included); `step_options`: extra keyword arguments of
     MeanTeacherStep (VAT radius / direction network); `used_options`: data-pipeline options the calling script does consume
-    on synthetic data (e.g. the aug script's rotation / scale magnitudes)."""
-    check_dataset(dataset)
+    on synthetic data (e.g. the aug script's rotation / scale magnitudes); `u8_unsup(batches, n, h, w, seed, device)`: builds the
+    unsupervised batch dict from `DeviceTrainPipeline.unsup_batch` outputs (`--dataset synthetic_u8`, one per unsupervised loader)."""
+    check_dataset(dataset, u8_supported=u8_unsup is not None)
+    if dataset == 'synthetic_u8':
+        used_options = tuple(used_options) + U8_USED_OPTIONS
     import numpy as np
     import torch
     from architectures import network_architectures
@@ -134,6 +146,26 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
 
     h, w = crop
     iter_i = 0
+    source = pipe = None
+    if dataset == 'synthetic_u8':
+        # the reference's train-time data path behind the decoder: semi-supervised split, two endless random samplers, the
+        # transform lists of :147-179 on the device (crop / scale / rotate, flips, colour jitter, normalise)
+        from . import input_pipeline
+        source = synthetic.U8ImageSource(max(4 * batch_size, 32), (h, w), n_classes, 4321 + rank, torch_device,
+                                         n_sup=settings['n_sup'], n_unsup=settings['n_unsup'], split_seed=settings['split_seed'])
+        pipe = input_pipeline.DeviceTrainPipeline(
+            (h, w), student_net.MEAN, student_net.STD, settings['aug_hflip'], settings['aug_vflip'], settings['aug_hvflip'],
+            settings['aug_scale_hung'], settings['aug_max_scale'], settings['aug_scale_non_uniform'], settings['aug_rot_mag'],
+            settings.get('aug_strong_colour', False), settings['aug_colour_brightness'], settings['aug_colour_contrast'],
+            settings['aug_colour_saturation'], settings['aug_colour_hue'], settings['aug_colour_prob'],
+            settings['aug_colour_greyscale_prob'], rng=np.random.RandomState(1000 + rank), flip_rng=np.random.RandomState(2000 + rank))
+        sample_gen = torch.Generator().manual_seed(3000 + rank)
+        sup_iter = source.sampler(source.sup_ndx, batch_size, sample_gen)
+        unsup_iter = source.sampler(source.unsup_ndx, batch_size, sample_gen)
+        if rank == 0:
+            print('synthetic_u8: {} images, {} supervised / {} unsupervised; {} geometric stage{}{}'.format(
+                len(source), len(source.sup_ndx), len(source.unsup_ndx), pipe.kind, ', flips' if pipe.any_flip else '',
+                ', strong colour (paired)' if pipe.unsup_paired else ''))
     print('Training...')
     for epoch_i in range(num_epochs):
         if lr_epoch_scheduler is not None:
@@ -156,11 +188,20 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
             if lr_iter_scheduler is not None:
                 lr_iter_scheduler.step(iter_i)
             seed = (iter_i * world + rank) * 7
-            sup = synthetic.make_sup_batch(batch_size, h, w, n_classes, seed, device=torch_device)
             unsup = []
-            if cons_weight > 0.0:
-                for r in range(unsup_batch_ratio):
-                    unsup.append(make_unsup(batch_size, h, w, seed + 1 + r, torch_device))
+            if source is not None:
+                b = pipe.sup_batch(source.sup(next(sup_iter)))
+                sup = (b['image'], b['labels'])
+                if cons_weight > 0.0:
+                    for r in range(unsup_batch_ratio):
+                        # one batch per unsupervised loader (:205-213: two loaders over the same sampler in mix mode)
+                        batches = [pipe.unsup_batch(source.unsup(next(unsup_iter))) for _ in range(2 if mask_mix else 1)]
+                        unsup.append(u8_unsup(batches, batch_size, h, w, seed + 1 + r, torch_device))
+            else:
+                sup = synthetic.make_sup_batch(batch_size, h, w, n_classes, seed, device=torch_device)
+                if cons_weight > 0.0:
+                    for r in range(unsup_batch_ratio):
+                        unsup.append(make_unsup(batch_size, h, w, seed + 1 + r, torch_device))
             out = trainer.step(sup, unsup, ramp_val=ramp_val)
             sup_acc += out['sup_loss']
             if out['cons_loss'] is not None:

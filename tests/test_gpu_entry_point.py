@@ -23,6 +23,15 @@ CASES = {
                                     '--mask_prop_range', '0:1', '--opt_type', 'sgd', '--sgd_nesterov', '--rampup', '3',
                                     '--unsup_batch_ratio', '2', '--cons_loss_fn', 'logits_var', '--aug_strong_colour'],
     'supervised_only': ['--arch', 'resnet101_deeplab_imagenet', '--cons_weight', '0.0', '--lr_sched', 'cosine'],
+    # `--dataset synthetic_u8` (the later --dataset wins): uint8 images of assorted sizes through the device input pipeline with
+    # the option sets of the reference's recipes (run_pascal_aug_experiments.sh / run_cityscapes_experiments.sh / run_isic2017_...)
+    'u8_pascal_recipe_hung_colour': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplab_imagenet', '--aug_hflip',
+                                     '--aug_scale_hung', '--aug_strong_colour', '--n_sup', '6'],
+    'u8_cityscapes_recipe_dl3plus': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes',
+                                     '19', '--aug_hflip', '--aug_strong_colour', '--crop_size', '64,96'],
+    'u8_isic_recipe_rot_scale_cutout': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplab_imagenet', '--aug_hflip', '--aug_vflip',
+                                        '--aug_hvflip', '--aug_max_scale', '1.1', '--aug_rot_mag', '45.0', '--mask_mode', 'zero',
+                                        '--mask_prop_range', '0:1'],
 }
 ICT_CASES = {
     'ict_mean_teacher_dl2': ['--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21', '--ict_alpha', '0.4'],

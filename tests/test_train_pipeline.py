@@ -105,3 +105,38 @@ def test_device_train_pipeline_matches_the_reference_composition(name):
             else:
                 assert np.array_equal(out['image'].cpu().numpy(), gold[key + '.image'])
                 assert np.array_equal(out['mask'].cpu().numpy(), gold[key + '.mask'])
+
+
+def test_u8_image_source_split_and_samplers():
+    """`--dataset synthetic_u8`: decoded-image stand-ins in the reference's sample format, the seeded semi-supervised split and the
+    endless random samplers (RepeatSampler(SubsetRandomSampler))."""
+    from cutmix_semisup_seg_b200.synthetic import U8ImageSource
+    src = U8ImageSource(40, (32, 48), 21, seed=1, device='cpu', n_sup=10, n_unsup=-1, split_seed=12345)
+    assert len(src) == 40 and len(src.sup_ndx) == 10 and sorted(src.unsup_ndx.tolist()) == list(range(40))
+    assert np.array_equal(src.sup_ndx, np.random.RandomState(12345).permutation(40)[:10])
+    sizes = [tuple(s['image_arr'].shape) for s in src.samples]
+    assert all(sh[2] == 3 for sh in sizes) and any(sh[0] < 32 or sh[1] < 48 for sh in sizes) and any(sh[0] > 32 and sh[1] > 48 for sh in sizes)
+    s0 = src.samples[0]
+    assert s0['image_arr'].dtype == torch.uint8 and s0['labels_arr'].shape == s0['image_arr'].shape[:2]
+    assert int(s0['labels_arr'][0, 0]) == 255 and int(s0['labels_arr'][-1, -1]) < 21 and int(s0['mask_arr'].min()) == 255
+    g = torch.Generator().manual_seed(0)
+    it = src.sampler(src.sup_ndx, 4, g)
+    seen = [next(it) for _ in range(5)]                       # 20 draws = two passes over the 10 supervised samples
+    flat = [i for b in seen for i in b]
+    assert all(len(b) == 4 for b in seen) and set(flat) == set(src.sup_ndx.tolist())
+    assert sorted(flat[:10]) == sorted(src.sup_ndx.tolist()) and sorted(flat[10:]) == sorted(src.sup_ndx.tolist())
+    assert set(src.sup(seen[0])[0]) == {'image_arr', 'labels_arr'} and set(src.unsup(seen[0])[0]) == {'image_arr', 'mask_arr'}
+    # the whole pipeline's host side runs on these samples (parameters only; the kernels need the GPU)
+    pipe = make_pipeline(PR.CASES['pascal'])
+    p = pipe._draw(src.sup(seen[0])[0])
+    assert p['mode'] == 0 and len(p['flips']) == 3
+
+
+def test_synthetic_u8_is_refused_by_entry_points_that_do_not_wire_it():
+    import click
+    from cutmix_semisup_seg_b200 import train_loop
+    with pytest.raises(click.UsageError, match='train_seg_semisup_mask_mt.py only'):
+        train_loop.check_dataset('synthetic_u8', u8_supported=False)
+    train_loop.check_dataset('synthetic_u8', u8_supported=True)
+    with pytest.raises(click.UsageError, match='synthetic_u8'):
+        train_loop.check_dataset('pascal_aug', u8_supported=True)

@@ -4,9 +4,11 @@ kernels (cutmix_semisup_seg_b200.step.MeanTeacherStep; the outer loop is cutmix_
 
 The click surface (option names and defaults, reference lines 581-650) and the job function signature are kept.
 Differences, all forced by the offline / GPU-native setting:
-  * `--dataset synthetic` (new choice) trains on synthetic tensors with the DataLoader's tensor contract; the real
-    datasets need the reference's CPU data pipeline (`datapipe`, out of scope of the hot path): if that package is
-    importable it is used unchanged, otherwise a clear error is raised;
+  * `--dataset synthetic` (new choice) trains on synthetic tensors with the DataLoader's tensor contract;
+    `--dataset synthetic_u8` (new choice) trains on seeded uint8 images of assorted sizes that go through the reference's
+    train-time transform lists (:147-179: crop / scale / rotation, flips, strong colour on the student's view, normalise)
+    ON THE DEVICE (cutmix_semisup_seg_b200.input_pipeline.DeviceTrainPipeline), honouring the split and aug_* options;
+    the real datasets need the reference's image archives and decoders (out of scope of the hot path): a usage error says so;
   * `--arch` networks are built with `pretrained` only if the weights are cached locally (`--no_pretrained`);
   * losses / confidence rate are kept on the device and read once per epoch (the reference synchronises three
     times per iteration, lines 413, 461, 469); the NaN bail-out is checked at the same point;
@@ -56,8 +58,28 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
         return synthetic.make_unsup_batch(n, h, w, seed, mask_generator, mask_mix=mask_mix, paired=aug_strong_colour,
                                           device=device)
 
+    def u8_unsup(batches, n, h, w, seed, device):
+        """Unsupervised batch dict from the device pipeline's output (`--dataset synthetic_u8`): with `unsup_paired` the teacher sees
+        `sample0` (weak) and the student `sample1` (colour-jittered), reference :313-323; box parameters as for synthetic tensors."""
+        import numpy as np
+        import torch
+
+        def views(b):
+            if 'sample0' in b:
+                return b['sample0']['image'], b['sample1']['image'], b['sample0']['mask']
+            return b['image'], b['image'], b['mask']
+        out = {}
+        if mask_mix:
+            out['ux0_tea'], out['ux0_stu'], out['um0'] = views(batches[0])
+            out['ux1_tea'], out['ux1_stu'], out['um1'] = views(batches[1])
+        else:
+            out['ux_tea'], out['ux_stu'], out['um'] = views(batches[0])
+        boxes = mask_generator.generate_boxes(n, (h, w), rng=np.random.RandomState(12345 + seed))
+        out['mask_params'] = torch.from_numpy(boxes).to(device)
+        return out
+
     train_loop.run_training(
-        submit_config, settings, make_unsup, mask_generator, mask_mix,
+        submit_config, settings, make_unsup, mask_generator, mask_mix, u8_unsup=u8_unsup,
         dataset=dataset, model=model, arch=arch, freeze_bn=freeze_bn, opt_type=opt_type, sgd_momentum=sgd_momentum,
         sgd_nesterov=sgd_nesterov, sgd_weight_decay=sgd_weight_decay, learning_rate=learning_rate, lr_sched=lr_sched,
         lr_step_epochs=lr_step_epochs, lr_step_gamma=lr_step_gamma, lr_poly_power=lr_poly_power, teacher_alpha=teacher_alpha,
@@ -69,7 +91,7 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
 
 @click.command()
 @click.option('--job_desc', type=str, default='')
-@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic']),
+@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic', 'synthetic_u8']),
               default='pascal_aug')
 @click.option('--model', type=click.Choice(['mean_teacher', 'pi']), default='mean_teacher')
 @click.option('--arch', type=str, default='resnet101_deeplab_imagenet')
