@@ -191,29 +191,44 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
     for (int e = 0; e < V; ++e) g[e] = 0.f;
     const int yo_lo = iy / 2, yo_hi = (iy + 1) / 2;   // windows with yo*2-1 <= iy <= yo*2+1
     const int xo_lo = ix / 2, xo_hi = (ix + 1) / 2;
-    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
-      if (yo >= oh) continue;
-      const int r = iy - (yo * 2 - 1);
-      if (r < 0 || r > 2) continue;
-      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
-        if (xo >= ow) continue;
-        const int s = ix - (xo * 2 - 1);
-        if (s < 0 || s > 2) continue;
-        const int64_t o = (((int64_t)img * oh + yo) * ow + xo) * c + ch;
-        const uint32_t want = (uint32_t)(r * 3 + s);
-        if (V == 4) {
-          const uint32_t k = __ldg(reinterpret_cast<const uint32_t*>(idx + o));
-          if (((k & 255u) == want) | (((k >> 8) & 255u) == want) | (((k >> 16) & 255u) == want) | ((k >> 24) == want)) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(dy + o));
-            if ((k & 255u) == want) g[0] += q.x;
-            if (((k >> 8) & 255u) == want) g[1] += q.y;
-            if (((k >> 16) & 255u) == want) g[2] += q.z;
-            if ((k >> 24) == want) g[3] += q.w;
-          }
-        } else {
-          if (idx[o] == want) g[0] += __ldg(dy + o);
+    // up to 4 windows (visited in the order yo, xo: the summation order): all argmax words are requested first, then all matching
+    // gradients -- two rounds of independent loads instead of four dependent index -> gradient chains (the serial form ran at
+    // 1.4 TB/s, latency bound)
+    int64_t off[4]; uint32_t want[4]; bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yo = (k >> 1) ? yo_hi : yo_lo, xo = (k & 1) ? xo_hi : xo_lo;
+      const int r = iy - (yo * 2 - 1), s = ix - (xo * 2 - 1);
+      ok[k] = yo < oh && xo < ow && r >= 0 && r <= 2 && s >= 0 && s <= 2 && !((k >> 1) && yo_hi == yo_lo) && !((k & 1) && xo_hi == xo_lo);
+      off[k] = (((int64_t)img * oh + yo) * ow + xo) * c + ch;
+      want[k] = (uint32_t)(r * 3 + s);
+    }
+    if (V == 4) {
+      uint32_t kw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) kw[k] = ok[k] ? __ldg(reinterpret_cast<const uint32_t*>(idx + off[k])) : 0xffffffffu;
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w_ = want[k];
+        const bool any = ok[k] && (((kw[k] & 255u) == w_) | (((kw[k] >> 8) & 255u) == w_) | (((kw[k] >> 16) & 255u) == w_) | ((kw[k] >> 24) == w_));
+        ok[k] = any;
+        q[k] = any ? __ldg(reinterpret_cast<const float4*>(dy + off[k])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ok[k]) {
+          const uint32_t w_ = want[k];
+          if ((kw[k] & 255u) == w_) g[0] += q[k].x;
+          if (((kw[k] >> 8) & 255u) == w_) g[1] += q[k].y;
+          if (((kw[k] >> 16) & 255u) == w_) g[2] += q[k].z;
+          if ((kw[k] >> 24) == w_) g[3] += q[k].w;
         }
       }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k] && idx[off[k]] == want[k]) g[0] += __ldg(dy + off[k]);
     }
     if (V == 4) *reinterpret_cast<float4*>(dx + (int64_t)i * 4) = make_float4(g[0], g[1], g[2], g[3]);
     else dx[i] = g[0];
@@ -499,31 +514,46 @@ __global__ void __launch_bounds__(256) bilinear_bwd_tab_kernel(const float* __re
 // pass finishes dX[n,yi,xi,c] = gs * sum_yo wy * tmp[n,c,yo,xi].  Same grouping and order of the sums as the
 // gather kernel above (rows of x-sums, then the y-sum), i.e. bit-identical results, with ~1.6x the bytes of dY moved
 // instead of every input pixel re-reading an 8 x 8 window per channel.
+// The run of outputs touching input column xi and its weights depend on xi only: they are worked out ONCE per block into shared
+// memory (first output xlo[xi], count nx[xi], weights w[j][xi] -- the very floats tab_weight() returns, so the sums below are
+// bit-identical to the per-element form), and the row loop is 8 predicated loads + FMAs per element instead of two trimming loops
+// and eight table evaluations (the per-element form ran at 0.64 TB/s, instruction bound; profiles/r02_v11_device_timeline_*).
 __global__ void __launch_bounds__(256) bilinear_bwd_h_kernel(const float* __restrict__ dy, float* __restrict__ tmp, int64_t planes_rows,
                                                              int iw, int ow, int align) {
   extern __shared__ LinTab tab[];
+  int* s_xlo = reinterpret_cast<int*>(tab + ow);
+  int* s_nx = s_xlo + iw;
+  float* s_w = reinterpret_cast<float*>(s_nx + iw);          // [8][iw]
   const float sw = lin_scale(iw, ow, align);
   for (int o = threadIdx.x; o < ow; o += blockDim.x) {
     const LinCoef k = lin_coef(o, iw, sw, align);
     tab[o].i0 = k.i0; tab[o].i1 = k.i1; tab[o].l1 = k.l1;
   }
   __syncthreads();
-  const int64_t total = planes_rows * iw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int xi = (int)(i % iw); const int64_t pr = i / iw;
+  for (int xi = threadIdx.x; xi < iw; xi += blockDim.x) {
     int xlo, xhi; bool hit;
     out_range(xi, iw, ow, sw, align, &xlo, &xhi);
     while (xlo <= xhi) { tab_weight(tab[xlo], xi, &hit); if (hit) break; ++xlo; }
     while (xhi >= xlo) { tab_weight(tab[xhi], xi, &hit); if (hit) break; --xhi; }
+    const int nx = xhi - xlo + 1;
+    s_xlo[xi] = xlo; s_nx[xi] = nx;
+#pragma unroll
+    for (int jx = 0; jx < 8; ++jx) s_w[jx * iw + xi] = (nx <= 8 && jx < nx) ? tab_weight(tab[xlo + jx], xi, &hit) : 0.f;
+  }
+  __syncthreads();
+  const int64_t total = planes_rows * iw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xi = (int)(i % iw); const int64_t pr = i / iw;
+    const int xlo = s_xlo[xi], nx = s_nx[xi];
     const float* rowp = dy + pr * ow;
     float rowacc = 0.f;
-    if (xhi - xlo + 1 <= 8) {
-      const int nx = xhi - xlo + 1;
+    if (nx <= 8) {
 #pragma unroll
       for (int jx = 0; jx < 8; ++jx)
-        if (jx < nx) rowacc += tab_weight(tab[xlo + jx], xi, &hit) * __ldg(rowp + xlo + jx);
+        if (jx < nx) rowacc += s_w[jx * iw + xi] * __ldg(rowp + xlo + jx);
     } else {
-      for (int xo = xlo; xo <= xhi; ++xo) {
+      bool hit;
+      for (int xo = xlo; xo < xlo + nx; ++xo) {
         const float wx = tab_weight(tab[xo], xi, &hit);
         if (hit) rowacc += wx * __ldg(rowp + xo);
       }
@@ -577,10 +607,12 @@ extern "C" int b2_bilinear_bwd_nchw(const float* dy, float* dx, float* workspace
                                     int align_corners, const float* scale_dev, float scale_host, int accumulate, void* stream) {
   B2_REQUIRE(dy && dx && workspace && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_bwd_nchw: bad args");
   B2_REQUIRE(oh <= BIL_MAX_TAB && ow <= BIL_MAX_TAB, "b2_bilinear_bwd_nchw: output larger than %d", BIL_MAX_TAB);
+  B2_REQUIRE((size_t)ow * sizeof(LinTab) + (size_t)iw * 10 * sizeof(int) <= 48 * 1024,
+             "b2_bilinear_bwd_nchw: tables of %d output / %d input columns exceed 48 KB (use b2_bilinear_bwd)", ow, iw);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t planes_rows = (int64_t)n * c * oh;
   int64_t b1 = ceil_div64(planes_rows * iw, 256); if (b1 > 148 * 32) b1 = 148 * 32;
-  bilinear_bwd_h_kernel<<<(unsigned)b1, 256, (size_t)ow * sizeof(LinTab), s>>>(dy, workspace, planes_rows, iw, ow, align_corners);
+  bilinear_bwd_h_kernel<<<(unsigned)b1, 256, (size_t)ow * sizeof(LinTab) + (size_t)iw * 10 * sizeof(int), s>>>(dy, workspace, planes_rows, iw, ow, align_corners);
   B2_LAUNCH_CHECK("bilinear_bwd_h_kernel");
   int64_t b2 = ceil_div64((int64_t)n * ih * iw, 128); if (b2 > 148 * 16) b2 = 148 * 16;
   bilinear_bwd_v_kernel<<<(unsigned)b2, 128, (size_t)oh * sizeof(LinTab), s>>>(workspace, dx, n, ih, iw, c, ldx, oh, align_corners, scale_dev,

@@ -277,7 +277,7 @@ class ActKernels(object):
 
     def bilinear_bwd_nchw(self, dy_nchw, dx, align_corners, scale_dev=None, scale_host=1.0, accumulate=False):
         n, c, oh, ow = dy_nchw.shape
-        if max(oh, ow) <= 3072:
+        if max(oh, ow) <= 3072 and ow * 12 + dx.w * 40 <= 48 * 1024:      # table sizes of the separable kernels (netops.cu)
             self.be.bilinear_bwd_nchw(dy_nchw, dx.ptr, dx.n, dx.h, dx.w, dx.c, dx.ld, align_corners, scale_dev=scale_dev,
                                       scale_host=scale_host, accumulate=accumulate)
         else:
