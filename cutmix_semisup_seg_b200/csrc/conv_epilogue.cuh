@@ -11,7 +11,7 @@
 //   * issues the residual and gate loads of all 8 row groups of a chunk before touching them (16 independent 16 B
 //     loads in flight per lane),
 //   * keeps the rare paths (channel count not a multiple of 4, unaligned pointers) out of line.
-// Rows are staged through a padded smem tile so that 8 consecutive lanes own 32 consecutive channels of one pixel:
+// Rows are staged through an XOR-swizzled smem tile so that 8 consecutive lanes own 32 consecutive channels of one pixel:
 // loads and stores are full 128 B segments.
 #pragma once
 #include "tc_common.cuh"
@@ -47,7 +47,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int PF_OPERAND_BYTES = 8 * 32 * 16;       // 8 row groups x 32 lanes x 16 B
 constexpr int PF_WARP_BYTES = 2 * PF_OPERAND_BYTES; // addend + gate
 
-constexpr int ROW_FLOATS = 36;                      // 32 columns + 4 pad: conflict-free 128-bit smem access
+constexpr int ROW_FLOATS = 32;                      // 128 B rows, 16 B chunk j of row r stored at chunk j ^ (r & 7): conflict-free
+                                                    // 128-bit accesses without padding (the 4 KB saved pay for a sixth operand stage)
 constexpr int WARP_BYTES = 32 * ROW_FLOATS * 4;
 constexpr int NUM_WARPS = 8;                        // two warps per TMEM lane quarter (even / odd 32-column chunks)
 constexpr int BYTES = NUM_WARPS * WARP_BYTES + NUM_WARPS * 32 * 4;  // staging tiles + per-row pixel indices
@@ -176,8 +177,11 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
   const bool fast = p.vec_ok;
   const bool acc = p.accumulate != 0;
   const int nchunks = block_n / 32;
-  const uint32_t st_w = tc::smem_u32(stg + lane * ROW_FLOATS);
-  const uint32_t st_r = tc::smem_u32(stg + sub_r * ROW_FLOATS + sub_c);
+  const uint32_t st_w = tc::smem_u32(stg + lane * ROW_FLOATS);          // this lane's row; chunk q goes to slot q ^ (lane & 7)
+  const uint32_t st_swz = (uint32_t)(lane & 7);
+  // read side: row i * 4 + sub_r, chunk lane & 7 -> slot (lane & 7) ^ (row & 7), row & 7 = (i & 1) * 4 + sub_r
+  const uint32_t st_r0 = tc::smem_u32(stg + sub_r * ROW_FLOATS) + (((uint32_t)(lane & 7) ^ (uint32_t)sub_r) << 4);
+  const uint32_t st_r1 = tc::smem_u32(stg + sub_r * ROW_FLOATS) + (((uint32_t)(lane & 7) ^ (uint32_t)(sub_r + 4)) << 4);
   if (half >= nchunks) release();       // nothing to read for this warp: still owes its arrival
 #pragma unroll 1                        // keep the body resident in the instruction cache (4 specialisations x 2 kernels)
   for (int ch = half; ch < nchunks; ch += 2) {
@@ -199,7 +203,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;     // STATS: this lane's column sums over its 8 rows
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      sts128(st_w + q * 16, r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      sts128(st_w + (((uint32_t)q ^ st_swz) << 4), r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
     __syncwarp();
     if (lane_fast) {
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), s2 = sc;
@@ -253,7 +257,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int i = b * 4 + j;
-          const float4 v = lds128(st_r + i * 4 * ROW_FLOATS * 4);
+          const float4 v = lds128(((i & 1) ? st_r1 : st_r0) + i * 4 * ROW_FLOATS * 4);
           float4 o;
           o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
           if (ADD) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
@@ -289,7 +293,7 @@ __device__ __forceinline__ void drain_tile_t(const Params& p, uint32_t taddr, in
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         if (od[i] < 0) continue;
-        slow_store(p, lds128(st_r + i * 4 * ROW_FLOATS * 4), od[i], c);
+        slow_store(p, lds128(((i & 1) ? st_r1 : st_r0) + i * 4 * ROW_FLOATS * 4), od[i], c);
       }
     }
     if (STATS) {

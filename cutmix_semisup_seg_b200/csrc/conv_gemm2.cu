@@ -27,7 +27,8 @@ constexpr int BLOCK_N = 256;
 // Two builds of the kernel: the compute-bound one keeps a 5-stage operand ring; the PF one (HBM-bound small-K layers
 // whose epilogue reads a residual addend / ReLU gate) trades two stages for the epilogue's asynchronous prefetch slots
 // (conv_epilogue.cuh).
-constexpr int STAGES_MAIN = 5;
+constexpr int STAGES_MAIN = 6;          // 6 x 32 KB + swizzled (unpadded) epilogue staging = 226.25 KB
+constexpr int STAGES_MAIN_OLD = 5;      // A/B timing (debug knob 10)
 constexpr int STAGES_PF = 3;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB
 constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;      // 16 KB: this CTA's half of the weight tile
@@ -399,6 +400,7 @@ int g_conv_pf_max_k = -1;
 // TMA epilogue of the PF build (conv_epilogue_tma.cuh): 1 = on where usable (default), 0 = register epilogue everywhere.
 // Override: environment B200SEG_TMA_EPI or b2_debug_set(8, v).
 int g_conv_tma_epi = -1;
+int g_conv_main_stages = STAGES_MAIN;   // b2_debug_set(10, 5): the 5-stage build of the compute-bound kernel (A/B timing)
 static long long* g_conv_trace = nullptr;
 extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
@@ -451,6 +453,7 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_MAIN, false)));
+    B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_MAIN_OLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_MAIN_OLD, false)));
     B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_PF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_PF, true)));
     attr_set = true;
   }
@@ -498,6 +501,8 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   if (clusters > a.num_pairs) clusters = a.num_pairs;
   if (use_pf)
     conv_gemm2_kernel<STAGES_PF, true><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+  else if (g_conv_main_stages == STAGES_MAIN_OLD)
+    conv_gemm2_kernel<STAGES_MAIN_OLD, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN_OLD, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   else
     conv_gemm2_kernel<STAGES_MAIN, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   B2_LAUNCH_CHECK("conv_gemm2_kernel");

@@ -646,6 +646,7 @@ extern int g_conv_epi_debug;
 extern int g_conv_pf_max_k;
 extern int g_conv_tap_outer;
 extern int g_conv_tma_epi;
+extern int g_conv_main_stages;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 5) g_wgrad_force_1cta = value;
   if (key == 6) g_wgrad_dbg = value;
@@ -655,6 +656,7 @@ extern "C" void b2_debug_set(int key, int value) {
   if (key == 4) g_conv_pf_max_k = value;
   if (key == 7) g_conv_tap_outer = value;
   if (key == 8) g_conv_tma_epi = value;
+  if (key == 10) g_conv_main_stages = value;
 }
 
 extern "C" size_t b2_conv_wgrad_workspace(const b2_wgrad_params* p) {

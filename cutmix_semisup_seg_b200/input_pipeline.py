@@ -85,7 +85,8 @@ class DeviceCropFlipNormalize(object):
         on = np.array([self.hflip, self.vflip, self.hvflip])
         # the entry points add the flip transform only if a flip is enabled (train_seg_semisup_mask_mt.py:163-165)
         flags = ((self.flip_rng.binomial(1, 0.5, size=(3,)) != 0) & on) if on.any() else np.zeros(3, bool)              # :480-481
-        return dict(pad_top=top, pad_left=left, padded=padded, pos=(int(pos[0]), int(pos[1])), flips=tuple(bool(f) for f in flags))
+        return dict(pad_top=top, pad_left=left, padded=padded, pos=(int(pos[0]), int(pos[1])), flips=tuple(bool(f) for f in flags),
+                    xf_cv=self._xf(pos, top, left, padded))
 
     def draw_pair(self, img_hw):
         import numpy as np
@@ -96,8 +97,19 @@ class DeviceCropFlipNormalize(object):
         pos1 = np.clip(pos1, np.array([0, 0]), extra)                                                        # :147
         on = np.array([[self.hflip, self.vflip, self.hvflip]])
         flags = ((self.flip_rng.binomial(1, 0.5, size=(2, 3)) != 0) & on) if on.any() else np.zeros((2, 3), bool)       # :503-504
-        return tuple(dict(pad_top=top, pad_left=left, padded=padded, pos=(int(p[0]), int(p[1])), flips=tuple(bool(f) for f in fl))
+        return tuple(dict(pad_top=top, pad_left=left, padded=padded, pos=(int(p[0]), int(p[1])), flips=tuple(bool(f) for f in fl),
+                          xf_cv=self._xf(p, top, left, padded))
                      for p, fl in ((pos0, flags[0]), (pos1, flags[1])))
+
+    @staticmethod
+    def _xf(pos, pad_top, pad_left, padded):
+        """The `xf_cv` entry the reference would leave in the sample for an identity input transform: translation by -pos
+        (:128-132, :150-159) after the padding's translation (:56-60, :94-97)."""
+        import numpy as np
+        parts = [_mat_translation(-np.array(pos)[None, ::-1])]
+        if padded:
+            parts.append(_mat_translation(np.array([[pad_left, pad_top]])))
+        return _mat_cat(*parts)[0]
 
     # ---- device
     @staticmethod
@@ -273,6 +285,52 @@ def _mat_cat(*x):
         a2, b2 = y[:, :, :2], b[:, :, :2]
         y = np.append(np.matmul(a2, b2), y[:, :, 2:3] + np.matmul(a2, b[:, :, 2:3]), axis=2)
     return y
+
+
+def _mat_identity(n):
+    """datapipe/affine.py:3-11."""
+    import numpy as np
+    xf = np.zeros((n, 2, 3), dtype=np.float32)
+    xf[:, 0, 0] = xf[:, 1, 1] = 1.0
+    return xf
+
+
+def _mat_inv(m):
+    """datapipe/affine.py:14-41 (inv_nx2x2 + inv_nx2x3), same numpy operations."""
+    import numpy as np
+    x = m[:, :, :2]
+    rdet = 1.0 / (x[:, 0, 0] * x[:, 1, 1] - x[:, 1, 0] * x[:, 0, 1])
+    y = np.zeros_like(x)
+    y[:, 0, 0] = x[:, 1, 1] * rdet
+    y[:, 1, 1] = x[:, 0, 0] * rdet
+    y[:, 0, 1] = -x[:, 0, 1] * rdet
+    y[:, 1, 0] = -x[:, 1, 0] * rdet
+    return np.append(y, np.matmul(y, -m[:, :, 2:3]), axis=2)
+
+
+def _mat_cv_to_torch(mtx, dst_size):
+    """datapipe/affine.py:185-232 with src_size = None: OpenCV pixel-space matrices -> F.affine_grid matrices (align_corners)."""
+    sx, sy = float(dst_size[1] - 1) / 2.0, float(dst_size[0] - 1) / 2.0
+    n = len(mtx)
+    mtx = _mat_inv(mtx)
+    torch_cv = _mat_identity(n)
+    torch_cv[:, 0, 0] = sx; torch_cv[:, 1, 1] = sy; torch_cv[:, 0, 2] = sx; torch_cv[:, 1, 2] = sy
+    cv_torch = _mat_identity(n)
+    cv_torch[:, 0, 0] = 1.0 / sx; cv_torch[:, 1, 1] = 1.0 / sy; cv_torch[:, 0, 2] = -1.0; cv_torch[:, 1, 2] = -1.0
+    return _mat_cat(cv_torch, mtx, torch_cv)
+
+
+def pair_flip_matrices(flags0, flags1, size_hw0, size_hw1, xf0, xf1):
+    """SegCVTransformRandomFlip.transform_pair's update of `xf_cv` (seg_transforms_cv.py:506-525): sizes are those of the FLIPPED
+    crops (the script reads them after flip_image)."""
+    import numpy as np
+    fl = np.array([flags0, flags1], dtype=bool)
+    scale_xy = fl[:, :2] * -2 + 1
+    xlat_xy = fl[:, :2] * (np.array([tuple(size_hw0)[::-1], tuple(size_hw1)[::-1]]).astype(float) - 1)
+    hv = _mat_identity(2)
+    hv[fl[:, 2]] = hv[fl[:, 2], ::-1, :]
+    out = _mat_cat(hv, _mat_translation(xlat_xy), _mat_scale(scale_xy), np.stack([xf0, xf1], axis=0))
+    return out[0], out[1]
 
 
 NEAREST, LINEAR, AREA2 = 0, 1, 2
@@ -601,25 +659,37 @@ class DeviceTrainPipeline(object):
     def __init__(self, crop_size, mean, std, aug_hflip=False, aug_vflip=False, aug_hvflip=False, aug_scale_hung=False,
                  aug_max_scale=1.0, aug_scale_non_uniform=False, aug_rot_mag=0.0, aug_strong_colour=False,
                  aug_colour_brightness=0.4, aug_colour_contrast=0.4, aug_colour_saturation=0.4, aug_colour_hue=0.1,
-                 aug_colour_prob=0.8, aug_colour_greyscale_prob=0.2, rng=None, flip_rng=None):
+                 aug_colour_prob=0.8, aug_colour_greyscale_prob=0.2, rng=None, flip_rng=None, script='mask_mt', aug_offset_range=16,
+                 aug_free_scale_rot=False):
+        """script='mask_mt': the lists above.  script='aug_mt': those of train_seg_semisup_aug_mt.py:126-163 -- the geometric
+        transforms get `crop_offset = (aug_offset_range, aug_offset_range)` and `constrain_rot_scale = not aug_free_scale_rot`, and the
+        unsupervised list is `[SegTransformToPair()] + train_transforms` (+ colour jitter on the second member): every unsupervised
+        sample becomes a PAIR of differently augmented crops whose relative transform `xf0_to_1` (seg_data.SegCollate._compute_xf_0_to_1)
+        drives the augmentation-consistency loss (`unsup_pair_batch`)."""
         if crop_size is None:
             raise NotImplementedError('the device pipeline needs a crop_size (fixed-size batches)')
+        if script not in ('mask_mt', 'aug_mt'):
+            raise ValueError('unknown script {!r}'.format(script))
+        self.script = script
+        offs = (aug_offset_range, aug_offset_range) if script == 'aug_mt' else (0, 0)
         any_flip = aug_hflip or aug_vflip or aug_hvflip
         common = dict(hflip=aug_hflip, vflip=aug_vflip, hvflip=aug_hvflip, mean=mean, std=std, flip_rng=flip_rng)
-        if aug_scale_hung:                                                                                   # :151-152
-            self.geom = DeviceRandomCropScaleHung(crop_size, (0, 0), uniform_scale=not aug_scale_non_uniform, rng=rng, **common)
+        if aug_scale_hung:                                                                                   # :151-152 / aug :130-131
+            self.geom = DeviceRandomCropScaleHung(crop_size, offs, uniform_scale=not aug_scale_non_uniform, rng=rng, **common)
             self.kind = 'hung'
-        elif aug_max_scale != 1.0 or aug_rot_mag != 0.0:                                                     # :153-155
-            self.geom = DeviceRandomCropRotateScale(crop_size, (0, 0), rot_mag=aug_rot_mag, max_scale=aug_max_scale,
-                                                    uniform_scale=not aug_scale_non_uniform, constrain_rot_scale=True, rng=rng, **common)
+        elif aug_max_scale != 1.0 or aug_rot_mag != 0.0:                                                     # :153-155 / aug :132-135
+            self.geom = DeviceRandomCropRotateScale(crop_size, offs, rot_mag=aug_rot_mag, max_scale=aug_max_scale,
+                                                    uniform_scale=not aug_scale_non_uniform,
+                                                    constrain_rot_scale=(not aug_free_scale_rot) if script == 'aug_mt' else True,
+                                                    rng=rng, **common)
             self.kind = 'rot'
-        else:                                                                                                # :156-157
-            self.geom = DeviceCropFlipNormalize(crop_size, (0, 0), crop_rng=rng, **common)
+        else:                                                                                                # :156-157 / aug :136-137
+            self.geom = DeviceCropFlipNormalize(crop_size, offs, crop_rng=rng, **common)
             self.kind = 'crop'
         self.any_flip = bool(any_flip)
         self.colour = DeviceColourJitter(aug_colour_brightness, aug_colour_contrast, aug_colour_saturation, aug_colour_hue,
                                          aug_colour_prob, aug_colour_greyscale_prob) if aug_strong_colour else None
-        self.unsup_paired = bool(aug_strong_colour)                                                          # :170-179
+        self.unsup_paired = bool(aug_strong_colour) or script == 'aug_mt'                                    # :170-179
         self.mean, self.std = self.geom.mean, self.geom.std
 
     def _draw(self, sample):
@@ -638,9 +708,50 @@ class DeviceTrainPipeline(object):
         be = self.geom.be
         return dict(image=be.normalize_to_tensor(rgba, self.mean, self.std), labels=labels)
 
+    def draw_pairs(self, samples):
+        """Host side of `unsup_pair_batch`: per sample the two parameter dicts of the geometric transform's `transform_pair` with the
+        flips' matrices folded into `xf_cv`, plus (N,2,3) `xf0_to_1_cv` / float32 `xf0_to_1` (SegCollate._compute_xf_0_to_1)."""
+        import numpy as np
+        h, w = (int(v) for v in self.geom.crop_size)
+        params, xf01_cv = [], []
+        for s in samples:
+            hw = s['image_arr'].shape[:2]
+            p0, p1 = self.geom.draw_pair(hw, s.get('labels_arr') is not None) if self.kind == 'rot' else self.geom.draw_pair(hw)
+            if self.any_flip:
+                # sizes of the flipped crops: a transposition swaps them (the crop is square when hvflip is enabled)
+                sz0 = (w, h) if p0['flips'][2] else (h, w)
+                sz1 = (w, h) if p1['flips'][2] else (h, w)
+                x0, x1 = pair_flip_matrices(p0['flips'], p1['flips'], sz0, sz1, p0['xf_cv'], p1['xf_cv'])
+                p0, p1 = dict(p0, xf_cv=x0), dict(p1, xf_cv=x1)
+            params += [p0, p1]
+            xf01_cv.append(_mat_cat(p1['xf_cv'][None], _mat_inv(p0['xf_cv'][None]))[0])
+        xf01_cv = np.stack(xf01_cv, axis=0)
+        xf01 = _mat_cv_to_torch(xf01_cv, (h, w)).astype(np.float32)
+        return params, xf01_cv, xf01
+
+    def unsup_pair_batch(self, samples):
+        """script='aug_mt': -> dict(sample0=dict(image, mask), sample1=dict(image, mask), xf0_to_1 fp32 (N,2,3) device tensor,
+        xf0_to_1_cv numpy): the tensors SegCollate stacks for train_seg_semisup_aug_mt.py:291-300 (`batch_ux0`, `batch_um0`,
+        `batch_ux1`, `batch_um1`, `batch_ufx0_to_1`).  Colour jitter (aug_strong_colour) acts on the second member only."""
+        assert self.script == 'aug_mt'
+        use = [{k: v for k, v in s.items() if k != 'labels_arr'} for s in samples]
+        params, xf01_cv, xf01 = self.draw_pairs(use)
+        both = [s for s in use for _ in (0, 1)]
+        rgba, _, mask = self.geom.crops_u8(both, params)
+        be = self.geom.be
+        rgba0, rgba1 = rgba[0::2].contiguous(), rgba[1::2].contiguous()
+        if self.colour is not None:
+            self.colour(rgba1, [self.colour.draw() for _ in use])
+        dev = rgba.device
+        return dict(sample0=dict(image=be.normalize_to_tensor(rgba0, self.mean, self.std), mask=mask[0::2].contiguous()),
+                    sample1=dict(image=be.normalize_to_tensor(rgba1, self.mean, self.std), mask=mask[1::2].contiguous()),
+                    xf0_to_1=torch.from_numpy(xf01).to(dev), xf0_to_1_cv=xf01_cv)
+
     def unsup_batch(self, samples):
         """-> dict(image, mask), or with aug_strong_colour dict(sample0=dict(image, mask), sample1=dict(image, mask)) where sample1 is
         the colour-jittered copy of the same crop (SegTransformToPair, then SegCVTransformTVT on the second member only)."""
+        if self.script == 'aug_mt':
+            return self.unsup_pair_batch(samples)
         rgba, _, mask = self._crops([{k: v for k, v in s.items() if k != 'labels_arr'} for s in samples])
         be = self.geom.be
         image0 = be.normalize_to_tensor(rgba, self.mean, self.std)

@@ -26,7 +26,8 @@ def check_dataset(dataset, u8_supported=False):
     data sets need the reference's image archives and decoders, which are outside the B200 hot path (SURVEY.md 8 'out of scope')."""
     import click
     if dataset == 'synthetic_u8' and not u8_supported:
-        raise click.UsageError("--dataset 'synthetic_u8' is wired into train_seg_semisup_mask_mt.py only; use --dataset synthetic here.")
+        raise click.UsageError("--dataset 'synthetic_u8' is wired into train_seg_semisup_mask_mt.py / train_seg_semisup_aug_mt.py only; "
+                               "use --dataset synthetic here.")
     if dataset not in ('synthetic', 'synthetic_u8'):
         raise click.UsageError(
             "--dataset {!r} is not available in the B200 build: the reference's CPU data pipeline (datapipe/, real image archives) "
@@ -36,7 +37,7 @@ def check_dataset(dataset, u8_supported=False):
 
 
 # data-pipeline options that `--dataset synthetic_u8` consumes (split + every augmentation option of the mask_mt script)
-U8_USED_OPTIONS = ('n_sup', 'n_unsup', 'split_seed', 'aug_hflip', 'aug_vflip', 'aug_hvflip', 'aug_scale_hung', 'aug_max_scale',
+U8_USED_OPTIONS = ('n_sup', 'n_unsup', 'split_seed', 'aug_offset_range', 'aug_hflip', 'aug_vflip', 'aug_hvflip', 'aug_scale_hung', 'aug_max_scale',
                    'aug_scale_non_uniform', 'aug_rot_mag', 'aug_colour_brightness', 'aug_colour_contrast', 'aug_colour_saturation',
                    'aug_colour_hue', 'aug_colour_prob', 'aug_colour_greyscale_prob')
 
@@ -56,12 +57,13 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
                  sgd_momentum, sgd_nesterov, sgd_weight_decay, learning_rate, lr_sched, lr_step_epochs, lr_step_gamma,
                  lr_poly_power, teacher_alpha, bin_fill_holes, crop_size, cons_loss_fn, cons_weight, conf_thresh,
                  conf_per_pixel, rampup, unsup_batch_ratio, num_epochs, iters_per_epoch, batch_size, save_model,
-                 no_pretrained, ddp, synthetic_classes, step_options=None, used_options=(), u8_unsup=None):
+                 no_pretrained, ddp, synthetic_classes, step_options=None, used_options=(), u8_unsup=None, pipeline_options=None, u8_loaders=None):
     """`make_unsup(batch_size, h, w, seed, device)` -> one unsupervised batch dict for MeanTeacherStep.step (CutMix / CutOut
     box parameters, ICT mix factors, augmentation maps or the VAT marker included); `step_options`: extra keyword arguments of
     MeanTeacherStep (VAT radius / direction network); `used_options`: data-pipeline options the calling script does consume
     on synthetic data (e.g. the aug script's rotation / scale magnitudes); `u8_unsup(batches, n, h, w, seed, device)`: builds the
-    unsupervised batch dict from `DeviceTrainPipeline.unsup_batch` outputs (`--dataset synthetic_u8`, one per unsupervised loader)."""
+    unsupervised batch dict from `DeviceTrainPipeline.unsup_batch` outputs (`--dataset synthetic_u8`, one per unsupervised loader:
+    `u8_loaders`, default two in mix mode); `pipeline_options`: extra DeviceTrainPipeline arguments (the aug script's pair mode)."""
     check_dataset(dataset, u8_supported=u8_unsup is not None)
     if dataset == 'synthetic_u8':
         used_options = tuple(used_options) + U8_USED_OPTIONS
@@ -158,7 +160,8 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
             settings['aug_scale_hung'], settings['aug_max_scale'], settings['aug_scale_non_uniform'], settings['aug_rot_mag'],
             settings.get('aug_strong_colour', False), settings['aug_colour_brightness'], settings['aug_colour_contrast'],
             settings['aug_colour_saturation'], settings['aug_colour_hue'], settings['aug_colour_prob'],
-            settings['aug_colour_greyscale_prob'], rng=np.random.RandomState(1000 + rank), flip_rng=np.random.RandomState(2000 + rank))
+            settings['aug_colour_greyscale_prob'], rng=np.random.RandomState(1000 + rank), flip_rng=np.random.RandomState(2000 + rank),
+            **(pipeline_options or {}))
         sample_gen = torch.Generator().manual_seed(3000 + rank)
         sup_iter = source.sampler(source.sup_ndx, batch_size, sample_gen)
         unsup_iter = source.sampler(source.unsup_ndx, batch_size, sample_gen)
@@ -195,7 +198,7 @@ def run_training(submit_config, settings, make_unsup, mask_generator, mask_mix, 
                 if cons_weight > 0.0:
                     for r in range(unsup_batch_ratio):
                         # one batch per unsupervised loader (:205-213: two loaders over the same sampler in mix mode)
-                        batches = [pipe.unsup_batch(source.unsup(next(unsup_iter))) for _ in range(2 if mask_mix else 1)]
+                        batches = [pipe.unsup_batch(source.unsup(next(unsup_iter))) for _ in range(u8_loaders or (2 if mask_mix else 1))]
                         unsup.append(u8_unsup(batches, batch_size, h, w, seed + 1 + r, torch_device))
             else:
                 sup = synthetic.make_sup_batch(batch_size, h, w, n_classes, seed, device=torch_device)

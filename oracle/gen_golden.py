@@ -636,6 +636,64 @@ def gen_train_pipeline():
     np.savez_compressed(os.path.join(OUT, 'train_pipeline.npz'), **out)
 
 
+def gen_aug_pipeline():
+    """SURVEY.md 8f rows 3-4, BASELINE config 4's data side: the unsupervised transform list of train_seg_semisup_aug_mt.py:126-163
+    (`[SegTransformToPair()] + train_transforms` [+ SegCVTransformTVT] + NormalizeToTensor) built from the reference's OWN classes with
+    seeded generators, applied to the unsupervised samples of tests/pipeline_recipe.py (each entering with the identity `xf_cv` the
+    data set accessor provides, seg_data.py:95-100), then seg_data.SegCollate._compute_xf_0_to_1 on every pair.
+    -> tests/golden/aug_pipeline.npz"""
+    import types
+    import torchvision.transforms as tvt
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    import pipeline_recipe as PR
+    fake = types.ModuleType('skimage')
+    fake.img_as_float = lambda a: np.multiply(a, 1. / 255, dtype=np.float64)
+    sys.modules.setdefault('skimage', fake)
+    from datapipe import seg_transforms, seg_transforms_cv, seg_data, affine
+    assert os.path.realpath(seg_data.__file__).startswith(os.path.realpath(REF))
+    NET_MEAN, NET_STD = np.array(PR.MEAN), np.array(PR.STD)
+    out = {}
+    for name, case in PR.AUG_CASES.items():
+        o = PR.options(case)
+        crop_size, aug_offset_range, aug_free_scale_rot = case['crop_size'], case['aug_offset_range'], case['aug_free_scale_rot']
+        rng, flip_rng = np.random.RandomState(case['seed']), np.random.RandomState(case['seed'] + 1)
+        # ---- train_seg_semisup_aug_mt.py:126-163 (the script's lines; only `rng=` added to the constructors)
+        train_transforms = []
+        if o['aug_scale_hung']:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCropScaleHung(crop_size, (aug_offset_range, aug_offset_range), uniform_scale=not o['aug_scale_non_uniform'], rng=rng))
+        elif o['aug_max_scale'] != 1.0 or o['aug_rot_mag'] != 0.0:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCropRotateScale(
+                crop_size, (aug_offset_range, aug_offset_range), rot_mag=o['aug_rot_mag'], max_scale=o['aug_max_scale'],
+                uniform_scale=not o['aug_scale_non_uniform'], constrain_rot_scale=not aug_free_scale_rot, rng=rng))
+        else:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomCrop(crop_size, (aug_offset_range, aug_offset_range), rng=rng))
+        if o['aug_hflip'] or o['aug_vflip'] or o['aug_hvflip']:
+            train_transforms.append(seg_transforms_cv.SegCVTransformRandomFlip(o['aug_hflip'], o['aug_vflip'], o['aug_hvflip'], rng=flip_rng))
+        train_unsup_transforms = [seg_transforms.SegTransformToPair()] + train_transforms
+        if o['aug_strong_colour']:
+            colour_xforms = tvt.Compose([
+                tvt.RandomApply([tvt.ColorJitter(o['aug_colour_brightness'], o['aug_colour_contrast'], o['aug_colour_saturation'],
+                                                 o['aug_colour_hue'])], p=o['aug_colour_prob']),
+                tvt.RandomGrayscale(p=o['aug_colour_greyscale_prob']),
+            ])
+            train_unsup_transforms.append(seg_transforms_cv.SegCVTransformTVT(colour_xforms))
+        train_unsup_transforms.append(seg_transforms_cv.SegCVTransformNormalizeToTensor(NET_MEAN, NET_STD))
+        unsup = seg_transforms.SegTransformCompose(train_unsup_transforms)
+        # ----
+        torch.manual_seed(case['torch_seed'])
+        res = []
+        for smp in PR.make_samples(case, 'unsup'):
+            pair = unsup.apply(dict(smp, xf_cv=affine.identity_xf(1)[0]))
+            res.append(seg_data.SegCollate._compute_xf_0_to_1(pair))
+        for m in ('sample0', 'sample1'):
+            out[name + '.' + m + '.image'] = np.stack([r[m]['image'] for r in res])
+            out[name + '.' + m + '.mask'] = np.stack([r[m]['mask'] for r in res])
+        out[name + '.xf0_to_1_cv'] = np.stack([r['xf0_to_1_cv'] for r in res])
+        out[name + '.xf0_to_1'] = np.stack([r['xf0_to_1'] for r in res])
+        print(' ', name, out[name + '.sample0.image'].shape, out[name + '.xf0_to_1'].dtype, out[name + '.xf0_to_1_cv'].dtype)
+    np.savez_compressed(os.path.join(OUT, 'aug_pipeline.npz'), **out)
+
+
 def gen_toy2d():
     """BASELINE config 1: the reference's OWN job function `toy2d_train.train_toy2d` (imported unmodified from /root/reference) run
     on the cases of tests/toy2d_recipe.py with torch.manual_seed(TORCH_SEED).  The reference's `toy2d/generate_data.py` cannot be

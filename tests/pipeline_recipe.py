@@ -40,3 +40,17 @@ def make_samples(case, part):
             s['labels_arr'] = lab
         out.append(s)
     return out
+
+
+# train_seg_semisup_aug_mt.py:126-163: every unsupervised sample becomes a pair of differently augmented crops (+ xf0_to_1)
+AUG_CASES = {
+    'aug_crop': dict(crop_size=(24, 48), seed=301, torch_seed=21, aug_offset_range=8, aug_free_scale_rot=False,
+                     opts=dict(aug_hflip=True, aug_strong_colour=True)),
+    'aug_hung': dict(crop_size=(32, 32), seed=311, torch_seed=22, aug_offset_range=6, aug_free_scale_rot=False,
+                     opts=dict(aug_hflip=True, aug_vflip=True, aug_scale_hung=True)),
+    # run_isic2017_experiments.sh:18
+    'aug_isic': dict(crop_size=(28, 28), seed=321, torch_seed=23, aug_offset_range=16, aug_free_scale_rot=False,
+                     opts=dict(aug_hflip=True, aug_vflip=True, aug_hvflip=True, aug_max_scale=1.1, aug_rot_mag=45.0, aug_strong_colour=True)),
+    'aug_free': dict(crop_size=(24, 32), seed=331, torch_seed=24, aug_offset_range=4, aug_free_scale_rot=True,
+                     opts=dict(aug_hflip=True, aug_max_scale=1.3, aug_rot_mag=20.0, aug_scale_non_uniform=True)),
+}

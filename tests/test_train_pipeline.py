@@ -135,8 +135,58 @@ def test_u8_image_source_split_and_samplers():
 def test_synthetic_u8_is_refused_by_entry_points_that_do_not_wire_it():
     import click
     from cutmix_semisup_seg_b200 import train_loop
-    with pytest.raises(click.UsageError, match='train_seg_semisup_mask_mt.py only'):
+    with pytest.raises(click.UsageError, match='train_seg_semisup_mask_mt.py / train_seg_semisup_aug_mt.py only'):
         train_loop.check_dataset('synthetic_u8', u8_supported=False)
     train_loop.check_dataset('synthetic_u8', u8_supported=True)
     with pytest.raises(click.UsageError, match='synthetic_u8'):
         train_loop.check_dataset('pascal_aug', u8_supported=True)
+
+
+# ------------------------------------------------------------------------------------------ train_seg_semisup_aug_mt.py pairs
+def make_aug_pipeline(case):
+    from cutmix_semisup_seg_b200.input_pipeline import DeviceTrainPipeline
+    return DeviceTrainPipeline(case['crop_size'], PR.MEAN, PR.STD, rng=np.random.RandomState(case['seed']),
+                               flip_rng=np.random.RandomState(case['seed'] + 1), script='aug_mt',
+                               aug_offset_range=case['aug_offset_range'], aug_free_scale_rot=case['aug_free_scale_rot'], **PR.options(case))
+
+
+@pytest.mark.parametrize('name', sorted(PR.AUG_CASES))
+def test_aug_pair_draws_matrices_and_kernel_statements_match_the_reference_composition(name):
+    """script='aug_mt' (train_seg_semisup_aug_mt.py:126-163 + SegCollate._compute_xf_0_to_1): pair parameters, the flips' matrices,
+    `xf0_to_1_cv` / `xf0_to_1`, and the crops (numpy statements of the kernels) against the reference's own classes."""
+    import colour_recipe as CR
+    gold = np.load(os.path.join(HERE, 'golden', 'aug_pipeline.npz'))
+    case = PR.AUG_CASES[name]
+    pipe = make_aug_pipeline(case)
+    torch.manual_seed(case['torch_seed'])
+    samples = [{k: v for k, v in s.items() if k != 'labels_arr'} for s in PR.make_samples(case, 'unsup')]
+    params, xf01_cv, xf01 = pipe.draw_pairs(samples)
+    assert xf01.dtype == np.float32 and np.array_equal(xf01, gold[name + '.xf0_to_1'])
+    assert xf01_cv.dtype == gold[name + '.xf0_to_1_cv'].dtype and np.array_equal(xf01_cv, gold[name + '.xf0_to_1_cv'])
+    crops = crops_statement(pipe, [s for s in samples for _ in (0, 1)], params)
+    c0, c1 = crops[0::2], crops[1::2]
+    assert np.array_equal(np.stack([normalise(c[0]) for c in c0]), gold[name + '.sample0.image'])
+    if pipe.colour is not None:
+        cparams = [pipe.colour.draw() for _ in samples]
+        c1 = [(np.concatenate([CR.apply(c[0][..., :3], cp), c[0][..., 3:]], axis=2), c[1], c[2]) for c, cp in zip(c1, cparams)]
+    assert np.array_equal(np.stack([normalise(c[0]) for c in c1]), gold[name + '.sample1.image'])
+    assert np.array_equal(np.stack([c[2] for c in c0]), gold[name + '.sample0.mask'])
+    assert np.array_equal(np.stack([c[2] for c in c1]), gold[name + '.sample1.mask'])
+    if name == 'aug_isic':
+        assert any(p['flips'][2] for p in params) and any(not p['flips'][2] for p in params)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(PR.AUG_CASES))
+def test_device_aug_pair_pipeline_matches_the_reference_composition(name):
+    gold = np.load(os.path.join(HERE, 'golden', 'aug_pipeline.npz'))
+    case = PR.AUG_CASES[name]
+    dev = torch.device('cuda:0')
+    pipe = make_aug_pipeline(case)
+    torch.manual_seed(case['torch_seed'])
+    samples = [{k: torch.from_numpy(v).to(dev) for k, v in s.items()} for s in PR.make_samples(case, 'unsup')]
+    out = pipe.unsup_batch(samples)
+    for m in ('sample0', 'sample1'):
+        assert np.array_equal(out[m]['image'].cpu().numpy(), gold[name + '.' + m + '.image']), m
+        assert np.array_equal(out[m]['mask'].cpu().numpy(), gold[name + '.' + m + '.mask']), m
+    assert out['xf0_to_1'].dtype == torch.float32 and np.array_equal(out['xf0_to_1'].cpu().numpy(), gold[name + '.xf0_to_1'])

@@ -181,6 +181,13 @@ AUG_CASES = {
     'aug_dl3plus_per_pixel_kld_sgd': ['--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes', '19',
                                       '--conf_per_pixel', '--cons_loss_fn', 'kld', '--opt_type', 'sgd', '--rampup', '2',
                                       '--aug_offset_range', '6'],
+    # `--dataset synthetic_u8`: uint8 images through the device pipeline's pair mode (script='aug_mt'); BASELINE config 4's option set
+    # (run_isic2017_experiments.sh:18) on the DenseNet-161 U-Net, and a scale-hung variant on DeepLab v2
+    'aug_u8_isic_recipe_denseunet': ['--dataset', 'synthetic_u8', '--arch', 'densenet161unet', '--synthetic_classes', '2', '--crop_size',
+                                     '64,64', '--aug_hflip', '--aug_vflip', '--aug_hvflip', '--aug_max_scale', '1.1', '--aug_rot_mag',
+                                     '45.0', '--aug_strong_colour'],
+    'aug_u8_scale_hung_dl2': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21',
+                              '--aug_hflip', '--aug_scale_hung', '--aug_offset_range', '8'],
 }
 BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size', '65,65', '--batch_size', '2',
         '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']

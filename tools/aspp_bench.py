@@ -48,6 +48,10 @@ if __name__ == '__main__':
         from cutmix_semisup_seg_b200 import lib as _lib0
         _lib0.load().b2_debug_set(7, int(os.environ['B200SEG_TAP_OUTER']))
         print('debug knob 7 (tap-outer producer order) =', os.environ['B200SEG_TAP_OUTER'])
+    if os.environ.get('B200SEG_MAIN_STAGES'):        # A/B of the operand ring depth of the compute-bound CTA-pair kernel (debug knob 10)
+        from cutmix_semisup_seg_b200 import lib as _lib1
+        _lib1.load().b2_debug_set(10, int(os.environ['B200SEG_MAIN_STAGES']))
+        print('debug knob 10 (operand stages of the main build) =', os.environ['B200SEG_MAIN_STAGES'])
     if which in ('all', 'aspp'):
         conv_case(16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N16')
     if which == 'l3':
@@ -109,6 +113,41 @@ if __name__ == '__main__':
             print('mma tile [begin, acc acquired]*:', tile[:24])
             print('epi  tile [wait begin, tfull ]*:', epi[:24])
             print('last stamps: prod {} mma {} tile {} epi {}'.format(prod[-1] if prod else 0, mma[-1] if mma else 0, tile[-1] if tile else 0, epi[-1] if epi else 0))
+    if which == 'trace3':
+        # pipeline timeline of CTA 0 for the compute-bound 3x3 shapes: per-stage cadence of the MMA issuer (cycles between
+        # consecutive `full` acquisitions), of the producer, and the per-tile waits (accumulator hand-over, epilogue)
+        import numpy as np
+        from cutmix_semisup_seg_b200 import lib as _lib
+        L = _lib.load()
+        for (n, h, w, cin, cout, k, dil, name) in ((32, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256 N32'),
+                                                   (16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 N16'),
+                                                   (32, 64, 64, 512, 512, 3, 4, 'layer4 3x3 d4 512->512 N32')):
+            pad = dil * (k // 2)
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            wt = torch.randn(cout, k * k, cin, device=dev) * 0.01
+            y = Act.alloc(n, h, w, cout, dev)
+            sc = torch.rand(cout, device=dev) + 0.5; sh = torch.randn(cout, device=dev)
+            buf = torch.zeros(2048, dtype=torch.int64, device=dev)
+            run = lambda: K.conv_fwd(x, wt, cout, k, k, cin, cin, 1, pad, dil, y, scale=sc, shift=sh, relu=True)
+            run(); flush.fill_(1.0); torch.cuda._sleep(600000)
+            L.b2_debug_trace(buf.data_ptr()); run(); torch.cuda.synchronize(); L.b2_debug_trace(None)
+            b = buf.cpu().numpy()
+            t0 = min(v for v in b if v > 0)
+            prod = np.array([v - t0 for v in b[0:512] if v > 0]); mma = np.array([v - t0 for v in b[512:1024] if v > 0])
+            tile = np.array([v - t0 for v in b[1024:1536] if v > 0]); epi = np.array([v - t0 for v in b[1536:2048] if v > 0])
+            stages_per_tile = 9 * (cin // 32)
+            dm, dp = np.diff(mma), np.diff(prod)
+            print('--- {}: {} stages per tile (ideal 512 cycles per stage at the tf32 rate)'.format(name, stages_per_tile))
+            print('  MMA stage cadence  : median {:.0f}  mean {:.0f}  p90 {:.0f}  max {:.0f} cycles  (n={})'.format(np.median(dm), dm.mean(), np.percentile(dm, 90), dm.max(), len(dm)))
+            print('  producer cadence   : median {:.0f}  mean {:.0f}  p90 {:.0f}  max {:.0f} cycles'.format(np.median(dp), dp.mean(), np.percentile(dp, 90), dp.max()))
+            big = np.argsort(dm)[-6:][::-1]
+            print('  largest MMA gaps at stage index (cycles):', [(int(i), int(dm[i])) for i in big])
+            tl = tile.reshape(-1, 2) if len(tile) % 2 == 0 else tile[:-1].reshape(-1, 2)
+            print('  tiles of CTA 0: begin ->', [int(v) for v in tl[:8, 0]], ' wait for the accumulator (cycles):', [int(v) for v in (tl[:, 1] - tl[:, 0])[:8]])
+            ep = epi.reshape(-1, 2) if len(epi) % 2 == 0 else epi[:-1].reshape(-1, 2)
+            print('  epilogue warp 4: wait begin ->', [int(v) for v in ep[:8, 0]], ' until the accumulator is full:', [int(v) for v in (ep[:, 1] - ep[:, 0])[:8]])
+            if len(tl) > 1:
+                print('  tile period (MMA warp, begin to begin):', [int(v) for v in np.diff(tl[:, 0])[:8]], ' = {:.0f} cycles per stage'.format(np.diff(tl[:, 0]).mean() / stages_per_tile))
     if which == 'l3full':
         # the two in-situ flavours of the HBM-bound layer3 1x1 (256 -> 1024 channels): forward with folded BN +
         # residual + ReLU, and the dgrad with partial-gradient addend + ReLU gate + fused BN statistics (+ residual sub)

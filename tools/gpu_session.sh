@@ -89,6 +89,12 @@ for l in sys.stdin:
     timeout -s KILL 400 ncu --set full --clock-control none --profile-from-start off -o gpurun_out/cublas_tf32_$tag -f python tools/cublas_tf32_probe.py > gpurun_out/ncu_cublas_$tag.log 2>&1
     python tools/ncu_summary.py gpurun_out/cublas_tf32_$tag.ncu-rep > gpurun_out/cublas_tf32_${tag}_summary.txt 2>&1; grep -E "kernel:|time_duration|tensor_cycles|mem_tensor|dram__bytes|lts__throughput|shared_mem_per_block|grid_size|block_size" gpurun_out/cublas_tf32_${tag}_summary.txt | head -40
     ;;
+  stages)     # 5 vs 6 operand stages of the compute-bound CTA-pair kernel (knob 10), kernel tests with the swizzled staging tile, pipeline trace
+    timeout -s KILL 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_$tag.log 2>&1; tail -3 gpurun_out/pytest_$tag.log | cut -c1-200
+    for v in 5 6; do B200SEG_MAIN_STAGES=$v timeout -s KILL 300 python tools/aspp_bench.py 5 all > gpurun_out/micro_${tag}_stages$v.log 2>&1; done
+    paste -d'|' <(cut -c1-78 gpurun_out/micro_${tag}_stages5.log) <(cut -c46-78 gpurun_out/micro_${tag}_stages6.log) | head -40
+    timeout -s KILL 300 python tools/aspp_bench.py 3 trace3 > gpurun_out/trace3_$tag.log 2>&1; cat gpurun_out/trace3_$tag.log | cut -c1-250
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;

@@ -9,7 +9,10 @@ cutmix_semisup_seg_b200.train_loop.run_training, shared with train_seg_semisup_m
 The click surface (option names and defaults, reference lines 515-577) and the job function signature are kept; the additions
 (`--dataset synthetic`, `--no_pretrained`, `--ddp`, `--synthetic_classes`) are those of train_seg_semisup_mask_mt.py.  With
 `--dataset synthetic` the affine maps are drawn from the script's own augmentation ranges (`--aug_rot_mag` degrees,
-`--aug_max_scale`, `--aug_offset_range` pixels; one draw per view, like the reference's per-crop transforms).
+`--aug_max_scale`, `--aug_offset_range` pixels; one draw per view, like the reference's per-crop transforms).  With
+`--dataset synthetic_u8` uint8 images of assorted sizes go through the script's own transform lists (:126-163: pairs of
+differently cropped / scaled / rotated / flipped views, colour jitter on the student's view, `xf0_to_1` from the two crops'
+matrices) ON THE DEVICE (cutmix_semisup_seg_b200.input_pipeline.DeviceTrainPipeline(script='aug_mt')).
 `--cons_loss_fn logits_var` fails on the first unsupervised batch exactly like the reference (its line 373 reads a variable
 only the `var` branch assigns).
 """
@@ -39,8 +42,16 @@ def train_seg_semisup_aug_mt(submit_config, dataset, model, arch, freeze_bn,
         return synthetic.make_aug_batch(n, h, w, seed, paired=aug_strong_colour, rot_mag=aug_rot_mag, max_scale=aug_max_scale,
                                         offset_range=aug_offset_range, device=device)
 
+    def u8_unsup(batches, n, h, w, seed, device):
+        """`--dataset synthetic_u8`: the pair batch of the device pipeline (script='aug_mt') in MeanTeacherStep's format -- teacher
+        view `sample0`, student view `sample1` (colour-jittered with --aug_strong_colour), `xf0_to_1` (reference :291-300)."""
+        b = batches[0]
+        return dict(ux0=b['sample0']['image'], um0=b['sample0']['mask'], ux1=b['sample1']['image'], um1=b['sample1']['mask'],
+                    xf0_to_1=b['xf0_to_1'])
+
     train_loop.run_training(
-        submit_config, settings, make_unsup, None, True,
+        submit_config, settings, make_unsup, None, True, u8_unsup=u8_unsup, u8_loaders=1,
+        pipeline_options=dict(script='aug_mt', aug_offset_range=aug_offset_range, aug_free_scale_rot=aug_free_scale_rot),
         dataset=dataset, model=model, arch=arch, freeze_bn=freeze_bn, opt_type=opt_type, sgd_momentum=sgd_momentum,
         sgd_nesterov=sgd_nesterov, sgd_weight_decay=sgd_weight_decay, learning_rate=learning_rate, lr_sched=lr_sched,
         lr_step_epochs=lr_step_epochs, lr_step_gamma=lr_step_gamma, lr_poly_power=lr_poly_power, teacher_alpha=teacher_alpha,
@@ -53,7 +64,7 @@ def train_seg_semisup_aug_mt(submit_config, dataset, model, arch, freeze_bn,
 
 @click.command()
 @click.option('--job_desc', type=str, default='')
-@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic']),
+@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic', 'synthetic_u8']),
               default='pascal_aug')
 @click.option('--model', type=click.Choice(['mean_teacher', 'pi']), default='mean_teacher')
 @click.option('--arch', type=str, default='resnet101_deeplab_imagenet')
