@@ -26,8 +26,7 @@ def check_dataset(dataset, u8_supported=False):
     data sets need the reference's image archives and decoders, which are outside the B200 hot path (SURVEY.md 8 'out of scope')."""
     import click
     if dataset == 'synthetic_u8' and not u8_supported:
-        raise click.UsageError("--dataset 'synthetic_u8' is wired into train_seg_semisup_mask_mt.py / train_seg_semisup_aug_mt.py only; "
-                               "use --dataset synthetic here.")
+        raise click.UsageError("--dataset 'synthetic_u8' is not wired into this entry point; use --dataset synthetic here.")
     if dataset not in ('synthetic', 'synthetic_u8'):
         raise click.UsageError(
             "--dataset {!r} is not available in the B200 build: the reference's CPU data pipeline (datapipe/, real image archives) "
@@ -40,6 +39,14 @@ def check_dataset(dataset, u8_supported=False):
 U8_USED_OPTIONS = ('n_sup', 'n_unsup', 'split_seed', 'aug_offset_range', 'aug_hflip', 'aug_vflip', 'aug_hvflip', 'aug_scale_hung', 'aug_max_scale',
                    'aug_scale_non_uniform', 'aug_rot_mag', 'aug_colour_brightness', 'aug_colour_contrast', 'aug_colour_saturation',
                    'aug_colour_hue', 'aug_colour_prob', 'aug_colour_greyscale_prob')
+
+
+def u8_views(batch):
+    """(teacher image, student image, valid mask) of one DeviceTrainPipeline.unsup_batch output: with `unsup_paired` the teacher
+    sees `sample0` (weak) and the student `sample1` (colour-jittered), reference train_seg_semisup_mask_mt.py:313-323."""
+    if 'sample0' in batch:
+        return batch['sample0']['image'], batch['sample1']['image'], batch['sample0']['mask']
+    return batch['image'], batch['image'], batch['mask']
 
 
 def ignored_options(settings, used=()):

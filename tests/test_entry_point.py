@@ -17,7 +17,7 @@ from architectures import network_architectures
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'entry_point.json')))
 # options this build adds (documented in the module docstring); everything else must be the reference's
 EXTRA_OPTIONS = {'no_pretrained', 'ddp', 'synthetic_classes'}
-EXTRA_CHOICES = {'dataset': {'synthetic'}}
+EXTRA_CHOICES = {'dataset': {'synthetic', 'synthetic_u8'}}
 
 
 SCRIPTS = {'train_seg_semisup_mask_mt': train_seg_semisup_mask_mt, 'train_seg_semisup_ict': train_seg_semisup_ict,

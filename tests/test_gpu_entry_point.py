@@ -37,6 +37,8 @@ ICT_CASES = {
     'ict_mean_teacher_dl2': ['--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21', '--ict_alpha', '0.4'],
     'ict_dl3plus_per_pixel_bce': ['--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes', '19',
                                   '--conf_per_pixel', '--cons_loss_fn', 'bce', '--opt_type', 'sgd', '--rampup', '2'],
+    'ict_u8_device_pipeline_colour': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21',
+                                      '--aug_hflip', '--aug_scale_hung', '--aug_strong_colour'],
 }
 
 

@@ -191,6 +191,8 @@ VAT_CASES = {
     'vat_dl3plus_adaptive_from_student': ['--arch', 'resnet101_deeplabv3plus_imagenet', '--synthetic_classes', '19',
                                           '--adaptive_vat_radius', '--vat_dir_from_student', '--cons_loss_fn', 'var',
                                           '--conf_per_pixel', '--opt_type', 'sgd', '--rampup', '2', '--aug_strong_colour'],
+    'vat_u8_device_pipeline_rot_scale': ['--dataset', 'synthetic_u8', '--arch', 'resnet101_deeplab_imagenet', '--synthetic_classes', '21',
+                                         '--aug_hflip', '--aug_max_scale', '1.2', '--aug_rot_mag', '20.0', '--aug_strong_colour'],
 }
 BASE = ['--dataset', 'synthetic', '--no_pretrained', '--freeze_bn', '--crop_size', '65,65', '--batch_size', '2',
         '--iters_per_epoch', '2', '--num_epochs', '2', '--learning_rate', '1e-5', '--conf_thresh', '0.5']

@@ -64,10 +64,7 @@ def train_seg_semisup_mask_mt(submit_config, dataset, model, arch, freeze_bn,
         import numpy as np
         import torch
 
-        def views(b):
-            if 'sample0' in b:
-                return b['sample0']['image'], b['sample1']['image'], b['sample0']['mask']
-            return b['image'], b['image'], b['mask']
+        views = train_loop.u8_views
         out = {}
         if mask_mix:
             out['ux0_tea'], out['ux0_stu'], out['um0'] = views(batches[0])

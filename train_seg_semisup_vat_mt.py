@@ -38,8 +38,16 @@ def train_seg_semisup_vat_mt(submit_config, dataset, model, arch, freeze_bn,
     def make_unsup(n, h, w, seed, device):
         return synthetic.make_vat_batch(n, h, w, seed, paired=aug_strong_colour, device=device)
 
+    def u8_unsup(batches, n, h, w, seed, device):
+        """`--dataset synthetic_u8`: one unsupervised batch of the device pipeline, marked as a VAT batch (reference :364-380)."""
+        import torch
+        out = {}
+        out['ux_tea'], out['ux_stu'], out['um'] = train_loop.u8_views(batches[0])
+        out['vat'] = torch.ones((1,), device=device)
+        return out
+
     train_loop.run_training(
-        submit_config, settings, make_unsup, None, True,
+        submit_config, settings, make_unsup, None, True, u8_unsup=u8_unsup, u8_loaders=1,
         dataset=dataset, model=model, arch=arch, freeze_bn=freeze_bn, opt_type=opt_type, sgd_momentum=sgd_momentum,
         sgd_nesterov=sgd_nesterov, sgd_weight_decay=sgd_weight_decay, learning_rate=learning_rate, lr_sched=lr_sched,
         lr_step_epochs=lr_step_epochs, lr_step_gamma=lr_step_gamma, lr_poly_power=lr_poly_power, teacher_alpha=teacher_alpha,
@@ -53,7 +61,7 @@ def train_seg_semisup_vat_mt(submit_config, dataset, model, arch, freeze_bn,
 
 @click.command()
 @click.option('--job_desc', type=str, default='')
-@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic']),
+@click.option('--dataset', type=click.Choice(['camvid', 'cityscapes', 'pascal', 'pascal_aug', 'isic2017', 'synthetic', 'synthetic_u8']),
               default='pascal_aug')
 @click.option('--model', type=click.Choice(['mean_teacher', 'pi']), default='mean_teacher')
 @click.option('--arch', type=str, default='resnet101_deeplab_imagenet')
