@@ -147,6 +147,11 @@ def _versions(*tensors):
 
 
 class Tape(object):
+    # `parts`: sizes of the mini-batches concatenated along the batch dimension while the graph of a multi-batch pass is recorded
+    # (netbase.b2_forward_multi); train-mode BatchNorm then normalises every mini-batch with its OWN statistics (bn_train), which
+    # is all that distinguishes one pass over [x1 ; x2] from consecutive passes over x1 and x2
+    parts = None
+
     def __init__(self, kernels, enabled):
         self.K = kernels
         self.enabled = enabled
@@ -473,11 +478,12 @@ class ConvNode(object):
 
 
 class BNTrainNode(object):
-    """y = dropout( relu( bn_train(raw) [+ residual] ) )"""
+    """y = dropout( relu( bn_train(raw) [+ residual] ) ); `parts`: [(first image, images, mean, rstd, dropmask)] -- one entry, or one
+    per mini-batch of a multi-batch pass (each normalised with its own statistics)."""
 
-    def __init__(self, raw, y, bn, mean, rstd, residual, relu, dropmask, drop_scale):
-        self.raw, self.y, self.bn, self.mean, self.rstd = raw, y, bn, mean, rstd
-        self.residual, self.relu, self.dropmask, self.drop_scale = residual, relu, dropmask, drop_scale
+    def __init__(self, raw, y, bn, parts, residual, relu, drop_scale):
+        self.raw, self.y, self.bn, self.parts = raw, y, bn, parts
+        self.residual, self.relu, self.drop_scale = residual, relu, drop_scale
 
     def backward(self, tape):
         K = tape.K
@@ -497,11 +503,15 @@ class BNTrainNode(object):
             dgam = dbet = None
             acc = False
         dyd = dy
-        if self.dropmask is not None and dy.ld != dy.c:
+        if any(p[4] is not None for p in self.parts) and dy.ld != dy.c:
             dyd = dy.like()
             K.copy_act(dyd, dy)
-        K.bn_bwd(dyd, self.raw, self.y, self.mean, self.rstd, bn.weight, self.relu, self.dropmask, self.drop_scale, dx,
-                 dgam, dbet, acc, g_out=g_out)
+        whole = len(self.parts) == 1
+        for i, (n0, n, mean, rstd, dropmask) in enumerate(self.parts):
+            def sl(a):
+                return a if (whole or a is None) else a.batch_slice(n0, n)
+            K.bn_bwd(sl(dyd), sl(self.raw), sl(self.y), mean, rstd, bn.weight, self.relu, dropmask, self.drop_scale, sl(dx),
+                     dgam, dbet, acc or i > 0, g_out=sl(g_out))
         if self.raw.parent is not None:      # input = a channel prefix of a concatenation buffer (DenseNet norm1, train mode)
             tape.contribute_slice(self.raw, lambda dst, accumulate: K.copy_act(dst, dx, accumulate=accumulate))
         else:
@@ -783,22 +793,37 @@ def conv_bn_act(tape, x, conv, bn=None, residual=None, relu=False, out=None, dro
 
 
 def bn_train(tape, raw, bn, residual=None, relu=False, out=None, dropout=None, ld_out=None):
+    """Train-mode BatchNorm (+residual, ReLU, dropout).  In a multi-batch pass (tape.parts) every mini-batch is normalised with its
+    own batch statistics, running statistics and dropout draws advance mini-batch by mini-batch -- exactly as in consecutive
+    forward calls (reference: one `net(x)` call per mini-batch), while the convolutions around it run once over all of them."""
     K = tape.K
-    mean = torch.empty_like(bn.running_mean)
-    rstd = torch.empty_like(bn.running_mean)
     momentum = bn.momentum if bn.momentum is not None else 0.1
-    K.bn_stats(raw, bn.eps, momentum, mean, rstd, bn.running_mean, bn.running_var)
-    bn.num_batches_tracked += 1
     y = out if out is not None else Act.alloc(raw.n, raw.h, raw.w, raw.c, raw.device, ld=ld_out)
-    dropmask, drop_scale = None, 1.0
-    if dropout is not None and dropout.training and dropout.p > 0:
-        dropmask = dropout.next_mask(K, raw.n, raw.h, raw.w, raw.c, raw.device)
-        drop_scale = 1.0 / (1.0 - dropout.p)
-    K.bn_apply(raw, mean, rstd, bn.weight, bn.bias, relu, dropmask, drop_scale, y, residual=residual)
-    node = BNTrainNode(raw, y, bn, mean, rstd, residual, relu, dropmask, drop_scale)
+    sizes = tape.parts if (tape.parts is not None and len(tape.parts) > 1 and sum(tape.parts) == raw.n) else [raw.n]
+    whole = len(sizes) == 1
+    use_drop = dropout is not None and dropout.training and dropout.p > 0
+    drop_scale = 1.0 / (1.0 - dropout.p) if use_drop else 1.0
+    parts, n0 = [], 0
+    for n in sizes:
+        def sl(a):
+            return a if (whole or a is None) else _batch_view(a, n0, n)
+        mean = torch.empty_like(bn.running_mean)
+        rstd = torch.empty_like(bn.running_mean)
+        K.bn_stats(sl(raw), bn.eps, momentum, mean, rstd, bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+        dropmask = dropout.next_mask(K, n, raw.h, raw.w, raw.c, raw.device) if use_drop else None
+        K.bn_apply(sl(raw), mean, rstd, bn.weight, bn.bias, relu, dropmask, drop_scale, sl(y), residual=sl(residual))
+        parts.append((n0, n, mean, rstd, dropmask))
+        n0 += n
+    node = BNTrainNode(raw, y, bn, parts, residual, relu, drop_scale)
     y.node = node
     tape.record(node, [raw] + ([residual] if residual is not None else []))
     return y
+
+
+def _batch_view(a, n0, n):
+    """Images [n0, n0 + n) of an activation (root or channel slice) as a plain view for a kernel call."""
+    return Act(a.base[n0:n0 + n], n, a.h, a.w, a.c, a.ld, a.off, a.name)
 
 
 def stem_conv(tape, x_nhwc, conv, bn):

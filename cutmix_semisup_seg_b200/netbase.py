@@ -60,6 +60,9 @@ class _B2Function(torch.autograd.Function):
 
 class B2SegNet(nn.Module):
     BLOCK_SIZE = (1, 1)
+    # multi-batch passes run the head's convolutions once over all mini-batches too (train-mode BatchNorm per mini-batch);
+    # B200SEG_BATCH_HEAD=0 restores the head-per-mini-batch schedule for A/B timing
+    b2_batched_head = os.environ.get('B200SEG_BATCH_HEAD', '1') != '0'
 
     # precision of the tensor-core convolutions: 'tf32' (one pass; what cuDNN does by default) or
     # '3xtf32' (operands split in hi/lo parts, three passes: ~fp32 accuracy, used by the parity tests)
@@ -74,8 +77,9 @@ class B2SegNet(nn.Module):
     # The graph is given in two parts: a TRUNK (the ResNet-101 backbone; DeepLab v2: the whole network) and a HEAD.  With
     # frozen BatchNorm the trunk is batch-invariant (every sample is processed independently), so the training step
     # runs it ONCE over the concatenation of several mini-batches (b2_forward_multi) -- bigger GEMMs, half the
-    # launches, no partial last wave on the 256-channel layers -- while the head (train-mode BatchNorm statistics,
-    # dropout; DeepLab v3+) runs per mini-batch exactly as in the reference.
+    # launches, no partial last wave on the 256-channel layers.  The head's convolutions run over the concatenation as well; its
+    # train-mode BatchNorm layers (DeepLab v3+) normalise every mini-batch with its own statistics and draw dropout masks per
+    # mini-batch (engine.bn_train with tape.parts), i.e. the arithmetic of consecutive reference passes.
     def _graph_trunk(self, tape, x, in_h, in_w):
         """Run the trunk on `x` (Act, NHWC, ld 4); return [(feature Act, split_is_only_consumer), ...]."""
         raise NotImplementedError
@@ -142,12 +146,22 @@ class B2SegNet(nn.Module):
         xin = K.nchw_to_act(x_all, 4)
         xin.needs_grad = False
         feats = self._graph_trunk(tape, xin, in_h, in_w)
-        split = [E.batch_split(tape, f, sizes, delegate_gate=only) for f, only in feats]
         logits, lows = [], []
-        for i in range(len(xs)):
-            low, align = self._graph_head(tape, [parts[i] for parts in split], in_h, in_w)
-            logits.append(E.to_logits_nchw(tape, low, in_h, in_w, align))
-            lows.append((low, align))
+        if self.b2_batched_head:
+            # the head's convolutions also run once over all mini-batches (a 16-image head launch fills 3.46 of 4 waves of CTA
+            # pairs, a 32-image one 6.92 of 7); its train-mode BatchNorms normalise per mini-batch (engine.bn_train, tape.parts)
+            tape.parts = sizes
+            low_all, align = self._graph_head(tape, [f for f, _ in feats], in_h, in_w)
+            tape.parts = None
+            for low in E.batch_split(tape, low_all, sizes):
+                logits.append(E.to_logits_nchw(tape, low, in_h, in_w, align))
+                lows.append((low, align))
+        else:
+            split = [E.batch_split(tape, f, sizes, delegate_gate=only) for f, only in feats]
+            for i in range(len(xs)):
+                low, align = self._graph_head(tape, [parts[i] for parts in split], in_h, in_w)
+                logits.append(E.to_logits_nchw(tape, low, in_h, in_w, align))
+                lows.append((low, align))
         if not record:
             tape.discard()
             return logits, None
