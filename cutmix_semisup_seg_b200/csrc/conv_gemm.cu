@@ -17,6 +17,7 @@
 //   * fused epilogue: BN scale/shift | bias, residual add, ReLU, ReLU-gate (backward), second scale,
 //     accumulate; output leading dimension + channel offset let a conv write into a slice of a wider
 //     buffer (no torch.cat), output stride/offset scatter handles strided dgrad.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "conv_epilogue.cuh"
 
@@ -111,6 +112,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc::pdl_wait();                 // everything above overlaps the predecessor's tail (tc_common.cuh)
+  tc::pdl_launch_dependents();
 
   const uint32_t rows_a = a.bw * a.bh * a.bn;
   const uint32_t stage_tx = rows_a * 128u + (uint32_t)a.block_n * 128u;
@@ -299,6 +302,11 @@ extern "C" int64_t b2_conv_stats_rows(const b2_conv_params* p) {
 }
 int g_conv_force_1cta = 0;
 int g_conv_epi_debug = 0;
+int g_conv_pdl = -1;              // b2_debug_set(11, v) / environment B200SEG_PDL: programmatic dependent launch (tc_common.cuh)
+bool tc::pdl_enabled() {
+  if (g_conv_pdl < 0) { const char* e = getenv("B200SEG_PDL"); g_conv_pdl = e ? atoi(e) : 0; }
+  return g_conv_pdl > 0;
+}
 int g_conv_tap_outer = 0;         // b2_debug_set(7, 1): producer loops tap-outer / K-block-inner (the round-1 order)
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
@@ -388,7 +396,7 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_gemm: no CUDA device");
   if (p->max_ctas > 0 && p->max_ctas < grid) grid = p->max_ctas;
   if (grid > a.num_tiles) grid = a.num_tiles;
-  conv_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+  tc::launch(conv_gemm_kernel, (unsigned)grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, a);
   B2_LAUNCH_CHECK("conv_gemm_kernel");
   return B2_OK;
 }

@@ -197,6 +197,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();                               // barriers of BOTH CTAs initialised, TMEM allocated
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc::pdl_wait();                 // everything above overlaps the predecessor's tail (tc_common.cuh)
+  tc::pdl_launch_dependents();
 
   const uint32_t rows_a = a.bw * a.bh * a.bn;
   const uint32_t stage_tx = 2u * (rows_a * 128u + (uint32_t)(BLOCK_N / 2) * 128u);     // both CTAs' bytes
@@ -500,11 +502,11 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   if (clusters < 1) clusters = 1;
   if (clusters > a.num_pairs) clusters = a.num_pairs;
   if (use_pf)
-    conv_gemm2_kernel<STAGES_PF, true><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_PF, true>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   else if (g_conv_main_stages == STAGES_MAIN_OLD)
-    conv_gemm2_kernel<STAGES_MAIN_OLD, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN_OLD, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_MAIN_OLD, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN_OLD, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   else
-    conv_gemm2_kernel<STAGES_MAIN, false><<<clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_MAIN, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
   B2_LAUNCH_CHECK("conv_gemm2_kernel");
   return B2_OK;
 }

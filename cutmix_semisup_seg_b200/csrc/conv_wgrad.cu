@@ -162,6 +162,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc::pdl_wait();                 // everything above overlaps the predecessor's tail (tc_common.cuh)
+  tc::pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
@@ -396,6 +398,8 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
   w2_cluster_sync();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc::pdl_wait();                 // everything above overlaps the predecessor's tail (tc_common.cuh)
+  tc::pdl_launch_dependents();
 
   const int half_n = a.block_n / 2;                   // this CTA's input channels of the N tile (multiple of 32)
   const int slot = a.kpix * 128;
@@ -527,6 +531,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_consta
 __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_splits, int64_t elems,
                                     float* __restrict__ dw, int accumulate) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  tc::pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += stride) {
     float s = accumulate ? dw[i] : 0.0f;
     for (int k = 0; k < n_splits; ++k) s += slabs[(int64_t)k * elems + i];
@@ -647,7 +652,9 @@ extern int g_conv_pf_max_k;
 extern int g_conv_tap_outer;
 extern int g_conv_tma_epi;
 extern int g_conv_main_stages;
+extern int g_conv_pdl;
 extern "C" void b2_debug_set(int key, int value) {
+  if (key == 11) g_conv_pdl = value;
   if (key == 5) g_wgrad_force_1cta = value;
   if (key == 6) g_wgrad_dbg = value;
   if (key == 1) g_wgrad_desc_variant = value;
@@ -777,13 +784,13 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     if (clusters <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
     if (p->max_ctas > 0 && p->max_ctas / 2 < clusters) clusters = p->max_ctas / 2 > 0 ? p->max_ctas / 2 : 1;
     if (clusters > a.num_units) clusters = a.num_units;
-    conv_wgrad2_kernel<<<clusters * 2, W_THREADS, W2_SMEM_BYTES, s>>>(y5, y5lo, x5, x5lo, a);
+    tc::launch(conv_wgrad2_kernel, clusters * 2, W_THREADS, W2_SMEM_BYTES, s, y5, y5lo, x5, x5lo, a);
     B2_LAUNCH_CHECK("conv_wgrad2_kernel");
     if (a.n_splits > 1) {
       const int64_t elems = (int64_t)p->m * p->tw * p->c;
       int64_t blocks = ceil_div64(elems, 256);
       if (blocks > 148 * 8) blocks = 148 * 8;
-      wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
+      tc::launch(wgrad_reduce_kernel, (unsigned)blocks, 256, 0, s, reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
       B2_LAUNCH_CHECK("wgrad_reduce_kernel");
     }
     return B2_OK;
@@ -792,13 +799,13 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
   if (grid <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
   if (p->max_ctas > 0 && p->max_ctas < grid) grid = p->max_ctas;
   if (grid > a.num_units) grid = a.num_units;
-  conv_wgrad_kernel<<<grid, W_THREADS, W_SMEM_BYTES, s>>>(tmY, tmYlo, tmX, tmXlo, tmY5, tmY5lo, tmX5, tmX5lo, a);
+  tc::launch(conv_wgrad_kernel, (unsigned)grid, W_THREADS, W_SMEM_BYTES, s, tmY, tmYlo, tmX, tmXlo, tmY5, tmY5lo, tmX5, tmX5lo, a);
   B2_LAUNCH_CHECK("conv_wgrad_kernel");
   if (a.n_splits > 1) {
     const int64_t elems = (int64_t)p->m * p->tw * p->c;
     int64_t blocks = ceil_div64(elems, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
+    tc::launch(wgrad_reduce_kernel, (unsigned)blocks, 256, 0, s, reinterpret_cast<const float*>(p->workspace), a.n_splits, elems, p->dw, p->accumulate);
     B2_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   return B2_OK;

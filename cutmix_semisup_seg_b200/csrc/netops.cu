@@ -702,6 +702,15 @@ extern "C" int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw
 // MODE 2: (g, g*xhat)       BN backward, g = dy * gate(y) * drop, xhat = (x - mean) * rstd
 // MODE 3: (g, g*y)          frozen-BN parameter gradients (y = BN output proxy), g = dy gated by gate>0
 constexpr int RED_ROWS_PER_CHUNK = 2048;
+// Rows per chunk for a (rows x c) reduction: 2048, halved (down to 256) until the grid has >= 4 blocks per SM -- with 2048 rows
+// per block a 65536 x 256 tensor gave 256 blocks = 1.7 per SM, too few bytes in flight to cover the HBM latency
+// (col_reduce_kernel at 3.8 TB/s in profiles/r02_v7_launch_list_summary.txt).
+static inline int red_rows_per_chunk(int64_t rows, int c) {
+  int rpc = RED_ROWS_PER_CHUNK;
+  const int64_t cb = (c + 31) / 32;
+  while (rpc > 256 && ((rows + rpc - 1) / rpc) * cb < 148 * 4) rpc >>= 1;
+  return rpc;
+}
 struct RedArgs {
   const float* a; int lda;      // dy or x
   const float* b; int ldb;      // x (mode 2) / y (mode 3)
@@ -711,6 +720,7 @@ struct RedArgs {
   const float* sub; int lds;    // mode 3: o = b - sub (residual removed from the block output)
   int64_t rows; int c;
   int vec;                      // every pointer 16 B aligned and every ld / c a multiple of 4
+  int rpc;                      // rows per chunk (red_rows_per_chunk)
 };
 // Block = 32 channels x one chunk of rows.  Thread (cg = tid & 7, rl = tid >> 3) owns 4 consecutive channels and walks
 // rows rl, rl+32, ... with 16 B loads: 8 lanes cover a 128 B row segment, a warp covers 4 rows per instruction, and the
@@ -721,15 +731,35 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
   const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch0 = blockIdx.y * 32 + cg * 4;
-  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS_PER_CHUNK;
-  int64_t r1 = r0 + RED_ROWS_PER_CHUNK; if (r1 > r.rows) r1 = r.rows;
+  const int64_t r0 = (int64_t)blockIdx.x * r.rpc;
+  int64_t r1 = r0 + r.rpc; if (r1 > r.rows) r1 = r.rows;
   double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1};
   if (MODE == 2) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) if (ch0 + e < r.c) { mean[e] = r.mean[ch0 + e]; rstd[e] = r.rstd[ch0 + e]; }
   }
-  if (r.vec && ch0 + 3 < r.c) {
+  if (MODE <= 1 && r.vec && ch0 + 3 < r.c) {
+    // one tensor: four independent 16 B loads per thread in flight (rows rl, rl + 32, rl + 64, rl + 96 of a 128-row group)
+    int64_t row = r0 + rl;
+    for (; row + 96 < r1; row += 128) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const float4*>(r.a + (row + 32 * u) * r.lda + ch0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float va[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s0[e] += va[e]; if (MODE == 1) s1[e] += (double)va[e] * (double)va[e]; }
+      }
+    }
+    for (; row < r1; row += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(r.a + row * r.lda + ch0));
+      const float va[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s0[e] += va[e]; if (MODE == 1) s1[e] += (double)va[e] * (double)va[e]; }
+    }
+  } else if (r.vec && ch0 + 3 < r.c) {
 #pragma unroll 2
     for (int64_t row = r0 + rl; row < r1; row += 32) {
       float4 v = __ldg(reinterpret_cast<const float4*>(r.a + row * r.lda + ch0));
@@ -804,15 +834,16 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
     }
   }
 }
-static inline int64_t red_chunks(int64_t rows) { return ceil_div64(rows, RED_ROWS_PER_CHUNK); }
-extern "C" int64_t b2_bn_workspace_doubles(int64_t rows, int c) { return red_chunks(rows) * c * 2 + 2 * (int64_t)c; }
+static inline int64_t red_chunks(int64_t rows, int c) { return ceil_div64(rows, red_rows_per_chunk(rows, c)); }
+extern "C" int64_t b2_bn_workspace_doubles(int64_t rows, int c) { return red_chunks(rows, c) * c * 2 + 2 * (int64_t)c; }
 
 template <int MODE>
 static int launch_col_reduce(const RedArgs& r0, double* ws, cudaStream_t s) {
   RedArgs r = r0;
   auto ok = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0); };
   r.vec = (r.c % 4 == 0) && ok(r.a, r.lda) && ok(r.b, r.ldb) && ok(r.gate, r.ldg) && ok(r.sub, r.lds) && ok(r.drop, r.lda);
-  dim3 grid((unsigned)red_chunks(r.rows), (r.c + 31) / 32);
+  r.rpc = red_rows_per_chunk(r.rows, r.c);
+  dim3 grid((unsigned)red_chunks(r.rows, r.c), (r.c + 31) / 32);
   col_reduce_kernel<MODE><<<grid, 256, 0, s>>>(r, ws);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return b2_fail(B2_ERR_CUDA, "col_reduce launch failed: %s", cudaGetErrorString(e));
@@ -855,8 +886,8 @@ extern "C" int b2_colsum(const float* dy, int ld, int64_t rows, int c, float* ou
   RedArgs r{}; r.a = dy; r.lda = ld; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<0>(r, workspace, s); if (rc) return rc;
-  double* fin = workspace + red_chunks(rows) * c * 2;
-  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  double* fin = workspace + red_chunks(rows, c) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   colsum_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, out, accumulate);
   B2_LAUNCH_CHECK("colsum");
   return B2_OK;
@@ -884,8 +915,8 @@ extern "C" int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float e
   RedArgs r{}; r.a = x; r.lda = ldx; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<1>(r, workspace, s); if (rc) return rc;
-  double* fin = workspace + red_chunks(rows) * c * 2;
-  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  double* fin = workspace + red_chunks(rows, c) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   bn_stats_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, rows, eps, momentum, mean, rstd, running_mean, running_var);
   B2_LAUNCH_CHECK("bn_stats");
   return B2_OK;
@@ -1062,8 +1093,8 @@ extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, con
   r.drop = dropmask; r.drop_scale = drop_scale; r.mean = mean; r.rstd = rstd; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<2>(r, workspace, s); if (rc) return rc;
-  double* fin = workspace + red_chunks(rows) * c * 2;
-  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  double* fin = workspace + red_chunks(rows, c) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   const bool vec = c % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && al16(dy) && al16(x) && al16(dx) &&
                    (!relu || (ldy % 4 == 0 && al16(y))) && (!dropmask || al16(dropmask)) && (!g_out || (ldgo % 4 == 0 && al16(g_out)));
   const int64_t total = rows * (vec ? c / 4 : c);
@@ -1117,8 +1148,8 @@ extern "C" int b2_bn_eval_param_grad(const float* dy, int lddy, const float* ybn
   RedArgs r{}; r.a = dy; r.lda = lddy; r.b = ybn; r.ldb = ldy; r.gate = gate; r.ldg = ldg; r.sub = sub; r.lds = lds; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<3>(r, workspace, s); if (rc) return rc;
-  double* fin = workspace + red_chunks(rows) * c * 2;
-  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  double* fin = workspace + red_chunks(rows, c) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   bn_eval_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, gamma, beta, dgamma, dbeta, accumulate);
   B2_LAUNCH_CHECK("bn_eval_param_grad");
   return B2_OK;
@@ -1282,8 +1313,8 @@ extern "C" int b2_bn_eval_param_grad_wdot(const float* dy, int lddy, int64_t row
   RedArgs r{}; r.a = dy; r.lda = lddy; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<0>(r, workspace, s); if (rc) return rc;
-  double* fin = workspace + red_chunks(rows) * c * 2;
-  launch_col_finalize(workspace, red_chunks(rows), c, fin, s);
+  double* fin = workspace + red_chunks(rows, c) * c * 2;
+  launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   B2_LAUNCH_CHECK("col_finalize_kernel");
   return launch_wdot(fin, 1, c, w, gw, row_len, gamma, mean, var, eps, dgamma, dbeta, accumulate, s);
 }

@@ -3,6 +3,7 @@
 // Encodings follow the PTX ISA tcgen05 matrix/instruction descriptor tables.
 #pragma once
 #include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace tc {
@@ -53,6 +54,16 @@ __device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one (
   return pred;
 }
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }   // provably warp-uniform
+
+// ---------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute (tc::launch below) may start while its predecessor
+// in the stream is still running: its CTAs become resident as the predecessor's CTAs retire, run their prologue (barrier
+// init, TMEM allocation, tensor-map prefetch -- nothing that touches global memory) and block in pdl_wait() until the
+// predecessor grid has completed and its memory operations are visible.  pdl_launch_dependents() is the predecessor's
+// side: "my dependents may be scheduled now" (they still wait for this grid's completion in their pdl_wait()).
+// Both are no-ops in a launch without the attribute / without dependents.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------- TMA
 // bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16 B aligned global address
@@ -163,5 +174,20 @@ PFN_encodeTiled get_encode_tiled();
 // fp32 tensor, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides_bytes has rank-1 entries.
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides, bool atom32 = false);
+
+// 1 = launch the tensor-core kernels with the programmatic-stream-serialization attribute (environment B200SEG_PDL or
+// b2_debug_set(11, v)); 0 = plain stream order
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
 
 }  // namespace tc

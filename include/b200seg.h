@@ -381,7 +381,8 @@ int b2_conv_wgrad_plan_check(const b2_wgrad_params* p, int64_t* out);
  * 3 = epilogue timing bits; 4 = PF-build K limit; 5 = 1 forces the single-CTA wgrad kernel; 6 = wgrad timing bits;
  * 7 = 1 restores the tap-outer / K-block-inner producer order of the conv kernels (A/B timing of the L2 working set);
  * 8 = 0 disables the TMA epilogue of the CTA-pair conv kernel (register epilogue everywhere);
- * 10 = 5 selects the 5-stage build of the compute-bound CTA-pair kernel (default 6 stages; A/B timing). */
+ * 10 = 5 selects the 5-stage build of the compute-bound CTA-pair kernel (default 6 stages; A/B timing);
+ * 11 = programmatic dependent launch of the tensor-core kernels (1 on, 0 off; environment B200SEG_PDL). */
 void b2_debug_set(int key, int value);
 /* Diagnostics: device buffer of 2048 int64 receiving clock64 stamps of CTA 0's pipeline roles in the 2-CTA conv
  * kernel ([0,512) producer stage issue, [512,1024) MMA stage acquired, [1024,1536) MMA tile begin/accumulator

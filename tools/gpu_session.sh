@@ -95,6 +95,16 @@ for l in sys.stdin:
     paste -d'|' <(cut -c1-78 gpurun_out/micro_${tag}_stages5.log) <(cut -c46-78 gpurun_out/micro_${tag}_stages6.log) | head -40
     timeout -s KILL 300 python tools/aspp_bench.py 3 trace3 > gpurun_out/trace3_$tag.log 2>&1; cat gpurun_out/trace3_$tag.log | cut -c1-250
     ;;
+  headab)     # whole suite on HEAD (batched head default), then bench A/B: head over all mini-batches vs head per mini-batch
+    run_tests $tag tests
+    grep "fullsize\|cutmix iter" gpurun_out/parity_$tag.txt | grep -v " tf32 " | cut -c1-230
+    for v in 1 0; do
+      B200SEG_BATCH_HEAD=$v B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_head$v.txt bench_line ${tag}_head$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    B200SEG_PDL=1 B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 bench_line ${tag}_pdl1 --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    B200SEG_PDL=1 timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_graph.py tests/test_gpu_nets.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}_pdl1.log 2>&1; tail -3 gpurun_out/pytest_${tag}_pdl1.log | cut -c1-200
+    head -45 gpurun_out/shape_profile_${tag}_head1.txt
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
