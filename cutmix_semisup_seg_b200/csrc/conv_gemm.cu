@@ -51,18 +51,22 @@ struct ConvKArgs {
   int kblocks;
   int n_pass;
   int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
+  int reverse;               // 1: walk the tiles from the last to the first (alternating launch directions, see b2_conv_gemm)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
 };
 
 struct TileInfo {
   int n_idx, w0, h0, n0;
+  int m_idx;                  // index of the M tile (row of the fused column statistics)
   uint32_t tap_mask;
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const ConvKArgs& a, int tile) {
   TileInfo t;
+  if (a.reverse) tile = a.num_tiles - 1 - tile;
   t.n_idx = tile % a.n_tiles_n;
   int m = tile / a.n_tiles_n;
+  t.m_idx = m;
   const int wt = m % a.tiles_w; m /= a.tiles_w;
   const int ht = m % a.tiles_h;
   const int nt = m / a.tiles_h;
@@ -221,7 +225,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
-      const int stat_row = (tile / a.n_tiles_n) * 4 + ew;      // fused column statistics: (M tile, lane quarter)
+      const int stat_row = t.m_idx * 4 + ew;                   // fused column statistics: (M tile, lane quarter)
       epi::drain_tile(ep, taddr, a.block_n, t.n_idx * a.block_n, stg, rowpix, lane, eh, stat_row, 0u, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
         __syncwarp();
@@ -307,6 +311,13 @@ bool tc::pdl_enabled() {
   if (g_conv_pdl < 0) { const char* e = getenv("B200SEG_PDL"); g_conv_pdl = e ? atoi(e) : 0; }
   return g_conv_pdl > 0;
 }
+// Alternating tile directions (b2_debug_set(12, v) / environment B200SEG_ALT_DIR): consecutive fprop / dgrad launches walk their
+// tiles in opposite directions.  A layer's input is usually the tensor the previous launch has just written; the ~100 MB it wrote
+// last are still in the 126 MB L2, so the consumer starts where the producer stopped instead of at the other end of the tensor
+// (whose L2 lines the producer itself has long evicted).  Results do not depend on the tile order.
+int g_conv_alt_dir = -1;
+int g_conv_next_reverse = 0;      // direction of the launch being prepared (set by b2_conv_gemm)
+static int g_conv_dir_state = 0;
 int g_conv_tap_outer = 0;         // b2_debug_set(7, 1): producer loops tap-outer / K-block-inner (the round-1 order)
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
@@ -329,6 +340,9 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
                (!p->stats_sub || (p->ld_stats_sub % 4 == 0 && al16(p->stats_sub))),
                "b2_conv_gemm: fused statistics need a gate, no accumulate, and 16 B aligned / 4-float-padded operands");
   }
+  if (g_conv_alt_dir < 0) { const char* e = getenv("B200SEG_ALT_DIR"); g_conv_alt_dir = e ? atoi(e) : 0; }
+  g_conv_next_reverse = 0;
+  if (g_conv_alt_dir > 0) { g_conv_next_reverse = g_conv_dir_state; g_conv_dir_state ^= 1; }
   // N tiles of 256 output channels run on CTA pairs (tcgen05 cta_group::2): see conv_gemm2.cu
   if (p->nb > 224 && !g_conv_force_1cta && b2_sm_count_cached() >= 2 && (p->max_ctas == 0 || p->max_ctas >= 2))
     return b2_conv_gemm_2cta(p, stream);
@@ -355,6 +369,7 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
   a.tap_outer = g_conv_tap_outer;
+  a.reverse = g_conv_next_reverse;
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;

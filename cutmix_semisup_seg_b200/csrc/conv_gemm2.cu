@@ -59,6 +59,7 @@ struct Conv2KArgs {
   int kblocks;
   int n_pass;
   int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
+  int reverse;               // 1: walk the tiles from the last to the first (alternating launch directions, conv_gemm.cu)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
   epi2::Geo tma;              // TMA epilogue (conv_epilogue_tma.cuh; PF build only)
   long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
@@ -66,10 +67,11 @@ struct Conv2KArgs {
 
 struct TileInfo {
   int n_idx, w0, h0, n0;
+  int m_idx;                  // index of this CTA's M tile (row of the fused column statistics)
   uint32_t tap_mask;
 };
 
-__device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, int m) {
+__host__ __device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, int m) {
   const int wt = m % a.tiles_w; m /= a.tiles_w;
   const int ht = m % a.tiles_h;
   if (m / a.tiles_h >= a.tiles_n) return 0;       // phantom tile of an odd tile count
@@ -85,12 +87,14 @@ __device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, int m) {
 
 // `pair` indexes (pair of adjacent M tiles, N tile), N fastest; `half` selects this CTA's M tile.  The tap mask is the
 // union over both halves: the two producers and the single MMA issuer must walk the same K sequence.
-__device__ __forceinline__ TileInfo decode_tile(const Conv2KArgs& a, int pair, int half) {
+__host__ __device__ __forceinline__ TileInfo decode_tile(const Conv2KArgs& a, int pair, int half) {
   TileInfo t;
+  if (a.reverse) pair = a.num_pairs - 1 - pair;
   t.n_idx = pair % a.n_tiles_n;
   const int mp = pair / a.n_tiles_n;
   const uint32_t both = tile_tap_mask(a, mp * 2) | tile_tap_mask(a, mp * 2 + 1);
   int m = mp * 2 + half;
+  t.m_idx = m;
   const int wt = m % a.tiles_w; m /= a.tiles_w;
   const int ht = m % a.tiles_h;
   const int nt = m / a.tiles_h;                   // == tiles_n for the phantom tile: every pixel out of range
@@ -322,7 +326,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      const int m_idx = (pair / a.n_tiles_n) * 2 + (int)rank;
+      const int m_idx = t.m_idx;
       const int stat_row = m_idx < a.tiles_w * a.tiles_h * a.tiles_n ? m_idx * 4 + ew : -1;   // phantom tile: none
       epi2::drain_tile(ep, &tmD, &tmAdd, &tmGate, ws, taddr, BLOCK_N, t.n_idx * BLOCK_N, q, have_next, tn.n_idx * BLOCK_N, qn,
                        lane, eh, stat_row, [&]() {
@@ -373,7 +377,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc::tc_fence_after();
       if (tracer && tr_e < 510) a.trace[1536 + tr_e++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      const int m_idx = (pair / a.n_tiles_n) * 2 + (int)rank;
+      const int m_idx = t.m_idx;
       const int stat_row = m_idx < a.tiles_w * a.tiles_h * a.tiles_n ? m_idx * 4 + ew : -1;   // phantom tile: none
       epi::drain_tile(ep, taddr, BLOCK_N, t.n_idx * BLOCK_N, stg, rowpix, lane, eh, stat_row, pf_slot, [&]() {
         tc::tc_fence_before();           // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -394,6 +398,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // choose_box is defined in conv_gemm.cu
 extern int g_conv_epi_debug;
 extern int g_conv_tap_outer;
+extern int g_conv_next_reverse;
 // PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never).  Measured on B200
 // (profiles/r01_v7_pf_microbench.log): faster up to K = 512 (HBM-bound 1x1 layers, 0.231 -> 0.163 ms for 256 -> 1024 with
 // addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
@@ -407,8 +412,8 @@ static long long* g_conv_trace = nullptr;
 extern "C" void b2_debug_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); }
 void b2_choose_box(int ow, int oh, int n, int max_rows, int istride, int* bw_o, int* bh_o, int* bn_o);
 
-int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
-  Conv2KArgs a;
+// Tile geometry of a launch (everything the tile walk of the three pipeline roles depends on).
+static int conv2_geometry(const b2_conv_params* p, Conv2KArgs& a) {
   memset(&a, 0, sizeof(a));
   a.n = p->n; a.ih = p->ih; a.iw = p->iw; a.k = p->k; a.nb = p->nb; a.oh = p->oh; a.ow = p->ow;
   a.fh = p->fh; a.fw = p->fw; a.ldd = p->ldd; a.ostride = p->ostride; a.ooh = p->ooh; a.oow = p->oow;
@@ -426,7 +431,43 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
+  return B2_OK;
+}
+
+// Host-only description of the launch the CTA-pair kernel would run for `p` on `sms` SMs (no GPU, pointers are not dereferenced):
+// out = int64[8] {bw, bh, bn, tile pairs, pipeline stages of the whole launch (padding-only taps skipped), stages of the busiest
+// CTA pair, CTA pairs, K steps of 8 per stage}.  One stage = BLOCK_K / 8 tcgen05.mma M256 x N256 x K8 instructions of 128 tensor-pipe
+// cycles each (2048 tf32 MAC per clock and SM), so   tensor-pipe busy cycles per SM = stages of its CTA pair x 512:
+// divided by a profiler's sm__cycles_elapsed this is the kernel's tensor-pipe occupancy (tools/tensor_busy.py).
+extern "C" int b2_conv_gemm_plan(const b2_conv_params* p, int sms, int64_t* out) {
+  B2_REQUIRE(p && out && p->taps && p->n_taps >= 1 && p->n_taps <= MAX_TAPS && p->n > 0 && p->oh > 0 && p->ow > 0 && p->k > 0 &&
+             p->nb > 0 && p->istride >= 1 && sms >= 2, "b2_conv_gemm_plan: bad args");
+  Conv2KArgs a;
+  int rc = conv2_geometry(p, a); if (rc) return rc;
+  int clusters = sms / 2;
+  if (clusters > a.num_pairs) clusters = a.num_pairs;
+  int64_t total = 0, worst = 0;
+  for (int c = 0; c < clusters; ++c) {
+    int64_t mine = 0;
+    for (int pair = c; pair < a.num_pairs; pair += clusters) {
+      const TileInfo t = decode_tile(a, pair, 0);
+      int taps = 0;
+      for (int i = 0; i < a.n_taps; ++i) taps += (int)(t.tap_mask >> i & 1u);
+      mine += (int64_t)taps * a.kblocks * (a.n_pass > 0 ? a.n_pass : 1);
+    }
+    total += mine;
+    if (mine > worst) worst = mine;
+  }
+  out[0] = a.bw; out[1] = a.bh; out[2] = a.bn; out[3] = a.num_pairs; out[4] = total; out[5] = worst; out[6] = clusters;
+  out[7] = BLOCK_K / 8;
+  return B2_OK;
+}
+
+int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
+  Conv2KArgs a;
+  { int rc = conv2_geometry(p, a); if (rc) return rc; }
   a.tap_outer = g_conv_tap_outer;
+  a.reverse = g_conv_next_reverse;
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;

@@ -8,6 +8,7 @@
 // TMA boxes of (32 channels x 32 pixels) land in smem exactly as the canonical MN-major 128B-swizzle (32 B atom)
 // atoms the tensor core reads; no transposes anywhere.  K is split over CTAs (pixel ranges) and the
 // partial slabs are reduced in a fixed order by a second kernel => deterministic gradients.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -38,6 +39,7 @@ struct WgradKArgs {
   int wlo[W_MAX_TAPS], whi[W_MAX_TAPS], hlo[W_MAX_TAPS], hhi[W_MAX_TAPS];
   int tw;
   int out_tiles, n_splits, num_units;
+  int tap_step;              // split s works on tap (t + s * tap_step) % n_taps: see balance_units
   int n_pass;
   float* out;                // dW (n_splits == 1) or workspace slabs
   int64_t slab_elems;
@@ -59,7 +61,7 @@ __host__ __device__ __forceinline__ UnitInfo decode_unit(const WgradKArgs& a, in
   r.split = u / a.out_tiles;
   int t = ot;
   const int ct = t % a.c_tiles; t /= a.c_tiles;
-  r.tap = t % a.n_taps;
+  r.tap = (t % a.n_taps + r.split * a.tap_step) % a.n_taps;
   const int mt = t / a.n_taps;
   r.m0 = mt * a.m_tile_rows; r.c0 = ct * a.block_n;
   r.pb_begin = (int)(((int64_t)a.num_pb * r.split) / a.n_splits);
@@ -322,10 +324,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 // Protocol as in conv_gemm2.cu (leader = cluster rank 0 issues the MMAs; TMA loads of both CTAs complete on the leader's
 // full barrier; tcgen05.commit multicasts to both CTAs; both epilogues arrive on the leader's accumulator-empty barrier).
 // Requirements (host-checked, else the single-CTA kernel runs): M % 256 == 0, C % 64 == 0 (5-D TMA for both operands).
-constexpr int W2_STAGES = 6;
+constexpr int W2_STAGES_DEFAULT = 6;
+constexpr int W2_STAGES_DEEP = 7;                                                 // b2_debug_set(13, 7): A/B of the operand ring depth
 constexpr int W2_A_STAGE_BYTES = (W_BLOCK_M / 32) * W_SLOT_BYTES;              // 16 KB: this CTA's 128 output channels
 constexpr int W2_B_STAGE_BYTES = (W_MAX_BLOCK_N / 64) * W_SLOT_BYTES;          // 16 KB: this CTA's half of the N tile
-constexpr int W2_SMEM_BYTES = W2_STAGES * (W2_A_STAGE_BYTES + W2_B_STAGE_BYTES) + 1024 + 256;
+constexpr int w2_smem_bytes(int stages) { return stages * (W2_A_STAGE_BYTES + W2_B_STAGE_BYTES) + 1024 + 256; }
+static_assert(w2_smem_bytes(W2_STAGES_DEEP) <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t w2_cluster_ctarank() {
   uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
@@ -361,6 +365,7 @@ __device__ __forceinline__ void w2_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+template <int W2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W_THREADS, 1)
 conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmY5, const __grid_constant__ CUtensorMap tmY5lo,
                    const __grid_constant__ CUtensorMap tmX5, const __grid_constant__ CUtensorMap tmX5lo,
@@ -542,6 +547,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int n_split
 int g_wgrad_desc_variant = 0;
 int g_wgrad_dbg = 0;              // b2_debug_set(6, v)
 int g_wgrad_force_1cta = 0;       // b2_debug_set(5, 1): always the single-CTA kernel
+int g_wgrad2_stages = -1;         // b2_debug_set(13, 6 | 7) / environment B200SEG_WGRAD_STAGES: operand ring depth of the CTA-pair kernel
 
 struct WPlan {
   WgradKArgs a;
@@ -563,6 +569,75 @@ void choose_kbox(int ow, int oh, int n, int istride, int* bw_o, int* bh_o, int* 
         if (score > best) { best = score; bbw = bw; bbh = bh; bbn = bn; bk = kp; }
       }
   *bw_o = bbw; *bh_o = bbh; *bn_o = bbn; *kpix_o = bk;
+}
+
+// Load balance of dilated layers.  A work unit is (output tile, tap, pixel range); pixel boxes whose input lies in the padding are
+// skipped, so the units of an off-centre tap are shorter than those of the centre tap (ASPP, 64 x 64 map: dilation 12 skips 19 %
+// of the boxes of six taps, dilation 36 up to 78 %).  With 72 units on 74 CTA pairs every pair owns ONE unit and the launch lasts
+// as long as the centre tap (4096 stages) although the mean unit is 3487 / 2989 / 1661 stages (d = 12 / 24 / 36).  More pixel
+// splits give every pair several units, and rotating the tap by `tap_step` from split to split makes them units of DIFFERENT
+// taps.  The pair (splits, tap_step) minimising  [stages of the busiest worker + cost of the extra slabs]  is searched once per
+// geometry (closed-form stage counts, a few thousand integer evaluations) and cached.  b2_debug_set(14, 0) disables it.
+int g_wgrad_balance = 1;
+struct BalanceKey {
+  int n, oh, ow, ih, iw, istride, m_tiles, c_tiles, n_taps, workers, base_splits, bw, bh, bn;
+  short dh[W_MAX_TAPS], dw[W_MAX_TAPS];
+  int64_t slab_elems;
+};
+struct BalanceEntry { BalanceKey key; int splits, tap_step; };
+static int64_t busiest_worker(WgradKArgs& a, int workers, int64_t* total) {
+  int64_t load[1024];
+  const int w = workers < 1024 ? workers : 1024;
+  for (int i = 0; i < w; ++i) load[i] = 0;
+  int64_t sum = 0;
+  for (int u = 0; u < a.num_units; ++u) {
+    const int64_t b = unit_boxes(a, decode_unit(a, u));
+    load[u % w] += b; sum += b;
+  }
+  int64_t worst = 0;
+  for (int i = 0; i < w; ++i) if (load[i] > worst) worst = load[i];
+  if (total) *total = sum;
+  return worst;
+}
+static void balance_units(WgradKArgs& a, int workers, int max_splits) {
+  if (a.n_taps < 2 || workers < 1) return;
+  static thread_local BalanceEntry cache[64];
+  static thread_local int n_cached = 0;
+  BalanceKey key;
+  memset(&key, 0, sizeof(key));
+  key.n = a.n; key.oh = a.oh; key.ow = a.ow; key.ih = a.ih; key.iw = a.iw; key.istride = a.istride; key.m_tiles = a.m_tiles;
+  key.c_tiles = a.c_tiles; key.n_taps = a.n_taps; key.workers = workers; key.base_splits = a.n_splits; key.bw = a.bw; key.bh = a.bh;
+  key.bn = a.bn; key.slab_elems = a.slab_elems;
+  for (int i = 0; i < a.n_taps; ++i) { key.dh[i] = a.dh[i]; key.dw[i] = a.dw[i]; }
+  for (int i = 0; i < n_cached; ++i)
+    if (memcmp(&cache[i].key, &key, sizeof(key)) == 0) {
+      a.n_splits = cache[i].splits; a.tap_step = cache[i].tap_step; a.num_units = a.out_tiles * a.n_splits;
+      return;
+    }
+  const int base = a.n_splits;
+  int64_t total = 0;
+  const int64_t worst0 = busiest_worker(a, workers, &total);
+  int best_s = base, best_step = 0;
+  // one pipeline stage ~ 0.35 us (512 tensor cycles); a slab costs a write by the kernel and a read by the reduction (~5 TB/s)
+  const double slab_stages = 2.0 * (double)a.slab_elems * 4.0 / 5.0e12 / 0.35e-6;
+  auto cost = [&](int64_t worst, int s) { return (double)worst + (s > 1 ? slab_stages * s : 0.0); };
+  double best = cost(worst0, base);
+  const int64_t mean = total / (workers < a.num_units ? workers : a.num_units);
+  if (worst0 * 100 > mean * 105) {              // otherwise already balanced within 5 %
+    static const int mult[] = {1, 2, 3, 4, 5, 6, 8, 9};
+    for (int mi = 0; mi < 8; ++mi) {
+      const int sp = base * mult[mi];
+      if (sp > max_splits || sp > 32 || (int64_t)a.out_tiles * sp > 16384) continue;
+      for (int step = 0; step < a.n_taps; ++step) {
+        if (sp == base && step == 0) continue;
+        a.n_splits = sp; a.tap_step = step; a.num_units = a.out_tiles * sp;
+        const double c = cost(busiest_worker(a, workers, nullptr), sp);
+        if (c < best * 0.97) { best = c; best_s = sp; best_step = step; }      // change the plan only for a real gain
+      }
+    }
+  }
+  a.n_splits = best_s; a.tap_step = best_step; a.num_units = a.out_tiles * best_s;
+  if (n_cached < 64) { cache[n_cached].key = key; cache[n_cached].splits = best_s; cache[n_cached].tap_step = best_step; ++n_cached; }
 }
 
 int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
@@ -636,6 +711,7 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   a.num_units = a.out_tiles * splits;
   a.n_pass = p->n_split;
   a.slab_elems = (int64_t)p->m * p->tw * p->c;
+  if (p->kchunk == 0 && g_wgrad_balance != 0) balance_units(a, sms, max_splits);
   a.accumulate = p->accumulate;
   a.desc_variant = g_wgrad_desc_variant;
   a.dbg = g_wgrad_dbg;
@@ -653,8 +729,12 @@ extern int g_conv_tap_outer;
 extern int g_conv_tma_epi;
 extern int g_conv_main_stages;
 extern int g_conv_pdl;
+extern int g_conv_alt_dir;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 11) g_conv_pdl = value;
+  if (key == 12) g_conv_alt_dir = value;
+  if (key == 13) g_wgrad2_stages = value;
+  if (key == 14) g_wgrad_balance = value;
   if (key == 5) g_wgrad_force_1cta = value;
   if (key == 6) g_wgrad_dbg = value;
   if (key == 1) g_wgrad_desc_variant = value;
@@ -694,6 +774,24 @@ extern "C" int b2_conv_wgrad_plan_check(const b2_wgrad_params* p, int64_t* out) 
     stages += (int64_t)walked * a.n_pass;
   }
   out[0] = a.n_splits; out[1] = a.num_units; out[2] = stages; out[3] = bad; out[4] = a.m_tile_rows == 2 * W_BLOCK_M;
+  return B2_OK;
+}
+
+// Host-only view of the load balance of the plan: out = int64[5] {pixel splits, tap rotation per split, pipeline stages of the
+// busiest worker (CTA or CTA pair), pipeline stages of the whole launch, workers}.
+extern "C" int b2_conv_wgrad_plan_balance(const b2_wgrad_params* p, int64_t* out) {
+  B2_REQUIRE(out, "b2_conv_wgrad_plan_balance: null output");
+  WgradKArgs a;
+  int rc = plan_wgrad(p, &a);
+  if (rc) return rc;
+  int workers = b2_sm_count_cached();
+  if (workers <= 0) workers = 148;
+  if (p->max_ctas > 0 && p->max_ctas < workers) workers = p->max_ctas;
+  if (a.m_tile_rows == 2 * W_BLOCK_M) workers /= 2;
+  if (workers > a.num_units) workers = a.num_units;
+  int64_t total = 0;
+  const int64_t worst = busiest_worker(a, workers, &total);
+  out[0] = a.n_splits; out[1] = a.tap_step; out[2] = worst * a.n_pass; out[3] = total * a.n_pass; out[4] = workers;
   return B2_OK;
 }
 
@@ -757,7 +855,8 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
-    B2_CUDA(cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(conv_wgrad2_kernel<W2_STAGES_DEFAULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2_smem_bytes(W2_STAGES_DEFAULT)));
+    B2_CUDA(cudaFuncSetAttribute(conv_wgrad2_kernel<W2_STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2_smem_bytes(W2_STAGES_DEEP)));
     attr_set = true;
   }
   if (a.m_tile_rows == 2 * W_BLOCK_M) {
@@ -784,7 +883,11 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_params* p, void* stream) {
     if (clusters <= 0) return b2_fail(B2_ERR_CUDA, "b2_conv_wgrad: no CUDA device");
     if (p->max_ctas > 0 && p->max_ctas / 2 < clusters) clusters = p->max_ctas / 2 > 0 ? p->max_ctas / 2 : 1;
     if (clusters > a.num_units) clusters = a.num_units;
-    tc::launch(conv_wgrad2_kernel, clusters * 2, W_THREADS, W2_SMEM_BYTES, s, y5, y5lo, x5, x5lo, a);
+    if (g_wgrad2_stages < 0) { const char* e = getenv("B200SEG_WGRAD_STAGES"); g_wgrad2_stages = e ? atoi(e) : W2_STAGES_DEFAULT; }
+    if (g_wgrad2_stages == W2_STAGES_DEEP)
+      tc::launch(conv_wgrad2_kernel<W2_STAGES_DEEP>, clusters * 2, W_THREADS, w2_smem_bytes(W2_STAGES_DEEP), s, y5, y5lo, x5, x5lo, a);
+    else
+      tc::launch(conv_wgrad2_kernel<W2_STAGES_DEFAULT>, clusters * 2, W_THREADS, w2_smem_bytes(W2_STAGES_DEFAULT), s, y5, y5lo, x5, x5lo, a);
     B2_LAUNCH_CHECK("conv_wgrad2_kernel");
     if (a.n_splits > 1) {
       const int64_t elems = (int64_t)p->m * p->tw * p->c;

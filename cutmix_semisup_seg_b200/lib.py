@@ -107,9 +107,11 @@ _SIGS = {
     'b2_scale_inplace': (c_int, [c_vp, c_i64, c_vp, c_f32, c_vp]),
     'b2_conv_gemm': (c_int, [ctypes.POINTER(ConvParams), c_vp]),
     'b2_conv_stats_rows': (c_i64, [ctypes.POINTER(ConvParams)]),
+    'b2_conv_gemm_plan': (c_int, [ctypes.POINTER(ConvParams), c_int, c_vp]),
     'b2_conv_wgrad_workspace': (c_sz, [ctypes.POINTER(WgradParams)]),
     'b2_conv_wgrad': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_conv_wgrad_plan_check': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
+    'b2_conv_wgrad_plan_balance': (c_int, [ctypes.POINTER(WgradParams), c_vp]),
     'b2_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b2_transpose_w': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b2_bn_fold_multi': (c_int, [c_vp, c_int, c_int, c_vp]),

@@ -351,6 +351,12 @@ typedef struct b2_conv_params {
 } b2_conv_params;
 int b2_conv_gemm(const b2_conv_params* p, void* stream);
 int64_t b2_conv_stats_rows(const b2_conv_params* p);
+/* Host-only description of the launch the CTA-pair kernel (output-channel tiles of 256) runs for `p` on `sms` SMs; no GPU, the
+ * tensor pointers are not dereferenced.  out = int64[8] {bw, bh, bn (pixel box of an M tile), tile pairs, pipeline stages of the
+ * whole launch with padding-only taps skipped, stages of the busiest CTA pair, CTA pairs, tcgen05.mma instructions per stage}.
+ * A stage keeps the tensor pipe of both SMs of a pair busy for instructions x 128 cycles (kind::tf32, M256 x N256 x K8), so
+ * stages x 512 / sm__cycles_elapsed is the launch's tensor-pipe occupancy (tools/tensor_busy.py). */
+int b2_conv_gemm_plan(const b2_conv_params* p, int32_t sms, int64_t* out);
 
 /* wgrad:  dW[m, tap, c] (+)= sum_pix dY[pix, m] * X[pix@tap, c]
  *   dY: NHWC (N, OH, OW, M) ld = ldy;  X: NHWC (N, IH, IW, C) ld = ldx;  dW: (M, T, C) fp32.
@@ -376,13 +382,23 @@ int b2_conv_wgrad(const b2_wgrad_params* p, void* stream);
 /* Host-only self check of the launch plan (no GPU, pointers are not dereferenced): out = int64[5] {splits, work units,
  * pipeline stages, units whose two stage counts (producer walk vs closed form of the MMA issuer) disagree, CTA-pair kernel}. */
 int b2_conv_wgrad_plan_check(const b2_wgrad_params* p, int64_t* out);
+/* Host-only view of the plan's load balance: out = int64[5] {pixel splits, tap rotation per split, pipeline stages of the busiest
+ * worker (CTA or CTA pair), pipeline stages of the whole launch, workers}.  Dilated layers skip the pixel boxes whose input lies
+ * in the padding, so the units of different taps differ in length; the planner picks more pixel splits and rotates the tap from
+ * split to split so that every worker gets a mix of taps (debug knob 14 = 0 turns that off). */
+int b2_conv_wgrad_plan_balance(const b2_wgrad_params* p, int64_t* out);
 
 /* Debug knobs (tests / timing experiments only): key 1 = wgrad smem-descriptor variant; 2 = 1 forces the single-CTA conv kernel;
  * 3 = epilogue timing bits; 4 = PF-build K limit; 5 = 1 forces the single-CTA wgrad kernel; 6 = wgrad timing bits;
  * 7 = 1 restores the tap-outer / K-block-inner producer order of the conv kernels (A/B timing of the L2 working set);
  * 8 = 0 disables the TMA epilogue of the CTA-pair conv kernel (register epilogue everywhere);
  * 10 = 5 selects the 5-stage build of the compute-bound CTA-pair kernel (default 6 stages; A/B timing);
- * 11 = programmatic dependent launch of the tensor-core kernels (1 on, 0 off; environment B200SEG_PDL). */
+ * 11 = programmatic dependent launch of the tensor-core kernels (1 on, 0 off; environment B200SEG_PDL);
+ * 12 = consecutive fprop / dgrad launches walk their tiles in alternating directions (L2 reuse of the tensor written last;
+ *      1 on, 0 off; environment B200SEG_ALT_DIR);
+ * 13 = operand ring depth of the CTA-pair weight-gradient kernel (6 or 7 stages; environment B200SEG_WGRAD_STAGES);
+ * 14 = 0 disables the load-balanced work decomposition of the weight-gradient kernel for dilated layers (more pixel splits,
+ *      taps rotated from split to split), 1 (default) enables it. */
 void b2_debug_set(int key, int value);
 /* Diagnostics: device buffer of 2048 int64 receiving clock64 stamps of CTA 0's pipeline roles in the 2-CTA conv
  * kernel ([0,512) producer stage issue, [512,1024) MMA stage acquired, [1024,1536) MMA tile begin/accumulator

@@ -279,6 +279,52 @@ def test_conv_dgrad_fused_bn_statistics(case):
     assert relerr(dgam2, ref_dgamma) < 1e-4 and relerr(dbet2, ref_dbeta) < 1e-4
 
 
+@pytest.mark.parametrize('case', [
+    # N, H, W, Cout(gemm K), Cin(gemm N), k, dil
+    (2, 12, 10, 48, 96, 3, 2),         # single-CTA kernel, ragged M tiles
+    (3, 17, 12, 64, 256, 1, 1),        # CTA-pair kernel (TMA epilogue), odd number of M tiles (phantom tile)
+    (2, 16, 16, 128, 512, 3, 1),       # CTA-pair kernel, two N tiles
+    (1, 64, 64, 64, 256, 3, 12),       # padding-only taps skipped per tile
+], ids=lambda c: 'x'.join(map(str, c)))
+def test_alternating_tile_direction_is_bit_identical(case):
+    """Debug knob 12 (B200SEG_ALT_DIR): consecutive fprop / dgrad launches walk their tiles in opposite directions (L2 reuse of
+    the tensor the previous launch wrote last).  The tile order must not change a single bit of the output or of the fused column
+    statistics (their rows are indexed by the M tile, not by the time a tile is processed)."""
+    from cutmix_semisup_seg_b200 import lib as L
+    from cutmix_semisup_seg_b200.kernels import ActKernels
+    from cutmix_semisup_seg_b200.acts import Act
+    N, H, W, Cout, Cin, k, dil = case
+    torch.manual_seed(sum(map(int, case)))
+    K = ActKernels(n_split=1)
+    pad = dil * (k // 2)
+    w = (torch.randn(Cout, k, k, Cin) / (Cin * k * k) ** 0.5).to(dev)
+    g = Act(torch.randn(N, H, W, Cout, device=dev), N, H, W, Cout)
+    partial = Act(torch.randn(N, H, W, Cin, device=dev), N, H, W, Cin)
+    yprev = Act(torch.randn(N, H, W, Cin, device=dev), N, H, W, Cin)
+    wt, ldb = K.transpose_w(w, Cout, k * k, Cin)
+    wf = (torch.randn(Cin, k, k, Cout) / (Cout * k * k) ** 0.5).to(dev)
+    scale = (torch.rand(Cin) + 0.5).to(dev); shift = torch.randn(Cin).to(dev)
+
+    def run():
+        dx = Act.alloc(N, H, W, Cin, dev)
+        st = K.conv_dgrad(g, wt, Cin, k, k, Cout, ldb, 1, pad, dil, dx, addend=partial, gate=yprev, want_stats=True)
+        y = Act.alloc(N, H, W, Cin, dev)
+        K.conv_fwd(g, wf, Cin, k, k, Cout, Cout, 1, pad, dil, y, scale=scale, shift=shift, addend=partial, relu=True)
+        return dx.base.clone(), st[0].clone(), y.base.clone()
+
+    lib = L.load()
+    ref = run()                                   # knob off: every launch ascending
+    lib.b2_debug_set(12, 1)
+    try:
+        a = run()                                 # dgrad ascending / fprop descending (or the other way round) ...
+        K.conv_fwd(g, wf, Cin, k, k, Cout, Cout, 1, pad, dil, Act.alloc(N, H, W, Cin, dev))   # ... one launch shifts the phase ...
+        b = run()                                 # ... so the second round runs each kernel in the other direction
+    finally:
+        lib.b2_debug_set(12, 0)
+    for r, x, y in zip(ref, a, b):
+        assert torch.equal(r, x) and torch.equal(r, y)
+
+
 def test_conv_fused_epilogue_and_concat_slice():
     """scale/shift + residual + ReLU epilogue writing into a channel slice of a wider buffer; dgrad with the
     fused addend + ReLU gate (the backward fusion the engine relies on)."""

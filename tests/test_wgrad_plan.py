@@ -110,3 +110,63 @@ def test_random_geometries_agree():
 def test_bad_arguments_are_reported_not_crashed():
     with pytest.raises(L.B2Error):
         _check(0, 8, 8, 64, 64, 3, 1, 1)
+
+
+def _balance(n, oh, ow, m, c, k, dil, pad, knob=1):
+    lib = L.load()
+    lib.b2_debug_set(14, knob)
+    try:
+        taps = _taps(k, dil, pad)
+        p = L.WgradParams()
+        fake = 0x10000
+        p.dy, p.x, p.dw = fake, fake, fake
+        p.n, p.oh, p.ow, p.m, p.ldy = n, oh, ow, m, (m + 3) // 4 * 4
+        p.ih, p.iw = oh, ow
+        p.c, p.ldx, p.istride = c, (c + 3) // 4 * 4, 1
+        p.n_taps, p.taps, p.tw = k * k, taps.ctypes.data, k * k
+        p.accumulate, p.n_split, p.max_ctas, p.kchunk = 0, 1, 0, 0
+        out = (ctypes.c_int64 * 5)()
+        L.call('b2_conv_wgrad_plan_balance', ctypes.byref(p), ctypes.cast(out, ctypes.c_void_p))
+        chk = (ctypes.c_int64 * 5)()
+        L.call('b2_conv_wgrad_plan_check', ctypes.byref(p), ctypes.cast(chk, ctypes.c_void_p))
+        assert chk[3] == 0 and chk[2] == out[3] and chk[0] == out[0]      # rotated units: producer walk == closed form, same totals
+        return dict(splits=out[0], tap_step=out[1], worst=out[2], total=out[3], workers=out[4])
+    finally:
+        lib.b2_debug_set(14, 1)
+
+
+@pytest.mark.parametrize('dil,min_gain', [(12, 1.08), (24, 1.2), (36, 1.8)])
+def test_dilated_weight_gradient_units_are_load_balanced(dil, min_gain):
+    """ASPP 3x3 weight gradients of the batched-head iteration (32 images, 64 x 64 map, 2048 -> 256): one unit per CTA pair made the
+    launch as long as the centre tap although the off-centre taps skip their padding boxes; the balanced plan (more pixel splits,
+    taps rotated from split to split) brings the busiest CTA pair close to the mean.  Total work is unchanged."""
+    old = _balance(32, 64, 64, 256, 2048, 3, dil, dil, knob=0)
+    new = _balance(32, 64, 64, 256, 2048, 3, dil, dil, knob=1)
+    assert old['splits'] == 1 and old['tap_step'] == 0 and old['worst'] == 32 * 64 * 64 // 32     # the centre tap: every box
+    assert new['total'] == old['total']
+    assert new['splits'] > 1 and old['worst'] / new['worst'] >= min_gain
+    assert new['worst'] * new['workers'] <= 1.25 * new['total']
+
+
+def test_undilated_weight_gradient_plans_are_unchanged():
+    for case in [(32, 64, 64, 256, 256, 3, 1, 1), (32, 64, 64, 1024, 256, 1, 1, 0), (32, 128, 128, 64, 64, 3, 1, 1)]:
+        assert _balance(*case, knob=1) == _balance(*case, knob=0)
+
+
+def test_conv_gemm_plan_of_the_aspp_launch():
+    """b2_conv_gemm_plan (host only): tile walk of the CTA-pair kernel on the ASPP 3x3 d12 launch of the batched-head iteration
+    (32 images, 64 x 64 map, 2048 -> 256) -- 512 tile pairs on 74 CTA pairs, 64 K blocks per tap, and only the top / bottom tile
+    rows skip the three taps that lie in the padding (tools/tensor_busy.py turns this into the tensor-pipe occupancy)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import tensor_busy
+    pl = tensor_busy.plan(32, 64, 64, 2048, 256, 3, 12)
+    assert pl['bw'] * pl['bh'] * pl['bn'] == 128 and pl['tile_pairs'] == 512 and pl['cta_pairs'] == 74 and pl['mma_per_stage'] == 4
+    dense = 512 * 9 * 64
+    assert 0.85 * dense < pl['stages_total'] < dense
+    assert pl['stages_busiest_pair'] <= 7 * 9 * 64 and pl['stages_busiest_pair'] * 74 >= pl['stages_total']
+    # dilation 36 on a 64 x 64 map: most off-centre taps of a tile lie in the padding
+    assert tensor_busy.plan(32, 64, 64, 2048, 256, 3, 36)['stages_total'] < 0.75 * dense
+    # a 1 x 1 layer has nothing to skip
+    pl1 = tensor_busy.plan(32, 64, 64, 1024, 256, 1, 1)
+    assert pl1['stages_total'] == 512 * 32

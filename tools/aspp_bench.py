@@ -54,6 +54,27 @@ if __name__ == '__main__':
         print('debug knob 10 (operand stages of the main build) =', os.environ['B200SEG_MAIN_STAGES'])
     if which in ('all', 'aspp'):
         conv_case(16, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N16')
+    if which == 'aspp32':      # the launch shapes of the iteration since the head runs once over both mini-batches (32 images)
+        conv_case(32, 64, 64, 2048, 256, 3, 12, 'ASPP 3x3 d12 2048->256 @64x64 N32')
+    if which == 'wg':          # weight-gradient A/B: load-balanced plan (knob 14) x operand ring depth (knob 13) on the head / trunk shapes
+        from cutmix_semisup_seg_b200 import lib as _lib2
+        L2 = _lib2.load()
+        for bal in (0, 1):
+            for st in (6, 7):
+                L2.b2_debug_set(14, bal); L2.b2_debug_set(13, st)
+                print('--- balance knob 14 = {}, wgrad ring depth (knob 13) = {}'.format(bal, st), flush=True)
+                for (n, h, w, cin, cout, k, dil, name) in ((32, 64, 64, 2048, 256, 3, 12, 'ASPP d12 N32'), (32, 64, 64, 2048, 256, 3, 24, 'ASPP d24 N32'),
+                                                           (32, 64, 64, 2048, 256, 3, 36, 'ASPP d36 N32'), (32, 64, 64, 256, 256, 3, 2, 'layer3 3x3 N32'),
+                                                           (32, 64, 64, 512, 512, 3, 4, 'layer4 3x3 N32'), (32, 64, 64, 256, 1024, 1, 1, 'layer3 1x1 256->1024 N32')):
+                    pad = dil * (k // 2)
+                    x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+                    g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+                    dw = torch.zeros(cout, k * k, cin, device=dev)
+                    timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), 2.0 * n * h * w * cin * cout * k * k, name + ' wgrad')
+                    del x, g, dw
+        L2.b2_debug_set(14, 1); L2.b2_debug_set(13, 6)
+    if which == 'l3x3':        # the largest compute-bound group of the trunk
+        conv_case(32, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256 @64x64 N32')
     if which == 'l3':
         conv_case(16, 64, 64, 256, 1024, 1, 1, 'layer3 1x1 256->1024 @64x64 N16')
     if which == 'all':

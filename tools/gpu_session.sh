@@ -105,6 +105,30 @@ for l in sys.stdin:
     B200SEG_PDL=1 timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_graph.py tests/test_gpu_nets.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}_pdl1.log 2>&1; tail -3 gpurun_out/pytest_${tag}_pdl1.log | cut -c1-200
     head -45 gpurun_out/shape_profile_${tag}_head1.txt
     ;;
+  aspp32)     # ncu --set full of the ASPP 3x3 d12 kernels and of the layer3 3x3 at the launch shapes of the batched-head iteration (32 images)
+    timeout -s KILL 300 python tools/aspp_bench.py 5 aspp32 > gpurun_out/micro_${tag}_aspp32.log 2>&1; timeout -s KILL 300 python tools/aspp_bench.py 5 l3x3 >> gpurun_out/micro_${tag}_aspp32.log 2>&1; cat gpurun_out/micro_${tag}_aspp32.log | cut -c1-120
+    for w in aspp32 l3x3; do
+      timeout -s KILL 600 ncu --set full --import-source on --clock-control none -k regex:'conv_gemm2|conv_wgrad2' -c 6 -o gpurun_out/${w}_$tag -f python tools/aspp_bench.py 1 $w > gpurun_out/ncu_${w}_$tag.log 2>&1; echo "[ncu $w exit $?]" >> gpurun_out/ncu_${w}_$tag.log
+      python tools/ncu_summary.py gpurun_out/${w}_$tag.ncu-rep > gpurun_out/${w}_${tag}_summary.txt 2>&1
+      grep -E "tensor_cycles_active|time_duration|kernel:|dram__bytes_read.sum |lts__throughput|sm__cycles_elapsed.max.per_second|mem_tensor" gpurun_out/${w}_${tag}_summary.txt | head -60
+    done
+    ;;
+  altdir)     # alternating tile directions (knob 12): bit-exactness test, kernel / network tests with the knob on, bench A/B on one box
+    timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -p no:cacheprovider -k "alternating" > gpurun_out/pytest_${tag}_alt.log 2>&1; tail -3 gpurun_out/pytest_${tag}_alt.log | cut -c1-200
+    B200SEG_ALT_DIR=1 timeout -s KILL 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_graph.py tests/test_gpu_nets.py tests/test_gpu_fullsize.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}_alt1.log 2>&1; tail -3 gpurun_out/pytest_${tag}_alt1.log | cut -c1-200
+    for v in 1 0 1 0; do
+      B200SEG_ALT_DIR=$v B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_alt$v.txt bench_line ${tag}_alt$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    paste -d'|' <(head -30 gpurun_out/shape_profile_${tag}_alt1.txt | cut -c1-100) <(head -30 gpurun_out/shape_profile_${tag}_alt0.txt | cut -c60-100)
+    ;;
+  wgbal)      # load-balanced weight-gradient plan + ring depth A/B (micro), wgrad / network tests with the new plan, bench
+    timeout -s KILL 600 python tools/aspp_bench.py 5 wg > gpurun_out/micro_${tag}_wg.log 2>&1; cat gpurun_out/micro_${tag}_wg.log | cut -c1-110
+    timeout -s KILL 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_nets.py tests/test_gpu_graph.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    for st in 6 7; do
+      B200SEG_WGRAD_STAGES=$st B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_st$st.txt bench_line ${tag}_st$st --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    grep wgrad gpurun_out/shape_profile_${tag}_st6.txt | head -12
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
