@@ -579,6 +579,7 @@ void choose_kbox(int ow, int oh, int n, int istride, int* bw_o, int* bh_o, int* 
 // taps.  The pair (splits, tap_step) minimising  [stages of the busiest worker + cost of the extra slabs]  is searched once per
 // geometry (closed-form stage counts, a few thousand integer evaluations) and cached.  b2_debug_set(14, 0) disables it.
 int g_wgrad_balance = 1;
+int g_wgrad_force_splits = 0, g_wgrad_force_step = -1;     // b2_debug_set(15 / 16, v): experiments (pixel splits, tap rotation)
 struct BalanceKey {
   int n, oh, ow, ih, iw, istride, m_tiles, c_tiles, n_taps, workers, base_splits, bw, bh, bn;
   short dh[W_MAX_TAPS], dw[W_MAX_TAPS];
@@ -712,6 +713,10 @@ int plan_wgrad(const b2_wgrad_params* p, WgradKArgs* out) {
   a.n_pass = p->n_split;
   a.slab_elems = (int64_t)p->m * p->tw * p->c;
   if (p->kchunk == 0 && g_wgrad_balance != 0) balance_units(a, sms, max_splits);
+  if (p->kchunk == 0 && g_wgrad_force_splits > 0 && g_wgrad_force_splits <= max_splits) {
+    a.n_splits = g_wgrad_force_splits; a.num_units = a.out_tiles * a.n_splits;
+    a.tap_step = g_wgrad_force_step >= 0 ? g_wgrad_force_step % a.n_taps : 0;
+  }
   a.accumulate = p->accumulate;
   a.desc_variant = g_wgrad_desc_variant;
   a.dbg = g_wgrad_dbg;
@@ -735,6 +740,8 @@ extern "C" void b2_debug_set(int key, int value) {
   if (key == 12) g_conv_alt_dir = value;
   if (key == 13) g_wgrad2_stages = value;
   if (key == 14) g_wgrad_balance = value;
+  if (key == 15) g_wgrad_force_splits = value;
+  if (key == 16) g_wgrad_force_step = value;
   if (key == 5) g_wgrad_force_1cta = value;
   if (key == 6) g_wgrad_dbg = value;
   if (key == 1) g_wgrad_desc_variant = value;

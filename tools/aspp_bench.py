@@ -73,6 +73,20 @@ if __name__ == '__main__':
                     timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, pad, dil), 2.0 * n * h * w * cin * cout * k * k, name + ' wgrad')
                     del x, g, dw
         L2.b2_debug_set(14, 1); L2.b2_debug_set(13, 6)
+    if which == 'wgscan':      # scan of (pixel splits, tap rotation) for the ASPP weight gradients (debug knobs 15 / 16)
+        from cutmix_semisup_seg_b200 import lib as _lib3
+        L3 = _lib3.load()
+        for dil in (12, 24, 36):
+            n, h, w, cin, cout, k = 32, 64, 64, 2048, 256, 3
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            g = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            dw = torch.zeros(cout, k * k, cin, device=dev)
+            for sp, st in ((1, 0), (2, 0), (2, 3), (3, 3), (3, 1), (4, 0), (4, 2), (4, 1), (6, 1), (8, 0), (8, 1), (8, 2), (9, 1), (9, 4), (16, 0), (16, 1), (16, 5), (32, 1)):
+                L3.b2_debug_set(15, sp); L3.b2_debug_set(16, st)
+                timeit(lambda: K.conv_wgrad(g, x, dw, cout, k, k, cin, 1, dil, dil), 2.0 * n * h * w * cin * cout * k * k,
+                       'ASPP d{} N32 wgrad splits {} step {}'.format(dil, sp, st))
+            del x, g, dw
+        L3.b2_debug_set(15, 0); L3.b2_debug_set(16, -1)
     if which == 'l3x3':        # the largest compute-bound group of the trunk
         conv_case(32, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256 @64x64 N32')
     if which == 'l3':

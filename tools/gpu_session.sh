@@ -129,6 +129,20 @@ for l in sys.stdin:
     done
     grep wgrad gpurun_out/shape_profile_${tag}_st6.txt | head -12
     ;;
+  wgscan)     # (pixel splits, tap rotation) scan of the ASPP weight gradients + DRAM bytes of the d36 launch under the old / new plan
+    timeout -s KILL 600 python tools/aspp_bench.py 4 wgscan > gpurun_out/micro_${tag}_wgscan.log 2>&1; cat gpurun_out/micro_${tag}_wgscan.log | cut -c1-110
+    timeout -s KILL 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:conv_wgrad2 --csv --log-file gpurun_out/wgscan_dram_$tag.csv python tools/aspp_bench.py 1 wgscan > /dev/null 2>&1
+    python - <<PYEOF
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/wgscan_dram_$tag.csv')) if len(r)>10]
+h=rows[0]; im=h.index('Metric Name'); iv=h.index('Metric Value'); iid=h.index('ID')
+cur={}
+for r in rows[1:]:
+    cur.setdefault(r[iid],{})[r[im]]=r[iv]
+for k,v in list(cur.items())[:120:2]:
+    print(k, v)
+PYEOF
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
