@@ -52,6 +52,8 @@ struct ConvKArgs {
   int n_pass;
   int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
   int reverse;               // 1: walk the tiles from the last to the first (alternating launch directions, see b2_conv_gemm)
+  tc::FastDiv fd_w, fd_h, fd_nn;   // division by tiles_w, tiles_h, n_tiles_n (tc_common.cuh "cheap tile decoding")
+  tc::TapTables tt;
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
 };
 
@@ -64,18 +66,23 @@ struct TileInfo {
 __device__ __forceinline__ TileInfo decode_tile(const ConvKArgs& a, int tile) {
   TileInfo t;
   if (a.reverse) tile = a.num_tiles - 1 - tile;
-  t.n_idx = tile % a.n_tiles_n;
-  int m = tile / a.n_tiles_n;
+  const int m = (int)tc::fast_div((uint32_t)tile, a.fd_nn);
+  t.n_idx = tile - m * a.n_tiles_n;
   t.m_idx = m;
-  const int wt = m % a.tiles_w; m /= a.tiles_w;
-  const int ht = m % a.tiles_h;
-  const int nt = m / a.tiles_h;
+  const int q = (int)tc::fast_div((uint32_t)m, a.fd_w);
+  const int wt = m - q * a.tiles_w;
+  const int nt = (int)tc::fast_div((uint32_t)q, a.fd_h);
+  const int ht = q - nt * a.tiles_h;
   t.w0 = wt * a.bw; t.h0 = ht * a.bh; t.n0 = nt * a.bn;
   uint32_t mask = 0;
-  for (int i = 0; i < a.n_taps; ++i) {
-    const int lo_h = t.h0 * a.istride + a.dh[i], hi_h = lo_h + (a.bh - 1) * a.istride;
-    const int lo_w = t.w0 * a.istride + a.dw[i], hi_w = lo_w + (a.bw - 1) * a.istride;
-    if (hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw) mask |= 1u << i;
+  if (a.tt.on) {
+    mask = (uint32_t)a.tt.rows[ht] & (uint32_t)a.tt.cols[wt];
+  } else {
+    for (int i = 0; i < a.n_taps; ++i) {
+      const int lo_h = t.h0 * a.istride + a.dh[i], hi_h = lo_h + (a.bh - 1) * a.istride;
+      const int lo_w = t.w0 * a.istride + a.dw[i], hi_w = lo_w + (a.bw - 1) * a.istride;
+      if (hi_h >= 0 && lo_h < a.ih && hi_w >= 0 && lo_w < a.iw) mask |= 1u << i;
+    }
   }
   if (mask == 0) mask = 1;  // accumulator must still be written (all-zero contribution)
   t.tap_mask = mask;
@@ -318,6 +325,7 @@ bool tc::pdl_enabled() {
 int g_conv_alt_dir = -1;
 int g_conv_next_reverse = 0;      // direction of the launch being prepared (set by b2_conv_gemm)
 static int g_conv_dir_state = 0;
+int g_conv_tap_tables = 1;        // b2_debug_set(17, 0): per-tile tap masks by the loop over the taps instead of the host-built tables (A/B)
 int g_conv_tap_outer = 0;         // b2_debug_set(7, 1): producer loops tap-outer / K-block-inner (the round-1 order)
 
 extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
@@ -370,6 +378,27 @@ extern "C" int b2_conv_gemm(const b2_conv_params* p, void* stream) {
   a.n_pass = p->n_split;
   a.tap_outer = g_conv_tap_outer;
   a.reverse = g_conv_next_reverse;
+  a.fd_w = tc::make_fastdiv((uint32_t)a.tiles_w); a.fd_h = tc::make_fastdiv((uint32_t)a.tiles_h);
+  a.fd_nn = tc::make_fastdiv((uint32_t)a.n_tiles_n);
+  if (a.tiles_w <= tc::TAP_TABLE && a.tiles_h <= tc::TAP_TABLE && g_conv_tap_tables != 0) {
+    for (int ht = 0; ht < a.tiles_h; ++ht) {
+      uint32_t mk = 0;
+      for (int i = 0; i < a.n_taps; ++i) {
+        const int lo = ht * a.bh * a.istride + a.dh[i], hi = lo + (a.bh - 1) * a.istride;
+        if (hi >= 0 && lo < a.ih) mk |= 1u << i;
+      }
+      a.tt.rows[ht] = (uint16_t)mk;
+    }
+    for (int wt = 0; wt < a.tiles_w; ++wt) {
+      uint32_t mk = 0;
+      for (int i = 0; i < a.n_taps; ++i) {
+        const int lo = wt * a.bw * a.istride + a.dw[i], hi = lo + (a.bw - 1) * a.istride;
+        if (hi >= 0 && lo < a.iw) mk |= 1u << i;
+      }
+      a.tt.cols[wt] = (uint16_t)mk;
+    }
+    a.tt.on = 1;
+  }
   a.ep.d = p->d; a.ep.ldd = p->ldd; a.ep.nb = p->nb;
   a.ep.scale = p->scale; a.ep.shift = p->shift; a.ep.addend = p->addend; a.ep.gate = p->gate; a.ep.scale2 = p->scale2;
   a.ep.ld_add = p->ld_add; a.ep.ld_gate = p->ld_gate; a.ep.relu = p->relu; a.ep.accumulate = p->accumulate;

@@ -60,6 +60,8 @@ struct Conv2KArgs {
   int n_pass;
   int tap_outer;             // 0: K-block outer / tap inner (default, see the producer); 1: tap outer (debug knob 7)
   int reverse;               // 1: walk the tiles from the last to the first (alternating launch directions, conv_gemm.cu)
+  tc::FastDiv fd_w, fd_h, fd_nn;   // division by tiles_w, tiles_h, n_tiles_n (tc_common.cuh "cheap tile decoding")
+  tc::TapTables tt;
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
   epi2::Geo tma;              // TMA epilogue (conv_epilogue_tma.cuh; PF build only)
   long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
@@ -72,9 +74,12 @@ struct TileInfo {
 };
 
 __host__ __device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, int m) {
-  const int wt = m % a.tiles_w; m /= a.tiles_w;
-  const int ht = m % a.tiles_h;
-  if (m / a.tiles_h >= a.tiles_n) return 0;       // phantom tile of an odd tile count
+  const int q = (int)tc::fast_div((uint32_t)m, a.fd_w);
+  const int wt = m - q * a.tiles_w;
+  const int nt = (int)tc::fast_div((uint32_t)q, a.fd_h);
+  const int ht = q - nt * a.tiles_h;
+  if (nt >= a.tiles_n) return 0;       // phantom tile of an odd tile count
+  if (a.tt.on) return (uint32_t)a.tt.rows[ht] & (uint32_t)a.tt.cols[wt];
   const int w0 = wt * a.bw, h0 = ht * a.bh;
   uint32_t mask = 0;
   for (int i = 0; i < a.n_taps; ++i) {
@@ -90,14 +95,15 @@ __host__ __device__ __forceinline__ uint32_t tile_tap_mask(const Conv2KArgs& a, 
 __host__ __device__ __forceinline__ TileInfo decode_tile(const Conv2KArgs& a, int pair, int half) {
   TileInfo t;
   if (a.reverse) pair = a.num_pairs - 1 - pair;
-  t.n_idx = pair % a.n_tiles_n;
-  const int mp = pair / a.n_tiles_n;
+  const int mp = (int)tc::fast_div((uint32_t)pair, a.fd_nn);
+  t.n_idx = pair - mp * a.n_tiles_n;
   const uint32_t both = tile_tap_mask(a, mp * 2) | tile_tap_mask(a, mp * 2 + 1);
-  int m = mp * 2 + half;
+  const int m = mp * 2 + half;
   t.m_idx = m;
-  const int wt = m % a.tiles_w; m /= a.tiles_w;
-  const int ht = m % a.tiles_h;
-  const int nt = m / a.tiles_h;                   // == tiles_n for the phantom tile: every pixel out of range
+  const int q = (int)tc::fast_div((uint32_t)m, a.fd_w);
+  const int wt = m - q * a.tiles_w;
+  const int nt = (int)tc::fast_div((uint32_t)q, a.fd_h);      // == tiles_n for the phantom tile: every pixel out of range
+  const int ht = q - nt * a.tiles_h;
   t.w0 = wt * a.bw; t.h0 = ht * a.bh; t.n0 = nt * a.bn;
   t.tap_mask = both ? both : 1u;
   return t;
@@ -399,6 +405,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 extern int g_conv_epi_debug;
 extern int g_conv_tap_outer;
 extern int g_conv_next_reverse;
+extern int g_conv_tap_tables;
 // PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never).  Measured on B200
 // (profiles/r01_v7_pf_microbench.log): faster up to K = 512 (HBM-bound 1x1 layers, 0.231 -> 0.163 ms for 256 -> 1024 with
 // addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
@@ -431,6 +438,27 @@ static int conv2_geometry(const b2_conv_params* p, Conv2KArgs& a) {
   }
   a.kblocks = (p->k + BLOCK_K - 1) / BLOCK_K;
   a.n_pass = p->n_split;
+  a.fd_w = tc::make_fastdiv((uint32_t)a.tiles_w); a.fd_h = tc::make_fastdiv((uint32_t)a.tiles_h);
+  a.fd_nn = tc::make_fastdiv((uint32_t)a.n_tiles_n);
+  if (a.tiles_w <= tc::TAP_TABLE && a.tiles_h <= tc::TAP_TABLE && g_conv_tap_tables != 0) {
+    for (int ht = 0; ht < a.tiles_h; ++ht) {
+      uint32_t mk = 0;
+      for (int i = 0; i < a.n_taps; ++i) {
+        const int lo = ht * a.bh * a.istride + a.dh[i], hi = lo + (a.bh - 1) * a.istride;
+        if (hi >= 0 && lo < a.ih) mk |= 1u << i;
+      }
+      a.tt.rows[ht] = (uint16_t)mk;
+    }
+    for (int wt = 0; wt < a.tiles_w; ++wt) {
+      uint32_t mk = 0;
+      for (int i = 0; i < a.n_taps; ++i) {
+        const int lo = wt * a.bw * a.istride + a.dw[i], hi = lo + (a.bw - 1) * a.istride;
+        if (hi >= 0 && lo < a.iw) mk |= 1u << i;
+      }
+      a.tt.cols[wt] = (uint16_t)mk;
+    }
+    a.tt.on = 1;
+  }
   return B2_OK;
 }
 

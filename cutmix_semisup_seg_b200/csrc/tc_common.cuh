@@ -55,6 +55,36 @@ __device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one (
 }
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }   // provably warp-uniform
 
+// ---------------------------------------------------------------------------- cheap tile decoding
+// Every pipeline role decodes its next tile from a linear index; with plain `/` and `%` by launch parameters and a loop over the
+// taps this took ~600-800 SASS instructions per tile (three to five emulated 32-bit divisions with I2F / MUFU.RCP chains), i.e.
+// ~2.5 k cycles in which the MMA issuer issues nothing (clock64 trace: one ~2650-cycle gap per tile, profiles/r02_v16_*).
+// Division by a launch constant: q = umulhi(n, mul) >> shr with mul = ceil(2^(31 + ceil(log2 d)) / d), exact for 0 <= n < 2^31
+// (round-up multiplier method); d == 1 is encoded as mul == 0.
+struct FastDiv { uint32_t mul, shr; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.mul = 0; f.shr = 0;
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                       // ceil(log2 d)
+  const uint32_t pw = 31 + l;
+  f.mul = (uint32_t)((((uint64_t)1 << pw) + d - 1) / d);
+  f.shr = pw - 32;
+  return f;
+}
+__host__ __device__ __forceinline__ uint32_t fast_div(uint32_t n, FastDiv f) {
+  if (f.mul == 0) return n;
+#ifdef __CUDA_ARCH__
+  return __umulhi(n, f.mul) >> f.shr;
+#else
+  return (uint32_t)(((uint64_t)n * f.mul) >> 32) >> f.shr;
+#endif
+}
+// Which taps of a tile touch the image at all (the others lie in the padding and are skipped) depends on the tile's row and on
+// its column separately: bit i of rows[ht] & cols[wt] = tap i contributes.  Built on the host when both tile counts fit.
+constexpr int TAP_TABLE = 256;
+struct TapTables { uint16_t rows[TAP_TABLE], cols[TAP_TABLE]; int on; };
+
 // ---------------------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with the programmatic-stream-serialization attribute (tc::launch below) may start while its predecessor
 // in the stream is still running: its CTAs become resident as the predecessor's CTAs retire, run their prologue (barrier

@@ -9,7 +9,8 @@ import os
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'libb200seg.so')
+# B200SEG_LIB: another build of the same library (A/B timing of two builds on one box, tools/gpu_session.sh libab)
+LIB_PATH = os.environ.get('B200SEG_LIB') or os.path.join(_PKG_DIR, 'libb200seg.so')
 
 c_int = ctypes.c_int
 c_i32 = ctypes.c_int32

@@ -143,6 +143,14 @@ for k,v in list(cur.items())[:120:2]:
     print(k, v)
 PYEOF
     ;;
+  libab)      # A/B of two builds of the library on one box (cutmix_semisup_seg_b200/libb200seg_prev.so = the previous commit): tests on the new one, bench prev / new / prev / new
+    timeout -s KILL 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_nets.py tests/test_gpu_graph.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    for v in prev new prev new; do
+      lib=; [ $v = prev ] && lib=$PWD/cutmix_semisup_seg_b200/libb200seg_prev.so
+      B200SEG_LIB=$lib B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_$v.txt bench_line ${tag}_$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    paste -d'|' <(head -34 gpurun_out/shape_profile_${tag}_new.txt | cut -c1-100) <(head -34 gpurun_out/shape_profile_${tag}_prev.txt | cut -c60-100)
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
