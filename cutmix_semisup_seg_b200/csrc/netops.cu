@@ -701,6 +701,7 @@ extern "C" int b2_bilinear_bwd(const float* dy, float* dx, int n, int ih, int iw
 // MODE 1: (x, x*x)          BN statistics
 // MODE 2: (g, g*xhat)       BN backward, g = dy * gate(y) * drop, xhat = (x - mean) * rstd
 // MODE 3: (g, g*y)          frozen-BN parameter gradients (y = BN output proxy), g = dy gated by gate>0
+__device__ __forceinline__ float bn_affine(float x, float mean, float rstd, float gamma, float beta);
 constexpr int RED_ROWS_PER_CHUNK = 2048;
 // Rows per chunk for a (rows x c) reduction: 2048, halved (down to 256) until the grid has >= 4 blocks per SM -- with 2048 rows
 // per block a 65536 x 256 tensor gave 256 blocks = 1.7 per SM, too few bytes in flight to cover the HBM latency
@@ -717,6 +718,7 @@ struct RedArgs {
   const float* gate; int ldg;   // relu gate tensor (y > 0) or NULL
   const float* drop; float drop_scale;  // dropout mask laid out like dy (ld = lda) or NULL
   const float* mean; const float* rstd;
+  const float* gamma; const float* gate_beta;   // mode 2, gate_beta != NULL: gate = bn_affine(x) > 0 recomputed from x (no gate tensor)
   const float* sub; int lds;    // mode 3: o = b - sub (residual removed from the block output)
   int64_t rows; int c;
   int vec;                      // every pointer 16 B aligned and every ld / c a multiple of 4
@@ -734,10 +736,14 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
   const int64_t r0 = (int64_t)blockIdx.x * r.rpc;
   int64_t r1 = r0 + r.rpc; if (r1 > r.rows) r1 = r.rows;
   double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
-  float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1};
+  float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, gam[4] = {0, 0, 0, 0}, bet[4] = {0, 0, 0, 0};
+  const bool regate = MODE == 2 && r.gate_beta != nullptr;
   if (MODE == 2) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) if (ch0 + e < r.c) { mean[e] = r.mean[ch0 + e]; rstd[e] = r.rstd[ch0 + e]; }
+    for (int e = 0; e < 4; ++e) if (ch0 + e < r.c) {
+      mean[e] = r.mean[ch0 + e]; rstd[e] = r.rstd[ch0 + e];
+      if (regate) { gam[e] = r.gamma[ch0 + e]; bet[e] = r.gate_beta[ch0 + e]; }
+    }
   }
   if (MODE <= 1 && r.vec && ch0 + 3 < r.c) {
     // one tensor: four independent 16 B loads per thread in flight (rows rl, rl + 32, rl + 64, rl + 96 of a 128-row group)
@@ -773,7 +779,10 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
       } else {
         const float4 bq = __ldg(reinterpret_cast<const float4*>(r.b + row * r.ldb + ch0));
         float vb[4] = {bq.x, bq.y, bq.z, bq.w};
-        if (r.gate) {
+        if (regate) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (!(bn_affine(vb[e], mean[e], rstd[e], gam[e], bet[e]) > 0.f)) va[e] = 0.f;
+        } else if (r.gate) {
           const float4 g = __ldg(reinterpret_cast<const float4*>(r.gate + row * r.ldg + ch0));
           if (!(g.x > 0.f)) va[0] = 0.f; if (!(g.y > 0.f)) va[1] = 0.f; if (!(g.z > 0.f)) va[2] = 0.f; if (!(g.w > 0.f)) va[3] = 0.f;
         }
@@ -802,9 +811,10 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(RedArgs r, double* __re
         if (MODE == 0) { s0[e] += v; }
         else if (MODE == 1) { s0[e] += v; s1[e] += (double)v * (double)v; }
         else {
-          if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
-          if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
           float bv = __ldg(r.b + row * r.ldb + ch);
+          if (regate) { if (!(bn_affine(bv, mean[e], rstd[e], gam[e], bet[e]) > 0.f)) v = 0.f; }
+          else if (r.gate && !(__ldg(r.gate + row * r.ldg + ch) > 0.f)) v = 0.f;
+          if (r.drop) v *= __ldg(r.drop + row * r.lda + ch) * r.drop_scale;
           if (MODE == 3 && r.sub) bv -= __ldg(r.sub + row * r.lds + ch);
           const float o = MODE == 2 ? (bv - mean[e]) * rstd[e] : bv;
           s0[e] += v; s1[e] += (double)v * (double)o;
@@ -922,6 +932,12 @@ extern "C" int b2_bn_stats(const float* x, int64_t rows, int c, int ldx, float e
   return B2_OK;
 }
 
+// y = gamma * (rstd * (x - mean)) + beta with the roundings bn_apply_kernel has always had (subtract, multiply, fused
+// multiply-add); bn_bwd recomputes the sign of y from x with the SAME three instructions instead of reading y (gate_beta).
+__device__ __forceinline__ float bn_affine(float x, float mean, float rstd, float gamma, float beta) {
+  return __fmaf_rn(gamma, __fmul_rn(rstd, __fsub_rn(x, mean)), beta);
+}
+
 template <int V, typename I>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, int64_t rows, int c, int ldx,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       v[0] = x[row * ldx + ch]; m[0] = mean[ch]; r[0] = rstd[ch]; g[0] = gamma[ch]; b[0] = beta[ch];
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) v[e] = (v[e] - m[e]) * r[e] * g[e] + b[e];
+    for (int e = 0; e < V; ++e) v[e] = bn_affine(v[e], m[e], r[e], g[e], b[e]);
     if (res) {
       if (V == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(res + row * ldr + ch)); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
       else v[0] += res[row * ldr + ch];
@@ -983,7 +999,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict_
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         const float* __restrict__ gamma, int relu, const float* __restrict__ drop,
                                                         float drop_scale, const double* __restrict__ fin, float* __restrict__ dx, int lddx,
-                                                        float* __restrict__ g_out, int ldgo) {
+                                                        float* __restrict__ g_out, int ldgo, const float* __restrict__ gate_beta) {
   const int cg = c / V;
   const I total = (I)(rows * cg);
   const double inv_n = 1.0 / (double)rows;
@@ -993,16 +1009,17 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict_
     if (V == 4) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + ch)); g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
       const float4 qx = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch)); xv[0] = qx.x; xv[1] = qx.y; xv[2] = qx.z; xv[3] = qx.w;
-      if (relu) { const float4 qy = __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)); yv[0] = qy.x; yv[1] = qy.y; yv[2] = qy.z; yv[3] = qy.w; }
+      if (relu && !gate_beta) { const float4 qy = __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)); yv[0] = qy.x; yv[1] = qy.y; yv[2] = qy.z; yv[3] = qy.w; }
       if (drop) { const float4 qd = __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)); dv[0] = qd.x; dv[1] = qd.y; dv[2] = qd.z; dv[3] = qd.w; }
     } else {
       g[0] = dy[row * lddy + ch]; xv[0] = x[row * ldx + ch];
-      if (relu) yv[0] = y[row * ldy + ch];
+      if (relu && !gate_beta) yv[0] = y[row * ldy + ch];
       if (drop) dv[0] = drop[row * c + ch];
     }
     float o[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
+      if (relu && gate_beta) yv[e] = bn_affine(xv[e], mean[ch + e], rstd[ch + e], gamma[ch + e], gate_beta[ch + e]);
       if (relu && !(yv[e] > 0.f)) g[e] = 0.f;
       if (drop) g[e] *= dv[e] * drop_scale;
       const float xhat = (xv[e] - mean[ch + e]) * rstd[ch + e];
@@ -1028,23 +1045,27 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_rows_kernel(const float* __rest
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, int relu, const float* __restrict__ drop,
                                                              float drop_scale, const double* __restrict__ fin, float* __restrict__ dx, int lddx,
-                                                             float* __restrict__ g_out, int ldgo, int cg, int rpb) {
+                                                             float* __restrict__ g_out, int ldgo, int cg, int rpb,
+                                                             const float* __restrict__ gate_beta) {
   const int lc = threadIdx.x % cg, lr = threadIdx.x / cg;          // blockDim.x == cg * rpb
   const int ch = lc * 4;
   const double inv_n = 1.0 / (double)rows;
-  float mu[4], rs[4], ga[4], mdb[4], mdg[4];
+  float mu[4], rs[4], ga[4], mdb[4], mdg[4], be[4];
+  const bool regate = relu && gate_beta != nullptr;        // gate from x (bn_affine), y is not read
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    mu[e] = mean[ch + e]; rs[e] = rstd[ch + e]; ga[e] = gamma[ch + e];
+    mu[e] = mean[ch + e]; rs[e] = rstd[ch + e]; ga[e] = gamma[ch + e]; be[e] = regate ? gate_beta[ch + e] : 0.f;
     mdb[e] = (float)(fin[(ch + e) * 2] * inv_n); mdg[e] = (float)(fin[(ch + e) * 2 + 1] * inv_n);
   }
   const int64_t step = (int64_t)gridDim.x * rpb;
   auto one_row = [&](int64_t row, const float4 q, const float4 qx, const float4 qy, const float4 qd) {
     float g[4] = {q.x, q.y, q.z, q.w};
-    const float xv[4] = {qx.x, qx.y, qx.z, qx.w}, yv[4] = {qy.x, qy.y, qy.z, qy.w}, dv[4] = {qd.x, qd.y, qd.z, qd.w};
+    const float xv[4] = {qx.x, qx.y, qx.z, qx.w}, dv[4] = {qd.x, qd.y, qd.z, qd.w};
+    float yv[4] = {qy.x, qy.y, qy.z, qy.w};
     float o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      if (regate) yv[e] = bn_affine(xv[e], mu[e], rs[e], ga[e], be[e]);
       if (relu && !(yv[e] > 0.f)) g[e] = 0.f;
       if (drop) g[e] *= dv[e] * drop_scale;
       const float xhat = (xv[e] - mu[e]) * rs[e];
@@ -1061,8 +1082,8 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_rows_kernel(const float* __rest
     const float4 qb = __ldg(reinterpret_cast<const float4*>(dy + r2 * lddy + ch));
     const float4 xa = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch));
     const float4 xb = __ldg(reinterpret_cast<const float4*>(x + r2 * ldx + ch));
-    const float4 ya = relu ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
-    const float4 yb = relu ? __ldg(reinterpret_cast<const float4*>(y + r2 * ldy + ch)) : zero;
+    const float4 ya = (relu && !regate) ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
+    const float4 yb = (relu && !regate) ? __ldg(reinterpret_cast<const float4*>(y + r2 * ldy + ch)) : zero;
     const float4 da = drop ? __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)) : zero;
     const float4 db = drop ? __ldg(reinterpret_cast<const float4*>(drop + r2 * c + ch)) : zero;
     one_row(row, qa, xa, ya, da);
@@ -1071,7 +1092,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_rows_kernel(const float* __rest
   if (row < rows) {
     const float4 qa = __ldg(reinterpret_cast<const float4*>(dy + row * lddy + ch));
     const float4 xa = __ldg(reinterpret_cast<const float4*>(x + row * ldx + ch));
-    const float4 ya = relu ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
+    const float4 ya = (relu && !regate) ? __ldg(reinterpret_cast<const float4*>(y + row * ldy + ch)) : zero;
     const float4 da = drop ? __ldg(reinterpret_cast<const float4*>(drop + row * c + ch)) : zero;
     one_row(row, qa, xa, ya, da);
   }
@@ -1085,27 +1106,29 @@ __global__ void bn_param_out_kernel(const double* __restrict__ fin, int c, float
 extern "C" int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y, int ldy, int64_t rows, int c,
                          const float* mean, const float* rstd, const float* gamma, int relu, const float* dropmask, float drop_scale,
                          float* dx, int lddx, float* dgamma, float* dbeta, int accumulate_params, float* g_out, int ldgo,
-                         double* workspace, void* stream) {
+                         const float* gate_beta, double* workspace, void* stream) {
   B2_REQUIRE(dy && x && dx && mean && rstd && gamma && workspace && rows > 0 && c > 0, "b2_bn_bwd: bad args");
-  B2_REQUIRE(!relu || y, "b2_bn_bwd: relu gate needs y");
+  B2_REQUIRE(!relu || y || gate_beta, "b2_bn_bwd: relu gate needs y or gate_beta");
+  if (!relu) gate_beta = nullptr;
   B2_REQUIRE(!dropmask || lddy == c, "b2_bn_bwd: dropout mask requires dense dy");
-  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = x; r.ldb = ldx; r.gate = relu ? y : nullptr; r.ldg = ldy;
+  RedArgs r{}; r.a = dy; r.lda = lddy; r.b = x; r.ldb = ldx; r.gate = (relu && !gate_beta) ? y : nullptr; r.ldg = ldy;
+  r.gamma = gamma; r.gate_beta = gate_beta;
   r.drop = dropmask; r.drop_scale = drop_scale; r.mean = mean; r.rstd = rstd; r.rows = rows; r.c = c;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_col_reduce<2>(r, workspace, s); if (rc) return rc;
   double* fin = workspace + red_chunks(rows, c) * c * 2;
   launch_col_finalize(workspace, red_chunks(rows, c), c, fin, s);
   const bool vec = c % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && al16(dy) && al16(x) && al16(dx) &&
-                   (!relu || (ldy % 4 == 0 && al16(y))) && (!dropmask || al16(dropmask)) && (!g_out || (ldgo % 4 == 0 && al16(g_out)));
+                   (!relu || gate_beta || (ldy % 4 == 0 && al16(y))) && (!dropmask || al16(dropmask)) && (!g_out || (ldgo % 4 == 0 && al16(g_out)));
   const int64_t total = rows * (vec ? c / 4 : c);
   int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
   if (vec && c / 4 <= 256) {
     const int cg = c / 4, rpb = 256 / cg;
     int64_t nb = ceil_div64(rows, rpb); if (nb > 148 * 16) nb = 148 * 16;
-    bn_bwd_dx_rows_kernel<<<(unsigned)nb, cg * rpb, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, cg, rpb);
-  } else if (vec && total < (1ll << 31)) bn_bwd_dx_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
-  else if (vec) bn_bwd_dx_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
-  else bn_bwd_dx_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo);
+    bn_bwd_dx_rows_kernel<<<(unsigned)nb, cg * rpb, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, cg, rpb, gate_beta);
+  } else if (vec && total < (1ll << 31)) bn_bwd_dx_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, gate_beta);
+  else if (vec) bn_bwd_dx_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, gate_beta);
+  else bn_bwd_dx_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, s>>>(dy, lddy, x, ldx, y, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale, fin, dx, lddx, g_out, ldgo, gate_beta);
   bn_param_out_kernel<<<(c + 127) / 128, 128, 0, s>>>(fin, c, dgamma, dbeta, accumulate_params);
   B2_LAUNCH_CHECK("bn_bwd");
   return B2_OK;

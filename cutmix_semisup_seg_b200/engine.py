@@ -15,6 +15,7 @@ Gradient bookkeeping
   * The same epilogue that finishes the gradient of a frozen-BN layer's output also writes the column sums the
     BN affine parameters need (sum g, sum g*(y - residual)); the separate reduction pass over g and y is skipped.
 """
+import os
 import weakref
 
 import torch
@@ -477,6 +478,11 @@ class ConvNode(object):
         K.bn_eval_param_grad_wdot(st, g, w, dw, bn, dgam, dbet, acc)
 
 
+# train-mode BatchNorm backward without a residual recomputes its ReLU gate from the raw input instead of reading the stored
+# output (b2_bn_bwd gate_beta); B200SEG_BN_REGATE=0 reads y as before (A/B timing)
+REGATE = os.environ.get('B200SEG_BN_REGATE', '1') != '0'
+
+
 class BNTrainNode(object):
     """y = dropout( relu( bn_train(raw) [+ residual] ) ); `parts`: [(first image, images, mean, rstd, dropmask)] -- one entry, or one
     per mini-batch of a multi-batch pass (each normalised with its own statistics)."""
@@ -510,8 +516,10 @@ class BNTrainNode(object):
         for i, (n0, n, mean, rstd, dropmask) in enumerate(self.parts):
             def sl(a):
                 return a if (whole or a is None) else a.batch_slice(n0, n)
+            # no residual: the gate y > 0 is recomputed from the raw input (same roundings as bn_apply), y is not read
             K.bn_bwd(sl(dyd), sl(self.raw), sl(self.y), mean, rstd, bn.weight, self.relu, dropmask, self.drop_scale, sl(dx),
-                     dgam, dbet, acc or i > 0, g_out=sl(g_out))
+                     dgam, dbet, acc or i > 0, g_out=sl(g_out),
+                     gate_beta=bn.bias if (self.relu and self.residual is None and REGATE) else None)
         if self.raw.parent is not None:      # input = a channel prefix of a concatenation buffer (DenseNet norm1, train mode)
             tape.contribute_slice(self.raw, lambda dst, accumulate: K.copy_act(dst, dx, accumulate=accumulate))
         else:

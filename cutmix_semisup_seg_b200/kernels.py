@@ -309,10 +309,11 @@ class ActKernels(object):
                          res_ptr=None if residual is None else residual.ptr, ldr=0 if residual is None else residual.ld)
 
     def bn_bwd(self, dy, x, y, mean, rstd, gamma, relu, dropmask, drop_scale, dx, dgamma, dbeta, accumulate_params,
-               g_out=None):
+               g_out=None, gate_beta=None):
         self.be.bn_bwd(dy.ptr, dy.ld, x.ptr, x.ld, y.ptr, y.ld, x.rows, x.c, mean, rstd, gamma, relu, dropmask, drop_scale,
                        dx.ptr, dx.ld, dgamma, dbeta, accumulate_params,
-                       g_out_ptr=None if g_out is None else g_out.ptr, ldgo=0 if g_out is None else g_out.ld)
+                       g_out_ptr=None if g_out is None else g_out.ptr, ldgo=0 if g_out is None else g_out.ld,
+                       gate_beta=gate_beta)
 
     def bn_fold(self, gamma, beta, mean, var, eps, scale, shift):
         self.be.bn_fold(gamma, beta, mean, var, eps, scale, shift)

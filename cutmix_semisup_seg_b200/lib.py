@@ -137,7 +137,7 @@ _SIGS = {
     'b2_bn_apply': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_f32, c_vp, c_int,
                             c_vp, c_int, c_vp]),
     'b2_bn_bwd': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp,
-                          c_f32, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
+                          c_f32, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'b2_bn_fold': (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_int, c_vp]),
     'b2_bn_eval_param_grad': (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int,
                                       c_vp, c_vp, c_int, c_vp, c_vp]),

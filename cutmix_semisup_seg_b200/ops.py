@@ -559,11 +559,13 @@ class CudaBackend(object):
                    int(bool(relu)), L.ptr(dropmask), float(drop_scale), y_ptr, ldy, res_ptr, ldr, self._s())
 
     def bn_bwd(self, dy_ptr, lddy, x_ptr, ldx, y_ptr, ldy, rows, c, mean, rstd, gamma, relu, dropmask, drop_scale,
-               dx_ptr, lddx, dgamma, dbeta, accumulate_params, g_out_ptr=None, ldgo=0):
+               dx_ptr, lddx, dgamma, dbeta, accumulate_params, g_out_ptr=None, ldgo=0, gate_beta=None):
+        """gate_beta: the layer's beta when the ReLU gate may be recomputed from x (no residual): y is then not read."""
         ws = self._red_ws(rows, c, mean.device)
         self._call('b2_bn_bwd', dy_ptr, lddy, x_ptr, ldx, y_ptr, ldy, rows, c, mean.data_ptr(), rstd.data_ptr(),
                    gamma.data_ptr(), int(bool(relu)), L.ptr(dropmask), float(drop_scale), dx_ptr, lddx,
-                   L.ptr(dgamma), L.ptr(dbeta), int(bool(accumulate_params)), g_out_ptr, ldgo, ws.data_ptr(), self._s())
+                   L.ptr(dgamma), L.ptr(dbeta), int(bool(accumulate_params)), g_out_ptr, ldgo, L.ptr(gate_beta),
+                   ws.data_ptr(), self._s())
         self.launches += 3
 
     def bn_fold(self, gamma, beta, mean, var, eps, scale, shift):

@@ -481,7 +481,9 @@ int b2_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* y
               int64_t rows, int c, const float* mean, const float* rstd, const float* gamma,
               int relu, const float* dropmask, float drop_scale, float* dx, int lddx,
               float* dgamma, float* dbeta, int accumulate_params, float* g_out, int ldgo,
-              double* workspace, void* stream);
+              const float* gate_beta, double* workspace, void* stream);
+/* gate_beta != NULL (relu layers WITHOUT a residual): the ReLU gate is recomputed from x as gamma*(rstd*(x-mean))+gate_beta > 0 with
+ * the instruction sequence of b2_bn_apply (bit-identical sign) and y is not read: 5 instead of 7 tensor passes over HBM. */
 /* Eval-mode (frozen) BN folded constants: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale. */
 int b2_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
                float eps, float* scale, float* shift, int c, void* stream);

@@ -282,7 +282,8 @@ class EmuKernels(object):
             y = y * dropmask.permute(0, 3, 1, 2).to(DT) * drop_scale
         _store(out, y)
 
-    def bn_bwd(self, dy, x, y, mean, rstd, gamma, relu, dropmask, drop_scale, dx, dgamma, dbeta, accumulate_params, g_out=None):
+    def bn_bwd(self, dy, x, y, mean, rstd, gamma, relu, dropmask, drop_scale, dx, dgamma, dbeta, accumulate_params, g_out=None,
+               gate_beta=None):        # gate_beta: the device kernel may recompute the gate from x; the sign of y is the same
         sh = (1, -1, 1, 1)
         g = _v(dy)
         if relu:

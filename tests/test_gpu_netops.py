@@ -154,6 +154,34 @@ def test_bn_train_stats_apply_bwd(K, case):
         assert rel(gog, goc) < 1e-6
 
 
+@pytest.mark.parametrize('case', [(4, 9, 7, 64, True), (3, 5, 5, 48, False), (2, 6, 6, 10, True), (16, 33, 31, 256, False)])
+def test_bn_bwd_gate_recomputed_from_x_is_bit_identical(K, case):
+    """b2_bn_bwd(gate_beta=beta): layers without a residual recompute the ReLU gate from the raw input with the instruction
+    sequence of b2_bn_apply instead of reading the stored output.  Every result must equal the y-reading path bit for bit,
+    including elements whose output is exactly zero or tiny (the sign test must see the value bn_apply stored)."""
+    n, h, w, c, use_drop = case
+    torch.manual_seed(n * 1000 + c)
+    x = Act(torch.randn(n, h, w, c, device=dev) * 3.0, n, h, w, c)
+    gam = (torch.rand(c) + 0.5).to(dev); bet = (torch.randn(c) * 0.5).to(dev)
+    bet[::3] = 0.0                                   # zero shift: many outputs within rounding of zero
+    mean = torch.empty(c, device=dev); rstd = torch.empty(c, device=dev)
+    K.bn_stats(x, 1e-5, 0.1, mean, rstd, torch.zeros(c, device=dev), torch.ones(c, device=dev))
+    x.view4()[0, 0, 0, :] = mean                     # exact zeros before the shift
+    mask = (torch.rand(n, h, w, c, device=dev) > 0.5).float() if use_drop else None
+    y = Act.alloc(n, h, w, c, dev)
+    K.bn_apply(x, mean, rstd, gam, bet, True, mask, 2.0, y)
+    dy = Act(torch.randn(n, h, w, c, device=dev), n, h, w, c)
+    outs = []
+    for gate_beta in (None, bet):
+        dx = Act.alloc(n, h, w, c, dev)
+        dgam = torch.full((c,), 0.25, device=dev); dbet = torch.full((c,), -0.75, device=dev)
+        K.bn_bwd(dy, x, y, mean, rstd, gam, True, mask, 2.0, dx, dgam, dbet, True, gate_beta=gate_beta)
+        outs.append((dx.view4().clone(), dgam, dbet))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float(outs[0][0].abs().max()) > 0
+
+
 @pytest.mark.parametrize('case', [(3, 8, 8, 2048, 2048), (2, 5, 7, 10, 12)])
 def test_gap_and_broadcast(K, case):
     n, h, w, c, ld = case

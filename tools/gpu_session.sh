@@ -151,6 +151,26 @@ PYEOF
     done
     paste -d'|' <(head -34 gpurun_out/shape_profile_${tag}_new.txt | cut -c1-100) <(head -34 gpurun_out/shape_profile_${tag}_prev.txt | cut -c60-100)
     ;;
+  regate)     # BatchNorm backward with the gate recomputed from x: bit-exactness + whole netops / network files, bench A/B (B200SEG_BN_REGATE)
+    timeout -s KILL 900 python -m pytest tests/test_gpu_netops.py tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_nets.py tests/test_gpu_graph.py tests/test_zzy_gpu_denseunet.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    for v in 0 1 0 1; do
+      B200SEG_BN_REGATE=$v B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_regate$v.txt bench_line ${tag}_regate$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    grep -h "bn_bwd" gpurun_out/shape_profile_${tag}_regate0.txt gpurun_out/shape_profile_${tag}_regate1.txt
+    ;;
+  final)      # what the driver runs at round end (whole suite, smoke, default bench) + launch list of one eager step + the other bench lines
+    run_tests $tag tests
+    grep "fullsize cfg3 3xtf32\|fullsize cfg2 3xtf32 iteration 0" gpurun_out/parity_$tag.txt | cut -c1-230
+    timeout -s KILL 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log | cut -c1-200
+    B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag
+    timeout -s KILL 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python tools/ncu_step.py > gpurun_out/ncu_step_$tag.log 2>&1; echo "[ncu step exit $?]" >> gpurun_out/ncu_step_$tag.log
+    python tools/launch_list_summary.py gpurun_out/launches_$tag.csv > gpurun_out/launch_list_summary_$tag.txt 2>&1; head -14 gpurun_out/launch_list_summary_$tag.txt
+    gzip -f gpurun_out/launches_$tag.csv
+    for spec in "aug:--loss aug" "vat:--loss vat" "ict:--loss ict" "config4:--arch denseunet --loss aug" "cfg2:--arch v2"; do
+      n=${spec%%:*}; a=${spec#*:}
+      B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 bench_line ${tag}_$n --steps 10 --warmup 3 --no-second-precision --no-tf32-peak $a
+    done
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;

@@ -1,6 +1,7 @@
 """Aggregate an `ncu --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
-sm__pipe_tensor_cycles_active_realtime...` launch list (tools/ncu_step.py) per kernel: launches, time, share of the
-step, DRAM traffic per launch, time-weighted tensor-pipe activity.  Usage: launch_list_summary.py launches.csv"""
+sm__mem_tensor_cycles_active...` launch list (tools/ncu_step.py) per kernel: launches, time, share of the
+step, DRAM traffic per launch, time-weighted tensor-pipe occupancy
+(sm__mem_tensor_cycles_active == tensor-pipe busy fraction of the tcgen05 kernels).  Usage: launch_list_summary.py launches.csv"""
 import collections
 import csv
 import re
@@ -39,7 +40,7 @@ def main(path):
         a['us'] += t
         a['rd'] += d.get('dram__bytes_read.sum', 0.0)
         a['wr'] += d.get('dram__bytes_write.sum', 0.0)
-        a['tensor_us'] += t * d.get('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0) / 100.0
+        a['tensor_us'] += t * d.get('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', d.get('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0)) / 100.0
     tot = sum(a['us'] for a in agg.values())
     print('launches {}   kernel time {:.1f} ms (per-launch times under ncu are cold-cache and serialised: read the SHARES)'
           .format(int(sum(a['n'] for a in agg.values())), tot / 1e3))
