@@ -171,6 +171,15 @@ PYEOF
       B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 bench_line ${tag}_$n --steps 10 --warmup 3 --no-second-precision --no-tf32-peak $a
     done
     ;;
+  ddp2b)      # 2 GPUs on HEAD: correctness of the bucketed / overlapped all-reduce with the batched head, one bench line
+    timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_check.py > gpurun_out/ddp_check_$tag.log 2>&1
+    grep -E "buckets=|overlapped|DDP_CHECK|Error|error" gpurun_out/ddp_check_$tag.log | head -20
+    B200SEG_SKIP_CPU_BASELINE=1 timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_${tag}_2gpu.log 2>&1
+    grep '^{' gpurun_out/bench_${tag}_2gpu.log | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print('2 GPUs', d['value'], 'img/s', d['ms_per_step'], 'ms e2e', d['e2e']['value'], d['clocks'])" || tail -5 gpurun_out/bench_${tag}_2gpu.log
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
