@@ -325,6 +325,40 @@ def test_alternating_tile_direction_is_bit_identical(case):
         assert torch.equal(r, x) and torch.equal(r, y)
 
 
+@pytest.mark.parametrize('case', [(8, 64, 64, 512, 256, 36), (2, 64, 64, 2048, 256, 36), (3, 41, 41, 512, 256, 12)])
+def test_balanced_weight_gradient_plan_equals_one_unit_per_tap(case):
+    """Dilated layers: the load-balanced plan of the weight-gradient kernel (more pixel splits, taps rotated from split to split,
+    debug knob 14) must give the gradient of the plain plan up to the order of the fp32 slab sums, and both must match float64."""
+    from cutmix_semisup_seg_b200 import lib as L
+    from cutmix_semisup_seg_b200.kernels import ActKernels
+    from cutmix_semisup_seg_b200.acts import Act
+    N, H, W, Cin, Cout, dil = case
+    torch.manual_seed(sum(case))
+    K = ActKernels(n_split=1)
+    x = torch.randn(N, H, W, Cin, device=dev); g = torch.randn(N, H, W, Cout, device=dev)
+    xa, ga = Act(x, N, H, W, Cin), Act(g, N, H, W, Cout)
+    lib = L.load()
+    out = []
+    for knob in (0, 1):
+        lib.b2_debug_set(14, knob)
+        try:
+            dw = torch.zeros(Cout, 9, Cin, device=dev)
+            K.conv_wgrad(ga, xa, dw, Cout, 3, 3, Cin, 1, dil, dil)
+            out.append(dw)
+        finally:
+            lib.b2_debug_set(14, 1)
+    scale = float(out[0].abs().max())
+    assert float((out[0] - out[1]).abs().max()) < 2e-5 * scale
+    # float64 reference on a sub-sample of the output channels (the full tensor is 1 TFLOP on the host)
+    sel = torch.arange(0, Cout, 37)
+    xd = x.permute(0, 3, 1, 2).double().cpu().requires_grad_(False)
+    w = torch.zeros(len(sel), Cin, 3, 3, dtype=torch.double, requires_grad=True)
+    y = F.conv2d(xd, w, padding=dil, dilation=dil)
+    y.backward(g.permute(0, 3, 1, 2)[:, sel].double().cpu())
+    ref = w.grad.permute(0, 2, 3, 1).reshape(len(sel), 9, Cin)
+    assert relerr(out[1][sel], ref) < 2e-3                      # single-pass TF32
+
+
 def test_conv_fused_epilogue_and_concat_slice():
     """scale/shift + residual + ReLU epilogue writing into a channel slice of a wider buffer; dgrad with the
     fused addend + ReLU gate (the backward fusion the engine relies on)."""
