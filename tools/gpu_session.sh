@@ -180,6 +180,22 @@ import json,sys
 for l in sys.stdin:
     d=json.loads(l); print('2 GPUs', d['value'], 'img/s', d['ms_per_step'], 'ms e2e', d['e2e']['value'], d['clocks'])" || tail -5 gpurun_out/bench_${tag}_2gpu.log
     ;;
+  occ2)       # after the cheap tile decoding: ncu of the layer3 3x3 / ASPP launches (occupancy = sm__mem_tensor_cycles_active) + clock64 pipeline trace
+    for w in l3x3 aspp32; do
+      timeout -s KILL 600 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.avg,sm__cycles_elapsed.max,sm__cycles_elapsed.avg.per_second,sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'conv_gemm2|conv_wgrad2' -c 6 --csv --log-file gpurun_out/occ_${w}_$tag.csv python tools/aspp_bench.py 1 $w > gpurun_out/ncu_occ_${w}_$tag.log 2>&1
+      python - <<PYEOF
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/occ_${w}_$tag.csv')) if len(r)>10]
+h=rows[0]; im=h.index('Metric Name'); iv=h.index('Metric Value'); iid=h.index('ID'); ik=h.index('Kernel Name')
+cur={}
+for r in rows[1:]:
+    cur.setdefault((r[iid], r[ik][:40]),{})[r[im]]=r[iv]
+for k,v in cur.items(): print('$w', k, v)
+PYEOF
+    done
+    timeout -s KILL 300 python tools/aspp_bench.py 3 trace3 > gpurun_out/trace3_$tag.log 2>&1; cat gpurun_out/trace3_$tag.log | cut -c1-250
+    timeout -s KILL 300 python tools/aspp_bench.py 5 all > gpurun_out/micro_${tag}_all.log 2>&1; cat gpurun_out/micro_${tag}_all.log | cut -c1-100
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
