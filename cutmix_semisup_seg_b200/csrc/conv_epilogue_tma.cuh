@@ -74,10 +74,16 @@ struct Quarter {
 };
 
 // One epilogue warp's persistent state (operand pipeline across chunks AND tiles).
+// Flavours with BOTH operands keep one request in flight (8 KB per warp): both slots and the first mbarrier.  Flavours with ONE
+// operand (forward BN + residual + ReLU: the bulk of the HBM-bound 1x1 time) would have 4 KB per warp = 32 KB per SM in flight,
+// ~2.9 TB/s of operand stream at DRAM latency; they use the idle second slot as a second buffer with its own mbarrier and keep TWO
+// requests in flight (`head` = slot of the next item to consume, `requested` = items requested and not yet consumed, 0..2).
 struct WarpState {
-  uint32_t stage, slot_add, slot_gate, tab, bar;   // shared-memory addresses
-  uint32_t phase;                                   // parity of the operand barrier for the NEXT wait
-  int requested;                                    // 1: operand boxes of the next item to process have been requested
+  uint32_t stage, slot_add, slot_gate, tab, bar;   // shared-memory addresses; the second mbarrier sits at bar + 8
+  uint32_t phase;                                   // parity of the operand barrier for the NEXT wait (two-operand flavours)
+  uint32_t ph0, ph1;                                // the same per slot (one-operand flavours)
+  int head;
+  int requested;                                    // operand boxes of the next item(s) to process have been requested
 };
 
 template <bool ADD, bool GATE>
@@ -86,6 +92,13 @@ __device__ __forceinline__ void request_operands(const CUtensorMap* tm_add, cons
   mbar_expect_tx_u32(w.bar, (uint32_t)((ADD ? 1 : 0) + (GATE ? 1 : 0)) * TILE_BYTES);
   if (ADD) tma_load_tile(w.slot_add, tm_add, w.bar, c0, q.x, q.y, q.z);
   if (GATE) tma_load_tile(w.slot_gate, tm_gate, w.bar, c0, q.x, q.y, q.z);
+}
+
+// one-operand flavours: the box of one item into slot `k` (0: slot_add, 1: slot_gate), completing on that slot's mbarrier
+__device__ __forceinline__ void request_single(const CUtensorMap* tm, const WarpState& w, int k, int c0, const Quarter& q) {
+  const uint32_t bar = w.bar + 8u * (uint32_t)k;
+  mbar_expect_tx_u32(bar, (uint32_t)TILE_BYTES);
+  tma_load_tile(k ? w.slot_gate : w.slot_add, tm, bar, c0, q.x, q.y, q.z);
 }
 
 // Drains this warp's chunks (32-column blocks `half`, `half + 2`, ... of the N tile starting at channel n0) of one accumulator.
@@ -118,13 +131,26 @@ __device__ __forceinline__ void drain_tile_t(const epi::Params& p, const CUtenso
   const uint32_t swz = (uint32_t)(lane & 7);
   const uint32_t row_off = (uint32_t)lane * 128u;
   const int sub_r = lane >> 3, sub_c4 = lane & 7;
-  if (OPS && !w.requested) {                     // first item of the kernel (or after a tile this warp skipped)
-    if (lane == 0) request_operands<ADD, GATE>(tm_add, tm_gate, w, n0 + half * 32, q);
-    w.requested = 1;
-  }
+  constexpr bool DUAL = (ADD != GATE) && !STATS;   // one operand: two slots, two requests in flight (see WarpState)
+  const CUtensorMap* tm_one = ADD ? tm_add : tm_gate;
   int next_cnt = 0;
   if (have_next && qn.active)
     for (int ch = half; ch < nchunks && n0n + ch * 32 < p.nb; ch += 2) ++next_cnt;
+  // item k of this warp, counted from the first chunk of this tile (k >= cnt: chunks of the next tile)
+  auto request_item = [&](int k, int slot) {
+    if (k < cnt) request_single(tm_one, w, slot, n0 + (half + 2 * k) * 32, q);
+    else request_single(tm_one, w, slot, n0n + (half + 2 * (k - cnt)) * 32, qn);
+  };
+  if (DUAL) {
+    // top up to two requests: first item of the kernel, after a skipped tile, or a predecessor tile with a single chunk
+    while (w.requested < 2 && w.requested < cnt + next_cnt) {
+      if (lane == 0) request_item(w.requested, (w.head + w.requested) & 1);
+      ++w.requested;
+    }
+  } else if (OPS && !w.requested) {              // first item of the kernel (or after a tile this warp skipped)
+    if (lane == 0) request_operands<ADD, GATE>(tm_add, tm_gate, w, n0 + half * 32, q);
+    w.requested = 1;
+  }
 #pragma unroll 1
   for (int i = 0; i < cnt; ++i) {
     const int ch = half + 2 * i;
@@ -142,7 +168,12 @@ __device__ __forceinline__ void drain_tile_t(const epi::Params& p, const CUtenso
     tc::tmem_ld_wait();
     if (i == cnt - 1) release();
     if (lane == 0) bulk_wait_read0();            // the previous tile's store has read the staging tile
-    if (OPS) { mbar_wait_u32(w.bar, w.phase); w.phase ^= 1; }
+    uint32_t slot_cur_add = w.slot_add, slot_cur_gate = w.slot_gate;
+    if (DUAL) {
+      mbar_wait_u32(w.bar + 8u * (uint32_t)w.head, w.head ? w.ph1 : w.ph0);
+      if (w.head) w.ph1 ^= 1; else w.ph0 ^= 1;
+      slot_cur_add = slot_cur_gate = w.head ? w.slot_gate : w.slot_add;
+    } else if (OPS) { mbar_wait_u32(w.bar, w.phase); w.phase ^= 1; }
     __syncwarp();
     const float relu_floor = p.relu ? 0.f : -3.402823466e38f;
 #pragma unroll
@@ -159,10 +190,10 @@ __device__ __forceinline__ void drain_tile_t(const epi::Params& p, const CUtenso
       } else if (p.shift) {
         const float4 t = epi::lds128(w.tab + 128 + j * 16); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
       }
-      if (ADD) { const float4 a = epi::lds128(w.slot_add + off); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+      if (ADD) { const float4 a = epi::lds128(slot_cur_add + off); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
       v.x = fmaxf(v.x, relu_floor); v.y = fmaxf(v.y, relu_floor); v.z = fmaxf(v.z, relu_floor); v.w = fmaxf(v.w, relu_floor);
       if (GATE) {
-        const float4 g = epi::lds128(w.slot_gate + off);
+        const float4 g = epi::lds128(slot_cur_gate + off);
         v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f; v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
       }
       if (p.scale2) { const float4 s = epi::lds128(w.tab + 256 + j * 16); v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w; }
@@ -197,8 +228,19 @@ __device__ __forceinline__ void drain_tile_t(const epi::Params& p, const CUtenso
       tc::fence_proxy_async();
       __syncwarp();                              // the gate slot may be refilled now
     }
+    if (DUAL) {
+      // item i has been consumed (all lanes have read the slot: the __syncwarp after the staging writes): its slot takes the
+      // item two ahead, i.e. item i + 1 + (requests still in flight)
+      --w.requested;
+      const int nxt = i + 1 + w.requested;
+      if (nxt < cnt + next_cnt) {
+        if (lane == 0) request_item(nxt, w.head);
+        ++w.requested;
+      }
+      w.head ^= 1;
+    }
     if (lane == 0) {
-      if (OPS) {                                 // operand slots are free: request the next item's boxes
+      if (OPS && !DUAL) {                        // operand slots are free: request the next item's boxes
         if (i + 1 < cnt) request_operands<ADD, GATE>(tm_add, tm_gate, w, c0 + 64, q);
         else if (next_cnt > 0) request_operands<ADD, GATE>(tm_add, tm_gate, w, n0n + half * 32, qn);
       }
@@ -207,7 +249,7 @@ __device__ __forceinline__ void drain_tile_t(const epi::Params& p, const CUtenso
       bulk_commit();
     }
   }
-  if (OPS) w.requested = next_cnt > 0 ? 1 : 0;
+  if (OPS && !DUAL) w.requested = next_cnt > 0 ? 1 : 0;
 }
 
 template <class Release>

@@ -195,7 +195,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (PF && a.tma.on) {
       uint8_t* aux = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + epi2::NUM_WARPS * epi2::WARP_BYTES;
       for (int i = 0; i < epi2::NUM_WARPS; ++i)
-        tc::mbar_init(reinterpret_cast<uint64_t*>(aux + i * epi2::WARP_AUX_BYTES + 384), 1);
+        for (int k = 0; k < 2; ++k)               // one operand barrier per slot (conv_epilogue_tma.cuh, WarpState)
+          tc::mbar_init(reinterpret_cast<uint64_t*>(aux + i * epi2::WARP_AUX_BYTES + 384 + 8 * k), 1);
     }
     tc::fence_barrier_init();
   }
@@ -311,7 +312,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* aux = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + epi2::NUM_WARPS * epi2::WARP_BYTES + ewi * epi2::WARP_AUX_BYTES;
     epi2::WarpState ws;
     ws.stage = tc::smem_u32(tiles); ws.slot_add = ws.stage + epi2::TILE_BYTES; ws.slot_gate = ws.stage + 2 * epi2::TILE_BYTES;
-    ws.tab = tc::smem_u32(aux); ws.bar = ws.tab + 384; ws.phase = 0; ws.requested = 0;
+    ws.tab = tc::smem_u32(aux); ws.bar = ws.tab + 384; ws.phase = 0; ws.ph0 = ws.ph1 = 0; ws.head = 0; ws.requested = 0;
     const int lin = ew * 32;              // first accumulator row of this warp's quarter
     const int bwbh = a.bw * a.bh;
     const int q_dn = lin / bwbh, q_dh = (lin - q_dn * bwbh) / a.bw, q_dw = lin - q_dn * bwbh - q_dh * a.bw;

@@ -267,7 +267,7 @@ if __name__ == '__main__':
             for knob in (0, 1):
                 L.b2_debug_set(8, knob)
                 t = ' {} [tma={}]'.format(tag, knob)
-                ys = [Act.alloc(n, h, w, cout, dev) for _ in range(5)]
+                ys = [Act.alloc(n, h, w, cout, dev) for _ in range(6)]
                 for y in ys:
                     y.base.fill_(0.5)
                 stats = [None]
@@ -275,6 +275,7 @@ if __name__ == '__main__':
                 def plain(): K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, ys[0])
                 def bnres(): K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, ys[1], scale=sc, shift=sh, addend=res, relu=True)
                 def addgate(): K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, ys[2], addend=res, gate=gate)
+                def gateonly(): K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, ys[5], gate=gate)
 
                 def addgatestats():
                     stats[0] = K.be.conv_gemm(x.ptr, 1, 1, x.rows, cin, x.ld, wt.data_ptr(), cout, 1, cin, ys[3].ptr, 1, x.rows, 1, x.rows,
@@ -285,7 +286,7 @@ if __name__ == '__main__':
                     K.be.conv_gemm(x.ptr, 1, 1, x.rows, cin, x.ld, wt.data_ptr(), cout, 1, cin, ys[4].ptr, 1, x.rows, 1, x.rows,
                                    ys[4].ld, O.conv_taps(1, 1, 1, 0), accumulate=True)
                 for fn, name in ((plain, 'fwd plain'), (bnres, 'fwd bn+residual+relu'), (addgate, 'dgrad addend+gate'),
-                                 (addgatestats, 'dgrad addend+gate+stats')):
+                                 (addgatestats, 'dgrad addend+gate+stats'), (gateonly, 'dgrad gate only')):
                     if time_it:
                         timeit(fn, fl, name + t)
                     else:
@@ -295,7 +296,7 @@ if __name__ == '__main__':
             L.b2_debug_set(8, 1)
             same = [bool(torch.equal(a, b)) for a, b in zip(outs[0], outs[1])]
             worst = max(float((a - b).abs().max()) for a, b in zip(outs[0], outs[1]))
-            print('   {}: bit-identical register / TMA epilogue (plain, bn+res, add+gate, stats out, accumulate, stats): {}  max abs diff {:.3e}'
+            print('   {}: bit-identical register / TMA epilogue (plain, bn+res, add+gate, stats out, accumulate, gate only, stats): {}  max abs diff {:.3e}'
                   .format(tag, same, worst), flush=True)
 
         flavours(32, 64, 64, 256, 1024, '1x1 256->1024 N32')

@@ -196,6 +196,16 @@ PYEOF
     timeout -s KILL 300 python tools/aspp_bench.py 3 trace3 > gpurun_out/trace3_$tag.log 2>&1; cat gpurun_out/trace3_$tag.log | cut -c1-250
     timeout -s KILL 300 python tools/aspp_bench.py 5 all > gpurun_out/micro_${tag}_all.log 2>&1; cat gpurun_out/micro_${tag}_all.log | cut -c1-100
     ;;
+  epi2slot)   # one-operand TMA epilogue flavours with two requests in flight: bit-exactness + timing per flavour, kernel tests, bench prev / new
+    timeout -s KILL 300 python tools/aspp_bench.py 3 tma > gpurun_out/micro_${tag}_tma.log 2>&1; echo "[tma exit $?]" >> gpurun_out/micro_${tag}_tma.log; cut -c1-200 gpurun_out/micro_${tag}_tma.log
+    B200SEG_LIB=$PWD/cutmix_semisup_seg_b200/libb200seg_prev.so timeout -s KILL 300 python tools/aspp_bench.py 3 tma > gpurun_out/micro_${tag}_tma_prev.log 2>&1; grep "residual\|gate only" gpurun_out/micro_${tag}_tma_prev.log | cut -c1-120
+    timeout -s KILL 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_nets.py tests/test_gpu_graph.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    for v in prev new prev new; do
+      lib=; [ $v = prev ] && lib=$PWD/cutmix_semisup_seg_b200/libb200seg_prev.so
+      B200SEG_LIB=$lib B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_$v.txt bench_line ${tag}_$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    paste -d'|' <(head -24 gpurun_out/shape_profile_${tag}_new.txt | cut -c1-100) <(head -24 gpurun_out/shape_profile_${tag}_prev.txt | cut -c60-100)
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
