@@ -281,6 +281,17 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
   return B2_OK;
 }
 
+int make_tmap_f32_linear(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, const uint32_t* elem_strides) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2_fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled (linear) failed with CUresult %d", (int)r);
+  return B2_OK;
+}
+
 }  // namespace tc
 
 // Pick the (BW, BH, BN) pixel box of at most `max_rows` rows that wastes the fewest tile slots.
@@ -325,6 +336,9 @@ bool tc::pdl_enabled() {
 int g_conv_alt_dir = -1;
 int g_conv_next_reverse = 0;      // direction of the launch being prepared (set by b2_conv_gemm)
 static int g_conv_dir_state = 0;
+// b2_debug_set(18, v) / environment B200SEG_WIDE_PF: the CTA-pair kernel prefetches the A stream of 1x1 layers with K >= 512 into
+// L2 in boxes of 256 channels (1 KB per pixel row instead of the 128 B rows of the operand boxes): DRAM-page-friendly reads
+int g_conv_wide_pf = -1;
 int g_conv_tap_tables = 1;        // b2_debug_set(17, 0): per-tile tap masks by the loop over the taps instead of the host-built tables (A/B)
 int g_conv_tap_outer = 0;         // b2_debug_set(7, 1): producer loops tap-outer / K-block-inner (the round-1 order)
 

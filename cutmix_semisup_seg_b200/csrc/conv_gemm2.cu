@@ -62,6 +62,7 @@ struct Conv2KArgs {
   int reverse;               // 1: walk the tiles from the last to the first (alternating launch directions, conv_gemm.cu)
   tc::FastDiv fd_w, fd_h, fd_nn;   // division by tiles_w, tiles_h, n_tiles_n (tc_common.cuh "cheap tile decoding")
   tc::TapTables tt;
+  int wide_pf;               // 1: L2 prefetch of the A stream in 256-channel boxes (1x1 layers with K >= 512, see the producer)
   epi::Params ep;             // epilogue parameter block (conv_epilogue.cuh)
   epi2::Geo tma;              // TMA epilogue (conv_epilogue_tma.cuh; PF build only)
   long long* trace;   // diagnostics (b2_debug_trace): clock64 stamps of CTA 0's pipeline roles, 4 x 512 slots
@@ -168,7 +169,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
-                  const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ Conv2KArgs a) {
+                  const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ CUtensorMap tmPf,
+                  const __grid_constant__ Conv2KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -231,6 +233,18 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const TileInfo t = decode_tile(a, pair, (int)rank);
       const int w_base = t.w0 * a.istride, h_base = t.h0 * a.istride;
       for (int o = 0; o < n_outer; ++o) {
+        if (a.wide_pf && (o & 7) == 4) {
+          // 1x1 layer: the operand boxes are 128 B per pixel row at a pitch of K * 4 bytes -- 128 B DRAM bursts scattered over as many
+          // pages as the tile has pixels.  Four stages before a group of 8 K blocks is needed, ONE prefetch pulls the group's 1 KB per
+          // pixel row into L2 (the first group of the next tile while the last group of this one is being loaded).
+          const int g = (o >> 3) + 1;
+          if (g * 8 < a.kblocks) {
+            if (el) tc::tma_prefetch_l2_4d(&tmPf, g * 256, w_base, h_base, t.n0);
+          } else if (pair + num_clusters < a.num_pairs) {
+            const TileInfo tn = decode_tile(a, pair + num_clusters, (int)rank);
+            if (el) tc::tma_prefetch_l2_4d(&tmPf, 0, tn.w0 * a.istride, tn.h0 * a.istride, tn.n0);
+          }
+        }
         for (int i = 0; i < n_inner; ++i) {
           const int tap = a.tap_outer ? o : i;
           const int kb = a.tap_outer ? i : o;
@@ -407,6 +421,7 @@ extern int g_conv_epi_debug;
 extern int g_conv_tap_outer;
 extern int g_conv_next_reverse;
 extern int g_conv_tap_tables;
+extern int g_conv_wide_pf;
 // PF build is used when the epilogue reads an addend / gate and K * taps <= this (0 = never).  Measured on B200
 // (profiles/r01_v7_pf_microbench.log): faster up to K = 512 (HBM-bound 1x1 layers, 0.231 -> 0.163 ms for 256 -> 1024 with
 // addend + gate), slower from K = 1024 on where the 3-stage operand ring starves the MMA pipe.
@@ -522,6 +537,17 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
     int rc = tc::make_tmap_f32(&tmB, p->b, 3, dims, strides, box, es); if (rc) return rc;
     rc = tc::make_tmap_f32(&tmBlo, p->b_lo ? p->b_lo : p->b, 3, dims, strides, box, es); if (rc) return rc;
   }
+  CUtensorMap tmPf = tmA;                                  // placeholder unless the wide prefetch is on
+  if (g_conv_wide_pf < 0) { const char* e = getenv("B200SEG_WIDE_PF"); g_conv_wide_pf = e ? atoi(e) : 0; }
+  if (g_conv_wide_pf > 0 && p->n_taps == 1 && p->istride == 1 && p->k >= 512 && p->k % 256 == 0 && !g_conv_tap_outer &&
+      p->taps[0] == 0 && p->taps[1] == 0) {
+    const uint64_t dims[4] = {(uint64_t)p->k, (uint64_t)p->iw, (uint64_t)p->ih, (uint64_t)p->n};
+    const uint64_t strides[3] = {(uint64_t)p->lda * 4, (uint64_t)p->iw * p->lda * 4, (uint64_t)p->ih * p->iw * p->lda * 4};
+    const uint32_t box[4] = {256, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = tc::make_tmap_f32_linear(&tmPf, p->a, 4, dims, strides, box, es); if (rc) return rc;
+    a.wide_pf = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<STAGES_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES_MAIN, false)));
@@ -572,11 +598,11 @@ int b2_conv_gemm_2cta(const b2_conv_params* p, void* stream) {
   if (clusters < 1) clusters = 1;
   if (clusters > a.num_pairs) clusters = a.num_pairs;
   if (use_pf)
-    tc::launch(conv_gemm2_kernel<STAGES_PF, true>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_PF, true>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_PF, true), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, tmPf, a);
   else if (g_conv_main_stages == STAGES_MAIN_OLD)
-    tc::launch(conv_gemm2_kernel<STAGES_MAIN_OLD, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN_OLD, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_MAIN_OLD, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN_OLD, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, tmPf, a);
   else
-    tc::launch(conv_gemm2_kernel<STAGES_MAIN, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, a);
+    tc::launch(conv_gemm2_kernel<STAGES_MAIN, false>, clusters * 2, NUM_THREADS, smem_bytes(STAGES_MAIN, false), (cudaStream_t)stream, tmA, tmAlo, tmB, tmBlo, tmD, tmAdd, tmGate, tmPf, a);
   B2_LAUNCH_CHECK("conv_gemm2_kernel");
   return B2_OK;
 }

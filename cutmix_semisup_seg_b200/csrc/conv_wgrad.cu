@@ -736,12 +736,14 @@ extern int g_conv_main_stages;
 extern int g_conv_pdl;
 extern int g_conv_alt_dir;
 extern int g_conv_tap_tables;
+extern int g_conv_wide_pf;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 11) g_conv_pdl = value;
   if (key == 12) g_conv_alt_dir = value;
   if (key == 13) g_wgrad2_stages = value;
   if (key == 14) g_wgrad_balance = value;
   if (key == 17) g_conv_tap_tables = value;
+  if (key == 18) g_conv_wide_pf = value;
   if (key == 15) g_wgrad_force_splits = value;
   if (key == 16) g_wgrad_force_step = value;
   if (key == 5) g_wgrad_force_1cta = value;

@@ -100,6 +100,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// L2 prefetch of a 4-D box (no shared-memory destination, no completion mechanism: a hint)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -204,6 +209,9 @@ PFN_encodeTiled get_encode_tiled();
 // fp32 tensor, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides_bytes has rank-1 entries.
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides, bool atom32 = false);
+// the same without swizzle: boxes with more than 128 B per row, used for L2 prefetches only (nothing lands in shared memory)
+int make_tmap_f32_linear(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, const uint32_t* elem_strides);
 
 // 1 = launch the tensor-core kernels with the programmatic-stream-serialization attribute (environment B200SEG_PDL or
 // b2_debug_set(11, v)); 0 = plain stream order

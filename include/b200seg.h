@@ -399,7 +399,9 @@ int b2_conv_wgrad_plan_balance(const b2_wgrad_params* p, int64_t* out);
  * 13 = operand ring depth of the CTA-pair weight-gradient kernel (6 or 7 stages; environment B200SEG_WGRAD_STAGES);
  * 14 = 0 disables the load-balanced work decomposition of the weight-gradient kernel for dilated layers (more pixel splits,
  *      taps rotated from split to split), 1 (default) enables it; 15 / 16 = force the pixel splits / the tap rotation (experiments);
- * 17 = 0: per-tile tap masks of the conv kernels by a loop over the taps instead of the host-built row / column tables (A/B). */
+ * 17 = 0: per-tile tap masks of the conv kernels by a loop over the taps instead of the host-built row / column tables (A/B);
+ * 18 = L2 prefetch of the A stream of 1x1 layers (K >= 512) in 256-channel boxes by the CTA-pair kernel (environment
+ *      B200SEG_WIDE_PF; 1 on, 0 off). */
 void b2_debug_set(int key, int value);
 /* Diagnostics: device buffer of 2048 int64 receiving clock64 stamps of CTA 0's pipeline roles in the 2-CTA conv
  * kernel ([0,512) producer stage issue, [512,1024) MMA stage acquired, [1024,1536) MMA tile begin/accumulator

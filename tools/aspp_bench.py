@@ -87,6 +87,27 @@ if __name__ == '__main__':
                        'ASPP d{} N32 wgrad splits {} step {}'.format(dil, sp, st))
             del x, g, dw
         L3.b2_debug_set(15, 0); L3.b2_debug_set(16, -1)
+    if which == 'widepf':      # L2 prefetch of the A stream in 256-channel boxes (debug knob 18) on the K-heavy 1x1 layers
+        from cutmix_semisup_seg_b200 import lib as _lib4
+        L4 = _lib4.load()
+        for (n, h, w, cin, cout, name) in ((32, 64, 64, 1024, 256, 'layer3 1x1 1024->256 N32'), (32, 64, 64, 2048, 512, 'layer4 1x1 2048->512 N32'),
+                                           (32, 64, 64, 2048, 256, 'ASPP 1x1 2048->256 N32'), (32, 64, 64, 1024, 2048, 'layer4 ds 1x1 1024->2048 N32'),
+                                           (32, 64, 64, 512, 128, 'layer2 1x1 512->128 N32')):
+            x = Act(torch.randn(n, h, w, cin, device=dev), n, h, w, cin)
+            wt = torch.randn(cout, 1, cin, device=dev) * 0.01
+            gate = Act(torch.randn(n, h, w, cout, device=dev), n, h, w, cout)
+            sc = torch.rand(cout, device=dev) + 0.5; sh = torch.randn(cout, device=dev)
+            outs = []
+            for knob in (0, 1, 0, 1):
+                L4.b2_debug_set(18, knob)
+                y = Act.alloc(n, h, w, cout, dev); y2 = Act.alloc(n, h, w, cout, dev)
+                fl = 2.0 * n * h * w * cin * cout
+                timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y, scale=sc, shift=sh, relu=True), fl, name + ' fwd bn+relu [wide_pf={}]'.format(knob))
+                timeit(lambda: K.conv_fwd(x, wt, cout, 1, 1, cin, cin, 1, 0, 1, y2, gate=gate), fl, name + ' dgrad gate [wide_pf={}]'.format(knob))
+                outs.append((y.base.clone(), y2.base.clone()))
+            print('   bit-identical with / without the prefetch:', all(torch.equal(a, b) for o in outs[1:] for a, b in zip(outs[0], o)), flush=True)
+            del x, gate
+        L4.b2_debug_set(18, 0)
     if which == 'l3x3':        # the largest compute-bound group of the trunk
         conv_case(32, 64, 64, 256, 256, 3, 2, 'layer3 3x3 d2 256->256 @64x64 N32')
     if which == 'l3':

@@ -206,6 +206,13 @@ PYEOF
     done
     paste -d'|' <(head -24 gpurun_out/shape_profile_${tag}_new.txt | cut -c1-100) <(head -24 gpurun_out/shape_profile_${tag}_prev.txt | cut -c60-100)
     ;;
+  widepf)     # wide L2 prefetch of the A stream (knob 18 / B200SEG_WIDE_PF): micro A/B, bench A/B
+    timeout -s KILL 300 python tools/aspp_bench.py 5 widepf > gpurun_out/micro_${tag}_widepf.log 2>&1; echo "[exit $?]" >> gpurun_out/micro_${tag}_widepf.log; cut -c1-120 gpurun_out/micro_${tag}_widepf.log
+    for v in 0 1 0 1; do
+      B200SEG_WIDE_PF=$v B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_pf$v.txt bench_line ${tag}_pf$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    paste -d'|' <(head -16 gpurun_out/shape_profile_${tag}_pf1.txt | cut -c1-100) <(head -16 gpurun_out/shape_profile_${tag}_pf0.txt | cut -c60-100)
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
