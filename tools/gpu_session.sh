@@ -213,6 +213,12 @@ PYEOF
     done
     paste -d'|' <(head -16 gpurun_out/shape_profile_${tag}_pf1.txt | cut -c1-100) <(head -16 gpurun_out/shape_profile_${tag}_pf0.txt | cut -c60-100)
     ;;
+  final2)     # whole suite + smoke + default bench on HEAD (no profiler passes)
+    run_tests $tag tests
+    grep "fullsize cfg3 3xtf32\|fullsize cfg2 3xtf32 iteration 0" gpurun_out/parity_$tag.txt | cut -c1-230
+    timeout -s KILL 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log | cut -c1-200
+    B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
