@@ -2,6 +2,7 @@
 // layout changes, stem im2col, 3x3/s2 max-pool, bilinear resize, global-average-pool / broadcast,
 // batch-norm (train-mode statistics, apply, backward; frozen-BN folding and parameter gradients),
 // per-channel reductions.  All reductions are two-level with a fixed summation order (deterministic).
+#include <stdlib.h>
 #include "common.cuh"
 #include <math_constants.h>
 
@@ -106,10 +107,64 @@ __global__ void __launch_bounds__(256) im2col_const_kernel(const float* __restri
     *reinterpret_cast<float4*>(crow + (int64_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
+// The same stem matrix from a shared-memory copy of the input window: a block owns PX consecutive output pixels of one output row,
+// stages the 7 input rows x ((PX - 1) * stride + 7) pixels it needs (16 B per pixel: 3 channels + the pad channel, ldx == 4; zeros
+// outside the image) with one 16 B load per pixel, and builds its PX x 40 sixteen-byte column groups from shared memory.  The
+// kernel above issues four scalar 4 B global loads with index arithmetic per 16 B store and ran at 2.8 TB/s of writes
+// (profiles/r02_v22_launch_list_summary.txt); values are copied, so the matrix is bit-identical.
+template <int PX>
+__global__ void __launch_bounds__(256) im2col_stem_smem_kernel(const float* __restrict__ x, float* __restrict__ col, int h, int w,
+                                                               int stride, int pad, int oh, int ow) {
+  constexpr int KH = 7, KW = 7, C = 3, KPAD = 160, GROUPS = KPAD / 4, KREAL = KH * KW * C;
+  extern __shared__ float4 win[];                      // [KH][wpx]
+  __shared__ short lut[KPAD];                          // column k -> float offset of (r, s, ch) in the window; -1 = zero padding
+  const int wpx = (PX - 1) * stride + KW;
+  if (threadIdx.x < KPAD) {
+    const int k = threadIdx.x;
+    const int tap = k / C, ch = k - tap * C;
+    const int r = tap / KW, s_ = tap - r * KW;
+    lut[k] = k < KREAL ? (short)((r * wpx + s_) * 4 + ch) : (short)-1;
+  }
+  const int y_o = blockIdx.y % oh, img = blockIdx.y / oh;
+  const int x0 = blockIdx.x * PX;
+  const int ix0 = x0 * stride - pad, iy0 = y_o * stride - pad;
+  const float4* __restrict__ ximg = reinterpret_cast<const float4*>(x) + (int64_t)img * h * w;
+  for (int i = threadIdx.x; i < KH * wpx; i += blockDim.x) {
+    const int r = i / wpx, px = i - r * wpx;
+    const int iy = iy0 + r, ix = ix0 + px;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(ximg + (int64_t)iy * w + ix);
+    win[i] = v;
+  }
+  __syncthreads();
+  const float* wf = reinterpret_cast<const float*>(win);
+  const int npx = min(PX, ow - x0);
+  float* __restrict__ crow = col + ((int64_t)blockIdx.y * ow + x0) * KPAD;
+  for (int i = threadIdx.x; i < npx * GROUPS; i += blockDim.x) {
+    const int xl = i / GROUPS, grp = i - xl * GROUPS;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int o = lut[grp * 4 + e];
+      v[e] = o >= 0 ? wf[o + xl * stride * 4] : 0.f;
+    }
+    *reinterpret_cast<float4*>(crow + (int64_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c, int ldx, int kh, int kw, int stride, int pad,
                          int dil, int oh, int ow, int kpad, void* stream) {
   B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
   B2_REQUIRE(kpad % 4 == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, "b2_im2col: kpad must be a multiple of 4 and col 16 B aligned");
+  if (c == 3 && kh == 7 && kw == 7 && kpad == 160 && ldx == 4 && dil == 1 && stride >= 1 && stride <= 2 && (int64_t)n * oh <= 65535 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !getenv("B200SEG_IM2COL_GLOBAL")) {
+    constexpr int PX = 64;
+    const int wpx = (PX - 1) * stride + 7;
+    dim3 grid((unsigned)((ow + PX - 1) / PX), (unsigned)(n * oh));
+    im2col_stem_smem_kernel<PX><<<grid, 256, 7 * wpx * sizeof(float4), (cudaStream_t)stream>>>(x, col, h, w, stride, pad, oh, ow);
+    B2_LAUNCH_CHECK("im2col_stem_smem_kernel");
+    return B2_OK;
+  }
   if (c == 3 && kh == 7 && kw == 7 && kpad == 160 && (int64_t)n * oh <= 65535 && (int64_t)ow * 40 < (1ll << 30)) {
     // 8 stores per thread: one-store blocks are bound by the block launch rate (330 k blocks per stem at 512 x 512)
     dim3 grid((unsigned)((ow * 40 + 256 * 8 - 1) / (256 * 8)), (unsigned)(n * oh));

@@ -49,7 +49,7 @@ def same_outside(gpu_act, cpu_act):
     return torch.equal(a, b)
 
 
-@pytest.mark.parametrize('shape', [(2, 3, 33, 41), (1, 3, 64, 64), (2, 4, 17, 9)])
+@pytest.mark.parametrize('shape', [(2, 3, 33, 41), (1, 3, 64, 64), (2, 4, 17, 9), (2, 3, 40, 300), (1, 3, 7, 129)])
 def test_im2col_stem(K, shape):
     n, c, h, w = shape
     xg, xc = pair(n, h, w, c, ld=4, seed=1)

@@ -219,6 +219,14 @@ PYEOF
     timeout -s KILL 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log | cut -c1-200
     B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag
     ;;
+  im2col)     # shared-memory stem im2col: bit-exactness tests, bench A/B (B200SEG_IM2COL_GLOBAL=1 = the previous kernel)
+    timeout -s KILL 600 python -m pytest tests/test_gpu_netops.py tests/test_gpu_nets.py tests/test_zz_gpu_vat.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    for v in 1 0 1 0; do
+      gl=; [ $v = 1 ] && gl=1
+      B200SEG_IM2COL_GLOBAL=$gl B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}_global$v.txt bench_line ${tag}_global$v --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    done
+    grep -h im2col gpurun_out/shape_profile_${tag}_global1.txt gpurun_out/shape_profile_${tag}_global0.txt
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
