@@ -737,6 +737,7 @@ extern int g_conv_pdl;
 extern int g_conv_alt_dir;
 extern int g_conv_tap_tables;
 extern int g_conv_wide_pf;
+extern int g_netops_flat_kernels;
 extern "C" void b2_debug_set(int key, int value) {
   if (key == 11) g_conv_pdl = value;
   if (key == 12) g_conv_alt_dir = value;
@@ -744,6 +745,7 @@ extern "C" void b2_debug_set(int key, int value) {
   if (key == 14) g_wgrad_balance = value;
   if (key == 17) g_conv_tap_tables = value;
   if (key == 18) g_conv_wide_pf = value;
+  if (key == 20) g_netops_flat_kernels = value;
   if (key == 15) g_wgrad_force_splits = value;
   if (key == 16) g_wgrad_force_step = value;
   if (key == 5) g_wgrad_force_1cta = value;

@@ -6,6 +6,10 @@
 #include "common.cuh"
 #include <math_constants.h>
 
+// b2_debug_set(20, 1): the flat-index forms of the stem im2col and of the NHWC bilinear resize instead of the row-based kernels
+// (bit-identical results; A/B timing and the bit-exactness tests)
+int g_netops_flat_kernels = 0;
+
 // ------------------------------------------------------------------------------------------ layout
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int c, int64_t hw, int ldd) {
   const int n = blockIdx.y;
@@ -157,7 +161,7 @@ extern "C" int b2_im2col(const float* x, float* col, int n, int h, int w, int c,
   B2_REQUIRE(x && col && n > 0 && h > 0 && w > 0 && c > 0 && kpad >= kh * kw * c, "b2_im2col: bad args");
   B2_REQUIRE(kpad % 4 == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, "b2_im2col: kpad must be a multiple of 4 and col 16 B aligned");
   if (c == 3 && kh == 7 && kw == 7 && kpad == 160 && ldx == 4 && dil == 1 && stride >= 1 && stride <= 2 && (int64_t)n * oh <= 65535 &&
-      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !getenv("B200SEG_IM2COL_GLOBAL")) {
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !g_netops_flat_kernels) {
     constexpr int PX = 64;
     const int wpx = (PX - 1) * stride + 7;
     dim3 grid((unsigned)((ow + PX - 1) / PX), (unsigned)(n * oh));
@@ -382,6 +386,36 @@ __global__ void __launch_bounds__(128) bilinear_fwd_nchw_kernel(const float* __r
   }
 }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// The same arithmetic with the thread -> channel group mapping fixed for the whole kernel: a block owns a run of output pixels of
+// ONE output row (image and row from blockIdx.y, vertical coefficients computed once), thread = (channel group, pixel lane); no
+// integer division in the pixel loop (the flat-index kernel above spends six run-time divisions per 16 B store: 2.25 TB/s at the
+// 64 x 64 -> 128 x 128 resize of the DeepLab v3+ decoder, profiles/r02_v22_launch_list_summary.txt).  Needs 256 % (c / 4) == 0.
+__global__ void __launch_bounds__(256) bilinear_fwd_nhwc_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int ih, int iw,
+                                                                     int ldx, int oh, int ow, int ldy, int align, int cg, int ppb,
+                                                                     int px_per_block) {
+  const int lc = threadIdx.x % cg, lp = threadIdx.x / cg;
+  const int yo = blockIdx.y % oh, img = blockIdx.y / oh;
+  const float sh = lin_scale(ih, oh, align), sw = lin_scale(iw, ow, align);
+  const LinCoef ky = lin_coef(yo, ih, sh, align);
+  const float* b = x + (int64_t)img * ih * iw * ldx + lc * 4;
+  const float* row0 = b + (int64_t)ky.i0 * iw * ldx;
+  const float* row1 = b + (int64_t)ky.i1 * iw * ldx;
+  float* orow = y + ((int64_t)img * oh + yo) * ow * ldy + lc * 4;
+  const int x_begin = blockIdx.x * px_per_block;
+  int x_end = x_begin + px_per_block; if (x_end > ow) x_end = ow;
+  for (int xo = x_begin + lp; xo < x_end; xo += ppb) {
+    const LinCoef kx = lin_coef(xo, iw, sw, align);
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(row0 + (int64_t)kx.i0 * ldx)), v01 = __ldg(reinterpret_cast<const float4*>(row0 + (int64_t)kx.i1 * ldx));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(row1 + (int64_t)kx.i0 * ldx)), v11 = __ldg(reinterpret_cast<const float4*>(row1 + (int64_t)kx.i1 * ldx));
+    float4 r;
+    r.x = ky.l0 * (kx.l0 * v00.x + kx.l1 * v01.x) + ky.l1 * (kx.l0 * v10.x + kx.l1 * v11.x);
+    r.y = ky.l0 * (kx.l0 * v00.y + kx.l1 * v01.y) + ky.l1 * (kx.l0 * v10.y + kx.l1 * v11.y);
+    r.z = ky.l0 * (kx.l0 * v00.z + kx.l1 * v01.z) + ky.l1 * (kx.l0 * v10.z + kx.l1 * v11.z);
+    r.w = ky.l0 * (kx.l0 * v00.w + kx.l1 * v01.w) + ky.l1 * (kx.l0 * v10.w + kx.l1 * v11.w);
+    *reinterpret_cast<float4*>(orow + (int64_t)xo * ldy) = r;
+  }
+}
+
 extern "C" int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int c, int ldx, int oh, int ow, int ldy,
                                int align_corners, int to_nchw, void* stream) {
   B2_REQUIRE(x && y && n > 0 && ih > 0 && iw > 0 && c > 0 && oh > 0 && ow > 0 && ldx >= c, "b2_bilinear_fwd: bad args");
@@ -398,7 +432,13 @@ extern "C" int b2_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, 
     const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && al16(y);
     const int64_t total = (int64_t)n * oh * ow * (vec ? c / 4 : c);
     int64_t blocks = ceil_div64(total, 256); if (blocks > 148 * 32) blocks = 148 * 32;
-    if (vec && total < (1ll << 31)) bilinear_fwd_nhwc_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
+    const int cg = c / 4;
+    if (vec && cg >= 1 && cg <= 256 && 256 % cg == 0 && (int64_t)n * oh <= 65535 && !g_netops_flat_kernels) {
+      const int ppb = 256 / cg;                      // pixel lanes of a block
+      const int px_per_block = ppb * 8;              // 8 pixels per thread
+      dim3 grid((unsigned)((ow + px_per_block - 1) / px_per_block), (unsigned)(n * oh));
+      bilinear_fwd_nhwc_rows_kernel<<<grid, 256, 0, s>>>(x, y, ih, iw, ldx, oh, ow, ldy, align_corners, cg, ppb, px_per_block);
+    } else if (vec && total < (1ll << 31)) bilinear_fwd_nhwc_kernel<4, int32_t><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
     else if (vec) bilinear_fwd_nhwc_kernel<4, int64_t><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
     else bilinear_fwd_nhwc_kernel<1, int64_t><<<(unsigned)blocks, 256, 0, s>>>(x, y, n, ih, iw, c, ldx, oh, ow, ldy, align_corners);
   }

@@ -401,7 +401,8 @@ int b2_conv_wgrad_plan_balance(const b2_wgrad_params* p, int64_t* out);
  *      taps rotated from split to split), 1 (default) enables it; 15 / 16 = force the pixel splits / the tap rotation (experiments);
  * 17 = 0: per-tile tap masks of the conv kernels by a loop over the taps instead of the host-built row / column tables (A/B);
  * 18 = L2 prefetch of the A stream of 1x1 layers (K >= 512) in 256-channel boxes by the CTA-pair kernel (environment
- *      B200SEG_WIDE_PF; 1 on, 0 off). */
+ *      B200SEG_WIDE_PF; 1 on, 0 off);
+ * 20 = 1: flat-index forms of the stem im2col and the NHWC bilinear resize instead of the row-based kernels (bit-identical). */
 void b2_debug_set(int key, int value);
 /* Diagnostics: device buffer of 2048 int64 receiving clock64 stamps of CTA 0's pipeline roles in the 2-CTA conv
  * kernel ([0,512) producer stage issue, [512,1024) MMA stage acquired, [1024,1536) MMA tile begin/accumulator

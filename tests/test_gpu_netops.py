@@ -101,6 +101,30 @@ def test_bilinear_nhwc_fwd_bwd(K, case):
     assert rel(gx, cx) < 1e-5
 
 
+@pytest.mark.parametrize('case', [(3, 64, 64, 256, 128, 128, False), (2, 9, 11, 64, 65, 81, True), (2, 33, 17, 48, 20, 9, False), (1, 5, 300, 8, 9, 517, True)])
+def test_row_based_resize_and_im2col_equal_the_flat_kernels(K, case):
+    """Debug knob 20: the row-based NHWC bilinear forward kernel / shared-memory stem im2col against their flat-index forms -- the
+    same arithmetic, so every bit must agree."""
+    from cutmix_semisup_seg_b200 import lib as L
+    n, ih, iw, c, oh, ow, align = case
+    torch.manual_seed(ih * iw + c)
+    x = Act(torch.randn(n, ih, iw, c, device=dev), n, ih, iw, c)
+    img = Act(torch.randn(n, 2 * oh + 5, 2 * ow + 3, 4, device=dev), n, 2 * oh + 5, 2 * ow + 3, 3, ld=4)
+    soh, sow = (img.h + 6 - 7) // 2 + 1, (img.w + 6 - 7) // 2 + 1
+    lib = L.load()
+    outs = []
+    for knob in (1, 0):
+        lib.b2_debug_set(20, knob)
+        try:
+            y = Act.alloc(n, oh, ow, c, dev)
+            K.bilinear_fwd(x, y, align)
+            col = K.im2col(img, 7, 7, 2, 3, 1, soh, sow, 160)
+            outs.append((y.base.clone(), col.base.clone()))
+        finally:
+            lib.b2_debug_set(20, 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize('case', [(2, 16, 16, 19, 20, 64, 64, False), (2, 9, 11, 21, 24, 65, 81, True), (1, 6, 7, 5, 5, 11, 9, False),
                                   (1, 4, 4, 3, 4, 40, 44, True)])
 def test_bilinear_nchw_fwd_bwd(K, case):

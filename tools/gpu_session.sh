@@ -227,6 +227,11 @@ PYEOF
     done
     grep -h im2col gpurun_out/shape_profile_${tag}_global1.txt gpurun_out/shape_profile_${tag}_global0.txt
     ;;
+  netops2)    # row-based resize / im2col kernels: bit-exactness vs the flat forms, netops + network tests, event timings, bench
+    timeout -s KILL 600 python -m pytest tests/test_gpu_netops.py tests/test_gpu_nets.py tests/test_gpu_graph.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_${tag}.log 2>&1; tail -3 gpurun_out/pytest_${tag}.log | cut -c1-200
+    B200SEG_SKIP_EXTRAS=1 B200SEG_SKIP_CPU_BASELINE=1 B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_${tag}.txt bench_line ${tag} --steps 10 --warmup 3 --no-second-precision --no-tf32-peak
+    grep "bilinear\|im2col\|maxpool\|gap\|bn_" gpurun_out/shape_profile_${tag}.txt
+    ;;
   micro)      timeout -s KILL 600 python tools/aspp_bench.py 3 ${3:-all} > gpurun_out/micro_$tag.log 2>&1; cat gpurun_out/micro_$tag.log | cut -c1-120 ;;
   bench)      shift 2; B200SEG_SHAPE_PROFILE=gpurun_out/shape_profile_$tag.txt bench_line $tag "$@" ;;
   *) echo "unknown stage $stage"; exit 2 ;;
