@@ -170,3 +170,72 @@ def test_conv_gemm_plan_of_the_aspp_launch():
     # a 1 x 1 layer has nothing to skip
     pl1 = tensor_busy.plan(32, 64, 64, 1024, 256, 1, 1)
     assert pl1['stages_total'] == 512 * 32
+
+
+def _choose_box(ow, oh, n, max_rows=128, istride=1):
+    """Python statement of b2_choose_box (conv_gemm.cu): the (bw, bh, bn) pixel box of an M tile."""
+    best, pick = -1.0, (1, 1, 1)
+    max_b = 256 // istride
+    for bw in range(1, min(ow, max_rows, max_b) + 1):
+        for bh in range(1, min(oh, max_b) + 1):
+            if bw * bh > max_rows:
+                break
+            bn = 1
+            if bw == ow and bh == oh:
+                bn = max(1, min(n, max_rows // (bw * bh)))
+            tiles = -(-ow // bw) * -(-oh // bh) * -(-n // bn)
+            score = (ow * oh * n) / (tiles * max_rows) + 1e-6 * bw
+            if score > best:
+                best, pick = score, (bw, bh, bn)
+    return pick
+
+
+@pytest.mark.parametrize('case', [
+    # n, h, w, cin, cout, k, dil  -- tile counts that are 1, powers of two, odd, prime (the fast-division multipliers), dilations
+    (32, 64, 64, 2048, 256, 3, 12), (32, 64, 64, 2048, 256, 3, 36), (3, 33, 41, 96, 304, 3, 2), (5, 7, 300, 64, 512, 3, 5),
+    (1, 129, 3, 32, 1024, 1, 1), (7, 19, 23, 256, 768, 3, 7), (2, 128, 128, 304, 256, 3, 1), (10, 41, 41, 2048, 512, 3, 24),
+], ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_gemm_plan_matches_a_python_walk_of_the_tiles(case):
+    """b2_conv_gemm_plan runs the kernel's own decode_tile on the host: division by multiplication with precomputed reciprocals
+    (tc::FastDiv) and tap masks from the row / column tables.  An independent walk with Python integers must give the same box,
+    tile-pair count and stage totals (debug knob 17 = 0: the same through the tap loop instead of the tables)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import tensor_busy
+    n, h, w, cin, cout, k, dil = case
+    pad = dil * (k // 2)
+    bw, bh, bn = _choose_box(w, h, n)
+    tw, th, tn = -(-w // bw), -(-h // bh), -(-n // bn)
+    m_tiles = tw * th * tn
+    n_tiles_n = -(-cout // 256)
+    kblocks = -(-cin // 32)
+    taps = [(r * dil - pad, s * dil - pad) for r in range(k) for s in range(k)]
+
+    def mask(m):
+        if m >= m_tiles:
+            return 0
+        wt, ht = m % tw, (m // tw) % th
+        mk = 0
+        for i, (dh, dw) in enumerate(taps):
+            lo_h, lo_w = ht * bh + dh, wt * bw + dw
+            if lo_h + bh - 1 >= 0 and lo_h < h and lo_w + bw - 1 >= 0 and lo_w < w:
+                mk |= 1 << i
+        return mk
+
+    pairs = -(-m_tiles // 2) * n_tiles_n
+    clusters = min(74, pairs)
+    loads = [0] * clusters
+    for p in range(pairs):
+        mp = p // n_tiles_n
+        both = mask(2 * mp) | mask(2 * mp + 1)
+        loads[p % clusters] += bin(both or 1).count('1') * kblocks
+    lib = L.load()
+    for knob in (1, 0):
+        lib.b2_debug_set(17, knob)
+        try:
+            pl = tensor_busy.plan(n, h, w, cin, cout, k, dil)
+        finally:
+            lib.b2_debug_set(17, 1)
+        assert (pl['bw'], pl['bh'], pl['bn']) == (bw, bh, bn)
+        assert pl['tile_pairs'] == pairs and pl['cta_pairs'] == clusters
+        assert pl['stages_total'] == sum(loads) and pl['stages_busiest_pair'] == max(loads)
